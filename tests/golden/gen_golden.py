@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF.
+
+Run in the build container (needs /root/reference):
+    python tests/golden/gen_golden.py
+
+It imports the mechanically py3-patched copy of the reference that
+oracle/make_ref.py builds (git-ignored oracle/_ref/), evaluates
+``objective_function`` / ``predict_*`` / layer-level kernels on small seeded
+inputs and stores inputs, parameters, energy and every gradient.  The shapes
+follow the reference's own tests (tests/test_grads_aep.py:18-30,124-135,230-259,
+370-410; tests/test_grads_vfe.py:18-39,130-153,371-411) plus BASELINE.json
+config 1.  numpy/scipy versions are recorded in each file's ``meta``.
+"""
+import io
+import json
+import os
+import sys
+import contextlib
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import make_ref  # noqa: E402
+
+aep, vfe, lik, kern, utils = make_ref.import_ref()
+
+
+def perturb(params, rng, scale=0.05):
+    out = {}
+    for k, v in params.items():
+        v = np.array(v, dtype=np.float64)
+        out[k] = v + scale * rng.standard_normal(v.shape)
+    return out
+
+
+def save(name, meta, inputs, params, energy, grads, extra=None):
+    d = {'meta': json.dumps(dict(meta, numpy=np.__version__, scipy=scipy.__version__,
+                                 floor=dict(FLOORS)))}
+    for k, v in inputs.items():
+        d['in__' + k] = np.asarray(v)
+    for k, v in params.items():
+        d['p__' + k] = np.asarray(v)
+    for k, v in grads.items():
+        d['g__' + k] = np.asarray(v)
+    d['energy'] = np.asarray(energy, dtype=np.float64).reshape(-1)[:1]
+    for k, v in (extra or {}).items():
+        d['x__' + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **d)
+    print('%-28s energy=%.10g  keys=%s' % (name, float(d['energy'][0]), sorted(grads)))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            return fn(*a, **k)
+
+
+FLOORS = {}
+
+
+def run(model, params, mb, alpha, seed=None):
+    """Evaluate the reference; also estimate its own conditioning floor: how much
+    each output moves when every parameter is perturbed by ~1e-15 relative (three
+    draws).  Parity cannot be tighter than that, whatever the implementation."""
+    import copy
+    p = copy.deepcopy(params)
+    if seed is not None:
+        np.random.seed(seed)
+    e, g = model.objective_function(p, mb, alpha=alpha)
+    e = np.array(e, dtype=np.float64).copy()
+    g = {k: np.array(v, dtype=np.float64).copy() for k, v in g.items()}
+    rng = np.random.RandomState(999)
+    floor = {k: 0.0 for k in g}
+    floor['energy'] = 0.0
+    for _ in range(3):
+        q = {k: np.array(v, dtype=np.float64) * (1.0 + 1e-15 * rng.standard_normal(np.shape(v)))
+             for k, v in params.items()}
+        if seed is not None:
+            np.random.seed(seed)
+        e2, g2 = model.objective_function(q, mb, alpha=alpha)
+        floor['energy'] = max(floor['energy'], float(np.max(np.abs(e2 - e)) / np.max(np.abs(e))))
+        for k in g:
+            sc = max(np.max(np.abs(g[k])), 1e-300)
+            floor[k] = max(floor[k], float(np.max(np.abs(np.asarray(g2[k]) - g[k])) / sc))
+    FLOORS.clear()
+    FLOORS.update(floor)
+    return e, g
+
+
+def case_sgpr(name, cls, N, M, D, Do, alpha, nat, mb=None, seed=0, xy=None):
+    rng = np.random.RandomState(seed)
+    if xy is None:
+        x = rng.standard_normal((N, D))
+        y = rng.standard_normal((N, Do))
+    else:
+        x, y = xy
+    np.random.seed(seed)
+    model = cls(x, y, M, lik='Gaussian', nat_param=nat)
+    params = perturb(quiet(model.init_hypers, y), rng)
+    params['sn'] = np.array(np.log(0.3) + 0.05 * rng.standard_normal())
+    mbs = N if mb is None else mb
+    e, g = run(model, params, mbs, alpha, seed=123)
+    extra = {}
+    if mb is None:
+        xs = rng.standard_normal((7, D))
+        model.update_hypers(params)
+        model.updated = False
+        mf, vf = model.predict_f(xs)
+        my, vy = model.predict_y(xs)
+        extra = {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy}
+    save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPR', N=N, M=M, D=D, Do=Do,
+                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123),
+         {'x': x, 'y': y}, params, e, g, extra)
+
+
+def case_sdgpr(name, N, M, D, hidden, Do, alpha, mb=None, seed=1):
+    rng = np.random.RandomState(seed)
+    x = rng.standard_normal((N, D))
+    y = rng.standard_normal((N, Do))
+    np.random.seed(seed)
+    model = aep.SDGPR(x, y, M, hidden, lik='Gaussian')
+    params = perturb(quiet(model.init_hypers, y), rng)
+    params['sn'] = np.array(np.log(0.3))
+    mbs = N if mb is None else mb
+    e, g = run(model, params, mbs, alpha, seed=123)
+    xs = rng.standard_normal((6, D))
+    model.update_hypers(params)
+    model.updated = False
+    mf, vf = model.predict_f(xs)
+    my, vy = model.predict_y(xs)
+    save(name, dict(model='aep_models.SDGPR', N=N, M=M, D=D, hidden=hidden, Do=Do, alpha=alpha,
+                    mb_size=mbs, rng_seed=123),
+         {'x': x, 'y': y}, params, e, g, {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy})
+
+
+def lvm_params(model, y, rng):
+    """Hand-built parameters (skips the nested L-BFGS fit of base_models.py:867-871
+    but follows the same recipe: base_models.py:853-859, 563-588)."""
+    N, Q = y.shape[0], model.Din
+    post_m = rng.standard_normal((N, Q))
+    post_v = 0.1 * np.ones((N, Q))
+    p = quiet(model.sgp_layer.init_hypers, post_m)
+    p = perturb(p, rng)
+    p['sn'] = np.array(np.log(0.3))
+    if model.nat_param:
+        post_2 = 1.0 / post_v
+        p['x1'] = post_2 * post_m
+        p['x2'] = np.log(post_2 - 1) / 2 + 0.05 * rng.standard_normal((N, Q))
+    else:
+        p['x1'] = post_m
+        p['x2'] = np.log(post_v) / 2 + 0.05 * rng.standard_normal((N, Q))
+    return p
+
+
+def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2):
+    rng = np.random.RandomState(seed)
+    y = rng.standard_normal((N, Do))
+    np.random.seed(seed)
+    model = cls(y, Q, M, lik='Gaussian', nat_param=nat)
+    params = lvm_params(model, y, rng)
+    mbs = N if mb is None else mb
+    e, g = run(model, params, mbs, alpha, seed=123)
+    save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPLVM', N=N, M=M, Q=Q, Do=Do,
+                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123),
+         {'y': y}, params, e, g)
+
+
+def ssm_params(model, y, rng, gp_emi):
+    N, Q = y.shape[0], model.Din
+    post_m = y[:, :Q] + 0.1 * rng.standard_normal((N, Q)) if y.shape[1] >= Q else rng.standard_normal((N, Q))
+    post_v = 0.1 * np.ones_like(post_m)
+    p = {'sn': np.array([np.log(0.2)])}
+    if model.nat_param:
+        post_2 = 1.0 / post_v
+        p['x_factor_1'] = post_2 * post_m / 3
+        p['x_factor_2'] = np.log(post_2 / 3) / 2 + 0.05 * rng.standard_normal((N, Q))
+    else:
+        p['x_factor_1'] = post_m.copy()
+        p['x_factor_2'] = np.log(post_v) / 2 + 0.05 * rng.standard_normal((N, Q))
+    xin = post_m[:N - 1]
+    if model.Dcon_dyn > 0:
+        xin = np.hstack((xin, model.x_control[:N - 1]))
+    p.update(perturb(quiet(model.dyn_layer.init_hypers, xin, key_suffix='_dynamic'), rng))
+    if gp_emi:
+        xin = post_m
+        if model.Dcon_emi > 0:
+            xin = np.hstack((xin, model.x_control))
+        p.update(perturb(quiet(model.emi_layer.init_hypers, xin, key_suffix='_emission'), rng))
+        p['sn_emission'] = np.array(np.log(0.25))
+    else:
+        Dout, Din = model.Dout, Q + model.Dcon_emi
+        p['C_emission'] = np.eye(Dout, Din) + 0.1 * rng.standard_normal((Dout, Din))
+        p['R_emission'] = np.log(0.2) * np.ones(Dout) + 0.05 * rng.standard_normal(Dout)
+    return p
+
+
+def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True, mb=None, seed=3):
+    rng = np.random.RandomState(seed)
+    y = np.cumsum(0.3 * rng.standard_normal((N, Do)), axis=0)
+    xc = rng.standard_normal((N, control)) if control else None
+    np.random.seed(seed)
+    if cls is aep.SGPSSM:
+        model = cls(y, Q, M, lik='Gaussian', x_control=xc, gp_emi=gp_emi)
+    else:
+        model = cls(y, Q, M, lik='Gaussian', x_control=xc, gp_emi=gp_emi, nat_param=nat)
+    params = ssm_params(model, y, rng, gp_emi)
+    mbs = N if mb is None else mb
+    e, g = run(model, params, mbs, alpha, seed=123)
+    inputs = {'y': y}
+    if control:
+        inputs['x_control'] = xc
+    save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPSSM', N=N, M=M, Q=Q, Do=Do,
+                    alpha=alpha, gp_emi=gp_emi, control=control, nat_param=nat, mb_size=mbs,
+                    rng_seed=123),
+         inputs, params, e, g)
+
+
+def case_kernels(seed=4):
+    rng = np.random.RandomState(seed)
+    N, M, Q = 9, 6, 3
+    mx = rng.standard_normal((N, Q))
+    vx = rng.rand(N, Q) * 0.5 + 0.01
+    z = rng.standard_normal((M, Q))
+    ls = 0.3 * rng.standard_normal(Q)
+    sf = np.array([0.2])
+    kfu = kern.compute_kernel(2 * ls, 2 * sf, mx, z)
+    psi1, psi2 = kern.compute_psi_weave(2 * ls, 2 * sf, mx, vx, z)
+    psi1n = kern.psi1computations(np.exp(2 * sf), np.exp(ls), z, mx, vx)
+    psi2n = kern.psi2computations(np.exp(2 * sf), np.exp(ls), z, mx, vx)
+    dpsi1 = rng.standard_normal((N, M))
+    dpsi2 = rng.standard_normal((N, M, M))
+    der = kern.compute_psi_derivatives(dpsi1, psi1, dpsi2, psi2, np.exp(ls), np.exp(2 * sf), mx, vx, z)
+    dk = kern.compute_kfu_derivatives(dpsi1, kfu, np.exp(ls), np.exp(2 * sf), mx, z, grad_x=True)
+    Mm = rng.standard_normal((M, M))
+    Kzz = kern.compute_kernel(2 * ls, 2 * sf, z, z)
+    tr = kern.d_trace_MKzz_dhypers(2 * ls, 2 * sf, z, Mm, Kzz)
+    d = dict(mx=mx, vx=vx, z=z, ls=ls, sf=sf, kfu=kfu, psi1=psi1, psi2=psi2, psi1_numpy=psi1n,
+             psi2_numpy=psi2n, dpsi1=dpsi1, dpsi2=dpsi2, Mm=Mm, Kzz=Kzz,
+             psider_var=der[0], psider_l=der[1], psider_z=der[2], psider_mu=der[3], psider_S=der[4],
+             kfuder_var=dk[0], kfuder_l=dk[1], kfuder_z=dk[2], kfuder_x=dk[3],
+             tr_sf=tr[0], tr_ls=tr[1], tr_z=tr[2],
+             meta=json.dumps(dict(numpy=np.__version__, scipy=scipy.__version__)))
+    np.savez_compressed(os.path.join(HERE, 'kernels.npz'), **d)
+    print('kernels.npz written')
+
+
+def case_emis(seed=5):
+    """tests/test_grads_emis.py shapes: Gauss_Emis tilted + log-lik-exp."""
+    rng = np.random.RandomState(seed)
+    N, Do, Q = 8, 3, 2
+    y = rng.standard_normal((N, Do))
+    em = lik.Gauss_Emis(y, Do, Q)
+    p = {'C': rng.standard_normal((Do, Q)), 'R': 0.3 * rng.standard_normal(Do)}
+    em.update_hypers(p)
+    mx = rng.standard_normal((N, Q))
+    vx = rng.rand(N, Q) + 0.05
+    lz, gi, gh = em.compute_emission_tilted(mx, vx, 0.7, -1.3)
+    le, gi2, gh2 = em.compute_emission_log_lik_exp(mx, vx, -1.3)
+    np.savez_compressed(os.path.join(HERE, 'gauss_emis.npz'), y=y, C=p['C'], R=p['R'], mx=mx, vx=vx,
+                        alpha=0.7, scale=-1.3, t_logZ=lz, t_dmx=gi['mx'], t_dvx=gi['vx'],
+                        t_dC=gh['C'], t_dR=gh['R'], e_logZ=le, e_dmx=gi2['mx'], e_dvx=gi2['vx'],
+                        e_dC=gh2['C'], e_dR=gh2['R'],
+                        meta=json.dumps(dict(numpy=np.__version__, scipy=scipy.__version__)))
+    print('gauss_emis.npz written')
+
+
+if __name__ == '__main__':
+    # tests/test_grads_aep.py:124-135 shape (alpha 0.5) + its alpha=1e-4 + non-natural params
+    case_sgpr('aep_sgpr', aep.SGPR, 20, 10, 2, 3, 0.5, True)
+    case_sgpr('aep_sgpr_alpha_small', aep.SGPR, 20, 10, 2, 3, 1e-4, True, seed=10)
+    case_sgpr('aep_sgpr_alpha_one', aep.SGPR, 20, 10, 2, 3, 1.0, True, seed=11)
+    case_sgpr('aep_sgpr_nonnat', aep.SGPR, 20, 10, 2, 3, 0.5, False, seed=12)
+    case_sgpr('aep_sgpr_minibatch', aep.SGPR, 20, 10, 2, 3, 0.5, True, mb=7, seed=13)
+    case_sgpr('vfe_sgpr', vfe.SGPR, 20, 10, 2, 3, 0.5, True, seed=14)
+    case_sgpr('vfe_sgpr_nonnat', vfe.SGPR, 20, 10, 2, 3, 0.5, False, seed=15)
+    # BASELINE.json config 1: examples/gpr_aep_examples.py:12-18 data, M=50, alpha=0.5
+    rs = np.random.RandomState(42)
+    X = rs.rand(200, 1)
+    Y = np.sin(12 * X) + 0.5 * np.cos(25 * X) + rs.randn(200, 1) * 0.2
+    case_sgpr('aep_sgpr_cfg1', aep.SGPR, 200, 50, 1, 1, 0.5, True, seed=16, xy=(X, Y))
+    # tests/test_grads_aep.py:230-259
+    case_sdgpr('aep_sdgpr', 10, 5, 2, [3, 2], 2, 1.0)
+    case_sdgpr('aep_sdgpr_alpha_half', 12, 6, 3, [2, 2], 1, 0.5, seed=20)
+    case_sdgpr('aep_sdgpr_minibatch', 12, 6, 3, [2], 1, 0.5, mb=5, seed=21)
+    # tests/test_grads_aep.py:18-30; tests/test_grads_vfe.py:18-39
+    case_sgplvm('aep_sgplvm', aep.SGPLVM, 10, 5, 3, 2, 0.5)
+    case_sgplvm('aep_sgplvm_minibatch', aep.SGPLVM, 12, 5, 2, 3, 0.7, mb=5, seed=30)
+    case_sgplvm('vfe_sgplvm', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=31)
+    case_sgplvm('vfe_sgplvm_nonnat', vfe.SGPLVM, 10, 5, 3, 2, 1.0, nat=False, seed=32)
+    # tests/test_grads_aep.py:370-410; tests/test_grads_vfe.py:371-411
+    case_sgpssm('aep_sgpssm_lin', aep.SGPSSM, 20, 4, 2, 2, 0.5)
+    case_sgpssm('aep_sgpssm_lin_1d', aep.SGPSSM, 30, 4, 1, 1, 0.4, seed=40)
+    case_sgpssm('aep_sgpssm_lin_window', aep.SGPSSM, 20, 4, 2, 2, 0.5, mb=8, seed=41)
+    case_sgpssm('aep_sgpssm_gp', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=42)
+    case_sgpssm('aep_sgpssm_control', aep.SGPSSM, 12, 4, 2, 2, 0.5, control=1, seed=43)
+    case_sgpssm('vfe_sgpssm_lin', vfe.SGPSSM, 20, 4, 2, 2, 1.0, seed=44)
+    case_sgpssm('vfe_sgpssm_gp', vfe.SGPSSM, 10, 4, 2, 3, 1.0, gp_emi=True, seed=45)
+    case_sgpssm('vfe_sgpssm_nonnat', vfe.SGPSSM, 12, 4, 2, 2, 1.0, nat=False, seed=46)
+    case_kernels()
+    case_emis()
