@@ -1,0 +1,1172 @@
+// gpb_kernels.cuh -- device kernels of the geepee_b200 hot path (sm_100a).
+//
+// Every kernel is a template on the arithmetic type T (double = "fp64 mode",
+// float = "fp32-psi mode"); all cross-row accumulators and all interfaces are
+// fp64.  The source is also compiled for the host by tests/emu (GPB_CPU_EMU),
+// see gpb_rt.cuh.  Reference formulas are cited per kernel (paths relative to
+// /root/reference/geepee/).
+//
+// Notation: n rows, M pseudo-points (MP = M padded to 128/256/512 for the GEMM
+// kernels), D/Q input dims, Do output dims, P = M(M+1)/2 unordered pairs.
+#pragma once
+#include "gpb_rt.cuh"
+
+namespace gpb {
+
+constexpr int kThreads = 256;
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+template <typename T> struct V16;
+template <> struct V16<double> { typedef double2 type; static constexpr int N = 2; };
+template <> struct V16<float> { typedef float4 type; static constexpr int N = 4; };
+
+template <typename T>
+union VecU {
+    typename V16<T>::type v;
+    T e[V16<T>::N];
+};
+
+// -------------------------------------------------------------------------
+// deterministic two-stage reduction helper: out[i] (+)= sum_g part[g*len + i]
+// -------------------------------------------------------------------------
+GPB_KERNEL void reduce_partials_kernel(const double* __restrict__ part, int G, long gstride,
+                                       long len, double* __restrict__ out, int accumulate) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < len;
+         i += (long)gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int g = 0; g < G; g++) s += part[(long)g * gstride + i];
+        out[i] = accumulate ? out[i] + s : s;
+    }
+}
+
+// sum of one double per thread over the block -> returned to thread 0 (others get junk)
+GPB_DEVICE double block_sum(double v, double* scratch /* >= 8 doubles of smem */) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    sync_threads();
+    if (lane == 0) scratch[w] = v;
+    sync_threads();
+    double s = 0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += scratch[i];
+    return s;
+}
+
+// -------------------------------------------------------------------------
+// a1. ARD-SE kernel matrix, kernels.py:10-22 (+ JITTER on the diagonal for Kuu,
+//     base_models.py:461-463).  fp64, one thread per entry.
+// -------------------------------------------------------------------------
+GPB_KERNEL void kmat_kernel(const double* __restrict__ x, const double* __restrict__ z,
+                            const double* __restrict__ ls, const double* __restrict__ sf,
+                            int n, int M, int D, double jitter, double* __restrict__ out) {
+    const double sf2 = exp(2.0 * sf[0]);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)n * M;
+         i += (long)gridDim.x * blockDim.x) {
+        int r = (int)(i / M), m = (int)(i % M);
+        double r2 = 0;
+        for (int q = 0; q < D; q++) {
+            double d = x[(long)r * D + q] - z[(long)m * D + q];
+            r2 += d * d * exp(-2.0 * ls[q]);
+        }
+        double k = sf2 * exp(-0.5 * r2);
+        if (jitter != 0.0 && r == m) k += jitter;
+        out[i] = k;
+    }
+}
+
+// -------------------------------------------------------------------------
+// a2. psi1[n,M], psi2[n,M,M] materialised -- the drop-in twin of the reference's
+//     one native routine, kernels.py:181-240 (compute_psi_weave).  Same log-domain
+//     expression as the weave body (lines 214-227).  Only the layer-level API and
+//     the parity tests use it; the training path never writes psi2 to HBM.
+// -------------------------------------------------------------------------
+GPB_KERNEL void psi_stats_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
+                                 const double* __restrict__ z, const double* __restrict__ ls,
+                                 const double* __restrict__ sf, int n, int M, int Q,
+                                 double* __restrict__ psi1, double* __restrict__ psi2) {
+    const double sf2 = exp(2.0 * sf[0]);
+    const long total = (long)n * M * M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        int b = (int)(i % M);
+        int a = (int)((i / M) % M);
+        long r = i / ((long)M * M);
+        double lp2 = 0, lp1 = 0;
+        for (int q = 0; q < Q; q++) {
+            double lq = exp(2.0 * ls[q]);
+            double vq = vx[r * Q + q], mq = mx[r * Q + q];
+            double z1 = z[(long)a * Q + q], z2 = z[(long)b * Q + q];
+            double muzhat = mq - (z1 + z2) / 2.0;
+            double dz = z1 - z2;
+            lp2 += -dz * dz / (4.0 * lq) - muzhat * muzhat / (2.0 * vq + lq) +
+                   0.5 * log(lq / (lq + 2.0 * vq));
+            if (b == 0) {
+                double muz = mq - z1;
+                lp1 += -muz * muz / 2.0 / (vq + lq) + 0.5 * log(lq / (lq + vq));
+            }
+        }
+        psi2[i] = sf2 * sf2 * exp(lp2);
+        if (b == 0) psi1[r * M + a] = sf2 * exp(lp1);
+    }
+}
+
+// -------------------------------------------------------------------------
+// a7 / a7'. Gaussian likelihood: lik_layers.py:104-133 (mode 0: AEP log Z tilted)
+//     and 183-199,217-226 (mode 1: VFE expected log-lik).  Elementwise over
+//     [n,Do]; writes dm, dv ALREADY multiplied by `scale` (what the layers'
+//     backward consumes) and per-block partials {sum logZ-terms, sum for dsn}.
+//     mode 0: part1 = sum of UNscaled dv (lik_layers.py:171-181)
+//     mode 1: part1 = sum(-1 + (y-m)^2/sn2 + v/sn2)
+// -------------------------------------------------------------------------
+GPB_KERNEL void gauss_lik_kernel(const double* __restrict__ m, const double* __restrict__ v,
+                                 const double* __restrict__ y, const double* __restrict__ sn,
+                                 double alpha, double scale, long total, int mode,
+                                 double* __restrict__ dm, double* __restrict__ dv,
+                                 double* __restrict__ part /* [gridDim.x][2] */) {
+    GPB_SHARED double scratch[16];
+    const double sn2 = exp(2.0 * sn[0]);
+    double s0 = 0, s1 = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        double mi = m[i], yi = y[i];
+        if (mode == 0) {
+            double vi = v[i] + sn2 / alpha;
+            double e = yi - mi;
+            s0 += -0.5 * (log(kTwoPi * vi) + e * e / vi) +
+                  (0.5 * log(kTwoPi * sn2 / alpha) - 0.5 * alpha * log(kTwoPi * sn2));
+            double dmi = e / vi;
+            double dvi = -0.5 / vi + 0.5 * e * e / (vi * vi);
+            s1 += dvi;
+            dm[i] = scale * dmi;
+            dv[i] = scale * dvi;
+        } else {
+            double vi = v[i];
+            double t = yi * yi - 2 * yi * mi + mi * mi + vi;
+            s0 += -0.5 * log(kTwoPi * sn2) - 0.5 / sn2 * t;
+            s1 += -1.0 + t / sn2;
+            dm[i] = scale * (yi - mi) / sn2;
+            dv[i] = scale * (-0.5 / sn2);
+        }
+    }
+    double r0 = block_sum(s0, scratch);
+    double r1 = block_sum(s1, scratch + 8);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 2 + 0] = r0;
+        part[blockIdx.x * 2 + 1] = r1;
+    }
+}
+
+// =========================================================================
+// Deterministic-input layer (a5, a8)
+// =========================================================================
+// Tile geometry of the fused Kfu-generation + Kfu.B GEMM kernel.  256 threads =
+// 8 warps arranged CW column-warps x RW row-warps; each warp owns 16 rows x 128
+// columns of the [TN x MP] output tile T = Kfu_tile . B_d, each thread 16 rows x 4
+// columns (64 accumulators).  The A operand (Kfu tile, generated on the fly from
+// x and zu) stays resident in shared memory; B_d is streamed through a
+// double-buffered cp.async ring in chunks of KB rows.
+template <typename T, int MP>
+struct DetCfg {
+    static constexpr int CW = MP / 128;
+    static constexpr int RW = 8 / CW;
+    static constexpr int TN = 16 * RW;
+    static constexpr int KB = 32768 / (MP * (int)sizeof(T));
+    static constexpr int VEC = V16<T>::N;
+    static constexpr int NJ = 4 / VEC;  // 16-byte column groups per thread
+    static constexpr int DPMAX = 32;
+    static constexpr size_t kt_bytes = (size_t)TN * MP * sizeof(T);
+    static constexpr size_t bs_bytes = 2 * (size_t)KB * MP * sizeof(T);
+    static constexpr size_t red_bytes = (size_t)CW * TN * 2 * sizeof(double);
+    static constexpr size_t smem_bytes = kt_bytes + bs_bytes + red_bytes + DPMAX * sizeof(T);
+};
+
+template <typename T>
+struct DetFwdArgs {
+    const double* x;   // [n, D]
+    const double* z;   // [M, D]
+    const double* ls;  // [D]   log lengthscales
+    const double* sf;  // [1]   log signal std
+    const T* Ap;       // [Do, MP]      zero padded (Ahat or A)
+    const T* Bp;       // [Do, MP, MP]  zero padded (Bhat_det or B_det)
+    int n, M, D, Do;
+    double* mout;      // [n, Do]
+    double* vout;      // [n, Do]
+    T* Ksave;          // [n, MP] or null
+    T* Tsave;          // [n, Do, MP] or null
+};
+
+// Kfu tile generation, kernels.py:10-22: thread per column, rows looped.
+template <typename T, int DP>
+GPB_DEVICE void gen_k_tile(T* Kt, int MP, const T* xs, const double* __restrict__ z,
+                           const T* ils2, T sf2, int M, int D, int TN, int rows_valid,
+                           T* Ksave_tile) {
+    for (int m = threadIdx.x; m < MP; m += blockDim.x) {
+        T zr[DP];
+        GPB_UNROLL
+        for (int q = 0; q < DP; q++) zr[q] = (m < M && q < D) ? (T)z[(long)m * D + q] : (T)0;
+        for (int r = 0; r < TN; r++) {
+            T r2 = 0;
+            GPB_UNROLL
+            for (int q = 0; q < DP; q++) {
+                T d = xs[r * DP + q] - zr[q];
+                r2 += d * d * ils2[q];
+            }
+            T k = (m < M && r < rows_valid) ? sf2 * fast_exp((T)(-0.5) * r2) : (T)0;
+            Kt[r * MP + m] = k;
+            if (Ksave_tile != nullptr && r < rows_valid) Ksave_tile[(long)r * MP + m] = k;
+        }
+    }
+}
+
+// a5: aep_models.py:142-158 / base_models.py:265-284.
+//   mout[n,d] = sum_m kfu[n,m] A[d,m];  vout[n,d] = sf2 + sum_ab B[d,a,b] kfu[n,a] kfu[n,b]
+// also emits T[n,d,:] = B_d kfu[n,:] and kfu itself for the backward kernels.
+template <typename T, int MP>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_kernel(DetFwdArgs<T> a) {
+    typedef DetCfg<T, MP> C;
+    typedef typename V16<T>::type VT;
+    constexpr int TN = C::TN, KB = C::KB, VEC = C::VEC, NJ = C::NJ, CW = C::CW;
+    GPB_DYN_SMEM(smem);
+    T* Kt = (T*)smem;
+    T* Bs = (T*)(smem + C::kt_bytes);
+    T* xs = Bs;  // x tile aliases the B ring (only live during Kfu generation)
+    double* red = (double*)(smem + C::kt_bytes + C::bs_bytes);
+    T* ils2 = (T*)(smem + C::kt_bytes + C::bs_bytes + C::red_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cw = warp % CW, rw = warp / CW;
+    const int D = a.D, M = a.M, Do = a.Do, n = a.n;
+    const int DP = D <= 4 ? 4 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32));
+    const T sf2 = (T)exp(2.0 * a.sf[0]);
+    if (tid < C::DPMAX) ils2[tid] = tid < D ? (T)exp(-2.0 * a.ls[tid]) : (T)0;
+
+    const int ntiles = (n + TN - 1) / TN;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * TN;
+        const int rows_valid = (n - row0) < TN ? (n - row0) : TN;
+        sync_threads();  // previous tile fully consumed (Kt, Bs/xs, red)
+        for (int i = tid; i < TN * DP; i += kThreads) {
+            int r = i / DP, q = i - r * DP;
+            xs[i] = (r < rows_valid && q < D) ? (T)a.x[(long)(row0 + r) * D + q] : (T)0;
+        }
+        sync_threads();
+        T* ks = a.Ksave ? a.Ksave + (long)row0 * MP : nullptr;
+        if (DP == 4) gen_k_tile<T, 4>(Kt, MP, xs, a.z, ils2, sf2, M, D, TN, rows_valid, ks);
+        else if (DP == 8) gen_k_tile<T, 8>(Kt, MP, xs, a.z, ils2, sf2, M, D, TN, rows_valid, ks);
+        else if (DP == 16) gen_k_tile<T, 16>(Kt, MP, xs, a.z, ils2, sf2, M, D, TN, rows_valid, ks);
+        else gen_k_tile<T, 32>(Kt, MP, xs, a.z, ils2, sf2, M, D, TN, rows_valid, ks);
+        sync_threads();
+
+        for (int d = 0; d < Do; d++) {
+            const T* Bd = a.Bp + (long)d * MP * MP;
+            T acc[16][4];
+            GPB_UNROLL
+            for (int r = 0; r < 16; r++)
+                GPB_UNROLL
+                for (int c = 0; c < 4; c++) acc[r][c] = 0;
+
+            constexpr int nchunks = MP / KB;
+            constexpr int chunk_vecs = KB * MP / VEC;  // 16B vectors per chunk
+            // prologue: chunk 0 -> buffer 0
+            for (int i = tid; i < chunk_vecs; i += kThreads)
+                cp_async16(Bs + (long)i * VEC, Bd + (long)i * VEC);
+            cp_async_commit();
+            for (int c = 0; c < nchunks; c++) {
+                if (c + 1 < nchunks) {
+                    T* dst = Bs + (long)((c + 1) & 1) * KB * MP;
+                    const T* src = Bd + (long)(c + 1) * KB * MP;
+                    for (int i = tid; i < chunk_vecs; i += kThreads)
+                        cp_async16(dst + (long)i * VEC, src + (long)i * VEC);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                sync_threads();
+                const T* Bc = Bs + (long)(c & 1) * KB * MP;
+                const T* Ka = Kt + (long)(rw * 16) * MP + c * KB;
+                GPB_UNROLL_N(2)
+                for (int k0 = 0; k0 < KB; k0 += VEC) {
+                    // B operand: VEC k-rows x 4 columns of this thread
+                    T b[VEC][4];
+                    GPB_UNROLL
+                    for (int kk = 0; kk < VEC; kk++)
+                        GPB_UNROLL
+                        for (int j = 0; j < NJ; j++) {
+                            VecU<T> u;
+                            u.v = *(const VT*)(Bc + (long)(k0 + kk) * MP + cw * 128 +
+                                               j * (32 * VEC) + lane * VEC);
+                            GPB_UNROLL
+                            for (int e = 0; e < VEC; e++) b[kk][j * VEC + e] = u.e[e];
+                        }
+                    GPB_UNROLL
+                    for (int r = 0; r < 16; r++) {
+                        VecU<T> av;  // VEC consecutive k of row r (warp-uniform address)
+                        av.v = *(const VT*)(Ka + (long)r * MP + k0);
+                        GPB_UNROLL
+                        for (int kk = 0; kk < VEC; kk++)
+                            GPB_UNROLL
+                            for (int cc = 0; cc < 4; cc++) acc[r][cc] += av.e[kk] * b[kk][cc];
+                    }
+                }
+                sync_threads();
+            }
+
+            // epilogue: row reductions  sum_m K[r,m] T[r,m]  and  sum_m K[r,m] A[d,m]
+            GPB_UNROLL
+            for (int r = 0; r < 16; r++) {
+                const int row = rw * 16 + r;
+                double pv = 0, pm = 0;
+                GPB_UNROLL
+                for (int j = 0; j < NJ; j++) {
+                    const int col = cw * 128 + j * (32 * VEC) + lane * VEC;
+                    VecU<T> kv, av;
+                    kv.v = *(const VT*)(Kt + (long)row * MP + col);
+                    av.v = *(const VT*)(a.Ap + (long)d * MP + col);
+                    GPB_UNROLL
+                    for (int e = 0; e < VEC; e++) {
+                        pv += (double)acc[r][j * VEC + e] * (double)kv.e[e];
+                        pm += (double)kv.e[e] * (double)av.e[e];
+                    }
+                    if (a.Tsave != nullptr && row < rows_valid) {
+                        VecU<T> tv;
+                        GPB_UNROLL
+                        for (int e = 0; e < VEC; e++) tv.e[e] = acc[r][j * VEC + e];
+                        *(VT*)(a.Tsave + ((long)(row0 + row) * Do + d) * MP + col) = tv.v;
+                    }
+                }
+                pv = warp_sum(pv);
+                pm = warp_sum(pm);
+                if (lane == 0) {
+                    red[(cw * TN + row) * 2 + 0] = pv;
+                    red[(cw * TN + row) * 2 + 1] = pm;
+                }
+            }
+            sync_threads();
+            if (tid < rows_valid) {
+                double pv = 0, pm = 0;
+                for (int w = 0; w < CW; w++) {
+                    pv += red[(w * TN + tid) * 2 + 0];
+                    pm += red[(w * TN + tid) * 2 + 1];
+                }
+                a.vout[(long)(row0 + tid) * Do + d] = (double)sf2 + pv;
+                a.mout[(long)(row0 + tid) * Do + d] = pm;
+            }
+        }
+    }
+}
+
+// a8 (row-streaming part), aep_models.py:452-460,490 + kernels.py:381-399 (kfucompDer):
+//   L[n,m] = (sum_d dm[n,d] A[d,m] + 2 dv[n,d] T[n,d,m]) kfu[n,m]
+//   dsf2 += sum L / sf2 ; dZ[m,q] -= L (z_mq - x_nq)/l_q^2 ; dl_q += L (z_mq-x_nq)^2/l_q^3
+//   dA[d,m] += dm[n,d] kfu[n,m]
+// Thread per pseudo-point column, rows streamed from the saved Kfu / T buffers.
+// grid = (row chunks, MP/CWB); each (block, row-group) writes one partial record:
+//   [ cs(MP) | dz(MP*D) | dl(MP*D) | dA(Do*MP) ]   (dl kept per column, summed later)
+// Input dims beyond DP are handled by extra passes over the rows (q0 loop), output
+// dims beyond 8 by extra dA passes (d0 loop).
+template <typename T, int DP>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
+    const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls,
+    const T* __restrict__ Ap, const double* __restrict__ dm, const double* __restrict__ dv,
+    const T* __restrict__ Ksave, const T* __restrict__ Tsave, int n, int M, int MP, int D, int Do,
+    int rows_per_block, double* __restrict__ part, long rec_len) {
+    constexpr int TR = 32;
+    GPB_SHARED T xs[TR * DP];
+    GPB_SHARED double dms[TR * 8];
+    const int tid = threadIdx.x;
+    const int CWB = MP < 256 ? MP : 256;
+    const int RY = kThreads / CWB;
+    const int cx = tid % CWB, ry = tid / CWB;
+    const int c = blockIdx.y * CWB + cx;
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = (r_begin + rows_per_block) < n ? (r_begin + rows_per_block) : n;
+    double* rec = part + ((long)(blockIdx.x * RY + ry)) * rec_len;
+
+    // ---- pass family 1: L-dependent sums, DP input dims at a time -------------------
+    for (int q0 = 0; q0 < D; q0 += DP) {
+        T zr[DP];
+        double dz[DP], dl[DP];
+        double cs = 0;
+        GPB_UNROLL
+        for (int q = 0; q < DP; q++) {
+            zr[q] = (c < M && q0 + q < D) ? (T)z[(long)c * D + q0 + q] : (T)0;
+            dz[q] = 0;
+            dl[q] = 0;
+        }
+        for (int t0 = r_begin; t0 < r_end; t0 += TR) {
+            const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+            sync_threads();
+            for (int i = tid; i < TR * DP; i += kThreads) {
+                int r = i / DP, q = i - r * DP;
+                xs[i] = (r < tv && q0 + q < D) ? (T)x[(long)(t0 + r) * D + q0 + q] : (T)0;
+            }
+            sync_threads();
+            for (int r = ry; r < tv; r += RY) {
+                const long row = t0 + r;
+                const double k = (double)Ksave[row * MP + c];
+                double g = 0;
+                for (int d = 0; d < Do; d++)
+                    g += dm[row * Do + d] * (double)Ap[(long)d * MP + c] +
+                         2.0 * dv[row * Do + d] * (double)Tsave[(row * Do + d) * MP + c];
+                const double L = g * k;
+                cs += L;
+                GPB_UNROLL
+                for (int q = 0; q < DP; q++) {
+                    double diff = (double)zr[q] - (double)xs[r * DP + q];
+                    double t = L * diff;
+                    dz[q] += t;
+                    dl[q] += t * diff;
+                }
+            }
+        }
+        if (q0 == 0) rec[c] = cs;
+        GPB_UNROLL
+        for (int q = 0; q < DP; q++)
+            if (q0 + q < D) {
+                double il2 = exp(-2.0 * ls[q0 + q]);
+                rec[(long)MP + (long)c * D + q0 + q] = -dz[q] * il2;
+                rec[(long)MP + (long)MP * D + (long)c * D + q0 + q] = dl[q] * il2 * exp(-ls[q0 + q]);
+            }
+    }
+    // ---- pass family 2: dA[d, c] = sum_n dm[n,d] kfu[n,c], 8 output dims at a time ---
+    for (int d0 = 0; d0 < Do; d0 += 8) {
+        const int dn = (Do - d0) < 8 ? (Do - d0) : 8;
+        double dA[8];
+        GPB_UNROLL
+        for (int i = 0; i < 8; i++) dA[i] = 0;
+        for (int t0 = r_begin; t0 < r_end; t0 += TR) {
+            const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+            sync_threads();
+            for (int i = tid; i < TR * 8; i += kThreads) {
+                int r = i / 8, d = i - r * 8;
+                dms[i] = (r < tv && d < dn) ? dm[(long)(t0 + r) * Do + d0 + d] : 0.0;
+            }
+            sync_threads();
+            for (int r = ry; r < tv; r += RY) {
+                const double k = (double)Ksave[(long)(t0 + r) * MP + c];
+                GPB_UNROLL
+                for (int i = 0; i < 8; i++) dA[i] += dms[r * 8 + i] * k;
+            }
+        }
+        for (int i = 0; i < dn; i++) rec[(long)MP + 2L * MP * D + (long)(d0 + i) * MP + c] = dA[i];
+    }
+}
+
+// a8 (rank-update part), aep_models.py:493: dB[d] = sum_n dv[n,d] kfu[n,:] kfu[n,:]^T.
+// Upper block-triangle of 128x128 output blocks; split over rows; partial records
+//   part[((split*Do + d)*NBU + ub)*128*128 + i*128 + j]
+template <typename T>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_kernel(const T* __restrict__ Ksave,
+                                                       const double* __restrict__ dv, int n, int MP,
+                                                       int Do, int rows_per_split,
+                                                       double* __restrict__ part) {
+    typedef typename V16<T>::type VT;
+    constexpr int VEC = V16<T>::N;
+    constexpr int RK = 64 / (int)sizeof(T);          // rows per staged chunk (32 KB of smem)
+    constexpr int NV = 8 / VEC;                      // 16B vectors per thread per operand row
+    constexpr int LOADS = 2 * RK * 128 / VEC / kThreads;  // staged vectors per thread per chunk
+    GPB_SHARED GPB_ALIGN16 T As[2][RK * 128];
+    GPB_SHARED GPB_ALIGN16 T Bsm[2][RK * 128];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int nb = MP / 128;
+    // decode upper-triangular block id -> (bi <= bj)
+    int ub = blockIdx.x, bi = 0;
+    while (ub >= nb - bi) { ub -= nb - bi; bi++; }
+    const int bj = bi + ub;
+    const int d = blockIdx.z;
+    const int r_begin = blockIdx.y * rows_per_split;
+    const int r_end = (r_begin + rows_per_split) < n ? (r_begin + rows_per_split) : n;
+
+    T acc[8][8];
+    GPB_UNROLL
+    for (int i = 0; i < 8; i++)
+        GPB_UNROLL
+        for (int j = 0; j < 8; j++) acc[i][j] = 0;
+
+    VecU<T> stage[LOADS];
+    auto fetch = [&](int t0) {
+        GPB_UNROLL
+        for (int i = 0; i < LOADS; i++) {
+            int v = tid + kThreads * i;
+            int which = v / (RK * 128 / VEC);
+            int rem = v - which * (RK * 128 / VEC);
+            int r = rem / (128 / VEC), cv = rem - r * (128 / VEC);
+            long row = (long)t0 + r;
+            if (row < r_end) {
+                stage[i].v = *(const VT*)(Ksave + row * MP + (which ? bj : bi) * 128 + cv * VEC);
+                if (which == 0) {
+                    T w = (T)dv[row * Do + d];
+                    GPB_UNROLL
+                    for (int e = 0; e < VEC; e++) stage[i].e[e] *= w;
+                }
+            } else {
+                GPB_UNROLL
+                for (int e = 0; e < VEC; e++) stage[i].e[e] = 0;
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+        GPB_UNROLL
+        for (int i = 0; i < LOADS; i++) {
+            int v = tid + kThreads * i;
+            int which = v / (RK * 128 / VEC);
+            int rem = v - which * (RK * 128 / VEC);
+            T* dst = which ? Bsm[buf] : As[buf];
+            *(VT*)(dst + (long)rem * VEC) = stage[i].v;
+        }
+    };
+
+    if (r_begin < r_end) {
+        fetch(r_begin);
+        stash(0);
+    }
+    sync_threads();
+    int buf = 0;
+    for (int t0 = r_begin; t0 < r_end; t0 += RK) {
+        const bool more = (t0 + RK) < r_end;
+        if (more) fetch(t0 + RK);
+        GPB_UNROLL
+        for (int r = 0; r < RK; r++) {
+            T av[8], bv[8];
+            GPB_UNROLL
+            for (int j = 0; j < NV; j++) {
+                VecU<T> ua, ub2;
+                ua.v = *(const VT*)(As[buf] + r * 128 + j * (16 * VEC) + ty * VEC);
+                ub2.v = *(const VT*)(Bsm[buf] + r * 128 + j * (16 * VEC) + tx * VEC);
+                GPB_UNROLL
+                for (int e = 0; e < VEC; e++) {
+                    av[j * VEC + e] = ua.e[e];
+                    bv[j * VEC + e] = ub2.e[e];
+                }
+            }
+            GPB_UNROLL
+            for (int i = 0; i < 8; i++)
+                GPB_UNROLL
+                for (int j = 0; j < 8; j++) acc[i][j] += av[i] * bv[j];
+        }
+        if (more) stash(buf ^ 1);
+        sync_threads();
+        buf ^= 1;
+    }
+    const int nbu = nb * (nb + 1) / 2;
+    double* out = part + (((long)blockIdx.y * Do + d) * nbu + blockIdx.x) * (128 * 128);
+    GPB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        const int oi = (i / VEC) * (16 * VEC) + ty * VEC + (i % VEC);
+        GPB_UNROLL
+        for (int j = 0; j < 8; j++) {
+            const int oj = (j / VEC) * (16 * VEC) + tx * VEC + (j % VEC);
+            out[oi * 128 + oj] = (double)acc[i][j];
+        }
+    }
+}
+
+// sum the row-splits of det_syrk and expand the block upper-triangle to dB[Do,M,M]
+GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nsplit, int MP, int M,
+                                       int Do, double* __restrict__ dB) {
+    const int nb = MP / 128, nbu = nb * (nb + 1) / 2;
+    const long total = (long)Do * M * M;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long)gridDim.x * blockDim.x) {
+        int j = (int)(idx % M), i = (int)((idx / M) % M), d = (int)(idx / ((long)M * M));
+        int bi = i / 128, bj = j / 128, ii = i % 128, jj = j % 128;
+        if (bi > bj) { int t = bi; bi = bj; bj = t; t = ii; ii = jj; jj = t; }
+        int ub = 0;
+        for (int b = 0; b < bi; b++) ub += nb - b;
+        ub += bj - bi;
+        double s = 0;
+        for (int sp = 0; sp < nsplit; sp++)
+            s += part[(((long)sp * Do + d) * nbu + ub) * (128 * 128) + ii * 128 + jj];
+        dB[idx] = s;
+    }
+}
+
+// =========================================================================
+// Moment-matched layer (a2 fused with a6 / a9)
+// =========================================================================
+// Pair table (n-independent): for every unordered pair p=(a>=b)
+//   zh[q][p]  = (z_a + z_b)/2
+//   ep[p]     = sf2^2 * exp(-sum_q (z_a-z_b)^2 / (4 l_q^2))        (kernels.py:222-226)
+//   bs[d][p]  = B[d,a,b] + B[d,b,a]  (a != b)   |   B[d,a,a]
+template <typename T>
+GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double* __restrict__ ls,
+                                     const double* __restrict__ sf, const double* __restrict__ B,
+                                     int M, int Q, int Qt, int Do, long P, long PP,
+                                     T* __restrict__ zh, T* __restrict__ ep, T* __restrict__ bs) {
+    const double sf2 = exp(2.0 * sf[0]);
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < PP;
+         p += (long)gridDim.x * blockDim.x) {
+        for (int q = Q; q < Qt; q++) zh[(long)q * PP + p] = 0;  // template-padded input dims
+        if (p >= P) {  // padding: contributes nothing
+            for (int q = 0; q < Q; q++) zh[(long)q * PP + p] = 0;
+            ep[p] = 0;
+            for (int d = 0; d < Do; d++) bs[(long)d * PP + p] = 0;
+            continue;
+        }
+        long a = (long)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= p) a++;
+        while (a * (a + 1) / 2 > p) a--;
+        long b = p - a * (a + 1) / 2;
+        double e = 0;
+        for (int q = 0; q < Q; q++) {
+            double za = z[a * Q + q], zb = z[b * Q + q];
+            zh[(long)q * PP + p] = (T)(0.5 * (za + zb));
+            double dz = za - zb;
+            e += dz * dz / (4.0 * exp(2.0 * ls[q]));
+        }
+        ep[p] = (T)(sf2 * sf2 * exp(-e));
+        for (int d = 0; d < Do; d++) {
+            const double* Bd = B + (long)d * M * M;
+            bs[(long)d * PP + p] = (T)(a == b ? Bd[a * M + a] : Bd[a * M + b] + Bd[b * M + a]);
+        }
+    }
+}
+
+template <int Q, int DOC>
+struct MMCfg {
+    // pairs per thread / rows per register block, sized to keep the per-thread state in registers
+    static constexpr int RP = (2 * Q + 2 * DOC + 2) <= 12 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
+    static constexpr int RB = Q <= 2 ? 8 : (Q <= 4 ? 4 : (Q <= 8 ? 2 : 1));
+    static constexpr int PC = kThreads * RP;  // pairs per block
+};
+
+template <typename T>
+struct MMArgs {
+    const double* mx;  // [n, Q]
+    const double* vx;  // [n, Q]
+    const double* ls;  // [Q]
+    const T* zh;       // [Q, PP]
+    const T* ep;       // [PP]
+    const T* bs;       // [Do, PP]
+    const double* dv;  // [n, Do]   (backward) scaled dlogZ/dv
+    int n, Qa, Do, d0; // Qa: actual input dims (<= template Q); d0: first output dim of this d-chunk
+    long PP;
+    int rows_per_split;
+    double* rowacc;    // fwd: [n, Do] += sum_p bs[d,p] psi2[n,p] ; bwd: [n, 1+2Q] += {s, U_q, V_q}
+    double* pairpart;  // bwd: [nsplit][DOC+1+Q][PP]: {dBp_d, S0, S1_q}
+    int full_coef;     // bwd: 1 -> coefficient sum over ALL Do from bs (generic path when Do > DOC)
+    int lam_pass;      // bwd: 1 -> this pass also produces the Lambda-dependent sums
+};
+
+// a2+a6 (forward) / a2+a9 (backward) over unordered pairs.  Each thread owns RP pairs for
+// the whole kernel (their constants and accumulators live in registers); rows are staged
+// RB at a time in shared memory and broadcast.  psi2[n,p] = cn[n] * ep[p] *
+// exp(-sum_q (mu_nq - zh_pq)^2 c2_nq) is formed in registers and consumed immediately:
+// the N x M x M tensor never exists in memory.
+//   forward : rowacc[n,d]  += sum_p bs[d,p] psi2[n,p]                   (aep_models.py:196-198)
+//   backward: Lam[n,p] = (sum_d dv[n,d] bs[d,p]) psi2[n,p]              (aep_models.py:243, kernels.py:415-419)
+//             rowacc[n,:]  += {sum_p Lam, sum_p Lam zh_q, sum_p Lam zh_q^2}
+//             pair sums     : dBp[d,p] = sum_n dv[n,d] psi2[n,p]         (aep_models.py:240)
+//                             S0[p] = sum_n Lam ; S1[p,q] = sum_n Lam c2_nq (mu_nq - zh_pq)
+template <typename T, int Q, int DOC, bool BWD>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
+    typedef MMCfg<Q, DOC> C;
+    constexpr int RP = C::RP, RB = C::RB;
+    constexpr int NS = BWD ? (1 + 2 * Q) : DOC;
+    GPB_SHARED T s_mu[RB * Q], s_c2[RB * Q], s_cn[RB];
+    GPB_SHARED double s_dv[RB * DOC];
+    GPB_SHARED double s_dvall[BWD ? RB * 64 : 1];  // generic path: all Do (<= 64) per row
+    GPB_SHARED double s_red[8 * RB * NS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long pbase = (long)blockIdx.x * C::PC;
+    const long PP = a.PP;
+    const int Do = a.Do;
+
+    T zh[RP][Q], ep[RP], bs[RP][DOC];
+    T accB[RP][DOC], accS0[RP], accS1[RP][Q];
+    GPB_UNROLL
+    for (int j = 0; j < RP; j++) {
+        const long p = pbase + j * kThreads + tid;
+        GPB_UNROLL
+        for (int q = 0; q < Q; q++) zh[j][q] = a.zh[(long)q * PP + p];
+        ep[j] = a.ep[p];
+        GPB_UNROLL
+        for (int d = 0; d < DOC; d++) {
+            bs[j][d] = (a.d0 + d < Do) ? a.bs[(long)(a.d0 + d) * PP + p] : (T)0;
+            accB[j][d] = 0;
+        }
+        accS0[j] = 0;
+        GPB_UNROLL
+        for (int q = 0; q < Q; q++) accS1[j][q] = 0;
+    }
+    const int r_begin = blockIdx.y * a.rows_per_split;
+    const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
+    for (int t0 = r_begin; t0 < r_end; t0 += RB) {
+        const int tv = (r_end - t0) < RB ? (r_end - t0) : RB;
+        sync_threads();
+        // stage RB rows: c2 = 1/(2S + l^2), cn = prod_q sqrt(l^2 c2)   (kernels.py:188-190)
+        if (tid < RB) {
+            double cn = 1.0;
+            for (int q = 0; q < Q; q++) {
+                double mu = 0, c2 = 0;
+                if (tid < tv && q < a.Qa) {
+                    mu = a.mx[(long)(t0 + tid) * a.Qa + q];
+                    double lq = exp(2.0 * a.ls[q]);
+                    c2 = 1.0 / (2.0 * a.vx[(long)(t0 + tid) * a.Qa + q] + lq);
+                    cn *= sqrt(lq * c2);
+                }
+                s_mu[tid * Q + q] = (T)mu;
+                s_c2[tid * Q + q] = (T)c2;
+            }
+            s_cn[tid] = tid < tv ? (T)cn : (T)0;
+            if (BWD) {
+                for (int d = 0; d < DOC; d++)
+                    s_dv[tid * DOC + d] =
+                        (tid < tv && a.d0 + d < Do) ? a.dv[(long)(t0 + tid) * Do + a.d0 + d] : 0.0;
+                if (a.full_coef)
+                    for (int d = 0; d < Do; d++)
+                        s_dvall[tid * 64 + d] = tid < tv ? a.dv[(long)(t0 + tid) * Do + d] : 0.0;
+            }
+        }
+        sync_threads();
+        double rs[RB][NS];
+        GPB_UNROLL
+        for (int r = 0; r < RB; r++)
+            GPB_UNROLL
+            for (int s = 0; s < NS; s++) rs[r][s] = 0;
+        GPB_UNROLL
+        for (int r = 0; r < RB; r++) {
+            T mu[Q], c2[Q];
+            GPB_UNROLL
+            for (int q = 0; q < Q; q++) {
+                mu[q] = s_mu[r * Q + q];
+                c2[q] = s_c2[r * Q + q];
+            }
+            const T cn = s_cn[r];
+            GPB_UNROLL
+            for (int j = 0; j < RP; j++) {
+                T e = 0, t[Q];
+                GPB_UNROLL
+                for (int q = 0; q < Q; q++) {
+                    T diff = mu[q] - zh[j][q];
+                    t[q] = diff * c2[q];
+                    e += t[q] * diff;
+                }
+                const T psi2 = cn * ep[j] * fast_exp(-e);
+                if (!BWD) {
+                    GPB_UNROLL
+                    for (int d = 0; d < DOC; d++) rs[r][d] += (double)(bs[j][d] * psi2);
+                } else {
+                    T coef = 0;
+                    GPB_UNROLL
+                    for (int d = 0; d < DOC; d++) {
+                        T dvd = (T)s_dv[r * DOC + d];
+                        accB[j][d] += dvd * psi2;
+                        coef += dvd * bs[j][d];
+                    }
+                    if (a.lam_pass) {
+                        if (a.full_coef) {
+                            const long p = pbase + j * kThreads + tid;
+                            coef = 0;
+                            for (int d = 0; d < Do; d++)
+                                coef += (T)s_dvall[r * 64 + d] * a.bs[(long)d * PP + p];
+                        }
+                        const T lam = coef * psi2;
+                        accS0[j] += lam;
+                        rs[r][0] += (double)lam;
+                        GPB_UNROLL
+                        for (int q = 0; q < Q; q++) {
+                            accS1[j][q] += lam * t[q];
+                            T lz = lam * zh[j][q];
+                            rs[r][1 + q] += (double)lz;
+                            rs[r][1 + Q + q] += (double)(lz * zh[j][q]);
+                        }
+                    }
+                }
+            }
+        }
+        // block reduction of the RB x NS row sums, then one atomic per value
+        GPB_UNROLL
+        for (int r = 0; r < RB; r++)
+            GPB_UNROLL
+            for (int s = 0; s < NS; s++) {
+                double v = warp_sum(rs[r][s]);
+                if (lane == 0) s_red[(warp * RB + r) * NS + s] = v;
+            }
+        sync_threads();
+        if (tid < RB * NS) {
+            const int r = tid / NS, s = tid - r * NS;
+            if (r < tv && (!BWD || a.lam_pass)) {
+                double v = 0;
+                for (int w = 0; w < 8; w++) v += s_red[(w * RB + r) * NS + s];
+                if (BWD)
+                    atomic_add(a.rowacc + (long)(t0 + r) * NS + s, v);
+                else if (a.d0 + s < Do)
+                    atomic_add(a.rowacc + (long)(t0 + r) * Do + a.d0 + s, v);
+            }
+        }
+    }
+    if (BWD) {
+        double* rec = a.pairpart + (long)blockIdx.y * (DOC + 1 + Q) * PP;
+        GPB_UNROLL
+        for (int j = 0; j < RP; j++) {
+            const long p = pbase + j * kThreads + tid;
+            GPB_UNROLL
+            for (int d = 0; d < DOC; d++) rec[(long)d * PP + p] = (double)accB[j][d];
+            rec[(long)DOC * PP + p] = (double)accS0[j];
+            GPB_UNROLL
+            for (int q = 0; q < Q; q++) rec[(long)(DOC + 1 + q) * PP + p] = (double)accS1[j][q];
+        }
+    }
+}
+
+// psi1 forward + moment matching epilogue (kernels.py:214-218,233; aep_models.py:195-198):
+//   mout[n,d] = sum_m A[d,m] psi1[n,m] ;  vout[n,d] = sf2 + vacc[n,d] - mout^2
+// thread per row, z/A staged in shared memory, per-thread row state in shared slots.
+template <typename T>
+GPB_KERNEL void mm_psi1_fwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
+                                   const double* __restrict__ z, const double* __restrict__ ls,
+                                   const double* __restrict__ sf, const double* __restrict__ A,
+                                   const double* __restrict__ vacc, int n, int M, int Q, int Do,
+                                   double* __restrict__ mout, double* __restrict__ vout) {
+    GPB_DYN_SMEM(smem);
+    double* acc = (double*)smem;              // [Do][blockDim]
+    T* zs = (T*)(acc + (long)Do * blockDim.x); // [M][Q]
+    T* As = zs + (long)M * Q;                 // [Do][M]
+    T* mu = As + (long)Do * M;                // [Q][blockDim]
+    T* c1 = mu + (long)Q * blockDim.x;        // [Q][blockDim]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < M * Q; i += nt) zs[i] = (T)z[i];
+    for (int i = tid; i < Do * M; i += nt) As[i] = (T)A[i];
+    const double sf2 = exp(2.0 * sf[0]);
+    sync_threads();
+    for (long row = (long)blockIdx.x * nt + tid; row < n; row += (long)gridDim.x * nt) {
+        double cn = 1.0;
+        for (int q = 0; q < Q; q++) {
+            double lq = exp(2.0 * ls[q]);
+            double cc = 1.0 / (vx[row * Q + q] + lq);
+            cn *= sqrt(lq * cc);
+            mu[q * nt + tid] = (T)mx[row * Q + q];
+            c1[q * nt + tid] = (T)cc;
+        }
+        for (int d = 0; d < Do; d++) acc[d * nt + tid] = 0;
+        for (int m = 0; m < M; m++) {
+            T e = 0;
+            for (int q = 0; q < Q; q++) {
+                T diff = mu[q * nt + tid] - zs[m * Q + q];
+                e += diff * diff * c1[q * nt + tid];
+            }
+            double p1 = sf2 * cn * (double)fast_exp((T)(-0.5) * e);
+            for (int d = 0; d < Do; d++) acc[d * nt + tid] += (double)As[d * M + m] * p1;
+        }
+        for (int d = 0; d < Do; d++) {
+            double mo = acc[d * nt + tid];
+            mout[row * Do + d] = mo;
+            vout[row * Do + d] = sf2 + vacc[row * Do + d] - mo * mo;
+        }
+    }
+}
+
+// Backward, row-wise part: finishes dmx, dvx per row from the psi1 terms
+// (kernels.py:355-378) and the reduced psi2 sums {s, U, V} (kernels.py:419-431),
+// and emits per-block partials of the row-summed hyper terms:
+//   part[blk][0]      : dsf2  = sum_n (sum_m L1 + 2 s_n)/sf2
+//   part[blk][1+q]    : dl_q  (psi1: Zmu2_denom.. , psi2: the n-dependent terms of kernels.py:441-442)
+//   part[blk][1+Q]    : sum of scaled dv  (dv_sum, aep_models.py:247)
+template <typename T>
+GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
+                                   const double* __restrict__ z, const double* __restrict__ ls,
+                                   const double* __restrict__ sf, const double* __restrict__ A,
+                                   const double* __restrict__ dm, const double* __restrict__ dv,
+                                   const double* __restrict__ mout, const double* __restrict__ rowacc,
+                                   int n, int M, int Q, int Qt, int Do, double* __restrict__ dmx,
+                                   double* __restrict__ dvx, double* __restrict__ part) {
+    GPB_DYN_SMEM(smem);
+    double* red = (double*)smem;                 // [16]
+    double* slot = red + 16;                     // per-thread: [ (4Q + Do) ][blockDim]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    T* zs = (T*)(slot + (long)(4 * Q + Do) * nt); // [M][Q]
+    T* As = zs + (long)M * Q;                    // [Do][M]
+    for (int i = tid; i < M * Q; i += nt) zs[i] = (T)z[i];
+    for (int i = tid; i < Do * M; i += nt) As[i] = (T)A[i];
+    const double sf2 = exp(2.0 * sf[0]);
+    double* s_mu = slot;                // [Q][nt]
+    double* s_c1 = slot + (long)Q * nt;
+    double* s_dmu = slot + 2L * Q * nt;
+    double* s_dS = slot + 3L * Q * nt;
+    double* s_dma = slot + 4L * Q * nt;  // [Do][nt]  dm_all
+    sync_threads();
+    double p_sf2 = 0, p_dvsum = 0;
+    // dl partials live in registers only through the final reduction: accumulate in smem slots
+    // (reuse: one extra array of Q per thread would cost more smem; loop q outermost at the end)
+    // -> keep a small per-thread array via second sweep over q (cheap: per row, not per m)
+    double p_dl[16];
+    for (int q = 0; q < 16; q++) p_dl[q] = 0;
+    const int NS = 1 + 2 * Qt;
+    for (long row = (long)blockIdx.x * nt + tid; row < n; row += (long)gridDim.x * nt) {
+        double cn = 1.0;
+        for (int q = 0; q < Q; q++) {
+            double lq = exp(2.0 * ls[q]);
+            double cc = 1.0 / (vx[row * Q + q] + lq);
+            cn *= sqrt(lq * cc);
+            s_mu[q * nt + tid] = mx[row * Q + q];
+            s_c1[q * nt + tid] = cc;
+            s_dmu[q * nt + tid] = 0;
+            s_dS[q * nt + tid] = 0;
+        }
+        for (int d = 0; d < Do; d++) {
+            double dvd = dv[row * Do + d];
+            s_dma[d * nt + tid] = dm[row * Do + d] - 2.0 * dvd * mout[row * Do + d];
+            p_dvsum += dvd;
+        }
+        double L1sum = 0;
+        for (int m = 0; m < M; m++) {
+            T e = 0;
+            for (int q = 0; q < Q; q++) {
+                T diff = (T)s_mu[q * nt + tid] - zs[m * Q + q];
+                e += diff * diff * (T)s_c1[q * nt + tid];
+            }
+            double p1 = sf2 * cn * (double)fast_exp((T)(-0.5) * e);
+            double g = 0;
+            for (int d = 0; d < Do; d++) g += s_dma[d * nt + tid] * (double)As[d * M + m];
+            double L1 = g * p1;
+            L1sum += L1;
+            for (int q = 0; q < Q; q++) {
+                double c = s_c1[q * nt + tid];
+                double zm = (double)zs[m * Q + q] - s_mu[q * nt + tid];
+                s_dmu[q * nt + tid] += L1 * zm * c;
+                s_dS[q * nt + tid] += L1 * (zm * zm * c - 1.0) * c;   // x 1/2 below
+            }
+        }
+        const double s = rowacc[row * NS];
+        p_sf2 += (L1sum + 2.0 * s) / sf2;
+        for (int q = 0; q < Q; q++) {
+            const double l = exp(ls[q]), lq = l * l;
+            const double S = vx[row * Q + q], mu = s_mu[q * nt + tid];
+            const double c1 = s_c1[q * nt + tid];
+            const double c2 = 1.0 / (2.0 * S + lq);
+            const double U = rowacc[row * NS + 1 + q], V = rowacc[row * NS + 1 + Qt + q];
+            // psi1: sum_m L1 ((z-mu)^2 c1 + S/l^2) c1 l  =  (dS_acc + (1 + S/l^2) L1sum c1) l
+            double dl1 = (s_dS[q * nt + tid] + (1.0 + S / lq) * c1 * L1sum) * l;
+            // psi2 (n-dependent part of kernels.py:441-442)
+            double dl2 = 2.0 * l * ((S / lq * c2 + mu * mu * c2 * c2) * s - 2.0 * mu * c2 * c2 * U + c2 * c2 * V);
+            if (q < 16) p_dl[q] += dl1 + dl2;
+            dmx[row * Q + q] = s_dmu[q * nt + tid] - 2.0 * c2 * (mu * s - U);
+            dvx[row * Q + q] = 0.5 * s_dS[q * nt + tid] +
+                               2.0 * c2 * c2 * (mu * mu * s - 2.0 * mu * U + V) - c2 * s;
+        }
+    }
+    double r = block_sum(p_sf2, red);
+    if (tid == 0) part[(long)blockIdx.x * (2 + Q)] = r;
+    for (int q = 0; q < Q; q++) {
+        r = block_sum(p_dl[q < 16 ? q : 15], red);
+        if (tid == 0) part[(long)blockIdx.x * (2 + Q) + 1 + q] = r;
+    }
+    r = block_sum(p_dvsum, red);
+    if (tid == 0) part[(long)blockIdx.x * (2 + Q) + 1 + Q] = r;
+}
+
+// Backward, column-wise psi1 part (kernels.py:355-378 terms indexed by m; aep_models.py:239):
+//   dA[d,m] = sum_n dm_all[n,d] psi1[n,m] ;  dZ1[m,q] = -sum_n L1 (z_mq - mu_nq) c1_nq
+// thread per pseudo point m, rows of this block's range staged in shared memory.
+// partial record per block: [ dA (Do*M) | dZ1 (M*Q) ]
+template <typename T>
+GPB_KERNEL void mm_cols_bwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
+                                   const double* __restrict__ z, const double* __restrict__ ls,
+                                   const double* __restrict__ sf, const double* __restrict__ A,
+                                   const double* __restrict__ dm, const double* __restrict__ dv,
+                                   const double* __restrict__ mout, int n, int M, int Q, int Do,
+                                   int rows_per_block, double* __restrict__ part) {
+    constexpr int TR = 32;
+    GPB_DYN_SMEM(smem);
+    double* s_mu = (double*)smem;         // [TR][Q]
+    double* s_c1 = s_mu + TR * Q;          // [TR][Q]
+    double* s_cn = s_c1 + TR * Q;          // [TR]
+    double* s_dma = s_cn + TR;             // [TR][Do]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* slot = s_dma + TR * Do;        // per-thread [Q (z) + Q (dZ) + Do (A) + Do (dA)][nt]
+    double* t_z = slot;
+    double* t_dz = slot + (long)Q * nt;
+    double* t_A = slot + 2L * Q * nt;
+    double* t_dA = slot + (2L * Q + Do) * nt;
+    const double sf2 = exp(2.0 * sf[0]);
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = (r_begin + rows_per_block) < n ? (r_begin + rows_per_block) : n;
+    double* rec = part + (long)blockIdx.x * ((long)Do * M + (long)M * Q);
+    for (int m0 = 0; m0 < M; m0 += nt) {
+        const int m = m0 + tid;
+        const bool act = m < M;
+        for (int q = 0; q < Q; q++) {
+            t_z[q * nt + tid] = act ? z[(long)m * Q + q] : 0.0;
+            t_dz[q * nt + tid] = 0;
+        }
+        for (int d = 0; d < Do; d++) {
+            t_A[d * nt + tid] = act ? A[(long)d * M + m] : 0.0;
+            t_dA[d * nt + tid] = 0;
+        }
+        for (int t0 = r_begin; t0 < r_end; t0 += TR) {
+            const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+            sync_threads();
+            for (int r = tid; r < TR; r += nt) {
+                double cn = 1.0;
+                for (int q = 0; q < Q; q++) {
+                    double lq = exp(2.0 * ls[q]);
+                    double cc = r < tv ? 1.0 / (vx[(long)(t0 + r) * Q + q] + lq) : 0.0;
+                    if (r < tv) cn *= sqrt(lq * cc);
+                    s_mu[r * Q + q] = r < tv ? mx[(long)(t0 + r) * Q + q] : 0.0;
+                    s_c1[r * Q + q] = cc;
+                }
+                s_cn[r] = r < tv ? cn : 0.0;
+                for (int d = 0; d < Do; d++)
+                    s_dma[r * Do + d] = r < tv ? dm[(long)(t0 + r) * Do + d] -
+                                                     2.0 * dv[(long)(t0 + r) * Do + d] * mout[(long)(t0 + r) * Do + d]
+                                               : 0.0;
+            }
+            sync_threads();
+            if (act)
+                for (int r = 0; r < tv; r++) {
+                    T e = 0;
+                    for (int q = 0; q < Q; q++) {
+                        T diff = (T)s_mu[r * Q + q] - (T)t_z[q * nt + tid];
+                        e += diff * diff * (T)s_c1[r * Q + q];
+                    }
+                    double p1 = sf2 * s_cn[r] * (double)fast_exp((T)(-0.5) * e);
+                    double g = 0;
+                    for (int d = 0; d < Do; d++) {
+                        g += s_dma[r * Do + d] * t_A[d * nt + tid];
+                        t_dA[d * nt + tid] += s_dma[r * Do + d] * p1;
+                    }
+                    double L1 = g * p1;
+                    for (int q = 0; q < Q; q++)
+                        t_dz[q * nt + tid] -= L1 * (t_z[q * nt + tid] - s_mu[r * Q + q]) * s_c1[r * Q + q];
+                }
+        }
+        if (act) {
+            for (int d = 0; d < Do; d++) rec[(long)d * M + m] = t_dA[d * nt + tid];
+            for (int q = 0; q < Q; q++) rec[(long)Do * M + (long)m * Q + q] = t_dz[q * nt + tid];
+        }
+        sync_threads();
+    }
+}
+
+// Backward, pair -> matrix scatter (deterministic gather form).  Inputs are the pair sums
+// already reduced over row splits: dBp[Do][PP], S0[PP], S1[Q][PP].
+//   dB[d,a,b]   = dBp[d,p(a,b)]                                   (aep_models.py:240)
+//   dZ2[a,q]    = sum_b { a!=b: S0/2 (z_b-z_a)/l^2 + S1_q ; a==b: 2 S1_q }   (kernels.py:436-440)
+//   W_q (dl)    = sum_p S0[p] (z_a-z_b)^2/4  ->  dlW[a,q] partial rows, summed on the host side
+GPB_KERNEL void mm_pair_finish_kernel(const double* __restrict__ pairsum, int DOCs, int Do,
+                                      const double* __restrict__ z, const double* __restrict__ ls,
+                                      int M, int Q, long PP, double* __restrict__ dB,
+                                      double* __restrict__ dZ2, double* __restrict__ dlW) {
+    // pairsum layout: [Do dBp rows][S0][S1 x Q], each of length PP
+    const double* S0 = pairsum + (long)Do * PP;
+    const double* S1 = pairsum + (long)(Do + 1) * PP;
+    (void)DOCs;
+    const long totalB = (long)Do * M * M;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalB;
+         idx += (long)gridDim.x * blockDim.x) {
+        int b = (int)(idx % M), a = (int)((idx / M) % M), d = (int)(idx / ((long)M * M));
+        int hi = a > b ? a : b, lo = a > b ? b : a;
+        dB[idx] = pairsum[(long)d * PP + (long)hi * (hi + 1) / 2 + lo];
+    }
+    const long totalZ = (long)M * Q;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalZ;
+         idx += (long)gridDim.x * blockDim.x) {
+        int q = (int)(idx % Q), a = (int)(idx / Q);
+        const double il2 = exp(-2.0 * ls[q]);
+        const double za = z[(long)a * Q + q];
+        double g = 0, w = 0;
+        for (int b = 0; b < M; b++) {
+            int hi = a > b ? a : b, lo = a > b ? b : a;
+            long p = (long)hi * (hi + 1) / 2 + lo;
+            double s1 = S1[(long)q * PP + p];
+            if (a == b) {
+                g += 2.0 * s1;
+            } else {
+                double dzb = z[(long)b * Q + q] - za;
+                g += 0.5 * S0[p] * dzb * il2 + s1;
+                if (b < a) w += S0[p] * dzb * dzb * 0.25;   // each unordered pair once
+            }
+        }
+        dZ2[idx] = g;
+        dlW[idx] = w;
+    }
+}
+
+// zero-padded typed operand copies for the deterministic layer kernels
+template <typename T>
+GPB_KERNEL void det_pad_kernel(const double* __restrict__ A, const double* __restrict__ B, int M,
+                               int MP, int Do, T* __restrict__ Ap, T* __restrict__ Bp) {
+    const long totalB = (long)Do * MP * MP;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < totalB;
+         i += (long)gridDim.x * blockDim.x) {
+        int j = (int)(i % MP), r = (int)((i / MP) % MP), d = (int)(i / ((long)MP * MP));
+        Bp[i] = (r < M && j < M) ? (T)B[((long)d * M + r) * M + j] : (T)0;
+        if (i < (long)Do * MP) {
+            int c = (int)(i % MP), dd = (int)(i / MP);
+            Ap[i] = c < M ? (T)A[(long)dd * M + c] : (T)0;
+        }
+    }
+}
+
+// det_bwd epilogue: fold the summed partial record [cs | dz | dl | dA] (padded MP columns)
+// into dA[Do,M], dzu[M,D], dl[D], dsf2[1].  One block.
+GPB_KERNEL void det_bwd_finish_kernel(const double* __restrict__ rec, const double* __restrict__ sf,
+                                      int M, int MP, int D, int Do, double* __restrict__ dA,
+                                      double* __restrict__ dzu, double* __restrict__ dl,
+                                      double* __restrict__ dsf2) {
+    GPB_SHARED double scratch[16];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < Do * M; i += nt) {
+        int d = i / M, m = i - d * M;
+        dA[i] = rec[(long)MP + 2L * MP * D + (long)d * MP + m];
+    }
+    for (int i = tid; i < M * D; i += nt) dzu[i] = rec[(long)MP + i];
+    double s = 0;
+    for (int m = tid; m < M; m += nt) s += rec[m];
+    double r = block_sum(s, scratch);
+    if (tid == 0) dsf2[0] = r / exp(2.0 * sf[0]);
+    for (int q = 0; q < D; q++) {
+        s = 0;
+        for (int m = tid; m < M; m += nt) s += rec[(long)MP + (long)MP * D + (long)m * D + q];
+        r = block_sum(s, scratch);
+        if (tid == 0) dl[q] = r;
+    }
+}
+
+// mm_bwd epilogue: dzu = dZ1 + dZ2 ; dl_q = dl_rows_q + 2 l_q W_q / l_q^4 (kernels.py:441-442);
+// scalars copied out.  One block.
+GPB_KERNEL void mm_final_kernel(const double* __restrict__ colsum /*[Do*M + M*Q]*/,
+                                const double* __restrict__ rowsum /*[2+Q]*/,
+                                const double* __restrict__ dZ2, const double* __restrict__ dlW,
+                                const double* __restrict__ ls, int M, int Q, int Do,
+                                double* __restrict__ dA, double* __restrict__ dzu,
+                                double* __restrict__ dl, double* __restrict__ dsf2,
+                                double* __restrict__ dvsum) {
+    GPB_SHARED double scratch[16];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < Do * M; i += nt) dA[i] = colsum[i];
+    for (int i = tid; i < M * Q; i += nt) dzu[i] = colsum[(long)Do * M + i] + dZ2[i];
+    for (int q = 0; q < Q; q++) {
+        double s = 0;
+        for (int a = tid; a < M; a += nt) s += dlW[(long)a * Q + q];
+        double r = block_sum(s, scratch);
+        if (tid == 0) {
+            double l = exp(ls[q]);
+            dl[q] = rowsum[1 + q] + 2.0 * l * r / (l * l * l * l);
+        }
+    }
+    if (tid == 0) {
+        dsf2[0] = rowsum[0];
+        dvsum[0] = rowsum[1 + Q];
+    }
+}
+
+// FMA-pipe peak microbenchmark (roofline denominator): 8 independent chains per thread
+template <typename T>
+GPB_KERNEL void fma_peak_kernel(long iters, double* __restrict__ sink) {
+    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+      a6 = a0 + 6, a7 = a0 + 7;
+    const T b = (T)0.999999, c = (T)1e-7;
+    for (long i = 0; i < iters; i++) {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+    }
+    // one real store per block keeps every chain live
+    double r = (double)(a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7);
+    r = warp_sum(r);
+    if (threadIdx.x == 0) sink[blockIdx.x] = r;
+}
+
+}  // namespace gpb

@@ -1,0 +1,206 @@
+"""Thin torch-tensor wrappers over the C ABI (include/geepee_b200.h).
+
+torch is used for device memory and the current CUDA stream only; every op below is one
+call into libgeepee_b200.so with raw device pointers.  Inputs are fp64, C-contiguous
+tensors that already live on the device; nothing here copies to the host or synchronises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+F64 = 0
+F32 = 1
+
+PREC = {'fp64': F64, 'f64': F64, 'fp32': F32, 'f32': F32, 'fp32_psi': F32, F64: F64, F32: F32}
+
+
+def prec_dtype(prec):
+    return torch.float64 if prec == F64 else torch.float32
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    if t.is_cuda:
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
+def _chk(rc, what):
+    if rc != 0:
+        msg = _lib.get().gpb_last_error()
+        raise RuntimeError('geepee_b200.%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def _c(t, dtype=torch.float64):
+    """Contract check: right device type, dtype, contiguous."""
+    if t.device.type != _lib.device_type():
+        raise RuntimeError('geepee_b200: tensor on %s, library expects %s (no CPU fallback)'
+                           % (t.device.type, _lib.device_type()))
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError('geepee_b200: expected contiguous %s tensor, got %s%s'
+                           % (dtype, t.dtype, '' if t.is_contiguous() else ' (strided)'))
+    return t
+
+
+def _ws(nbytes, like):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def launch_count():
+    return int(_lib.get().gpb_launch_count())
+
+
+def kmat(x, z, ls, sf, jitter=0.0):
+    """kernels.py:10-22 compute_kernel(2*ls, 2*sf, x, z) (+ jitter*I when x is z)."""
+    lib = _lib.get()
+    n, D = x.shape
+    M = z.shape[0]
+    out = torch.empty((n, M), dtype=torch.float64, device=x.device)
+    _chk(lib.gpb_kmat(_p(_c(x)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), n, M, D, float(jitter),
+                      _p(out), _stream(x)), 'kmat')
+    return out
+
+
+def psi_stats(mx, vx, z, ls, sf):
+    """kernels.py:181-240 compute_psi_weave(2*ls, 2*sf, mx, vx, z), materialised."""
+    lib = _lib.get()
+    n, Q = mx.shape
+    M = z.shape[0]
+    psi1 = torch.empty((n, M), dtype=torch.float64, device=mx.device)
+    psi2 = torch.empty((n, M, M), dtype=torch.float64, device=mx.device)
+    _chk(lib.gpb_psi_stats(_p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), n, M, Q,
+                           _p(psi1), _p(psi2), _stream(mx)), 'psi_stats')
+    return psi1, psi2
+
+
+def gauss_lik(m, v, y, sn, alpha, scale, mode):
+    """lik_layers.py:104-133 (mode 0) / 183-199 (mode 1).  Returns scaled dm, dv and a
+    device tensor [sum of log terms, dsn-sum]."""
+    lib = _lib.get()
+    total = m.numel()
+    dm = torch.empty_like(m)
+    dv = torch.empty_like(m)
+    out2 = torch.empty(2, dtype=torch.float64, device=m.device)
+    nb = lib.gpb_gauss_lik_ws_bytes(total)
+    ws = _ws(nb, m)
+    _chk(lib.gpb_gauss_lik(_p(_c(m)), _p(_c(v)), _p(_c(y)), _p(_c(sn)), float(alpha), float(scale),
+                           total, int(mode), _p(dm), _p(dv), _p(out2), _p(ws), ws.numel(),
+                           _stream(m)), 'gauss_lik')
+    return dm, dv, out2
+
+
+class DetOperands(object):
+    """Zero-padded, precision-typed copies of (A, B_det) for the deterministic layer."""
+
+    def __init__(self, prec, A, B):
+        lib = _lib.get()
+        self.prec = prec
+        self.Do, self.M = A.shape
+        self.MP = lib.gpb_det_pad_m(self.M)
+        if self.MP < 0:
+            raise RuntimeError('geepee_b200: M=%d unsupported by the deterministic layer kernels (max 512)' % self.M)
+        dt = prec_dtype(prec)
+        self.Ap = torch.empty((self.Do, self.MP), dtype=dt, device=A.device)
+        self.Bp = torch.empty((self.Do, self.MP, self.MP), dtype=dt, device=A.device)
+        _chk(lib.gpb_det_pad_operands(prec, _p(_c(A)), _p(_c(B)), self.M, self.Do, _p(self.Ap),
+                                      _p(self.Bp), _stream(A)), 'det_pad_operands')
+
+
+def det_fwd(prec, x, z, ls, sf, opnd, save=True):
+    """aep_models.py:142-158 / base_models.py:265-284.  Returns mout, vout and (if save)
+    the on-device Kfu[n,MP] and T[n,Do,MP] buffers the backward kernels stream."""
+    lib = _lib.get()
+    n, D = x.shape
+    Do, M, MP = opnd.Do, opnd.M, opnd.MP
+    mout = torch.empty((n, Do), dtype=torch.float64, device=x.device)
+    vout = torch.empty((n, Do), dtype=torch.float64, device=x.device)
+    Ks = Ts = None
+    if save:
+        dt = prec_dtype(prec)
+        Ks = torch.empty((n, MP), dtype=dt, device=x.device)
+        Ts = torch.empty((n, Do, MP), dtype=dt, device=x.device)
+    _chk(lib.gpb_det_fwd(prec, _p(_c(x)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(opnd.Ap), _p(opnd.Bp),
+                         n, M, D, Do, _p(mout), _p(vout), _p(Ks), _p(Ts), _stream(x)), 'det_fwd')
+    return mout, vout, Ks, Ts
+
+
+def det_bwd(prec, x, z, ls, sf, opnd, dm, dv, Ks, Ts):
+    """aep_models.py:452-460,490 + kernels.py:381-399.  -> dA, dzu, dl, dsf2 (device)."""
+    lib = _lib.get()
+    n, D = x.shape
+    Do, M = opnd.Do, opnd.M
+    dev = x.device
+    dA = torch.empty((Do, M), dtype=torch.float64, device=dev)
+    dzu = torch.empty((M, D), dtype=torch.float64, device=dev)
+    dl = torch.empty((D,), dtype=torch.float64, device=dev)
+    dsf2 = torch.empty((1,), dtype=torch.float64, device=dev)
+    ws = _ws(lib.gpb_det_bwd_ws_bytes(n, M, D, Do), x)
+    _chk(lib.gpb_det_bwd(prec, _p(_c(x)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(opnd.Ap), _p(_c(dm)),
+                         _p(_c(dv)), _p(Ks), _p(Ts), n, M, D, Do, _p(dA), _p(dzu), _p(dl), _p(dsf2),
+                         _p(ws), ws.numel(), _stream(x)), 'det_bwd')
+    return dA, dzu, dl, dsf2
+
+
+def det_syrk(prec, Ks, dv, M):
+    """aep_models.py:493  dB[d] = sum_n dv[n,d] kfu kfu^T."""
+    lib = _lib.get()
+    n, Do = dv.shape
+    dB = torch.empty((Do, M, M), dtype=torch.float64, device=dv.device)
+    ws = _ws(lib.gpb_det_syrk_ws_bytes(n, M, Do), dv)
+    _chk(lib.gpb_det_syrk(prec, _p(Ks), _p(_c(dv)), n, M, Do, _p(dB), _p(ws), ws.numel(),
+                          _stream(dv)), 'det_syrk')
+    return dB
+
+
+def mm_fwd(prec, mx, vx, z, ls, sf, A, B):
+    """aep_models.py:183-199 / base_models.py:286-307; psi2 stays on chip."""
+    lib = _lib.get()
+    n, Q = mx.shape
+    Do, M = A.shape
+    mout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
+    vout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
+    ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 0), mx)
+    _chk(lib.gpb_mm_fwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
+                        _p(_c(B)), n, M, Q, Do, _p(mout), _p(vout), _p(ws), ws.numel(),
+                        _stream(mx)), 'mm_fwd')
+    return mout, vout
+
+
+def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout):
+    """aep_models.py:238-250 + kernels.py:302-309,355-378,402-444."""
+    lib = _lib.get()
+    n, Q = mx.shape
+    Do, M = A.shape
+    dev = mx.device
+    f = torch.float64
+    out = {
+        'dA': torch.empty((Do, M), dtype=f, device=dev),
+        'dB': torch.empty((Do, M, M), dtype=f, device=dev),
+        'dzu': torch.empty((M, Q), dtype=f, device=dev),
+        'dl': torch.empty((Q,), dtype=f, device=dev),
+        'dsf2': torch.empty((1,), dtype=f, device=dev),
+        'dvsum': torch.empty((1,), dtype=f, device=dev),
+        'dmx': torch.empty((n, Q), dtype=f, device=dev),
+        'dvx': torch.empty((n, Q), dtype=f, device=dev),
+    }
+    ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 1), mx)
+    _chk(lib.gpb_mm_bwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
+                        _p(_c(B)), _p(_c(dm)), _p(_c(dv)), _p(_c(mout)), n, M, Q, Do,
+                        _p(out['dA']), _p(out['dB']), _p(out['dzu']), _p(out['dl']), _p(out['dsf2']),
+                        _p(out['dvsum']), _p(out['dmx']), _p(out['dvx']), _p(ws), ws.numel(),
+                        _stream(mx)), 'mm_bwd')
+    return out
+
+
+def fma_peak(prec, iters, device):
+    """Launch the FMA microbenchmark; returns the flop count (time it with CUDA events)."""
+    lib = _lib.get()
+    sink = torch.zeros(8 * lib.gpb_sm_count(), dtype=torch.float64, device=device)
+    flops = ctypes.c_double(0.0)
+    _chk(lib.gpb_fma_peak(prec, int(iters), _p(sink), ctypes.byref(flops), _stream(sink)), 'fma_peak')
+    return flops.value

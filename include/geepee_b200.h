@@ -1,0 +1,126 @@
+/*
+ * geepee_b200.h -- C ABI of the B200-native hot path of thangbui/geepee.
+ *
+ * Drop-in boundary.  geepee is a pure-Python/numpy library; the only foreign
+ * function interface on its hot path is `weave.inline(...)` in
+ * geepee/kernels.py:236-239, which compiles the C++ loop of
+ * `compute_psi_weave` (kernels.py:181-240) at run time.  `gpb_psi_stats` is the
+ * 1:1 replacement of that routine.  Every other entry point replaces one
+ * numpy/scipy contraction group of the SGP_Layer forward / backward
+ * (file:line cited per function) so that the N x M (Kfu) and N x M x M (psi2)
+ * intermediates the reference materialises are produced tile by tile on chip.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory (HBM) unless
+ *     the name starts with `h_`; all arrays are C-contiguous row-major.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     every call is asynchronous and stream ordered, none synchronises.
+ *   - `prec`: GPB_F64 ("fp64 mode", reference arithmetic) or GPB_F32 ("fp32-psi
+ *     mode": kernel / psi generation and tile contractions in fp32; every
+ *     cross-row accumulator and every interface array stays fp64).
+ *   - hyper-parameters are passed as the reference stores them: `ls[D]` = log
+ *     lengthscales, `sf[1]` = log signal std, `sn[1]` = log noise std
+ *     (base_models.py:630-658), on the device.
+ *   - return value 0 = ok, otherwise a negative error code; gpb_last_error()
+ *     gives the message.  No entry point has a CPU fallback.
+ *   - workspaces: `gpb_*_ws_bytes` returns the scratch size an op needs; the
+ *     caller owns the buffer (256-byte aligned).
+ */
+#ifndef GEEPEE_B200_H
+#define GEEPEE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_F64 0
+#define GPB_F32 1
+
+#define GPB_OK 0
+#define GPB_ERR_ARG -1   /* unsupported size / null pointer */
+#define GPB_ERR_CUDA -2  /* CUDA runtime error (launch, attribute, ...) */
+#define GPB_ERR_WS -3    /* workspace too small */
+
+int gpb_version(void);
+const char* gpb_last_error(void);
+/* number of SMs the launch heuristics size grids for (148 on B200) */
+int gpb_sm_count(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+long gpb_launch_count(void);
+
+/* ---- a1: ARD-SE kernel matrix.  kernels.py:10-22 compute_kernel(2*ls, 2*sf, x, z);
+ *      with jitter != 0 and n == M it is Kuu of base_models.py:454-464. */
+int gpb_kmat(const double* x, const double* z, const double* ls, const double* sf,
+             int n, int M, int D, double jitter, double* out /*[n,M]*/, void* stream);
+
+/* ---- a2: psi statistics, materialised.  kernels.py:181-240 compute_psi_weave(2*ls, 2*sf,
+ *      mx, vx, z) -> psi1[n,M], psi2[n,M,M].  The reference's weave FFI, one to one. */
+int gpb_psi_stats(const double* mx, const double* vx, const double* z, const double* ls,
+                  const double* sf, int n, int M, int Q, double* psi1, double* psi2, void* stream);
+
+/* ---- a7 / a7': Gaussian likelihood.  mode 0: lik_layers.py:104-133 compute_log_Z (+ the dv sum of
+ *      backprop_grads 154-181); mode 1: lik_layers.py:183-199 compute_log_lik_exp (+ the sum of
+ *      backprop_grads_log_lik_exp 217-226).  dm, dv come out multiplied by `scale`.
+ *      out2[0] = sum of log-terms (unscaled), out2[1] = mode 0: sum of unscaled dv; mode 1: dsn sum. */
+size_t gpb_gauss_lik_ws_bytes(long total);
+int gpb_gauss_lik(const double* m, const double* v, const double* y, const double* sn,
+                  double alpha, double scale, long total, int mode, double* dm, double* dv,
+                  double* out2, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- deterministic-input layer -------------------------------------------------------------- */
+/* M padded to the GEMM tile (128, 256 or 512); -1 if M > 512. */
+int gpb_det_pad_m(int M);
+/* element size of `prec` (8 or 4) */
+int gpb_prec_bytes(int prec);
+/* zero-padded, `prec`-typed copies of A[Do,M] -> Ap[Do,MP] and B[Do,M,M] -> Bp[Do,MP,MP] */
+int gpb_det_pad_operands(int prec, const double* A, const double* B, int M, int Do,
+                         void* Ap, void* Bp, void* stream);
+/* a5: aep_models.py:142-158 _forward_prop_deterministic_thru_cav (post twin base_models.py:265-284):
+ *      mout = kfu A^T, vout = sf2 + sum_ab B[d,a,b] kfu_a kfu_b, kfu generated on chip.
+ *      Optionally saves kfu[n,MP] and T[n,Do,MP] = B_d kfu (typed by prec) for the backward. */
+int gpb_det_fwd(int prec, const double* x, const double* z, const double* ls, const double* sf,
+                const void* Ap, const void* Bp, int n, int M, int D, int Do,
+                double* mout, double* vout, void* Ksave, void* Tsave, void* stream);
+/* a8 (per-row part): aep_models.py:452-460,490 + kernels.py:381-399 (kfucompDer), vfe twin
+ *      vfe_models.py:498-506.  dm, dv are the SCALED upstream gradients.
+ *      -> dA[Do,M] = sum_n dm kfu ; dzu[M,D] ; dl[D] (wrt lengthscale) ; dsf2[1] (wrt variance) */
+size_t gpb_det_bwd_ws_bytes(int n, int M, int D, int Do);
+int gpb_det_bwd(int prec, const double* x, const double* z, const double* ls, const double* sf,
+                const void* Ap, const double* dm, const double* dv, const void* Ksave,
+                const void* Tsave, int n, int M, int D, int Do, double* dA, double* dzu,
+                double* dl, double* dsf2, void* ws, size_t ws_bytes, void* stream);
+/* a8 (rank update): aep_models.py:493  dB[Do,M,M] = sum_n dv[n,d] kfu kfu^T */
+size_t gpb_det_syrk_ws_bytes(int n, int M, int Do);
+int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, int Do,
+                 double* dB, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- moment-matched (uncertain-input) layer ------------------------------------------------- */
+/* a6: aep_models.py:183-199 _forward_prop_random_thru_cav_mm (post twin base_models.py:286-307):
+ *      mout = psi1 A^T, vout = sf2 + sum_ab B[d,a,b] psi2[n,a,b] - mout^2; psi2 never stored. */
+size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward);
+int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
+               const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
+               double* mout, double* vout, void* ws, size_t ws_bytes, void* stream);
+/* a9 (per-row part): aep_models.py:238-250 + kernels.py:302-309,355-378,402-444
+ *      (compute_psi_derivatives), vfe twin vfe_models.py:351-361.
+ *      dm, dv scaled upstream gradients; mout from the forward.
+ *      -> dA[Do,M] = sum_n dm_all psi1 ; dB[Do,M,M] = sum_n dv psi2 ; dzu[M,Q] ; dl[Q] ; dsf2[1] ;
+ *         dvsum[1] = sum dv ; dmx[n,Q], dvx[n,Q] */
+int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
+               const double* sf, const double* A, const double* B, const double* dm,
+               const double* dv, const double* mout, int n, int M, int Q, int Do,
+               double* dA, double* dB, double* dzu, double* dl, double* dsf2, double* dvsum,
+               double* dmx, double* dvx, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------- */
+/* runs `iters` dependent-chain-free FMAs per thread on a full grid; returns total flops in
+ * *h_flops (host pointer).  `sink` is a device buffer of >= 8*gpb_sm_count() doubles.
+ * Time it with events on `stream`. */
+int gpb_fma_peak(int prec, long iters, double* sink, double* h_flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEEPEE_B200_H */
