@@ -1,0 +1,357 @@
+"""AEP (black-box alpha / approximate EP) models on the B200 hot path.
+
+Reference: geepee/aep_models.py -- SGPR 589-667, SGPLVM 670-867, SDGPR 870-988,
+SGPSSM 991-1437.  Same constructors, same ``objective_function(params, mb_size, alpha,
+prop_mode) -> (energy, grads)`` with the same dict keys and shapes.
+
+Every objective has the same three-phase shape:
+  1. per-row phase on this rank's slice of the minibatch: fused CUDA kernels ->
+     additive sufficient statistics (+ per-row input gradients that stay local);
+  2. one packed all-reduce of the statistics (no-op on one GPU);
+  3. the replicated O(Dout M^3) tail in fp64 -> gradients wrt every parameter.
+"""
+import numpy as np
+import torch
+
+from . import dist
+from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
+from .config import PROP_MM, PROP_MC, PROP_LIN
+from .layers import AEP_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
+
+_F = torch.float64
+
+
+def _check_mode(prop_mode):
+    if prop_mode == PROP_MM:
+        return
+    if prop_mode in (PROP_MC, PROP_LIN):
+        raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet '
+                                  '(SURVEY.md section 8f)' % prop_mode)
+    raise NotImplementedError('propagation mode not implemented')
+
+
+def _zeros(dev, *shape):
+    return torch.zeros(shape, dtype=_F, device=dev)
+
+
+def _zero_stats(layer, with_rows=0):
+    dev, Do, M, Q = layer.device, layer.Dout, layer.M, layer.Din
+    st = {'dA': _zeros(dev, Do, M), 'dB': _zeros(dev, Do, M, M), 'dzu': _zeros(dev, M, Q),
+          'dl': _zeros(dev, Q), 'dsf2': _zeros(dev, 1), 'dvsum': _zeros(dev, 1)}
+    return st
+
+
+_STAT_KEYS = ('dA', 'dB', 'dzu', 'dl', 'dsf2', 'dvsum')
+
+
+def _add_stats(add, prefix, st):
+    for k in _STAT_KEYS:
+        add[prefix + k] = st[k]
+
+
+def _get_stats(add, prefix):
+    return {k: add[prefix + k] for k in _STAT_KEYS}
+
+
+class SGPR(Base_SGPR):
+    """aep_models.py:589-667."""
+
+    def __init__(self, x_train, y_train, no_pseudo, lik='Gaussian', nat_param=True,
+                 prec=None, device=None):
+        super(SGPR, self).__init__(x_train, y_train, no_pseudo, lik, nat_param, prec, device)
+        self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        N, L, dev = self.N, self.sgp_layer, self.device
+        xb, yb, n = self._batch(mb_size)
+        scale_logZ = -N * 1.0 / n / alpha
+        self.update_hypers(params)
+        L.compute_cavity(alpha)
+        add = {}
+        if xb.shape[0] > 0:
+            m, v, ctx = L._fwd_det(xb, cav=True, save=True)
+            dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
+            _add_stats(add, 's_', L._bwd_det(ctx, dm, dv))
+            add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
+        else:
+            _add_stats(add, 's_', _zero_stats(L))
+            add['logZ'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
+        add = dist.allreduce_dict(add)
+        grads = L._tail_det(_get_stats(add, 's_'), alpha)
+        grads['sn'] = add['dsn'].reshape(())
+        energy = scale_logZ * add['logZ'] + L._phi(alpha)
+        return self._finish(energy, grads)
+
+
+class SDGPR(Base_SDGPR):
+    """aep_models.py:870-988 (layers are always natural-parameter: line 893)."""
+
+    def __init__(self, x_train, y_train, no_pseudos, hidden_sizes, lik='Gaussian',
+                 prec=None, device=None):
+        super(SDGPR, self).__init__(x_train, y_train, no_pseudos, hidden_sizes, lik, prec, device)
+        self.sgp_layers = [SGP_Layer(self.N, self.size[i], self.size[i + 1], self.Ms[i], True,
+                                     prec, self.device) for i in range(self.L)]
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        _check_mode(prop_mode)
+        N, dev = self.N, self.device
+        xb, yb, n = self._batch(mb_size)
+        scale_logZ = -N * 1.0 / n / alpha
+        self.update_hypers(params)
+        for layer in self.sgp_layers:
+            layer.compute_cavity(alpha)
+        add = {}
+        if xb.shape[0] > 0:
+            ctxs = []
+            m, v, ctx = self.sgp_layers[0]._fwd_det(xb, cav=True, save=True)
+            ctxs.append(ctx)
+            for layer in self.sgp_layers[1:]:
+                m, v, ctx = layer._fwd_mm(m, v, cav=True)
+                ctxs.append(ctx)
+            dmi, dvi, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
+            for i in range(self.L - 1, -1, -1):
+                layer = self.sgp_layers[i]
+                if i == 0:
+                    st = layer._bwd_det(ctxs[0], dmi, dvi)
+                else:
+                    st = layer._bwd_mm(ctxs[i], dmi, dvi)
+                    dmi, dvi = st['dmx'], st['dvx']
+                _add_stats(add, 's%d_' % i, st)
+            add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
+        else:
+            for i, layer in enumerate(self.sgp_layers):
+                _add_stats(add, 's%d_' % i, _zero_stats(layer))
+            add['logZ'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
+        add = dist.allreduce_dict(add)
+        grads = {}
+        energy = scale_logZ * add['logZ']
+        for i, layer in enumerate(self.sgp_layers):
+            st = _get_stats(add, 's%d_' % i)
+            g = layer._tail_det(st, alpha) if i == 0 else layer._tail_mm(st, alpha)
+            for k, val in g.items():
+                grads[k + '_%d' % i] = val
+            energy = energy + layer._phi(alpha)
+        grads['sn'] = add['dsn'].reshape(())
+        return self._finish(energy, grads)
+
+
+class SGPLVM(Base_SGPLVM):
+    """aep_models.py:670-867."""
+
+    def __init__(self, y_train, hidden_size, no_pseudo, lik='Gaussian', prior_mean=0, prior_var=1,
+                 nat_param=True, prec=None, device=None):
+        super(SGPLVM, self).__init__(y_train, hidden_size, no_pseudo, lik, prior_mean, prior_var,
+                                     nat_param, prec, device)
+        self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
+
+    def get_cavity_x(self, alpha, idxs=None):
+        """aep_models.py:840-861 (numpy API)."""
+        if idxs is None:
+            idxs = np.arange(self.N)
+        sel = torch.as_tensor(idxs, device=self.device)
+        m, v = self._cavity_x(alpha, sel)
+        return m.cpu().numpy(), v.cpu().numpy()
+
+    def _cavity_x(self, alpha, sel):
+        if self.nat_param:
+            c1 = self.prior_x1 + (1.0 - alpha) * self._f1[sel]
+            c2 = self.prior_x2 + (1.0 - alpha) * self._f2[sel]
+        else:
+            mpost, vpost = self._f1[sel], self._f2[sel]
+            c1 = self.prior_x1 + (mpost / vpost - self.prior_x1) * (1 - alpha)
+            c2 = self.prior_x2 + (1 / vpost - self.prior_x2) * (1 - alpha)
+        return (c1 / c2).contiguous(), (1.0 / c2).contiguous()
+
+    @staticmethod
+    def _phi_x(mx, vx):
+        """aep_models.py:863-867."""
+        return (0.5 * (mx**2 / vx + torch.log(vx))).sum(), mx / vx, 0.5 * (-mx**2 / vx**2 + 1 / vx)
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        _check_mode(prop_mode)
+        N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
+        sel, n = self._rows(mb_size)
+        scale_logZ = -N * 1.0 / n / alpha
+        s_cav = -N * 1.0 / n / alpha
+        s_post = -N * 1.0 / n * (1.0 - 1.0 / alpha)
+        self.update_hypers(params)
+        L.compute_cavity(alpha)
+        add = {'gx1': _zeros(dev, N, Q), 'gx2': _zeros(dev, N, Q)}
+        if sel.shape[0] > 0:
+            yb = self._y.index_select(0, sel)
+            mcav, vcav = self._cavity_x(alpha, sel)
+            p1, p2 = self._post1[sel], self._post2[sel]
+            mpost, vpost = p1 / p2, 1.0 / p2
+            m, v, ctx = L._fwd_mm(mcav, vcav, cav=True)
+            dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
+            st = L._bwd_mm(ctx, dm, dv)
+            _add_stats(add, 's_', st)
+            # latent-variable terms, aep_models.py:785-801, 817-838; base_models.py:913-929
+            phi_cav, dmc, dvc = self._phi_x(mcav, vcav)
+            phi_post, dmp, dvp = self._phi_x(mpost, vpost)
+            dmc = s_cav * dmc + st['dmx']
+            dvc = s_cav * dvc + st['dvx']
+            dmp, dvp = s_post * dmp, s_post * dvp
+            f2 = self._f2[sel]
+            t1, t2 = mcav / vcav, 1.0 / vcav
+            d1 = (1.0 - alpha) * dmc / t2
+            d2 = (1.0 - alpha) * (-dmc * t1 / t2**2 - dvc / t2**2)
+            if self.nat_param:
+                d2 = d2 * 2 * f2
+                d1 = d1 + dmp / p2
+                d2 = d2 + (-dmp * p1 / p2**2 - dvp / p2**2) * 2 * f2
+            else:
+                mp_, vp_ = self._f1[sel], f2
+                dmq = d1 / vp_
+                dvq = -d1 * mp_ / vp_**2 - d2 / vp_**2
+                d1 = dmq + dmp
+                d2 = (dvq + dvp) * 2 * f2
+            add['gx1'].index_copy_(0, sel, d1)
+            add['gx2'].index_copy_(0, sel, d2)
+            add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
+            add['phi_cav'], add['phi_post'] = phi_cav.reshape(1), phi_post.reshape(1)
+        else:
+            _add_stats(add, 's_', _zero_stats(L))
+            for k in ('logZ', 'dsn', 'phi_cav', 'phi_post'):
+                add[k] = _zeros(dev, 1)
+        add = dist.allreduce_dict(add)
+        grads = L._tail_mm(_get_stats(add, 's_'), alpha)
+        grads['sn'] = add['dsn'].reshape(())
+        grads['x1'], grads['x2'] = add['gx1'], add['gx2']
+        pm, pv = self.prior_mean, self.prior_var
+        phi_prior = 0.5 * (pm**2 / pv + np.log(pv)) * N * Q
+        x_contrib = phi_prior + s_cav * add['phi_cav'] + s_post * add['phi_post']
+        energy = scale_logZ * add['logZ'] + x_contrib + L._phi(alpha)
+        return self._finish(energy, grads, divide_by_N=False)   # aep_models.py:815: no /N
+
+
+class SGPSSM(Base_SGPSSM):
+    """aep_models.py:991-1437."""
+
+    def __init__(self, y_train, hidden_size, no_pseudo, lik='Gaussian', prior_mean=0, prior_var=1,
+                 x_control=None, gp_emi=False, control_to_emi=True, prec=None, device=None):
+        super(SGPSSM, self).__init__(y_train, hidden_size, no_pseudo, lik, prior_mean, prior_var,
+                                     x_control, gp_emi, control_to_emi, True, prec, device)
+        self.dyn_layer = SGP_Layer(self.N - 1, self.Din + self.Dcon_dyn, self.Din, self.M, True,
+                                   prec, self.device)
+        if gp_emi:
+            self.emi_layer = SGP_Layer(self.N, self.Din + self.Dcon_emi, self.Dout, self.M, True,
+                                       prec, self.device)
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        _check_mode(prop_mode)
+        N, Q, dev = self.N, self.Din, self.device
+        dyn, emi = self.dyn_layer, self.emi_layer
+        start, end = self._window(mb_size)
+        n_emi = end - start
+        n_dyn = n_emi - 1
+        s_dyn = -(N - 1) * 1.0 / n_dyn / alpha
+        s_emi = -N * 1.0 / n_emi / alpha
+        self.update_hypers(params)
+        dyn.compute_cavity(alpha)
+        if self.gp_emi:
+            emi.compute_cavity(alpha)
+        # cavity of every latent state (aep_models.py:1376-1387); replicated elementwise work
+        f1, f2, p1, p2 = self._f1, self._f2, self._post1, self._post2
+        cav1 = p1 - alpha * f1
+        cav2 = p2 - alpha * f2
+        cav_m, cav_v = cav1 / (cav2 + 1e-16), 1.0 / (cav2 + 1e-16)
+        sn2 = torch.exp(2.0 * self._sn)
+        add = {'l1': _zeros(dev, N, Q), 'l2': _zeros(dev, N, Q)}
+
+        def push(rows_lo, rows_hi, dmc, dvc):
+            """aep_models.py:1252-1275: chain a cavity-moment gradient to the cavity naturals."""
+            c1, c2 = cav1[rows_lo:rows_hi], cav2[rows_lo:rows_hi]
+            add['l1'][rows_lo:rows_hi] += dmc / c2
+            add['l2'][rows_lo:rows_hi] += -dmc * c1 / c2**2 - dvc / c2**2
+
+        # ---- transition factors t -> t+1 (aep_models.py:1092-1098, 1317-1374) ------------
+        dlo, dhi = dist.shard(n_dyn)
+        t0, t1 = start + dlo, start + dhi
+        if t1 > t0:
+            mtm1, vtm1 = self._with_control(cav_m[t0:t1], cav_v[t0:t1], t0, t1, self.Dcon_dyn)
+            mt, vt = cav_m[t0 + 1:t1 + 1], cav_v[t0 + 1:t1 + 1]
+            mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=True)
+            vsum = vt + vp + sn2 / alpha
+            md = mt - mp
+            lz = -0.5 * md**2 / vsum - 0.5 * torch.log(1 + alpha * (vt + vp) / sn2) \
+                - 0.5 * alpha * torch.log(2 * np.pi * sn2)
+            dvt = s_dyn * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+            dmt = s_dyn * (-md / vsum)
+            add['logZ_dyn'] = (s_dyn * lz.sum()).reshape(1)
+            add['dsn'] = (dvt.sum() * 2 * sn2 / alpha + s_dyn * (t1 - t0) * Q * (1 - alpha)).reshape(1)
+            st = dyn._bwd_mm(ctx, (-dmt).contiguous(), dvt.contiguous())
+            _add_stats(add, 'd_', st)
+            push(t0 + 1, t1 + 1, dmt, dvt)                                   # "prev" source
+            push(t0, t1, st['dmx'][:, :Q], st['dvx'][:, :Q])                 # "next" source
+        else:
+            _add_stats(add, 'd_', _zero_stats(dyn))
+            add['logZ_dyn'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
+        # ---- emission factors (aep_models.py:1100-1113, 1149-1151) --------------------------
+        elo, ehi = dist.shard(n_emi)
+        e0, e1 = start + elo, start + ehi
+        if e1 > e0:
+            mup, vup = self._with_control(cav_m[e0:e1], cav_v[e0:e1], e0, e1, self.Dcon_emi)
+            yb = self._y[e0:e1]
+            if self.gp_emi:
+                mo, vo, ctx = emi._fwd_mm(mup, vup, cav=True)
+                dme, dve, lZe, dsn_e = self.lik_layer._log_Z(mo, vo, yb, alpha, s_emi)
+                ste = emi._bwd_mm(ctx, dme, dve)
+                _add_stats(add, 'e_', ste)
+                add['logZ_emi'] = (s_emi * lZe).reshape(1)
+                add['dsn_emission'] = dsn_e.reshape(1)
+                push(e0, e1, ste['dmx'][:, :Q], ste['dvx'][:, :Q])
+            else:
+                lZe, dmx, dvx, ge = emi._tilted(mup, vup, alpha, s_emi, yb)
+                add['logZ_emi'] = lZe.reshape(1)
+                add['dC'], add['dR'] = ge['C'], ge['R']
+                push(e0, e1, dmx[:, :Q], dvx[:, :Q])
+        else:
+            add['logZ_emi'] = _zeros(dev, 1)
+            if self.gp_emi:
+                _add_stats(add, 'e_', _zero_stats(emi))
+                add['dsn_emission'] = _zeros(dev, 1)
+            else:
+                add['dC'] = _zeros(dev, self.Dout, Q + self.Dcon_emi)
+                add['dR'] = _zeros(dev, self.Dout)
+        add = dist.allreduce_dict(add)
+
+        # ---- replicated tail ----------------------------------------------------------------
+        grads = {'sn': add['dsn'].reshape(tuple(np.shape(self.sn)))}
+        for k, val in dyn._tail_mm(_get_stats(add, 'd_'), alpha).items():
+            grads[k + '_dynamic'] = val
+        if self.gp_emi:
+            for k, val in emi._tail_mm(_get_stats(add, 'e_'), alpha).items():
+                grads[k + '_emission'] = val
+            grads['sn_emission'] = add['dsn_emission'].reshape(())
+        else:
+            grads['C_emission'], grads['R_emission'] = add['dC'], add['dR']
+        # x gradients from the posterior / cavity log-partitions over ALL T rows
+        # (aep_models.py:1208-1232, 1287-1315) + the logZ sources gathered above (1234-1285)
+        one = torch.ones((N, 1), dtype=_F, device=dev)
+        s_post = -(1.0 - 1.0 / alpha) * one
+        s_post[0:N - 1] += 1.0 / alpha
+        s_post[1:N] += 1.0 / alpha
+        w3 = 3.0 * one
+        w3[0] = 2.0
+        w3[-1] = 2.0
+        gp1 = s_post * (p1 / p2)
+        gp2 = s_post * (-0.5 * p1**2 / p2**2 - 0.5 / p2)
+        gx1 = w3 * gp1
+        gx2 = 2.0 * w3 * gp2 * f2
+        w = w3 - alpha
+        sc = (-1.0 / alpha) * one
+        sc[0:N - 1] += -1.0 / alpha
+        sc[1:N] += -1.0 / alpha
+        gx1 = gx1 + (sc * (cav1 / cav2) + add['l1']) * w
+        gx2 = gx2 + (sc * (-0.5 * cav1**2 / cav2**2 - 0.5 / cav2) + add['l2']) * w * 2 * f2
+        grads['x_factor_1'], grads['x_factor_2'] = gx1, gx2
+        # energy (aep_models.py:1186-1197, 1389-1437)
+        m0, v0 = self.x_prior_1 / self.x_prior_2, 1.0 / self.x_prior_2
+        phi_prior = 0.5 * Q * (m0**2 / v0 + np.log(v0))
+        phi_post = (s_post * 0.5 * (p1**2 / p2 - torch.log(p2))).sum()
+        phi_cav = (sc * 0.5 * (cav1**2 / cav2 - torch.log(cav2))).sum()
+        energy = add['logZ_dyn'] + add['logZ_emi'] + phi_prior + phi_post + phi_cav + dyn._phi(alpha)
+        if self.gp_emi:
+            energy = energy + emi._phi(alpha)
+        return self._finish(energy, grads)

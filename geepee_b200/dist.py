@@ -1,0 +1,44 @@
+"""Data parallelism over minibatch rows.
+
+One process per GPU.  Every rank holds the (small) parameters and the training arrays;
+each evaluates the per-row kernels on its contiguous slice of the minibatch and the ranks
+exchange ONE packed fp64 buffer of additive sufficient statistics per objective call
+(`all_reduce(sum)`: NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests).  The
+O(Dout M^3) tail then runs redundantly and identically on every rank, so no broadcast of the
+result is needed.  With world size 1 everything here is a no-op.
+"""
+import torch
+
+
+def world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def shard(n):
+    """Contiguous slice [lo, hi) of `n` rows owned by this rank."""
+    rank, ws = world()
+    return (rank * n) // ws, ((rank + 1) * n) // ws
+
+
+def allreduce_packed(tensors):
+    """Sum a list of same-dtype device tensors across ranks with one collective.
+    Returns new tensors (views into the packed buffer)."""
+    rank, ws = world()
+    if ws == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+    out, off = [], 0
+    for t in tensors:
+        k = t.numel()
+        out.append(flat[off:off + k].reshape(t.shape))
+        off += k
+    return out
+
+
+def allreduce_dict(d):
+    keys = sorted(d.keys())
+    vals = allreduce_packed([d[k] for k in keys])
+    return dict(zip(keys, vals))

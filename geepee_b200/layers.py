@@ -1,0 +1,497 @@
+"""Sparse-GP layer: host-side mirror of the reference's SGP_Layer family.
+
+Reference: geepee/base_models.py:168-658 (Base_SGP_Layer), geepee/aep_models.py:26-586
+(AEP SGP_Layer), geepee/vfe_models.py:290-548 (VFE SGP_Layer).  Same method names, argument
+meaning and parameter dict keys.
+
+Division of labour
+  * every O(n) pass over rows runs in the CUDA kernels of libgeepee_b200.so (ops.py):
+    Kfu / psi generation fused with the contractions; the kernels return only the
+    cross-row sufficient statistics  S = {dA, dB, dzu, dl, dsf2, ...}  (SURVEY.md section 8a);
+  * the data-independent O(Dout M^3) "tail" (q(u) algebra, cavity, log-partitions, chain
+    rules back to eta1_R / eta2 / kernel hypers) is evaluated here in fp64 on the device with
+    batched Cholesky + GEMM calls; it is identical for every rank of a data-parallel job.
+All state lives in device tensors; the numpy views the reference exposes (``layer.Kuu`` ...)
+are materialised on attribute access for the layer-level API and the tests.
+"""
+import numpy as np
+import torch
+
+from . import config, ops, _lib
+
+_F = torch.float64
+
+# device tensors exposed under the reference's attribute names
+_EXPORTED = ('Kuu', 'Kuuinv', 'Su', 'Suinv', 'mu', 'Splusmm', 'A', 'B_det', 'B_sto', 'theta_1',
+             'theta_1_R', 'theta_2', 'Suhat', 'Suhatinv', 'muhat', 'Splusmmhat', 'Ahat', 'Bhat_det',
+             'Bhat_sto')
+
+
+def default_device():
+    if _lib.device_type() == 'cuda':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')       # only reachable through the test hook (emulator)
+
+
+def to_dev(a, device):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+def spd_inverse(A):
+    """inverse and log-determinant of (a batch of) SPD matrices via Cholesky.
+    Replaces np.linalg.inv / slogdet at base_models.py:464,471,476 and aep_models.py:68,78,91,525,533."""
+    L = torch.linalg.cholesky(A)
+    inv = torch.cholesky_inverse(L)
+    logdet = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
+    return inv, logdet
+
+
+def bmv(A, x):
+    """batched matrix-vector product [d,a,b] x [d,b] -> [d,a]"""
+    return torch.matmul(A, x.unsqueeze(-1)).squeeze(-1)
+
+
+def outer(a, b):
+    return a.unsqueeze(-1) * b.unsqueeze(-2)
+
+
+class Base_SGP_Layer(object):
+    """base_models.py:168-658."""
+
+    def __init__(self, no_train, input_size, output_size, no_pseudo, nat_param=True,
+                 prec=None, device=None):
+        self.Din, self.Dout, self.M, self.N = input_size, output_size, no_pseudo, no_train
+        self.nat_param = nat_param
+        self.prec = ops.PREC[prec if prec is not None else config.DEFAULT_PREC]
+        self.device = device if device is not None else default_device()
+        iu = torch.triu_indices(no_pseudo, no_pseudo)
+        self._iu = (iu[0].to(self.device), iu[1].to(self.device))
+        self._t = {}
+        self._opnd = {}
+        self.ls = np.zeros([input_size, ])
+        self.sf = 0
+        self.zu = np.zeros([no_pseudo, input_size])
+
+    def __getattr__(self, name):
+        if name in _EXPORTED:
+            t = self.__dict__.get('_t', {})
+            if name in t:
+                return t[name].detach().cpu().numpy()
+        raise AttributeError(name)
+
+    # ---- hyper-parameter plumbing ---------------------------------------------------------
+    def update_hypers(self, params, key_suffix=''):
+        """base_models.py:630-658: eta1_R -> R (log-diagonal upper triangle), theta_1 = R^T R."""
+        M, Dout, dev = self.M, self.Dout, self.device
+        self.ls = params['ls' + key_suffix]
+        self.sf = params['sf' + key_suffix]
+        self.zu = params['zu' + key_suffix]
+        t = self._t
+        t['ls'] = to_dev(np.reshape(self.ls, (self.Din,)), dev)
+        t['sf'] = to_dev(np.reshape(self.sf, (-1,))[:1], dev)
+        t['zu'] = to_dev(np.reshape(self.zu, (M, self.Din)), dev)
+        eta1 = to_dev(params['eta1_R' + key_suffix], dev)
+        R = torch.zeros((Dout, M, M), dtype=_F, device=dev)
+        R[:, self._iu[0], self._iu[1]] = eta1
+        dg = torch.diagonal(R, dim1=1, dim2=2)
+        dg.copy_(torch.exp(dg))
+        t['theta_1_R'] = R
+        t['theta_1'] = torch.matmul(R.transpose(1, 2), R)
+        t['theta_2'] = to_dev(params['eta2' + key_suffix], dev)
+        self.compute_kuu()
+        self.update_posterior()
+
+    def compute_kuu(self):
+        """base_models.py:454-464."""
+        t = self._t
+        t['Kuu'] = ops.kmat(t['zu'], t['zu'], t['ls'], t['sf'], config.JITTER)
+        t['Kuuinv'], t['logdet_Kuu'] = spd_inverse(t['Kuu'])
+
+    def update_posterior(self):
+        """base_models.py:466-488."""
+        t = self._t
+        Ki = t['Kuuinv']
+        if self.nat_param:
+            t['Suinv'] = Ki + t['theta_1']
+            t['Su'], ld = spd_inverse(t['Suinv'])
+            t['logdet_Su'] = -ld
+            t['mu'] = bmv(t['Su'], t['theta_2'])
+        else:
+            t['Su'] = t['theta_1']
+            t['Suinv'], ld = spd_inverse(t['Su'])
+            t['logdet_Su'] = ld
+            t['mu'] = t['theta_2']
+        t['Splusmm'] = t['Su'] + outer(t['mu'], t['mu'])
+        t['A'] = torch.matmul(t['mu'], Ki)
+        t['B_sto'] = torch.matmul(Ki, torch.matmul(t['Splusmm'], Ki)) - Ki
+        t['B_det'] = torch.matmul(Ki, torch.matmul(t['Su'], Ki)) - Ki
+        self._opnd.pop('post', None)
+
+    def get_hypers(self, key_suffix=''):
+        """base_models.py:599-628."""
+        M = self.M
+        R = self.theta_1_R.copy()
+        iu = np.triu_indices(M)
+        di = np.diag_indices(M)
+        eta1 = np.zeros((self.Dout, M * (M + 1) // 2))
+        for d in range(self.Dout):
+            Rd = R[d]
+            Rd[di] = np.log(Rd[di])
+            eta1[d, :] = Rd[iu]
+        return {'ls' + key_suffix: self.ls, 'sf' + key_suffix: self.sf, 'zu' + key_suffix: self.zu,
+                'eta1_R' + key_suffix: eta1, 'eta2' + key_suffix: self.theta_2}
+
+    def init_hypers(self, x_train=None, key_suffix=''):
+        """base_models.py:518-597 (host side: kmeans / median heuristic / random q(u))."""
+        from scipy.cluster.vq import kmeans2
+        from scipy.spatial.distance import cdist
+        N, M, Din, Dout = self.N, self.M, self.Din, self.Dout
+        if x_train is None:
+            ls = np.log(np.ones((Din, )) + 0.1 * np.random.rand(Din, ))
+            sf = np.log(np.array([1]))
+            zu = np.tile(np.linspace(-1, 1, M).reshape((M, 1)), (1, Din))
+        else:
+            if N < 10000:
+                centroids, label = kmeans2(x_train, M, minit='points')
+            else:
+                randind = np.random.permutation(N)
+                centroids = x_train[randind[0:M], :]
+            zu = centroids
+            if N < 1000:
+                X1 = np.copy(x_train)
+            else:
+                randind = np.random.permutation(N)
+                X1 = x_train[randind[:1000], :]
+            x_dist = cdist(X1, X1, 'euclidean')
+            triu_ind = np.triu_indices(X1.shape[0])
+            d2imed = np.median(x_dist[triu_ind])
+            ls = np.log(d2imed / 2 + 1e-16) * np.ones((Din, ))
+            sf = np.log(np.array([0.5]))
+        ls2, sf2 = np.exp(2 * ls), np.exp(2 * sf)
+        diff = zu[:, None, :] - zu[None, :, :]
+        Kuu = sf2 * np.exp(-0.5 * np.sum(diff * diff / ls2, axis=2)) + config.JITTER * np.eye(M)
+        Kuuinv = np.linalg.inv(Kuu)
+        eta1_R = np.zeros((Dout, M * (M + 1) // 2))
+        eta2 = np.zeros((Dout, M))
+        iu = np.triu_indices(M)
+        di = np.diag_indices(M)
+        for d in range(Dout):
+            mu = np.linspace(-1, 1, M).reshape((M, 1))
+            alpha = 0.5 * np.random.rand(M)
+            if self.nat_param:
+                theta1 = np.diag(1 / alpha)
+                theta2 = np.dot(theta1, mu)
+            else:
+                Su = np.linalg.inv(np.diag(1 / alpha) + Kuuinv)
+                theta1 = Su
+                theta2 = np.dot(Su, mu / alpha.reshape((M, 1)))
+            R = np.linalg.cholesky(theta1).T
+            R[di] = np.log(R[di])
+            eta1_R[d, :] = R[iu]
+            eta2[d, :] = theta2.reshape((M,))
+        return {'sf' + key_suffix: sf, 'ls' + key_suffix: ls, 'zu' + key_suffix: zu,
+                'eta1_R' + key_suffix: eta1_R, 'eta2' + key_suffix: eta2}
+
+    # ---- device fast path ------------------------------------------------------------------
+    def _AB(self, cav, stochastic):
+        t = self._t
+        if cav:
+            return t['Ahat'], (t['Bhat_sto'] if stochastic else t['Bhat_det'])
+        return t['A'], (t['B_sto'] if stochastic else t['B_det'])
+
+    def _det_operands(self, cav):
+        key = 'cav' if cav else 'post'
+        if key not in self._opnd:
+            A, B = self._AB(cav, False)
+            self._opnd[key] = ops.DetOperands(self.prec, A.contiguous(), B.contiguous())
+        return self._opnd[key]
+
+    def _fwd_det(self, x, cav, save):
+        """a5 on the device: (mout, vout, ctx)."""
+        t = self._t
+        opnd = self._det_operands(cav)
+        m, v, Ks, Ts = ops.det_fwd(self.prec, x, t['zu'], t['ls'], t['sf'], opnd, save=save)
+        return m, v, (x, opnd, Ks, Ts)
+
+    def _bwd_det(self, ctx, dm, dv):
+        """a8 per-row part: sufficient statistics of one deterministic layer."""
+        t = self._t
+        x, opnd, Ks, Ts = ctx
+        dA, dzu, dl, dsf2 = ops.det_bwd(self.prec, x, t['zu'], t['ls'], t['sf'], opnd, dm, dv, Ks, Ts)
+        dB = ops.det_syrk(self.prec, Ks, dv, self.M)
+        return {'dA': dA, 'dB': dB, 'dzu': dzu, 'dl': dl, 'dsf2': dsf2,
+                'dvsum': dv.sum().reshape(1)}
+
+    def _fwd_mm(self, mx, vx, cav):
+        """a6 on the device."""
+        t = self._t
+        A, B = self._AB(cav, True)
+        m, v = ops.mm_fwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous())
+        return m, v, (mx, vx, cav, m)
+
+    def _bwd_mm(self, ctx, dm, dv):
+        """a9 per-row part: statistics + per-row input gradients."""
+        t = self._t
+        mx, vx, cav, mout = ctx
+        A, B = self._AB(cav, True)
+        return ops.mm_bwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous(),
+                          dm, dv, mout)
+
+    # ---- shared chain rules ------------------------------------------------------------------
+    def _pack_eta1(self, dtheta1):
+        """theta_1 = R^T R with log-diagonal packing (base_models.py:505-514)."""
+        R = self._t['theta_1_R']
+        dR = torch.matmul(R, dtheta1 + dtheta1.transpose(1, 2))
+        dg = torch.diagonal(dR, dim1=1, dim2=2)
+        dg.mul_(torch.diagonal(R, dim1=1, dim2=2))
+        return dR[:, self._iu[0], self._iu[1]]
+
+    def _posterior_grad_u(self, dmu, dSu):
+        """base_models.py:490-516 -> (deta1_R, deta2, dKuuinv)."""
+        t = self._t
+        if self.nat_param:
+            dSu = dSu + outer(dmu, t['theta_2'])
+            dSuinv = -torch.matmul(t['Su'], torch.matmul(dSu, t['Su']))
+            return self._pack_eta1(dSuinv), bmv(t['Su'], dmu), dSuinv.sum(0)
+        return self._pack_eta1(dSu), dmu, torch.zeros_like(t['Kuu'])
+
+    def compute_posterior_grad_u(self, dmu, dSu):
+        r = self._posterior_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device))
+        return tuple(x.cpu().numpy() for x in r)
+
+    def _kernel_hyper_tail(self, st, Mm):
+        """aep_models.py:455-460 + 497-504 + kernels.py:447-475 (d_trace_MKzz_dhypers with
+        Kzz = Kuu - JITTER I): fold direct kernel derivatives with the Kuu path."""
+        t = self._t
+        z = t['zu']
+        l = torch.exp(t['ls'])
+        ls2 = l * l
+        sf2 = torch.exp(2.0 * t['sf'])
+        Kzz = t['Kuu'] - config.JITTER * torch.eye(self.M, dtype=_F, device=z.device)
+        dls = st['dl'] * l
+        dsf = 2.0 * sf2 * (st['dsf2'] + st['dvsum'])
+        g_sf = (Mm * Kzz).sum()
+        Ml = 0.5 * Mm * Kzz
+        Xl = z / l
+        Xl2 = Xl * Xl
+        g_ls = (Ml.sum(0).unsqueeze(1) * Xl2).sum(0) + (Ml.sum(1).unsqueeze(1) * Xl2).sum(0) \
+            - 2.0 * (Xl * torch.matmul(Ml, Xl)).sum(0)
+        Xb = z / ls2
+        g_z = torch.zeros_like(z)
+        for Mb in (-Mm.t() * Kzz, -Mm * Kzz):
+            g_z = g_z + Xb * Mb.sum(0).unsqueeze(1) - torch.matmul(Mb, Xb)
+        return dsf + 2.0 * g_sf, dls + 2.0 * g_ls, st['dzu'] + g_z
+
+    # ---- prediction path (base_models.py:235-307) -----------------------------------------
+    def forward_prop_thru_post(self, mx, vx=None, mode=config.PROP_MM, return_info=False):
+        dev = self.device
+        if vx is None:
+            x = to_dev(mx, dev)
+            m, v, _ = self._fwd_det(x, cav=False, save=False)
+            if return_info:
+                t = self._t
+                return m.cpu().numpy(), v.cpu().numpy(), ops.kmat(x, t['zu'], t['ls'], t['sf']).cpu().numpy()
+            return m.cpu().numpy(), v.cpu().numpy()
+        if mode == config.PROP_MM:
+            a, b = to_dev(mx, dev), to_dev(vx, dev)
+            m, v, _ = self._fwd_mm(a, b, cav=False)
+            if return_info:
+                t = self._t
+                p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
+                return m.cpu().numpy(), v.cpu().numpy(), p1.cpu().numpy(), p2.cpu().numpy()
+            return m.cpu().numpy(), v.cpu().numpy()
+        if mode in (config.PROP_MC, config.PROP_LIN):
+            raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet (SURVEY 8f)' % mode)
+        raise NotImplementedError('unknown propagation mode')
+
+
+class AEP_SGP_Layer(Base_SGP_Layer):
+    """aep_models.py:26-586."""
+
+    def compute_cavity(self, alpha):
+        """aep_models.py:513-546."""
+        t = self._t
+        Ki = t['Kuuinv']
+        beta = (self.N - alpha) * 1.0 / self.N
+        if self.nat_param:
+            t['Suhatinv'] = Ki + beta * t['theta_1']
+            t['Suhat'], ld = spd_inverse(t['Suhatinv'])
+            t['muhat'] = bmv(t['Suhat'], beta * t['theta_2'])
+        else:
+            f1 = t['Suinv'] - Ki
+            f2 = bmv(t['Suinv'], t['mu'])
+            t['Suhatinv'] = Ki + beta * f1
+            t['Suhat'], ld = spd_inverse(t['Suhatinv'])
+            t['muhat'] = bmv(t['Suhat'], beta * f2)
+        t['logdet_Suhat'] = -ld
+        t['Ahat'] = torch.matmul(t['muhat'], Ki)
+        t['Splusmmhat'] = t['Suhat'] + outer(t['muhat'], t['muhat'])
+        t['Bhat_sto'] = torch.matmul(Ki, torch.matmul(t['Splusmmhat'], Ki)) - Ki
+        t['Bhat_det'] = torch.matmul(Ki, torch.matmul(t['Suhat'], Ki)) - Ki
+        self._opnd.pop('cav', None)
+
+    def _phi(self, alpha):
+        """aep_models.py:62-114 (device scalar)."""
+        t = self._t
+        N = self.N
+        phi_prior = 0.5 * self.Dout * t['logdet_Kuu']
+        phi_post = 0.5 * t['logdet_Su'].sum() + 0.5 * (t['mu'] * bmv(t['Suinv'], t['mu'])).sum()
+        phi_cav = 0.5 * t['logdet_Suhat'].sum() + 0.5 * (t['muhat'] * bmv(t['Suhatinv'], t['muhat'])).sum()
+        return phi_prior + (N * 1.0 / alpha - 1.0) * phi_post - (N * 1.0 / alpha) * phi_cav
+
+    def compute_phi(self, alpha=1.0):
+        return float(self._phi(alpha).item())
+
+    def _cav_grad_u(self, dmu, dSu, alpha):
+        """aep_models.py:548-586."""
+        t = self._t
+        beta = (self.N - alpha) * 1.0 / self.N
+        if self.nat_param:
+            dSu = dSu + outer(dmu, beta * t['theta_2'])
+            dSuinv = -torch.matmul(t['Suhat'], torch.matmul(dSu, t['Suhat']))
+            return self._pack_eta1(beta * dSuinv), beta * bmv(t['Suhat'], dmu), dSuinv.sum(0)
+        f2 = bmv(t['Suinv'], t['mu'])
+        dSuhat = dSu + outer(dmu, beta * f2)
+        dSuhatinv = -torch.matmul(t['Suhat'], torch.matmul(dSuhat, t['Suhat']))
+        dSuinv_1 = beta * dSuhatinv
+        Sdm = bmv(t['Suhat'], dmu)
+        dSuinv = dSuinv_1 + beta * outer(Sdm, t['mu'])
+        dtheta1 = -torch.matmul(t['Suinv'], torch.matmul(dSuinv, t['Suinv']))
+        return self._pack_eta1(dtheta1), beta * bmv(t['Suinv'], Sdm), (1 - beta) / beta * dSuinv_1.sum(0)
+
+    def compute_cav_grad_u(self, dmu, dSu, alpha):
+        r = self._cav_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device), alpha)
+        return tuple(x.cpu().numpy() for x in r)
+
+    def _tail_det(self, st, alpha):
+        """aep_models.py:462-511 rewritten on the statistics (dA = sum_n dm kfu,
+        dB = sum_n dv kfu kfu^T): dmucav = dA Kuuinv, dSucav = Kuuinv dB Kuuinv."""
+        t = self._t
+        N, Ki = self.N, t['Kuuinv']
+        scale_post = N * 1.0 / alpha - 1.0
+        scale_cav = -N * 1.0 / alpha
+        dA, dB = st['dA'], st['dB']
+        dmucav = torch.matmul(dA, Ki)
+        dSucav = torch.matmul(Ki, torch.matmul(dB, Ki))
+        Sim = bmv(t['Suhatinv'], t['muhat'])
+        dmucav = dmucav + scale_cav * Sim
+        dSucav = dSucav + scale_cav * (0.5 * t['Suhatinv'] - 0.5 * outer(Sim, Sim))
+        e1c, e2c, dKi_cav = self._cav_grad_u(dmucav, dSucav, alpha)
+        Sim = bmv(t['Suinv'], t['mu'])
+        dmu = scale_post * Sim
+        dSu = scale_post * (0.5 * t['Suinv'] - 0.5 * outer(Sim, Sim))
+        e1p, e2p, dKi_post = self._posterior_grad_u(dmu, dSu)
+        dKi = torch.matmul(dA.t(), t['muhat']) \
+            + 2.0 * torch.matmul(torch.matmul(Ki, t['Suhat']).transpose(1, 2), dB).sum(0) \
+            - dB.sum(0) + dKi_cav + dKi_post - 0.5 * self.Dout * t['Kuu']
+        Mm = -torch.matmul(Ki, torch.matmul(dKi, Ki))
+        dsf, dls, dzu = self._kernel_hyper_tail(st, Mm)
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1c + e1p, 'eta2': e2c + e2p}
+
+    def _tail_mm(self, st, alpha):
+        """aep_models.py:252-297 on the statistics (dA = sum_n dm_all psi1, dB = sum_n dv psi2)."""
+        t = self._t
+        N, Ki = self.N, t['Kuuinv']
+        if not self.nat_param:
+            raise NotImplementedError('AEP moment-matched layers need nat_param=True (the reference '
+                                      'has no valid non-natural variant: aep_models.py:252-297)')
+        beta = (N - alpha) * 1.0 / N
+        scale_post = N * 1.0 / alpha - 1.0
+        scale_cav = -N * 1.0 / alpha
+        dA, dB = st['dA'], st['dB']
+        dvcav = torch.matmul(Ki, torch.matmul(dB, Ki))
+        dmcav = 2.0 * bmv(dvcav, t['muhat']) + torch.matmul(dA, Ki)
+        dvcav = dvcav + beta * outer(dmcav, t['theta_2'])
+        dvcavinv = -torch.matmul(t['Suhat'], torch.matmul(dvcav, t['Suhat']))
+        dtheta1 = beta * dvcavinv
+        dtheta2 = beta * bmv(t['Suhat'], dmcav)
+        dKi = torch.matmul(dA.t(), t['muhat']) \
+            + 2.0 * torch.matmul(torch.matmul(Ki, t['Splusmmhat']).transpose(1, 2), dB).sum(0) \
+            - dB.sum(0) + dvcavinv.sum(0)
+        Minner = scale_post * t['Splusmm'].sum(0) + scale_cav * t['Splusmmhat'].sum(0) - 2.0 * dKi
+        dtheta1 = -0.5 * scale_post * t['Splusmm'] - 0.5 * scale_cav * beta * t['Splusmmhat'] + dtheta1
+        dtheta2 = scale_post * t['mu'] + scale_cav * beta * t['muhat'] + dtheta2
+        M_all = 0.5 * (self.Dout * Ki + torch.matmul(Ki, torch.matmul(Minner, Ki)))
+        dsf, dls, dzu = self._kernel_hyper_tail(st, M_all)
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1(dtheta1), 'eta2': dtheta2}
+
+    # ---- layer-level API of the reference (numpy in / numpy out; small n) ------------------
+    def forward_prop_thru_cav(self, mx, vx=None, mode=config.PROP_MM):
+        """aep_models.py:116-140; returns the materialised kfu / psi like the reference."""
+        dev, t = self.device, self._t
+        if vx is None:
+            x = to_dev(mx, dev)
+            m, v, _ = self._fwd_det(x, cav=True, save=False)
+            return m.cpu().numpy(), v.cpu().numpy(), ops.kmat(x, t['zu'], t['ls'], t['sf']).cpu().numpy()
+        if mode == config.PROP_MM:
+            a, b = to_dev(mx, dev), to_dev(vx, dev)
+            m, v, _ = self._fwd_mm(a, b, cav=True)
+            p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
+            return m.cpu().numpy(), v.cpu().numpy(), p1.cpu().numpy(), p2.cpu().numpy()
+        if mode in (config.PROP_MC, config.PROP_LIN):
+            raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet (SURVEY 8f)' % mode)
+        raise NotImplementedError('unknown propagation mode')
+
+    def backprop_grads_reg(self, m, v, dm, dv, kfu, x, alpha=1.0):
+        """aep_models.py:413-511.  kfu is recomputed on chip; the argument is ignored."""
+        dev = self.device
+        xd = to_dev(x, dev)
+        _, _, ctx = self._fwd_det(xd, cav=True, save=True)
+        st = self._bwd_det(ctx, to_dev(dm, dev), to_dev(dv, dev))
+        return {k: g.cpu().numpy() for k, g in self._tail_det(st, alpha).items()}
+
+    def backprop_grads_lvm_mm(self, m, v, dm, dv, psi1, psi2, mx, vx, alpha=1.0):
+        """aep_models.py:202-304.  psi1 / psi2 are regenerated on chip; arguments ignored."""
+        dev = self.device
+        ctx = (to_dev(mx, dev), to_dev(vx, dev), True, to_dev(m, dev))
+        st = self._bwd_mm(ctx, to_dev(dm, dev), to_dev(dv, dev))
+        gh = {k: g.cpu().numpy() for k, g in self._tail_mm(st, alpha).items()}
+        return gh, {'mx': st['dmx'].cpu().numpy(), 'vx': st['dvx'].cpu().numpy()}
+
+
+class VFE_SGP_Layer(Base_SGP_Layer):
+    """vfe_models.py:290-548."""
+
+    def _kl(self):
+        """vfe_models.py:309-325."""
+        t = self._t
+        tr = (t['Kuuinv'] * t['Splusmm']).sum()
+        return 0.5 * (self.Dout * t['logdet_Kuu'] - t['logdet_Su'].sum() - self.Dout * self.M + tr)
+
+    def compute_KL(self):
+        return float(self._kl().item())
+
+    def _tail(self, st, stochastic):
+        """vfe_models.py:518-541 (det) / 363-394 (mm) on the statistics."""
+        t = self._t
+        Ki = t['Kuuinv']
+        dA, dB = st['dA'], st['dB']
+        dSu = torch.matmul(Ki, torch.matmul(dB, Ki))
+        dmu = torch.matmul(dA, Ki)
+        if stochastic:
+            dmu = dmu + 2.0 * bmv(dSu, t['mu'])
+        dmu = dmu + torch.matmul(t['mu'], Ki)
+        dSu = dSu + 0.5 * (Ki - t['Suinv'])
+        e1, e2, dKi_u = self._posterior_grad_u(dmu, dSu)
+        S = t['Splusmm'] if stochastic else t['Su']
+        dKi = torch.matmul(dA.t(), t['mu']) \
+            + 2.0 * torch.matmul(torch.matmul(Ki, S).transpose(1, 2), dB).sum(0) - dB.sum(0) \
+            + dKi_u - 0.5 * self.Dout * t['Kuu'] + 0.5 * t['Splusmm'].sum(0)
+        Mm = -torch.matmul(Ki, torch.matmul(dKi, Ki))
+        dsf, dls, dzu = self._kernel_hyper_tail(st, Mm)
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1, 'eta2': e2}
+
+    def backprop_grads_reg(self, m, v, dm, dv, kfu, x):
+        """vfe_models.py:479-548."""
+        dev = self.device
+        _, _, ctx = self._fwd_det(to_dev(x, dev), cav=False, save=True)
+        st = self._bwd_det(ctx, to_dev(dm, dev), to_dev(dv, dev))
+        return {k: g.cpu().numpy() for k, g in self._tail(st, False).items()}
+
+    def backprop_grads_lvm_mm(self, m, v, dm, dv, psi1, psi2, mx, vx):
+        """vfe_models.py:328-401."""
+        dev = self.device
+        ctx = (to_dev(mx, dev), to_dev(vx, dev), False, to_dev(m, dev))
+        st = self._bwd_mm(ctx, to_dev(dm, dev), to_dev(dv, dev))
+        gh = {k: g.cpu().numpy() for k, g in self._tail(st, True).items()}
+        return gh, {'mx': st['dmx'].cpu().numpy(), 'vx': st['dvx'].cpu().numpy()}

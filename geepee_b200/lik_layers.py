@@ -1,0 +1,183 @@
+"""Likelihood layers (reference: geepee/lik_layers.py).
+
+Gauss_Layer (85-283): the per-row log-partition / expected log-likelihood and their
+derivatives run in the `gauss_lik` CUDA kernel, fused with the scaling by scale_logZ.
+Gauss_Emis (474-676): linear-Gaussian emission of the state-space model; a batched
+Dout x Dout problem per row, evaluated on the device in fp64.
+Probit_Layer (285-471) is a "next" row of the scope table.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .layers import to_dev
+
+_F = torch.float64
+
+
+class Lik_Layer(object):
+    def __init__(self, N, D):
+        self.N = N
+        self.D = D
+
+    def init_hypers(self, key_suffix=''):
+        return {}
+
+    def get_hypers(self, key_suffix=''):
+        return {}
+
+    def update_hypers(self, params, key_suffix=''):
+        pass
+
+
+class Gauss_Layer(Lik_Layer):
+    def __init__(self, N, D, device=None):
+        super(Gauss_Layer, self).__init__(N, D)
+        self.sn = 0
+        self.device = device
+        self._sn = None
+
+    # ---- device path ------------------------------------------------------------------------
+    def _log_Z(self, m, v, y, alpha, scale):
+        """lik_layers.py:104-133 + 154-181.  Returns (scale*dm, scale*dv, logZ_sum, dsn) with
+        logZ_sum unscaled and dsn = scale*(sum(dv) 2 sn2/alpha + n D (1-alpha)), all on device."""
+        dm, dv, o = ops.gauss_lik(m, v, y, self._sn, alpha, scale, 0)
+        sn2 = torch.exp(2.0 * self._sn)
+        dsn = scale * (o[1] * 2.0 * sn2 / alpha + m.shape[0] * self.D * (1.0 - alpha))
+        return dm, dv, o[0], dsn.reshape(())
+
+    def _log_lik_exp(self, m, v, y, scale):
+        """lik_layers.py:183-199 + 217-226."""
+        dm, dv, o = ops.gauss_lik(m, v, y, self._sn, 1.0, scale, 1)
+        return dm, dv, o[0], (scale * o[1]).reshape(())
+
+    # ---- reference API (numpy) ---------------------------------------------------------------
+    def compute_log_Z(self, mout, vout, y, alpha=1.0):
+        """lik_layers.py:104-133, 2-D branch.  Like the reference, adds sn2/alpha to the
+        caller's vout array in place (line 122)."""
+        if mout.ndim != 2:
+            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+        dev = self._sn.device
+        dm, dv, o = ops.gauss_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._sn, alpha, 1.0, 0)
+        vout += np.exp(2.0 * self.sn) / alpha
+        return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
+
+    def backprop_grads(self, mout, vout, dmout, dvout, alpha=1.0, scale=1.0):
+        """lik_layers.py:154-181."""
+        sn2 = np.exp(2.0 * self.sn)
+        dim_prod = mout.shape[0] * self.D
+        return {'sn': scale * (np.sum(dvout) * 2 * sn2 / alpha + dim_prod * (1 - alpha))}
+
+    def compute_log_lik_exp(self, mout, vout, y):
+        if mout.ndim != 2:
+            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+        dev = self._sn.device
+        dm, dv, o = ops.gauss_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._sn, 1.0, 1.0, 1)
+        return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
+
+    def output_probabilistic(self, mf, vf, alpha=1.0):
+        """lik_layers.py:238-249."""
+        return mf, vf + np.exp(2.0 * self.sn) / alpha
+
+    def init_hypers(self, key_suffix=''):
+        self.sn = np.log(0.01)
+        return {'sn' + key_suffix: self.sn}
+
+    def get_hypers(self, key_suffix=''):
+        return {'sn' + key_suffix: self.sn}
+
+    def update_hypers(self, params, key_suffix=''):
+        self.sn = params['sn' + key_suffix]
+        self._sn = to_dev(np.reshape(self.sn, (-1,))[:1], self.device)
+
+
+class Gauss_Emis(object):
+    """lik_layers.py:474-676: y ~ N(C x, diag(R))."""
+
+    def __init__(self, y, Dout, Din, device=None):
+        self.y = y
+        self.N = y.shape[0]
+        self.Dout = Dout
+        self.Din = Din
+        self.device = device
+        self.C = np.zeros((Dout, Din))
+        self.R = np.zeros(Dout)
+        self._y = to_dev(y, device)
+
+    def update_hypers(self, params, key_suffix=''):
+        self.C = params['C' + key_suffix]
+        self.R = np.exp(2 * params['R' + key_suffix])
+        self._C = to_dev(self.C, self.device)
+        self._R = to_dev(self.R, self.device)
+
+    def init_hypers(self, key_suffix=''):
+        return {'C' + key_suffix: np.ones((self.Dout, self.Din)) / (self.Dout * self.Din),
+                'R' + key_suffix: np.log(0.01) * np.ones(self.Dout)}
+
+    def get_hypers(self, key_suffix=''):
+        return {'C' + key_suffix: self.C, 'R' + key_suffix: 0.5 * np.log(self.R)}
+
+    def output_probabilistic(self, mf, vf):
+        my = np.einsum('ab,nb->na', self.C, mf)
+        vy_noiseless = np.einsum('ab,nb,bc->nac', self.C, vf, self.C.T)
+        return my, vy_noiseless, vy_noiseless + np.diag(self.R)
+
+    def _tilted(self, mx, vx, alpha, scale, y):
+        """lik_layers.py:573-627 on the device: per-row Dout x Dout Cholesky.
+        Returns (scale*logZ, scale*dmx, scale*dvx, {'C','R'} grads)."""
+        C, R, Do = self._C, self._R, self.Dout
+        Nb = mx.shape[0]
+        CVC = torch.einsum('da,na,ba->ndb', C, vx, C)
+        Vy = torch.diag(R / alpha).unsqueeze(0) + CVC
+        Yd = y - torch.matmul(mx, C.t())
+        Lc = torch.linalg.cholesky(Vy)
+        VinvY = torch.cholesky_solve(Yd.unsqueeze(-1), Lc).squeeze(-1)
+        quad = -0.5 * (Yd * VinvY).sum()
+        # log|I + alpha CVC / R| = log|Vy| - sum log(R/alpha)
+        ld_Vy = 2.0 * torch.log(torch.diagonal(Lc, dim1=1, dim2=2)).sum()
+        vlog = -0.5 * (ld_Vy - Nb * torch.log(R / alpha).sum())
+        logZ = (-Nb * Do * 0.5 * alpha * np.log(2 * np.pi) - 0.5 * Nb * alpha * torch.log(R).sum()
+                + vlog + quad)
+        Vyinv = torch.cholesky_inverse(Lc)
+        dR = (-0.5 * torch.diagonal(Vyinv, dim1=1, dim2=2).sum(0) + 0.5 * (VinvY**2).sum(0)) / alpha
+        dR = (dR + 0.5 * Nb * (1 - alpha) / R) * 2 * R
+        dSig = -0.5 * Vyinv + 0.5 * VinvY.unsqueeze(-1) * VinvY.unsqueeze(-2)
+        dC = torch.matmul(VinvY.t(), mx) + 2.0 * torch.einsum('nc,bc,nab->ac', vx, C, dSig)
+        dmx = torch.matmul(VinvY, C)
+        dvx = torch.einsum('nab,ad,bd->nd', dSig, C, C)
+        return logZ * scale, dmx * scale, dvx * scale, {'C': dC * scale, 'R': dR * scale}
+
+    def _log_lik_exp(self, mx, vx, scale, y):
+        """lik_layers.py:629-676 on the device."""
+        C, R, Do = self._C, self._R, self.Dout
+        Nb = mx.shape[0]
+        Cm = torch.matmul(mx, C.t())
+        CRC_diag = (C * C / R.unsqueeze(1)).sum(0)
+        sv = vx.sum(0)
+        res2 = ((y - Cm)**2).sum(0)
+        logZ = (-0.5 * Nb * Do * np.log(2 * np.pi) - 0.5 * Nb * torch.log(R).sum()
+                - 0.5 * (res2 / R).sum() - 0.5 * (sv * CRC_diag).sum())
+        dR = (-0.5 * Nb / R + 0.5 * res2 / R**2 + 0.5 * (C * C * sv.unsqueeze(0)).sum(1) / R**2) * 2 * R
+        dC = torch.matmul((y - Cm).t(), mx) / R.unsqueeze(1) - C * sv.unsqueeze(0) / R.unsqueeze(1)
+        dmx = torch.matmul((y - Cm) / R.unsqueeze(0), C)
+        dvx = (-0.5 * CRC_diag).unsqueeze(0).expand(Nb, -1).contiguous()
+        return logZ * scale, dmx * scale, dvx * scale, {'C': dC * scale, 'R': dR * scale}
+
+    # reference API (numpy)
+    def compute_emission_tilted(self, mx, vx, alpha, scale, idxs=None):
+        if idxs is None:
+            idxs = np.arange(self.N)
+        dev = self.device
+        y = self._y[torch.as_tensor(idxs, device=dev)]
+        lz, dmx, dvx, g = self._tilted(to_dev(mx, dev), to_dev(vx, dev), alpha, scale, y)
+        return (float(lz.item()), {'mx': dmx.cpu().numpy(), 'vx': dvx.cpu().numpy()},
+                {k: v.cpu().numpy() for k, v in g.items()})
+
+    def compute_emission_log_lik_exp(self, mx, vx, scale, idxs=None):
+        if idxs is None:
+            idxs = np.arange(self.N)
+        dev = self.device
+        y = self._y[torch.as_tensor(idxs, device=dev)]
+        lz, dmx, dvx, g = self._log_lik_exp(to_dev(mx, dev), to_dev(vx, dev), scale, y)
+        return (float(lz.item()), {'mx': dmx.cpu().numpy(), 'vx': dvx.cpu().numpy()},
+                {k: v.cpu().numpy() for k, v in g.items()})

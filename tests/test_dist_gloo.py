@@ -1,0 +1,69 @@
+"""Data-parallel path on CPU: world_size=2 over gloo, each rank running the emulated kernels on
+its slice of the minibatch rows, ONE packed all-reduce of the statistics, replicated tail.
+The 2-rank result must equal the golden (single-process reference) result."""
+import copy
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, names, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, '..'))
+    sys.path.insert(0, os.path.join(HERE, '..', 'oracle'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.distributed.init_process_group('gloo', rank=rank, world_size=world)
+    import emu_util
+    import golden_util as gu
+    import model_cases as mc
+    emu_util.attach()
+    try:
+        for name in names:
+            mc.check_model(name, 'fp64', 1e-6)       # every rank checks the full result
+        q.put((rank, 'ok'))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, 'FAIL %s: %r' % (name, e)))
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize('names', [
+    ['aep_sgpr', 'aep_sgpr_minibatch', 'aep_sdgpr', 'vfe_sgpr'],
+    ['aep_sgplvm', 'aep_sgplvm_minibatch', 'aep_sgpssm_lin', 'aep_sgpssm_lin_window', 'aep_sgpssm_gp',
+     'vfe_sgplvm', 'vfe_sgpssm_lin'],
+])
+def test_two_ranks_match_golden(names):
+    import emu_util
+    emu_util.attach()          # build the emulator once, before forking
+    emu_util.detach()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, names, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == 'ok' for r in res), res
+
+
+def test_shard_covers_rows():
+    from geepee_b200 import dist
+    assert dist.shard(10) == (0, 10)

@@ -1,0 +1,29 @@
+"""Model-level parity on the CPU fiber emulator: the product's host code (geepee_b200 models,
+torch fp64 tail) driving the emulated kernels, against golden vectors from the reference."""
+import pytest
+
+import emu_util
+import golden_util as gu
+import model_cases as mc
+
+
+@pytest.fixture(scope='module', autouse=True)
+def emu():
+    emu_util.attach()
+    yield
+    emu_util.detach()
+
+
+@pytest.mark.parametrize('name', gu.model_cases())
+def test_objective_fp64(name):
+    mc.check_model(name, 'fp64', 1e-6)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr', 'aep_sgplvm', 'aep_sgpssm_lin', 'vfe_sgpr'])
+def test_objective_fp32(name):
+    mc.check_model(name, 'fp32', 1e-3)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat'])
+def test_predict(name):
+    mc.check_predict(name, 'fp64', 1e-8)

@@ -1,121 +1,31 @@
 """Kernel-level parity on the CPU fiber emulator (tests/emu): the SAME kernel and launch
 source as the CUDA library, compiled for the host, checked against the oracle's numpy
 formulas.  The `-m gpu` twin of this file is tests/test_gpu_ops.py."""
-import numpy as np
 import pytest
-import torch
 
 import emu_util
-import geepee_oracle as go
-import golden_util as gu
+import ops_cases as oc
 
 
 @pytest.fixture(scope='module', autouse=True)
 def emu():
     emu_util.attach()
+    oc.DEV = 'cpu'
     yield
     emu_util.detach()
 
 
-def T(a):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
-
-
-def problem(n, M, D, Do, seed, uncertain=False):
-    rng = np.random.RandomState(seed)
-    p = dict(x=rng.standard_normal((n, D)), z=rng.standard_normal((M, D)),
-             ls=0.3 * rng.standard_normal(D) + 0.3, sf=np.array([0.2]),
-             A=rng.standard_normal((Do, M)), dm=rng.standard_normal((n, Do)),
-             dv=rng.standard_normal((n, Do)))
-    B = rng.standard_normal((Do, M, M))
-    p['B'] = B + np.transpose(B, (0, 2, 1))
-    if uncertain:
-        p['vx'] = 0.05 + rng.rand(n, D)
-        p['Bn'] = B                      # non-symmetric B exercises the symmetrisation
-    return p
-
-
-DET_SHAPES = [(37, 5, 2, 3), (300, 10, 1, 1), (150, 130, 3, 2), (70, 260, 17, 1), (33, 128, 9, 9)]
-
-
 @pytest.mark.parametrize('prec,tol', [('fp64', 1e-12), ('fp32', 2e-4)])
-@pytest.mark.parametrize('n,M,D,Do', DET_SHAPES)
+@pytest.mark.parametrize('n,M,D,Do', oc.DET_SHAPES)
 def test_det_layer(n, M, D, Do, prec, tol):
-    from geepee_b200 import ops
-    pr = ops.PREC[prec]
-    p = problem(n, M, D, Do, seed=n + M)
-    x, z, ls, sf = T(p['x']), T(p['z']), T(p['ls']), T(p['sf'])
-    opnd = ops.DetOperands(pr, T(p['A']), T(p['B']))
-    mout, vout, Ks, Ts = ops.det_fwd(pr, x, z, ls, sf, opnd, save=True)
-    kfu = go.ard_kernel(2 * p['ls'], 2 * p['sf'], p['x'], p['z'])
-    m_ref = np.einsum('nm,dm->nd', kfu, p['A'])
-    v_ref = np.exp(2 * p['sf']) + np.einsum('dab,na,nb->nd', p['B'], kfu, kfu)
-    assert gu.rel_err(mout.numpy(), m_ref) < tol
-    assert gu.rel_err(vout.numpy(), v_ref) < tol
-    assert gu.rel_err(Ks.numpy()[:, :M], kfu) < tol
-    assert np.all(Ks.numpy()[:, M:] == 0)
-    assert gu.rel_err(Ts.numpy()[:, :, :M], np.einsum('dab,nb->nda', p['B'], kfu)) < tol
-    # backward
-    dm, dv = T(p['dm']), T(p['dv'])
-    dA, dzu, dl, dsf2 = ops.det_bwd(pr, x, z, ls, sf, opnd, dm, dv, Ks, Ts)
-    dB = ops.det_syrk(pr, Ks, dv, M)
-    dkfu = np.einsum('nd,dm->nm', p['dm'], p['A']) + 2 * np.einsum('nd,dab,na->nb', p['dv'], p['B'], kfu)
-    r_var, r_l, r_z = go.kfu_derivs(dkfu, kfu, np.exp(p['ls']), np.exp(2 * p['sf']), p['x'], p['z'])
-    assert gu.rel_err(dA.numpy(), np.einsum('nd,nm->dm', p['dm'], kfu)) < tol
-    assert gu.rel_err(dB.numpy(), np.einsum('nd,na,nb->dab', p['dv'], kfu, kfu)) < tol
-    assert gu.rel_err(dzu.numpy(), r_z) < tol
-    assert gu.rel_err(dl.numpy(), r_l) < tol
-    assert gu.rel_err(dsf2.numpy(), np.ravel(r_var)) < tol
-
-
-MM_SHAPES = [(9, 6, 3, 2), (40, 5, 2, 1), (21, 50, 1, 4), (13, 12, 5, 3), (11, 7, 7, 2), (10, 9, 4, 6)]
+    oc.check_det_layer(n, M, D, Do, prec, tol)
 
 
 @pytest.mark.parametrize('prec,tol', [('fp64', 1e-12), ('fp32', 3e-4)])
-@pytest.mark.parametrize('n,M,Q,Do', MM_SHAPES)
+@pytest.mark.parametrize('n,M,Q,Do', oc.MM_SHAPES)
 def test_mm_layer(n, M, Q, Do, prec, tol):
-    from geepee_b200 import ops
-    pr = ops.PREC[prec]
-    p = problem(n, M, Q, Do, seed=7 * n + M, uncertain=True)
-    mx, vx, z, ls, sf = T(p['x']), T(p['vx']), T(p['z']), T(p['ls']), T(p['sf'])
-    A, B = T(p['A']), T(p['Bn'])
-    mout, vout = ops.mm_fwd(pr, mx, vx, z, ls, sf, A, B)
-    psi1, psi2 = go.psi_stats(2 * p['ls'], 2 * p['sf'], p['x'], p['vx'], p['z'])
-    m_ref = np.einsum('nm,dm->nd', psi1, p['A'])
-    v_ref = np.exp(2 * p['sf']) + np.einsum('dab,nab->nd', p['Bn'], psi2) - m_ref**2
-    assert gu.rel_err(mout.numpy(), m_ref) < tol
-    assert gu.rel_err(vout.numpy(), v_ref) < tol * 10
-    out = ops.mm_bwd(pr, mx, vx, z, ls, sf, A, B, T(p['dm']), T(p['dv']), T(m_ref))
-    dm_all = p['dm'] - 2 * p['dv'] * m_ref
-    dpsi1 = np.einsum('nd,dm->nm', dm_all, p['A'])
-    dpsi2 = np.einsum('nd,dab->nab', p['dv'], p['Bn'])
-    r_var, r_l, r_z, r_mu, r_S = go.psi_derivs(dpsi1, psi1, dpsi2, psi2, np.exp(p['ls']),
-                                               np.exp(2 * p['sf']), p['x'], p['vx'], p['z'])
-    chk = [('dA', np.einsum('nd,nm->dm', dm_all, psi1)), ('dB', np.einsum('nd,nab->dab', p['dv'], psi2)),
-           ('dzu', r_z), ('dl', r_l), ('dsf2', np.ravel(r_var)), ('dvsum', np.ravel(p['dv'].sum())),
-           ('dmx', r_mu), ('dvx', r_S)]
-    for k, ref in chk:
-        assert gu.rel_err(out[k].numpy(), ref) < tol * 10, k
+    oc.check_mm_layer(n, M, Q, Do, prec, tol)
 
 
 def test_kmat_psi_lik():
-    from geepee_b200 import ops
-    f = np.load(gu.GOLDEN + '/kernels.npz')
-    ls, sf, mx, vx, z = (T(f[k]) for k in ['ls', 'sf', 'mx', 'vx', 'z'])
-    assert gu.rel_err(ops.kmat(mx, z, ls, sf).numpy(), f['kfu']) < 1e-14
-    kuu = ops.kmat(z, z, ls, sf, jitter=1e-5).numpy()
-    assert gu.rel_err(kuu, f['Kzz'] + 1e-5 * np.eye(z.shape[0])) < 1e-14
-    p1, p2 = ops.psi_stats(mx, vx, z, ls, sf)
-    assert gu.rel_err(p1.numpy(), f['psi1']) < 1e-13 and gu.rel_err(p2.numpy(), f['psi2']) < 1e-13
-    rng = np.random.RandomState(3)
-    m, v, y = rng.standard_normal((50, 3)), rng.rand(50, 3) + 0.1, rng.standard_normal((50, 3))
-    sn = np.array([-0.7])
-    dm, dv, o = ops.gauss_lik(T(m), T(v), T(y), T(sn), 0.6, -2.5, 0)
-    lz, rdm, rdv = go.gauss_log_Z(sn[0], m, v, y, 0.6)
-    assert abs(o[0].item() - lz) < 1e-12 * abs(lz) and abs(o[1].item() - rdv.sum()) < 1e-12 * abs(rdv.sum())
-    assert gu.rel_err(dm.numpy(), -2.5 * rdm) < 1e-13 and gu.rel_err(dv.numpy(), -2.5 * rdv) < 1e-13
-    dm, dv, o = ops.gauss_lik(T(m), T(v), T(y), T(sn), 1.0, -2.5, 1)
-    le, rdm, rdv = go.gauss_log_lik_exp(sn[0], m, v, y)
-    assert abs(o[0].item() - le) < 1e-12 * abs(le)
-    assert abs(-2.5 * o[1].item() - go.gauss_dsn_log_lik_exp(sn[0], m, v, y, -2.5)) < 1e-10
-    assert gu.rel_err(dm.numpy(), -2.5 * rdm) < 1e-13 and gu.rel_err(dv.numpy(), -2.5 * rdv) < 1e-13
+    oc.check_kmat_psi_lik()

@@ -1,0 +1,113 @@
+"""Model-level parity on the B200: geepee_b200 models (reference API) through the C ABI against
+the golden vectors generated from the reference -- energy and EVERY gradient key, 1e-6 relative
+in fp64 mode and 1e-3 in fp32-psi mode (BASELINE.json north_star) -- plus size-independent
+properties at larger shapes where the oracle would take too long."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import model_cases as mc
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-6
+TOL32 = 1e-3
+
+
+@pytest.fixture(scope='module', autouse=True)
+def cuda_lib():
+    from geepee_b200 import _lib
+    _lib._testing_detach()
+    assert torch.cuda.is_available()
+    _lib.get()
+    yield
+
+
+@pytest.mark.parametrize('name', gu.model_cases())
+def test_objective_fp64(name):
+    mc.check_model(name, 'fp64', TOL64)
+
+
+@pytest.mark.parametrize('name', gu.model_cases())
+def test_objective_fp32(name):
+    gold = gu.load(name)
+    if max(gold['meta'].get('floor', {}).values() or [0]) > 1e-7:
+        pytest.skip('ill-conditioned case (reference floor > 1e-7): fp64 only')
+    mc.check_model(name, 'fp32', TOL32)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat', 'aep_sgpr_cfg1'])
+def test_predict(name):
+    mc.check_predict(name, 'fp64', 1e-7)
+
+
+def _oracle_vs_gpu(make_oracle, make_gpu, params, N, alpha, tol):
+    import geepee_oracle as go  # noqa: F401
+    eo, g_o = make_oracle().objective_function(copy.deepcopy(params), N, alpha=alpha)
+    eg, g_g = make_gpu().objective_function(copy.deepcopy(params), N, alpha=alpha)
+    gold = {'energy': float(np.ravel(eo)[0]), 'g': g_o, 'meta': {}}
+    gu.assert_close(eg, g_g, gold, tol, 'oracle-vs-gpu')
+
+
+def test_sgpr_medium_vs_oracle():
+    """N=3000, M=60, D=4: several tiles / blocks / row splits, compared with the oracle."""
+    import geepee_oracle as go
+    from geepee_b200 import aep_models as aep
+    rng = np.random.RandomState(0)
+    N, M, D, Do = 3000, 60, 4, 2
+    x = rng.standard_normal((N, D))
+    y = np.sin(x[:, :Do]) + 0.1 * rng.standard_normal((N, Do))
+    np.random.seed(0)
+    model = aep.SGPR(x, y, M)
+    p = model.init_hypers(y)
+    p['sn'] = np.array(np.log(0.2))
+    _oracle_vs_gpu(lambda: go.AepSGPR(x, y, M), lambda: model, p, N, 0.5, TOL64)
+
+
+def test_sdgpr_medium_vs_oracle():
+    import geepee_oracle as go
+    from geepee_b200 import aep_models as aep
+    rng = np.random.RandomState(1)
+    N, M, D = 400, 30, 3
+    x = rng.standard_normal((N, D))
+    y = np.sin(x[:, :1]) + 0.1 * rng.standard_normal((N, 1))
+    np.random.seed(1)
+    model = aep.SDGPR(x, y, M, [2, 2])
+    p = model.init_hypers(y)
+    p['sn'] = np.array(np.log(0.2))
+    _oracle_vs_gpu(lambda: go.AepSDGPR(x, y, M, [2, 2]), lambda: model, p, N, 1.0, TOL64)
+
+
+def test_linearity_in_rows_large():
+    """Size-independent property at a large shape: the per-row statistics are additive over
+    rows, so energy*N - phi over [rows A + rows B] equals the sum of the two halves.  Checked
+    through the public objective by comparing a full batch to the mean of its two half-batch
+    'datasets' is not exact for AEP (N enters phi), so check the additive kernels directly."""
+    from geepee_b200 import ops
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(0)
+    n, M, D, Do = 200000, 256, 10, 1
+    x = torch.randn(n, D, generator=g, dtype=torch.float64).to(dev)
+    z = torch.randn(M, D, generator=g, dtype=torch.float64).to(dev)
+    ls = torch.full((D,), 0.7, dtype=torch.float64, device=dev)
+    sf = torch.zeros(1, dtype=torch.float64, device=dev)
+    A = torch.randn(Do, M, generator=g, dtype=torch.float64).to(dev)
+    B = 0.01 * torch.randn(Do, M, M, generator=g, dtype=torch.float64).to(dev)
+    B = (B + B.transpose(1, 2)).contiguous()
+    dm = torch.randn(n, Do, generator=g, dtype=torch.float64).to(dev)
+    dv = torch.randn(n, Do, generator=g, dtype=torch.float64).to(dev)
+    opnd = ops.DetOperands(ops.F64, A, B)
+
+    def stats(lo, hi):
+        xs, dms, dvs = x[lo:hi].contiguous(), dm[lo:hi].contiguous(), dv[lo:hi].contiguous()
+        m, v, Ks, Ts = ops.det_fwd(ops.F64, xs, z, ls, sf, opnd, save=True)
+        dA, dzu, dl, dsf2 = ops.det_bwd(ops.F64, xs, z, ls, sf, opnd, dms, dvs, Ks, Ts)
+        return [dA, dzu, dl, dsf2, ops.det_syrk(ops.F64, Ks, dvs, M), m.sum(0), v.sum(0)]
+
+    full = stats(0, n)
+    a, b = stats(0, 70001), stats(70001, n)
+    for f, p, q in zip(full, a, b):
+        assert gu.rel_err((p + q).cpu().numpy(), f.cpu().numpy()) < 1e-10
