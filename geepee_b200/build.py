@@ -23,11 +23,27 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """nvcc -c every .cu in parallel (one process per translation unit), then link."""
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + sources()
-    subprocess.check_call(cmd)
+    objdir = os.path.join(CSRC, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != '-shared'] + (['-Xptxas', '-v'] if verbose else [])
+    procs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        log = open(obj + '.log', 'w')
+        procs.append((src, log, subprocess.Popen([nvcc] + flags + ['-c', src, '-o', obj],
+                                                 stdout=log, stderr=subprocess.STDOUT)))
+    for src, log, p in procs:
+        rc = p.wait()
+        log.close()
+        if rc != 0:
+            raise RuntimeError('nvcc failed on %s:\n%s' % (src, open(log.name).read()[-4000:]))
+    subprocess.check_call([nvcc, '-shared', '-o', OUT] + objs)
     return OUT
 
 

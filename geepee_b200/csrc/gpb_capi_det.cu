@@ -1,0 +1,200 @@
+// gpb_capi_det.cu -- deterministic-input layer entry points (a5, a8).
+#include "gpb_common.cuh"
+
+namespace {
+
+// ------------------------------- deterministic layer ------------------------------------
+struct DetBwdPlan {
+    int MP, CWB, RY, gx, gy, rows_per_block, G;
+    long rec_len;
+};
+DetBwdPlan det_bwd_plan(int n, int M, int D, int Do) {
+    DetBwdPlan p;
+    p.MP = gpb_det_pad_m(M);
+    p.CWB = p.MP < 256 ? p.MP : 256;
+    p.RY = 256 / p.CWB;
+    p.gy = p.MP / p.CWB;
+    int want = 2 * sm_count() / p.gy;
+    if (want < 1) want = 1;
+    int rpb = (int)cdiv(n, want);
+    if (rpb < 32) rpb = 32;
+    p.rows_per_block = rpb;
+    p.gx = (int)cdiv(n, rpb);
+    p.G = p.gx * p.RY;
+    p.rec_len = (long)p.MP + 2L * p.MP * D + (long)Do * p.MP;
+    return p;
+}
+
+struct SyrkPlan {
+    int MP, nb, nbu, nsplit, rows_per_split;
+};
+SyrkPlan syrk_plan(int n, int M, int Do) {
+    SyrkPlan p;
+    p.MP = gpb_det_pad_m(M);
+    p.nb = p.MP / 128;
+    p.nbu = p.nb * (p.nb + 1) / 2;
+    int want = (int)cdiv(2L * sm_count(), (long)p.nbu * Do);
+    if (want < 1) want = 1;
+    int rps = (int)cdiv(n, want);
+    rps = (int)(cdiv(rps, 16) * 16);
+    if (rps < 16) rps = 16;
+    p.rows_per_split = rps;
+    p.nsplit = (int)cdiv(n, rps);
+    return p;
+}
+
+template <typename T, int MP>
+int det_fwd_launch(const double* x, const double* z, const double* ls, const double* sf,
+                   const void* Ap, const void* Bp, int n, int M, int D, int Do, double* mout,
+                   double* vout, void* Ksave, void* Tsave, void* stream) {
+    typedef gpb::DetCfg<T, MP> C;
+    gpb::DetFwdArgs<T> a;
+    a.x = x; a.z = z; a.ls = ls; a.sf = sf;
+    a.Ap = (const T*)Ap; a.Bp = (const T*)Bp;
+    a.n = n; a.M = M; a.D = D; a.Do = Do;
+    a.mout = mout; a.vout = vout; a.Ksave = (T*)Ksave; a.Tsave = (T*)Tsave;
+    auto kern = gpb::det_fwd_kernel<T, MP>;
+    int rc = allow_smem(kern, C::smem_bytes);
+    if (rc) return rc;
+    int ntiles = (int)cdiv(n, C::TN);
+    int grid = ntiles < sm_count() ? ntiles : sm_count();
+    prof_begin(0, stream);
+    GPB_LAUNCH(kern, dim3(grid), dim3(256), C::smem_bytes, stream, a);
+    prof_end(0, stream);
+    return GPB_CHECK_LAUNCH();
+}
+
+template <typename T>
+int det_fwd_t(const double* x, const double* z, const double* ls, const double* sf, const void* Ap,
+              const void* Bp, int n, int M, int D, int Do, double* mout, double* vout, void* Ksave,
+              void* Tsave, void* stream) {
+    switch (gpb_det_pad_m(M)) {
+        case 128: return det_fwd_launch<T, 128>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+        case 256: return det_fwd_launch<T, 256>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+        case 512: return det_fwd_launch<T, 512>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+    }
+    return fail(GPB_ERR_ARG, "det_fwd: M=%d unsupported (max 512)", M);
+}
+
+template <typename T>
+int det_bwd_t(const double* x, const double* z, const double* ls, const double* sf, const void* Ap,
+              const double* dm, const double* dv, const void* Ksave, const void* Tsave, int n, int M,
+              int D, int Do, double* dA, double* dzu, double* dl, double* dsf2, void* ws,
+              size_t ws_bytes, void* stream) {
+    DetBwdPlan p = det_bwd_plan(n, M, D, Do);
+    Carver cv(ws, ws_bytes);
+    double* part = (double*)cv.take(sizeof(double) * p.G * p.rec_len);
+    double* rec = (double*)cv.take(sizeof(double) * p.rec_len);
+    if (!cv.ok()) return fail(GPB_ERR_WS, "det_bwd: workspace %zu < %zu", ws_bytes, cv.off);
+    dim3 grid(p.gx, p.gy);
+#define GPB_BWD(DP)                                                                             \
+    {                                                                                           \
+        auto kern = gpb::det_bwd_kernel<T, DP>;                                                 \
+        GPB_LAUNCH(kern, grid, dim3(256), 0, stream, x, z, ls, (const T*)Ap, dm, dv,            \
+                   (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block, part, \
+                   p.rec_len);                                                                  \
+    }
+    prof_begin(1, stream);
+    if (D <= 4) GPB_BWD(4) else if (D <= 8) GPB_BWD(8) else GPB_BWD(16)
+    prof_end(1, stream);
+#undef GPB_BWD
+    int rc = GPB_CHECK_LAUNCH();
+    if (rc) return rc;
+    auto red = gpb::reduce_partials_kernel;
+    GPB_LAUNCH(red, dim3(elementwise_grid(p.rec_len)), dim3(256), 0, stream, part, p.G, p.rec_len,
+               p.rec_len, rec, 0);
+    auto fin = gpb::det_bwd_finish_kernel;
+    GPB_LAUNCH(fin, dim3(1), dim3(256), 0, stream, rec, sf, M, p.MP, D, Do, dA, dzu, dl, dsf2);
+    return GPB_CHECK_LAUNCH();
+}
+
+template <typename T>
+int det_syrk_t(const void* Ksave, const double* dv, int n, int M, int Do, double* dB, void* ws,
+               size_t ws_bytes, void* stream) {
+    SyrkPlan p = syrk_plan(n, M, Do);
+    Carver cv(ws, ws_bytes);
+    double* part = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
+    if (!cv.ok()) return fail(GPB_ERR_WS, "det_syrk: workspace %zu < %zu", ws_bytes, cv.off);
+    auto kern = gpb::det_syrk_kernel<T>;
+    prof_begin(2, stream);
+    GPB_LAUNCH(kern, dim3(p.nbu, p.nsplit, Do), dim3(256), 0, stream, (const T*)Ksave, dv, n, p.MP,
+               Do, p.rows_per_split, part);
+    prof_end(2, stream);
+    int rc = GPB_CHECK_LAUNCH();
+    if (rc) return rc;
+    auto fin = gpb::det_syrk_finish_kernel;
+    GPB_LAUNCH(fin, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, part, p.nsplit,
+               p.MP, M, Do, dB);
+    return GPB_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpb_det_pad_m(int M) {
+    if (M < 1) return -1;
+    if (M <= 128) return 128;
+    if (M <= 256) return 256;
+    if (M <= 512) return 512;
+    return -1;
+}
+
+int gpb_det_pad_operands(int prec, const double* A, const double* B, int M, int Do, void* Ap, void* Bp,
+                         void* stream) {
+    int MP = gpb_det_pad_m(M);
+    if (MP < 0 || !A || !B || !Ap || !Bp || Do < 1) return fail(GPB_ERR_ARG, "det_pad_operands: bad argument");
+    int grid = elementwise_grid((long)Do * MP * MP);
+    if (prec == GPB_F64) {
+        auto kern = gpb::det_pad_kernel<double>;
+        GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, A, B, M, MP, Do, (double*)Ap, (double*)Bp);
+    } else {
+        auto kern = gpb::det_pad_kernel<float>;
+        GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, A, B, M, MP, Do, (float*)Ap, (float*)Bp);
+    }
+    return GPB_CHECK_LAUNCH();
+}
+
+int gpb_det_fwd(int prec, const double* x, const double* z, const double* ls, const double* sf,
+                const void* Ap, const void* Bp, int n, int M, int D, int Do, double* mout, double* vout,
+                void* Ksave, void* Tsave, void* stream) {
+    if (!x || !z || !ls || !sf || !Ap || !Bp || !mout || !vout || n < 1 || D < 1 || Do < 1)
+        return fail(GPB_ERR_ARG, "det_fwd: bad argument");
+    if (D > 32) return fail(GPB_ERR_ARG, "det_fwd: D=%d unsupported (max 32)", D);
+    if (prec == GPB_F64) return det_fwd_t<double>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+    return det_fwd_t<float>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+}
+
+size_t gpb_det_bwd_ws_bytes(int n, int M, int D, int Do) {
+    if (gpb_det_pad_m(M) < 0) return 0;
+    DetBwdPlan p = det_bwd_plan(n, M, D, Do);
+    return align256(sizeof(double) * p.G * p.rec_len) + align256(sizeof(double) * p.rec_len);
+}
+
+int gpb_det_bwd(int prec, const double* x, const double* z, const double* ls, const double* sf,
+                const void* Ap, const double* dm, const double* dv, const void* Ksave, const void* Tsave,
+                int n, int M, int D, int Do, double* dA, double* dzu, double* dl, double* dsf2, void* ws,
+                size_t ws_bytes, void* stream) {
+    if (!x || !z || !ls || !sf || !Ap || !dm || !dv || !Ksave || !Tsave || !dA || !dzu || !dl || !dsf2 || !ws)
+        return fail(GPB_ERR_ARG, "det_bwd: null pointer");
+    if (gpb_det_pad_m(M) < 0 || n < 1 || D < 1 || Do < 1) return fail(GPB_ERR_ARG, "det_bwd: bad size");
+    if (prec == GPB_F64)
+        return det_bwd_t<double>(x, z, ls, sf, Ap, dm, dv, Ksave, Tsave, n, M, D, Do, dA, dzu, dl, dsf2, ws, ws_bytes, stream);
+    return det_bwd_t<float>(x, z, ls, sf, Ap, dm, dv, Ksave, Tsave, n, M, D, Do, dA, dzu, dl, dsf2, ws, ws_bytes, stream);
+}
+
+size_t gpb_det_syrk_ws_bytes(int n, int M, int Do) {
+    if (gpb_det_pad_m(M) < 0) return 0;
+    SyrkPlan p = syrk_plan(n, M, Do);
+    return align256(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
+}
+
+int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, int Do, double* dB,
+                 void* ws, size_t ws_bytes, void* stream) {
+    if (!Ksave || !dv || !dB || !ws || gpb_det_pad_m(M) < 0 || n < 1 || Do < 1)
+        return fail(GPB_ERR_ARG, "det_syrk: bad argument");
+    if (prec == GPB_F64) return det_syrk_t<double>(Ksave, dv, n, M, Do, dB, ws, ws_bytes, stream);
+    return det_syrk_t<float>(Ksave, dv, n, M, Do, dB, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// gpb_capi_misc.cu -- shared state + small entry points (kmat, psi_stats, gauss_lik, profiling).
+#include "gpb_common.cuh"
+
+char g_gpb_err[512] = "";
+long g_gpb_launches = 0;
+int g_gpb_prof_on = 0;
+#ifndef GPB_CPU_EMU
+GpbProfPair g_gpb_prof_pending[4096];
+int g_gpb_prof_n = 0;
+namespace {
+double g_prof_ms[8] = {0};
+long g_prof_cnt[8] = {0};
+}
+#endif
+
+extern "C" {
+
+int gpb_version(void) { return 100; }
+const char* gpb_last_error(void) { return g_err; }
+int gpb_sm_count(void) { return sm_count(); }
+long gpb_launch_count(void) { return g_launches; }
+int gpb_prec_bytes(int prec) { return prec == GPB_F32 ? 4 : 8; }
+
+
+int gpb_kmat(const double* x, const double* z, const double* ls, const double* sf, int n, int M,
+             int D, double jitter, double* out, void* stream) {
+    if (!x || !z || !ls || !sf || !out || n < 1 || M < 1 || D < 1) return fail(GPB_ERR_ARG, "kmat: bad argument");
+    auto kern = gpb::kmat_kernel;
+    GPB_LAUNCH(kern, dim3(elementwise_grid((long)n * M)), dim3(256), 0, stream, x, z, ls, sf, n, M, D,
+               jitter, out);
+    return GPB_CHECK_LAUNCH();
+}
+
+
+int gpb_psi_stats(const double* mx, const double* vx, const double* z, const double* ls,
+                  const double* sf, int n, int M, int Q, double* psi1, double* psi2, void* stream) {
+    if (!mx || !vx || !z || !ls || !sf || !psi1 || !psi2 || n < 1 || M < 1 || Q < 1)
+        return fail(GPB_ERR_ARG, "psi_stats: bad argument");
+    auto kern = gpb::psi_stats_kernel;
+    GPB_LAUNCH(kern, dim3(elementwise_grid((long)n * M * M)), dim3(256), 0, stream, mx, vx, z, ls, sf, n,
+               M, Q, psi1, psi2);
+    return GPB_CHECK_LAUNCH();
+}
+
+size_t gpb_gauss_lik_ws_bytes(long total) { return align256(sizeof(double) * 2 * (size_t)elementwise_grid(total)); }
+
+int gpb_gauss_lik(const double* m, const double* v, const double* y, const double* sn, double alpha,
+                  double scale, long total, int mode, double* dm, double* dv, double* out2, void* ws,
+                  size_t ws_bytes, void* stream) {
+    if (!m || !v || !y || !sn || !dm || !dv || !out2 || total < 1 || (mode != 0 && mode != 1))
+        return fail(GPB_ERR_ARG, "gauss_lik: bad argument");
+    int grid = elementwise_grid(total);
+    if (ws_bytes < sizeof(double) * 2 * (size_t)grid) return fail(GPB_ERR_WS, "gauss_lik: workspace too small");
+    auto kern = gpb::gauss_lik_kernel;
+    GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, m, v, y, sn, alpha, scale, total, mode, dm, dv,
+               (double*)ws);
+    auto red = gpb::reduce_partials_kernel;
+    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)ws, grid, 2L, 2L, out2, 0);
+    return GPB_CHECK_LAUNCH();
+}
+
+int gpb_profile_enable(int on) {
+    g_prof_on = on ? 1 : 0;
+    return GPB_OK;
+}
+
+int gpb_profile_collect(double* h_ms, long* h_count) {
+#ifndef GPB_CPU_EMU
+    for (int i = 0; i < g_prof_n; i++) {
+        ProfPair& p = g_prof_pending[i];
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof_ms[p.slot] += ms;
+            g_prof_cnt[p.slot]++;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_n = 0;
+    for (int i = 0; i < 8; i++) {
+        if (h_ms) h_ms[i] = g_prof_ms[i];
+        if (h_count) h_count[i] = g_prof_cnt[i];
+        g_prof_ms[i] = 0;
+        g_prof_cnt[i] = 0;
+    }
+#else
+    for (int i = 0; i < 8; i++) {
+        if (h_ms) h_ms[i] = 0;
+        if (h_count) h_count[i] = 0;
+    }
+#endif
+    return GPB_OK;
+}
+
+int gpb_fma_peak(int prec, long iters, double* sink, double* h_flops, void* stream) {
+    if (!sink || iters < 1) return fail(GPB_ERR_ARG, "fma_peak: bad argument");
+    int blocks = sm_count() * 8;
+    if (prec == GPB_F64) {
+        auto kern = gpb::fma_peak_kernel<double>;
+        GPB_LAUNCH(kern, dim3(blocks), dim3(256), 0, stream, iters, sink);
+    } else {
+        auto kern = gpb::fma_peak_kernel<float>;
+        GPB_LAUNCH(kern, dim3(blocks), dim3(256), 0, stream, iters, sink);
+    }
+    if (h_flops) *h_flops = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0;
+    return GPB_CHECK_LAUNCH();
+}
+
+}  // extern "C"

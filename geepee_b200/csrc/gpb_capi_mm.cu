@@ -1,0 +1,269 @@
+// gpb_capi_mm.cu -- moment-matched (uncertain-input) layer entry points (a2+a6, a2+a9).
+#include "gpb_common.cuh"
+
+namespace {
+
+// ------------------------------- moment-matched layer -----------------------------------
+struct MMPlan {
+    int Qt, DOC, RP, PC;
+    long P, PP;
+    int nchunks, nsplit, rows_per_split, npass;
+    int rows_grid, cols_grid, cols_rows_per_block;
+    // workspace byte offsets are carved in order by mm_carve
+};
+int q_template(int Q) {
+    if (Q <= 6) return Q;
+    if (Q <= 8) return 8;
+    if (Q <= 16) return 16;
+    return -1;
+}
+int mm_rp(int Qt, int DOC) {
+    int s = 2 * Qt + 2 * DOC + 2;
+    return s <= 12 ? 4 : (s <= 26 ? 2 : 1);
+}
+int mm_rb(int Qt) { return Qt <= 2 ? 8 : (Qt <= 4 ? 4 : (Qt <= 8 ? 2 : 1)); }
+
+MMPlan mm_plan(int n, int M, int Q, int Do) {
+    MMPlan p;
+    p.Qt = q_template(Q);
+    p.DOC = Do == 1 ? 1 : (Do == 2 ? 2 : 4);
+    p.npass = (int)cdiv(Do, p.DOC);
+    p.RP = mm_rp(p.Qt, p.DOC);
+    p.PC = 256 * p.RP;
+    p.P = (long)M * (M + 1) / 2;
+    p.PP = cdiv(p.P, 1024) * 1024;
+    p.nchunks = (int)(p.PP / p.PC);
+    int want = (int)cdiv(2L * sm_count(), p.nchunks);
+    if (want < 1) want = 1;
+    int rb = mm_rb(p.Qt);
+    long rps = cdiv(n, want);
+    rps = cdiv(rps, rb) * rb;
+    if (rps < rb) rps = rb;
+    p.rows_per_split = (int)rps;
+    p.nsplit = (int)cdiv(n, rps);
+    p.rows_grid = (int)cdiv(n, 128);
+    if (p.rows_grid > 4 * sm_count()) p.rows_grid = 4 * sm_count();
+    if (p.rows_grid < 1) p.rows_grid = 1;
+    int cb = 2 * sm_count();
+    long crpb = cdiv(n, cb);
+    if (crpb < 32) crpb = 32;
+    p.cols_rows_per_block = (int)crpb;
+    p.cols_grid = (int)cdiv(n, crpb);
+    return p;
+}
+
+template <typename T>
+struct MMWs {
+    T *zh, *ep, *bs;
+    double *rowacc, *pairpart, *pairsum, *rowpart, *rowsum, *colpart, *colsum, *dZ2, *dlW;
+    size_t bytes;
+};
+template <typename T>
+MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, void* ws, size_t cap) {
+    MMWs<T> w;
+    Carver cv(ws, cap);
+    w.zh = (T*)cv.take(sizeof(T) * p.Qt * p.PP);
+    w.ep = (T*)cv.take(sizeof(T) * p.PP);
+    w.bs = (T*)cv.take(sizeof(T) * Do * p.PP);
+    if (!backward) {
+        w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * Do);
+        w.pairpart = w.pairsum = w.rowpart = w.rowsum = w.colpart = w.colsum = w.dZ2 = w.dlW = nullptr;
+    } else {
+        w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * (1 + 2 * p.Qt));
+        w.pairpart = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * (p.DOC + 1 + p.Qt) * p.PP);
+        w.pairsum = (double*)cv.take(sizeof(double) * (size_t)(Do + 1 + p.Qt) * p.PP);
+        w.rowpart = (double*)cv.take(sizeof(double) * (size_t)p.rows_grid * (2 + Q));
+        w.rowsum = (double*)cv.take(sizeof(double) * (2 + Q));
+        w.colpart = (double*)cv.take(sizeof(double) * (size_t)p.cols_grid * ((size_t)Do * M + (size_t)M * Q));
+        w.colsum = (double*)cv.take(sizeof(double) * ((size_t)Do * M + (size_t)M * Q));
+        w.dZ2 = (double*)cv.take(sizeof(double) * (size_t)M * Q);
+        w.dlW = (double*)cv.take(sizeof(double) * (size_t)M * Q);
+    }
+    w.bytes = cv.off;
+    return w;
+}
+
+template <typename T, int Q, int DOC, bool BWD>
+void mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
+    auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD>;
+    prof_begin(BWD ? 4 : 3, stream);
+    GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+    prof_end(BWD ? 4 : 3, stream);
+}
+template <typename T, int Q, bool BWD>
+int mm_pairs_doc(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
+    switch (p.DOC) {
+        case 1: mm_pairs_launch<T, Q, 1, BWD>(p, a, stream); return GPB_OK;
+        case 2: mm_pairs_launch<T, Q, 2, BWD>(p, a, stream); return GPB_OK;
+        case 4: mm_pairs_launch<T, Q, 4, BWD>(p, a, stream); return GPB_OK;
+    }
+    return fail(GPB_ERR_ARG, "mm: bad DOC %d", p.DOC);
+}
+template <typename T, bool BWD>
+int mm_pairs_dispatch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
+    switch (p.Qt) {
+        case 1: return mm_pairs_doc<T, 1, BWD>(p, a, stream);
+        case 2: return mm_pairs_doc<T, 2, BWD>(p, a, stream);
+        case 3: return mm_pairs_doc<T, 3, BWD>(p, a, stream);
+        case 4: return mm_pairs_doc<T, 4, BWD>(p, a, stream);
+        case 5: return mm_pairs_doc<T, 5, BWD>(p, a, stream);
+        case 6: return mm_pairs_doc<T, 6, BWD>(p, a, stream);
+        case 8: return mm_pairs_doc<T, 8, BWD>(p, a, stream);
+        case 16: return mm_pairs_doc<T, 16, BWD>(p, a, stream);
+    }
+    return fail(GPB_ERR_ARG, "mm: input dim template %d unsupported", p.Qt);
+}
+
+template <typename T>
+int mm_check(int n, int M, int Q, int Do) {
+    if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
+    if (q_template(Q) < 0) return fail(GPB_ERR_ARG, "mm: Q=%d unsupported (max 16)", Q);
+    if (Do > 64) return fail(GPB_ERR_ARG, "mm: Do=%d unsupported (max 64)", Do);
+    return GPB_OK;
+}
+
+template <typename T>
+int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
+             const double* A, const double* B, int n, int M, int Q, int Do, double* mout,
+             double* vout, void* ws, size_t ws_bytes, void* stream) {
+    int rc = mm_check<T>(n, M, Q, Do);
+    if (rc) return rc;
+    MMPlan p = mm_plan(n, M, Q, Do);
+    MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 0, ws, ws_bytes);
+    if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_fwd: workspace %zu < %zu", ws_bytes, w.bytes);
+    auto tab = gpb::mm_pair_table_kernel<T>;
+    GPB_LAUNCH(tab, dim3(elementwise_grid(p.PP)), dim3(256), 0, stream, z, ls, sf, B, M, Q, p.Qt, Do,
+               p.P, p.PP, w.zh, w.ep, w.bs);
+    dev_memset(w.rowacc, sizeof(double) * (size_t)n * Do, stream);
+    gpb::MMArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.mx = mx; a.vx = vx; a.ls = ls; a.zh = w.zh; a.ep = w.ep; a.bs = w.bs; a.dv = nullptr;
+    a.n = n; a.Qa = Q; a.Do = Do; a.PP = p.PP; a.rows_per_split = p.rows_per_split;
+    a.rowacc = w.rowacc; a.pairpart = nullptr; a.full_coef = 0; a.lam_pass = 0;
+    for (int pass = 0; pass < p.npass; pass++) {
+        a.d0 = pass * p.DOC;
+        rc = mm_pairs_dispatch<T, false>(p, a, stream);
+        if (rc) return rc;
+    }
+    rc = GPB_CHECK_LAUNCH();
+    if (rc) return rc;
+    auto fin = gpb::mm_psi1_fwd_kernel<T>;
+    const int nt = 128;
+    size_t smem = sizeof(double) * Do * nt + sizeof(T) * ((size_t)M * Q + (size_t)Do * M + 2 * (size_t)Q * nt);
+    rc = allow_smem(fin, smem);
+    if (rc) return rc;
+    GPB_LAUNCH(fin, dim3(p.rows_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, w.rowacc, n, M, Q,
+               Do, mout, vout);
+    return GPB_CHECK_LAUNCH();
+}
+
+template <typename T>
+int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
+             const double* A, const double* B, const double* dm, const double* dv,
+             const double* mout, int n, int M, int Q, int Do, double* dA, double* dB, double* dzu,
+             double* dl, double* dsf2, double* dvsum, double* dmx, double* dvx, void* ws,
+             size_t ws_bytes, void* stream) {
+    int rc = mm_check<T>(n, M, Q, Do);
+    if (rc) return rc;
+    MMPlan p = mm_plan(n, M, Q, Do);
+    MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 1, ws, ws_bytes);
+    if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_bwd: workspace %zu < %zu", ws_bytes, w.bytes);
+    auto tab = gpb::mm_pair_table_kernel<T>;
+    GPB_LAUNCH(tab, dim3(elementwise_grid(p.PP)), dim3(256), 0, stream, z, ls, sf, B, M, Q, p.Qt, Do,
+               p.P, p.PP, w.zh, w.ep, w.bs);
+    const int NS = 1 + 2 * p.Qt;
+    dev_memset(w.rowacc, sizeof(double) * (size_t)n * NS, stream);
+    gpb::MMArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.mx = mx; a.vx = vx; a.ls = ls; a.zh = w.zh; a.ep = w.ep; a.bs = w.bs; a.dv = dv;
+    a.n = n; a.Qa = Q; a.Do = Do; a.PP = p.PP; a.rows_per_split = p.rows_per_split;
+    a.rowacc = w.rowacc; a.pairpart = w.pairpart;
+    a.full_coef = p.npass > 1 ? 1 : 0;
+    auto red = gpb::reduce_partials_kernel;
+    const long recstride = (long)(p.DOC + 1 + p.Qt) * p.PP;
+    for (int pass = 0; pass < p.npass; pass++) {
+        a.d0 = pass * p.DOC;
+        a.lam_pass = pass == 0 ? 1 : 0;
+        rc = mm_pairs_dispatch<T, true>(p, a, stream);
+        if (rc) return rc;
+        // fold the row splits: dBp rows of this d-chunk, and (first pass) S0 | S1
+        int nd = (Do - a.d0) < p.DOC ? (Do - a.d0) : p.DOC;
+        GPB_LAUNCH(red, dim3(elementwise_grid((long)nd * p.PP)), dim3(256), 0, stream, w.pairpart,
+                   p.nsplit, recstride, (long)nd * p.PP, w.pairsum + (long)a.d0 * p.PP, 0);
+        if (pass == 0)
+            GPB_LAUNCH(red, dim3(elementwise_grid((long)(1 + p.Qt) * p.PP)), dim3(256), 0, stream,
+                       w.pairpart + (long)p.DOC * p.PP, p.nsplit, recstride, (long)(1 + p.Qt) * p.PP,
+                       w.pairsum + (long)Do * p.PP, 0);
+    }
+    rc = GPB_CHECK_LAUNCH();
+    if (rc) return rc;
+    {   // row-wise epilogue: dmx, dvx + row-summed hyper terms
+        auto kern = gpb::mm_rows_bwd_kernel<T>;
+        const int nt = 128;
+        size_t smem = sizeof(double) * (16 + (size_t)(4 * Q + Do) * nt) + sizeof(T) * ((size_t)M * Q + (size_t)Do * M);
+        rc = allow_smem(kern, smem);
+        if (rc) return rc;
+        prof_begin(5, stream);
+        GPB_LAUNCH(kern, dim3(p.rows_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout,
+                   w.rowacc, n, M, Q, p.Qt, Do, dmx, dvx, w.rowpart);
+        prof_end(5, stream);
+        GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
+                   (long)(2 + Q), w.rowsum, 0);
+    }
+    {   // column-wise psi1 part: dA, dZ1
+        auto kern = gpb::mm_cols_bwd_kernel<T>;
+        const int nt = 128;
+        size_t smem = sizeof(double) * ((size_t)32 * (2 * Q + 1 + Do) + (size_t)(2 * Q + 2 * Do) * nt);
+        rc = allow_smem(kern, smem);
+        if (rc) return rc;
+        prof_begin(6, stream);
+        GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout, n,
+                   M, Q, Do, p.cols_rows_per_block, w.colpart);
+        prof_end(6, stream);
+        long len = (long)Do * M + (long)M * Q;
+        GPB_LAUNCH(red, dim3(elementwise_grid(len)), dim3(256), 0, stream, w.colpart, p.cols_grid, len,
+                   len, w.colsum, 0);
+    }
+    {
+        auto kern = gpb::mm_pair_finish_kernel;
+        GPB_LAUNCH(kern, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, w.pairsum, p.DOC,
+                   Do, z, ls, M, Q, p.PP, dB, w.dZ2, w.dlW);
+        auto fin = gpb::mm_final_kernel;
+        GPB_LAUNCH(fin, dim3(1), dim3(256), 0, stream, w.colsum, w.rowsum, w.dZ2, w.dlW, ls, M, Q, Do, dA,
+                   dzu, dl, dsf2, dvsum);
+    }
+    return GPB_CHECK_LAUNCH();
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward) {
+    if (q_template(Q) < 0 || n < 1 || M < 1 || Do < 1) return 0;
+    MMPlan p = mm_plan(n, M, Q, Do);
+    return mm_carve<double>(p, n, M, Q, Do, backward, nullptr, 0).bytes;  // fp64 sizing covers fp32
+}
+
+int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
+               const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
+               double* mout, double* vout, void* ws, size_t ws_bytes, void* stream) {
+    if (!mx || !vx || !z || !ls || !sf || !A || !B || !mout || !vout || !ws) return fail(GPB_ERR_ARG, "mm_fwd: null pointer");
+    if (prec == GPB_F64) return mm_fwd_t<double>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, ws, ws_bytes, stream);
+    return mm_fwd_t<float>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, ws, ws_bytes, stream);
+}
+
+int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
+               const double* sf, const double* A, const double* B, const double* dm, const double* dv,
+               const double* mout, int n, int M, int Q, int Do, double* dA, double* dB, double* dzu,
+               double* dl, double* dsf2, double* dvsum, double* dmx, double* dvx, void* ws,
+               size_t ws_bytes, void* stream) {
+    if (!mx || !vx || !z || !ls || !sf || !A || !B || !dm || !dv || !mout || !dA || !dB || !dzu || !dl ||
+        !dsf2 || !dvsum || !dmx || !dvx || !ws)
+        return fail(GPB_ERR_ARG, "mm_bwd: null pointer");
+    if (prec == GPB_F64)
+        return mm_bwd_t<double>(mx, vx, z, ls, sf, A, B, dm, dv, mout, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+    return mm_bwd_t<float>(mx, vx, z, ls, sf, A, B, dm, dv, mout, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

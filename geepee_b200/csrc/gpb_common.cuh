@@ -1,0 +1,146 @@
+// gpb_common.cuh -- shared host-side helpers of the C-ABI translation units
+// (gpb_capi_misc.cu, gpb_capi_det.cu, gpb_capi_mm.cu; see include/geepee_b200.h).
+//
+// Host-side launch logic only: tile-shape dispatch, grid sizing in multiples of the SM
+// count, workspace carving, deterministic two-stage reductions.  No allocation, no
+// synchronisation, no torch types.  The same file is compiled with -DGPB_CPU_EMU by
+// tests/emu/build.py, where GPB_LAUNCH runs the kernels on the fiber emulator.
+#pragma once
+#include "../../include/geepee_b200.h"
+#include "gpb_kernels.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+// shared state lives in gpb_capi_misc.cu
+extern char g_gpb_err[512];
+extern long g_gpb_launches;
+extern int g_gpb_prof_on;
+#define g_err g_gpb_err
+#define g_launches g_gpb_launches
+#define g_prof_on g_gpb_prof_on
+
+namespace {
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#ifdef GPB_CPU_EMU
+}  // namespace
+namespace gpb_emu {
+void launch_begin(dim3 grid, dim3 block, size_t smem);
+bool launch_next_block();
+void run_block(void (*tramp)(void*), void* ctx);
+}  // namespace gpb_emu
+namespace {
+template <typename F>
+void emu_tramp(void* p) { (*(F*)p)(); }
+template <typename F>
+void emu_launch(dim3 grid, dim3 block, size_t smem, F f) {
+    gpb_emu::launch_begin(grid, block, smem);
+    while (gpb_emu::launch_next_block()) gpb_emu::run_block(&emu_tramp<F>, (void*)&f);
+}
+#define GPB_LAUNCH(kern, grid, block, smem, stream, ...)                          \
+    do {                                                                          \
+        (void)(stream);                                                           \
+        g_launches++;                                                             \
+        emu_launch(grid, block, smem, [&]() { kern(__VA_ARGS__); });              \
+    } while (0)
+#define GPB_CHECK_LAUNCH() GPB_OK
+inline int sm_count() { return 2; }
+inline void dev_memset(void* p, size_t bytes, void*) { memset(p, 0, bytes); }
+template <typename K>
+inline int allow_smem(K, size_t) { return GPB_OK; }
+#else
+#define GPB_LAUNCH(kern, grid, block, smem, stream, ...)                          \
+    do {                                                                          \
+        g_launches++;                                                             \
+        kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__);         \
+    } while (0)
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GPB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return GPB_OK;
+}
+#define GPB_CHECK_LAUNCH() check_launch(__func__)
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+inline void dev_memset(void* p, size_t bytes, void* stream) {
+    cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
+}
+template <typename K>
+int allow_smem(K kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return GPB_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(GPB_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
+    return GPB_OK;
+}
+#endif
+
+// ---- optional per-kernel device timing (CUDA events on the launching stream) -------------
+// slots: 0 det_fwd, 1 det_bwd, 2 det_syrk, 3 mm_pairs fwd, 4 mm_pairs bwd, 5 mm_rows_bwd,
+//        6 mm_cols_bwd, 7 unused
+#ifdef GPB_CPU_EMU
+inline void prof_begin(int, void*) {}
+inline void prof_end(int, void*) {}
+#else
+}  // namespace
+struct GpbProfPair { cudaEvent_t a, b; int slot; };
+extern GpbProfPair g_gpb_prof_pending[4096];
+extern int g_gpb_prof_n;
+namespace {
+#define g_prof_pending g_gpb_prof_pending
+#define g_prof_n g_gpb_prof_n
+typedef GpbProfPair ProfPair;
+inline void prof_begin(int slot, void* stream) {
+    if (!g_prof_on || g_prof_n >= 4096) return;
+    ProfPair& p = g_prof_pending[g_prof_n];
+    p.slot = slot;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, (cudaStream_t)stream);
+}
+inline void prof_end(int slot, void* stream) {
+    if (!g_prof_on || g_prof_n >= 4096) return;
+    (void)slot;
+    cudaEventRecord(g_prof_pending[g_prof_n].b, (cudaStream_t)stream);
+    g_prof_n++;
+}
+#endif
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+
+struct Carver {  // bump allocator over the caller's workspace
+    char* base;
+    size_t off, cap;
+    Carver(void* p, size_t c) : base((char*)p), off(0), cap(c) {}
+    void* take(size_t bytes) {
+        void* r = base ? base + off : nullptr;
+        off += align256(bytes);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+inline int elementwise_grid(long total) {
+    long b = cdiv(total, 256);
+    long cap = (long)sm_count() * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace

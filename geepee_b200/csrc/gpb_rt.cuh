@@ -14,7 +14,7 @@
 #include <stdint.h>
 
 #define GPB_DEVICE __device__ __forceinline__
-#define GPB_KERNEL __global__
+#define GPB_KERNEL static __global__
 #define GPB_SHARED __shared__
 #define GPB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define GPB_LAUNCH_BOUNDS(n) __launch_bounds__(n)

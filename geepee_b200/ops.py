@@ -204,3 +204,19 @@ def fma_peak(prec, iters, device):
     flops = ctypes.c_double(0.0)
     _chk(lib.gpb_fma_peak(prec, int(iters), _p(sink), ctypes.byref(flops), _stream(sink)), 'fma_peak')
     return flops.value
+
+
+PROFILE_SLOTS = ('det_fwd', 'det_bwd', 'det_syrk', 'mm_pairs_fwd', 'mm_pairs_bwd', 'mm_rows_bwd',
+                 'mm_cols_bwd', 'unused')
+
+
+def profile_enable(on):
+    _lib.get().gpb_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """-> {slot name: (total ms, launches)} since the last collect (synchronises the events)."""
+    ms = (ctypes.c_double * 8)()
+    cnt = (ctypes.c_long * 8)()
+    _lib.get().gpb_profile_collect(ms, cnt)
+    return {PROFILE_SLOTS[i]: (ms[i], cnt[i]) for i in range(8)}

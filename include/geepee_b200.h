@@ -114,6 +114,13 @@ int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, co
                double* dA, double* dB, double* dzu, double* dl, double* dsf2, double* dvsum,
                double* dmx, double* dvx, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- per-kernel device timing for bench.py's roofline (CUDA events on the launching stream).
+ *      slots: 0 det_fwd, 1 det_bwd, 2 det_syrk, 3 mm_pairs(fwd), 4 mm_pairs(bwd), 5 mm_rows_bwd,
+ *      6 mm_cols_bwd, 7 unused.  collect() synchronises the recorded events, returns the summed
+ *      milliseconds and launch counts per slot into HOST arrays of 8 and resets them. */
+int gpb_profile_enable(int on);
+int gpb_profile_collect(double* h_ms, long* h_count);
+
 /* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------- */
 /* runs `iters` dependent-chain-free FMAs per thread on a full grid; returns total flops in
  * *h_flops (host pointer).  `sink` is a device buffer of >= 8*gpb_sm_count() doubles.

@@ -12,16 +12,23 @@ OUT = os.path.join(HERE, '_build', 'libgeepee_b200_emu.so')
 
 
 def build(force=False):
-    srcs = [os.path.join(CSRC, 'gpb_capi.cu'), os.path.join(HERE, 'gpb_emu.cpp')]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith('.cu')] + \
+        [os.path.join(HERE, 'gpb_emu.cpp')]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.cu'))] + \
         [os.path.join(ROOT, 'include', 'geepee_b200.h')]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-DGPB_CPU_EMU', '-Wall',
-           '-Wno-unused-function', '-Wno-unknown-pragmas', '-Wno-unused-variable',
-           '-x', 'c++', srcs[0], srcs[1], '-o', OUT, '-lm']
-    subprocess.check_call(cmd)
+    flags = ['-std=c++17', '-O1', '-g', '-fPIC', '-DGPB_CPU_EMU', '-Wall', '-Wno-unused-function',
+             '-Wno-unknown-pragmas', '-Wno-unused-variable', '-x', 'c++']
+    objs, procs = [], []
+    for src in srcs:
+        obj = os.path.join(os.path.dirname(OUT), os.path.basename(src) + '.o')
+        objs.append(obj)
+        procs.append(subprocess.Popen(['g++'] + flags + ['-c', src, '-o', obj]))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError('emulator build failed')
+    subprocess.check_call(['g++', '-shared', '-o', OUT] + objs + ['-lm'])
     return OUT
 
 
