@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', 'nvcc')
     objdir = os.path.join(CSRC, 'build')
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != '-shared'] + (['-Xptxas', '-v'] if verbose else [])
+    flags = [f for f in NVCC_FLAGS if f != '-shared'] + (['-Xptxas', '-v'] if verbose else []) + \
+        os.environ.get('GPB_EXTRA_NVCC_FLAGS', '').split()
     procs = []
     objs = []
     for src in sources():

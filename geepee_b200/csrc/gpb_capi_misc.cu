@@ -94,7 +94,9 @@ int gpb_profile_collect(double* h_ms, long* h_count) {
 
 int gpb_fma_peak(int prec, long iters, double* sink, double* h_flops, void* stream) {
     if (!sink || iters < 1) return fail(GPB_ERR_ARG, "fma_peak: bad argument");
+    // sink[0] > 0 on entry selects blocks per SM (occupancy experiments); default 8
     int blocks = sm_count() * 8;
+    if (h_flops && *h_flops >= 1.0 && *h_flops <= 32.0) blocks = sm_count() * (int)(*h_flops);
     if (prec == GPB_F64) {
         auto kern = gpb::fma_peak_kernel<double>;
         GPB_LAUNCH(kern, dim3(blocks), dim3(256), 0, stream, iters, sink);

@@ -17,11 +17,8 @@ int q_template(int Q) {
     if (Q <= 16) return 16;
     return -1;
 }
-int mm_rp(int Qt, int DOC) {
-    int s = 2 * Qt + 2 * DOC + 2;
-    return s <= 12 ? 4 : (s <= 26 ? 2 : 1);
-}
-int mm_rb(int Qt) { return Qt <= 2 ? 8 : (Qt <= 4 ? 4 : (Qt <= 8 ? 2 : 1)); }
+int mm_rp(int Qt, int DOC) { return gpb::MMCfg<1, 1>::RP == 2 ? ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1)
+                                                            : ((2 * Qt + 2 * DOC + 2) <= 12 ? 4 : ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1)); }
 
 MMPlan mm_plan(int n, int M, int Q, int Do) {
     MMPlan p;
@@ -33,12 +30,16 @@ MMPlan mm_plan(int n, int M, int Q, int Do) {
     p.P = (long)M * (M + 1) / 2;
     p.PP = cdiv(p.P, 1024) * 1024;
     p.nchunks = (int)(p.PP / p.PC);
-    int want = (int)cdiv(2L * sm_count(), p.nchunks);
-    if (want < 1) want = 1;
-    int rb = mm_rb(p.Qt);
-    long rps = cdiv(n, want);
-    rps = cdiv(rps, rb) * rb;
-    if (rps < rb) rps = rb;
+    // row splits: as many blocks as fit an integer number of waves (1 block/SM), 8 waves when the
+    // problem is large enough, never less than 4 row tiles per block
+    const int TR = 32;
+    int best = 1;
+    for (int waves = 8; waves >= 1; waves--) {
+        int ns = (int)((long)waves * sm_count() / p.nchunks);
+        if (ns >= 1 && cdiv(n, ns) >= 4 * TR) { best = ns; break; }
+    }
+    long rps = cdiv(n, best);
+    rps = cdiv(rps, TR) * TR;
     p.rows_per_split = (int)rps;
     p.nsplit = (int)cdiv(n, rps);
     p.rows_grid = (int)cdiv(n, 128);
@@ -85,9 +86,19 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
 
 template <typename T, int Q, int DOC, bool BWD>
 void mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
-    auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD>;
     prof_begin(BWD ? 4 : 3, stream);
-    GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+    if constexpr (BWD && DOC == 4) {
+        if (p.npass > 1) {   // Do > 4: generic multi-pass kernel
+            auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, true>;
+            GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+            prof_end(4, stream);
+            return;
+        }
+    }
+    {
+        auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, false>;
+        GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+    }
     prof_end(BWD ? 4 : 3, stream);
 }
 template <typename T, int Q, bool BWD>

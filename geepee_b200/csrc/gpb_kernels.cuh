@@ -587,7 +587,7 @@ GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nspl
 // =========================================================================
 // Pair table (n-independent): for every unordered pair p=(a>=b)
 //   zh[q][p]  = (z_a + z_b)/2
-//   ep[p]     = sf2^2 * exp(-sum_q (z_a-z_b)^2 / (4 l_q^2))        (kernels.py:222-226)
+//   ep[p]     = log( sf2^2 * exp(-sum_q (z_a-z_b)^2 / (4 l_q^2)) )  (kernels.py:222-226, log domain)
 //   bs[d][p]  = B[d,a,b] + B[d,b,a]  (a != b)   |   B[d,a,a]
 template <typename T>
 GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double* __restrict__ ls,
@@ -598,9 +598,9 @@ GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double*
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < PP;
          p += (long)gridDim.x * blockDim.x) {
         for (int q = Q; q < Qt; q++) zh[(long)q * PP + p] = 0;  // template-padded input dims
-        if (p >= P) {  // padding: contributes nothing
+        if (p >= P) {  // padding: exp(lep) underflows to ~1e-308 and every bs is 0
             for (int q = 0; q < Q; q++) zh[(long)q * PP + p] = 0;
-            ep[p] = 0;
+            ep[p] = (T)(-1.0e5);
             for (int d = 0; d < Do; d++) bs[(long)d * PP + p] = 0;
             continue;
         }
@@ -615,7 +615,7 @@ GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double*
             double dz = za - zb;
             e += dz * dz / (4.0 * exp(2.0 * ls[q]));
         }
-        ep[p] = (T)(sf2 * sf2 * exp(-e));
+        ep[p] = (T)(4.0 * sf[0] - e);   // log(sf2^2) - sum_q dz^2/(4 l^2)
         for (int d = 0; d < Do; d++) {
             const double* Bd = B + (long)d * M * M;
             bs[(long)d * PP + p] = (T)(a == b ? Bd[a * M + a] : Bd[a * M + b] + Bd[b * M + a]);
@@ -625,9 +625,13 @@ GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double*
 
 template <int Q, int DOC>
 struct MMCfg {
-    // pairs per thread / rows per register block, sized to keep the per-thread state in registers
+    // pairs per thread, sized to keep the per-thread pair state in registers
+#ifdef GPB_MM_EXPERIMENT_RP2
+    static constexpr int RP = (2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1;
+#else
     static constexpr int RP = (2 * Q + 2 * DOC + 2) <= 12 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
-    static constexpr int RB = Q <= 2 ? 8 : (Q <= 4 ? 4 : (Q <= 8 ? 2 : 1));
+#endif
+    static constexpr int TR = 32;             // rows per staged tile = lanes per warp
     static constexpr int PC = kThreads * RP;  // pairs per block
 };
 
@@ -649,9 +653,93 @@ struct MMArgs {
     int lam_pass;      // bwd: 1 -> this pass also produces the Lambda-dependent sums
 };
 
+// exp(x) for x <= 0 without the special-case branches of libm: 2^k * P(r), k = rint(x log2 e),
+// |r| <= ln2/2, degree-11 Taylor polynomial in Estrin form (dependency depth 5 instead of 12;
+// relative error < 1e-14).  The 2^k scaling is an integer add into the exponent field; k is
+// clamped at -1021 so that deep underflow returns ~1e-308 * P instead of garbage.
+// fp32: the SFU path (ex2.approx).
+#ifndef GPB_CPU_EMU
+__constant__ double c_exp_coef[12] = {
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.333333333333333e-03,
+    1.388888888888889e-03, 1.984126984126984e-04, 2.48015873015873e-05, 2.7557319223985893e-06,
+    2.755731922398589e-07, 2.505210838544172e-08};
+#else
+static const double c_exp_coef[12] = {
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.333333333333333e-03,
+    1.388888888888889e-03, 1.984126984126984e-04, 2.48015873015873e-05, 2.7557319223985893e-06,
+    2.755731922398589e-07, 2.505210838544172e-08};
+#endif
+GPB_DEVICE double exp_neg(double x) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    double kd = x * 1.4426950408889634 + magic;
+#ifndef GPB_CPU_EMU
+    int k = __double2loint(kd);
+#else
+    int64_t bits;
+    memcpy(&bits, &kd, 8);
+    int k = (int)(int32_t)(bits & 0xffffffff);
+#endif
+    kd -= magic;
+    double r = kd * -6.93147180369123816490e-01 + x;
+    r = kd * -1.90821492927058770002e-10 + r;
+    const double r2 = r * r;
+    const double p01 = c_exp_coef[1] * r + c_exp_coef[0];
+    const double p23 = c_exp_coef[3] * r + c_exp_coef[2];
+    const double p45 = c_exp_coef[5] * r + c_exp_coef[4];
+    const double p67 = c_exp_coef[7] * r + c_exp_coef[6];
+    const double p89 = c_exp_coef[9] * r + c_exp_coef[8];
+    const double pab = c_exp_coef[11] * r + c_exp_coef[10];
+    const double r4 = r2 * r2;
+    const double q0 = p23 * r2 + p01;
+    const double q1 = p67 * r2 + p45;
+    const double q2 = pab * r2 + p89;
+    const double r8 = r4 * r4;
+    double p = q1 * r4 + q0;
+    p = q2 * r8 + p;
+    k = k < -1021 ? -1021 : k;
+#ifndef GPB_CPU_EMU
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    return ldexp(p, k);
+#endif
+}
+GPB_DEVICE float exp_neg(float x) { return fast_exp(x); }
+
+// Running warp-transpose reduction.  Row r (0..31) of a tile contributes NS per-lane partial sums;
+// after the 32nd push lane L holds the NS sums of row L added over all 32 lanes.  Pending partial
+// sets are merged like a binary counter (level k pairs blocks of 2^k rows with one xor-shuffle),
+// so a tile costs 31*NS shuffles instead of 160*NS and only 5 named register sets are live.
+template <typename T, int NS>
+struct RowCascade {
+    T l0[NS], l1[NS], l2[NS], l3[NS], l4[NS];
+    GPB_MEMBER static void merge(const T (&early)[NS], const T (&late)[NS], int bit, int lane, T (&out)[NS]) {
+        const bool up = (lane & bit) != 0;   // lanes with the bit set keep the later rows
+        GPB_UNROLL
+        for (int s = 0; s < NS; s++) {
+            T keep = up ? late[s] : early[s];
+            T send = up ? early[s] : late[s];
+            out[s] = keep + shfl_xor(send, bit);
+        }
+    }
+    // returns true when `v` holds the finished sums of rows (r-31 .. r), i.e. after r == 31
+    GPB_MEMBER bool push(int r, int lane, T (&v)[NS]) {
+        if ((r & 1) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l0[s] = v[s]; return false; }
+        merge(l0, v, 1, lane, v);
+        if ((r & 2) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l1[s] = v[s]; return false; }
+        merge(l1, v, 2, lane, v);
+        if ((r & 4) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l2[s] = v[s]; return false; }
+        merge(l2, v, 4, lane, v);
+        if ((r & 8) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l3[s] = v[s]; return false; }
+        merge(l3, v, 8, lane, v);
+        if ((r & 16) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l4[s] = v[s]; return false; }
+        merge(l4, v, 16, lane, v);
+        return true;
+    }
+};
+
 // a2+a6 (forward) / a2+a9 (backward) over unordered pairs.  Each thread owns RP pairs for
 // the whole kernel (their constants and accumulators live in registers); rows are staged
-// RB at a time in shared memory and broadcast.  psi2[n,p] = cn[n] * ep[p] *
+// 32 at a time in shared memory and broadcast.  psi2[n,p] = cn[n] * ep[p] *
 // exp(-sum_q (mu_nq - zh_pq)^2 c2_nq) is formed in registers and consumed immediately:
 // the N x M x M tensor never exists in memory.
 //   forward : rowacc[n,d]  += sum_p bs[d,p] psi2[n,p]                   (aep_models.py:196-198)
@@ -659,28 +747,45 @@ struct MMArgs {
 //             rowacc[n,:]  += {sum_p Lam, sum_p Lam zh_q, sum_p Lam zh_q^2}
 //             pair sums     : dBp[d,p] = sum_n dv[n,d] psi2[n,p]         (aep_models.py:240)
 //                             S0[p] = sum_n Lam ; S1[p,q] = sum_n Lam c2_nq (mu_nq - zh_pq)
-template <typename T, int Q, int DOC, bool BWD>
+// The per-row sums are reduced over the warp by RowCascade, over the 8 warps through shared
+// memory, and over the pair chunks (blocks) by one fp64 atomic per value.
+// GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
+// GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
+template <typename T, int Q, int DOC, bool BWD, bool GEN>
+#ifdef GPB_MM_EXPERIMENT_RP2
+GPB_KERNEL void __launch_bounds__(256, 2) mm_pairs_kernel(MMArgs<T> a) {
+#else
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
+#endif
     typedef MMCfg<Q, DOC> C;
-    constexpr int RP = C::RP, RB = C::RB;
+    constexpr int RP = C::RP, TR = C::TR;
     constexpr int NS = BWD ? (1 + 2 * Q) : DOC;
-    GPB_SHARED T s_mu[RB * Q], s_c2[RB * Q], s_cn[RB];
-    GPB_SHARED double s_dv[RB * DOC];
-    GPB_SHARED double s_dvall[BWD ? RB * 64 : 1];  // generic path: all Do (<= 64) per row
-    GPB_SHARED double s_red[8 * RB * NS];
+    constexpr bool kGen = BWD && GEN;
+    // Row tiles are double buffered (tile t+1 is staged while tile t is consumed) and so is the
+    // cross-warp staging of the row sums, which leaves ONE barrier per tile.  For wide inputs the
+    // staging would not fit the static 48 KB; then every warp issues its own atomics.
+    constexpr bool WARP_ATOMICS = (2 * 8 * TR * NS * sizeof(T) + 4 * TR * Q * sizeof(T) + (kGen ? TR * 64 * 8 : 0)) > 40 * 1024;
+    GPB_SHARED T s_mu[2][TR * Q], s_c2[2][TR * Q], s_lcn[2][TR];
+    GPB_SHARED T s_dv[2][TR * DOC];
+    GPB_SHARED double s_dvall[kGen ? TR * 64 : 1];  // generic path (single buffered): all Do (<= 64) per row
+    GPB_SHARED T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
+    GPB_SHARED double s_l2[Q];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long pbase = (long)blockIdx.x * C::PC;
     const long PP = a.PP;
     const int Do = a.Do;
 
-    T zh[RP][Q], ep[RP], bs[RP][DOC];
+    T zh[RP][Q], zh2[RP][Q], lep[RP], bs[RP][DOC];
     T accB[RP][DOC], accS0[RP], accS1[RP][Q];
     GPB_UNROLL
     for (int j = 0; j < RP; j++) {
         const long p = pbase + j * kThreads + tid;
         GPB_UNROLL
-        for (int q = 0; q < Q; q++) zh[j][q] = a.zh[(long)q * PP + p];
-        ep[j] = a.ep[p];
+        for (int q = 0; q < Q; q++) {
+            zh[j][q] = a.zh[(long)q * PP + p];
+            zh2[j][q] = zh[j][q] * zh[j][q];
+        }
+        lep[j] = a.ep[p];
         GPB_UNROLL
         for (int d = 0; d < DOC; d++) {
             bs[j][d] = (a.d0 + d < Do) ? a.bs[(long)(a.d0 + d) * PP + p] : (T)0;
@@ -690,73 +795,92 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         GPB_UNROLL
         for (int q = 0; q < Q; q++) accS1[j][q] = 0;
     }
+    if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
-    for (int t0 = r_begin; t0 < r_end; t0 += RB) {
-        const int tv = (r_end - t0) < RB ? (r_end - t0) : RB;
-        sync_threads();
-        // stage RB rows: c2 = 1/(2S + l^2), cn = prod_q sqrt(l^2 c2)   (kernels.py:188-190)
-        if (tid < RB) {
-            double cn = 1.0;
+
+    // stage one tile: 4 lanes of every warp take one row each (spreads the fp64 div/sqrt/log
+    // evenly over the warps).  c2 = 1/(2S + l^2); lcn = sum_q log sqrt(l^2 c2)  (kernels.py:188-190)
+    auto stage = [&](int buf, int t0) {
+        if (lane < 4) {
+            const int row = warp * 4 + lane;
+            const bool ok = (t0 + row) < r_end;
+            double lcn = 0.0;
             for (int q = 0; q < Q; q++) {
                 double mu = 0, c2 = 0;
-                if (tid < tv && q < a.Qa) {
-                    mu = a.mx[(long)(t0 + tid) * a.Qa + q];
-                    double lq = exp(2.0 * a.ls[q]);
-                    c2 = 1.0 / (2.0 * a.vx[(long)(t0 + tid) * a.Qa + q] + lq);
-                    cn *= sqrt(lq * c2);
+                if (ok && q < a.Qa) {
+                    mu = a.mx[(long)(t0 + row) * a.Qa + q];
+                    const double lq = s_l2[q];
+                    c2 = 1.0 / (2.0 * a.vx[(long)(t0 + row) * a.Qa + q] + lq);
+                    lcn += 0.5 * log(lq * c2);
                 }
-                s_mu[tid * Q + q] = (T)mu;
-                s_c2[tid * Q + q] = (T)c2;
+                s_mu[buf][row * Q + q] = (T)mu;
+                s_c2[buf][row * Q + q] = (T)c2;
             }
-            s_cn[tid] = tid < tv ? (T)cn : (T)0;
+            // rows past the end: psi2 = exp(-1e5 + ...) ~ 1e-308 and their dv is 0
+            s_lcn[buf][row] = ok ? (T)lcn : (T)(-1.0e5);
             if (BWD) {
                 for (int d = 0; d < DOC; d++)
-                    s_dv[tid * DOC + d] =
-                        (tid < tv && a.d0 + d < Do) ? a.dv[(long)(t0 + tid) * Do + a.d0 + d] : 0.0;
-                if (a.full_coef)
+                    s_dv[buf][row * DOC + d] =
+                        (ok && a.d0 + d < Do) ? (T)a.dv[(long)(t0 + row) * Do + a.d0 + d] : (T)0;
+                if (kGen && a.full_coef)
                     for (int d = 0; d < Do; d++)
-                        s_dvall[tid * 64 + d] = tid < tv ? a.dv[(long)(t0 + tid) * Do + d] : 0.0;
+                        s_dvall[row * 64 + d] = ok ? a.dv[(long)(t0 + row) * Do + d] : 0.0;
             }
         }
-        sync_threads();
-        double rs[RB][NS];
-        GPB_UNROLL
-        for (int r = 0; r < RB; r++)
-            GPB_UNROLL
-            for (int s = 0; s < NS; s++) rs[r][s] = 0;
-        GPB_UNROLL
-        for (int r = 0; r < RB; r++) {
-            T mu[Q], c2[Q];
+    };
+
+    sync_threads();                 // s_l2 visible
+    if (!kGen && r_begin < r_end) stage(0, r_begin);
+    sync_threads();
+    int buf = 0;
+    for (int t0 = r_begin; t0 < r_end; t0 += TR, buf ^= 1) {
+        const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+        if (kGen) {                 // generic path: s_dvall is single buffered -> stage in place
+            sync_threads();
+            stage(buf, t0);
+            sync_threads();
+        } else if (t0 + TR < r_end) {
+            stage(buf ^ 1, t0 + TR);
+        }
+        RowCascade<T, NS> casc;
+        T fin[NS];
+        GPB_UNROLL_N(1)
+        for (int r = 0; r < TR; r++) {
+            T mu[Q], c2[Q], v[NS];
             GPB_UNROLL
             for (int q = 0; q < Q; q++) {
-                mu[q] = s_mu[r * Q + q];
-                c2[q] = s_c2[r * Q + q];
+                mu[q] = s_mu[buf][r * Q + q];
+                c2[q] = s_c2[buf][r * Q + q];
             }
-            const T cn = s_cn[r];
+            GPB_UNROLL
+            for (int s = 0; s < NS; s++) v[s] = 0;
+            const T lcn = s_lcn[buf][r];
             GPB_UNROLL
             for (int j = 0; j < RP; j++) {
-                T e = 0, t[Q];
+                // x = lep + lcn - sum_q c2 (mu - zh)^2  (log-domain psi2, as kernels.py:222-227)
+                T x = lep[j] + lcn, t[Q];
                 GPB_UNROLL
                 for (int q = 0; q < Q; q++) {
                     T diff = mu[q] - zh[j][q];
                     t[q] = diff * c2[q];
-                    e += t[q] * diff;
+                    x -= t[q] * diff;
                 }
-                const T psi2 = cn * ep[j] * fast_exp(-e);
+                const T psi2 = exp_neg(x);
                 if (!BWD) {
                     GPB_UNROLL
-                    for (int d = 0; d < DOC; d++) rs[r][d] += (double)(bs[j][d] * psi2);
+                    for (int d = 0; d < DOC; d++) v[d] += bs[j][d] * psi2;
                 } else {
                     T coef = 0;
                     GPB_UNROLL
                     for (int d = 0; d < DOC; d++) {
-                        T dvd = (T)s_dv[r * DOC + d];
+                        const T dvd = s_dv[buf][r * DOC + d];
                         accB[j][d] += dvd * psi2;
                         coef += dvd * bs[j][d];
                     }
-                    if (a.lam_pass) {
-                        if (a.full_coef) {
+                    if (!GEN || a.lam_pass) {
+                        if (kGen && a.full_coef) {
                             const long p = pbase + j * kThreads + tid;
                             coef = 0;
                             for (int d = 0; d < Do; d++)
@@ -764,37 +888,51 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                         }
                         const T lam = coef * psi2;
                         accS0[j] += lam;
-                        rs[r][0] += (double)lam;
+                        v[0] += lam;
                         GPB_UNROLL
                         for (int q = 0; q < Q; q++) {
                             accS1[j][q] += lam * t[q];
-                            T lz = lam * zh[j][q];
-                            rs[r][1 + q] += (double)lz;
-                            rs[r][1 + Q + q] += (double)(lz * zh[j][q]);
+                            v[1 + q] += lam * zh[j][q];
+                            v[1 + Q + q] += lam * zh2[j][q];
                         }
                     }
                 }
             }
+            if (casc.push(r, lane, v)) {
+                GPB_UNROLL
+                for (int s = 0; s < NS; s++) fin[s] = v[s];
+            }
         }
-        // block reduction of the RB x NS row sums, then one atomic per value
-        GPB_UNROLL
-        for (int r = 0; r < RB; r++)
+        // lane L now holds row L's sums over this warp's pairs: add the 8 warps, then one atomic
+        const bool emit = !BWD || !GEN || a.lam_pass;
+        if (WARP_ATOMICS) {
+            if (emit && lane < tv) {
+                GPB_UNROLL
+                for (int s = 0; s < NS; s++) {
+                    if (BWD)
+                        atomic_add(a.rowacc + (long)(t0 + lane) * NS + s, (double)fin[s]);
+                    else if (a.d0 + s < Do)
+                        atomic_add(a.rowacc + (long)(t0 + lane) * Do + a.d0 + s, (double)fin[s]);
+                }
+            }
+            sync_threads();         // next tile staged; this tile's buffers free
+        } else {
+            T* red = s_red[buf];
             GPB_UNROLL
-            for (int s = 0; s < NS; s++) {
-                double v = warp_sum(rs[r][s]);
-                if (lane == 0) s_red[(warp * RB + r) * NS + s] = v;
-            }
-        sync_threads();
-        if (tid < RB * NS) {
-            const int r = tid / NS, s = tid - r * NS;
-            if (r < tv && (!BWD || a.lam_pass)) {
-                double v = 0;
-                for (int w = 0; w < 8; w++) v += s_red[(w * RB + r) * NS + s];
-                if (BWD)
-                    atomic_add(a.rowacc + (long)(t0 + r) * NS + s, v);
-                else if (a.d0 + s < Do)
-                    atomic_add(a.rowacc + (long)(t0 + r) * Do + a.d0 + s, v);
-            }
+            for (int s = 0; s < NS; s++) red[(warp * TR + lane) * NS + s] = fin[s];
+            sync_threads();         // the only barrier per tile (also publishes the staged next tile)
+            if (emit)
+                for (int i = tid; i < TR * NS; i += kThreads) {
+                    const int r = i / NS, s = i - r * NS;
+                    if (r < tv) {
+                        double acc = 0;
+                        for (int w = 0; w < 8; w++) acc += (double)red[(w * TR + r) * NS + s];
+                        if (BWD)
+                            atomic_add(a.rowacc + (long)(t0 + r) * NS + s, acc);
+                        else if (a.d0 + s < Do)
+                            atomic_add(a.rowacc + (long)(t0 + r) * Do + a.d0 + s, acc);
+                    }
+                }
         }
     }
     if (BWD) {

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #define GPB_DEVICE __device__ __forceinline__
+#define GPB_MEMBER __device__ __forceinline__
 #define GPB_KERNEL static __global__
 #define GPB_SHARED __shared__
 #define GPB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -53,6 +54,7 @@ GPB_DEVICE float ldg(const float* p) { return __ldg(p); }
 #include <string.h>
 
 #define GPB_DEVICE static inline
+#define GPB_MEMBER inline
 #define GPB_KERNEL static
 #define GPB_SHARED static
 #define GPB_DYN_SMEM(name) unsigned char* name = gpb_emu::dyn_smem

@@ -197,11 +197,12 @@ def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout):
     return out
 
 
-def fma_peak(prec, iters, device):
-    """Launch the FMA microbenchmark; returns the flop count (time it with CUDA events)."""
+def fma_peak(prec, iters, device, blocks_per_sm=0):
+    """Launch the FMA microbenchmark; returns the flop count (time it with CUDA events).
+    blocks_per_sm (1..32) overrides the default of 8 resident 256-thread blocks per SM."""
     lib = _lib.get()
-    sink = torch.zeros(8 * lib.gpb_sm_count(), dtype=torch.float64, device=device)
-    flops = ctypes.c_double(0.0)
+    sink = torch.zeros(32 * lib.gpb_sm_count(), dtype=torch.float64, device=device)
+    flops = ctypes.c_double(float(blocks_per_sm))
     _chk(lib.gpb_fma_peak(prec, int(iters), _p(sink), ctypes.byref(flops), _stream(sink)), 'fma_peak')
     return flops.value
 
