@@ -17,7 +17,7 @@ DetBwdPlan det_bwd_plan(int n, int M, int D, int Do) {
     int want = 2 * sm_count() / p.gy;
     if (want < 1) want = 1;
     int rpb = (int)cdiv(n, want);
-    if (rpb < 32) rpb = 32;
+    if (rpb < 64) rpb = 64;
     p.rows_per_block = rpb;
     p.gx = (int)cdiv(n, rpb);
     p.G = p.gx * p.RY;
@@ -33,9 +33,13 @@ SyrkPlan syrk_plan(int n, int M, int Do) {
     p.MP = gpb_det_pad_m(M);
     p.nb = p.MP / 128;
     p.nbu = p.nb * (p.nb + 1) / 2;
-    int want = (int)cdiv(2L * sm_count(), (long)p.nbu * Do);
-    if (want < 1) want = 1;
-    int rps = (int)cdiv(n, want);
+    // row splits: an integer number of waves (1 block/SM), up to 6, at least 256 rows per block
+    int best = 1;
+    for (int waves = 6; waves >= 1; waves--) {
+        int ns = (int)((long)waves * sm_count() / ((long)p.nbu * Do));
+        if (ns >= 1 && cdiv(n, ns) >= 256) { best = ns; break; }
+    }
+    int rps = (int)cdiv(n, best);
     rps = (int)(cdiv(rps, 16) * 16);
     if (rps < 16) rps = 16;
     p.rows_per_split = rps;
@@ -87,17 +91,25 @@ int det_bwd_t(const double* x, const double* z, const double* ls, const double* 
     double* rec = (double*)cv.take(sizeof(double) * p.rec_len);
     if (!cv.ok()) return fail(GPB_ERR_WS, "det_bwd: workspace %zu < %zu", ws_bytes, cv.off);
     dim3 grid(p.gx, p.gy);
-#define GPB_BWD(DP)                                                                             \
+#define GPB_BWD2(DP, DOB)                                                                       \
     {                                                                                           \
-        auto kern = gpb::det_bwd_kernel<T, DP>;                                                 \
+        auto kern = gpb::det_bwd_kernel<T, DP, DOB>;                                            \
         GPB_LAUNCH(kern, grid, dim3(256), 0, stream, x, z, ls, (const T*)Ap, dm, dv,            \
                    (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block, part, \
                    p.rec_len);                                                                  \
     }
+#define GPB_BWD(DP)                                                                             \
+    {                                                                                           \
+        if (Do == 1) GPB_BWD2(DP, 1) else if (Do == 2) GPB_BWD2(DP, 2) else if (Do <= 4)        \
+            GPB_BWD2(DP, 4) else GPB_BWD2(DP, 0)                                                \
+    }
     prof_begin(1, stream);
-    if (D <= 4) GPB_BWD(4) else if (D <= 8) GPB_BWD(8) else GPB_BWD(16)
+    if (D <= 2) GPB_BWD(2) else if (D <= 4) GPB_BWD(4) else if (D <= 6) GPB_BWD(6)
+    else if (D <= 8) GPB_BWD(8) else if (D <= 10) GPB_BWD(10) else if (D <= 12) GPB_BWD(12)
+    else GPB_BWD(16)
     prof_end(1, stream);
 #undef GPB_BWD
+#undef GPB_BWD2
     int rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;
     auto red = gpb::reduce_partials_kernel;
@@ -116,11 +128,13 @@ int det_syrk_t(const void* Ksave, const double* dv, int n, int M, int Do, double
     double* part = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
     if (!cv.ok()) return fail(GPB_ERR_WS, "det_syrk: workspace %zu < %zu", ws_bytes, cv.off);
     auto kern = gpb::det_syrk_kernel<T>;
+    int rc = allow_smem(kern, gpb::SyrkCfg<T>::smem_bytes);
+    if (rc) return rc;
     prof_begin(2, stream);
-    GPB_LAUNCH(kern, dim3(p.nbu, p.nsplit, Do), dim3(256), 0, stream, (const T*)Ksave, dv, n, p.MP,
-               Do, p.rows_per_split, part);
+    GPB_LAUNCH(kern, dim3(p.nbu, p.nsplit, Do), dim3(256), gpb::SyrkCfg<T>::smem_bytes, stream,
+               (const T*)Ksave, dv, n, p.MP, Do, p.rows_per_split, part);
     prof_end(2, stream);
-    int rc = GPB_CHECK_LAUNCH();
+    rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;
     auto fin = gpb::det_syrk_finish_kernel;
     GPB_LAUNCH(fin, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, part, p.nsplit,

@@ -360,20 +360,23 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_kernel(DetFwdArgs<T> a) {
 //   L[n,m] = (sum_d dm[n,d] A[d,m] + 2 dv[n,d] T[n,d,m]) kfu[n,m]
 //   dsf2 += sum L / sf2 ; dZ[m,q] -= L (z_mq - x_nq)/l_q^2 ; dl_q += L (z_mq-x_nq)^2/l_q^3
 //   dA[d,m] += dm[n,d] kfu[n,m]
-// Thread per pseudo-point column, rows streamed from the saved Kfu / T buffers.
+// Thread per pseudo-point column, rows streamed from the saved Kfu / T buffers, U rows in
+// flight per thread (all loads issued before the first use) so the kernel runs at HBM speed.
 // grid = (row chunks, MP/CWB); each (block, row-group) writes one partial record:
 //   [ cs(MP) | dz(MP*D) | dl(MP*D) | dA(Do*MP) ]   (dl kept per column, summed later)
-// Input dims beyond DP are handled by extra passes over the rows (q0 loop), output
-// dims beyond 8 by extra dA passes (d0 loop).
-template <typename T, int DP>
+// DP = input dims per pass (exact for the common D, extra passes if D > 16);
+// DOB = output dims unrolled at compile time (1, 2, 4) or 0 = runtime loop (any Do).
+template <typename T, int DP, int DOB>
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
     const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls,
     const T* __restrict__ Ap, const double* __restrict__ dm, const double* __restrict__ dv,
     const T* __restrict__ Ksave, const T* __restrict__ Tsave, int n, int M, int MP, int D, int Do,
     int rows_per_block, double* __restrict__ part, long rec_len) {
-    constexpr int TR = 32;
+    constexpr int TR = 64;
+    constexpr int U = 4;
+    constexpr int DOS = DOB > 0 ? DOB : 1;
     GPB_SHARED T xs[TR * DP];
-    GPB_SHARED double dms[TR * 8];
+    GPB_SHARED double dms[TR * 8], dvs[TR * 8];
     const int tid = threadIdx.x;
     const int CWB = MP < 256 ? MP : 256;
     const int RY = kThreads / CWB;
@@ -388,12 +391,15 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
         T zr[DP];
         double dz[DP], dl[DP];
         double cs = 0;
+        T ap[DOS];
         GPB_UNROLL
         for (int q = 0; q < DP; q++) {
             zr[q] = (c < M && q0 + q < D) ? (T)z[(long)c * D + q0 + q] : (T)0;
             dz[q] = 0;
             dl[q] = 0;
         }
+        GPB_UNROLL
+        for (int d = 0; d < DOS; d++) ap[d] = (DOB > 0 && d < Do) ? Ap[(long)d * MP + c] : (T)0;
         for (int t0 = r_begin; t0 < r_end; t0 += TR) {
             const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
             sync_threads();
@@ -401,22 +407,51 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
                 int r = i / DP, q = i - r * DP;
                 xs[i] = (r < tv && q0 + q < D) ? (T)x[(long)(t0 + r) * D + q0 + q] : (T)0;
             }
+            if (DOB > 0)
+                for (int i = tid; i < TR * DOS; i += kThreads) {
+                    int r = i / DOS, d = i - r * DOS;
+                    bool ok = r < tv && d < Do;
+                    dms[r * 8 + d] = ok ? dm[(long)(t0 + r) * Do + d] : 0.0;
+                    dvs[r * 8 + d] = ok ? 2.0 * dv[(long)(t0 + r) * Do + d] : 0.0;
+                }
             sync_threads();
-            for (int r = ry; r < tv; r += RY) {
-                const long row = t0 + r;
-                const double k = (double)Ksave[row * MP + c];
-                double g = 0;
-                for (int d = 0; d < Do; d++)
-                    g += dm[row * Do + d] * (double)Ap[(long)d * MP + c] +
-                         2.0 * dv[row * Do + d] * (double)Tsave[(row * Do + d) * MP + c];
-                const double L = g * k;
-                cs += L;
+            for (int rb = ry * U; rb < tv; rb += RY * U) {
+                // issue every global load of U rows first
+                T kk[U], tt[U][DOS];
                 GPB_UNROLL
-                for (int q = 0; q < DP; q++) {
-                    double diff = (double)zr[q] - (double)xs[r * DP + q];
-                    double t = L * diff;
-                    dz[q] += t;
-                    dl[q] += t * diff;
+                for (int u = 0; u < U; u++) {
+                    const bool ok = (rb + u) < tv;
+                    const long row = t0 + (ok ? rb + u : rb);
+                    kk[u] = ok ? Ksave[row * MP + c] : (T)0;
+                    if (DOB > 0) {
+                        GPB_UNROLL
+                        for (int d = 0; d < DOS; d++)
+                            tt[u][d] = (d < Do) ? Tsave[(row * Do + d) * MP + c] : (T)0;
+                    }
+                }
+                GPB_UNROLL
+                for (int u = 0; u < U; u++) {
+                    const int r = (rb + u) < tv ? rb + u : rb;   // clamped rows carry k = 0
+                    double g = 0;
+                    if (DOB > 0) {
+                        GPB_UNROLL
+                        for (int d = 0; d < DOS; d++)
+                            g += dms[r * 8 + d] * (double)ap[d] + dvs[r * 8 + d] * (double)tt[u][d];
+                    } else {
+                        const long row = t0 + r;
+                        for (int d = 0; d < Do; d++)
+                            g += dm[row * Do + d] * (double)Ap[(long)d * MP + c] +
+                                 2.0 * dv[row * Do + d] * (double)Tsave[(row * Do + d) * MP + c];
+                    }
+                    const double L = g * (double)kk[u];
+                    cs += L;
+                    GPB_UNROLL
+                    for (int q = 0; q < DP; q++) {
+                        double diff = (double)zr[q] - (double)xs[r * DP + q];
+                        double t = L * diff;
+                        dz[q] += t;
+                        dl[q] += t * diff;
+                    }
                 }
             }
         }
@@ -443,10 +478,17 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
                 dms[i] = (r < tv && d < dn) ? dm[(long)(t0 + r) * Do + d0 + d] : 0.0;
             }
             sync_threads();
-            for (int r = ry; r < tv; r += RY) {
-                const double k = (double)Ksave[(long)(t0 + r) * MP + c];
+            for (int rb = ry * U; rb < tv; rb += RY * U) {
+                T kk[U];
                 GPB_UNROLL
-                for (int i = 0; i < 8; i++) dA[i] += dms[r * 8 + i] * k;
+                for (int u = 0; u < U; u++)
+                    kk[u] = (rb + u) < tv ? Ksave[(long)(t0 + rb + u) * MP + c] : (T)0;
+                GPB_UNROLL
+                for (int u = 0; u < U; u++) {
+                    const int r = (rb + u) < tv ? rb + u : rb;
+                    GPB_UNROLL
+                    for (int i = 0; i < 8; i++) dA[i] += dms[r * 8 + i] * (double)kk[u];
+                }
             }
         }
         for (int i = 0; i < dn; i++) rec[(long)MP + 2L * MP * D + (long)(d0 + i) * MP + c] = dA[i];
@@ -456,107 +498,120 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
 // a8 (rank-update part), aep_models.py:493: dB[d] = sum_n dv[n,d] kfu[n,:] kfu[n,:]^T.
 // Upper block-triangle of 128x128 output blocks; split over rows; partial records
 //   part[((split*Do + d)*NBU + ub)*128*128 + i*128 + j]
+// Each thread owns a 4 x 16 register tile (64 accumulators).  The two 128-column operand
+// panels of RK saved-Kfu rows are brought in by a 3-stage cp.async ring (no register
+// staging, one barrier per chunk); the row weight dv[n,d] is applied to the 4 A values
+// of a row as they are read (4 multiplies per 64 FMAs).
+template <typename T>
+struct SyrkCfg {
+    static constexpr int RK = 64 / (int)sizeof(T);   // rows per chunk: 8 KB per operand panel
+    static constexpr int STAGES = 3;
+    static constexpr int VEC = V16<T>::N;
+    static constexpr size_t stage_bytes = 2 * (size_t)RK * 128 * sizeof(T);
+    static constexpr size_t smem_bytes = STAGES * stage_bytes + STAGES * RK * sizeof(double);
+};
+
 template <typename T>
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_kernel(const T* __restrict__ Ksave,
                                                        const double* __restrict__ dv, int n, int MP,
                                                        int Do, int rows_per_split,
                                                        double* __restrict__ part) {
     typedef typename V16<T>::type VT;
-    constexpr int VEC = V16<T>::N;
-    constexpr int RK = 64 / (int)sizeof(T);          // rows per staged chunk (32 KB of smem)
-    constexpr int NV = 8 / VEC;                      // 16B vectors per thread per operand row
-    constexpr int LOADS = 2 * RK * 128 / VEC / kThreads;  // staged vectors per thread per chunk
-    GPB_SHARED GPB_ALIGN16 T As[2][RK * 128];
-    GPB_SHARED GPB_ALIGN16 T Bsm[2][RK * 128];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    typedef SyrkCfg<T> C;
+    constexpr int VEC = C::VEC, RK = C::RK, STAGES = C::STAGES;
+    constexpr int NA = 4 / VEC > 0 ? 4 / VEC : 1;    // 16B vectors of the 4 A values (fp64: 2, fp32: 1)
+    constexpr int NB = 16 / VEC;                      // 16B vectors of the 16 B values
+    constexpr int CPT = 2 * RK * 128 / VEC / kThreads;  // cp.async vectors per thread per chunk
+    GPB_DYN_SMEM(smem);
+    double* s_dv = (double*)(smem + STAGES * C::stage_bytes);
+    const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;   // 32 row groups x 8 column groups
     const int nb = MP / 128;
-    // decode upper-triangular block id -> (bi <= bj)
     int ub = blockIdx.x, bi = 0;
     while (ub >= nb - bi) { ub -= nb - bi; bi++; }
     const int bj = bi + ub;
     const int d = blockIdx.z;
     const int r_begin = blockIdx.y * rows_per_split;
     const int r_end = (r_begin + rows_per_split) < n ? (r_begin + rows_per_split) : n;
+    const int nchunk = (r_end - r_begin + RK - 1) / RK;
 
-    T acc[8][8];
+    T acc[4][16];
     GPB_UNROLL
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 4; i++)
         GPB_UNROLL
-        for (int j = 0; j < 8; j++) acc[i][j] = 0;
+        for (int j = 0; j < 16; j++) acc[i][j] = 0;
 
-    VecU<T> stage[LOADS];
-    auto fetch = [&](int t0) {
-        GPB_UNROLL
-        for (int i = 0; i < LOADS; i++) {
-            int v = tid + kThreads * i;
-            int which = v / (RK * 128 / VEC);
-            int rem = v - which * (RK * 128 / VEC);
-            int r = rem / (128 / VEC), cv = rem - r * (128 / VEC);
-            long row = (long)t0 + r;
-            if (row < r_end) {
-                stage[i].v = *(const VT*)(Ksave + row * MP + (which ? bj : bi) * 128 + cv * VEC);
-                if (which == 0) {
-                    T w = (T)dv[row * Do + d];
-                    GPB_UNROLL
-                    for (int e = 0; e < VEC; e++) stage[i].e[e] *= w;
-                }
-            } else {
-                GPB_UNROLL
-                for (int e = 0; e < VEC; e++) stage[i].e[e] = 0;
+    auto issue = [&](int chunk) {
+        if (chunk < nchunk) {
+            const int st = chunk % STAGES;
+            T* base = (T*)(smem + (size_t)st * C::stage_bytes);
+            const int t0 = r_begin + chunk * RK;
+            GPB_UNROLL
+            for (int i = 0; i < CPT; i++) {
+                int v = tid + kThreads * i;
+                int which = v / (RK * 128 / VEC);
+                int rem = v - which * (RK * 128 / VEC);
+                int r = rem / (128 / VEC), cv = rem - r * (128 / VEC);
+                long row = (long)t0 + r;
+                bool ok = row < r_end;
+                const T* src = Ksave + (ok ? row : (long)r_begin) * MP + (which ? bj : bi) * 128 + cv * VEC;
+                cp_async16_zfill(base + (long)which * RK * 128 + (long)rem * VEC, src, ok);
+            }
+            if (tid < RK) {
+                long row = (long)t0 + tid;
+                s_dv[st * RK + tid] = row < r_end ? dv[row * Do + d] : 0.0;
             }
         }
-    };
-    auto stash = [&](int buf) {
-        GPB_UNROLL
-        for (int i = 0; i < LOADS; i++) {
-            int v = tid + kThreads * i;
-            int which = v / (RK * 128 / VEC);
-            int rem = v - which * (RK * 128 / VEC);
-            T* dst = which ? Bsm[buf] : As[buf];
-            *(VT*)(dst + (long)rem * VEC) = stage[i].v;
-        }
+        cp_async_commit();   // always commit (possibly empty) so the group counting stays uniform
     };
 
-    if (r_begin < r_end) {
-        fetch(r_begin);
-        stash(0);
-    }
-    sync_threads();
-    int buf = 0;
-    for (int t0 = r_begin; t0 < r_end; t0 += RK) {
-        const bool more = (t0 + RK) < r_end;
-        if (more) fetch(t0 + RK);
+    issue(0);
+    issue(1);
+    for (int c = 0; c < nchunk; c++) {
+        cp_async_wait<STAGES - 2>();   // chunk c has landed (this thread's copies)
+        sync_threads();                // ... everybody's copies; stage (c+2)%3 is free again
+        issue(c + 2);
+        const int st = c % STAGES;
+        const T* As = (const T*)(smem + (size_t)st * C::stage_bytes);
+        const T* Bs = As + RK * 128;
         GPB_UNROLL
         for (int r = 0; r < RK; r++) {
-            T av[8], bv[8];
-            GPB_UNROLL
-            for (int j = 0; j < NV; j++) {
-                VecU<T> ua, ub2;
-                ua.v = *(const VT*)(As[buf] + r * 128 + j * (16 * VEC) + ty * VEC);
-                ub2.v = *(const VT*)(Bsm[buf] + r * 128 + j * (16 * VEC) + tx * VEC);
+            const T w = (T)s_dv[st * RK + r];
+            T av[4], bv[16];
+            if (VEC == 2) {
                 GPB_UNROLL
-                for (int e = 0; e < VEC; e++) {
-                    av[j * VEC + e] = ua.e[e];
-                    bv[j * VEC + e] = ub2.e[e];
+                for (int j = 0; j < 2; j++) {
+                    VecU<T> u;
+                    u.v = *(const VT*)(As + r * 128 + j * 64 + ty * 2);
+                    av[j * 2 + 0] = u.e[0] * w;
+                    av[j * 2 + 1] = u.e[1 % VEC] * w;
                 }
+            } else {
+                VecU<T> u;
+                u.v = *(const VT*)(As + r * 128 + ty * 4);
+                GPB_UNROLL
+                for (int e = 0; e < 4; e++) av[e] = u.e[e % VEC] * w;
             }
             GPB_UNROLL
-            for (int i = 0; i < 8; i++)
+            for (int j = 0; j < NB; j++) {
+                VecU<T> u;
+                u.v = *(const VT*)(Bs + r * 128 + j * (8 * VEC) + tx * VEC);
                 GPB_UNROLL
-                for (int j = 0; j < 8; j++) acc[i][j] += av[i] * bv[j];
+                for (int e = 0; e < VEC; e++) bv[j * VEC + e] = u.e[e];
+            }
+            GPB_UNROLL
+            for (int i = 0; i < 4; i++)
+                GPB_UNROLL
+                for (int j = 0; j < 16; j++) acc[i][j] += av[i] * bv[j];
         }
-        if (more) stash(buf ^ 1);
-        sync_threads();
-        buf ^= 1;
     }
     const int nbu = nb * (nb + 1) / 2;
     double* out = part + (((long)blockIdx.y * Do + d) * nbu + blockIdx.x) * (128 * 128);
     GPB_UNROLL
-    for (int i = 0; i < 8; i++) {
-        const int oi = (i / VEC) * (16 * VEC) + ty * VEC + (i % VEC);
+    for (int i = 0; i < 4; i++) {
+        const int oi = VEC == 2 ? ((i / 2) * 64 + ty * 2 + (i % 2)) : (ty * 4 + i);
         GPB_UNROLL
-        for (int j = 0; j < 8; j++) {
-            const int oj = (j / VEC) * (16 * VEC) + tx * VEC + (j % VEC);
+        for (int j = 0; j < 16; j++) {
+            const int oj = (j / VEC) * (8 * VEC) + tx * VEC + (j % VEC);
             out[oi * 128 + oj] = (double)acc[i][j];
         }
     }

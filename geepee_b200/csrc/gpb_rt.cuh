@@ -36,6 +36,12 @@ GPB_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 }
+// same, but writes 16 zero bytes when !valid (src-size 0: nothing is read from gmem_src)
+GPB_DEVICE void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(n));
+}
 GPB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 GPB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -94,6 +100,9 @@ static inline double shfl_xor(double v, int m) { return gpb_emu::shfl_xor_f64(v,
 static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f64((double)v, m); }
 static inline void atomic_add(double* p, double v) { *p += v; }
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async16_zfill(void* d, const void* s, bool valid) {
+    if (valid) memcpy(d, s, 16); else memset(d, 0, 16);
+}
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
