@@ -65,6 +65,7 @@ class SGPR(Base_SGPR):
         N, L, dev = self.N, self.sgp_layer, self.device
         xb, yb, n = self._batch(mb_size)
         scale_logZ = -N * 1.0 / n / alpha
+        L._fuse_cavity_alpha = alpha
         self.update_hypers(params)
         L.compute_cavity(alpha)
         add = {}
@@ -97,6 +98,8 @@ class SDGPR(Base_SDGPR):
         N, dev = self.N, self.device
         xb, yb, n = self._batch(mb_size)
         scale_logZ = -N * 1.0 / n / alpha
+        for layer in self.sgp_layers:
+            layer._fuse_cavity_alpha = alpha
         self.update_hypers(params)
         for layer in self.sgp_layers:
             layer.compute_cavity(alpha)
@@ -174,6 +177,7 @@ class SGPLVM(Base_SGPLVM):
         scale_logZ = -N * 1.0 / n / alpha
         s_cav = -N * 1.0 / n / alpha
         s_post = -N * 1.0 / n * (1.0 - 1.0 / alpha)
+        L._fuse_cavity_alpha = alpha
         self.update_hypers(params)
         L.compute_cavity(alpha)
         add = {'gx1': _zeros(dev, N, Q), 'gx2': _zeros(dev, N, Q)}
@@ -247,6 +251,9 @@ class SGPSSM(Base_SGPSSM):
         n_dyn = n_emi - 1
         s_dyn = -(N - 1) * 1.0 / n_dyn / alpha
         s_emi = -N * 1.0 / n_emi / alpha
+        dyn._fuse_cavity_alpha = alpha
+        if self.gp_emi:
+            emi._fuse_cavity_alpha = alpha
         self.update_hypers(params)
         dyn.compute_cavity(alpha)
         if self.gp_emi:

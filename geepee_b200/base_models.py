@@ -13,7 +13,7 @@ from scipy.optimize import minimize
 
 from . import config, dist
 from .config import PROP_MM, PROP_MC
-from .layers import default_device, to_dev
+from .layers import default_device, to_dev, pack_to_device
 from .lik_layers import Gauss_Layer, Gauss_Emis
 from .utils import ObjectiveWrapper, flatten_dict, unflatten_dict, adam, PCA_reduce
 
@@ -175,8 +175,9 @@ class Base_SGPR(Base_Model):
         return params
 
     def update_hypers(self, params):
-        self.sgp_layer.update_hypers(params)
-        self.lik_layer.update_hypers(params)
+        dev = pack_to_device(params, self.device)
+        self.sgp_layer.update_hypers(params, _dev=dev)
+        self.lik_layer.update_hypers(params, _dev=dev)
 
 
 class Base_SDGPR(Base_Model):
@@ -240,9 +241,10 @@ class Base_SDGPR(Base_Model):
         return params
 
     def update_hypers(self, params):
+        dev = pack_to_device(params, self.device)
         for i, layer in enumerate(self.sgp_layers):
-            layer.update_hypers(params, key_suffix='_%d' % i)
-        self.lik_layer.update_hypers(params)
+            layer.update_hypers(params, key_suffix='_%d' % i, _dev=dev)
+        self.lik_layer.update_hypers(params, _dev=dev)
 
 
 class Base_SGPLVM(Base_Model):
@@ -318,12 +320,13 @@ class Base_SGPLVM(Base_Model):
 
     def update_hypers(self, params):
         """base_models.py:899-911."""
-        self.sgp_layer.update_hypers(params)
-        self.lik_layer.update_hypers(params)
+        dev = pack_to_device(params, self.device)
+        self.sgp_layer.update_hypers(params, _dev=dev)
+        self.lik_layer.update_hypers(params, _dev=dev)
         self.factor_x1 = params['x1']
         self.factor_x2 = np.exp(2 * params['x2'])
-        self._f1 = to_dev(params['x1'], self.device)
-        self._f2 = torch.exp(2.0 * to_dev(params['x2'], self.device))
+        self._f1 = dev['x1'].reshape(self.N, self.Din)
+        self._f2 = torch.exp(2.0 * dev['x2'].reshape(self.N, self.Din))
         if self.nat_param:
             self._post1 = self.prior_x1 + self._f1
             self._post2 = self.prior_x2 + self._f2
@@ -398,16 +401,17 @@ class Base_SGPSSM(Base_Model):
     def update_hypers(self, params):
         """base_models.py:1711-1728."""
         dev = self.device
-        self.dyn_layer.update_hypers(params, key_suffix='_dynamic')
-        self.emi_layer.update_hypers(params, key_suffix='_emission')
+        dp = pack_to_device(params, dev)
+        self.dyn_layer.update_hypers(params, key_suffix='_dynamic', _dev=dp)
+        self.emi_layer.update_hypers(params, key_suffix='_emission', _dev=dp)
         if self.gp_emi:
-            self.lik_layer.update_hypers(params, key_suffix='_emission')
+            self.lik_layer.update_hypers(params, key_suffix='_emission', _dev=dp)
         self.sn = params['sn']
-        self._sn = to_dev(np.reshape(self.sn, (-1,))[:1], dev)
+        self._sn = dp['sn'].reshape(-1)[:1].contiguous()
         self.x_factor_1 = params['x_factor_1']
         self.x_factor_2 = np.exp(2 * params['x_factor_2'])
-        self._f1 = to_dev(params['x_factor_1'], dev)
-        self._f2 = torch.exp(2.0 * to_dev(params['x_factor_2'], dev))
+        self._f1 = dp['x_factor_1'].reshape(self.N, self.Din)
+        self._f2 = torch.exp(2.0 * dp['x_factor_2'].reshape(self.N, self.Din))
         if self.nat_param:
             w = torch.full((self.N, 1), 3.0, dtype=_F, device=dev)
             w[0] = 2.0

@@ -708,49 +708,56 @@ struct MMArgs {
     int lam_pass;      // bwd: 1 -> this pass also produces the Lambda-dependent sums
 };
 
-// exp(x) for x <= 0 without the special-case branches of libm: 2^k * P(r), k = rint(x log2 e),
-// |r| <= ln2/2, degree-11 Taylor polynomial in Estrin form (dependency depth 5 instead of 12;
-// relative error < 1e-14).  The 2^k scaling is an integer add into the exponent field; k is
-// clamped at -1021 so that deep underflow returns ~1e-308 * P instead of garbage.
-// fp32: the SFU path (ex2.approx).
+// exp(x) for x <= 0 without the special-case branches of libm and with a short polynomial:
+//   x = (64 k + j) ln2/64 + r,  |r| <= ln2/128   ->   exp(x) = 2^k * 2^(j/64) * P5(r)
+// 2^(j/64) comes from a 64-entry table in shared memory, P5 is the degree-5 Taylor polynomial in
+// Estrin form (relative error 5e-16, checked against libm in tests), the 2^k scaling is an
+// integer add into the exponent field with k clamped at -1021 (deep underflow returns ~1e-308).
+// 12 fp64 instructions instead of ~25 for libm exp.  fp32: the SFU path (ex2.approx).
 #ifndef GPB_CPU_EMU
-__constant__ double c_exp_coef[12] = {
-    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.333333333333333e-03,
-    1.388888888888889e-03, 1.984126984126984e-04, 2.48015873015873e-05, 2.7557319223985893e-06,
-    2.755731922398589e-07, 2.505210838544172e-08};
+__constant__ double c_exp2_tab[64] = {
 #else
-static const double c_exp_coef[12] = {
-    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.333333333333333e-03,
-    1.388888888888889e-03, 1.984126984126984e-04, 2.48015873015873e-05, 2.7557319223985893e-06,
-    2.755731922398589e-07, 2.505210838544172e-08};
+static const double c_exp2_tab[64] = {
 #endif
-GPB_DEVICE double exp_neg(double x) {
+    1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00,
+    1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00,
+    1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00,
+    1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00,
+    1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00,
+    1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00,
+    1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00,
+    1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00,
+    1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00,
+    1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00,
+    1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00,
+    1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00,
+    1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00,
+    1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00,
+    1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00,
+    1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
+GPB_DEVICE double exp_neg(double x, const double* __restrict__ tab /* 64 doubles in smem */) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    double kd = x * 1.4426950408889634 + magic;
+    double kd = x * 92.332482616893656877 + magic;          // 64 / ln 2
 #ifndef GPB_CPU_EMU
-    int k = __double2loint(kd);
+    int n = __double2loint(kd);
 #else
     int64_t bits;
     memcpy(&bits, &kd, 8);
-    int k = (int)(int32_t)(bits & 0xffffffff);
+    int n = (int)(int32_t)(bits & 0xffffffff);
 #endif
     kd -= magic;
-    double r = kd * -6.93147180369123816490e-01 + x;
-    r = kd * -1.90821492927058770002e-10 + r;
+    double r = kd * -0.01083042469326756 + x;               // ln2/64, high part (21 trailing zero bits)
+    r = kd * -2.9815858269852933e-12 + r;                   // ln2/64, low part
+    const double t = tab[n & 63];
+    int k = n >> 6;
     const double r2 = r * r;
-    const double p01 = c_exp_coef[1] * r + c_exp_coef[0];
-    const double p23 = c_exp_coef[3] * r + c_exp_coef[2];
-    const double p45 = c_exp_coef[5] * r + c_exp_coef[4];
-    const double p67 = c_exp_coef[7] * r + c_exp_coef[6];
-    const double p89 = c_exp_coef[9] * r + c_exp_coef[8];
-    const double pab = c_exp_coef[11] * r + c_exp_coef[10];
+    const double p01 = 1.0 + r;
+    const double p23 = r * 1.6666666666666666e-01 + 0.5;
+    const double p45 = r * 8.333333333333333e-03 + 4.1666666666666664e-02;
     const double r4 = r2 * r2;
-    const double q0 = p23 * r2 + p01;
-    const double q1 = p67 * r2 + p45;
-    const double q2 = pab * r2 + p89;
-    const double r8 = r4 * r4;
-    double p = q1 * r4 + q0;
-    p = q2 * r8 + p;
+    double p = p23 * r2 + p01;
+    p = p45 * r4 + p;
+    p *= t;
     k = k < -1021 ? -1021 : k;
 #ifndef GPB_CPU_EMU
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
@@ -758,7 +765,7 @@ GPB_DEVICE double exp_neg(double x) {
     return ldexp(p, k);
 #endif
 }
-GPB_DEVICE float exp_neg(float x) { return fast_exp(x); }
+GPB_DEVICE float exp_neg(float x, const double*) { return fast_exp(x); }
 
 // Running warp-transpose reduction.  Row r (0..31) of a tile contributes NS per-lane partial sums;
 // after the 32nd push lane L holds the NS sums of row L added over all 32 lanes.  Pending partial
@@ -825,6 +832,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     GPB_SHARED double s_dvall[kGen ? TR * 64 : 1];  // generic path (single buffered): all Do (<= 64) per row
     GPB_SHARED T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
     GPB_SHARED double s_l2[Q];
+    GPB_SHARED double s_exp2[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long pbase = (long)blockIdx.x * C::PC;
     const long PP = a.PP;
@@ -851,6 +859,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         for (int q = 0; q < Q; q++) accS1[j][q] = 0;
     }
     if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+    if (tid >= 64 && tid < 128) s_exp2[tid - 64] = c_exp2_tab[tid - 64];
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
@@ -922,7 +931,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                     t[q] = diff * c2[q];
                     x -= t[q] * diff;
                 }
-                const T psi2 = exp_neg(x);
+                const T psi2 = exp_neg(x, s_exp2);
                 if (!BWD) {
                     GPB_UNROLL
                     for (int d = 0; d < DOC; d++) v[d] += bs[j][d] * psi2;

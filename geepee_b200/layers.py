@@ -37,11 +37,31 @@ def to_dev(a, device):
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)
 
 
+def pack_to_device(params, device):
+    """Upload a whole parameter dict with ONE host->device copy; returns {key: fp64 device view}."""
+    keys = sorted(params.keys())
+    arrs = [np.ascontiguousarray(params[k], dtype=np.float64) for k in keys]
+    flat = np.concatenate([a.reshape(-1) for a in arrs]) if arrs else np.zeros(0)
+    t = torch.from_numpy(flat).to(device)
+    out, off = {}, 0
+    for k, a in zip(keys, arrs):
+        out[k] = t[off:off + a.size].reshape(a.shape if a.ndim > 0 else (1,))
+        off += a.size
+    return out
+
+
 def spd_inverse(A):
     """inverse and log-determinant of (a batch of) SPD matrices via Cholesky.
-    Replaces np.linalg.inv / slogdet at base_models.py:464,471,476 and aep_models.py:68,78,91,525,533."""
-    L = torch.linalg.cholesky(A)
-    inv = torch.cholesky_inverse(L)
+    Replaces np.linalg.inv / slogdet at base_models.py:464,471,476 and aep_models.py:68,78,91,525,533.
+    No host synchronisation: `cholesky_ex` does not check `info` (a non-SPD input yields NaNs,
+    which the optimiser wrapper treats like the reference treats non-finite gradients), and
+    A^-1 = L^-T L^-1 is one triangular solve + one GEMM instead of the much slower potri."""
+    L, _ = torch.linalg.cholesky_ex(A, check_errors=False)
+    eye = torch.eye(A.shape[-1], dtype=A.dtype, device=A.device)
+    if A.dim() == 3:
+        eye = eye.expand(A.shape[0], -1, -1)
+    Linv = torch.linalg.solve_triangular(L, eye, upper=False)
+    inv = torch.matmul(Linv.transpose(-1, -2), Linv)
     logdet = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
     return inv, logdet
 
@@ -80,24 +100,28 @@ class Base_SGP_Layer(object):
         raise AttributeError(name)
 
     # ---- hyper-parameter plumbing ---------------------------------------------------------
-    def update_hypers(self, params, key_suffix=''):
-        """base_models.py:630-658: eta1_R -> R (log-diagonal upper triangle), theta_1 = R^T R."""
+    def update_hypers(self, params, key_suffix='', _dev=None):
+        """base_models.py:630-658: eta1_R -> R (log-diagonal upper triangle), theta_1 = R^T R.
+        `_dev` (optional): the same dict already on the device (models upload all keys at once)."""
         M, Dout, dev = self.M, self.Dout, self.device
         self.ls = params['ls' + key_suffix]
         self.sf = params['sf' + key_suffix]
         self.zu = params['zu' + key_suffix]
         t = self._t
-        t['ls'] = to_dev(np.reshape(self.ls, (self.Din,)), dev)
-        t['sf'] = to_dev(np.reshape(self.sf, (-1,))[:1], dev)
-        t['zu'] = to_dev(np.reshape(self.zu, (M, self.Din)), dev)
-        eta1 = to_dev(params['eta1_R' + key_suffix], dev)
+        if _dev is None:
+            _dev = pack_to_device({k: params[k + key_suffix] for k in ('ls', 'sf', 'zu', 'eta1_R', 'eta2')}, dev)
+            key_suffix = ''
+        t['ls'] = _dev['ls' + key_suffix].reshape(self.Din).contiguous()
+        t['sf'] = _dev['sf' + key_suffix].reshape(-1)[:1].contiguous()
+        t['zu'] = _dev['zu' + key_suffix].reshape(M, self.Din).contiguous()
+        eta1 = _dev['eta1_R' + key_suffix].reshape(Dout, -1)
         R = torch.zeros((Dout, M, M), dtype=_F, device=dev)
         R[:, self._iu[0], self._iu[1]] = eta1
         dg = torch.diagonal(R, dim1=1, dim2=2)
         dg.copy_(torch.exp(dg))
         t['theta_1_R'] = R
         t['theta_1'] = torch.matmul(R.transpose(1, 2), R)
-        t['theta_2'] = to_dev(params['eta2' + key_suffix], dev)
+        t['theta_2'] = _dev['eta2' + key_suffix].reshape(Dout, M).contiguous()
         self.compute_kuu()
         self.update_posterior()
 
@@ -111,7 +135,21 @@ class Base_SGP_Layer(object):
         """base_models.py:466-488."""
         t = self._t
         Ki = t['Kuuinv']
-        if self.nat_param:
+        self._cavity_ready = None
+        alpha = getattr(self, '_fuse_cavity_alpha', None)
+        if self.nat_param and alpha is not None:
+            # AEP fast path: q(u) and the cavity need inv(Ki + theta_1) and inv(Ki + beta theta_1);
+            # factorise both in ONE batched call (halves the launch count of the tail)
+            beta = (self.N - alpha) * 1.0 / self.N
+            Do = self.Dout
+            both = torch.cat((Ki + t['theta_1'], Ki + beta * t['theta_1']), dim=0)
+            inv, ld = spd_inverse(both)
+            t['Suinv'], t['Suhatinv'] = both[:Do], both[Do:]
+            t['Su'], t['Suhat'] = inv[:Do], inv[Do:]
+            t['logdet_Su'], t['logdet_Suhat'] = -ld[:Do], -ld[Do:]
+            t['mu'] = bmv(t['Su'], t['theta_2'])
+            self._cavity_ready = alpha
+        elif self.nat_param:
             t['Suinv'] = Ki + t['theta_1']
             t['Su'], ld = spd_inverse(t['Suinv'])
             t['logdet_Su'] = -ld
@@ -313,7 +351,10 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         t = self._t
         Ki = t['Kuuinv']
         beta = (self.N - alpha) * 1.0 / self.N
-        if self.nat_param:
+        ld = None
+        if self.nat_param and getattr(self, '_cavity_ready', None) == alpha:
+            t['muhat'] = bmv(t['Suhat'], beta * t['theta_2'])     # Suhat came with the posterior
+        elif self.nat_param:
             t['Suhatinv'] = Ki + beta * t['theta_1']
             t['Suhat'], ld = spd_inverse(t['Suhatinv'])
             t['muhat'] = bmv(t['Suhat'], beta * t['theta_2'])
@@ -323,7 +364,8 @@ class AEP_SGP_Layer(Base_SGP_Layer):
             t['Suhatinv'] = Ki + beta * f1
             t['Suhat'], ld = spd_inverse(t['Suhatinv'])
             t['muhat'] = bmv(t['Suhat'], beta * f2)
-        t['logdet_Suhat'] = -ld
+        if ld is not None:
+            t['logdet_Suhat'] = -ld
         t['Ahat'] = torch.matmul(t['muhat'], Ki)
         t['Splusmmhat'] = t['Suhat'] + outer(t['muhat'], t['muhat'])
         t['Bhat_sto'] = torch.matmul(Ki, torch.matmul(t['Splusmmhat'], Ki)) - Ki

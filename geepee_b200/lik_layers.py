@@ -86,9 +86,12 @@ class Gauss_Layer(Lik_Layer):
     def get_hypers(self, key_suffix=''):
         return {'sn' + key_suffix: self.sn}
 
-    def update_hypers(self, params, key_suffix=''):
+    def update_hypers(self, params, key_suffix='', _dev=None):
         self.sn = params['sn' + key_suffix]
-        self._sn = to_dev(np.reshape(self.sn, (-1,))[:1], self.device)
+        if _dev is not None:
+            self._sn = _dev['sn' + key_suffix].reshape(-1)[:1].contiguous()
+        else:
+            self._sn = to_dev(np.reshape(self.sn, (-1,))[:1], self.device)
 
 
 class Gauss_Emis(object):
@@ -104,11 +107,15 @@ class Gauss_Emis(object):
         self.R = np.zeros(Dout)
         self._y = to_dev(y, device)
 
-    def update_hypers(self, params, key_suffix=''):
+    def update_hypers(self, params, key_suffix='', _dev=None):
         self.C = params['C' + key_suffix]
         self.R = np.exp(2 * params['R' + key_suffix])
-        self._C = to_dev(self.C, self.device)
-        self._R = to_dev(self.R, self.device)
+        if _dev is not None:
+            self._C = _dev['C' + key_suffix].reshape(self.Dout, self.Din).contiguous()
+            self._R = torch.exp(2.0 * _dev['R' + key_suffix].reshape(self.Dout))
+        else:
+            self._C = to_dev(self.C, self.device)
+            self._R = to_dev(self.R, self.device)
 
     def init_hypers(self, key_suffix=''):
         return {'C' + key_suffix: np.ones((self.Dout, self.Din)) / (self.Dout * self.Din),
@@ -130,7 +137,7 @@ class Gauss_Emis(object):
         CVC = torch.einsum('da,na,ba->ndb', C, vx, C)
         Vy = torch.diag(R / alpha).unsqueeze(0) + CVC
         Yd = y - torch.matmul(mx, C.t())
-        Lc = torch.linalg.cholesky(Vy)
+        Lc, _ = torch.linalg.cholesky_ex(Vy, check_errors=False)   # no host sync
         VinvY = torch.cholesky_solve(Yd.unsqueeze(-1), Lc).squeeze(-1)
         quad = -0.5 * (Yd * VinvY).sum()
         # log|I + alpha CVC / R| = log|Vy| - sum log(R/alpha)
