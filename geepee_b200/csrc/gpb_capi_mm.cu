@@ -17,18 +17,21 @@ int q_template(int Q) {
     if (Q <= 16) return 16;
     return -1;
 }
-int mm_rp(int Qt, int DOC) { return gpb::MMCfg<1, 1>::RP == 2 ? ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1)
-                                                            : ((2 * Qt + 2 * DOC + 2) <= 12 ? 4 : ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1)); }
+// pairs per thread: mirrors gpb::MMCfg<T,Q,DOC>::RP (fp32 holds twice as many)
+int mm_rp(int tbytes, int Qt, int DOC) {
+    int rp = (2 * Qt + 2 * DOC + 2) <= 12 ? 4 : ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1);
+    return tbytes == 4 ? 2 * rp : rp;
+}
 
-MMPlan mm_plan(int n, int M, int Q, int Do) {
+MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do) {
     MMPlan p;
     p.Qt = q_template(Q);
     p.DOC = Do == 1 ? 1 : (Do == 2 ? 2 : 4);
     p.npass = (int)cdiv(Do, p.DOC);
-    p.RP = mm_rp(p.Qt, p.DOC);
+    p.RP = mm_rp(tbytes, p.Qt, p.DOC);
     p.PC = 256 * p.RP;
     p.P = (long)M * (M + 1) / 2;
-    p.PP = cdiv(p.P, 1024) * 1024;
+    p.PP = cdiv(p.P, p.PC) * p.PC;
     p.nchunks = (int)(p.PP / p.PC);
     // row splits: as many blocks as fit an integer number of waves (1 block/SM), 8 waves when the
     // problem is large enough, never less than 4 row tiles per block
@@ -67,10 +70,10 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
     w.ep = (T*)cv.take(sizeof(T) * p.PP);
     w.bs = (T*)cv.take(sizeof(T) * Do * p.PP);
     if (!backward) {
-        w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * Do);
+        w.rowacc = nullptr;   // the forward accumulates straight into the caller's vacc[n,Do]
         w.pairpart = w.pairsum = w.rowpart = w.rowsum = w.colpart = w.colsum = w.dZ2 = w.dlW = nullptr;
     } else {
-        w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * (1 + 2 * p.Qt));
+        w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * (2 * p.Qt));
         w.pairpart = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * (p.DOC + 1 + p.Qt) * p.PP);
         w.pairsum = (double*)cv.take(sizeof(double) * (size_t)(Do + 1 + p.Qt) * p.PP);
         w.rowpart = (double*)cv.take(sizeof(double) * (size_t)p.rows_grid * (2 + Q));
@@ -136,15 +139,16 @@ int mm_check(int n, int M, int Q, int Do) {
 template <typename T>
 int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
              const double* A, const double* B, int n, int M, int Q, int Do, double* mout,
-             double* vout, void* ws, size_t ws_bytes, void* stream) {
+             double* vout, double* vacc, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
     if (rc) return rc;
-    MMPlan p = mm_plan(n, M, Q, Do);
+    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do);
     MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 0, ws, ws_bytes);
     if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_fwd: workspace %zu < %zu", ws_bytes, w.bytes);
     auto tab = gpb::mm_pair_table_kernel<T>;
     GPB_LAUNCH(tab, dim3(elementwise_grid(p.PP)), dim3(256), 0, stream, z, ls, sf, B, M, Q, p.Qt, Do,
                p.P, p.PP, w.zh, w.ep, w.bs);
+    w.rowacc = vacc;
     dev_memset(w.rowacc, sizeof(double) * (size_t)n * Do, stream);
     gpb::MMArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -171,18 +175,18 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
 template <typename T>
 int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
              const double* A, const double* B, const double* dm, const double* dv,
-             const double* mout, int n, int M, int Q, int Do, double* dA, double* dB, double* dzu,
-             double* dl, double* dsf2, double* dvsum, double* dmx, double* dvx, void* ws,
-             size_t ws_bytes, void* stream) {
+             const double* mout, const double* vacc, int n, int M, int Q, int Do, double* dA,
+             double* dB, double* dzu, double* dl, double* dsf2, double* dvsum, double* dmx,
+             double* dvx, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
     if (rc) return rc;
-    MMPlan p = mm_plan(n, M, Q, Do);
+    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do);
     MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 1, ws, ws_bytes);
     if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_bwd: workspace %zu < %zu", ws_bytes, w.bytes);
     auto tab = gpb::mm_pair_table_kernel<T>;
     GPB_LAUNCH(tab, dim3(elementwise_grid(p.PP)), dim3(256), 0, stream, z, ls, sf, B, M, Q, p.Qt, Do,
                p.P, p.PP, w.zh, w.ep, w.bs);
-    const int NS = 1 + 2 * p.Qt;
+    const int NS = 2 * p.Qt;
     dev_memset(w.rowacc, sizeof(double) * (size_t)n * NS, stream);
     gpb::MMArgs<T> a;
     memset(&a, 0, sizeof(a));
@@ -216,7 +220,7 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
         if (rc) return rc;
         prof_begin(5, stream);
         GPB_LAUNCH(kern, dim3(p.rows_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout,
-                   w.rowacc, n, M, Q, p.Qt, Do, dmx, dvx, w.rowpart);
+                   vacc, w.rowacc, n, M, Q, p.Qt, Do, dmx, dvx, w.rowpart);
         prof_end(5, stream);
         GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
                    (long)(2 + Q), w.rowsum, 0);
@@ -252,29 +256,32 @@ extern "C" {
 
 size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward) {
     if (q_template(Q) < 0 || n < 1 || M < 1 || Do < 1) return 0;
-    MMPlan p = mm_plan(n, M, Q, Do);
-    return mm_carve<double>(p, n, M, Q, Do, backward, nullptr, 0).bytes;  // fp64 sizing covers fp32
+    // the pair padding (and with it the fp64 partial records) depends on the precision: take the max
+    MMPlan p8 = mm_plan(8, n, M, Q, Do), p4 = mm_plan(4, n, M, Q, Do);
+    size_t b8 = mm_carve<double>(p8, n, M, Q, Do, backward, nullptr, 0).bytes;
+    size_t b4 = mm_carve<float>(p4, n, M, Q, Do, backward, nullptr, 0).bytes;
+    return b8 > b4 ? b8 : b4;
 }
 
 int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
-               double* mout, double* vout, void* ws, size_t ws_bytes, void* stream) {
-    if (!mx || !vx || !z || !ls || !sf || !A || !B || !mout || !vout || !ws) return fail(GPB_ERR_ARG, "mm_fwd: null pointer");
-    if (prec == GPB_F64) return mm_fwd_t<double>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, ws, ws_bytes, stream);
-    return mm_fwd_t<float>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, ws, ws_bytes, stream);
+               double* mout, double* vout, double* vacc, void* ws, size_t ws_bytes, void* stream) {
+    if (!mx || !vx || !z || !ls || !sf || !A || !B || !mout || !vout || !vacc || !ws) return fail(GPB_ERR_ARG, "mm_fwd: null pointer");
+    if (prec == GPB_F64) return mm_fwd_t<double>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, ws, ws_bytes, stream);
+    return mm_fwd_t<float>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, ws, ws_bytes, stream);
 }
 
 int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, const double* dm, const double* dv,
-               const double* mout, int n, int M, int Q, int Do, double* dA, double* dB, double* dzu,
-               double* dl, double* dsf2, double* dvsum, double* dmx, double* dvx, void* ws,
-               size_t ws_bytes, void* stream) {
-    if (!mx || !vx || !z || !ls || !sf || !A || !B || !dm || !dv || !mout || !dA || !dB || !dzu || !dl ||
+               const double* mout, const double* vacc, int n, int M, int Q, int Do, double* dA,
+               double* dB, double* dzu, double* dl, double* dsf2, double* dvsum, double* dmx,
+               double* dvx, void* ws, size_t ws_bytes, void* stream) {
+    if (!mx || !vx || !z || !ls || !sf || !A || !B || !dm || !dv || !mout || !vacc || !dA || !dB || !dzu || !dl ||
         !dsf2 || !dvsum || !dmx || !dvx || !ws)
         return fail(GPB_ERR_ARG, "mm_bwd: null pointer");
     if (prec == GPB_F64)
-        return mm_bwd_t<double>(mx, vx, z, ls, sf, A, B, dm, dv, mout, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
-    return mm_bwd_t<float>(mx, vx, z, ls, sf, A, B, dm, dv, mout, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+        return mm_bwd_t<double>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+    return mm_bwd_t<float>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

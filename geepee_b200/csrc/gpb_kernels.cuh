@@ -642,20 +642,21 @@ GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nspl
 // =========================================================================
 // Pair table (n-independent): for every unordered pair p=(a>=b)
 //   zh[q][p]  = (z_a + z_b)/2
-//   ep[p]     = log( sf2^2 * exp(-sum_q (z_a-z_b)^2 / (4 l_q^2)) )  (kernels.py:222-226, log domain)
-//   bs[d][p]  = B[d,a,b] + B[d,b,a]  (a != b)   |   B[d,a,a]
+//   ep[p]     = sf2^2 * exp(-sum_q (z_a-z_b)^2 / (4 l_q^2))          (kernels.py:222-226)
+//   bs[d][p]  = ep[p] * ( B[d,a,b] + B[d,b,a]  (a != b)  |  B[d,a,a] )
+// The n-independent factor ep is folded into the contraction weights, so the row loop only
+// forms psi2' = psi2 / ep (one fewer add per pair and row) and the pair sums are rescaled once.
 template <typename T>
 GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double* __restrict__ ls,
                                      const double* __restrict__ sf, const double* __restrict__ B,
                                      int M, int Q, int Qt, int Do, long P, long PP,
                                      T* __restrict__ zh, T* __restrict__ ep, T* __restrict__ bs) {
-    const double sf2 = exp(2.0 * sf[0]);
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < PP;
          p += (long)gridDim.x * blockDim.x) {
         for (int q = Q; q < Qt; q++) zh[(long)q * PP + p] = 0;  // template-padded input dims
-        if (p >= P) {  // padding: exp(lep) underflows to ~1e-308 and every bs is 0
+        if (p >= P) {  // padding pairs: every weight is 0
             for (int q = 0; q < Q; q++) zh[(long)q * PP + p] = 0;
-            ep[p] = (T)(-1.0e5);
+            ep[p] = 0;
             for (int d = 0; d < Do; d++) bs[(long)d * PP + p] = 0;
             continue;
         }
@@ -670,22 +671,21 @@ GPB_KERNEL void mm_pair_table_kernel(const double* __restrict__ z, const double*
             double dz = za - zb;
             e += dz * dz / (4.0 * exp(2.0 * ls[q]));
         }
-        ep[p] = (T)(4.0 * sf[0] - e);   // log(sf2^2) - sum_q dz^2/(4 l^2)
+        const double epv = exp(4.0 * sf[0] - e);   // sf2^2 exp(-sum_q dz^2/(4 l^2))
+        ep[p] = (T)epv;
         for (int d = 0; d < Do; d++) {
             const double* Bd = B + (long)d * M * M;
-            bs[(long)d * PP + p] = (T)(a == b ? Bd[a * M + a] : Bd[a * M + b] + Bd[b * M + a]);
+            bs[(long)d * PP + p] = (T)(epv * (a == b ? Bd[a * M + a] : Bd[a * M + b] + Bd[b * M + a]));
         }
     }
 }
 
-template <int Q, int DOC>
+template <typename T, int Q, int DOC>
 struct MMCfg {
-    // pairs per thread, sized to keep the per-thread pair state in registers
-#ifdef GPB_MM_EXPERIMENT_RP2
-    static constexpr int RP = (2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1;
-#else
-    static constexpr int RP = (2 * Q + 2 * DOC + 2) <= 12 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
-#endif
+    // pairs per thread, sized to keep the per-thread pair state in registers (fp32: twice as many,
+    // the fp32 path is issue bound and the per-row overhead is amortised over the pairs)
+    static constexpr int RP64 = (2 * Q + 2 * DOC + 2) <= 12 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
+    static constexpr int RP = sizeof(T) == 4 ? 2 * RP64 : RP64;
     static constexpr int TR = 32;             // rows per staged tile = lanes per warp
     static constexpr int PC = kThreads * RP;  // pairs per block
 };
@@ -702,62 +702,50 @@ struct MMArgs {
     int n, Qa, Do, d0; // Qa: actual input dims (<= template Q); d0: first output dim of this d-chunk
     long PP;
     int rows_per_split;
-    double* rowacc;    // fwd: [n, Do] += sum_p bs[d,p] psi2[n,p] ; bwd: [n, 1+2Q] += {s, U_q, V_q}
+    double* rowacc;    // fwd: [n, Do] += sum_p bs[d,p] psi2[n,p] ; bwd: [n, 2Q] += {U_q, V_q}
     double* pairpart;  // bwd: [nsplit][DOC+1+Q][PP]: {dBp_d, S0, S1_q}
     int full_coef;     // bwd: 1 -> coefficient sum over ALL Do from bs (generic path when Do > DOC)
     int lam_pass;      // bwd: 1 -> this pass also produces the Lambda-dependent sums
 };
 
-// exp(x) for x <= 0 without the special-case branches of libm and with a short polynomial:
-//   x = (64 k + j) ln2/64 + r,  |r| <= ln2/128   ->   exp(x) = 2^k * 2^(j/64) * P5(r)
-// 2^(j/64) comes from a 64-entry table in shared memory, P5 is the degree-5 Taylor polynomial in
-// Estrin form (relative error 5e-16, checked against libm in tests), the 2^k scaling is an
-// integer add into the exponent field with k clamped at -1021 (deep underflow returns ~1e-308).
-// 12 fp64 instructions instead of ~25 for libm exp.  fp32: the SFU path (ex2.approx).
-#ifndef GPB_CPU_EMU
-__constant__ double c_exp2_tab[64] = {
-#else
-static const double c_exp2_tab[64] = {
-#endif
-    1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00,
-    1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00,
-    1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00,
-    1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00,
-    1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00,
-    1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00,
-    1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00,
-    1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00,
-    1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00,
-    1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00,
-    1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00,
-    1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00,
-    1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00,
-    1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00,
-    1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00,
-    1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
-GPB_DEVICE double exp_neg(double x, const double* __restrict__ tab /* 64 doubles in smem */) {
+// exp() in a pre-scaled domain.  The pair kernel forms xs = S * x directly (S is folded into the
+// per-row constants), so that no multiply is spent on the argument reduction:
+//   fp64: S = 2048/ln2.  xs = 2048 k + j + r, |r| <= 1/2  ->  exp(x) = 2^k * 2^(j/2048) * e^(r ln2/2048).
+//         2^(j/2048) comes from a 16 KB shared-memory table, e^(r h) (h = ln2/2048, |r h| <= 1.7e-4)
+//         from the degree-3 Taylor polynomial (truncation 3.4e-17) folded with the table value:
+//         t + (t r)(c1 + r (c2 + r c3)).  7 fp64 instructions (3 add, 1 mul, 3 fma) instead of ~25
+//         for libm's exp; the 2^k scaling is an integer add into the exponent field with k clamped
+//         at -1021 (deep underflow returns ~1e-308 instead of 0).
+//   fp32: S = log2(e); one SFU instruction (ex2.approx).
+template <typename T> struct ExpDom;
+template <> struct ExpDom<double> {
+    static constexpr int TAB = 2048;
+    static constexpr double S = 2048.0 / 0.693147180559945309417232;
+};
+template <> struct ExpDom<float> {
+    static constexpr int TAB = 1;
+    static constexpr double S = 1.4426950408889634074;
+};
+GPB_DEVICE double exp_dom(double xs, const double* __restrict__ tab /* 2048 doubles in smem */) {
+    constexpr double h = 0.693147180559945309417232 / 2048.0;
+    constexpr double c1 = h, c2 = h * h / 2.0, c3 = h * h * h / 6.0;
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    double kd = x * 92.332482616893656877 + magic;          // 64 / ln 2
+    double kd = xs + magic;
 #ifndef GPB_CPU_EMU
-    int n = __double2loint(kd);
+    const int n = __double2loint(kd);
 #else
     int64_t bits;
     memcpy(&bits, &kd, 8);
-    int n = (int)(int32_t)(bits & 0xffffffff);
+    const int n = (int)(int32_t)(bits & 0xffffffff);
 #endif
     kd -= magic;
-    double r = kd * -0.01083042469326756 + x;               // ln2/64, high part (21 trailing zero bits)
-    r = kd * -2.9815858269852933e-12 + r;                   // ln2/64, low part
-    const double t = tab[n & 63];
-    int k = n >> 6;
-    const double r2 = r * r;
-    const double p01 = 1.0 + r;
-    const double p23 = r * 1.6666666666666666e-01 + 0.5;
-    const double p45 = r * 8.333333333333333e-03 + 4.1666666666666664e-02;
-    const double r4 = r2 * r2;
-    double p = p23 * r2 + p01;
-    p = p45 * r4 + p;
-    p *= t;
+    const double r = xs - kd;                 // exact, |r| <= 1/2
+    const double t = tab[n & 2047];
+    const double u = t * r;
+    double q = c3 * r + c2;
+    q = q * r + c1;
+    const double p = u * q + t;
+    int k = n >> 11;
     k = k < -1021 ? -1021 : k;
 #ifndef GPB_CPU_EMU
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
@@ -765,7 +753,15 @@ GPB_DEVICE double exp_neg(double x, const double* __restrict__ tab /* 64 doubles
     return ldexp(p, k);
 #endif
 }
-GPB_DEVICE float exp_neg(float x, const double*) { return fast_exp(x); }
+GPB_DEVICE float exp_dom(float xs, const double*) {
+#ifndef GPB_CPU_EMU
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xs));
+    return y;
+#else
+    return exp2f(xs);
+#endif
+}
 
 // Running warp-transpose reduction.  Row r (0..31) of a tile contributes NS per-lane partial sums;
 // after the 32nd push lane L holds the NS sums of row L added over all 32 lanes.  Pending partial
@@ -783,9 +779,13 @@ struct RowCascade {
             out[s] = keep + shfl_xor(send, bit);
         }
     }
-    // returns true when `v` holds the finished sums of rows (r-31 .. r), i.e. after r == 31
-    GPB_MEMBER bool push(int r, int lane, T (&v)[NS]) {
-        if ((r & 1) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l0[s] = v[s]; return false; }
+    GPB_MEMBER void push_even(T (&v)[NS]) {
+        GPB_UNROLL
+        for (int s = 0; s < NS; s++) l0[s] = v[s];
+    }
+    // second row of a pair (r odd); returns true when `v` holds the finished sums of rows
+    // (r-31 .. r), i.e. after r == 31
+    GPB_MEMBER bool push_odd(int r, int lane, T (&v)[NS]) {
         merge(l0, v, 1, lane, v);
         if ((r & 2) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l1[s] = v[s]; return false; }
         merge(l1, v, 2, lane, v);
@@ -801,44 +801,53 @@ struct RowCascade {
 
 // a2+a6 (forward) / a2+a9 (backward) over unordered pairs.  Each thread owns RP pairs for
 // the whole kernel (their constants and accumulators live in registers); rows are staged
-// 32 at a time in shared memory and broadcast.  psi2[n,p] = cn[n] * ep[p] *
-// exp(-sum_q (mu_nq - zh_pq)^2 c2_nq) is formed in registers and consumed immediately:
-// the N x M x M tensor never exists in memory.
-//   forward : rowacc[n,d]  += sum_p bs[d,p] psi2[n,p]                   (aep_models.py:196-198)
-//   backward: Lam[n,p] = (sum_d dv[n,d] bs[d,p]) psi2[n,p]              (aep_models.py:243, kernels.py:415-419)
-//             rowacc[n,:]  += {sum_p Lam, sum_p Lam zh_q, sum_p Lam zh_q^2}
-//             pair sums     : dBp[d,p] = sum_n dv[n,d] psi2[n,p]         (aep_models.py:240)
-//                             S0[p] = sum_n Lam ; S1[p,q] = sum_n Lam c2_nq (mu_nq - zh_pq)
+// 32 at a time in shared memory as one 16-byte aligned record per row and broadcast.
+// psi2'[n,p] = cn[n] exp(-sum_q (mu_nq - zh_pq)^2 c2_nq)  (= psi2 / ep[p]) is formed in registers
+// and consumed immediately: the N x M x M tensor never exists in memory.
+//   forward : rowacc[n,d]  += sum_p bs[d,p] psi2'[n,p]                  (aep_models.py:196-198)
+//   backward: Lam[n,p] = (sum_d dv[n,d] bs[d,p]) psi2'[n,p]             (aep_models.py:243, kernels.py:415-419)
+//             rowacc[n,:]  += {sum_p Lam zh_q, sum_p Lam zh_q^2}
+//               (sum_p Lam itself equals sum_d dv[n,d] * forward rowacc[n,d]: not recomputed)
+//             pair sums     : dBp[d,p] = ep[p] sum_n dv[n,d] psi2'[n,p]  (aep_models.py:240)
+//                             S0[p] = sum_n Lam = sum_d bs[d,p] sum_n dv[n,d] psi2'  (from the dBp sums)
+//                             S1[p,q] = sum_n Lam c2_nq (mu_nq - zh_pq)
+// The exponent is formed in the ExpDom<T>-scaled domain.  fp64 forward uses the expanded form
+// xs = a0_n + sum_q (b_nq zh_pq + c_nq zh_pq^2) (2Q fma); the backward needs c2 (mu - zh) anyway.
+// Two rows are processed per loop trip when Q <= 4 (independent dependency chains for the fp64 pipe).
 // The per-row sums are reduced over the warp by RowCascade, over the 8 warps through shared
 // memory, and over the pair chunks (blocks) by one fp64 atomic per value.
 // GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
 // GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
 template <typename T, int Q, int DOC, bool BWD, bool GEN>
-#ifdef GPB_MM_EXPERIMENT_RP2
-GPB_KERNEL void __launch_bounds__(256, 2) mm_pairs_kernel(MMArgs<T> a) {
-#else
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
-#endif
-    typedef MMCfg<Q, DOC> C;
+    typedef MMCfg<T, Q, DOC> C;
     constexpr int RP = C::RP, TR = C::TR;
-    constexpr int NS = BWD ? (1 + 2 * Q) : DOC;
+    constexpr int NS = BWD ? 2 * Q : DOC;
     constexpr bool kGen = BWD && GEN;
+    constexpr bool kExpand = !BWD && sizeof(T) == 8;
+    constexpr int VW = 16 / (int)sizeof(T);
+    constexpr int RLraw = 1 + 2 * Q + (BWD ? DOC : 0);
+    constexpr int RL = (RLraw + VW - 1) / VW * VW;       // row record length (16-byte multiple)
+    constexpr int kTab = ExpDom<T>::TAB;
+    constexpr bool kTwoRows = Q <= 4;   // wide inputs: one row per trip (register budget)
+    constexpr double kS = ExpDom<T>::S;
     // Row tiles are double buffered (tile t+1 is staged while tile t is consumed) and so is the
     // cross-warp staging of the row sums, which leaves ONE barrier per tile.  For wide inputs the
     // staging would not fit the static 48 KB; then every warp issues its own atomics.
-    constexpr bool WARP_ATOMICS = (2 * 8 * TR * NS * sizeof(T) + 4 * TR * Q * sizeof(T) + (kGen ? TR * 64 * 8 : 0)) > 40 * 1024;
-    GPB_SHARED T s_mu[2][TR * Q], s_c2[2][TR * Q], s_lcn[2][TR];
-    GPB_SHARED T s_dv[2][TR * DOC];
+    constexpr int kBufs = kGen ? 1 : 2;   // the generic path restages in place
+    constexpr size_t kFixed = kBufs * TR * RL * sizeof(T) + kTab * 8 + (kGen ? TR * 64 * 8 : 8) + Q * 8;
+    constexpr bool WARP_ATOMICS = kFixed + 2 * 8 * TR * NS * sizeof(T) > 46 * 1024;
+    GPB_SHARED GPB_ALIGN16 T s_rec[kBufs][TR * RL];
     GPB_SHARED double s_dvall[kGen ? TR * 64 : 1];  // generic path (single buffered): all Do (<= 64) per row
-    GPB_SHARED T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
+    GPB_SHARED GPB_ALIGN16 T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
     GPB_SHARED double s_l2[Q];
-    GPB_SHARED double s_exp2[64];
+    GPB_SHARED double s_tab[kTab];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long pbase = (long)blockIdx.x * C::PC;
     const long PP = a.PP;
     const int Do = a.Do;
 
-    T zh[RP][Q], zh2[RP][Q], lep[RP], bs[RP][DOC];
+    T zh[RP][Q], zh2[RP][Q], bs[RP][DOC];
     T accB[RP][DOC], accS0[RP], accS1[RP][Q];
     GPB_UNROLL
     for (int j = 0; j < RP; j++) {
@@ -848,7 +857,6 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
             zh[j][q] = a.zh[(long)q * PP + p];
             zh2[j][q] = zh[j][q] * zh[j][q];
         }
-        lep[j] = a.ep[p];
         GPB_UNROLL
         for (int d = 0; d < DOC; d++) {
             bs[j][d] = (a.d0 + d < Do) ? a.bs[(long)(a.d0 + d) * PP + p] : (T)0;
@@ -859,18 +867,22 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         for (int q = 0; q < Q; q++) accS1[j][q] = 0;
     }
     if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
-    if (tid >= 64 && tid < 128) s_exp2[tid - 64] = c_exp2_tab[tid - 64];
+    if (kTab > 1)
+        for (int i = tid; i < kTab; i += kThreads) s_tab[i] = exp2((double)i * (1.0 / kTab));
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
 
     // stage one tile: 4 lanes of every warp take one row each (spreads the fp64 div/sqrt/log
     // evenly over the warps).  c2 = 1/(2S + l^2); lcn = sum_q log sqrt(l^2 c2)  (kernels.py:188-190)
+    // record: [0] = kS lcn, then (mu_q, kS c2_q), then dv_d -- or, expanded forward:
+    //         [0] = kS (lcn - sum c2 mu^2), then (2 kS c2_q mu_q, -kS c2_q)
     auto stage = [&](int buf, int t0) {
         if (lane < 4) {
             const int row = warp * 4 + lane;
             const bool ok = (t0 + row) < r_end;
-            double lcn = 0.0;
+            T* rec = &s_rec[kGen ? 0 : buf][row * RL];
+            double lcn = 0.0, a0 = 0.0;
             for (int q = 0; q < Q; q++) {
                 double mu = 0, c2 = 0;
                 if (ok && q < a.Qa) {
@@ -879,14 +891,21 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                     c2 = 1.0 / (2.0 * a.vx[(long)(t0 + row) * a.Qa + q] + lq);
                     lcn += 0.5 * log(lq * c2);
                 }
-                s_mu[buf][row * Q + q] = (T)mu;
-                s_c2[buf][row * Q + q] = (T)c2;
+                const double c2s = c2 * kS;
+                if (kExpand) {
+                    rec[1 + q] = (T)(2.0 * c2s * mu);
+                    rec[1 + Q + q] = (T)(-c2s);
+                    a0 -= c2s * mu * mu;
+                } else {
+                    rec[1 + q] = (T)mu;
+                    rec[1 + Q + q] = (T)c2s;
+                }
             }
-            // rows past the end: psi2 = exp(-1e5 + ...) ~ 1e-308 and their dv is 0
-            s_lcn[buf][row] = ok ? (T)lcn : (T)(-1.0e5);
+            // rows past the end: psi2' = exp(-1e5 + ...) ~ 0 (1e-308 in fp64) and their dv is 0
+            rec[0] = (T)((ok ? lcn : -1.0e5) * kS + a0);
             if (BWD) {
                 for (int d = 0; d < DOC; d++)
-                    s_dv[buf][row * DOC + d] =
+                    rec[1 + 2 * Q + d] =
                         (ok && a.d0 + d < Do) ? (T)a.dv[(long)(t0 + row) * Do + a.d0 + d] : (T)0;
                 if (kGen && a.full_coef)
                     for (int d = 0; d < Do; d++)
@@ -910,28 +929,32 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         }
         RowCascade<T, NS> casc;
         T fin[NS];
-        GPB_UNROLL_N(1)
-        for (int r = 0; r < TR; r++) {
-            T mu[Q], c2[Q], v[NS];
+        // one row against this thread's RP pairs; v = this thread's part of the row sums
+        auto row_body = [&](int r, T (&v)[NS]) {
+            T rc[RL];
             GPB_UNROLL
-            for (int q = 0; q < Q; q++) {
-                mu[q] = s_mu[buf][r * Q + q];
-                c2[q] = s_c2[buf][r * Q + q];
-            }
+            for (int k = 0; k < RL; k++) rc[k] = s_rec[kGen ? 0 : buf][r * RL + k];
             GPB_UNROLL
             for (int s = 0; s < NS; s++) v[s] = 0;
-            const T lcn = s_lcn[buf][r];
             GPB_UNROLL
             for (int j = 0; j < RP; j++) {
-                // x = lep + lcn - sum_q c2 (mu - zh)^2  (log-domain psi2, as kernels.py:222-227)
-                T x = lep[j] + lcn, t[Q];
-                GPB_UNROLL
-                for (int q = 0; q < Q; q++) {
-                    T diff = mu[q] - zh[j][q];
-                    t[q] = diff * c2[q];
-                    x -= t[q] * diff;
+                T x = rc[0], t[Q];
+                if (kExpand) {
+                    GPB_UNROLL
+                    for (int q = 0; q < Q; q++) {
+                        x += rc[1 + q] * zh[j][q];
+                        x += rc[1 + Q + q] * zh2[j][q];
+                        t[q] = 0;
+                    }
+                } else {
+                    GPB_UNROLL
+                    for (int q = 0; q < Q; q++) {
+                        const T diff = rc[1 + q] - zh[j][q];
+                        t[q] = diff * rc[1 + Q + q];
+                        x -= t[q] * diff;
+                    }
                 }
-                const T psi2 = exp_neg(x, s_exp2);
+                const T psi2 = exp_dom(x, s_tab);
                 if (!BWD) {
                     GPB_UNROLL
                     for (int d = 0; d < DOC; d++) v[d] += bs[j][d] * psi2;
@@ -939,7 +962,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                     T coef = 0;
                     GPB_UNROLL
                     for (int d = 0; d < DOC; d++) {
-                        const T dvd = s_dv[buf][r * DOC + d];
+                        const T dvd = rc[1 + 2 * Q + d];
                         accB[j][d] += dvd * psi2;
                         coef += dvd * bs[j][d];
                     }
@@ -951,20 +974,40 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                                 coef += (T)s_dvall[r * 64 + d] * a.bs[(long)d * PP + p];
                         }
                         const T lam = coef * psi2;
-                        accS0[j] += lam;
-                        v[0] += lam;
+                        if (kGen) accS0[j] += lam;
                         GPB_UNROLL
                         for (int q = 0; q < Q; q++) {
                             accS1[j][q] += lam * t[q];
-                            v[1 + q] += lam * zh[j][q];
-                            v[1 + Q + q] += lam * zh2[j][q];
+                            v[q] += lam * zh[j][q];
+                            v[Q + q] += lam * zh2[j][q];
                         }
                     }
                 }
             }
-            if (casc.push(r, lane, v)) {
-                GPB_UNROLL
-                for (int s = 0; s < NS; s++) fin[s] = v[s];
+        };
+        if (kTwoRows) {
+            GPB_UNROLL_N(1)
+            for (int rr = 0; rr < TR / 2; rr++) {
+                T v0[NS], v1[NS];
+                row_body(2 * rr, v0);
+                row_body(2 * rr + 1, v1);
+                casc.push_even(v0);
+                if (casc.push_odd(2 * rr + 1, lane, v1)) {
+                    GPB_UNROLL
+                    for (int s = 0; s < NS; s++) fin[s] = v1[s];
+                }
+            }
+        } else {
+            GPB_UNROLL_N(1)
+            for (int r = 0; r < TR; r++) {
+                T v[NS];
+                row_body(r, v);
+                if ((r & 1) == 0) {
+                    casc.push_even(v);
+                } else if (casc.push_odd(r, lane, v)) {
+                    GPB_UNROLL
+                    for (int s = 0; s < NS; s++) fin[s] = v[s];
+                }
             }
         }
         // lane L now holds row L's sums over this warp's pairs: add the 8 warps, then one atomic
@@ -1004,11 +1047,16 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         GPB_UNROLL
         for (int j = 0; j < RP; j++) {
             const long p = pbase + j * kThreads + tid;
+            const double epv = (double)a.ep[p];
+            double s0 = (double)accS0[j];
             GPB_UNROLL
-            for (int d = 0; d < DOC; d++) rec[(long)d * PP + p] = (double)accB[j][d];
-            rec[(long)DOC * PP + p] = (double)accS0[j];
+            for (int d = 0; d < DOC; d++) {
+                rec[(long)d * PP + p] = epv * (double)accB[j][d];
+                if (!kGen) s0 += (double)bs[j][d] * (double)accB[j][d];
+            }
+            rec[(long)DOC * PP + p] = s0;
             GPB_UNROLL
-            for (int q = 0; q < Q; q++) rec[(long)(DOC + 1 + q) * PP + p] = (double)accS1[j][q];
+            for (int q = 0; q < Q; q++) rec[(long)(DOC + 1 + q) * PP + p] = (double)accS1[j][q] * (1.0 / kS);
         }
     }
 }
@@ -1061,7 +1109,7 @@ GPB_KERNEL void mm_psi1_fwd_kernel(const double* __restrict__ mx, const double* 
 }
 
 // Backward, row-wise part: finishes dmx, dvx per row from the psi1 terms
-// (kernels.py:355-378) and the reduced psi2 sums {s, U, V} (kernels.py:419-431),
+// (kernels.py:355-378) and the reduced psi2 sums {s = dv . vacc, U, V} (kernels.py:419-431),
 // and emits per-block partials of the row-summed hyper terms:
 //   part[blk][0]      : dsf2  = sum_n (sum_m L1 + 2 s_n)/sf2
 //   part[blk][1+q]    : dl_q  (psi1: Zmu2_denom.. , psi2: the n-dependent terms of kernels.py:441-442)
@@ -1071,7 +1119,8 @@ GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* 
                                    const double* __restrict__ z, const double* __restrict__ ls,
                                    const double* __restrict__ sf, const double* __restrict__ A,
                                    const double* __restrict__ dm, const double* __restrict__ dv,
-                                   const double* __restrict__ mout, const double* __restrict__ rowacc,
+                                   const double* __restrict__ mout, const double* __restrict__ vacc,
+                                   const double* __restrict__ rowacc,
                                    int n, int M, int Q, int Qt, int Do, double* __restrict__ dmx,
                                    double* __restrict__ dvx, double* __restrict__ part) {
     GPB_DYN_SMEM(smem);
@@ -1095,7 +1144,7 @@ GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* 
     // -> keep a small per-thread array via second sweep over q (cheap: per row, not per m)
     double p_dl[16];
     for (int q = 0; q < 16; q++) p_dl[q] = 0;
-    const int NS = 1 + 2 * Qt;
+    const int NS = 2 * Qt;
     for (long row = (long)blockIdx.x * nt + tid; row < n; row += (long)gridDim.x * nt) {
         double cn = 1.0;
         for (int q = 0; q < Q; q++) {
@@ -1107,10 +1156,12 @@ GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* 
             s_dmu[q * nt + tid] = 0;
             s_dS[q * nt + tid] = 0;
         }
+        double s = 0;   // sum_p Lam = sum_d dv_d * (forward sum_p bs[d,p] psi2[n,p])
         for (int d = 0; d < Do; d++) {
             double dvd = dv[row * Do + d];
             s_dma[d * nt + tid] = dm[row * Do + d] - 2.0 * dvd * mout[row * Do + d];
             p_dvsum += dvd;
+            s += dvd * vacc[row * Do + d];
         }
         double L1sum = 0;
         for (int m = 0; m < M; m++) {
@@ -1131,14 +1182,13 @@ GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* 
                 s_dS[q * nt + tid] += L1 * (zm * zm * c - 1.0) * c;   // x 1/2 below
             }
         }
-        const double s = rowacc[row * NS];
         p_sf2 += (L1sum + 2.0 * s) / sf2;
         for (int q = 0; q < Q; q++) {
             const double l = exp(ls[q]), lq = l * l;
             const double S = vx[row * Q + q], mu = s_mu[q * nt + tid];
             const double c1 = s_c1[q * nt + tid];
             const double c2 = 1.0 / (2.0 * S + lq);
-            const double U = rowacc[row * NS + 1 + q], V = rowacc[row * NS + 1 + Qt + q];
+            const double U = rowacc[row * NS + q], V = rowacc[row * NS + Qt + q];
             // psi1: sum_m L1 ((z-mu)^2 c1 + S/l^2) c1 l  =  (dS_acc + (1 + S/l^2) L1sum c1) l
             double dl1 = (s_dS[q * nt + tid] + (1.0 + S / lq) * c1 * L1sum) * l;
             // psi2 (n-dependent part of kernels.py:441-442)

@@ -264,16 +264,16 @@ class Base_SGP_Layer(object):
         """a6 on the device."""
         t = self._t
         A, B = self._AB(cav, True)
-        m, v = ops.mm_fwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous())
-        return m, v, (mx, vx, cav, m)
+        m, v, vacc = ops.mm_fwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous())
+        return m, v, (mx, vx, cav, m, vacc)
 
     def _bwd_mm(self, ctx, dm, dv):
         """a9 per-row part: statistics + per-row input gradients."""
         t = self._t
-        mx, vx, cav, mout = ctx
+        mx, vx, cav, mout, vacc = ctx
         A, B = self._AB(cav, True)
         return ops.mm_bwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous(),
-                          dm, dv, mout)
+                          dm, dv, mout, vacc)
 
     # ---- shared chain rules ------------------------------------------------------------------
     def _pack_eta1(self, dtheta1):
@@ -483,9 +483,10 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         return {k: g.cpu().numpy() for k, g in self._tail_det(st, alpha).items()}
 
     def backprop_grads_lvm_mm(self, m, v, dm, dv, psi1, psi2, mx, vx, alpha=1.0):
-        """aep_models.py:202-304.  psi1 / psi2 are regenerated on chip; arguments ignored."""
+        """aep_models.py:202-304.  psi1 / psi2 (and m, v: the caller's v may already carry the
+        likelihood's in-place noise term, lik_layers.py:121) are regenerated on chip."""
         dev = self.device
-        ctx = (to_dev(mx, dev), to_dev(vx, dev), True, to_dev(m, dev))
+        _, _, ctx = self._fwd_mm(to_dev(mx, dev), to_dev(vx, dev), cav=True)
         st = self._bwd_mm(ctx, to_dev(dm, dev), to_dev(dv, dev))
         gh = {k: g.cpu().numpy() for k, g in self._tail_mm(st, alpha).items()}
         return gh, {'mx': st['dmx'].cpu().numpy(), 'vx': st['dvx'].cpu().numpy()}
@@ -533,7 +534,7 @@ class VFE_SGP_Layer(Base_SGP_Layer):
     def backprop_grads_lvm_mm(self, m, v, dm, dv, psi1, psi2, mx, vx):
         """vfe_models.py:328-401."""
         dev = self.device
-        ctx = (to_dev(mx, dev), to_dev(vx, dev), False, to_dev(m, dev))
+        _, _, ctx = self._fwd_mm(to_dev(mx, dev), to_dev(vx, dev), cav=False)
         st = self._bwd_mm(ctx, to_dev(dm, dev), to_dev(dv, dev))
         gh = {k: g.cpu().numpy() for k, g in self._tail(st, True).items()}
         return gh, {'mx': st['dmx'].cpu().numpy(), 'vx': st['dvx'].cpu().numpy()}

@@ -158,21 +158,24 @@ def det_syrk(prec, Ks, dv, M):
 
 
 def mm_fwd(prec, mx, vx, z, ls, sf, A, B):
-    """aep_models.py:183-199 / base_models.py:286-307; psi2 stays on chip."""
+    """aep_models.py:183-199 / base_models.py:286-307; psi2 stays on chip.
+    Returns mout, vout and vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b] (reused by mm_bwd)."""
     lib = _lib.get()
     n, Q = mx.shape
     Do, M = A.shape
     mout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
     vout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
+    vacc = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
     ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 0), mx)
     _chk(lib.gpb_mm_fwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
-                        _p(_c(B)), n, M, Q, Do, _p(mout), _p(vout), _p(ws), ws.numel(),
+                        _p(_c(B)), n, M, Q, Do, _p(mout), _p(vout), _p(vacc), _p(ws), ws.numel(),
                         _stream(mx)), 'mm_fwd')
-    return mout, vout
+    return mout, vout, vacc
 
 
-def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout):
-    """aep_models.py:238-250 + kernels.py:302-309,355-378,402-444."""
+def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc):
+    """aep_models.py:238-250 + kernels.py:302-309,355-378,402-444.
+    mout, vacc: outputs of mm_fwd on the same inputs and the same B."""
     lib = _lib.get()
     n, Q = mx.shape
     Do, M = A.shape
@@ -190,7 +193,7 @@ def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout):
     }
     ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 1), mx)
     _chk(lib.gpb_mm_bwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
-                        _p(_c(B)), _p(_c(dm)), _p(_c(dv)), _p(_c(mout)), n, M, Q, Do,
+                        _p(_c(B)), _p(_c(dm)), _p(_c(dv)), _p(_c(mout)), _p(_c(vacc)), n, M, Q, Do,
                         _p(out['dA']), _p(out['dB']), _p(out['dzu']), _p(out['dl']), _p(out['dsf2']),
                         _p(out['dvsum']), _p(out['dmx']), _p(out['dvx']), _p(ws), ws.numel(),
                         _stream(mx)), 'mm_bwd')
