@@ -406,6 +406,12 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    # Native libraries (NCCL's version banner, ...) write to fd 1 behind Python's back; the contract
+    # is ONE JSON line on stdout, so fd 1 is pointed at stderr and Python keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w')
     if args.impl == 'reference':
         run_reference(args, w)
     else:

@@ -87,29 +87,50 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
     return w;
 }
 
+// The fp64 pair kernels keep the replicated exp table in dynamic shared memory; together with
+// their static buffers they exceed the 48 KB a kernel gets without opting in.
+template <typename K>
+int mm_pairs_smem(K kern, size_t dyn) {
+#ifndef GPB_CPU_EMU
+    if (dyn == 0) return GPB_OK;
+    static K done = nullptr;   // one static per kernel instantiation
+    if (done == kern) return GPB_OK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return fail(GPB_ERR_CUDA, "mm_pairs: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    done = kern;
+#else
+    (void)kern; (void)dyn;
+#endif
+    return GPB_OK;
+}
+
 template <typename T, int Q, int DOC, bool BWD>
-void mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
+int mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
+    const size_t smem = sizeof(double) * gpb::ExpDom<T>::TAB;
     prof_begin(BWD ? 4 : 3, stream);
     if constexpr (BWD && DOC == 4) {
         if (p.npass > 1) {   // Do > 4: generic multi-pass kernel
             auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, true>;
-            GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+            if (mm_pairs_smem(kern, smem)) return GPB_ERR_CUDA;
+            GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), smem, stream, a);
             prof_end(4, stream);
-            return;
+            return GPB_OK;
         }
     }
     {
         auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, false>;
-        GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), 0, stream, a);
+        if (mm_pairs_smem(kern, smem)) return GPB_ERR_CUDA;
+        GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), smem, stream, a);
     }
     prof_end(BWD ? 4 : 3, stream);
+    return GPB_OK;
 }
 template <typename T, int Q, bool BWD>
 int mm_pairs_doc(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
     switch (p.DOC) {
-        case 1: mm_pairs_launch<T, Q, 1, BWD>(p, a, stream); return GPB_OK;
-        case 2: mm_pairs_launch<T, Q, 2, BWD>(p, a, stream); return GPB_OK;
-        case 4: mm_pairs_launch<T, Q, 4, BWD>(p, a, stream); return GPB_OK;
+        case 1: return mm_pairs_launch<T, Q, 1, BWD>(p, a, stream);
+        case 2: return mm_pairs_launch<T, Q, 2, BWD>(p, a, stream);
+        case 4: return mm_pairs_launch<T, Q, 4, BWD>(p, a, stream);
     }
     return fail(GPB_ERR_ARG, "mm: bad DOC %d", p.DOC);
 }

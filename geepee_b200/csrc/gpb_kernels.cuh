@@ -710,57 +710,85 @@ struct MMArgs {
 
 // exp() in a pre-scaled domain.  The pair kernel forms xs = S * x directly (S is folded into the
 // per-row constants), so that no multiply is spent on the argument reduction:
-//   fp64: S = 2048/ln2.  xs = 2048 k + j + r, |r| <= 1/2  ->  exp(x) = 2^k * 2^(j/2048) * e^(r ln2/2048).
-//         2^(j/2048) comes from a 16 KB shared-memory table, e^(r h) (h = ln2/2048, |r h| <= 1.7e-4)
-//         from the degree-3 Taylor polynomial (truncation 3.4e-17) folded with the table value:
-//         t + (t r)(c1 + r (c2 + r c3)).  7 fp64 instructions (3 add, 1 mul, 3 fma) instead of ~25
-//         for libm's exp; the 2^k scaling is an integer add into the exponent field with k clamped
-//         at -1021 (deep underflow returns ~1e-308 instead of 0).
+//   fp64: S = 256/ln2.  xs = 256 k + j + r, |r| <= 1/2  ->  exp(x) = 2^k * 2^(j/256) * e^(r ln2/256).
+//         2^(j/256) comes from a shared-memory table that is replicated 16 times (32 KB): lane l
+//         reads copy l mod 16, so the data-dependent lookups of a half warp always fall into 16
+//         different 8-byte banks (the un-replicated 2048-entry table of v9 spent 6 wavefronts per
+//         lookup on bank conflicts and made the kernel shared-memory bound; ncu, profiles/).
+//         e^(r h) (h = ln2/256, |r h| <= 1.36e-3) is the degree-4 Taylor polynomial (truncation
+//         3.8e-17) folded with the table value: t + (t r)(c1 + r (c2 + r (c3 + r c4))).
+//         8 fp64 instructions (3 add, 1 mul, 4 fma) instead of ~25 for libm's exp; the 2^k scaling
+//         is an integer add into the exponent field with k clamped at -1021 (deep underflow returns
+//         ~1e-308 instead of 0).
 //   fp32: S = log2(e); one SFU instruction (ex2.approx).
+// exp_dom_n evaluates N independent arguments in lock step (stage by stage), which is what lets
+// the fp64 pipe overlap the 8-deep dependency chains of different pairs / rows.
 template <typename T> struct ExpDom;
 template <> struct ExpDom<double> {
-    static constexpr int TAB = 2048;
-    static constexpr double S = 2048.0 / 0.693147180559945309417232;
+    static constexpr int ENT = 256, REP = 16;
+    static constexpr int TAB = ENT * REP;                 // doubles of dynamic shared memory
+    static constexpr double S = 256.0 / 0.693147180559945309417232;
 };
 template <> struct ExpDom<float> {
-    static constexpr int TAB = 1;
+    static constexpr int ENT = 0, REP = 0, TAB = 0;
     static constexpr double S = 1.4426950408889634074;
 };
-GPB_DEVICE double exp_dom(double xs, const double* __restrict__ tab /* 2048 doubles in smem */) {
-    constexpr double h = 0.693147180559945309417232 / 2048.0;
-    constexpr double c1 = h, c2 = h * h / 2.0, c3 = h * h * h / 6.0;
+template <int N>
+GPB_DEVICE void exp_dom_n(double (&x)[N], const double* __restrict__ tab, int lane16) {
+    constexpr double h = 0.693147180559945309417232 / 256.0;
+    constexpr double c1 = h, c2 = h * h / 2.0, c3 = h * h * h / 6.0, c4 = h * h * h * h / 24.0;
     const double magic = 6755399441055744.0;  // 1.5 * 2^52
-    double kd = xs + magic;
+    double kd[N], t[N], q[N];
+    int n[N];
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) kd[i] = x[i] + magic;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
 #ifndef GPB_CPU_EMU
-    const int n = __double2loint(kd);
+        n[i] = __double2loint(kd[i]);
 #else
-    int64_t bits;
-    memcpy(&bits, &kd, 8);
-    const int n = (int)(int32_t)(bits & 0xffffffff);
+        int64_t bits;
+        memcpy(&bits, &kd[i], 8);
+        n[i] = (int)(int32_t)(bits & 0xffffffff);
 #endif
-    kd -= magic;
-    const double r = xs - kd;                 // exact, |r| <= 1/2
-    const double t = tab[n & 2047];
-    const double u = t * r;
-    double q = c3 * r + c2;
-    q = q * r + c1;
-    const double p = u * q + t;
-    int k = n >> 11;
-    k = k < -1021 ? -1021 : k;
+        t[i] = tab[((n[i] & 255) << 4) + lane16];
+    }
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) kd[i] -= magic;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) x[i] -= kd[i];             // r: exact, |r| <= 1/2
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = c4 * x[i] + c3;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = q[i] * x[i] + c2;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = q[i] * x[i] + c1;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) kd[i] = t[i] * x[i];
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
+        const double p = kd[i] * q[i] + t[i];
+        int k = n[i] >> 8;
+        k = k < -1021 ? -1021 : k;
 #ifndef GPB_CPU_EMU
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+        x[i] = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 #else
-    return ldexp(p, k);
+        x[i] = ldexp(p, k);
 #endif
+    }
 }
-GPB_DEVICE float exp_dom(float xs, const double*) {
+template <int N>
+GPB_DEVICE void exp_dom_n(float (&x)[N], const double*, int) {
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
 #ifndef GPB_CPU_EMU
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xs));
-    return y;
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x[i]));
+        x[i] = y;
 #else
-    return exp2f(xs);
+        x[i] = exp2f(x[i]);
 #endif
+    }
 }
 
 // Running warp-transpose reduction.  Row r (0..31) of a tile contributes NS per-lane partial sums;
@@ -829,19 +857,20 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     constexpr int RLraw = 1 + 2 * Q + (BWD ? DOC : 0);
     constexpr int RL = (RLraw + VW - 1) / VW * VW;       // row record length (16-byte multiple)
     constexpr int kTab = ExpDom<T>::TAB;
-    constexpr bool kTwoRows = Q <= 4;   // wide inputs: one row per trip (register budget)
+    constexpr int NR = Q <= 4 ? 2 : 1;  // rows per loop trip (wide inputs: one, register budget)
     constexpr double kS = ExpDom<T>::S;
     // Row tiles are double buffered (tile t+1 is staged while tile t is consumed) and so is the
     // cross-warp staging of the row sums, which leaves ONE barrier per tile.  For wide inputs the
     // staging would not fit the static 48 KB; then every warp issues its own atomics.
     constexpr int kBufs = kGen ? 1 : 2;   // the generic path restages in place
-    constexpr size_t kFixed = kBufs * TR * RL * sizeof(T) + kTab * 8 + (kGen ? TR * 64 * 8 : 8) + Q * 8;
+    constexpr size_t kFixed = kBufs * TR * RL * sizeof(T) + (kGen ? TR * 64 * 8 : 8) + Q * 8;   // static
     constexpr bool WARP_ATOMICS = kFixed + 2 * 8 * TR * NS * sizeof(T) > 46 * 1024;
     GPB_SHARED GPB_ALIGN16 T s_rec[kBufs][TR * RL];
     GPB_SHARED double s_dvall[kGen ? TR * 64 : 1];  // generic path (single buffered): all Do (<= 64) per row
     GPB_SHARED GPB_ALIGN16 T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
     GPB_SHARED double s_l2[Q];
-    GPB_SHARED double s_tab[kTab];
+    GPB_DYN_SMEM(dsm);                               // fp64: the replicated exp table (32 KB)
+    double* s_tab = (double*)dsm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long pbase = (long)blockIdx.x * C::PC;
     const long PP = a.PP;
@@ -867,8 +896,10 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         for (int q = 0; q < Q; q++) accS1[j][q] = 0;
     }
     if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
-    if (kTab > 1)
-        for (int i = tid; i < kTab; i += kThreads) s_tab[i] = exp2((double)i * (1.0 / kTab));
+    if (kTab > 0)
+        for (int i = tid; i < kTab; i += kThreads)
+            s_tab[i] = exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
+    const int lane16 = lane & 15;
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
@@ -929,85 +960,94 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         }
         RowCascade<T, NS> casc;
         T fin[NS];
-        // one row against this thread's RP pairs; v = this thread's part of the row sums
-        auto row_body = [&](int r, T (&v)[NS]) {
-            T rc[RL];
+        // NR rows against this thread's RP pairs; v[i] = this thread's part of the sums of row r0+i.
+        // All NR*RP exponents are formed first, then exponentiated in lock step, then consumed.
+        auto rows_body = [&](int r0, T (&v)[NR][NS]) {
+            T rc[NR][RL], x[NR * RP], t[NR][RP][Q];
             GPB_UNROLL
-            for (int k = 0; k < RL; k++) rc[k] = s_rec[kGen ? 0 : buf][r * RL + k];
+            for (int i = 0; i < NR; i++) {
+                GPB_UNROLL
+                for (int k = 0; k < RL; k++) rc[i][k] = s_rec[kGen ? 0 : buf][(r0 + i) * RL + k];
+                GPB_UNROLL
+                for (int s = 0; s < NS; s++) v[i][s] = 0;
+            }
             GPB_UNROLL
-            for (int s = 0; s < NS; s++) v[s] = 0;
-            GPB_UNROLL
-            for (int j = 0; j < RP; j++) {
-                T x = rc[0], t[Q];
-                if (kExpand) {
-                    GPB_UNROLL
-                    for (int q = 0; q < Q; q++) {
-                        x += rc[1 + q] * zh[j][q];
-                        x += rc[1 + Q + q] * zh2[j][q];
-                        t[q] = 0;
-                    }
-                } else {
-                    GPB_UNROLL
-                    for (int q = 0; q < Q; q++) {
-                        const T diff = rc[1 + q] - zh[j][q];
-                        t[q] = diff * rc[1 + Q + q];
-                        x -= t[q] * diff;
-                    }
-                }
-                const T psi2 = exp_dom(x, s_tab);
-                if (!BWD) {
-                    GPB_UNROLL
-                    for (int d = 0; d < DOC; d++) v[d] += bs[j][d] * psi2;
-                } else {
-                    T coef = 0;
-                    GPB_UNROLL
-                    for (int d = 0; d < DOC; d++) {
-                        const T dvd = rc[1 + 2 * Q + d];
-                        accB[j][d] += dvd * psi2;
-                        coef += dvd * bs[j][d];
-                    }
-                    if (!GEN || a.lam_pass) {
-                        if (kGen && a.full_coef) {
-                            const long p = pbase + j * kThreads + tid;
-                            coef = 0;
-                            for (int d = 0; d < Do; d++)
-                                coef += (T)s_dvall[r * 64 + d] * a.bs[(long)d * PP + p];
-                        }
-                        const T lam = coef * psi2;
-                        if (kGen) accS0[j] += lam;
+            for (int i = 0; i < NR; i++) {
+                GPB_UNROLL
+                for (int j = 0; j < RP; j++) {
+                    T xx = rc[i][0];
+                    if (kExpand) {
                         GPB_UNROLL
                         for (int q = 0; q < Q; q++) {
-                            accS1[j][q] += lam * t[q];
-                            v[q] += lam * zh[j][q];
-                            v[Q + q] += lam * zh2[j][q];
+                            xx += rc[i][1 + q] * zh[j][q];
+                            xx += rc[i][1 + Q + q] * zh2[j][q];
+                            t[i][j][q] = 0;
+                        }
+                    } else {
+                        GPB_UNROLL
+                        for (int q = 0; q < Q; q++) {
+                            const T diff = rc[i][1 + q] - zh[j][q];
+                            t[i][j][q] = diff * rc[i][1 + Q + q];
+                            xx -= t[i][j][q] * diff;
+                        }
+                    }
+                    x[i * RP + j] = xx;
+                }
+            }
+            exp_dom_n<NR * RP>(x, s_tab, lane16);
+            GPB_UNROLL
+            for (int i = 0; i < NR; i++) {
+                GPB_UNROLL
+                for (int j = 0; j < RP; j++) {
+                    const T psi2 = x[i * RP + j];
+                    if (!BWD) {
+                        GPB_UNROLL
+                        for (int d = 0; d < DOC; d++) v[i][d] += bs[j][d] * psi2;
+                    } else {
+                        T coef = 0;
+                        GPB_UNROLL
+                        for (int d = 0; d < DOC; d++) {
+                            const T dvd = rc[i][1 + 2 * Q + d];
+                            accB[j][d] += dvd * psi2;
+                            coef += dvd * bs[j][d];
+                        }
+                        if (!GEN || a.lam_pass) {
+                            if (kGen && a.full_coef) {
+                                const long p = pbase + j * kThreads + tid;
+                                coef = 0;
+                                for (int d = 0; d < Do; d++)
+                                    coef += (T)s_dvall[(r0 + i) * 64 + d] * a.bs[(long)d * PP + p];
+                            }
+                            const T lam = coef * psi2;
+                            if (kGen) accS0[j] += lam;
+                            GPB_UNROLL
+                            for (int q = 0; q < Q; q++) {
+                                accS1[j][q] += lam * t[i][j][q];
+                                v[i][q] += lam * zh[j][q];
+                                v[i][Q + q] += lam * zh2[j][q];
+                            }
                         }
                     }
                 }
             }
         };
-        if (kTwoRows) {
-            GPB_UNROLL_N(1)
-            for (int rr = 0; rr < TR / 2; rr++) {
-                T v0[NS], v1[NS];
-                row_body(2 * rr, v0);
-                row_body(2 * rr + 1, v1);
-                casc.push_even(v0);
-                if (casc.push_odd(2 * rr + 1, lane, v1)) {
-                    GPB_UNROLL
-                    for (int s = 0; s < NS; s++) fin[s] = v1[s];
-                }
+        GPB_UNROLL_N(1)
+        for (int r0 = 0; r0 < TR; r0 += NR) {
+            T v[NR][NS];
+            rows_body(r0, v);
+            bool done;
+            if (NR == 2) {
+                casc.push_even(v[0]);
+                done = casc.push_odd(r0 + 1, lane, v[NR - 1]);
+            } else if ((r0 & 1) == 0) {
+                casc.push_even(v[0]);
+                done = false;
+            } else {
+                done = casc.push_odd(r0, lane, v[0]);
             }
-        } else {
-            GPB_UNROLL_N(1)
-            for (int r = 0; r < TR; r++) {
-                T v[NS];
-                row_body(r, v);
-                if ((r & 1) == 0) {
-                    casc.push_even(v);
-                } else if (casc.push_odd(r, lane, v)) {
-                    GPB_UNROLL
-                    for (int s = 0; s < NS; s++) fin[s] = v[s];
-                }
+            if (done) {
+                GPB_UNROLL
+                for (int s = 0; s < NS; s++) fin[s] = v[NR - 1][s];
             }
         }
         // lane L now holds row L's sums over this warp's pairs: add the 8 warps, then one atomic
