@@ -95,7 +95,7 @@ int mm_pairs_smem(K kern, size_t dyn) {
     if (dyn == 0) return GPB_OK;
     static K done = nullptr;   // one static per kernel instantiation
     if (done == kern) return GPB_OK;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024);
     if (e != cudaSuccess) return fail(GPB_ERR_CUDA, "mm_pairs: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     done = kern;
 #else
@@ -106,7 +106,8 @@ int mm_pairs_smem(K kern, size_t dyn) {
 
 template <typename T, int Q, int DOC, bool BWD>
 int mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
-    const size_t smem = sizeof(double) * gpb::ExpDom<T>::TAB;
+    constexpr int NS = BWD ? 2 * Q : DOC;
+    const size_t smem = sizeof(double) * gpb::ExpDom<T>::TAB + gpb::RowXpose<T, NS>::kBytes;
     prof_begin(BWD ? 4 : 3, stream);
     if constexpr (BWD && DOC == 4) {
         if (p.npass > 1) {   // Do > 4: generic multi-pass kernel

@@ -299,14 +299,19 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_kernel(DetFwdArgs<T> a) {
                             GPB_UNROLL
                             for (int e = 0; e < VEC; e++) b[kk][j * VEC + e] = u.e[e];
                         }
+                    // 8 rows at a time, k outermost inside the group: an accumulator is touched again
+                    // only after 32 other FMAs (the fp64 pipe stalls on back-to-back dependent FMAs)
                     GPB_UNROLL
-                    for (int r = 0; r < 16; r++) {
-                        VecU<T> av;  // VEC consecutive k of row r (warp-uniform address)
-                        av.v = *(const VT*)(Ka + (long)r * MP + k0);
+                    for (int rg = 0; rg < 16; rg += 8) {
+                        VecU<T> av[8];  // VEC consecutive k of each row (warp-uniform addresses)
+                        GPB_UNROLL
+                        for (int r = 0; r < 8; r++) av[r].v = *(const VT*)(Ka + (long)(rg + r) * MP + k0);
                         GPB_UNROLL
                         for (int kk = 0; kk < VEC; kk++)
                             GPB_UNROLL
-                            for (int cc = 0; cc < 4; cc++) acc[r][cc] += av.e[kk] * b[kk][cc];
+                            for (int r = 0; r < 8; r++)
+                                GPB_UNROLL
+                                for (int cc = 0; cc < 4; cc++) acc[rg + r][cc] += av[r].e[kk] * b[kk][cc];
                     }
                 }
                 sync_threads();
@@ -791,40 +796,20 @@ GPB_DEVICE void exp_dom_n(float (&x)[N], const double*, int) {
     }
 }
 
-// Running warp-transpose reduction.  Row r (0..31) of a tile contributes NS per-lane partial sums;
-// after the 32nd push lane L holds the NS sums of row L added over all 32 lanes.  Pending partial
-// sets are merged like a binary counter (level k pairs blocks of 2^k rows with one xor-shuffle),
-// so a tile costs 31*NS shuffles instead of 160*NS and only 5 named register sets are live.
+// Geometry of the per-warp transposition buffer of the pair kernel: every lane stores the NS row
+// sums of its pairs for HT consecutive rows (one 16-byte padded line of 32 lane records per row);
+// then lane L adds up row L % HT over a slice of HT lanes.  One store + one load per value
+// instead of the 5-level select/shuffle cascade of v4-v10 (which cost ~8 non-fp64 instructions per
+// pair and row -- the fp64 pipe only stays busy if at most one other instruction issues per fp64
+// instruction, see profiles/).  HT is sized so that the 8 warps use <= 64 KB.
 template <typename T, int NS>
-struct RowCascade {
-    T l0[NS], l1[NS], l2[NS], l3[NS], l4[NS];
-    GPB_MEMBER static void merge(const T (&early)[NS], const T (&late)[NS], int bit, int lane, T (&out)[NS]) {
-        const bool up = (lane & bit) != 0;   // lanes with the bit set keep the later rows
-        GPB_UNROLL
-        for (int s = 0; s < NS; s++) {
-            T keep = up ? late[s] : early[s];
-            T send = up ? early[s] : late[s];
-            out[s] = keep + shfl_xor(send, bit);
-        }
-    }
-    GPB_MEMBER void push_even(T (&v)[NS]) {
-        GPB_UNROLL
-        for (int s = 0; s < NS; s++) l0[s] = v[s];
-    }
-    // second row of a pair (r odd); returns true when `v` holds the finished sums of rows
-    // (r-31 .. r), i.e. after r == 31
-    GPB_MEMBER bool push_odd(int r, int lane, T (&v)[NS]) {
-        merge(l0, v, 1, lane, v);
-        if ((r & 2) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l1[s] = v[s]; return false; }
-        merge(l1, v, 2, lane, v);
-        if ((r & 4) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l2[s] = v[s]; return false; }
-        merge(l2, v, 4, lane, v);
-        if ((r & 8) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l3[s] = v[s]; return false; }
-        merge(l3, v, 8, lane, v);
-        if ((r & 16) == 0) { GPB_UNROLL for (int s = 0; s < NS; s++) l4[s] = v[s]; return false; }
-        merge(l4, v, 16, lane, v);
-        return true;
-    }
+struct RowXpose {
+    static constexpr int kRecB = NS * (int)sizeof(T);     // bytes of one lane record
+    static constexpr int kRowB = 32 * kRecB + 16;          // padded row stride (conflict-free reads)
+    static constexpr int kRaw = 65536 / (8 * kRowB);
+    static constexpr int HT = kRaw >= 32 ? 32 : (kRaw >= 16 ? 16 : (kRaw >= 8 ? 8 : (kRaw >= 4 ? 4 : 2)));
+    static constexpr int kWarpB = HT * kRowB;
+    static constexpr int kBytes = 8 * kWarpB;
 };
 
 // a2+a6 (forward) / a2+a9 (backward) over unordered pairs.  Each thread owns RP pairs for
@@ -842,8 +827,8 @@ struct RowCascade {
 // The exponent is formed in the ExpDom<T>-scaled domain.  fp64 forward uses the expanded form
 // xs = a0_n + sum_q (b_nq zh_pq + c_nq zh_pq^2) (2Q fma); the backward needs c2 (mu - zh) anyway.
 // Two rows are processed per loop trip when Q <= 4 (independent dependency chains for the fp64 pipe).
-// The per-row sums are reduced over the warp by RowCascade, over the 8 warps through shared
-// memory, and over the pair chunks (blocks) by one fp64 atomic per value.
+// The per-row sums are reduced over the warp through a shared-memory transposition (RowXpose), over
+// the 8 warps through shared memory, and over the pair chunks (blocks) by one fp64 atomic per value.
 // GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
 // GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
 template <typename T, int Q, int DOC, bool BWD, bool GEN>
@@ -869,7 +854,9 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     GPB_SHARED double s_dvall[kGen ? TR * 64 : 1];  // generic path (single buffered): all Do (<= 64) per row
     GPB_SHARED GPB_ALIGN16 T s_red[2][WARP_ATOMICS ? 1 : 8 * TR * NS];
     GPB_SHARED double s_l2[Q];
-    GPB_DYN_SMEM(dsm);                               // fp64: the replicated exp table (32 KB)
+    typedef RowXpose<T, NS> X;
+    constexpr int HT = X::HT;
+    GPB_DYN_SMEM(dsm);      // [ replicated exp table (fp64: 32 KB) | 8 x per-warp transposition buffers ]
     double* s_tab = (double*)dsm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long pbase = (long)blockIdx.x * C::PC;
@@ -900,6 +887,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         for (int i = tid; i < kTab; i += kThreads)
             s_tab[i] = exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
     const int lane16 = lane & 15;
+    unsigned char* xw = dsm + kTab * sizeof(double) + warp * X::kWarpB;   // this warp's buffer
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
@@ -958,8 +946,6 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         } else if (t0 + TR < r_end) {
             stage(buf ^ 1, t0 + TR);
         }
-        RowCascade<T, NS> casc;
-        T fin[NS];
         // NR rows against this thread's RP pairs; v[i] = this thread's part of the sums of row r0+i.
         // All NR*RP exponents are formed first, then exponentiated in lock step, then consumed.
         auto rows_body = [&](int r0, T (&v)[NR][NS]) {
@@ -1031,42 +1017,59 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                 }
             }
         };
+        T* red = s_red[buf];
+        const bool emit = !BWD || !GEN || a.lam_pass;
         GPB_UNROLL_N(1)
         for (int r0 = 0; r0 < TR; r0 += NR) {
             T v[NR][NS];
             rows_body(r0, v);
-            bool done;
-            if (NR == 2) {
-                casc.push_even(v[0]);
-                done = casc.push_odd(r0 + 1, lane, v[NR - 1]);
-            } else if ((r0 & 1) == 0) {
-                casc.push_even(v[0]);
-                done = false;
-            } else {
-                done = casc.push_odd(r0, lane, v[0]);
-            }
-            if (done) {
+            GPB_UNROLL
+            for (int i = 0; i < NR; i++) {
+                T* dst = (T*)(xw + ((r0 + i) & (HT - 1)) * X::kRowB + lane * X::kRecB);
                 GPB_UNROLL
-                for (int s = 0; s < NS; s++) fin[s] = v[NR - 1][s];
+                for (int s = 0; s < NS; s++) dst[s] = v[i][s];
+            }
+            if (((r0 + NR) & (HT - 1)) == 0) {
+                // HT rows complete: lane L adds row L % HT over lanes [slice*HT, slice*HT + HT)
+                sync_warp();
+                const int xr = lane & (HT - 1), xs = lane / HT;
+                const unsigned char* src = xw + xr * X::kRowB + (xs * HT) * X::kRecB;
+                T acc[NS];
+                GPB_UNROLL
+                for (int s = 0; s < NS; s++) acc[s] = 0;
+                GPB_UNROLL_N(4)
+                for (int k = 0; k < HT; k++) {
+                    const T* p = (const T*)(src + k * X::kRecB);
+                    GPB_UNROLL
+                    for (int s = 0; s < NS; s++) acc[s] += p[s];
+                }
+                GPB_UNROLL
+                for (int m = HT; m < 32; m <<= 1) {
+                    GPB_UNROLL
+                    for (int s = 0; s < NS; s++) acc[s] += shfl_xor(acc[s], m);
+                }
+                const int row = r0 + NR - HT + xr;       // row of the 32-row tile
+                if (WARP_ATOMICS) {
+                    if (emit && lane < HT && row < tv) {
+                        GPB_UNROLL
+                        for (int s = 0; s < NS; s++) {
+                            if (BWD)
+                                atomic_add(a.rowacc + (long)(t0 + row) * NS + s, (double)acc[s]);
+                            else if (a.d0 + s < Do)
+                                atomic_add(a.rowacc + (long)(t0 + row) * Do + a.d0 + s, (double)acc[s]);
+                        }
+                    }
+                } else if (lane < HT) {
+                    GPB_UNROLL
+                    for (int s = 0; s < NS; s++) red[(warp * TR + row) * NS + s] = acc[s];
+                }
+                sync_warp();                             // buffer free for the next HT rows
             }
         }
-        // lane L now holds row L's sums over this warp's pairs: add the 8 warps, then one atomic
-        const bool emit = !BWD || !GEN || a.lam_pass;
+        // rows of this tile summed per warp: add the 8 warps, then one atomic per value
         if (WARP_ATOMICS) {
-            if (emit && lane < tv) {
-                GPB_UNROLL
-                for (int s = 0; s < NS; s++) {
-                    if (BWD)
-                        atomic_add(a.rowacc + (long)(t0 + lane) * NS + s, (double)fin[s]);
-                    else if (a.d0 + s < Do)
-                        atomic_add(a.rowacc + (long)(t0 + lane) * Do + a.d0 + s, (double)fin[s]);
-                }
-            }
             sync_threads();         // next tile staged; this tile's buffers free
         } else {
-            T* red = s_red[buf];
-            GPB_UNROLL
-            for (int s = 0; s < NS; s++) red[(warp * TR + lane) * NS + s] = fin[s];
             sync_threads();         // the only barrier per tile (also publishes the staged next tile)
             if (emit)
                 for (int i = tid; i < TR * NS; i += kThreads) {

@@ -27,6 +27,7 @@
 namespace gpb {
 
 GPB_DEVICE void sync_threads() { __syncthreads(); }
+GPB_DEVICE void sync_warp() { __syncwarp(); }
 GPB_DEVICE double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE void atomic_add(double* p, double v) { atomicAdd(p, v); }
@@ -96,6 +97,7 @@ double shfl_xor_f64(double v, int m);  // warp exchange through a mailbox
 namespace gpb {
 
 static inline void sync_threads() { gpb_emu::barrier(); }
+static inline void sync_warp() { (void)gpb_emu::shfl_xor_f64(0.0, 0); }   // warp rendezvous
 static inline double shfl_xor(double v, int m) { return gpb_emu::shfl_xor_f64(v, m); }
 static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f64((double)v, m); }
 static inline void atomic_add(double* p, double v) { *p += v; }
