@@ -14,9 +14,10 @@ import numpy as np
 import torch
 
 from . import dist
+from .sched import TailStreams
 from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
 from .config import PROP_MM, PROP_MC, PROP_LIN
-from .layers import AEP_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
+from .layers import pack_to_device, AEP_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
 
 _F = torch.float64
 
@@ -92,49 +93,69 @@ class SDGPR(Base_SDGPR):
         super(SDGPR, self).__init__(x_train, y_train, no_pseudos, hidden_sizes, lik, prec, device)
         self.sgp_layers = [SGP_Layer(self.N, self.size[i], self.size[i + 1], self.Ms[i], True,
                                      prec, self.device) for i in range(self.L)]
+        self._tail_streams = TailStreams(self.device, self.L)
 
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        """aep_models.py:895-988.  Per-row kernels on the current stream; every layer's tail (and,
+        with several ranks, the all-reduce of its statistics) on its own side stream (sched.py)."""
         _check_mode(prop_mode)
         N, dev = self.N, self.device
         xb, yb, n = self._batch(mb_size)
         scale_logZ = -N * 1.0 / n / alpha
-        for layer in self.sgp_layers:
+        ts = self._tail_streams
+        pdev = pack_to_device(params, dev)
+        self.lik_layer.update_hypers(params, _dev=pdev)
+        for i, layer in enumerate(self.sgp_layers):
             layer._fuse_cavity_alpha = alpha
-        self.update_hypers(params)
-        for layer in self.sgp_layers:
-            layer.compute_cavity(alpha)
-        add = {}
-        if xb.shape[0] > 0:
-            ctxs = []
+            ts.fork(i)
+            with ts.on(i):
+                layer.update_hypers(params, key_suffix='_%d' % i, _dev=pdev)
+                layer.compute_cavity(alpha)
+        grads, phis = {}, [None] * self.L
+        has_rows = xb.shape[0] > 0
+        ctxs = []
+        if has_rows:
+            ts.join(0)
             m, v, ctx = self.sgp_layers[0]._fwd_det(xb, cav=True, save=True)
             ctxs.append(ctx)
-            for layer in self.sgp_layers[1:]:
+            for i, layer in enumerate(self.sgp_layers[1:], start=1):
+                ts.join(i)
                 m, v, ctx = layer._fwd_mm(m, v, cav=True)
                 ctxs.append(ctx)
             dmi, dvi, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
-            for i in range(self.L - 1, -1, -1):
-                layer = self.sgp_layers[i]
+        else:
+            ts.join_all()
+        top = None
+        for i in range(self.L - 1, -1, -1):
+            layer = self.sgp_layers[i]
+            add = {}
+            if has_rows:
                 if i == 0:
                     st = layer._bwd_det(ctxs[0], dmi, dvi)
                 else:
                     st = layer._bwd_mm(ctxs[i], dmi, dvi)
                     dmi, dvi = st['dmx'], st['dvx']
-                _add_stats(add, 's%d_' % i, st)
-            add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
-        else:
-            for i, layer in enumerate(self.sgp_layers):
-                _add_stats(add, 's%d_' % i, _zero_stats(layer))
-            add['logZ'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
-        add = dist.allreduce_dict(add)
-        grads = {}
-        energy = scale_logZ * add['logZ']
-        for i, layer in enumerate(self.sgp_layers):
-            st = _get_stats(add, 's%d_' % i)
-            g = layer._tail_det(st, alpha) if i == 0 else layer._tail_mm(st, alpha)
-            for k, val in g.items():
-                grads[k + '_%d' % i] = val
-            energy = energy + layer._phi(alpha)
-        grads['sn'] = add['dsn'].reshape(())
+                _add_stats(add, 's_', st)
+            else:
+                _add_stats(add, 's_', _zero_stats(layer))
+            if i == self.L - 1:
+                add['logZ'] = logZ.reshape(1) if has_rows else _zeros(dev, 1)
+                add['dsn'] = dsn.reshape(1) if has_rows else _zeros(dev, 1)
+            ts.fork(i)
+            with ts.on(i):
+                add = dist.allreduce_dict(add)
+                g = layer._tail_det(_get_stats(add, 's_'), alpha) if i == 0 else \
+                    layer._tail_mm(_get_stats(add, 's_'), alpha)
+                for k, val in g.items():
+                    grads[k + '_%d' % i] = val
+                phis[i] = layer._phi(alpha)
+                if i == self.L - 1:
+                    top = add
+        ts.join_all()
+        energy = scale_logZ * top['logZ']
+        for i in range(self.L):
+            energy = energy + phis[i]
+        grads['sn'] = top['dsn'].reshape(())
         return self._finish(energy, grads)
 
 

@@ -804,8 +804,13 @@ GPB_DEVICE void exp_dom_n(float (&x)[N], const double*, int) {
 // instruction, see profiles/).  HT is sized so that the 8 warps use <= 64 KB.
 template <typename T, int NS>
 struct RowXpose {
-    static constexpr int kRecB = NS * (int)sizeof(T);     // bytes of one lane record
-    static constexpr int kRowB = 32 * kRecB + 16;          // padded row stride (conflict-free reads)
+    // a row line holds the NS values of the 32 lanes in 16-byte vectors, vector-major:
+    //   [vector c][lane] -- stores of a quarter warp cover 128 contiguous bytes, and so do the
+    //   reads (8 lanes read the same source lane of 8 different rows; row stride = 16 mod 128)
+    static constexpr int VW = 16 / (int)sizeof(T);         // values per 16-byte vector
+    static constexpr int NV = (NS + VW - 1) / VW;          // vectors per lane record
+    static constexpr int kRecB = NV * 16;                  // bytes of one lane record
+    static constexpr int kRowB = 32 * kRecB + 16;          // padded row stride
     static constexpr int kRaw = 65536 / (8 * kRowB);
     static constexpr int HT = kRaw >= 32 ? 32 : (kRaw >= 16 ? 16 : (kRaw >= 8 ? 8 : (kRaw >= 4 ? 4 : 2)));
     static constexpr int kWarpB = HT * kRowB;
@@ -1025,23 +1030,32 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
             rows_body(r0, v);
             GPB_UNROLL
             for (int i = 0; i < NR; i++) {
-                T* dst = (T*)(xw + ((r0 + i) & (HT - 1)) * X::kRowB + lane * X::kRecB);
+                unsigned char* dst = xw + ((r0 + i) & (HT - 1)) * X::kRowB + lane * 16;
                 GPB_UNROLL
-                for (int s = 0; s < NS; s++) dst[s] = v[i][s];
+                for (int c = 0; c < X::NV; c++) {
+                    VecU<T> u;
+                    GPB_UNROLL
+                    for (int e = 0; e < X::VW; e++) u.e[e] = (c * X::VW + e < NS) ? v[i][c * X::VW + e] : (T)0;
+                    *(typename V16<T>::type*)(dst + c * 512) = u.v;
+                }
             }
             if (((r0 + NR) & (HT - 1)) == 0) {
                 // HT rows complete: lane L adds row L % HT over lanes [slice*HT, slice*HT + HT)
                 sync_warp();
                 const int xr = lane & (HT - 1), xs = lane / HT;
-                const unsigned char* src = xw + xr * X::kRowB + (xs * HT) * X::kRecB;
-                T acc[NS];
+                const unsigned char* src = xw + xr * X::kRowB + (xs * HT) * 16;
+                T acc[X::NV * X::VW];
                 GPB_UNROLL
-                for (int s = 0; s < NS; s++) acc[s] = 0;
+                for (int s = 0; s < X::NV * X::VW; s++) acc[s] = 0;
                 GPB_UNROLL_N(4)
                 for (int k = 0; k < HT; k++) {
-                    const T* p = (const T*)(src + k * X::kRecB);
                     GPB_UNROLL
-                    for (int s = 0; s < NS; s++) acc[s] += p[s];
+                    for (int c = 0; c < X::NV; c++) {
+                        VecU<T> u;
+                        u.v = *(const typename V16<T>::type*)(src + c * 512 + k * 16);
+                        GPB_UNROLL
+                        for (int e = 0; e < X::VW; e++) acc[c * X::VW + e] += u.e[e];
+                    }
                 }
                 GPB_UNROLL
                 for (int m = HT; m < 32; m <<= 1) {
