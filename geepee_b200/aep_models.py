@@ -105,25 +105,37 @@ class SDGPR(Base_SDGPR):
         ts = self._tail_streams
         pdev = pack_to_device(params, dev)
         self.lik_layer.update_hypers(params, _dev=pdev)
-        for i, layer in enumerate(self.sgp_layers):
+        uploaded = ts.mark()
+
+        def pre_tail(i):
+            # q(u) + cavity of layer i on its side stream; issued right after the forward kernel
+            # of layer i-1 was queued, so it runs underneath that kernel
+            layer = self.sgp_layers[i]
             layer._fuse_cavity_alpha = alpha
-            ts.fork(i)
+            ts.fork(i, after=uploaded)
             with ts.on(i):
                 layer.update_hypers(params, key_suffix='_%d' % i, _dev=pdev)
                 layer.compute_cavity(alpha)
+
         grads, phis = {}, [None] * self.L
         has_rows = xb.shape[0] > 0
         ctxs = []
+        pre_tail(0)
         if has_rows:
-            ts.join(0)
-            m, v, ctx = self.sgp_layers[0]._fwd_det(xb, cav=True, save=True)
-            ctxs.append(ctx)
-            for i, layer in enumerate(self.sgp_layers[1:], start=1):
+            m = v = None
+            for i, layer in enumerate(self.sgp_layers):
                 ts.join(i)
-                m, v, ctx = layer._fwd_mm(m, v, cav=True)
+                if i == 0:
+                    m, v, ctx = layer._fwd_det(xb, cav=True, save=True)
+                else:
+                    m, v, ctx = layer._fwd_mm(m, v, cav=True)
                 ctxs.append(ctx)
+                if i + 1 < self.L:
+                    pre_tail(i + 1)
             dmi, dvi, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
         else:
+            for i in range(1, self.L):
+                pre_tail(i)
             ts.join_all()
         top = None
         for i in range(self.L - 1, -1, -1):

@@ -26,9 +26,22 @@ class TailStreams(object):
         self.cuda = (device.type == 'cuda')
         self.streams = [torch.cuda.Stream(device) for _ in range(n)] if self.cuda else [None] * n
 
-    def fork(self, i):
+    def mark(self):
+        """Event on the current stream (e.g. 'parameters uploaded')."""
         if self.cuda:
-            self.streams[i].wait_stream(torch.cuda.current_stream())
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            return ev
+        return None
+
+    def fork(self, i, after=None):
+        """Side stream i waits for the main stream -- or only for the event `after` (used at the
+        start of a step, when everything older than the upload is already complete)."""
+        if self.cuda:
+            if after is not None:
+                self.streams[i].wait_event(after)
+            else:
+                self.streams[i].wait_stream(torch.cuda.current_stream())
 
     def on(self, i):
         if self.cuda:
