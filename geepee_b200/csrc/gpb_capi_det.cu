@@ -80,6 +80,39 @@ int det_fwd_t(const double* x, const double* z, const double* ls, const double* 
     return fail(GPB_ERR_ARG, "det_fwd: M=%d unsupported (max 512)", M);
 }
 
+// fp64: tensor-core (DMMA) kernel
+template <int MP>
+int det_fwd_mma_launch(const double* x, const double* z, const double* ls, const double* sf,
+                       const void* Ap, const void* Bp, int n, int M, int D, int Do, double* mout,
+                       double* vout, void* Ksave, void* Tsave, void* stream) {
+    typedef gpb::DetMmaCfg<MP> C;
+    gpb::DetFwdArgs<double> a;
+    a.x = x; a.z = z; a.ls = ls; a.sf = sf;
+    a.Ap = (const double*)Ap; a.Bp = (const double*)Bp;
+    a.n = n; a.M = M; a.D = D; a.Do = Do;
+    a.mout = mout; a.vout = vout; a.Ksave = (double*)Ksave; a.Tsave = (double*)Tsave;
+    auto kern = gpb::det_fwd_mma_kernel<MP>;
+    int rc = allow_smem(kern, C::smem_bytes);
+    if (rc) return rc;
+    int ntiles = (int)cdiv(n, C::TN);
+    int grid = ntiles < sm_count() ? ntiles : sm_count();
+    prof_begin(0, stream);
+    GPB_LAUNCH(kern, dim3(grid), dim3(256), C::smem_bytes, stream, a);
+    prof_end(0, stream);
+    return GPB_CHECK_LAUNCH();
+}
+template <>
+int det_fwd_t<double>(const double* x, const double* z, const double* ls, const double* sf, const void* Ap,
+                      const void* Bp, int n, int M, int D, int Do, double* mout, double* vout, void* Ksave,
+                      void* Tsave, void* stream) {
+    switch (gpb_det_pad_m(M)) {
+        case 128: return det_fwd_mma_launch<128>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+        case 256: return det_fwd_mma_launch<256>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+        case 512: return det_fwd_mma_launch<512>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+    }
+    return fail(GPB_ERR_ARG, "det_fwd: M=%d unsupported (max 512)", M);
+}
+
 template <typename T>
 int det_bwd_t(const double* x, const double* z, const double* ls, const double* sf, const void* Ap,
               const double* dm, const double* dv, const void* Ksave, const void* Tsave, int n, int M,
@@ -133,6 +166,29 @@ int det_syrk_t(const void* Ksave, const double* dv, int n, int M, int Do, double
     prof_begin(2, stream);
     GPB_LAUNCH(kern, dim3(p.nbu, p.nsplit, Do), dim3(256), gpb::SyrkCfg<T>::smem_bytes, stream,
                (const T*)Ksave, dv, n, p.MP, Do, p.rows_per_split, part);
+    prof_end(2, stream);
+    rc = GPB_CHECK_LAUNCH();
+    if (rc) return rc;
+    auto fin = gpb::det_syrk_finish_kernel;
+    GPB_LAUNCH(fin, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, part, p.nsplit,
+               p.MP, M, Do, dB);
+    return GPB_CHECK_LAUNCH();
+}
+
+// fp64: tensor-core (DMMA) rank update
+template <>
+int det_syrk_t<double>(const void* Ksave, const double* dv, int n, int M, int Do, double* dB, void* ws,
+                       size_t ws_bytes, void* stream) {
+    SyrkPlan p = syrk_plan(n, M, Do);
+    Carver cv(ws, ws_bytes);
+    double* part = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
+    if (!cv.ok()) return fail(GPB_ERR_WS, "det_syrk: workspace %zu < %zu", ws_bytes, cv.off);
+    auto kern = gpb::det_syrk_mma_kernel;
+    int rc = allow_smem(kern, gpb::SyrkMmaCfg::smem_bytes);
+    if (rc) return rc;
+    prof_begin(2, stream);
+    GPB_LAUNCH(kern, dim3(p.nbu, p.nsplit, Do), dim3(256), gpb::SyrkMmaCfg::smem_bytes, stream,
+               (const double*)Ksave, dv, n, p.MP, Do, p.rows_per_split, part);
     prof_end(2, stream);
     rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;

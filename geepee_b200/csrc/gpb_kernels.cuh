@@ -361,6 +361,226 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_kernel(DetFwdArgs<T> a) {
     }
 }
 
+// -------------------------------------------------------------------------
+// fp64 tensor-core variant of a5 (DMMA.8x8x4, the native FP64 MMA of sm_100a).
+// Measured on this pool's B200 (tools/probe): DMMA sustains 37 TFLOP/s = the nominal FP64 peak with 8
+// resident warps, whereas DFMA streams with three distinct register operands top out at 65-78 %
+// of it (register-operand bandwidth) -- the SIMT kernel above reaches 16.4 TFLOP/s.
+//   * tile: TN rows x MP columns per CTA pass; 8 warps as CW column-warps x RW row-warps, each
+//     warp 32 rows x 64 columns = 4 x 8 C fragments (64 accumulators per lane);
+//   * A operand: the Kfu tile, generated on chip into shared memory (row stride MP+4 doubles =
+//     4 mod 16, so the 32 fragment loads of a warp hit 32 different banks); the exponent is
+//     formed in expanded form  S(-|x'|^2/2 + 2 sf) + S(-|z'|^2/2) + sum_q (S x'_q) z'_q  with
+//     x' = x/l, z' = z/l (D fma per element) and exponentiated with the table-based exp
+//     (64 entries x 16 replicas, degree-5 polynomial, see ExpDom);
+//   * B operand: B_d streamed through a double-buffered cp.async ring of KB rows, same padding;
+//   * epilogue on the C fragments: mout, vout row sums (quad shuffle + cross-warp smem), T store.
+template <int MP>
+struct DetMmaCfg {
+    static constexpr int CW = MP / 64;            // 2, 4, 8 column warps
+    static constexpr int RW = 8 / CW;             // 4, 2, 1 row warps
+    static constexpr int TN = 32 * RW;            // 128, 64, 32 rows per tile
+    static constexpr int LD = MP + 4;             // padded row stride in doubles
+    static constexpr int KB = 4096 / MP;          // B rows per ring stage: 32, 16, 8
+    static constexpr int DPMAX = 32;
+    static constexpr int ETAB = 64 * 16;          // replicated 2^(j/64) table
+    static constexpr size_t kt_bytes = (size_t)TN * LD * 8;
+    static constexpr size_t bs_bytes = 2 * (size_t)KB * LD * 8;     // also holds the x tile
+    static constexpr size_t red_bytes = (size_t)CW * TN * 2 * 8;
+    static constexpr size_t misc_bytes = (ETAB + TN + DPMAX) * 8;
+    static constexpr size_t smem_bytes = kt_bytes + bs_bytes + red_bytes + misc_bytes;
+};
+
+// exp(xs / S) for xs = S x, S = 64/ln2: xs = 64 k + j + r -> 2^k 2^(j/64) e^(r ln2/64); 9 fp64 ops.
+GPB_DEVICE double exp_dom64(double xs, const double* __restrict__ tab /* [64][16] */, int lane16) {
+    constexpr double h = 0.693147180559945309417232 / 64.0;
+    constexpr double c1 = h, c2 = h * h / 2, c3 = h * h * h / 6, c4 = h * h * h * h / 24,
+                     c5 = h * h * h * h * h / 120;
+    const double magic = 6755399441055744.0;
+    double kd = xs + magic;
+#ifndef GPB_CPU_EMU
+    const int n = __double2loint(kd);
+#else
+    int64_t bits;
+    memcpy(&bits, &kd, 8);
+    const int n = (int)(int32_t)(bits & 0xffffffff);
+#endif
+    kd -= magic;
+    const double r = xs - kd;
+    const double t = tab[((n & 63) << 4) + lane16];
+    double q = c5 * r + c4;
+    q = q * r + c3;
+    q = q * r + c2;
+    q = q * r + c1;
+    const double p = (t * r) * q + t;
+    int k = n >> 6;
+    k = k < -1021 ? -1021 : k;
+#ifndef GPB_CPU_EMU
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    return ldexp(p, k);
+#endif
+}
+
+template <int MP, int DP>
+GPB_DEVICE void gen_k_tile_mma(double* Kt, const double* xs, const double* an, const double* __restrict__ z,
+                               const double* ils, const double* tab, int M, int D, int TN, int LD,
+                               int rows_valid, double* Ksave_tile) {
+    const int lane16 = threadIdx.x & 15;
+    for (int m = threadIdx.x; m < MP; m += blockDim.x) {
+        double zr[DP], bm = 0;
+        GPB_UNROLL
+        for (int q = 0; q < DP; q++) {
+            zr[q] = (m < M && q < D) ? z[(long)m * D + q] * ils[q] : 0.0;
+            bm -= zr[q] * zr[q];
+        }
+        bm *= 0.5 * (64.0 / 0.693147180559945309417232);
+        GPB_UNROLL_N(4)
+        for (int r = 0; r < TN; r++) {
+            double e = an[r] + bm;
+            GPB_UNROLL
+            for (int q = 0; q < DP; q++) e += xs[r * DP + q] * zr[q];
+            const double k = (m < M && r < rows_valid) ? exp_dom64(e, tab, lane16) : 0.0;
+            Kt[r * LD + m] = k;
+            if (Ksave_tile != nullptr && r < rows_valid) Ksave_tile[(long)r * MP + m] = k;
+        }
+    }
+}
+
+template <int MP>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_mma_kernel(DetFwdArgs<double> a) {
+    typedef DetMmaCfg<MP> C;
+    constexpr int TN = C::TN, KB = C::KB, LD = C::LD, CW = C::CW;
+    constexpr double kS = 64.0 / 0.693147180559945309417232;
+    GPB_DYN_SMEM(smem);
+    double* Kt = (double*)smem;
+    double* Bs = (double*)(smem + C::kt_bytes);
+    double* xs = Bs;   // x tile aliases the B ring (only live during Kfu generation)
+    double* red = (double*)(smem + C::kt_bytes + C::bs_bytes);
+    double* tab = (double*)(smem + C::kt_bytes + C::bs_bytes + C::red_bytes);
+    double* an = tab + C::ETAB;
+    double* ils = an + TN;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int cw = warp % CW, rw = warp / CW;
+    const int D = a.D, M = a.M, Do = a.Do, n = a.n;
+    const int DP = D <= 4 ? 4 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32));
+    const double sf2 = exp(2.0 * a.sf[0]);
+    if (tid < C::DPMAX) ils[tid] = tid < D ? exp(-a.ls[tid]) : 0.0;
+    for (int i = tid; i < C::ETAB; i += kThreads) tab[i] = exp2((double)(i >> 4) * (1.0 / 64.0));
+
+    const int ntiles = (n + TN - 1) / TN;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * TN;
+        const int rows_valid = (n - row0) < TN ? (n - row0) : TN;
+        sync_threads();  // previous tile fully consumed (Kt, Bs/xs, red); ils/tab visible
+        for (int i = tid; i < TN * DP; i += kThreads) {
+            int r = i / DP, q = i - r * DP;
+            xs[i] = (r < rows_valid && q < D) ? a.x[(long)(row0 + r) * D + q] * ils[q] : 0.0;
+        }
+        sync_threads();
+        if (tid < TN) {   // an = S (2 sf - |x'|^2 / 2); then scale the row by S
+            double s = 0;
+            for (int q = 0; q < DP; q++) s += xs[tid * DP + q] * xs[tid * DP + q];
+            an[tid] = kS * (2.0 * a.sf[0] - 0.5 * s);
+        }
+        sync_threads();
+        for (int i = tid; i < TN * DP; i += kThreads) xs[i] *= kS;
+        sync_threads();
+        double* ks = a.Ksave ? a.Ksave + (long)row0 * MP : nullptr;
+        if (DP == 4) gen_k_tile_mma<MP, 4>(Kt, xs, an, a.z, ils, tab, M, D, TN, LD, rows_valid, ks);
+        else if (DP == 8) gen_k_tile_mma<MP, 8>(Kt, xs, an, a.z, ils, tab, M, D, TN, LD, rows_valid, ks);
+        else if (DP == 16) gen_k_tile_mma<MP, 16>(Kt, xs, an, a.z, ils, tab, M, D, TN, LD, rows_valid, ks);
+        else gen_k_tile_mma<MP, 32>(Kt, xs, an, a.z, ils, tab, M, D, TN, LD, rows_valid, ks);
+        sync_threads();
+
+        for (int d = 0; d < Do; d++) {
+            const double* Bd = a.Bp + (long)d * MP * MP;
+            double acc[4][8][2];
+            GPB_UNROLL
+            for (int i = 0; i < 4; i++)
+                GPB_UNROLL
+                for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0;
+
+            constexpr int nchunks = MP / KB;
+            constexpr int row_vecs = MP / 2;              // 16-byte vectors per B row
+            constexpr int chunk_vecs = KB * row_vecs;
+            auto issue = [&](int c) {
+                double* dst = Bs + (long)(c & 1) * KB * LD;
+                const double* src = Bd + (long)c * KB * MP;
+                for (int i = tid; i < chunk_vecs; i += kThreads) {
+                    const int r = i / row_vecs, cv = i - r * row_vecs;
+                    cp_async16(dst + (long)r * LD + cv * 2, src + (long)r * MP + cv * 2);
+                }
+                cp_async_commit();
+            };
+            issue(0);
+            for (int c = 0; c < nchunks; c++) {
+                if (c + 1 < nchunks) {
+                    issue(c + 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                sync_threads();
+                const double* Bc = Bs + (long)(c & 1) * KB * LD + cw * 64 + g;
+                const double* Ka = Kt + (long)(rw * 32 + g) * LD + c * KB + t;
+                GPB_UNROLL_N(2)
+                for (int ks4 = 0; ks4 < KB; ks4 += 4) {
+                    double af[4], bf[8];
+                    GPB_UNROLL
+                    for (int i = 0; i < 4; i++) af[i] = Ka[(long)(i * 8) * LD + ks4];
+                    GPB_UNROLL
+                    for (int j = 0; j < 8; j++) bf[j] = Bc[(long)(ks4 + t) * LD + j * 8];
+                    GPB_UNROLL
+                    for (int i = 0; i < 4; i++)
+                        GPB_UNROLL
+                        for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+                sync_threads();
+            }
+
+            // epilogue: this lane holds T[row][col], T[row][col+1] for row = rw*32 + i*8 + g,
+            // col = cw*64 + j*8 + 2t
+            GPB_UNROLL
+            for (int i = 0; i < 4; i++) {
+                const int row = rw * 32 + i * 8 + g;
+                double pv = 0, pm = 0;
+                GPB_UNROLL
+                for (int j = 0; j < 8; j++) {
+                    const int col = cw * 64 + j * 8 + 2 * t;
+                    const double2 kv = *(const double2*)(Kt + (long)row * LD + col);
+                    const double2 av = *(const double2*)(a.Ap + (long)d * MP + col);
+                    pv += acc[i][j][0] * kv.x + acc[i][j][1] * kv.y;
+                    pm += kv.x * av.x + kv.y * av.y;
+                    if (a.Tsave != nullptr && row < rows_valid)
+                        *(double2*)(a.Tsave + ((long)(row0 + row) * Do + d) * MP + col) =
+                            make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+                pv += shfl_xor(pv, 1);
+                pm += shfl_xor(pm, 1);
+                pv += shfl_xor(pv, 2);
+                pm += shfl_xor(pm, 2);
+                if (t == 0) {
+                    red[(cw * TN + row) * 2 + 0] = pv;
+                    red[(cw * TN + row) * 2 + 1] = pm;
+                }
+            }
+            sync_threads();
+            if (tid < rows_valid) {
+                double pv = 0, pm = 0;
+                for (int w = 0; w < CW; w++) {
+                    pv += red[(w * TN + tid) * 2 + 0];
+                    pm += red[(w * TN + tid) * 2 + 1];
+                }
+                a.vout[(long)(row0 + tid) * Do + d] = sf2 + pv;
+                a.mout[(long)(row0 + tid) * Do + d] = pm;
+            }
+        }
+    }
+}
+
 // a8 (row-streaming part), aep_models.py:452-460,490 + kernels.py:381-399 (kfucompDer):
 //   L[n,m] = (sum_d dm[n,d] A[d,m] + 2 dv[n,d] T[n,d,m]) kfu[n,m]
 //   dsf2 += sum L / sf2 ; dZ[m,q] -= L (z_mq - x_nq)/l_q^2 ; dl_q += L (z_mq-x_nq)^2/l_q^3
@@ -618,6 +838,105 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_kernel(const T* __restrict__ Ksa
         for (int j = 0; j < 16; j++) {
             const int oj = (j / VEC) * (8 * VEC) + tx * VEC + (j % VEC);
             out[oi * 128 + oj] = (double)acc[i][j];
+        }
+    }
+}
+
+// fp64 tensor-core variant of the rank update (DMMA.8x8x4): the reduction index of the MMA is
+// the data row, A = (dv o K)^T and B = K come from the same staged [RK x 128] panels (row stride
+// 132 doubles = 4 mod 16: conflict-free fragment loads).  8 warps = 4 row-warps x 2 column-warps,
+// each 32 x 64 of the 128 x 128 output block (4 x 8 C fragments); 3-stage cp.async ring.
+struct SyrkMmaCfg {
+    static constexpr int RK = 16;        // data rows per stage
+    static constexpr int LD = 132;       // padded panel row stride (doubles)
+    static constexpr int STAGES = 3;
+    static constexpr size_t stage_bytes = 2 * (size_t)RK * LD * 8;
+    static constexpr size_t smem_bytes = STAGES * stage_bytes + STAGES * RK * sizeof(double);
+};
+
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_mma_kernel(const double* __restrict__ Ksave,
+                                                           const double* __restrict__ dv, int n, int MP,
+                                                           int Do, int rows_per_split,
+                                                           double* __restrict__ part) {
+    typedef SyrkMmaCfg C;
+    constexpr int RK = C::RK, LD = C::LD, STAGES = C::STAGES;
+    constexpr int CPT = 2 * RK * 64 / kThreads;       // 16-byte copies per thread per stage
+    GPB_DYN_SMEM(smem);
+    double* s_dv = (double*)(smem + STAGES * C::stage_bytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int rw = warp >> 1, cw = warp & 1;
+    const int nb = MP / 128;
+    int ub = blockIdx.x, bi = 0;
+    while (ub >= nb - bi) { ub -= nb - bi; bi++; }
+    const int bj = bi + ub;
+    const int d = blockIdx.z;
+    const int r_begin = blockIdx.y * rows_per_split;
+    const int r_end = (r_begin + rows_per_split) < n ? (r_begin + rows_per_split) : n;
+    const int nchunk = (r_end - r_begin + RK - 1) / RK;
+
+    double acc[4][8][2];
+    GPB_UNROLL
+    for (int i = 0; i < 4; i++)
+        GPB_UNROLL
+        for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0;
+
+    auto issue = [&](int chunk) {
+        if (chunk < nchunk) {
+            const int st = chunk % STAGES;
+            double* base = (double*)(smem + (size_t)st * C::stage_bytes);
+            const int t0 = r_begin + chunk * RK;
+            GPB_UNROLL
+            for (int i = 0; i < CPT; i++) {
+                const int v = tid + kThreads * i;
+                const int which = v / (RK * 64);
+                const int rem = v - which * (RK * 64);
+                const int r = rem / 64, cv = rem - r * 64;
+                const long row = (long)t0 + r;
+                const bool ok = row < r_end;
+                const double* src = Ksave + (ok ? row : (long)r_begin) * MP + (which ? bj : bi) * 128 + cv * 2;
+                cp_async16_zfill(base + (long)which * RK * LD + (long)r * LD + cv * 2, src, ok);
+            }
+            if (tid < RK) {
+                const long row = (long)t0 + tid;
+                s_dv[st * RK + tid] = row < r_end ? dv[row * Do + d] : 0.0;
+            }
+        }
+        cp_async_commit();   // always commit (possibly empty) so the group counting stays uniform
+    };
+
+    issue(0);
+    issue(1);
+    for (int c = 0; c < nchunk; c++) {
+        cp_async_wait<STAGES - 2>();
+        sync_threads();
+        issue(c + 2);
+        const int st = c % STAGES;
+        const double* As = (const double*)(smem + (size_t)st * C::stage_bytes) + rw * 32 + g;
+        const double* Bs = (const double*)(smem + (size_t)st * C::stage_bytes) + RK * LD + cw * 64 + g;
+        GPB_UNROLL
+        for (int k4 = 0; k4 < RK; k4 += 4) {
+            const double w = s_dv[st * RK + k4 + t];
+            double af[4], bf[8];
+            GPB_UNROLL
+            for (int i = 0; i < 4; i++) af[i] = As[(k4 + t) * LD + i * 8] * w;
+            GPB_UNROLL
+            for (int j = 0; j < 8; j++) bf[j] = Bs[(k4 + t) * LD + j * 8];
+            GPB_UNROLL
+            for (int i = 0; i < 4; i++)
+                GPB_UNROLL
+                for (int j = 0; j < 8; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    const int nbu = nb * (nb + 1) / 2;
+    double* out = part + (((long)blockIdx.y * Do + d) * nbu + blockIdx.x) * (128 * 128);
+    GPB_UNROLL
+    for (int i = 0; i < 4; i++) {
+        const int oi = rw * 32 + i * 8 + g;
+        GPB_UNROLL
+        for (int j = 0; j < 8; j++) {
+            const int oj = cw * 64 + j * 8 + 2 * t;
+            *(double2*)(out + oi * 128 + oj) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
     }
 }

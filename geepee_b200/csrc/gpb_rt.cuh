@@ -31,6 +31,12 @@ GPB_DEVICE void sync_warp() { __syncwarp(); }
 GPB_DEVICE double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE void atomic_add(double* p, double v) { atomicAdd(p, v); }
+// FP64 tensor-core MMA (DMMA.8x8x4): C[8x8] += A[8x4] * B[4x8].  Fragments, with g = lane / 4 and
+// t = lane % 4:  a = A[g][t],  b = B[t][g],  c0 = C[g][2t],  c1 = C[g][2t+1].
+GPB_DEVICE void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // 16-byte async global->shared copy (LDGSTS).  Both pointers 16B aligned.
 GPB_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -87,6 +93,7 @@ extern dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 extern unsigned char* dyn_smem;
 void barrier();                       // yield until every fiber of the block arrives
 double shfl_xor_f64(double v, int m);  // warp exchange through a mailbox
+double shfl_idx_f64(double v, int src); // read `v` of lane `src`
 }  // namespace gpb_emu
 
 #define threadIdx (gpb_emu::t_threadIdx)
@@ -101,6 +108,17 @@ static inline void sync_warp() { (void)gpb_emu::shfl_xor_f64(0.0, 0); }   // war
 static inline double shfl_xor(double v, int m) { return gpb_emu::shfl_xor_f64(v, m); }
 static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f64((double)v, m); }
 static inline void atomic_add(double* p, double v) { *p += v; }
+// emulated DMMA: same fragment layout as the PTX instruction, operands exchanged lane to lane
+static inline void dmma(double& c0, double& c1, double a, double b) {
+    const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; k++) {
+        const double ak = gpb_emu::shfl_idx_f64(a, g * 4 + k);
+        const double b0 = gpb_emu::shfl_idx_f64(b, (2 * t) * 4 + k);
+        const double b1 = gpb_emu::shfl_idx_f64(b, (2 * t + 1) * 4 + k);
+        c0 += ak * b0;
+        c1 += ak * b1;
+    }
+}
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async16_zfill(void* d, const void* s, bool valid) {
     if (valid) memcpy(d, s, 16); else memset(d, 0, 16);

@@ -82,6 +82,15 @@ double shfl_xor_f64(double v, int m) {
     return fibers[cur].res;
 }
 
+double shfl_idx_f64(double v, int src) {
+    Fiber& f = fibers[cur];
+    f.state = AT_SHFL;
+    f.val = v;
+    f.mask = 0x100 | (src & 31);   // bit 8: indexed read instead of xor
+    swapcontext(&f.ctx, &sched);
+    return fibers[cur].res;
+}
+
 void run_block(void (*tramp)(void*), void* ctx) {
     g_tramp = tramp;
     g_ctx = ctx;
@@ -117,7 +126,8 @@ void run_block(void (*tramp)(void*), void* ctx) {
             if (!(all && any)) continue;
             for (int i = w0; i < w1; i++)
                 if (fibers[i].state == AT_SHFL) {
-                    int p = w0 + (((i - w0) ^ fibers[i].mask) & 31);
+                    int p = (fibers[i].mask & 0x100) ? w0 + (fibers[i].mask & 31)
+                                                     : w0 + (((i - w0) ^ fibers[i].mask) & 31);
                     fibers[i].res = (p < w1 && fibers[p].state == AT_SHFL) ? fibers[p].val : fibers[i].val;
                 }
             for (int i = w0; i < w1; i++)
