@@ -41,8 +41,8 @@ _SIGS = {
                      [c_dp, c_dp, ctypes.c_size_t, c_dp]),
     'gpb_mm_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 5),
     'gpb_mm_fwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 7 + [ctypes.c_int] * 4 +
-                   [c_dp, c_dp, c_dp, c_dp, ctypes.c_size_t, c_dp]),
-    'gpb_mm_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 11 + [ctypes.c_int] * 4 + [c_dp] * 9 +
+                   [c_dp, c_dp, c_dp, c_dp, c_dp, ctypes.c_size_t, c_dp]),
+    'gpb_mm_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 12 + [ctypes.c_int] * 4 + [c_dp] * 9 +
                    [ctypes.c_size_t, c_dp]),
     'gpb_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'gpb_profile_collect': (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),

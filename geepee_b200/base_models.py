@@ -215,7 +215,7 @@ class Base_SDGPR(Base_Model):
             if i == 0:
                 mf, vf, _ = layer._fwd_det(x, cav=False, save=False)
             else:
-                mf, vf, _ = layer._fwd_mm(mf, vf, cav=False)
+                mf, vf, _ = layer._fwd_mm(mf, vf, cav=False, save=False)
         return mf.cpu().numpy(), vf.cpu().numpy()
 
     def predict_y(self, inputs):

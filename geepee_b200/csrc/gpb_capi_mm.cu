@@ -8,7 +8,7 @@ struct MMPlan {
     int Qt, DOC, RP, PC;
     long P, PP;
     int nchunks, nsplit, rows_per_split, npass;
-    int rows_grid, cols_grid, cols_rows_per_block;
+    int rows_grid, cols_grid, cols_rows_per_block, fwd_grid;
     // workspace byte offsets are carved in order by mm_carve
 };
 int q_template(int Q) {
@@ -45,9 +45,12 @@ MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do) {
     rps = cdiv(rps, TR) * TR;
     p.rows_per_split = (int)rps;
     p.nsplit = (int)cdiv(n, rps);
-    p.rows_grid = (int)cdiv(n, 128);
-    if (p.rows_grid > 4 * sm_count()) p.rows_grid = 4 * sm_count();
+    p.rows_grid = (int)cdiv(n, 8);               // one warp per row, 8 rows per block trip
+    if (p.rows_grid > 8 * sm_count()) p.rows_grid = 8 * sm_count();
     if (p.rows_grid < 1) p.rows_grid = 1;
+    p.fwd_grid = (int)cdiv(n, 32);               // psi1 forward: row tiles of 32
+    if (p.fwd_grid > 2 * sm_count()) p.fwd_grid = 2 * sm_count();
+    if (p.fwd_grid < 1) p.fwd_grid = 1;
     int cb = 2 * sm_count();
     long crpb = cdiv(n, cb);
     if (crpb < 32) crpb = 32;
@@ -150,6 +153,66 @@ int mm_pairs_dispatch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
     return fail(GPB_ERR_ARG, "mm: input dim template %d unsupported", p.Qt);
 }
 
+template <typename T, int QT>
+int mm_psi1_fwd_launch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                       const double* ls, const double* sf, const double* A, const double* vacc, int n,
+                       int M, int Q, int Do, double* mout, double* vout, double* psi1save, void* stream) {
+    auto kern = gpb::mm_psi1_fwd_kernel<T, QT>;
+    size_t smem = sizeof(double) * ((size_t)32 * (M + 1) + 32 + 1024 + QT) + sizeof(T) * 2 * 32 * QT;
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    prof_begin(7, stream);
+    GPB_LAUNCH(kern, dim3(p.fwd_grid), dim3(256), smem, stream, mx, vx, z, ls, sf, A, vacc, n, M, Q, Do,
+               mout, vout, psi1save);
+    prof_end(7, stream);
+    return GPB_CHECK_LAUNCH();
+}
+template <int QT>
+int mm_rows_bwd_launch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                       const double* ls, const double* sf, const double* A, const double* dm,
+                       const double* dv, const double* mout, const double* vacc, const double* rowacc,
+                       const double* psi1, int n, int M, int Q, int Do, double* dmx, double* dvx,
+                       double* rowpart, void* stream) {
+    auto kern = gpb::mm_rows_bwd_kernel<QT>;
+    size_t smem = sizeof(double) * ((size_t)QT * M + (size_t)Do * M + 8 * (size_t)Do + 8 * (QT + 2));
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    prof_begin(5, stream);
+    GPB_LAUNCH(kern, dim3(p.rows_grid), dim3(256), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout, vacc,
+               rowacc, psi1, n, M, Q, Do, dmx, dvx, rowpart);
+    prof_end(5, stream);
+    return GPB_CHECK_LAUNCH();
+}
+#define GPB_QT_SWITCH(CALL)                                   \
+    switch (p.Qt) {                                           \
+        case 1: return CALL(1);                               \
+        case 2: return CALL(2);                               \
+        case 3: return CALL(3);                               \
+        case 4: return CALL(4);                               \
+        case 5: return CALL(5);                               \
+        case 6: return CALL(6);                               \
+        case 8: return CALL(8);                               \
+        case 16: return CALL(16);                             \
+    }                                                         \
+    return fail(GPB_ERR_ARG, "mm: input dim template %d unsupported", p.Qt)
+template <typename T>
+int mm_psi1_fwd_dispatch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                         const double* ls, const double* sf, const double* A, const double* vacc, int n,
+                         int M, int Q, int Do, double* mout, double* vout, double* psi1save, void* stream) {
+#define GPB_CALL(QT) mm_psi1_fwd_launch<T, QT>(p, mx, vx, z, ls, sf, A, vacc, n, M, Q, Do, mout, vout, psi1save, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
+int mm_rows_bwd_dispatch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                         const double* ls, const double* sf, const double* A, const double* dm,
+                         const double* dv, const double* mout, const double* vacc, const double* rowacc,
+                         const double* psi1, int n, int M, int Q, int Do, double* dmx, double* dvx,
+                         double* rowpart, void* stream) {
+#define GPB_CALL(QT) mm_rows_bwd_launch<QT>(p, mx, vx, z, ls, sf, A, dm, dv, mout, vacc, rowacc, psi1, n, M, Q, Do, dmx, dvx, rowpart, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
+
 template <typename T>
 int mm_check(int n, int M, int Q, int Do) {
     if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
@@ -161,7 +224,7 @@ int mm_check(int n, int M, int Q, int Do) {
 template <typename T>
 int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
              const double* A, const double* B, int n, int M, int Q, int Do, double* mout,
-             double* vout, double* vacc, void* ws, size_t ws_bytes, void* stream) {
+             double* vout, double* vacc, double* psi1save, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
     if (rc) return rc;
     MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do);
@@ -184,20 +247,14 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
     }
     rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;
-    auto fin = gpb::mm_psi1_fwd_kernel<T>;
-    const int nt = 128;
-    size_t smem = sizeof(double) * Do * nt + sizeof(T) * ((size_t)M * Q + (size_t)Do * M + 2 * (size_t)Q * nt);
-    rc = allow_smem(fin, smem);
-    if (rc) return rc;
-    GPB_LAUNCH(fin, dim3(p.rows_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, w.rowacc, n, M, Q,
-               Do, mout, vout);
-    return GPB_CHECK_LAUNCH();
+    if (M > 512) return fail(GPB_ERR_ARG, "mm: M=%d unsupported (max 512)", M);
+    return mm_psi1_fwd_dispatch<T>(p, mx, vx, z, ls, sf, A, w.rowacc, n, M, Q, Do, mout, vout, psi1save, stream);
 }
 
 template <typename T>
 int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* ls, const double* sf,
              const double* A, const double* B, const double* dm, const double* dv,
-             const double* mout, const double* vacc, int n, int M, int Q, int Do, double* dA,
+             const double* mout, const double* vacc, const double* psi1, int n, int M, int Q, int Do, double* dA,
              double* dB, double* dzu, double* dl, double* dsf2, double* dvsum, double* dmx,
              double* dvx, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
@@ -234,27 +291,20 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
     }
     rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;
-    {   // row-wise epilogue: dmx, dvx + row-summed hyper terms
-        auto kern = gpb::mm_rows_bwd_kernel<T>;
-        const int nt = 128;
-        size_t smem = sizeof(double) * (16 + (size_t)(4 * Q + Do) * nt) + sizeof(T) * ((size_t)M * Q + (size_t)Do * M);
-        rc = allow_smem(kern, smem);
-        if (rc) return rc;
-        prof_begin(5, stream);
-        GPB_LAUNCH(kern, dim3(p.rows_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout,
-                   vacc, w.rowacc, n, M, Q, p.Qt, Do, dmx, dvx, w.rowpart);
-        prof_end(5, stream);
-        GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
-                   (long)(2 + Q), w.rowsum, 0);
-    }
+    // row-wise epilogue: dmx, dvx + row-summed hyper terms
+    rc = mm_rows_bwd_dispatch(p, mx, vx, z, ls, sf, A, dm, dv, mout, vacc, w.rowacc, psi1, n, M, Q, Do, dmx,
+                              dvx, w.rowpart, stream);
+    if (rc) return rc;
+    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
+               (long)(2 + Q), w.rowsum, 0);
     {   // column-wise psi1 part: dA, dZ1
-        auto kern = gpb::mm_cols_bwd_kernel<T>;
+        auto kern = gpb::mm_cols_bwd_kernel;
         const int nt = 128;
-        size_t smem = sizeof(double) * ((size_t)32 * (2 * Q + 1 + Do) + (size_t)(2 * Q + 2 * Do) * nt);
+        size_t smem = sizeof(double) * ((size_t)32 * (2 * Q + Do) + (size_t)(2 * Q + 2 * Do) * nt);
         rc = allow_smem(kern, smem);
         if (rc) return rc;
         prof_begin(6, stream);
-        GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(nt), smem, stream, mx, vx, z, ls, sf, A, dm, dv, mout, n,
+        GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(nt), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1, n,
                    M, Q, Do, p.cols_rows_per_block, w.colpart);
         prof_end(6, stream);
         long len = (long)Do * M + (long)M * Q;
@@ -287,23 +337,24 @@ size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward) {
 
 int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
-               double* mout, double* vout, double* vacc, void* ws, size_t ws_bytes, void* stream) {
+               double* mout, double* vout, double* vacc, double* psi1save, void* ws, size_t ws_bytes,
+               void* stream) {
     if (!mx || !vx || !z || !ls || !sf || !A || !B || !mout || !vout || !vacc || !ws) return fail(GPB_ERR_ARG, "mm_fwd: null pointer");
-    if (prec == GPB_F64) return mm_fwd_t<double>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, ws, ws_bytes, stream);
-    return mm_fwd_t<float>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, ws, ws_bytes, stream);
+    if (prec == GPB_F64) return mm_fwd_t<double>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, psi1save, ws, ws_bytes, stream);
+    return mm_fwd_t<float>(mx, vx, z, ls, sf, A, B, n, M, Q, Do, mout, vout, vacc, psi1save, ws, ws_bytes, stream);
 }
 
 int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, const double* dm, const double* dv,
-               const double* mout, const double* vacc, int n, int M, int Q, int Do, double* dA,
+               const double* mout, const double* vacc, const double* psi1, int n, int M, int Q, int Do, double* dA,
                double* dB, double* dzu, double* dl, double* dsf2, double* dvsum, double* dmx,
                double* dvx, void* ws, size_t ws_bytes, void* stream) {
-    if (!mx || !vx || !z || !ls || !sf || !A || !B || !dm || !dv || !mout || !vacc || !dA || !dB || !dzu || !dl ||
+    if (!mx || !vx || !z || !ls || !sf || !A || !B || !dm || !dv || !mout || !vacc || !psi1 || !dA || !dB || !dzu || !dl ||
         !dsf2 || !dvsum || !dmx || !dvx || !ws)
         return fail(GPB_ERR_ARG, "mm_bwd: null pointer");
     if (prec == GPB_F64)
-        return mm_bwd_t<double>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
-    return mm_bwd_t<float>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+        return mm_bwd_t<double>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, psi1, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
+    return mm_bwd_t<float>(mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, psi1, n, M, Q, Do, dA, dB, dzu, dl, dsf2, dvsum, dmx, dvx, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

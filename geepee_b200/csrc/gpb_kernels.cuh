@@ -1438,48 +1438,105 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
 }
 
 // psi1 forward + moment matching epilogue (kernels.py:214-218,233; aep_models.py:195-198):
+//   psi1[n,m] = sf2 prod_q sqrt(l_q^2 c1_nq) exp(-1/2 sum_q (mu_nq - z_mq)^2 c1_nq),  c1 = 1/(S + l^2)
 //   mout[n,d] = sum_m A[d,m] psi1[n,m] ;  vout[n,d] = sf2 + vacc[n,d] - mout^2
-// thread per row, z/A staged in shared memory, per-thread row state in shared slots.
-template <typename T>
-GPB_KERNEL void mm_psi1_fwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
-                                   const double* __restrict__ z, const double* __restrict__ ls,
-                                   const double* __restrict__ sf, const double* __restrict__ A,
-                                   const double* __restrict__ vacc, int n, int M, int Q, int Do,
-                                   double* __restrict__ mout, double* __restrict__ vout) {
+// Row tiles of 32.  Phase A: thread per pseudo-point column (z_m in registers) fills the
+// psi1 tile in shared memory and -- coalesced -- the optional psi1 save buffer that both
+// backward kernels stream instead of re-evaluating the exponentials.  Phase B: each warp takes
+// 4 rows, lanes stride over the columns, warp reduction per (row, d).
+template <typename T> struct Psi1Dom;   // exponent scale folded into c1 (argument of exp is -e)
+template <> struct Psi1Dom<double> { static constexpr double kH = 0.5 * 64.0 / 0.693147180559945309417232; };
+template <> struct Psi1Dom<float> { static constexpr double kH = 0.5 * 1.4426950408889634074; };
+GPB_DEVICE double psi1_exp(double e, const double* tab, int lane16) { return exp_dom64(-e, tab, lane16); }
+GPB_DEVICE double psi1_exp(float e, const double*, int) {
+#ifndef GPB_CPU_EMU
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-e));
+    return (double)y;
+#else
+    return (double)exp2f(-e);
+#endif
+}
+
+template <typename T, int QT>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_psi1_fwd_kernel(
+    const double* __restrict__ mx, const double* __restrict__ vx, const double* __restrict__ z,
+    const double* __restrict__ ls, const double* __restrict__ sf, const double* __restrict__ A,
+    const double* __restrict__ vacc, int n, int M, int Q, int Do, double* __restrict__ mout,
+    double* __restrict__ vout, double* __restrict__ psi1save) {
+    constexpr int TR = 32, MAXC = 2;              // M <= 512: at most 2 columns per thread
     GPB_DYN_SMEM(smem);
-    double* acc = (double*)smem;              // [Do][blockDim]
-    T* zs = (T*)(acc + (long)Do * blockDim.x); // [M][Q]
-    T* As = zs + (long)M * Q;                 // [Do][M]
-    T* mu = As + (long)Do * M;                // [Q][blockDim]
-    T* c1 = mu + (long)Q * blockDim.x;        // [Q][blockDim]
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < M * Q; i += nt) zs[i] = (T)z[i];
-    for (int i = tid; i < Do * M; i += nt) As[i] = (T)A[i];
+    const int LDT = M + 1;
+    double* tile = (double*)smem;                 // [TR][LDT]
+    double* s_cn = tile + (long)TR * LDT;         // [TR]   sf2 * prod sqrt(l^2 c1)
+    double* tab = s_cn + TR;                      // [64*16]
+    double* s_l2 = tab + 1024;                    // [QT]
+    T* s_mu = (T*)(s_l2 + QT);                    // [TR][QT]
+    T* s_c1 = s_mu + TR * QT;                     // [TR][QT]  c1 * kH
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lane16 = tid & 15;
     const double sf2 = exp(2.0 * sf[0]);
-    sync_threads();
-    for (long row = (long)blockIdx.x * nt + tid; row < n; row += (long)gridDim.x * nt) {
-        double cn = 1.0;
-        for (int q = 0; q < Q; q++) {
-            double lq = exp(2.0 * ls[q]);
-            double cc = 1.0 / (vx[row * Q + q] + lq);
-            cn *= sqrt(lq * cc);
-            mu[q * nt + tid] = (T)mx[row * Q + q];
-            c1[q * nt + tid] = (T)cc;
-        }
-        for (int d = 0; d < Do; d++) acc[d * nt + tid] = 0;
-        for (int m = 0; m < M; m++) {
-            T e = 0;
-            for (int q = 0; q < Q; q++) {
-                T diff = mu[q * nt + tid] - zs[m * Q + q];
-                e += diff * diff * c1[q * nt + tid];
+    for (int i = tid; i < 1024; i += kThreads) tab[i] = exp2((double)(i >> 4) * (1.0 / 64.0));
+    if (tid < QT) s_l2[tid] = tid < Q ? exp(2.0 * ls[tid]) : 1.0;
+    T zr[MAXC][QT];
+    GPB_UNROLL
+    for (int c = 0; c < MAXC; c++) {
+        const int m = tid + c * kThreads;
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) zr[c][q] = (m < M && q < Q) ? (T)z[(long)m * Q + q] : (T)0;
+    }
+    const int ntiles = (n + TR - 1) / TR;
+    for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const int t0 = tile_i * TR;
+        const int tv = (n - t0) < TR ? (n - t0) : TR;
+        sync_threads();                            // previous tile consumed; tab / s_l2 visible
+        for (int i = tid; i < TR * QT; i += kThreads) {
+            const int r = i / QT, q = i - r * QT;
+            double mu = 0, cc = 0;
+            if (r < tv && q < Q) {
+                mu = mx[(long)(t0 + r) * Q + q];
+                cc = 1.0 / (vx[(long)(t0 + r) * Q + q] + s_l2[q]);
             }
-            double p1 = sf2 * cn * (double)fast_exp((T)(-0.5) * e);
-            for (int d = 0; d < Do; d++) acc[d * nt + tid] += (double)As[d * M + m] * p1;
+            s_mu[i] = (T)mu;
+            s_c1[i] = (T)(cc * Psi1Dom<T>::kH);
         }
-        for (int d = 0; d < Do; d++) {
-            double mo = acc[d * nt + tid];
-            mout[row * Do + d] = mo;
-            vout[row * Do + d] = sf2 + vacc[row * Do + d] - mo * mo;
+        if (tid < TR) {
+            double cn = sf2;
+            if (tid < tv)
+                for (int q = 0; q < Q; q++) cn *= sqrt(s_l2[q] / (vx[(long)(t0 + tid) * Q + q] + s_l2[q]));
+            s_cn[tid] = tid < tv ? cn : 0.0;
+        }
+        sync_threads();
+        GPB_UNROLL
+        for (int c = 0; c < MAXC; c++) {
+            const int m = tid + c * kThreads;
+            if (m < M) {
+                GPB_UNROLL_N(4)
+                for (int r = 0; r < TR; r++) {
+                    T e = 0;
+                    GPB_UNROLL
+                    for (int q = 0; q < QT; q++) {
+                        const T diff = s_mu[r * QT + q] - zr[c][q];
+                        e += diff * diff * s_c1[r * QT + q];
+                    }
+                    const double p = s_cn[r] * psi1_exp(e, tab, lane16);
+                    tile[(long)r * LDT + m] = p;
+                    if (psi1save != nullptr && r < tv) psi1save[(long)(t0 + r) * M + m] = p;
+                }
+            }
+        }
+        sync_threads();
+        for (int rr = 0; rr < 4; rr++) {
+            const int r = warp * 4 + rr;
+            if (r >= tv) continue;                 // warp-uniform
+            for (int d = 0; d < Do; d++) {
+                double acc = 0;
+                for (int m = lane; m < M; m += 32) acc += ldg(A + (long)d * M + m) * tile[(long)r * LDT + m];
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    mout[(long)(t0 + r) * Do + d] = acc;
+                    vout[(long)(t0 + r) * Do + d] = sf2 + vacc[(long)(t0 + r) * Do + d] - acc * acc;
+                }
+            }
         }
     }
 }
@@ -1490,125 +1547,131 @@ GPB_KERNEL void mm_psi1_fwd_kernel(const double* __restrict__ mx, const double* 
 //   part[blk][0]      : dsf2  = sum_n (sum_m L1 + 2 s_n)/sf2
 //   part[blk][1+q]    : dl_q  (psi1: Zmu2_denom.. , psi2: the n-dependent terms of kernels.py:441-442)
 //   part[blk][1+Q]    : sum of scaled dv  (dv_sum, aep_models.py:247)
-template <typename T>
-GPB_KERNEL void mm_rows_bwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
-                                   const double* __restrict__ z, const double* __restrict__ ls,
-                                   const double* __restrict__ sf, const double* __restrict__ A,
-                                   const double* __restrict__ dm, const double* __restrict__ dv,
-                                   const double* __restrict__ mout, const double* __restrict__ vacc,
-                                   const double* __restrict__ rowacc,
-                                   int n, int M, int Q, int Qt, int Do, double* __restrict__ dmx,
-                                   double* __restrict__ dvx, double* __restrict__ part) {
+// One warp per row: lanes stride over the pseudo-points and stream the saved psi1 row
+// (coalesced); z^T and A sit in shared memory; the 1+2Q row sums are warp-reduced and lane q
+// finishes input dimension q.
+template <int QT>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_rows_bwd_kernel(
+    const double* __restrict__ mx, const double* __restrict__ vx, const double* __restrict__ z,
+    const double* __restrict__ ls, const double* __restrict__ sf, const double* __restrict__ A,
+    const double* __restrict__ dm, const double* __restrict__ dv, const double* __restrict__ mout,
+    const double* __restrict__ vacc, const double* __restrict__ rowacc,
+    const double* __restrict__ psi1, int n, int M, int Q, int Do, double* __restrict__ dmx,
+    double* __restrict__ dvx, double* __restrict__ part) {
     GPB_DYN_SMEM(smem);
-    double* red = (double*)smem;                 // [16]
-    double* slot = red + 16;                     // per-thread: [ (4Q + Do) ][blockDim]
-    const int tid = threadIdx.x, nt = blockDim.x;
-    T* zs = (T*)(slot + (long)(4 * Q + Do) * nt); // [M][Q]
-    T* As = zs + (long)M * Q;                    // [Do][M]
-    for (int i = tid; i < M * Q; i += nt) zs[i] = (T)z[i];
-    for (int i = tid; i < Do * M; i += nt) As[i] = (T)A[i];
+    double* zsT = (double*)smem;                  // [QT][M]
+    double* As = zsT + (long)QT * M;              // [Do][M]
+    double* s_dma = As + (long)Do * M;            // [8][Do]
+    double* s_red = s_dma + 8 * Do;               // [8][QT + 2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < QT * M; i += kThreads) {
+        const int q = i / M, m = i - q * M;
+        zsT[i] = q < Q ? z[(long)m * Q + q] : 0.0;
+    }
+    for (int i = tid; i < Do * M; i += kThreads) As[i] = A[i];
     const double sf2 = exp(2.0 * sf[0]);
-    double* s_mu = slot;                // [Q][nt]
-    double* s_c1 = slot + (long)Q * nt;
-    double* s_dmu = slot + 2L * Q * nt;
-    double* s_dS = slot + 3L * Q * nt;
-    double* s_dma = slot + 4L * Q * nt;  // [Do][nt]  dm_all
     sync_threads();
-    double p_sf2 = 0, p_dvsum = 0;
-    // dl partials live in registers only through the final reduction: accumulate in smem slots
-    // (reuse: one extra array of Q per thread would cost more smem; loop q outermost at the end)
-    // -> keep a small per-thread array via second sweep over q (cheap: per row, not per m)
-    double p_dl[16];
-    for (int q = 0; q < 16; q++) p_dl[q] = 0;
-    const int NS = 2 * Qt;
-    for (long row = (long)blockIdx.x * nt + tid; row < n; row += (long)gridDim.x * nt) {
-        double cn = 1.0;
-        for (int q = 0; q < Q; q++) {
-            double lq = exp(2.0 * ls[q]);
-            double cc = 1.0 / (vx[row * Q + q] + lq);
-            cn *= sqrt(lq * cc);
-            s_mu[q * nt + tid] = mx[row * Q + q];
-            s_c1[q * nt + tid] = cc;
-            s_dmu[q * nt + tid] = 0;
-            s_dS[q * nt + tid] = 0;
+    const int NS = 2 * QT;
+    double p_sf2 = 0, p_dvsum = 0, p_dl = 0;      // lane 0 / lane 0 / lane q
+    double* dma = s_dma + warp * Do;
+    for (long row = (long)blockIdx.x * 8 + warp; row < n; row += (long)gridDim.x * 8) {
+        double mu[QT], c1[QT], dmu[QT], dS[QT];
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) {
+            mu[q] = q < Q ? mx[row * Q + q] : 0.0;
+            c1[q] = q < Q ? 1.0 / (vx[row * Q + q] + exp(2.0 * ls[q])) : 0.0;
+            dmu[q] = 0;
+            dS[q] = 0;
         }
-        double s = 0;   // sum_p Lam = sum_d dv_d * (forward sum_p bs[d,p] psi2[n,p])
-        for (int d = 0; d < Do; d++) {
-            double dvd = dv[row * Do + d];
-            s_dma[d * nt + tid] = dm[row * Do + d] - 2.0 * dvd * mout[row * Do + d];
-            p_dvsum += dvd;
+        double s = 0, dvs = 0;
+        sync_warp();                               // previous row's dma fully consumed
+        for (int d = lane; d < Do; d += 32) {
+            const double dvd = dv[row * Do + d];
+            dma[d] = dm[row * Do + d] - 2.0 * dvd * mout[row * Do + d];
+            dvs += dvd;
             s += dvd * vacc[row * Do + d];
         }
+        sync_warp();
+        s = warp_sum(s);                           // sum_p Lam = sum_d dv_d * forward vacc_d
+        dvs = warp_sum(dvs);
         double L1sum = 0;
-        for (int m = 0; m < M; m++) {
-            T e = 0;
-            for (int q = 0; q < Q; q++) {
-                T diff = (T)s_mu[q * nt + tid] - zs[m * Q + q];
-                e += diff * diff * (T)s_c1[q * nt + tid];
-            }
-            double p1 = sf2 * cn * (double)fast_exp((T)(-0.5) * e);
+        for (int m = lane; m < M; m += 32) {
+            const double p1 = psi1[row * M + m];
             double g = 0;
-            for (int d = 0; d < Do; d++) g += s_dma[d * nt + tid] * (double)As[d * M + m];
-            double L1 = g * p1;
+            for (int d = 0; d < Do; d++) g += dma[d] * As[(long)d * M + m];
+            const double L1 = g * p1;
             L1sum += L1;
-            for (int q = 0; q < Q; q++) {
-                double c = s_c1[q * nt + tid];
-                double zm = (double)zs[m * Q + q] - s_mu[q * nt + tid];
-                s_dmu[q * nt + tid] += L1 * zm * c;
-                s_dS[q * nt + tid] += L1 * (zm * zm * c - 1.0) * c;   // x 1/2 below
+            GPB_UNROLL
+            for (int q = 0; q < QT; q++) {
+                const double zm = zsT[(long)q * M + m] - mu[q];
+                const double w = zm * c1[q];
+                dmu[q] += L1 * w;
+                dS[q] += L1 * (zm * w - 1.0) * c1[q];   // x 1/2 below
             }
         }
-        p_sf2 += (L1sum + 2.0 * s) / sf2;
-        for (int q = 0; q < Q; q++) {
+        L1sum = warp_sum(L1sum);
+        double my_dmu = 0, my_dS = 0, my_mu = 0, my_c1 = 0;
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) {
+            const double a = warp_sum(dmu[q]), b = warp_sum(dS[q]);
+            if (q == lane) { my_dmu = a; my_dS = b; my_mu = mu[q]; my_c1 = c1[q]; }
+        }
+        if (lane == 0) {
+            p_sf2 += (L1sum + 2.0 * s) / sf2;
+            p_dvsum += dvs;
+        }
+        if (lane < Q) {
+            const int q = lane;
             const double l = exp(ls[q]), lq = l * l;
-            const double S = vx[row * Q + q], mu = s_mu[q * nt + tid];
-            const double c1 = s_c1[q * nt + tid];
+            const double S = vx[row * Q + q];
             const double c2 = 1.0 / (2.0 * S + lq);
-            const double U = rowacc[row * NS + q], V = rowacc[row * NS + Qt + q];
+            const double U = rowacc[row * NS + q], V = rowacc[row * NS + QT + q];
             // psi1: sum_m L1 ((z-mu)^2 c1 + S/l^2) c1 l  =  (dS_acc + (1 + S/l^2) L1sum c1) l
-            double dl1 = (s_dS[q * nt + tid] + (1.0 + S / lq) * c1 * L1sum) * l;
+            const double dl1 = (my_dS + (1.0 + S / lq) * my_c1 * L1sum) * l;
             // psi2 (n-dependent part of kernels.py:441-442)
-            double dl2 = 2.0 * l * ((S / lq * c2 + mu * mu * c2 * c2) * s - 2.0 * mu * c2 * c2 * U + c2 * c2 * V);
-            if (q < 16) p_dl[q] += dl1 + dl2;
-            dmx[row * Q + q] = s_dmu[q * nt + tid] - 2.0 * c2 * (mu * s - U);
-            dvx[row * Q + q] = 0.5 * s_dS[q * nt + tid] +
-                               2.0 * c2 * c2 * (mu * mu * s - 2.0 * mu * U + V) - c2 * s;
+            const double dl2 = 2.0 * l * ((S / lq * c2 + my_mu * my_mu * c2 * c2) * s -
+                                          2.0 * my_mu * c2 * c2 * U + c2 * c2 * V);
+            p_dl += dl1 + dl2;
+            dmx[row * Q + q] = my_dmu - 2.0 * c2 * (my_mu * s - U);
+            dvx[row * Q + q] = 0.5 * my_dS + 2.0 * c2 * c2 * (my_mu * my_mu * s - 2.0 * my_mu * U + V) - c2 * s;
         }
     }
-    double r = block_sum(p_sf2, red);
-    if (tid == 0) part[(long)blockIdx.x * (2 + Q)] = r;
-    for (int q = 0; q < Q; q++) {
-        r = block_sum(p_dl[q < 16 ? q : 15], red);
-        if (tid == 0) part[(long)blockIdx.x * (2 + Q) + 1 + q] = r;
+    // per-block partials: sum the 8 warps
+    double* rr = s_red + warp * (QT + 2);
+    if (lane == 0) { rr[0] = p_sf2; rr[1] = p_dvsum; }
+    if (lane < QT) rr[2 + lane] = p_dl;
+    sync_threads();
+    if (tid < Q + 2) {
+        const int k = tid == 0 ? 0 : (tid == Q + 1 ? 1 : 2 + (tid - 1));   // -> [sf2 | dl_q | dvsum]
+        double acc = 0;
+        for (int w = 0; w < 8; w++) acc += s_red[w * (QT + 2) + k];
+        part[(long)blockIdx.x * (2 + Q) + tid] = acc;
     }
-    r = block_sum(p_dvsum, red);
-    if (tid == 0) part[(long)blockIdx.x * (2 + Q) + 1 + Q] = r;
 }
 
 // Backward, column-wise psi1 part (kernels.py:355-378 terms indexed by m; aep_models.py:239):
 //   dA[d,m] = sum_n dm_all[n,d] psi1[n,m] ;  dZ1[m,q] = -sum_n L1 (z_mq - mu_nq) c1_nq
-// thread per pseudo point m, rows of this block's range staged in shared memory.
+// thread per pseudo point m, rows of this block's range staged in shared memory, psi1 streamed
+// (coalesced) from the forward's save buffer.
 // partial record per block: [ dA (Do*M) | dZ1 (M*Q) ]
-template <typename T>
 GPB_KERNEL void mm_cols_bwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
                                    const double* __restrict__ z, const double* __restrict__ ls,
-                                   const double* __restrict__ sf, const double* __restrict__ A,
+                                   const double* __restrict__ A,
                                    const double* __restrict__ dm, const double* __restrict__ dv,
-                                   const double* __restrict__ mout, int n, int M, int Q, int Do,
+                                   const double* __restrict__ mout, const double* __restrict__ psi1,
+                                   int n, int M, int Q, int Do,
                                    int rows_per_block, double* __restrict__ part) {
     constexpr int TR = 32;
     GPB_DYN_SMEM(smem);
     double* s_mu = (double*)smem;         // [TR][Q]
     double* s_c1 = s_mu + TR * Q;          // [TR][Q]
-    double* s_cn = s_c1 + TR * Q;          // [TR]
-    double* s_dma = s_cn + TR;             // [TR][Do]
+    double* s_dma = s_c1 + TR * Q;         // [TR][Do]
     const int tid = threadIdx.x, nt = blockDim.x;
     double* slot = s_dma + TR * Do;        // per-thread [Q (z) + Q (dZ) + Do (A) + Do (dA)][nt]
     double* t_z = slot;
     double* t_dz = slot + (long)Q * nt;
     double* t_A = slot + 2L * Q * nt;
     double* t_dA = slot + (2L * Q + Do) * nt;
-    const double sf2 = exp(2.0 * sf[0]);
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = (r_begin + rows_per_block) < n ? (r_begin + rows_per_block) : n;
     double* rec = part + (long)blockIdx.x * ((long)Do * M + (long)M * Q);
@@ -1626,36 +1689,28 @@ GPB_KERNEL void mm_cols_bwd_kernel(const double* __restrict__ mx, const double* 
         for (int t0 = r_begin; t0 < r_end; t0 += TR) {
             const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
             sync_threads();
-            for (int r = tid; r < TR; r += nt) {
-                double cn = 1.0;
-                for (int q = 0; q < Q; q++) {
-                    double lq = exp(2.0 * ls[q]);
-                    double cc = r < tv ? 1.0 / (vx[(long)(t0 + r) * Q + q] + lq) : 0.0;
-                    if (r < tv) cn *= sqrt(lq * cc);
-                    s_mu[r * Q + q] = r < tv ? mx[(long)(t0 + r) * Q + q] : 0.0;
-                    s_c1[r * Q + q] = cc;
-                }
-                s_cn[r] = r < tv ? cn : 0.0;
-                for (int d = 0; d < Do; d++)
-                    s_dma[r * Do + d] = r < tv ? dm[(long)(t0 + r) * Do + d] -
-                                                     2.0 * dv[(long)(t0 + r) * Do + d] * mout[(long)(t0 + r) * Do + d]
-                                               : 0.0;
+            for (int i = tid; i < TR * Q; i += nt) {
+                const int r = i / Q, q = i - r * Q;
+                const bool ok = r < tv;
+                s_mu[i] = ok ? mx[(long)(t0 + r) * Q + q] : 0.0;
+                s_c1[i] = ok ? 1.0 / (vx[(long)(t0 + r) * Q + q] + exp(2.0 * ls[q])) : 0.0;
+            }
+            for (int i = tid; i < TR * Do; i += nt) {
+                const int r = i / Do, d = i - r * Do;
+                s_dma[i] = r < tv ? dm[(long)(t0 + r) * Do + d] -
+                                        2.0 * dv[(long)(t0 + r) * Do + d] * mout[(long)(t0 + r) * Do + d]
+                                  : 0.0;
             }
             sync_threads();
             if (act)
                 for (int r = 0; r < tv; r++) {
-                    T e = 0;
-                    for (int q = 0; q < Q; q++) {
-                        T diff = (T)s_mu[r * Q + q] - (T)t_z[q * nt + tid];
-                        e += diff * diff * (T)s_c1[r * Q + q];
-                    }
-                    double p1 = sf2 * s_cn[r] * (double)fast_exp((T)(-0.5) * e);
+                    const double p1 = psi1[(long)(t0 + r) * M + m];
                     double g = 0;
                     for (int d = 0; d < Do; d++) {
                         g += s_dma[r * Do + d] * t_A[d * nt + tid];
                         t_dA[d * nt + tid] += s_dma[r * Do + d] * p1;
                     }
-                    double L1 = g * p1;
+                    const double L1 = g * p1;
                     for (int q = 0; q < Q; q++)
                         t_dz[q * nt + tid] -= L1 * (t_z[q * nt + tid] - s_mu[r * Q + q]) * s_c1[r * Q + q];
                 }

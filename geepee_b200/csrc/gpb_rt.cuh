@@ -94,6 +94,7 @@ extern unsigned char* dyn_smem;
 void barrier();                       // yield until every fiber of the block arrives
 double shfl_xor_f64(double v, int m);  // warp exchange through a mailbox
 double shfl_idx_f64(double v, int src); // read `v` of lane `src`
+void dmma_f64(double a, double b, double* d0, double* d1);  // one 8x8x4 MMA: returns A.B for this lane
 }  // namespace gpb_emu
 
 #define threadIdx (gpb_emu::t_threadIdx)
@@ -110,14 +111,10 @@ static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f
 static inline void atomic_add(double* p, double v) { *p += v; }
 // emulated DMMA: same fragment layout as the PTX instruction, operands exchanged lane to lane
 static inline void dmma(double& c0, double& c1, double a, double b) {
-    const int lane = (int)(threadIdx.x & 31), g = lane >> 2, t = lane & 3;
-    for (int k = 0; k < 4; k++) {
-        const double ak = gpb_emu::shfl_idx_f64(a, g * 4 + k);
-        const double b0 = gpb_emu::shfl_idx_f64(b, (2 * t) * 4 + k);
-        const double b1 = gpb_emu::shfl_idx_f64(b, (2 * t + 1) * 4 + k);
-        c0 += ak * b0;
-        c1 += ak * b1;
-    }
+    double d0, d1;
+    gpb_emu::dmma_f64(a, b, &d0, &d1);
+    c0 += d0;
+    c1 += d1;
 }
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async16_zfill(void* d, const void* s, bool valid) {

@@ -260,20 +260,21 @@ class Base_SGP_Layer(object):
         return {'dA': dA, 'dB': dB, 'dzu': dzu, 'dl': dl, 'dsf2': dsf2,
                 'dvsum': dv.sum().reshape(1)}
 
-    def _fwd_mm(self, mx, vx, cav):
-        """a6 on the device."""
+    def _fwd_mm(self, mx, vx, cav, save=True):
+        """a6 on the device (save=False: prediction, nothing kept for a backward)."""
         t = self._t
         A, B = self._AB(cav, True)
-        m, v, vacc = ops.mm_fwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous())
-        return m, v, (mx, vx, cav, m, vacc)
+        m, v, vacc, psi1 = ops.mm_fwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(),
+                                      B.contiguous(), save=save)
+        return m, v, (mx, vx, cav, m, vacc, psi1)
 
     def _bwd_mm(self, ctx, dm, dv):
         """a9 per-row part: statistics + per-row input gradients."""
         t = self._t
-        mx, vx, cav, mout, vacc = ctx
+        mx, vx, cav, mout, vacc, psi1 = ctx
         A, B = self._AB(cav, True)
         return ops.mm_bwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous(),
-                          dm, dv, mout, vacc)
+                          dm, dv, mout, vacc, psi1)
 
     # ---- shared chain rules ------------------------------------------------------------------
     def _pack_eta1(self, dtheta1):
@@ -332,7 +333,7 @@ class Base_SGP_Layer(object):
             return m.cpu().numpy(), v.cpu().numpy()
         if mode == config.PROP_MM:
             a, b = to_dev(mx, dev), to_dev(vx, dev)
-            m, v, _ = self._fwd_mm(a, b, cav=False)
+            m, v, _ = self._fwd_mm(a, b, cav=False, save=False)
             if return_info:
                 t = self._t
                 p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
@@ -467,7 +468,7 @@ class AEP_SGP_Layer(Base_SGP_Layer):
             return m.cpu().numpy(), v.cpu().numpy(), ops.kmat(x, t['zu'], t['ls'], t['sf']).cpu().numpy()
         if mode == config.PROP_MM:
             a, b = to_dev(mx, dev), to_dev(vx, dev)
-            m, v, _ = self._fwd_mm(a, b, cav=True)
+            m, v, _ = self._fwd_mm(a, b, cav=True, save=False)
             p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
             return m.cpu().numpy(), v.cpu().numpy(), p1.cpu().numpy(), p2.cpu().numpy()
         if mode in (config.PROP_MC, config.PROP_LIN):

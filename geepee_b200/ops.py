@@ -157,25 +157,27 @@ def det_syrk(prec, Ks, dv, M):
     return dB
 
 
-def mm_fwd(prec, mx, vx, z, ls, sf, A, B):
+def mm_fwd(prec, mx, vx, z, ls, sf, A, B, save=True):
     """aep_models.py:183-199 / base_models.py:286-307; psi2 stays on chip.
-    Returns mout, vout and vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b] (reused by mm_bwd)."""
+    Returns mout, vout and the two buffers mm_bwd reuses: vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b]
+    and (save=True) psi1[n,M]."""
     lib = _lib.get()
     n, Q = mx.shape
     Do, M = A.shape
     mout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
     vout = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
     vacc = torch.empty((n, Do), dtype=torch.float64, device=mx.device)
+    psi1 = torch.empty((n, M), dtype=torch.float64, device=mx.device) if save else None
     ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 0), mx)
     _chk(lib.gpb_mm_fwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
-                        _p(_c(B)), n, M, Q, Do, _p(mout), _p(vout), _p(vacc), _p(ws), ws.numel(),
+                        _p(_c(B)), n, M, Q, Do, _p(mout), _p(vout), _p(vacc), _p(psi1), _p(ws), ws.numel(),
                         _stream(mx)), 'mm_fwd')
-    return mout, vout, vacc
+    return mout, vout, vacc, psi1
 
 
-def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc):
+def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, psi1):
     """aep_models.py:238-250 + kernels.py:302-309,355-378,402-444.
-    mout, vacc: outputs of mm_fwd on the same inputs and the same B."""
+    mout, vacc, psi1: outputs of mm_fwd(save=True) on the same inputs and the same B."""
     lib = _lib.get()
     n, Q = mx.shape
     Do, M = A.shape
@@ -193,7 +195,7 @@ def mm_bwd(prec, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc):
     }
     ws = _ws(lib.gpb_mm_ws_bytes(n, M, Q, Do, 1), mx)
     _chk(lib.gpb_mm_bwd(prec, _p(_c(mx)), _p(_c(vx)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(_c(A)),
-                        _p(_c(B)), _p(_c(dm)), _p(_c(dv)), _p(_c(mout)), _p(_c(vacc)), n, M, Q, Do,
+                        _p(_c(B)), _p(_c(dm)), _p(_c(dv)), _p(_c(mout)), _p(_c(vacc)), _p(_c(psi1)), n, M, Q, Do,
                         _p(out['dA']), _p(out['dB']), _p(out['dzu']), _p(out['dl']), _p(out['dsf2']),
                         _p(out['dvsum']), _p(out['dmx']), _p(out['dvx']), _p(ws), ws.numel(),
                         _stream(mx)), 'mm_bwd')
@@ -211,7 +213,7 @@ def fma_peak(prec, iters, device, blocks_per_sm=0):
 
 
 PROFILE_SLOTS = ('det_fwd', 'det_bwd', 'det_syrk', 'mm_pairs_fwd', 'mm_pairs_bwd', 'mm_rows_bwd',
-                 'mm_cols_bwd', 'unused')
+                 'mm_cols_bwd', 'mm_psi1_fwd')
 
 
 def profile_enable(on):

@@ -99,25 +99,28 @@ int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, in
 /* ---- moment-matched (uncertain-input) layer ------------------------------------------------- */
 /* a6: aep_models.py:183-199 _forward_prop_random_thru_cav_mm (post twin base_models.py:286-307):
  *      mout = psi1 A^T, vout = sf2 + sum_ab B[d,a,b] psi2[n,a,b] - mout^2; psi2 never stored.
- *      Also returns vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b], which the backward reuses. */
+ *      Also returns vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b] and (if psi1save != NULL) psi1[n,M],
+ *      which the backward reuses instead of re-evaluating them. */
 size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward);
 int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
-               double* mout, double* vout, double* vacc, void* ws, size_t ws_bytes, void* stream);
+               double* mout, double* vout, double* vacc, double* psi1save, void* ws, size_t ws_bytes,
+               void* stream);
 /* a9 (per-row part): aep_models.py:238-250 + kernels.py:302-309,355-378,402-444
  *      (compute_psi_derivatives), vfe twin vfe_models.py:351-361.
- *      dm, dv scaled upstream gradients; mout, vacc from gpb_mm_fwd on the same inputs and B.
+ *      dm, dv scaled upstream gradients; mout, vacc, psi1 from gpb_mm_fwd on the same inputs and B.
  *      -> dA[Do,M] = sum_n dm_all psi1 ; dB[Do,M,M] = sum_n dv psi2 ; dzu[M,Q] ; dl[Q] ; dsf2[1] ;
  *         dvsum[1] = sum dv ; dmx[n,Q], dvx[n,Q] */
 int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, const double* dm,
-               const double* dv, const double* mout, const double* vacc, int n, int M, int Q, int Do,
+               const double* dv, const double* mout, const double* vacc, const double* psi1,
+               int n, int M, int Q, int Do,
                double* dA, double* dB, double* dzu, double* dl, double* dsf2, double* dvsum,
                double* dmx, double* dvx, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- per-kernel device timing for bench.py's roofline (CUDA events on the launching stream).
  *      slots: 0 det_fwd, 1 det_bwd, 2 det_syrk, 3 mm_pairs(fwd), 4 mm_pairs(bwd), 5 mm_rows_bwd,
- *      6 mm_cols_bwd, 7 unused.  collect() synchronises the recorded events, returns the summed
+ *      6 mm_cols_bwd, 7 mm_psi1_fwd.  collect() synchronises the recorded events, returns the summed
  *      milliseconds and launch counts per slot into HOST arrays of 8 and resets them. */
 int gpb_profile_enable(int on);
 int gpb_profile_collect(double* h_ms, long* h_count);

@@ -26,7 +26,7 @@ struct Fiber {
     ucontext_t ctx;
     unsigned char* stack;
     int state, mask;
-    double val, res;
+    double val, val2, res, res2;
 };
 static const size_t kStack = 256 * 1024;
 static std::vector<Fiber> fibers;
@@ -91,6 +91,19 @@ double shfl_idx_f64(double v, int src) {
     return fibers[cur].res;
 }
 
+// DMMA.8x8x4 in one warp rendezvous: every lane deposits its A and B fragment element, the
+// scheduler computes the lane's two C increments (fragment layout of the PTX instruction).
+void dmma_f64(double a, double b, double* d0, double* d1) {
+    Fiber& f = fibers[cur];
+    f.state = AT_SHFL;
+    f.val = a;
+    f.val2 = b;
+    f.mask = 0x200;
+    swapcontext(&f.ctx, &sched);
+    *d0 = fibers[cur].res;
+    *d1 = fibers[cur].res2;
+}
+
 void run_block(void (*tramp)(void*), void* ctx) {
     g_tramp = tramp;
     g_ctx = ctx;
@@ -125,7 +138,17 @@ void run_block(void (*tramp)(void*), void* ctx) {
             }
             if (!(all && any)) continue;
             for (int i = w0; i < w1; i++)
-                if (fibers[i].state == AT_SHFL) {
+                if (fibers[i].state == AT_SHFL && (fibers[i].mask & 0x200)) {
+                    const int l = i - w0, g = l >> 2, t = l & 3;
+                    double s0 = 0, s1 = 0;
+                    for (int k = 0; k < 4; k++) {
+                        const double ak = fibers[w0 + g * 4 + k].val;
+                        s0 += ak * fibers[w0 + (2 * t) * 4 + k].val2;
+                        s1 += ak * fibers[w0 + (2 * t + 1) * 4 + k].val2;
+                    }
+                    fibers[i].res = s0;
+                    fibers[i].res2 = s1;
+                } else if (fibers[i].state == AT_SHFL) {
                     int p = (fibers[i].mask & 0x100) ? w0 + (fibers[i].mask & 31)
                                                      : w0 + (((i - w0) ^ fibers[i].mask) & 31);
                     fibers[i].res = (p < w1 && fibers[p].state == AT_SHFL) ? fibers[p].val : fibers[i].val;

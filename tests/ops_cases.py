@@ -71,13 +71,13 @@ def check_mm_layer(n, M, Q, Do, prec, tol):
     p = problem(n, M, Q, Do, seed=7 * n + M, uncertain=True)
     mx, vx, z, ls, sf = T(p['x']), T(p['vx']), T(p['z']), T(p['ls']), T(p['sf'])
     A, B = T(p['A']), T(p['Bn'])
-    mout, vout, vacc = ops.mm_fwd(pr, mx, vx, z, ls, sf, A, B)
+    mout, vout, vacc, psi1s = ops.mm_fwd(pr, mx, vx, z, ls, sf, A, B)
     psi1, psi2 = go.psi_stats(2 * p['ls'], 2 * p['sf'], p['x'], p['vx'], p['z'])
     m_ref = np.einsum('nm,dm->nd', psi1, p['A'])
     v_ref = np.exp(2 * p['sf']) + np.einsum('dab,nab->nd', p['Bn'], psi2) - m_ref**2
     assert gu.rel_err(N(mout), m_ref) < tol
     assert gu.rel_err(N(vout), v_ref) < tol * 10
-    out = ops.mm_bwd(pr, mx, vx, z, ls, sf, A, B, T(p['dm']), T(p['dv']), T(m_ref), vacc)
+    out = ops.mm_bwd(pr, mx, vx, z, ls, sf, A, B, T(p['dm']), T(p['dv']), T(m_ref), vacc, psi1s)
     dm_all = p['dm'] - 2 * p['dv'] * m_ref
     dpsi1 = np.einsum('nd,dm->nm', dm_all, p['A'])
     dpsi2 = np.einsum('nd,dab->nab', p['dv'], p['Bn'])

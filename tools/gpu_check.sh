@@ -19,7 +19,7 @@ PY
 tail -3 gpurun_out/bench_$TAG.err
 grep '"mm_\|det_' gpurun_out/kbench_$TAG.log | cut -c1-200
 if [ "$2" != "noncu" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mm_pairs_kernel|det_fwd_kernel|det_syrk_kernel" -s 2 -c 4 -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mm_pairs_kernel|det_fwd|det_syrk_" -s 2 -c 4 -f \
     -o gpurun_out/prof_mm_pairs_$TAG python tools/ncu_target.py fp64 65536 > gpurun_out/ncu_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_$TAG.log
 fi

@@ -97,12 +97,12 @@ for n, M, Q, Do in mm_cfgs:
         dm, dv = rnd(n, Do, seed=5), rnd(n, Do, seed=6)
         res = {}
         med, mn = timeit(lambda: res.update(r=ops.mm_fwd(pr, mx, vx, z, ls, sf, A, B)))
-        mout, vacc = res['r'][0], res['r'][2]
+        mout, vacc, psi1s = res['r'][0], res['r'][2], res['r'][3]
         P = M * (M + 1) // 2
         fl_f = n * (P * (4 * Q + 1 + 2 * Do + 2) + M * (6 * Q + 2 * Do))
         emit(kind='mm_fwd', prec=name, n=n, M=M, Q=Q, Do=Do, ms=med, ms_min=mn, rows_per_s=n / (mn * 1e-3),
              alg_tflops=fl_f / (mn * 1e-3) / 1e12)
-        med, mn = timeit(lambda: ops.mm_bwd(pr, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc))
+        med, mn = timeit(lambda: ops.mm_bwd(pr, mx, vx, z, ls, sf, A, B, dm, dv, mout, vacc, psi1s))
         fl_b = n * (P * (18 * Q + 6 * Do + 6) + M * (14 * Q + 6 * Do)) - fl_f
         emit(kind='mm_bwd', prec=name, n=n, M=M, Q=Q, Do=Do, ms=med, ms_min=mn, rows_per_s=n / (mn * 1e-3),
              alg_tflops=fl_b / (mn * 1e-3) / 1e12)

@@ -33,7 +33,7 @@ for _ in range(2):
 mx, vx, z2 = rnd(n, Q), (0.1 + torch.rand(n, Q, dtype=torch.float64)).to(dev), rnd(M, Q)
 ls2 = torch.full((Q,), 0.3, dtype=torch.float64, device=dev)
 for _ in range(2):
-    mo, vo, va = ops.mm_fwd(prec, mx, vx, z2, ls2, sf, A, B)
-    ops.mm_bwd(prec, mx, vx, z2, ls2, sf, A, B, dm, dv, mo, va)
+    mo, vo, va, p1 = ops.mm_fwd(prec, mx, vx, z2, ls2, sf, A, B)
+    ops.mm_bwd(prec, mx, vx, z2, ls2, sf, A, B, dm, dv, mo, va, p1)
 torch.cuda.synchronize()
 print('ok')
