@@ -195,6 +195,40 @@ int mm_rows_bwd_launch(const MMPlan& p, const double* mx, const double* vx, cons
         case 16: return CALL(16);                             \
     }                                                         \
     return fail(GPB_ERR_ARG, "mm: input dim template %d unsupported", p.Qt)
+template <int QT>
+int mm_cols_bwd_launch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                       const double* ls, const double* A, const double* dm, const double* dv,
+                       const double* mout, const double* psi1, int n, int M, int Q, int Do,
+                       double* colpart, void* stream) {
+    const size_t smem = sizeof(double) * 32 * (2 * (size_t)QT + Do);
+    const int DOB = Do == 1 ? 1 : (Do == 2 ? 2 : 4);
+    prof_begin(6, stream);
+    for (int d0 = 0; d0 < Do; d0 += DOB) {
+        if (DOB == 1) {
+            auto kern = gpb::mm_cols_bwd_kernel<QT, 1>;
+            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
+                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
+        } else if (DOB == 2) {
+            auto kern = gpb::mm_cols_bwd_kernel<QT, 2>;
+            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
+                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
+        } else {
+            auto kern = gpb::mm_cols_bwd_kernel<QT, 4>;
+            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
+                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
+        }
+    }
+    prof_end(6, stream);
+    return GPB_CHECK_LAUNCH();
+}
+int mm_cols_bwd_dispatch(const MMPlan& p, const double* mx, const double* vx, const double* z,
+                         const double* ls, const double* A, const double* dm, const double* dv,
+                         const double* mout, const double* psi1, int n, int M, int Q, int Do,
+                         double* colpart, void* stream) {
+#define GPB_CALL(QT) mm_cols_bwd_launch<QT>(p, mx, vx, z, ls, A, dm, dv, mout, psi1, n, M, Q, Do, colpart, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
 template <typename T>
 int mm_psi1_fwd_dispatch(const MMPlan& p, const double* mx, const double* vx, const double* z,
                          const double* ls, const double* sf, const double* A, const double* vacc, int n,
@@ -298,15 +332,8 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
     GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
                (long)(2 + Q), w.rowsum, 0);
     {   // column-wise psi1 part: dA, dZ1
-        auto kern = gpb::mm_cols_bwd_kernel;
-        const int nt = 128;
-        size_t smem = sizeof(double) * ((size_t)32 * (2 * Q + Do) + (size_t)(2 * Q + 2 * Do) * nt);
-        rc = allow_smem(kern, smem);
+        rc = mm_cols_bwd_dispatch(p, mx, vx, z, ls, A, dm, dv, mout, psi1, n, M, Q, Do, w.colpart, stream);
         if (rc) return rc;
-        prof_begin(6, stream);
-        GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(nt), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1, n,
-                   M, Q, Do, p.cols_rows_per_block, w.colpart);
-        prof_end(6, stream);
         long len = (long)Do * M + (long)M * Q;
         GPB_LAUNCH(red, dim3(elementwise_grid(len)), dim3(256), 0, stream, w.colpart, p.cols_grid, len,
                    len, w.colsum, 0);

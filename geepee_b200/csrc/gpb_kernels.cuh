@@ -1650,52 +1650,53 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_rows_bwd_kernel(
 }
 
 // Backward, column-wise psi1 part (kernels.py:355-378 terms indexed by m; aep_models.py:239):
-//   dA[d,m] = sum_n dm_all[n,d] psi1[n,m] ;  dZ1[m,q] = -sum_n L1 (z_mq - mu_nq) c1_nq
-// thread per pseudo point m, rows of this block's range staged in shared memory, psi1 streamed
-// (coalesced) from the forward's save buffer.
+//   dA[d,m] = sum_n dm_all[n,d] psi1[n,m] ;  dZ1[m,q] = -sum_n L1 (z_mq - mu_nq) c1_nq,
+//   L1[n,m] = (sum_d dm_all[n,d] A[d,m]) psi1[n,m]
+// Thread per pseudo-point column (z, A, and the accumulators in registers), the rows of this
+// block's range staged 32 at a time in shared memory, psi1 streamed (coalesced, U rows in
+// flight) from the forward's save buffer.  DOB output dims per pass (Do <= 4: one pass); the
+// first pass of a wider layer forms g over all Do with a runtime loop.
 // partial record per block: [ dA (Do*M) | dZ1 (M*Q) ]
-GPB_KERNEL void mm_cols_bwd_kernel(const double* __restrict__ mx, const double* __restrict__ vx,
-                                   const double* __restrict__ z, const double* __restrict__ ls,
-                                   const double* __restrict__ A,
-                                   const double* __restrict__ dm, const double* __restrict__ dv,
-                                   const double* __restrict__ mout, const double* __restrict__ psi1,
-                                   int n, int M, int Q, int Do,
-                                   int rows_per_block, double* __restrict__ part) {
-    constexpr int TR = 32;
+template <int QT, int DOB>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_cols_bwd_kernel(
+    const double* __restrict__ mx, const double* __restrict__ vx, const double* __restrict__ z,
+    const double* __restrict__ ls, const double* __restrict__ A, const double* __restrict__ dm,
+    const double* __restrict__ dv, const double* __restrict__ mout, const double* __restrict__ psi1,
+    int n, int M, int Q, int Do, int d0, int rows_per_block, double* __restrict__ part) {
+    constexpr int TR = 32, U = 8;
     GPB_DYN_SMEM(smem);
-    double* s_mu = (double*)smem;         // [TR][Q]
-    double* s_c1 = s_mu + TR * Q;          // [TR][Q]
-    double* s_dma = s_c1 + TR * Q;         // [TR][Do]
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double* slot = s_dma + TR * Do;        // per-thread [Q (z) + Q (dZ) + Do (A) + Do (dA)][nt]
-    double* t_z = slot;
-    double* t_dz = slot + (long)Q * nt;
-    double* t_A = slot + 2L * Q * nt;
-    double* t_dA = slot + (2L * Q + Do) * nt;
+    double* s_mu = (double*)smem;          // [TR][QT]
+    double* s_c1 = s_mu + TR * QT;          // [TR][QT]
+    double* s_dma = s_c1 + TR * QT;         // [TR][Do]   dm_all (all output dims)
+    const int tid = threadIdx.x;
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = (r_begin + rows_per_block) < n ? (r_begin + rows_per_block) : n;
     double* rec = part + (long)blockIdx.x * ((long)Do * M + (long)M * Q);
-    for (int m0 = 0; m0 < M; m0 += nt) {
+    const bool wide = Do > DOB;             // g needs output dims outside this pass' registers
+    for (int m0 = 0; m0 < M; m0 += kThreads) {
         const int m = m0 + tid;
         const bool act = m < M;
-        for (int q = 0; q < Q; q++) {
-            t_z[q * nt + tid] = act ? z[(long)m * Q + q] : 0.0;
-            t_dz[q * nt + tid] = 0;
+        double zr[QT], dz[QT], Ar[DOB], dA[DOB];
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) {
+            zr[q] = (act && q < Q) ? z[(long)m * Q + q] : 0.0;
+            dz[q] = 0;
         }
-        for (int d = 0; d < Do; d++) {
-            t_A[d * nt + tid] = act ? A[(long)d * M + m] : 0.0;
-            t_dA[d * nt + tid] = 0;
+        GPB_UNROLL
+        for (int d = 0; d < DOB; d++) {
+            Ar[d] = (act && d0 + d < Do) ? A[(long)(d0 + d) * M + m] : 0.0;
+            dA[d] = 0;
         }
         for (int t0 = r_begin; t0 < r_end; t0 += TR) {
             const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
             sync_threads();
-            for (int i = tid; i < TR * Q; i += nt) {
-                const int r = i / Q, q = i - r * Q;
-                const bool ok = r < tv;
+            for (int i = tid; i < TR * QT; i += kThreads) {
+                const int r = i / QT, q = i - r * QT;
+                const bool ok = r < tv && q < Q;
                 s_mu[i] = ok ? mx[(long)(t0 + r) * Q + q] : 0.0;
                 s_c1[i] = ok ? 1.0 / (vx[(long)(t0 + r) * Q + q] + exp(2.0 * ls[q])) : 0.0;
             }
-            for (int i = tid; i < TR * Do; i += nt) {
+            for (int i = tid; i < TR * Do; i += kThreads) {
                 const int r = i / Do, d = i - r * Do;
                 s_dma[i] = r < tv ? dm[(long)(t0 + r) * Do + d] -
                                         2.0 * dv[(long)(t0 + r) * Do + d] * mout[(long)(t0 + r) * Do + d]
@@ -1703,23 +1704,42 @@ GPB_KERNEL void mm_cols_bwd_kernel(const double* __restrict__ mx, const double* 
             }
             sync_threads();
             if (act)
-                for (int r = 0; r < tv; r++) {
-                    const double p1 = psi1[(long)(t0 + r) * M + m];
-                    double g = 0;
-                    for (int d = 0; d < Do; d++) {
-                        g += s_dma[r * Do + d] * t_A[d * nt + tid];
-                        t_dA[d * nt + tid] += s_dma[r * Do + d] * p1;
+                for (int rb = 0; rb < tv; rb += U) {
+                    double p1[U];
+                    GPB_UNROLL
+                    for (int u = 0; u < U; u++)
+                        p1[u] = (rb + u) < tv ? psi1[(long)(t0 + rb + u) * M + m] : 0.0;
+                    GPB_UNROLL
+                    for (int u = 0; u < U; u++) {
+                        const int r = (rb + u) < tv ? rb + u : rb;   // clamped rows carry p1 = 0
+                        double g = 0;
+                        GPB_UNROLL
+                        for (int d = 0; d < DOB; d++) {
+                            const double w = (d0 + d < Do) ? s_dma[r * Do + d0 + d] : 0.0;
+                            g += w * Ar[d];
+                            dA[d] += w * p1[u];
+                        }
+                        if (wide) {
+                            g = 0;
+                            if (d0 == 0)
+                                for (int d = 0; d < Do; d++) g += s_dma[r * Do + d] * ldg(A + (long)d * M + m);
+                        }
+                        const double L1 = g * p1[u];
+                        GPB_UNROLL
+                        for (int q = 0; q < QT; q++) dz[q] -= L1 * (zr[q] - s_mu[r * QT + q]) * s_c1[r * QT + q];
                     }
-                    const double L1 = g * p1;
-                    for (int q = 0; q < Q; q++)
-                        t_dz[q * nt + tid] -= L1 * (t_z[q * nt + tid] - s_mu[r * Q + q]) * s_c1[r * Q + q];
                 }
         }
         if (act) {
-            for (int d = 0; d < Do; d++) rec[(long)d * M + m] = t_dA[d * nt + tid];
-            for (int q = 0; q < Q; q++) rec[(long)Do * M + (long)m * Q + q] = t_dz[q * nt + tid];
+            GPB_UNROLL
+            for (int d = 0; d < DOB; d++)
+                if (d0 + d < Do) rec[(long)(d0 + d) * M + m] = dA[d];
+            if (d0 == 0) {
+                GPB_UNROLL
+                for (int q = 0; q < QT; q++)
+                    if (q < Q) rec[(long)Do * M + (long)m * Q + q] = dz[q];
+            }
         }
-        sync_threads();
     }
 }
 
