@@ -289,9 +289,12 @@ def run_gpu(args, w):
     xh = torch.from_numpy(X).pin_memory()
     yh = torch.from_numpy(Y).pin_memory()
 
+    # each rank's inputs for a step are its own contiguous slice of the rows (geepee_b200/dist.py)
+    lo, hi = (rank * N) // world, ((rank + 1) * N) // world
+
     def step_e2e():
-        model._x.copy_(xh, non_blocking=True)
-        model._y.copy_(yh, non_blocking=True)
+        model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
+        model._y[lo:hi].copy_(yh[lo:hi], non_blocking=True)
         return model.objective_function(params, N, alpha=alpha)
 
     def timed(fn, steps):
@@ -325,8 +328,8 @@ def run_gpu(args, w):
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     ms_e2e /= args.steps
-    h2d = X.nbytes + Y.nbytes + sum(np.asarray(v).nbytes for v in params.values())
-    d2h = 8 + sum(np.asarray(v).nbytes for v in grads.values())
+    h2d = (X[lo:hi].nbytes + Y[lo:hi].nbytes) * world + world * sum(np.asarray(v).nbytes for v in params.values())
+    d2h = world * (8 + sum(np.asarray(v).nbytes for v in grads.values()))
     # ---- FMA-pipe peak of this box (the binding roofline is the FP64 / FP32 FMA pipe) ----
     pr = ops.PREC[args.prec]
     flops_box = [0.0]
@@ -358,7 +361,9 @@ def run_gpu(args, w):
         slot, kname = 'mm_pairs_bwd', 'mm_pairs_kernel<T,Q,DOC,BWD=true> (psi2 regenerated on chip; all moment-matched layers)'
     else:
         fl = rows_rank * 2.0 * w['Do'] * w['M'] ** 2
-        slot, kname = 'det_fwd', 'det_fwd_kernel<T,MP> (Kfu generation fused with Kfu.B)'
+        slot = 'det_fwd'
+        kname = ('det_fwd_mma_kernel<MP> (Kfu generation fused with Kfu.B on the FP64 tensor cores, DMMA.8x8x4)'
+                 if pr == ops.F64 else 'det_fwd_kernel<float,MP> (Kfu generation fused with Kfu.B, SIMT)')
     k_ms, k_cnt = prof[slot]
     k_ms_step = k_ms / args.steps
     achieved = fl / (k_ms_step * 1e-3) / 1e12 if k_ms_step > 0 else 0.0
