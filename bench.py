@@ -35,6 +35,12 @@ WORKLOADS = {
                     desc='aep.SGPR N=1e6, D=10, M=256, alpha=0.5, full batch'),
     'cfg5_sgpr': dict(model='SGPR', N=10000000, D=16, Do=1, M=512, alpha=0.5, seed=5,
                       desc='aep.SGPR N=1e7, D=16, M=512, alpha=0.5, full batch'),
+    # BASELINE.json configs[1] and configs[3] (parity-test shapes; measurable with --workload)
+    'cfg2_sgplvm': dict(model='SGPLVM', N=100000, Q=5, Do=50, M=128, alpha=0.5, seed=2,
+                        desc='aep.SGPLVM N=1e5, D_out=50, latent Q=5, M=128, alpha=0.5, full batch'),
+    'cfg4_sgpssm': dict(model='SGPSSM', N=1000000, Q=4, Do=4, M=200, alpha=0.5, seed=4,
+                        desc='aep.SGPSSM T=1e6, latent dim 4, M=200, alpha=0.5, linear-Gaussian emission, '
+                             'full window'),
     'cfg1_sgpr': dict(model='SGPR', N=200, D=1, Do=1, M=50, alpha=0.5, seed=42,
                       desc='aep.SGPR N=200, D=1, M=50, alpha=0.5 (examples/gpr_aep_examples.py)'),
     'small_sdgpr': dict(model='SDGPR', N=20000, D=10, hidden=[2, 2], Do=1, M=64, alpha=1.0, seed=3,
@@ -55,6 +61,10 @@ def flops_per_row(w):
     """Algorithmic flops per data point (SURVEY.md section 8d formulas)."""
     if w['model'] == 'SGPR':
         return f_det(w['D'], w['M'], w['Do'])
+    if w['model'] == 'SGPLVM':
+        return f_mm(w['Q'], w['M'], w['Do'])
+    if w['model'] == 'SGPSSM':
+        return f_mm(w['Q'], w['M'], w['Q'])      # dynamics layer; emission + x terms add < 1 %
     sizes = [w['D']] + list(w['hidden']) + [w['Do']]
     tot = f_det(sizes[0], w['M'], sizes[1])
     for i in range(1, len(sizes) - 1):
@@ -66,6 +76,20 @@ def make_data(w, n=None):
     """Synthetic data of the workload's shape (fixed seed)."""
     n = w['N'] if n is None else n
     rng = np.random.RandomState(w['seed'])
+    if w['model'] == 'SGPLVM':     # SURVEY.md 8d cfg 2: Y = tanh(X* W1) W2 + 0.1 noise, standardised
+        Xs = rng.standard_normal((n, w['Q']))
+        W1, W2 = rng.standard_normal((w['Q'], 20)), rng.standard_normal((20, w['Do']))
+        Y = np.tanh(Xs.dot(W1)).dot(W2) + 0.1 * rng.standard_normal((n, w['Do']))
+        Y = (Y - Y.mean(0)) / Y.std(0)
+        return Xs, Y
+    if w['model'] == 'SGPSSM':     # SURVEY.md 8d cfg 4 (fallback): 4-D damped nonlinear oscillator
+        t = np.arange(n) * 0.05
+        ph = rng.uniform(0, 2 * np.pi, w['Do'])
+        fr = np.array([1.0, 1.7, 0.6, 2.3])[:w['Do']]
+        Y = np.stack([np.sin(fr[i] * t + ph[i]) * (1.0 + 0.3 * np.cos(0.11 * fr[i] * t)) for i in range(w['Do'])], 1)
+        Y = np.tanh(1.5 * Y) + 0.05 * rng.standard_normal((n, w['Do']))
+        Y = (Y - Y.mean(0)) / Y.std(0)
+        return None, Y
     if w['model'] == 'SGPR' and w['D'] == 1:
         X = rng.rand(n, 1)
         Y = np.sin(12 * X) + 0.5 * np.cos(25 * X) + rng.randn(n, 1) * 0.2
@@ -76,8 +100,35 @@ def make_data(w, n=None):
     return X, Y
 
 
-def make_params(model, Y):
+def _layer_recipe(N, M, Din, Dout, X, sfx=''):
+    """Base_SGP_Layer.init_hypers recipe (base_models.py:518-597) without building a model."""
+    from geepee_b200 import layers
+    lay = layers.Base_SGP_Layer.__new__(layers.Base_SGP_Layer)
+    lay.N, lay.M, lay.Din, lay.Dout, lay.nat_param = N, M, Din, Dout, True
+    return layers.Base_SGP_Layer.init_hypers(lay, X, key_suffix=sfx)
+
+
+def make_params(model, Y, w=None, X=None):
     np.random.seed(0)
+    if w is not None and w['model'] == 'SGPLVM':
+        # hand-built (SURVEY.md 8d cfg 2): skips the nested GPR fit of base_models.py:839-881
+        p = _layer_recipe(Y.shape[0], w['M'], w['Q'], w['Do'], X)
+        p['ls'] = np.zeros(w['Q'])
+        p['sf'] = np.zeros(1)
+        p['sn'] = np.array(np.log(0.1))
+        p['x1'] = X / 0.1
+        p['x2'] = 0.5 * np.log(1.0 / 0.1 - 1.0) * np.ones_like(X)
+        return p
+    if w is not None and w['model'] == 'SGPSSM':
+        # SURVEY.md 8d cfg 4: x factors from base_models.py:1628-1634, C = I, R / sn as in
+        # examples/gpssm_hodgkin_huxley.py:328-329, dynamics layer from the layer recipe
+        p = _layer_recipe(Y.shape[0] - 1, w['M'], w['Q'], w['Q'], Y[:-1], '_dynamic')
+        p['x_factor_1'] = Y / 0.1 / 3.0
+        p['x_factor_2'] = 0.5 * np.log(10.0 / 3.0) * np.ones_like(Y)
+        p['C_emission'] = np.eye(w['Q'])
+        p['R_emission'] = np.log(0.01) / 2 * np.ones(w['Do'])
+        p['sn'] = np.log(0.01) / 2 * np.ones(1)
+        return p
     p = model.init_hypers(Y)
     p['sn'] = np.array(np.log(0.1))
     return p
@@ -99,6 +150,10 @@ def cpu_model_factory():
             def build(w, X, Y):
                 if w['model'] == 'SGPR':
                     return aep.SGPR(X, Y, w['M'], lik='Gaussian')
+                if w['model'] == 'SGPLVM':
+                    return aep.SGPLVM(Y, w['Q'], w['M'], lik='Gaussian')
+                if w['model'] == 'SGPSSM':
+                    return aep.SGPSSM(Y, w['Q'], w['M'], lik='Gaussian')
                 return aep.SDGPR(X, Y, w['M'], w['hidden'], lik='Gaussian')
             return 'reference', build
         except Exception:  # noqa: BLE001
@@ -109,6 +164,10 @@ def cpu_model_factory():
     def build(w, X, Y):
         if w['model'] == 'SGPR':
             return go.AepSGPR(X, Y, w['M'])
+        if w['model'] == 'SGPLVM':
+            return go.AepSGPLVM(Y, w['Q'], w['M'])
+        if w['model'] == 'SGPSSM':
+            return go.AepSGPSSM(Y, w['Q'], w['M'])
         return go.AepSDGPR(X, Y, w['M'], w['hidden'])
     return 'port', build
 
@@ -119,6 +178,9 @@ def cpu_params(w, X, Y):
     import contextlib
     from geepee_b200 import layers
     np.random.seed(0)
+    if w['model'] in ('SGPLVM', 'SGPSSM'):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return make_params(None, Y, w, X)
     sizes = [w['D']] + list(w.get('hidden', [])) + [w['Do']]
     p = {}
     with contextlib.redirect_stdout(io.StringIO()):
@@ -157,7 +219,7 @@ def time_cpu(w, budget_s, steps=1, warmup=0):
         m.objective_function(copy.deepcopy(p), n, alpha=w['alpha'])
         return time.perf_counter() - t
 
-    n1 = min(64, w['N'])
+    n1 = min(64 if w['model'] in ('SGPR', 'SDGPR') else 2 * w['M'], w['N'])
     t1 = call(n1)
     if n1 >= w['N']:
         return dict(value=n1 / t1, unit='rows/s', cores=1, threads_available=os.cpu_count(), kind=kind,
@@ -272,9 +334,13 @@ def run_gpu(args, w):
     with contextlib.redirect_stdout(io.StringIO()):
         if w['model'] == 'SGPR':
             model = aep.SGPR(X, Y, w['M'], prec=args.prec, device=dev)
+        elif w['model'] == 'SGPLVM':
+            model = aep.SGPLVM(Y, w['Q'], w['M'], prec=args.prec, device=dev)
+        elif w['model'] == 'SGPSSM':
+            model = aep.SGPSSM(Y, w['Q'], w['M'], prec=args.prec, device=dev)
         else:
             model = aep.SDGPR(X, Y, w['M'], w['hidden'], prec=args.prec, device=dev)
-        params = make_params(model, Y)
+        params = make_params(model, Y, w, X)
     alpha = w['alpha']
 
     def barrier():
@@ -286,14 +352,15 @@ def run_gpu(args, w):
         return model.objective_function(params, N, alpha=alpha)
 
     # pinned host copies of the step's inputs for the end-to-end leg
-    xh = torch.from_numpy(X).pin_memory()
+    xh = torch.from_numpy(X).pin_memory() if w['model'] in ('SGPR', 'SDGPR') else None
     yh = torch.from_numpy(Y).pin_memory()
 
     # each rank's inputs for a step are its own contiguous slice of the rows (geepee_b200/dist.py)
     lo, hi = (rank * N) // world, ((rank + 1) * N) // world
 
     def step_e2e():
-        model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
+        if xh is not None:
+            model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
         model._y[lo:hi].copy_(yh[lo:hi], non_blocking=True)
         return model.objective_function(params, N, alpha=alpha)
 
@@ -328,7 +395,7 @@ def run_gpu(args, w):
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     ms_e2e /= args.steps
-    h2d = (X[lo:hi].nbytes + Y[lo:hi].nbytes) * world + world * sum(np.asarray(v).nbytes for v in params.values())
+    h2d = ((X[lo:hi].nbytes if xh is not None else 0) + Y[lo:hi].nbytes) * world + world * sum(np.asarray(v).nbytes for v in params.values())
     d2h = world * (8 + sum(np.asarray(v).nbytes for v in grads.values()))
     # ---- FMA-pipe peak of this box (the binding roofline is the FP64 / FP32 FMA pipe) ----
     pr = ops.PREC[args.prec]
@@ -354,8 +421,11 @@ def run_gpu(args, w):
         return
     # dominant kernel + its algorithmic flops per launch, rows of ONE rank
     rows_rank = N // world
-    if w['model'] == 'SDGPR':
-        sizes = [w['D']] + list(w['hidden']) + [w['Do']]
+    if w['model'] in ('SDGPR', 'SGPLVM', 'SGPSSM'):
+        if w['model'] == 'SDGPR':
+            sizes = [w['D']] + list(w['hidden']) + [w['Do']]
+        else:
+            sizes = [0, w['Q'], w['Do'] if w['model'] == 'SGPLVM' else w['Q']]
         P = w['M'] * (w['M'] + 1) // 2
         fl = sum(rows_rank * P * (14 * sizes[i] + 4 * sizes[i + 1] + 5) for i in range(1, len(sizes) - 1))
         slot, kname = 'mm_pairs_bwd', 'mm_pairs_kernel<T,Q,DOC,BWD=true> (psi2 regenerated on chip; all moment-matched layers)'
