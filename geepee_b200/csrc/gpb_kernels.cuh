@@ -598,7 +598,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
     const T* __restrict__ Ksave, const T* __restrict__ Tsave, int n, int M, int MP, int D, int Do,
     int rows_per_block, double* __restrict__ part, long rec_len) {
     constexpr int TR = 64;
-    constexpr int U = 8;
+    constexpr int U = 4;
     constexpr int DOS = DOB > 0 ? DOB : 1;
     GPB_SHARED T xs[TR * DP];
     GPB_SHARED double dms[TR * 8], dvs[TR * 8];
