@@ -13,6 +13,33 @@ long g_prof_cnt[8] = {0};
 }
 #endif
 
+// a14: lik_layers.py:573-627.  out = [ sum quad | sum log|Vy| | dRacc[Do] | dC[Do*Q] ] (unscaled sums)
+namespace {
+int emis_pad(int x) { return x <= 2 ? 2 : (x <= 4 ? 4 : (x <= 8 ? 8 : -1)); }
+int emis_grid(int n) {
+    long b = cdiv(n, 128);
+    long cap = (long)sm_count() * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+template <int DO, int QT>
+int emis_launch(const double* mx, const double* vx, const double* y, const double* C, const double* R,
+                double alpha, double scale, int n, int Q, int Do, double* dmx, double* dvx, double* out,
+                double* part, void* stream) {
+    constexpr int NV = 2 + DO * (1 + QT);
+    const int grid = emis_grid(n);
+    auto kern = gpb::gauss_emis_kernel<DO, QT>;
+    GPB_LAUNCH(kern, dim3(grid), dim3(128), 0, stream, mx, vx, y, C, R, alpha, scale, n, Q, Do, dmx, dvx, part);
+    // fold the per-block records, then compact the padded record to [2 + Do + Do*Q]
+    auto red = gpb::reduce_partials_kernel;
+    double* full = part + (size_t)grid * NV;
+    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)part, grid, (long)NV, (long)NV, full, 0);
+    auto cmp = gpb::gauss_emis_compact_kernel;
+    GPB_LAUNCH(cmp, dim3(1), dim3(128), 0, stream, (const double*)full, DO, QT, Do, Q, out);
+    return GPB_CHECK_LAUNCH();
+}
+}  // namespace
+
+
 extern "C" {
 
 int gpb_version(void) { return 100; }
@@ -57,6 +84,31 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
     auto red = gpb::reduce_partials_kernel;
     GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)ws, grid, 2L, 2L, out2, 0);
     return GPB_CHECK_LAUNCH();
+}
+
+size_t gpb_gauss_emis_ws_bytes(int n, int Do, int Q) {
+    const int DO = emis_pad(Do), QT = emis_pad(Q);
+    if (DO < 0 || QT < 0 || n < 1) return 0;
+    const size_t NV = 2 + (size_t)DO * (1 + QT);
+    return align256(sizeof(double) * NV * ((size_t)emis_grid(n) + 1));
+}
+
+int gpb_gauss_emis(const double* mx, const double* vx, const double* y, const double* C, const double* R,
+                   double alpha, double scale, int n, int Q, int Do, double* dmx, double* dvx, double* out,
+                   void* ws, size_t ws_bytes, void* stream) {
+    if (!mx || !vx || !y || !C || !R || !dmx || !dvx || !out || !ws || n < 1)
+        return fail(GPB_ERR_ARG, "gauss_emis: bad argument");
+    const int DO = emis_pad(Do), QT = emis_pad(Q);
+    if (DO < 0 || QT < 0) return fail(GPB_ERR_ARG, "gauss_emis: Do=%d, Q=%d unsupported (max 8)", Do, Q);
+    if (ws_bytes < gpb_gauss_emis_ws_bytes(n, Do, Q)) return fail(GPB_ERR_WS, "gauss_emis: workspace too small");
+    double* part = (double*)ws;
+#define GPB_EMIS(DOV, QTV) \
+    if (DO == DOV && QT == QTV) return emis_launch<DOV, QTV>(mx, vx, y, C, R, alpha, scale, n, Q, Do, dmx, dvx, out, part, stream)
+    GPB_EMIS(2, 2); GPB_EMIS(2, 4); GPB_EMIS(2, 8);
+    GPB_EMIS(4, 2); GPB_EMIS(4, 4); GPB_EMIS(4, 8);
+    GPB_EMIS(8, 2); GPB_EMIS(8, 4); GPB_EMIS(8, 8);
+#undef GPB_EMIS
+    return fail(GPB_ERR_ARG, "gauss_emis: unreachable");
 }
 
 int gpb_profile_enable(int on) {

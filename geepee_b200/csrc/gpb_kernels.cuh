@@ -156,6 +156,164 @@ GPB_KERNEL void gauss_lik_kernel(const double* __restrict__ m, const double* __r
     }
 }
 
+// -------------------------------------------------------------------------
+// a14. Linear-Gaussian emission, tilted (AEP): lik_layers.py:573-627
+//     y ~ N(C x, diag(R)):  per row  Vy = diag(R/alpha) + C diag(vx) C^T  (Do x Do, SPD),
+//     w = Vy^-1 (y - C mx),  log|Vy|,  Vy^-1;  dSig = -Vy^-1/2 + w w^T/2.
+//     Thread per row; Cholesky, triangular inverse and Vy^-1 fully unrolled in registers
+//     (DO, QT compile-time, zero / identity padded); writes scale*dmx, scale*dvx and per-block
+//     partials  [ sum quad | sum log|Vy| | dRacc[DO] | dC[DO][QT] ]  with
+//       dRacc[a] = sum_n (-Vy^-1[a,a]/2 + w_a^2/2),
+//       dC[a,q]  = sum_n ( w_a mx_q + 2 vx_q sum_b dSig[a,b] C[b,q] ).
+//     Replaces a batched cuSOLVER potrf/potrs/potri over n tiny matrices (whose per-call
+//     cudaMalloc/cudaFree cost 220 ms per step at T = 1e6 in the first version of this round).
+// -------------------------------------------------------------------------
+template <int DO, int QT>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(128) gauss_emis_kernel(
+    const double* __restrict__ mx, const double* __restrict__ vx, const double* __restrict__ y,
+    const double* __restrict__ C, const double* __restrict__ R, double alpha, double scale, int n,
+    int Q, int Do, double* __restrict__ dmx, double* __restrict__ dvx, double* __restrict__ part) {
+    constexpr int NV = 2 + DO + DO * QT;
+    GPB_SHARED double sC[DO * QT], sR[DO];
+    GPB_SHARED double s_red[4 * NV];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < DO * QT; i += blockDim.x) {
+        const int a = i / QT, q = i - a * QT;
+        sC[i] = (a < Do && q < Q) ? C[a * Q + q] : 0.0;
+    }
+    if (tid < DO) sR[tid] = tid < Do ? R[tid] / alpha : 1.0;    // padded outputs: Vy = 1, y = 0
+    sync_threads();
+    double acc[NV];
+    GPB_UNROLL
+    for (int i = 0; i < NV; i++) acc[i] = 0;
+    for (long row = (long)blockIdx.x * blockDim.x + tid; row < n; row += (long)gridDim.x * blockDim.x) {
+        double m[QT], v[QT], L[DO][DO], yd[DO];
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) {
+            m[q] = q < Q ? mx[row * Q + q] : 0.0;
+            v[q] = q < Q ? vx[row * Q + q] : 0.0;
+        }
+        GPB_UNROLL
+        for (int a = 0; a < DO; a++) {
+            double s = a < Do ? y[row * Do + a] : 0.0;
+            GPB_UNROLL
+            for (int q = 0; q < QT; q++) s -= sC[a * QT + q] * m[q];
+            yd[a] = s;
+            GPB_UNROLL
+            for (int b = 0; b <= a; b++) {
+                double t = a == b ? sR[a] : 0.0;
+                GPB_UNROLL
+                for (int q = 0; q < QT; q++) t += sC[a * QT + q] * v[q] * sC[b * QT + q];
+                L[a][b] = t;
+            }
+        }
+        // Cholesky (lower, in place), log-determinant
+        double ld = 0;
+        GPB_UNROLL
+        for (int j = 0; j < DO; j++) {
+            double s = L[j][j];
+            GPB_UNROLL
+            for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
+            const double d = sqrt(s), inv = 1.0 / d;
+            L[j][j] = inv;                      // keep 1/L_jj on the diagonal
+            ld += log(s);                       // = 2 log L_jj
+            GPB_UNROLL
+            for (int i = j + 1; i < DO; i++) {
+                double t = L[i][j];
+                GPB_UNROLL
+                for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+                L[i][j] = t * inv;
+            }
+        }
+        // Linv (lower) in place: column by column
+        double Li[DO][DO];
+        GPB_UNROLL
+        for (int j = 0; j < DO; j++) {
+            Li[j][j] = L[j][j];
+            GPB_UNROLL
+            for (int i = j + 1; i < DO; i++) {
+                double t = 0;
+                GPB_UNROLL
+                for (int k = j; k < i; k++) t -= L[i][k] * Li[k][j];
+                Li[i][j] = t * L[i][i];
+            }
+        }
+        // Vinv = Linv^T Linv (symmetric), w = Vinv yd
+        double Vi[DO][DO], wv[DO];
+        GPB_UNROLL
+        for (int a = 0; a < DO; a++)
+            GPB_UNROLL
+            for (int b = 0; b <= a; b++) {
+                double t = 0;
+                GPB_UNROLL
+                for (int k = a; k < DO; k++) t += Li[k][a] * Li[k][b];
+                Vi[a][b] = t;
+                Vi[b][a] = t;
+            }
+        double quad = 0;
+        GPB_UNROLL
+        for (int a = 0; a < DO; a++) {
+            double t = 0;
+            GPB_UNROLL
+            for (int b = 0; b < DO; b++) t += Vi[a][b] * yd[b];
+            wv[a] = t;
+            quad += t * yd[a];
+        }
+        acc[0] += -0.5 * quad;
+        acc[1] += ld;
+        // dSig C  and the per-row input gradients
+        double dm_[QT], dv_[QT];
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++) { dm_[q] = 0; dv_[q] = 0; }
+        GPB_UNROLL
+        for (int a = 0; a < DO; a++) {
+            acc[2 + a] += -0.5 * Vi[a][a] + 0.5 * wv[a] * wv[a];
+            GPB_UNROLL
+            for (int q = 0; q < QT; q++) {
+                double sc = 0;                  // (dSig C)[a][q]
+                GPB_UNROLL
+                for (int b = 0; b < DO; b++) sc += (-0.5 * Vi[a][b] + 0.5 * wv[a] * wv[b]) * sC[b * QT + q];
+                acc[2 + DO + a * QT + q] += wv[a] * m[q] + 2.0 * v[q] * sc;
+                dm_[q] += wv[a] * sC[a * QT + q];
+                dv_[q] += sc * sC[a * QT + q];
+            }
+        }
+        GPB_UNROLL
+        for (int q = 0; q < QT; q++)
+            if (q < Q) {
+                dmx[row * Q + q] = scale * dm_[q];
+                dvx[row * Q + q] = scale * dv_[q];
+            }
+    }
+    // block reduction of the NV sums (4 warps)
+    GPB_UNROLL
+    for (int i = 0; i < NV; i++) {
+        const double r = warp_sum(acc[i]);
+        if (lane == 0) s_red[warp * NV + i] = r;
+    }
+    sync_threads();
+    for (int i = tid; i < NV; i += blockDim.x) {
+        double r = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += s_red[w * NV + i];
+        part[(long)blockIdx.x * NV + i] = r;
+    }
+}
+
+// padded record [2 | DO | DO*QT] -> compact [2 | Do | Do*Q]
+GPB_KERNEL void gauss_emis_compact_kernel(const double* __restrict__ full, int DO, int QT, int Do, int Q,
+                                          double* __restrict__ out) {
+    for (int i = threadIdx.x; i < 2 + Do + Do * Q; i += blockDim.x) {
+        double v;
+        if (i < 2) v = full[i];
+        else if (i < 2 + Do) v = full[2 + (i - 2)];
+        else {
+            const int k = i - 2 - Do, a = k / Q, q = k - a * Q;
+            v = full[2 + DO + a * QT + q];
+        }
+        out[i] = v;
+    }
+}
+
 // =========================================================================
 // Deterministic-input layer (a5, a8)
 // =========================================================================

@@ -94,6 +94,25 @@ def gauss_lik(m, v, y, sn, alpha, scale, mode):
     return dm, dv, out2
 
 
+def gauss_emis_supported(Do, Q):
+    return Do <= 8 and Q <= 8
+
+
+def gauss_emis(mx, vx, y, C, R, alpha, scale):
+    """lik_layers.py:573-627 (tilted linear-Gaussian emission), per-row part.  R: variances.
+    -> scale*dmx, scale*dvx, and the unscaled sums [quad | logdet | dRacc[Do] | dC[Do*Q]]."""
+    lib = _lib.get()
+    n, Q = mx.shape
+    Do = y.shape[1]
+    dmx = torch.empty_like(mx)
+    dvx = torch.empty_like(mx)
+    out = torch.empty(2 + Do + Do * Q, dtype=torch.float64, device=mx.device)
+    ws = _ws(lib.gpb_gauss_emis_ws_bytes(n, Do, Q), mx)
+    _chk(lib.gpb_gauss_emis(_p(_c(mx)), _p(_c(vx)), _p(_c(y)), _p(_c(C)), _p(_c(R)), float(alpha), float(scale),
+                            n, Q, Do, _p(dmx), _p(dvx), _p(out), _p(ws), ws.numel(), _stream(mx)), 'gauss_emis')
+    return dmx, dvx, out
+
+
 class DetOperands(object):
     """Zero-padded, precision-typed copies of (A, B_det) for the deterministic layer."""
 

@@ -69,6 +69,17 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
                   double alpha, double scale, long total, int mode, double* dm, double* dv,
                   double* out2, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- a14: linear-Gaussian emission, tilted.  lik_layers.py:573-627 Gauss_Emis.compute_emission_tilted:
+ *      y ~ N(C x, diag(R)), per row Vy = diag(R/alpha) + C diag(vx) C^T.  R[Do] are VARIANCES.
+ *      dmx, dvx[n,Q] come out multiplied by `scale`;
+ *      out[2 + Do + Do*Q] = [ sum_n -(y-Cm)^T Vy^-1 (y-Cm)/2 | sum_n log|Vy| |
+ *                             sum_n (-Vy^-1[a,a]/2 + w_a^2/2) | dC1 + dC2 of lines 612-615 ] (unscaled).
+ *      Do <= 8 and Q <= 8 (GPB_ERR_ARG otherwise). */
+size_t gpb_gauss_emis_ws_bytes(int n, int Do, int Q);
+int gpb_gauss_emis(const double* mx, const double* vx, const double* y, const double* C, const double* R,
+                   double alpha, double scale, int n, int Q, int Do, double* dmx, double* dvx,
+                   double* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- deterministic-input layer -------------------------------------------------------------- */
 /* M padded to the GEMM tile (128, 256 or 512); -1 if M > 512. */
 int gpb_det_pad_m(int M);

@@ -111,3 +111,29 @@ def check_kmat_psi_lik():
     assert abs(o[0].item() - le) < 1e-12 * abs(le)
     assert abs(-2.5 * o[1].item() - go.gauss_dsn_log_lik_exp(sn[0], m, v, y, -2.5)) < 1e-10
     assert gu.rel_err(N(dm), -2.5 * rdm) < 1e-13 and gu.rel_err(N(dv), -2.5 * rdv) < 1e-13
+
+
+EMIS_SHAPES = [(37, 3, 2), (300, 4, 4), (129, 5, 3), (64, 8, 8), (50, 1, 6)]
+
+
+def check_gauss_emis(n, Do, Q):
+    """Fused tilted linear-Gaussian emission (lik_layers.py:573-627) through the layer class
+    against the oracle's numpy restatement (padded and exact template sizes)."""
+    from geepee_b200 import lik_layers
+    import torch
+    rng = np.random.RandomState(11 * n + Do)
+    y = rng.standard_normal((n, Do))
+    mx, vx = rng.standard_normal((n, Q)), rng.rand(n, Q) + 0.05
+    p = {'C': rng.standard_normal((Do, Q)) * 0.7, 'R': np.log(0.3 + rng.rand(Do)) / 2}
+    alpha, scale = 0.7, -3.25
+    ref = go.GaussEmis(y, Do, Q)
+    ref.set_params(p)
+    lz, gi, ge = ref.tilted(mx, vx, alpha, scale, np.arange(n))
+    em = lik_layers.Gauss_Emis(y, Do, Q, device=torch.device(DEV))
+    em.update_hypers(p)
+    lz2, gi2, ge2 = em.compute_emission_tilted(mx, vx, alpha, scale)
+    assert abs(lz2 - lz) < 1e-11 * abs(lz)
+    for k in ('mx', 'vx'):
+        assert gu.rel_err(gi2[k], gi[k]) < 1e-11, k
+    for k in ('C', 'R'):
+        assert gu.rel_err(ge2[k], ge[k]) < 1e-11, k

@@ -29,3 +29,8 @@ def test_mm_layer(n, M, Q, Do, prec, tol):
 
 def test_kmat_psi_lik():
     oc.check_kmat_psi_lik()
+
+
+@pytest.mark.parametrize('n,Do,Q', oc.EMIS_SHAPES)
+def test_gauss_emis(n, Do, Q):
+    oc.check_gauss_emis(n, Do, Q)

@@ -16,8 +16,15 @@ X, Y = bench.make_data(w)
 dev = torch.device('cuda:0')
 import io, contextlib
 with contextlib.redirect_stdout(io.StringIO()):
-    model = aep.SGPR(X, Y, w['M'], device=dev) if w['model'] == 'SGPR' else aep.SDGPR(X, Y, w['M'], w['hidden'], device=dev)
-    params = bench.make_params(model, Y)
+    if w['model'] == 'SGPR':
+        model = aep.SGPR(X, Y, w['M'], device=dev)
+    elif w['model'] == 'SGPLVM':
+        model = aep.SGPLVM(Y, w['Q'], w['M'], device=dev)
+    elif w['model'] == 'SGPSSM':
+        model = aep.SGPSSM(Y, w['Q'], w['M'], device=dev)
+    else:
+        model = aep.SDGPR(X, Y, w['M'], w['hidden'], device=dev)
+    params = bench.make_params(model, Y, w, X)
 for _ in range(3):
     model.objective_function(params, w['N'], alpha=w['alpha'])
 torch.cuda.synchronize()
