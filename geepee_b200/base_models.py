@@ -13,7 +13,7 @@ from scipy.optimize import minimize
 
 from . import config, dist
 from .config import PROP_MM, PROP_MC
-from .layers import default_device, to_dev, pack_to_device
+from .layers import default_device, to_dev, pack_to_device, to_host
 from .lik_layers import Gauss_Layer, Gauss_Emis
 from .utils import ObjectiveWrapper, flatten_dict, unflatten_dict, adam, PCA_reduce
 
@@ -107,7 +107,7 @@ class Base_Model(object):
         keys = sorted(grads.keys())
         scale = 1.0 / self.N if divide_by_N else 1.0
         flat = torch.cat([energy.reshape(1)] + [grads[k].reshape(-1) for k in keys]) * scale
-        host = flat.cpu().numpy()
+        host = to_host(flat)
         out, off = {}, 1
         for k in keys:
             n = grads[k].numel()

@@ -37,17 +37,60 @@ def to_dev(a, device):
     return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)
 
 
+_PIN = {}   # pinned staging buffers, one per device (grown on demand)
+
+
+def _pinned(device, n, slot):
+    key = (str(device), slot)
+    buf = _PIN.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1024), dtype=torch.float64, pin_memory=True)
+        _PIN[key] = buf
+    return buf
+
+
 def pack_to_device(params, device):
-    """Upload a whole parameter dict with ONE host->device copy; returns {key: fp64 device view}."""
+    """Upload a whole parameter dict with ONE host->device copy; returns {key: fp64 device view}.
+    On a GPU the arrays are gathered straight into a pinned staging buffer (no pageable bounce:
+    the latent arrays of SGPLVM / SGPSSM are [N,Q] parameters, 64 MB at T = 1e6)."""
     keys = sorted(params.keys())
-    arrs = [np.ascontiguousarray(params[k], dtype=np.float64) for k in keys]
-    flat = np.concatenate([a.reshape(-1) for a in arrs]) if arrs else np.zeros(0)
-    t = torch.from_numpy(flat).to(device)
+    arrs = [np.asarray(params[k], dtype=np.float64) for k in keys]
+    total = int(sum(a.size for a in arrs))
+    if device.type == 'cuda' and total > 0:
+        ev = _PIN.get((str(device), 'h2d_event'))
+        if ev is not None:
+            ev.synchronize()        # the previous upload has left the staging buffer
+        pin = _pinned(device, total, 'h2d')
+        view = pin.numpy()
+        off = 0
+        for a in arrs:
+            view[off:off + a.size] = a.reshape(-1)
+            off += a.size
+        t = torch.empty(total, dtype=torch.float64, device=device)
+        t.copy_(pin[:total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        _PIN[(str(device), 'h2d_event')] = ev
+    else:
+        flat = np.concatenate([a.reshape(-1) for a in arrs]) if arrs else np.zeros(0)
+        t = torch.from_numpy(flat).to(device)
     out, off = {}, 0
     for k, a in zip(keys, arrs):
         out[k] = t[off:off + a.size].reshape(a.shape if a.ndim > 0 else (1,))
         off += a.size
     return out
+
+
+def to_host(flat):
+    """One device->host copy of a flat fp64 tensor through a pinned buffer -> numpy (a view of the
+    staging buffer: copy what you keep)."""
+    if flat.is_cuda:
+        n = flat.numel()
+        pin = _pinned(flat.device, n, 'd2h')
+        pin[:n].copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(flat.device).synchronize()
+        return pin[:n].numpy()
+    return flat.cpu().numpy()
 
 
 def spd_inverse(A):
