@@ -26,7 +26,9 @@ int mm_rp(int tbytes, int Qt, int DOC) {
 MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do) {
     MMPlan p;
     p.Qt = q_template(Q);
-    p.DOC = Do == 1 ? 1 : (Do == 2 ? 2 : 4);
+    // output dims held in registers per pass: exact for Do <= 4, else 8 / 16 / 32 with one pair
+    // per thread (wide layers, e.g. SGPLVM with Do = 50: 2 passes instead of 13)
+    p.DOC = Do == 1 ? 1 : (Do == 2 ? 2 : (Do <= 4 ? 4 : (Do <= 8 ? 8 : (Do <= 16 ? 16 : 32))));
     p.npass = (int)cdiv(Do, p.DOC);
     p.RP = mm_rp(tbytes, p.Qt, p.DOC);
     p.PC = 256 * p.RP;
@@ -112,8 +114,8 @@ int mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
     constexpr int NS = BWD ? 2 * Q : DOC;
     const size_t smem = sizeof(double) * gpb::ExpDom<T>::TAB + gpb::RowXpose<T, NS>::kBytes;
     prof_begin(BWD ? 4 : 3, stream);
-    if constexpr (BWD && DOC == 4) {
-        if (p.npass > 1) {   // Do > 4: generic multi-pass kernel
+    if constexpr (BWD && DOC == 32) {
+        if (p.npass > 1) {   // Do > 32: generic multi-pass kernel
             auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, true>;
             if (mm_pairs_smem(kern, smem)) return GPB_ERR_CUDA;
             GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), smem, stream, a);
@@ -135,6 +137,9 @@ int mm_pairs_doc(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
         case 1: return mm_pairs_launch<T, Q, 1, BWD>(p, a, stream);
         case 2: return mm_pairs_launch<T, Q, 2, BWD>(p, a, stream);
         case 4: return mm_pairs_launch<T, Q, 4, BWD>(p, a, stream);
+        case 8: return mm_pairs_launch<T, Q, 8, BWD>(p, a, stream);
+        case 16: return mm_pairs_launch<T, Q, 16, BWD>(p, a, stream);
+        case 32: return mm_pairs_launch<T, Q, 32, BWD>(p, a, stream);
     }
     return fail(GPB_ERR_ARG, "mm: bad DOC %d", p.DOC);
 }

@@ -1431,11 +1431,12 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
         // NR rows against this thread's RP pairs; v[i] = this thread's part of the sums of row r0+i.
         // All NR*RP exponents are formed first, then exponentiated in lock step, then consumed.
         auto rows_body = [&](int r0, T (&v)[NR][NS]) {
-            T rc[NR][RL], x[NR * RP], t[NR][RP][Q];
+            constexpr int RCN = DOC > 4 ? 1 + 2 * Q : RL;   // wide layers read dv from smem in place
+            T rc[NR][RCN], x[NR * RP], t[NR][RP][Q];
             GPB_UNROLL
             for (int i = 0; i < NR; i++) {
                 GPB_UNROLL
-                for (int k = 0; k < RL; k++) rc[i][k] = s_rec[kGen ? 0 : buf][(r0 + i) * RL + k];
+                for (int k = 0; k < RCN; k++) rc[i][k] = s_rec[kGen ? 0 : buf][(r0 + i) * RL + k];
                 GPB_UNROLL
                 for (int s = 0; s < NS; s++) v[i][s] = 0;
             }
@@ -1475,15 +1476,17 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                         T coef = 0;
                         GPB_UNROLL
                         for (int d = 0; d < DOC; d++) {
-                            const T dvd = rc[i][1 + 2 * Q + d];
+                            const T dvd = DOC > 4 ? s_rec[kGen ? 0 : buf][(r0 + i) * RL + 1 + 2 * Q + d]
+                                                  : rc[i][(1 + 2 * Q + d) < RCN ? (1 + 2 * Q + d) : 0];
                             accB[j][d] += dvd * psi2;
                             coef += dvd * bs[j][d];
                         }
                         if (!GEN || a.lam_pass) {
                             if (kGen && a.full_coef) {
+                                // coef holds the first DOC output dims (the Lambda pass is the pass
+                                // with d0 == 0); the remaining ones come from the L1-resident table
                                 const long p = pbase + j * kThreads + tid;
-                                coef = 0;
-                                for (int d = 0; d < Do; d++)
+                                for (int d = DOC; d < Do; d++)
                                     coef += (T)s_dvall[(r0 + i) * 64 + d] * a.bs[(long)d * PP + p];
                             }
                             const T lam = coef * psi2;
