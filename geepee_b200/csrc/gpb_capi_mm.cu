@@ -23,12 +23,15 @@ int mm_rp(int tbytes, int Qt, int DOC) {
     return tbytes == 4 ? 2 * rp : rp;
 }
 
-MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do) {
+MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do, int backward) {
     MMPlan p;
     p.Qt = q_template(Q);
     // output dims held in registers per pass: exact for Do <= 4, else 8 / 16 / 32 with one pair
     // per thread (wide layers, e.g. SGPLVM with Do = 50: 2 passes instead of 13)
     p.DOC = Do == 1 ? 1 : (Do == 2 ? 2 : (Do <= 4 ? 4 : (Do <= 8 ? 8 : (Do <= 16 ? 16 : 32))));
+    // forward: the DOC row sums per pair chunk go through the warp transposition, whose cost grows
+    // with DOC while only one pair per thread is left to amortise it -> 4 dims per pass there
+    if (!backward && p.DOC > 4) p.DOC = 4;
     p.npass = (int)cdiv(Do, p.DOC);
     p.RP = mm_rp(tbytes, p.Qt, p.DOC);
     p.PC = 256 * p.RP;
@@ -266,7 +269,7 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
              double* vout, double* vacc, double* psi1save, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
     if (rc) return rc;
-    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do);
+    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do, 0);
     MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 0, ws, ws_bytes);
     if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_fwd: workspace %zu < %zu", ws_bytes, w.bytes);
     auto tab = gpb::mm_pair_table_kernel<T>;
@@ -298,7 +301,7 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
              double* dvx, void* ws, size_t ws_bytes, void* stream) {
     int rc = mm_check<T>(n, M, Q, Do);
     if (rc) return rc;
-    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do);
+    MMPlan p = mm_plan((int)sizeof(T), n, M, Q, Do, 1);
     MMWs<T> w = mm_carve<T>(p, n, M, Q, Do, 1, ws, ws_bytes);
     if (w.bytes > ws_bytes) return fail(GPB_ERR_WS, "mm_bwd: workspace %zu < %zu", ws_bytes, w.bytes);
     auto tab = gpb::mm_pair_table_kernel<T>;
@@ -361,7 +364,7 @@ extern "C" {
 size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward) {
     if (q_template(Q) < 0 || n < 1 || M < 1 || Do < 1) return 0;
     // the pair padding (and with it the fp64 partial records) depends on the precision: take the max
-    MMPlan p8 = mm_plan(8, n, M, Q, Do), p4 = mm_plan(4, n, M, Q, Do);
+    MMPlan p8 = mm_plan(8, n, M, Q, Do, backward), p4 = mm_plan(4, n, M, Q, Do, backward);
     size_t b8 = mm_carve<double>(p8, n, M, Q, Do, backward, nullptr, 0).bytes;
     size_t b4 = mm_carve<float>(p4, n, M, Q, Do, backward, nullptr, 0).bytes;
     return b8 > b4 ? b8 : b4;

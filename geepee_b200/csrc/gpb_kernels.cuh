@@ -1464,6 +1464,46 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
                 }
             }
             exp_dom_n<NR * RP>(x, s_tab, lane16);
+            if (BWD && !GEN && DOC <= 4) {
+                // Register-operand bandwidth: an fp64 FMA with three distinct register operands
+                // issues at ~2/3 rate on this chip, one that shares an operand with its predecessor
+                // at full rate (tools/probe).  The accumulations are therefore emitted in groups
+                // whose consecutive FMAs share an operand and never hit the same accumulator.
+                T lam[NR][RP];
+                GPB_UNROLL
+                for (int i = 0; i < NR; i++)
+                    GPB_UNROLL
+                    for (int j = 0; j < RP; j++) {
+                        T coef = 0;
+                        GPB_UNROLL
+                        for (int d = 0; d < DOC; d++) coef += rc[i][(1 + 2 * Q + d) < RCN ? (1 + 2 * Q + d) : 0] * bs[j][d];
+                        lam[i][j] = coef * x[i * RP + j];
+                    }
+                GPB_UNROLL
+                for (int d = 0; d < DOC; d++)
+                    GPB_UNROLL
+                    for (int i = 0; i < NR; i++)
+                        GPB_UNROLL
+                        for (int j = 0; j < RP; j++)      // shares dv[i][d]
+                            accB[j][d] += rc[i][(1 + 2 * Q + d) < RCN ? (1 + 2 * Q + d) : 0] * x[i * RP + j];
+                GPB_UNROLL
+                for (int i = 0; i < NR; i++)
+                    GPB_UNROLL
+                    for (int j = 0; j < RP; j++)
+                        GPB_UNROLL
+                        for (int q = 0; q < Q; q++)       // shares lam[i][j]
+                            accS1[j][q] += lam[i][j] * t[i][j][q];
+                GPB_UNROLL
+                for (int j = 0; j < RP; j++)
+                    GPB_UNROLL
+                    for (int q = 0; q < Q; q++) {
+                        GPB_UNROLL
+                        for (int i = 0; i < NR; i++) v[i][q] += lam[i][j] * zh[j][q];        // shares zh
+                        GPB_UNROLL
+                        for (int i = 0; i < NR; i++) v[i][Q + q] += lam[i][j] * zh2[j][q];   // shares zh2
+                    }
+                return;
+            }
             GPB_UNROLL
             for (int i = 0; i < NR; i++) {
                 GPB_UNROLL
