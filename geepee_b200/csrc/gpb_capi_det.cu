@@ -124,12 +124,23 @@ int det_bwd_t(const double* x, const double* z, const double* ls, const double* 
     double* rec = (double*)cv.take(sizeof(double) * p.rec_len);
     if (!cv.ok()) return fail(GPB_ERR_WS, "det_bwd: workspace %zu < %zu", ws_bytes, cv.off);
     dim3 grid(p.gx, p.gy);
+    // Do <= 4 and D <= 16: cp.async ring kernel; otherwise the register-batched generic kernel
 #define GPB_BWD2(DP, DOB)                                                                       \
     {                                                                                           \
-        auto kern = gpb::det_bwd_kernel<T, DP, DOB>;                                            \
-        GPB_LAUNCH(kern, grid, dim3(256), 0, stream, x, z, ls, (const T*)Ap, dm, dv,            \
-                   (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block, part, \
-                   p.rec_len);                                                                  \
+        if (DOB > 0 && D <= 16) {                                                               \
+            auto kern = gpb::det_bwd_ring_kernel<T, DP, (DOB > 0 ? DOB : 1)>;                   \
+            const size_t smem = gpb::DetBwdRing<T, (DOB > 0 ? DOB : 1)>::smem_bytes;            \
+            int rcs = allow_smem(kern, smem);                                                   \
+            if (rcs) return rcs;                                                                \
+            GPB_LAUNCH(kern, grid, dim3(256), smem, stream, x, z, ls, (const T*)Ap, dm, dv,     \
+                       (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block,   \
+                       part, p.rec_len);                                                        \
+        } else {                                                                                \
+            auto kern = gpb::det_bwd_kernel<T, DP, DOB>;                                        \
+            GPB_LAUNCH(kern, grid, dim3(256), 0, stream, x, z, ls, (const T*)Ap, dm, dv,        \
+                       (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block,   \
+                       part, p.rec_len);                                                        \
+        }                                                                                       \
     }
 #define GPB_BWD(DP)                                                                             \
     {                                                                                           \

@@ -878,6 +878,139 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
     }
 }
 
+// Ring version of the row-streaming backward (Do <= 4, D <= 16): the saved Kfu / T rows and the
+// per-row x, dm, dv records of TRS rows travel through a cp.async ring (2-3 stages, no register
+// staging), so the global loads of the next chunks are in flight while a chunk is reduced --
+// the register-batched kernel above exposes the full load latency once per 4 rows (ncu: 50 %
+// long-scoreboard stalls, 27 % of HBM peak).  dA is accumulated in the same sweep (the kernel
+// above re-reads Kfu for it).  Same partial-record layout.
+template <typename T, int DOS>
+struct DetBwdRing {
+    static constexpr int TRS = 8;                                   // rows per stage
+    static constexpr int STAGES = DOS == 4 ? 2 : 3;
+    static constexpr int CW = 256;                                  // columns per block (<= MP)
+    static constexpr size_t tile_bytes = (size_t)TRS * CW * sizeof(T) * (1 + DOS);
+    static constexpr size_t rec_doubles = TRS * (16 + 2 * DOS);     // x (DP <= 16), dm, 2 dv
+    static constexpr size_t stage_bytes = tile_bytes + rec_doubles * sizeof(double);
+    static constexpr size_t smem_bytes = STAGES * stage_bytes;
+};
+
+template <typename T, int DP, int DOS>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_ring_kernel(
+    const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls,
+    const T* __restrict__ Ap, const double* __restrict__ dm, const double* __restrict__ dv,
+    const T* __restrict__ Ksave, const T* __restrict__ Tsave, int n, int M, int MP, int D, int Do,
+    int rows_per_block, double* __restrict__ part, long rec_len) {
+    typedef DetBwdRing<T, DOS> C;
+    constexpr int TRS = C::TRS, STAGES = C::STAGES, VEC = V16<T>::N;
+    GPB_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int CWB = MP < 256 ? MP : 256;
+    const int RY = kThreads / CWB;
+    const int cx = tid % CWB, ry = tid / CWB;
+    const int cbase = blockIdx.y * CWB;
+    const int c = cbase + cx;
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = (r_begin + rows_per_block) < n ? (r_begin + rows_per_block) : n;
+    const int nchunk = (r_end - r_begin + TRS - 1) / TRS;
+    double* rec = part + ((long)(blockIdx.x * RY + ry)) * rec_len;
+
+    auto stage_K = [&](int st) { return (T*)(smem + (size_t)st * C::stage_bytes); };
+    auto stage_R = [&](int st) { return (double*)(smem + (size_t)st * C::stage_bytes + C::tile_bytes); };
+    auto issue = [&](int chunk) {
+        if (chunk < nchunk) {
+            const int st = chunk % STAGES;
+            T* Ks = stage_K(st);
+            double* Rs = stage_R(st);          // [x: TRS*DP | dm: TRS*DOS | 2dv (raw dv here): TRS*DOS]
+            const int t0 = r_begin + chunk * TRS;
+            const int vec_per_row = CWB / VEC;
+            const int nvec = TRS * vec_per_row * (1 + DOS);
+            for (int v = tid; v < nvec; v += kThreads) {
+                const int which = v / (TRS * vec_per_row);          // 0: K, 1..DOS: T_d
+                const int rem = v - which * (TRS * vec_per_row);
+                const int r = rem / vec_per_row, cv = rem - r * vec_per_row;
+                const long row = (long)t0 + r;
+                const bool ok = row < r_end && (which == 0 || which - 1 < Do);
+                const long rowc = row < r_end ? row : (long)r_begin;
+                const T* src = which == 0 ? Ksave + rowc * MP + cbase + cv * VEC
+                                          : Tsave + (rowc * Do + (which - 1 < Do ? which - 1 : 0)) * MP + cbase + cv * VEC;
+                cp_async16_zfill(Ks + (long)which * TRS * CWB + (long)r * CWB + cv * VEC, src, ok);
+            }
+            for (int i = tid; i < TRS * DP; i += kThreads) {
+                const int r = i / DP, q = i - r * DP;
+                const long row = (long)t0 + r;
+                const bool ok = row < r_end && q < D;
+                cp_async8_zfill(Rs + i, x + (ok ? row * D + q : 0), ok);
+            }
+            for (int i = tid; i < 2 * TRS * DOS; i += kThreads) {
+                const int w = i / (TRS * DOS), rem = i - w * (TRS * DOS);
+                const int r = rem / DOS, d = rem - r * DOS;
+                const long row = (long)t0 + r;
+                const bool ok = row < r_end && d < Do;
+                const double* src = (w == 0 ? dm : dv) + (ok ? row * Do + d : 0);
+                cp_async8_zfill(Rs + TRS * DP + i, src, ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    T zr[DP];
+    double dz[DP], dl[DP], dA[DOS], cs = 0;
+    T ap[DOS];
+    GPB_UNROLL
+    for (int q = 0; q < DP; q++) {
+        zr[q] = (c < M && q < D) ? (T)z[(long)c * D + q] : (T)0;
+        dz[q] = 0;
+        dl[q] = 0;
+    }
+    GPB_UNROLL
+    for (int d = 0; d < DOS; d++) {
+        ap[d] = d < Do ? Ap[(long)d * MP + c] : (T)0;
+        dA[d] = 0;
+    }
+    GPB_UNROLL
+    for (int s0 = 0; s0 < STAGES - 1; s0++) issue(s0);
+    for (int ch = 0; ch < nchunk; ch++) {
+        if (STAGES == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        sync_threads();                       // chunk ch landed everywhere; stage (ch-1) is free
+        issue(ch + STAGES - 1);
+        const int st = ch % STAGES;
+        const T* Ks = stage_K(st);
+        const double* Rs = stage_R(st);
+        for (int r = ry; r < TRS; r += RY) {
+            const double k = (double)Ks[r * CWB + cx];
+            double g = 0;
+            GPB_UNROLL
+            for (int d = 0; d < DOS; d++) {
+                const double dmd = Rs[TRS * DP + r * DOS + d];
+                const double dvd = Rs[TRS * DP + TRS * DOS + r * DOS + d];
+                g += dmd * (double)ap[d] + 2.0 * dvd * (double)Ks[(long)(1 + d) * TRS * CWB + r * CWB + cx];
+                dA[d] += dmd * k;
+            }
+            const double L = g * k;
+            cs += L;
+            GPB_UNROLL
+            for (int q = 0; q < DP; q++) {
+                const double diff = (double)zr[q] - Rs[r * DP + q];
+                const double t = L * diff;
+                dz[q] += t;
+                dl[q] += t * diff;
+            }
+        }
+    }
+    rec[c] = cs;
+    GPB_UNROLL
+    for (int q = 0; q < DP; q++)
+        if (q < D) {
+            const double il2 = exp(-2.0 * ls[q]);
+            rec[(long)MP + (long)c * D + q] = -dz[q] * il2;
+            rec[(long)MP + (long)MP * D + (long)c * D + q] = dl[q] * il2 * exp(-ls[q]);
+        }
+    GPB_UNROLL
+    for (int d = 0; d < DOS; d++)
+        if (d < Do) rec[(long)MP + 2L * MP * D + (long)d * MP + c] = dA[d];
+}
+
 // a8 (rank-update part), aep_models.py:493: dB[d] = sum_n dv[n,d] kfu[n,:] kfu[n,:]^T.
 // Upper block-triangle of 128x128 output blocks; split over rows; partial records
 //   part[((split*Do + d)*NBU + ub)*128*128 + i*128 + j]

@@ -49,6 +49,12 @@ GPB_DEVICE void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool vali
     int n = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(n));
 }
+// 8-byte variant (element-granular staging of small per-row records), zero-fill when !valid
+GPB_DEVICE void cp_async8_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(n));
+}
 GPB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 GPB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -119,6 +125,9 @@ static inline void dmma(double& c0, double& c1, double a, double b) {
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async16_zfill(void* d, const void* s, bool valid) {
     if (valid) memcpy(d, s, 16); else memset(d, 0, 16);
+}
+static inline void cp_async8_zfill(void* d, const void* s, bool valid) {
+    if (valid) memcpy(d, s, 8); else memset(d, 0, 8);
 }
 static inline void cp_async_commit() {}
 template <int N>
