@@ -128,13 +128,22 @@ int det_bwd_t(const double* x, const double* z, const double* ls, const double* 
 #define GPB_BWD2(DP, DOB)                                                                       \
     {                                                                                           \
         if (DOB > 0 && D <= 16) {                                                               \
-            auto kern = gpb::det_bwd_ring_kernel<T, DP, (DOB > 0 ? DOB : 1)>;                   \
             const size_t smem = gpb::DetBwdRing<T, (DOB > 0 ? DOB : 1)>::smem_bytes;            \
-            int rcs = allow_smem(kern, smem);                                                   \
-            if (rcs) return rcs;                                                                \
-            GPB_LAUNCH(kern, grid, dim3(256), smem, stream, x, z, ls, (const T*)Ap, dm, dv,     \
-                       (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do, p.rows_per_block,   \
-                       part, p.rec_len);                                                        \
+            if (p.CWB == 128) {                                                                 \
+                auto kern = gpb::det_bwd_ring_kernel<T, DP, (DOB > 0 ? DOB : 1), 128>;          \
+                int rcs = allow_smem(kern, smem);                                               \
+                if (rcs) return rcs;                                                            \
+                GPB_LAUNCH(kern, grid, dim3(256), smem, stream, x, z, ls, (const T*)Ap, dm, dv, \
+                           (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do,                 \
+                           p.rows_per_block, part, p.rec_len);                                  \
+            } else {                                                                            \
+                auto kern = gpb::det_bwd_ring_kernel<T, DP, (DOB > 0 ? DOB : 1), 256>;          \
+                int rcs = allow_smem(kern, smem);                                               \
+                if (rcs) return rcs;                                                            \
+                GPB_LAUNCH(kern, grid, dim3(256), smem, stream, x, z, ls, (const T*)Ap, dm, dv, \
+                           (const T*)Ksave, (const T*)Tsave, n, M, p.MP, D, Do,                 \
+                           p.rows_per_block, part, p.rec_len);                                  \
+            }                                                                                   \
         } else {                                                                                \
             auto kern = gpb::det_bwd_kernel<T, DP, DOB>;                                        \
             GPB_LAUNCH(kern, grid, dim3(256), 0, stream, x, z, ls, (const T*)Ap, dm, dv,        \

@@ -895,7 +895,7 @@ struct DetBwdRing {
     static constexpr size_t smem_bytes = STAGES * stage_bytes;
 };
 
-template <typename T, int DP, int DOS>
+template <typename T, int DP, int DOS, int CWB>
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_ring_kernel(
     const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls,
     const T* __restrict__ Ap, const double* __restrict__ dm, const double* __restrict__ dv,
@@ -905,8 +905,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_ring_kernel(
     constexpr int TRS = C::TRS, STAGES = C::STAGES, VEC = V16<T>::N;
     GPB_DYN_SMEM(smem);
     const int tid = threadIdx.x;
-    const int CWB = MP < 256 ? MP : 256;
-    const int RY = kThreads / CWB;
+    constexpr int RY = kThreads / CWB;            // CWB = min(MP, 256) columns per block
     const int cx = tid % CWB, ry = tid / CWB;
     const int cbase = blockIdx.y * CWB;
     const int c = cbase + cx;
@@ -923,9 +922,12 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_ring_kernel(
             T* Ks = stage_K(st);
             double* Rs = stage_R(st);          // [x: TRS*DP | dm: TRS*DOS | 2dv (raw dv here): TRS*DOS]
             const int t0 = r_begin + chunk * TRS;
-            const int vec_per_row = CWB / VEC;
-            const int nvec = TRS * vec_per_row * (1 + DOS);
-            for (int v = tid; v < nvec; v += kThreads) {
+            constexpr int vec_per_row = CWB / VEC;
+            constexpr int nvec = TRS * vec_per_row * (1 + DOS);
+            static_assert(nvec % kThreads == 0, "tile copies must divide evenly");
+            GPB_UNROLL
+            for (int it = 0; it < nvec / kThreads; it++) {
+                const int v = tid + it * kThreads;
                 const int which = v / (TRS * vec_per_row);          // 0: K, 1..DOS: T_d
                 const int rem = v - which * (TRS * vec_per_row);
                 const int r = rem / vec_per_row, cv = rem - r * vec_per_row;
