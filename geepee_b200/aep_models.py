@@ -80,7 +80,8 @@ class SGPR(Base_SGPR):
             add['logZ'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
         add = dist.allreduce_dict(add)
         grads = L._tail_det(_get_stats(add, 's_'), alpha)
-        grads['sn'] = add['dsn'].reshape(())
+        if self.lik_layer.has_sn:
+            grads['sn'] = add['dsn'].reshape(())
         energy = scale_logZ * add['logZ'] + L._phi(alpha)
         return self._finish(energy, grads)
 
@@ -167,7 +168,8 @@ class SDGPR(Base_SDGPR):
         energy = scale_logZ * top['logZ']
         for i in range(self.L):
             energy = energy + phis[i]
-        grads['sn'] = top['dsn'].reshape(())
+        if self.lik_layer.has_sn:
+            grads['sn'] = top['dsn'].reshape(())
         return self._finish(energy, grads)
 
 
@@ -253,7 +255,8 @@ class SGPLVM(Base_SGPLVM):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
         grads = L._tail_mm(_get_stats(add, 's_'), alpha)
-        grads['sn'] = add['dsn'].reshape(())
+        if self.lik_layer.has_sn:
+            grads['sn'] = add['dsn'].reshape(())
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']
         pm, pv = self.prior_mean, self.prior_var
         phi_prior = 0.5 * (pm**2 / pv + np.log(pv)) * N * Q

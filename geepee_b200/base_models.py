@@ -14,7 +14,7 @@ from scipy.optimize import minimize
 from . import config, dist
 from .config import PROP_MM, PROP_MC
 from .layers import default_device, to_dev, pack_to_device, to_host
-from .lik_layers import Gauss_Layer, Gauss_Emis
+from .lik_layers import Gauss_Layer, Probit_Layer, Gauss_Emis
 from .utils import ObjectiveWrapper, flatten_dict, unflatten_dict, adam, PCA_reduce
 
 _F = torch.float64
@@ -24,8 +24,7 @@ def _make_lik(lik, N, Dout, device):
     if lik.lower() == 'gaussian':
         return Gauss_Layer(N, Dout, device)
     if lik.lower() == 'probit':
-        raise NotImplementedError('Probit likelihood is not part of the B200 hot path yet '
-                                  '(SURVEY.md section 8f, rank 1)')
+        return Probit_Layer(N, Dout, device)
     raise NotImplementedError('likelihood not implemented')
 
 

@@ -86,6 +86,22 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
     return GPB_CHECK_LAUNCH();
 }
 
+int gpb_probit_lik(const double* m, const double* v, const double* y, const double* gh_x,
+                   const double* gh_w, int ngh, double alpha, double scale, long total, int mode,
+                   double* dm, double* dv, double* out2, void* ws, size_t ws_bytes, void* stream) {
+    if (!m || !v || !y || !gh_x || !gh_w || !dm || !dv || !out2 || total < 1 || (mode != 0 && mode != 1) ||
+        ngh < 1 || ngh > 64)
+        return fail(GPB_ERR_ARG, "probit_lik: bad argument");
+    int grid = elementwise_grid(total);
+    if (ws_bytes < sizeof(double) * 2 * (size_t)grid) return fail(GPB_ERR_WS, "probit_lik: workspace too small");
+    auto kern = gpb::probit_lik_kernel;
+    GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, m, v, y, gh_x, gh_w, ngh, alpha, scale, total, mode,
+               dm, dv, (double*)ws);
+    auto red = gpb::reduce_partials_kernel;
+    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)ws, grid, 2L, 2L, out2, 0);
+    return GPB_CHECK_LAUNCH();
+}
+
 size_t gpb_gauss_emis_ws_bytes(int n, int Do, int Q) {
     const int DO = emis_pad(Do), QT = emis_pad(Q);
     if (DO < 0 || QT < 0 || n < 1) return 0;

@@ -157,6 +157,77 @@ GPB_KERNEL void gauss_lik_kernel(const double* __restrict__ m, const double* __r
 }
 
 // -------------------------------------------------------------------------
+// (8f rank 1) Probit likelihood for binary y in {-1,+1}: lik_layers.py:303-362 (mode 0: AEP
+//     log Z tilted -- closed form for alpha == 1, Gauss-Hermite quadrature of degree ngh
+//     otherwise, with the reference's eps guards) and 418-436 (mode 1: VFE expected log-lik).
+//     Elementwise over [n,Do]; writes scale*dm, scale*dv and per-block sums of the log terms.
+// -------------------------------------------------------------------------
+GPB_KERNEL void probit_lik_kernel(const double* __restrict__ m, const double* __restrict__ v,
+                                  const double* __restrict__ y, const double* __restrict__ gh_x,
+                                  const double* __restrict__ gh_w, int ngh, double alpha, double scale,
+                                  long total, int mode, double* __restrict__ dm, double* __restrict__ dv,
+                                  double* __restrict__ part /* [gridDim.x][2] */) {
+    GPB_SHARED double scratch[16];
+    GPB_SHARED double sx[64], sw[64];
+    for (int i = threadIdx.x; i < ngh && i < 64; i += blockDim.x) { sx[i] = gh_x[i]; sw[i] = gh_w[i]; }
+    sync_threads();
+    const double kSqrt2 = 1.4142135623730951, kPi = 3.14159265358979323846;
+    double s0 = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long)gridDim.x * blockDim.x) {
+        const double mi = m[i], vi = v[i], yi = y[i];
+        double dmi, dvi;
+        if (mode == 0 && alpha == 1.0) {
+            const double t = yi * mi / sqrt(1.0 + vi);
+            const double Z = 0.5 * (1.0 + erf(t / kSqrt2));
+            const double eps = 1e-16;
+            s0 += log(Z + eps);
+            const double dt = 1.0 / (Z + eps) / sqrt(2.0 * kPi) * exp(-t * t / 2.0);
+            dmi = dt * yi / sqrt(1.0 + vi);
+            dvi = dt * (-0.5 * yi * mi / ((1.0 + vi) * sqrt(1.0 + vi)));
+        } else if (mode == 0) {
+            const double eps = 1e-8, sd = sqrt(2.0 * vi);
+            double Zt = 0, sa = 0, sax = 0;
+            for (int k = 0; k < ngh; k++) {
+                const double ts = sx[k] * sd + mi;
+                const double pdf = 0.5 * (1.0 + erf(yi * ts / kSqrt2)) + eps;
+                Zt += pow(pdf, alpha) * sw[k];
+                const double a = pow(pdf, alpha - 1.0) * exp(-ts * ts / 2.0);
+                sa += sw[k] * a;
+                sax += sw[k] * (a * sx[k]);
+            }
+            Zt /= sqrt(kPi);
+            s0 += log(Zt);
+            const double dZdm = sa * yi * alpha / kPi / kSqrt2;
+            const double dZdv = sax * yi * alpha / kPi / kSqrt2 / sd;
+            dmi = dZdm / Zt + eps;
+            dvi = dZdv / Zt + eps;
+        } else {
+            const double sd = sqrt(2.0 * vi), isp = 1.0 / sqrt(kPi);
+            double a = 0, b = 0;
+            for (int k = 0; k < ngh; k++) {
+                const double u = (sx[k] * sd + mi) * yi;
+                const double cdf = 0.5 * erfc(-u / kSqrt2);
+                const double w = sw[k] * isp;
+                s0 += w * log(cdf);
+                const double g = yi * w * exp(-u * u / 2.0) / sqrt(2.0 * kPi) / cdf;
+                a += g;
+                b += g * 0.5 * sx[k] * sqrt(2.0 / vi);
+            }
+            dmi = a;
+            dvi = b;
+        }
+        dm[i] = scale * dmi;
+        dv[i] = scale * dvi;
+    }
+    const double r0 = block_sum(s0, scratch);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 2 + 0] = r0;
+        part[blockIdx.x * 2 + 1] = 0.0;
+    }
+}
+
+// -------------------------------------------------------------------------
 // a14. Linear-Gaussian emission, tilted (AEP): lik_layers.py:573-627
 //     y ~ N(C x, diag(R)):  per row  Vy = diag(R/alpha) + C diag(vx) C^T  (Do x Do, SPD),
 //     w = Vy^-1 (y - C mx),  log|Vy|,  Vy^-1;  dSig = -Vy^-1/2 + w w^T/2.
@@ -1198,6 +1269,10 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_mma_kernel(const double* __restr
         cp_async_commit();   // always commit (possibly empty) so the group counting stays uniform
     };
 
+    // diagonal blocks are symmetric: the warp tiles that lie entirely below the diagonal
+    // (rows >= 64, columns < 64) are never read by det_syrk_finish_kernel and skip their MMAs,
+    // which frees a quarter of the FP64 tensor pipe for the other six warps
+    const bool skip = (bi == bj) && rw >= 2 && cw == 0;
     issue(0);
     issue(1);
     for (int c = 0; c < nchunk; c++) {
@@ -1207,6 +1282,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_mma_kernel(const double* __restr
         const int st = c % STAGES;
         const double* As = (const double*)(smem + (size_t)st * C::stage_bytes) + rw * 32 + g;
         const double* Bs = (const double*)(smem + (size_t)st * C::stage_bytes) + RK * LD + cw * 64 + g;
+        if (skip) continue;
         GPB_UNROLL
         for (int k4 = 0; k4 < RK; k4 += 4) {
             const double w = s_dv[st * RK + k4 + t];
@@ -1243,7 +1319,9 @@ GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nspl
          idx += (long)gridDim.x * blockDim.x) {
         int j = (int)(idx % M), i = (int)((idx / M) % M), d = (int)(idx / ((long)M * M));
         int bi = i / 128, bj = j / 128, ii = i % 128, jj = j % 128;
-        if (bi > bj) { int t = bi; bi = bj; bj = t; t = ii; ii = jj; jj = t; }
+        // only the upper block triangle exists, and inside a diagonal block only its upper triangle
+        // is guaranteed (the fp64 tensor kernel skips the warp tiles below it)
+        if (bi > bj || (bi == bj && ii > jj)) { int t = bi; bi = bj; bj = t; t = ii; ii = jj; jj = t; }
         int ub = 0;
         for (int b = 0; b < bi; b++) ub += nb - b;
         ub += bj - bi;

@@ -4,7 +4,8 @@ Gauss_Layer (85-283): the per-row log-partition / expected log-likelihood and th
 derivatives run in the `gauss_lik` CUDA kernel, fused with the scaling by scale_logZ.
 Gauss_Emis (474-676): linear-Gaussian emission of the state-space model; a batched
 Dout x Dout problem per row, evaluated on the device in fp64.
-Probit_Layer (285-471) is a "next" row of the scope table.
+Probit_Layer (285-471): binary classification, closed form for
+alpha = 1 and Gauss-Hermite quadrature otherwise, in the `probit_lik` CUDA kernel.
 """
 import numpy as np
 import torch
@@ -16,6 +17,8 @@ _F = torch.float64
 
 
 class Lik_Layer(object):
+    has_sn = False          # does the layer own a noise hyper-parameter 'sn'?
+
     def __init__(self, N, D):
         self.N = N
         self.D = D
@@ -30,7 +33,58 @@ class Lik_Layer(object):
         pass
 
 
+class Probit_Layer(Lik_Layer):
+    """lik_layers.py:285-471 (2-D branches; y in {-1,+1}; no hyper-parameters)."""
+
+    def __init__(self, N, D, device=None):
+        super(Probit_Layer, self).__init__(N, D)
+        self.device = device
+        from . import config
+        gx, gw = np.polynomial.hermite.hermgauss(config.GH_DEGREE)   # lik_layers.py:290-301
+        self._gx, self._gw = to_dev(gx, device), to_dev(gw, device)
+
+    def update_hypers(self, params, key_suffix='', _dev=None):
+        pass
+
+    # ---- device path (same contract as Gauss_Layer; the 'sn' slot is a zero) ---------------
+    def _log_Z(self, m, v, y, alpha, scale):
+        dm, dv, o = ops.probit_lik(m, v, y, self._gx, self._gw, alpha, scale, 0)
+        return dm, dv, o[0], o[1].reshape(())
+
+    def _log_lik_exp(self, m, v, y, scale):
+        dm, dv, o = ops.probit_lik(m, v, y, self._gx, self._gw, 1.0, scale, 1)
+        return dm, dv, o[0], o[1].reshape(())
+
+    # ---- reference API (numpy) ---------------------------------------------------------------
+    def compute_log_Z(self, mout, vout, y, alpha=1.0, compute_dm2=False):
+        if mout.ndim != 2 or compute_dm2:
+            raise NotImplementedError('Monte-Carlo (3-D) branch / dm2 are not part of the B200 hot path yet')
+        dev = self.device
+        dm, dv, o = ops.probit_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._gx, self._gw,
+                                   alpha, 1.0, 0)
+        return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
+
+    def compute_log_lik_exp(self, m, v, y):
+        if m.ndim != 2:
+            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+        dev = self.device
+        dm, dv, o = ops.probit_lik(to_dev(m, dev), to_dev(v, dev), to_dev(y, dev), self._gx, self._gw,
+                                   1.0, 1.0, 1)
+        return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
+
+    def backprop_grads(self, mout, vout, dmout, dvout, alpha=1.0, scale=1.0):
+        return {}
+
+    def backprop_grads_log_lik_exp(self, m, v, dm, dv, y, scale=1.0):
+        return {}
+
+    def output_probabilistic(self, mf, vf, alpha=1.0):
+        raise NotImplementedError('TODO: return probablity of y=1')     # lik_layers.py:471
+
+
 class Gauss_Layer(Lik_Layer):
+    has_sn = True
+
     def __init__(self, N, D, device=None):
         super(Gauss_Layer, self).__init__(N, D)
         self.sn = 0

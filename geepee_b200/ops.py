@@ -94,6 +94,21 @@ def gauss_lik(m, v, y, sn, alpha, scale, mode):
     return dm, dv, out2
 
 
+def probit_lik(m, v, y, gh_x, gh_w, alpha, scale, mode):
+    """lik_layers.py:303-362 (mode 0) / 418-436 (mode 1).  Returns scaled dm, dv and a device
+    tensor [sum of log terms, 0]."""
+    lib = _lib.get()
+    total = m.numel()
+    dm = torch.empty_like(m)
+    dv = torch.empty_like(m)
+    out2 = torch.empty(2, dtype=torch.float64, device=m.device)
+    ws = _ws(lib.gpb_gauss_lik_ws_bytes(total), m)
+    _chk(lib.gpb_probit_lik(_p(_c(m)), _p(_c(v)), _p(_c(y)), _p(_c(gh_x)), _p(_c(gh_w)), int(gh_x.numel()),
+                            float(alpha), float(scale), total, int(mode), _p(dm), _p(dv), _p(out2), _p(ws),
+                            ws.numel(), _stream(m)), 'probit_lik')
+    return dm, dv, out2
+
+
 def gauss_emis_supported(Do, Q):
     return Do <= 8 and Q <= 8
 

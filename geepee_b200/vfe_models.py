@@ -41,7 +41,8 @@ class SGPR(Base_SGPR):
             add['ll'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
         add = dist.allreduce_dict(add)
         grads = L._tail(_get_stats(add, 's_'), False)
-        grads['sn'] = add['dsn'].reshape(())
+        if self.lik_layer.has_sn:
+            grads['sn'] = add['dsn'].reshape(())
         energy = scale * add['ll'] + L._kl()
         return self._finish(energy, grads)
 
@@ -91,7 +92,8 @@ class SGPLVM(Base_SGPLVM):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
         grads = L._tail(_get_stats(add, 's_'), True)
-        grads['sn'] = add['dsn'].reshape(())
+        if self.lik_layer.has_sn:
+            grads['sn'] = add['dsn'].reshape(())
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']
         energy = scale * add['ll'] + sx * add['klx'] + L._kl()
         return self._finish(energy, grads)

@@ -69,6 +69,15 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
                   double alpha, double scale, long total, int mode, double* dm, double* dv,
                   double* out2, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- (8f rank 1) Probit likelihood, y in {-1,+1}.  mode 0: lik_layers.py:303-362 Probit_Layer.compute_log_Z
+ *      (alpha == 1: closed form; otherwise Gauss-Hermite quadrature with the nodes / weights of
+ *      numpy.polynomial.hermite.hermgauss(ngh), ngh <= 64, passed in device arrays);
+ *      mode 1: lik_layers.py:418-436 compute_log_lik_exp.  dm, dv come out multiplied by `scale`;
+ *      out2[0] = sum of the log terms (unscaled).  Workspace: gpb_gauss_lik_ws_bytes(total). */
+int gpb_probit_lik(const double* m, const double* v, const double* y, const double* gh_x,
+                   const double* gh_w, int ngh, double alpha, double scale, long total, int mode,
+                   double* dm, double* dv, double* out2, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- a14: linear-Gaussian emission, tilted.  lik_layers.py:573-627 Gauss_Emis.compute_emission_tilted:
  *      y ~ N(C x, diag(R)), per row Vy = diag(R/alpha) + C diag(vx) C^T.  R[Do] are VARIANCES.
  *      dmx, dvx[n,Q] come out multiplied by `scale`;

@@ -486,6 +486,62 @@ def gauss_dsn_log_lik_exp(sn, m, v, y, scale):
     return scale * np.sum(-1 + (y**2 - 2 * y * m + m**2 + v) / sn2)
 
 
+GH_DEGREE = 10   # config.py:12
+
+
+def probit_log_Z(mout, vout, y, alpha):
+    """lik_layers.py:303-362 Probit_Layer.compute_log_Z, 2-D branch (y in {-1,+1})."""
+    from scipy import special
+    if alpha == 1.0:
+        t = y * mout / np.sqrt(1 + vout)
+        Z = 0.5 * (1 + special.erf(t / np.sqrt(2)))
+        eps = 1e-16
+        logZ = np.sum(np.log(Z + eps))
+        dlogZ_dt = 1 / (Z + eps) / np.sqrt(2 * np.pi) * np.exp(-t**2.0 / 2)
+        return logZ, dlogZ_dt * y / np.sqrt(1 + vout), dlogZ_dt * (-0.5 * y * mout / (1 + vout)**1.5)
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(GH_DEGREE)
+    gh_x, gh_w = gh_x[:, None, None], gh_w[:, None, None]
+    ts = gh_x * np.sqrt(2 * vout[None]) + mout[None]
+    eps = 1e-8
+    pdfs = 0.5 * (1 + special.erf(y * ts / np.sqrt(2))) + eps
+    Zt = np.sum(pdfs**alpha * gh_w, axis=0) / np.sqrt(np.pi)
+    logZ = np.sum(np.log(Zt))
+    a = pdfs**(alpha - 1.0) * np.exp(-ts**2 / 2)
+    dZdm = np.sum(gh_w * a, axis=0) * y * alpha / np.pi / np.sqrt(2)
+    dZdv = np.sum(gh_w * (a * gh_x), axis=0) * y * alpha / np.pi / np.sqrt(2) / np.sqrt(2 * vout)
+    return logZ, dZdm / Zt + eps, dZdv / Zt + eps
+
+
+def probit_log_lik_exp(m, v, y):
+    """lik_layers.py:418-436 Probit_Layer.compute_log_lik_exp, 2-D branch."""
+    from scipy.stats import norm
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(GH_DEGREE)
+    gh_x, gh_w = gh_x[:, None, None], gh_w[:, None, None] / np.sqrt(np.pi)
+    ts = gh_x * np.sqrt(2 * v[None]) + m[None]
+    loglik = np.sum(gh_w * norm.logcdf(ts * y))
+    grad_cdfs = y * gh_w * norm.pdf(ts * y) / norm.cdf(ts * y)
+    return loglik, np.sum(grad_cdfs, axis=0), np.sum(grad_cdfs * 0.5 * gh_x * np.sqrt(2 / v[None]), axis=0)
+
+
+def lik_log_Z(lik, params, m, v, y, alpha, scale, g, sn_key='sn'):
+    """Tilted log-partition of the output likelihood + its hyper gradient into g."""
+    if lik == 'Probit':
+        return probit_log_Z(m, v, y, alpha)
+    sn = params[sn_key]
+    logZ, dm, dv = gauss_log_Z(sn, m, v, y, alpha)
+    g[sn_key] = gauss_dsn(sn, m, dv, alpha, scale)
+    return logZ, dm, dv
+
+
+def lik_log_lik_exp(lik, params, m, v, y, scale, g, sn_key='sn'):
+    if lik == 'Probit':
+        return probit_log_lik_exp(m, v, y)
+    sn = params[sn_key]
+    ll, dm, dv = gauss_log_lik_exp(sn, m, v, y)
+    g[sn_key] = gauss_dsn_log_lik_exp(sn, m, v, y, scale)
+    return ll, dm, dv
+
+
 class GaussEmis(object):
     """lik_layers.py:474-676 Gauss_Emis: y ~ N(C x, diag(R))."""
 
@@ -551,8 +607,8 @@ def _pick_rows(N, mb_size):
 class AepSGPR(object):
     """aep_models.py:589-667."""
 
-    def __init__(self, x, y, M, nat_param=True):
-        self.x, self.y = x, y
+    def __init__(self, x, y, M, nat_param=True, lik='Gaussian'):
+        self.x, self.y, self.lik = x, y, lik
         self.N, self.Din, self.Dout, self.M = y.shape[0], x.shape[1], y.shape[1], M
         self.layer = Layer(self.N, self.Din, self.Dout, M, nat_param)
         self.fixed_params = []
@@ -564,12 +620,13 @@ class AepSGPR(object):
         scale = -N * 1.0 / yb.shape[0] / alpha
         L = self.layer
         L.set_params(params)
-        sn = params['sn']
+        sn = params.get('sn')
         L.cavity(alpha)
         m, v, kfu = L.prop_det(xb)
-        logZ, dm, dv = gauss_log_Z(sn, m, v, yb, alpha)
+        gl = {}
+        logZ, dm, dv = lik_log_Z(self.lik, params, m, v, yb, alpha, scale, gl)
         g = L.aep_grads_det(m, v, scale * dm, scale * dv, kfu, xb, alpha)
-        g['sn'] = gauss_dsn(sn, m, dv, alpha, scale)
+        g.update(gl)
         energy = scale * logZ + L.phi(alpha)
         for p in self.fixed_params:
             g[p] = np.zeros_like(g[p])
@@ -579,8 +636,8 @@ class AepSGPR(object):
 class VfeSGPR(object):
     """vfe_models.py:551-632."""
 
-    def __init__(self, x, y, M, nat_param=True):
-        self.x, self.y = x, y
+    def __init__(self, x, y, M, nat_param=True, lik='Gaussian'):
+        self.x, self.y, self.lik = x, y, lik
         self.N, self.Din, self.Dout, self.M = y.shape[0], x.shape[1], y.shape[1], M
         self.layer = Layer(self.N, self.Din, self.Dout, M, nat_param)
         self.fixed_params = []
@@ -592,11 +649,12 @@ class VfeSGPR(object):
         scale = -N * 1.0 / yb.shape[0]
         L = self.layer
         L.set_params(params)
-        sn = params['sn']
+        sn = params.get('sn')
         m, v, kfu = L.prop_det(xb, cav=False)
-        ll, dm, dv = gauss_log_lik_exp(sn, m, v, yb)
+        gl = {}
+        ll, dm, dv = lik_log_lik_exp(self.lik, params, m, v, yb, scale, gl)
         g = L.vfe_grads_det(m, v, scale * dm, scale * dv, kfu, xb)
-        g['sn'] = gauss_dsn_log_lik_exp(sn, m, v, yb, scale)
+        g.update(gl)
         energy = scale * ll + L.kl()
         for p in self.fixed_params:
             g[p] = np.zeros_like(g[p])
@@ -606,8 +664,8 @@ class VfeSGPR(object):
 class AepSDGPR(object):
     """aep_models.py:870-988 (layers always nat_param: line 893)."""
 
-    def __init__(self, x, y, Ms, hidden_sizes):
-        self.x, self.y = x, y
+    def __init__(self, x, y, Ms, hidden_sizes, lik='Gaussian'):
+        self.x, self.y, self.lik = x, y, lik
         self.N, self.Din, self.Dout = y.shape[0], x.shape[1], y.shape[1]
         self.size = [self.Din] + list(hidden_sizes) + [self.Dout]
         self.L = len(self.size) - 1
@@ -624,7 +682,7 @@ class AepSDGPR(object):
         for i, L in enumerate(self.layers):
             L.set_params(params, '_%d' % i)
             L.cavity(alpha)
-        sn = params['sn']
+        sn = params.get('sn')
         ms, vs, p1, p2 = [], [], [], []
         for i, L in enumerate(self.layers):
             if i == 0:
@@ -633,7 +691,8 @@ class AepSDGPR(object):
             else:
                 m, v, k, q = L.prop_mm(ms[-1], vs[-1])
             ms.append(m), vs.append(v), p1.append(k), p2.append(q)
-        logZ, dm, dv = gauss_log_Z(sn, ms[-1], vs[-1], yb, alpha)
+        gl = {}
+        logZ, dm, dv = lik_log_Z(self.lik, params, ms[-1], vs[-1], yb, alpha, scale, gl)
         dmi, dvi = scale * dm, scale * dv
         g = {}
         for i in range(self.L - 1, -1, -1):
@@ -646,7 +705,7 @@ class AepSDGPR(object):
                 dmi, dvi = gi['mx'], gi['vx']
             for k, val in gh.items():
                 g[k + '_%d' % i] = val
-        g['sn'] = gauss_dsn(sn, ms[-1], dv, alpha, scale)
+        g.update(gl)
         energy = scale * logZ + sum(L.phi(alpha) for L in self.layers)
         for p in self.fixed_params:
             g[p] = np.zeros_like(g[p])
@@ -663,8 +722,8 @@ class AepSGPLVM(object):
     """aep_models.py:670-867 + base_models.py:661-929 (nat_param=True only: the
     reference's AEP moment-matched tail has no valid nat_param=False variant)."""
 
-    def __init__(self, y, Q, M, prior_mean=0, prior_var=1):
-        self.y = y
+    def __init__(self, y, Q, M, prior_mean=0, prior_var=1, lik='Gaussian'):
+        self.y, self.lik = y, lik
         self.N, self.Dout, self.Din, self.M = y.shape[0], y.shape[1], Q, M
         self.layer = Layer(self.N, Q, self.Dout, M)
         self.prior_mean, self.prior_var = prior_mean, prior_var
@@ -682,7 +741,7 @@ class AepSGPLVM(object):
         scale = -N * 1.0 / nb / alpha
         L = self.layer
         L.set_params(params)
-        sn = params['sn']
+        sn = params.get('sn')
         f1 = params['x1']
         f2 = np.exp(2 * params['x2'])                       # base_models.py:903-904
         post1, post2 = self.prior_x1 + f1, self.prior_x2 + f2
@@ -692,9 +751,10 @@ class AepSGPLVM(object):
         mcav, vcav = c1 / c2, 1.0 / c2
         mpost, vpost = post1[idx] / post2[idx], 1.0 / post2[idx]
         m, v, psi1, psi2 = L.prop_mm(mcav, vcav)
-        logZ, dm, dv = gauss_log_Z(sn, m, v, yb, alpha)
+        gl = {}
+        logZ, dm, dv = lik_log_Z(self.lik, params, m, v, yb, alpha, scale, gl)
         g, gin = L.aep_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mcav, vcav, alpha)
-        g['sn'] = gauss_dsn(sn, m, dv, alpha, scale)
+        g.update(gl)
         # aep_models.py:785-801
         phi_prior, _, _ = _phi_x(self.prior_mean, self.prior_var)
         phi_prior *= N * self.Din
@@ -727,8 +787,8 @@ class AepSGPLVM(object):
 class VfeSGPLVM(object):
     """vfe_models.py:722-863."""
 
-    def __init__(self, y, Q, M, prior_mean=0, prior_var=1, nat_param=True):
-        self.y = y
+    def __init__(self, y, Q, M, prior_mean=0, prior_var=1, nat_param=True, lik='Gaussian'):
+        self.y, self.lik = y, lik
         self.N, self.Dout, self.Din, self.M = y.shape[0], y.shape[1], Q, M
         self.nat_param = nat_param
         self.layer = Layer(self.N, Q, self.Dout, M, nat_param)
@@ -747,7 +807,7 @@ class VfeSGPLVM(object):
         scale = -N * 1.0 / nb
         L = self.layer
         L.set_params(params)
-        sn = params['sn']
+        sn = params.get('sn')
         f1 = params['x1']
         f2 = np.exp(2 * params['x2'])
         if self.nat_param:
@@ -756,9 +816,10 @@ class VfeSGPLVM(object):
             post1, post2 = f1 / f2, 1.0 / f2
         mx, vx = post1[idx] / post2[idx], 1.0 / post2[idx]
         m, v, psi1, psi2 = L.prop_mm(mx, vx, cav=False)
-        ll, dm, dv = gauss_log_lik_exp(sn, m, v, yb)
+        gl = {}
+        ll, dm, dv = lik_log_lik_exp(self.lik, params, m, v, yb, scale, gl)
         g, gin = L.vfe_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mx, vx)
-        g['sn'] = gauss_dsn_log_lik_exp(sn, m, v, yb, scale)
+        g.update(gl)
         m0, v0 = self.prior_mean, self.prior_var            # vfe_models.py:857-863
         klx = np.sum(0.5 * (np.log(v0) - np.log(vx) + (vx + (mx - m0)**2) / v0 - 1))
         sx = N * 1.0 / nb

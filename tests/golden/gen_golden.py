@@ -93,21 +93,24 @@ def run(model, params, mb, alpha, seed=None):
     return e, g
 
 
-def case_sgpr(name, cls, N, M, D, Do, alpha, nat, mb=None, seed=0, xy=None):
+def case_sgpr(name, cls, N, M, D, Do, alpha, nat, mb=None, seed=0, xy=None, lk='Gaussian'):
     rng = np.random.RandomState(seed)
     if xy is None:
         x = rng.standard_normal((N, D))
         y = rng.standard_normal((N, Do))
     else:
         x, y = xy
+    if lk == 'Probit':       # binary labels, tests/test_grads_aep.py:138-146
+        y = 2.0 * (y > 0) - 1.0
     np.random.seed(seed)
-    model = cls(x, y, M, lik='Gaussian', nat_param=nat)
+    model = cls(x, y, M, lik=lk, nat_param=nat)
     params = perturb(quiet(model.init_hypers, y), rng)
-    params['sn'] = np.array(np.log(0.3) + 0.05 * rng.standard_normal())
+    if lk == 'Gaussian':
+        params['sn'] = np.array(np.log(0.3) + 0.05 * rng.standard_normal())
     mbs = N if mb is None else mb
     e, g = run(model, params, mbs, alpha, seed=123)
     extra = {}
-    if mb is None:
+    if mb is None and lk == 'Gaussian':
         xs = rng.standard_normal((7, D))
         model.update_hypers(params)
         model.updated = False
@@ -115,20 +118,27 @@ def case_sgpr(name, cls, N, M, D, Do, alpha, nat, mb=None, seed=0, xy=None):
         my, vy = model.predict_y(xs)
         extra = {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy}
     save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPR', N=N, M=M, D=D, Do=Do,
-                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123),
+                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123, lik=lk),
          {'x': x, 'y': y}, params, e, g, extra)
 
 
-def case_sdgpr(name, N, M, D, hidden, Do, alpha, mb=None, seed=1):
+def case_sdgpr(name, N, M, D, hidden, Do, alpha, mb=None, seed=1, lk='Gaussian'):
     rng = np.random.RandomState(seed)
     x = rng.standard_normal((N, D))
     y = rng.standard_normal((N, Do))
+    if lk == 'Probit':
+        y = 2.0 * (y > 0) - 1.0
     np.random.seed(seed)
-    model = aep.SDGPR(x, y, M, hidden, lik='Gaussian')
+    model = aep.SDGPR(x, y, M, hidden, lik=lk)
     params = perturb(quiet(model.init_hypers, y), rng)
-    params['sn'] = np.array(np.log(0.3))
+    if lk == 'Gaussian':
+        params['sn'] = np.array(np.log(0.3))
     mbs = N if mb is None else mb
     e, g = run(model, params, mbs, alpha, seed=123)
+    if lk == 'Probit':
+        save(name, dict(model='aep_models.SDGPR', N=N, M=M, D=D, hidden=hidden, Do=Do, alpha=alpha,
+                        mb_size=mbs, rng_seed=123, lik=lk), {'x': x, 'y': y}, params, e, g)
+        return
     xs = rng.standard_normal((6, D))
     model.update_hypers(params)
     model.updated = False
@@ -147,7 +157,8 @@ def lvm_params(model, y, rng):
     post_v = 0.1 * np.ones((N, Q))
     p = quiet(model.sgp_layer.init_hypers, post_m)
     p = perturb(p, rng)
-    p['sn'] = np.array(np.log(0.3))
+    if getattr(model, '_gold_lik', 'Gaussian') == 'Gaussian':
+        p['sn'] = np.array(np.log(0.3))
     if model.nat_param:
         post_2 = 1.0 / post_v
         p['x1'] = post_2 * post_m
@@ -158,16 +169,19 @@ def lvm_params(model, y, rng):
     return p
 
 
-def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2):
+def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2, lk='Gaussian'):
     rng = np.random.RandomState(seed)
     y = rng.standard_normal((N, Do))
+    if lk == 'Probit':       # tests/test_grads_aep.py:33-40
+        y = 2.0 * (y > 0) - 1.0
     np.random.seed(seed)
-    model = cls(y, Q, M, lik='Gaussian', nat_param=nat)
+    model = cls(y, Q, M, lik=lk, nat_param=nat)
+    model._gold_lik = lk
     params = lvm_params(model, y, rng)
     mbs = N if mb is None else mb
     e, g = run(model, params, mbs, alpha, seed=123)
     save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPLVM', N=N, M=M, Q=Q, Do=Do,
-                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123),
+                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123, lik=lk),
          {'y': y}, params, e, g)
 
 
@@ -270,7 +284,20 @@ def case_emis(seed=5):
     print('gauss_emis.npz written')
 
 
+def probit_cases():
+    # tests/test_grads_aep.py:33-40,138-146,246-256; tests/test_grads_vfe.py probit twins
+    case_sgpr('aep_sgpr_probit', aep.SGPR, 20, 10, 2, 3, 0.5, True, seed=50, lk='Probit')
+    case_sgpr('aep_sgpr_probit_alpha_one', aep.SGPR, 20, 10, 2, 3, 1.0, True, seed=51, lk='Probit')
+    case_sgpr('vfe_sgpr_probit', vfe.SGPR, 20, 10, 2, 3, 1.0, True, seed=52, lk='Probit')
+    case_sdgpr('aep_sdgpr_probit', 10, 5, 2, [3, 2], 2, 0.5, seed=53, lk='Probit')
+    case_sgplvm('aep_sgplvm_probit', aep.SGPLVM, 10, 5, 3, 2, 0.5, seed=54, lk='Probit')
+    case_sgplvm('vfe_sgplvm_probit', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=55, lk='Probit')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'probit':   # only the files added with the probit layer
+        probit_cases()
+        sys.exit(0)
     # tests/test_grads_aep.py:124-135 shape (alpha 0.5) + its alpha=1e-4 + non-natural params
     case_sgpr('aep_sgpr', aep.SGPR, 20, 10, 2, 3, 0.5, True)
     case_sgpr('aep_sgpr_alpha_small', aep.SGPR, 20, 10, 2, 3, 1e-4, True, seed=10)
@@ -302,5 +329,6 @@ if __name__ == '__main__':
     case_sgpssm('vfe_sgpssm_lin', vfe.SGPSSM, 20, 4, 2, 2, 1.0, seed=44)
     case_sgpssm('vfe_sgpssm_gp', vfe.SGPSSM, 10, 4, 2, 3, 1.0, gp_emi=True, seed=45)
     case_sgpssm('vfe_sgpssm_nonnat', vfe.SGPSSM, 12, 4, 2, 2, 1.0, nat=False, seed=46)
+    probit_cases()
     case_kernels()
     case_emis()

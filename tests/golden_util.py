@@ -64,16 +64,17 @@ def build_oracle_model(gold):
     m = gold['meta']
     i = gold['in']
     kind = m['model']
+    lk = m.get('lik', 'Gaussian')
     if kind == 'aep_models.SGPR':
-        return go.AepSGPR(i['x'], i['y'], m['M'], m['nat_param'])
+        return go.AepSGPR(i['x'], i['y'], m['M'], m['nat_param'], lik=lk)
     if kind == 'vfe_models.SGPR':
-        return go.VfeSGPR(i['x'], i['y'], m['M'], m['nat_param'])
+        return go.VfeSGPR(i['x'], i['y'], m['M'], m['nat_param'], lik=lk)
     if kind == 'aep_models.SDGPR':
-        return go.AepSDGPR(i['x'], i['y'], m['M'], m['hidden'])
+        return go.AepSDGPR(i['x'], i['y'], m['M'], m['hidden'], lik=lk)
     if kind == 'aep_models.SGPLVM':
-        return go.AepSGPLVM(i['y'], m['Q'], m['M'])
+        return go.AepSGPLVM(i['y'], m['Q'], m['M'], lik=lk)
     if kind == 'vfe_models.SGPLVM':
-        return go.VfeSGPLVM(i['y'], m['Q'], m['M'], nat_param=m['nat_param'])
+        return go.VfeSGPLVM(i['y'], m['Q'], m['M'], nat_param=m['nat_param'], lik=lk)
     if kind == 'aep_models.SGPSSM':
         return go.AepSGPSSM(i['y'], m['Q'], m['M'], x_control=i.get('x_control'), gp_emi=m['gp_emi'])
     if kind == 'vfe_models.SGPSSM':

@@ -13,16 +13,17 @@ def build_model(gold, prec='fp64', device=None):
     m, i = gold['meta'], gold['in']
     kind = m['model']
     kw = dict(prec=prec, device=device)
+    lk = m.get('lik', 'Gaussian')
     if kind == 'aep_models.SGPR':
-        return aep.SGPR(i['x'], i['y'], m['M'], nat_param=m['nat_param'], **kw)
+        return aep.SGPR(i['x'], i['y'], m['M'], lik=lk, nat_param=m['nat_param'], **kw)
     if kind == 'vfe_models.SGPR':
-        return vfe.SGPR(i['x'], i['y'], m['M'], nat_param=m['nat_param'], **kw)
+        return vfe.SGPR(i['x'], i['y'], m['M'], lik=lk, nat_param=m['nat_param'], **kw)
     if kind == 'aep_models.SDGPR':
-        return aep.SDGPR(i['x'], i['y'], m['M'], m['hidden'], **kw)
+        return aep.SDGPR(i['x'], i['y'], m['M'], m['hidden'], lik=lk, **kw)
     if kind == 'aep_models.SGPLVM':
-        return aep.SGPLVM(i['y'], m['Q'], m['M'], **kw)
+        return aep.SGPLVM(i['y'], m['Q'], m['M'], lik=lk, **kw)
     if kind == 'vfe_models.SGPLVM':
-        return vfe.SGPLVM(i['y'], m['Q'], m['M'], nat_param=m['nat_param'], **kw)
+        return vfe.SGPLVM(i['y'], m['Q'], m['M'], lik=lk, nat_param=m['nat_param'], **kw)
     if kind == 'aep_models.SGPSSM':
         return aep.SGPSSM(i['y'], m['Q'], m['M'], x_control=i.get('x_control'), gp_emi=m['gp_emi'], **kw)
     if kind == 'vfe_models.SGPSSM':

@@ -138,3 +138,22 @@ def check_gauss_emis(n, Do, Q):
         assert gu.rel_err(gi2[k], gi[k]) < 1e-11, k
     for k in ('C', 'R'):
         assert gu.rel_err(ge2[k], ge[k]) < 1e-11, k
+
+
+def check_probit_lik():
+    """probit_lik kernel (lik_layers.py:303-362, 418-436) against the oracle, alpha = 1 (closed
+    form), alpha != 1 (Gauss-Hermite) and the VFE expectation."""
+    from geepee_b200 import ops
+    rng = np.random.RandomState(5)
+    m, v = rng.standard_normal((60, 3)) * 1.5, rng.rand(60, 3) * 2 + 0.05
+    y = 2.0 * (rng.rand(60, 3) > 0.5) - 1.0
+    gx, gw = np.polynomial.hermite.hermgauss(10)
+    for alpha in (1.0, 0.5, 0.05):
+        dm, dv, o = ops.probit_lik(T(m), T(v), T(y), T(gx), T(gw), alpha, -1.7, 0)
+        lz, rdm, rdv = go.probit_log_Z(m, v, y, alpha)
+        assert abs(o[0].item() - lz) < 1e-12 * abs(lz), alpha
+        assert gu.rel_err(N(dm), -1.7 * rdm) < 1e-12 and gu.rel_err(N(dv), -1.7 * rdv) < 1e-12, alpha
+    dm, dv, o = ops.probit_lik(T(m), T(v), T(y), T(gx), T(gw), 1.0, 2.5, 1)
+    le, rdm, rdv = go.probit_log_lik_exp(m, v, y)
+    assert abs(o[0].item() - le) < 1e-11 * abs(le)
+    assert gu.rel_err(N(dm), 2.5 * rdm) < 1e-11 and gu.rel_err(N(dv), 2.5 * rdv) < 1e-11

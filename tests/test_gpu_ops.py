@@ -43,3 +43,7 @@ def test_kmat_psi_lik():
 @pytest.mark.parametrize('n,Do,Q', oc.EMIS_SHAPES)
 def test_gauss_emis(n, Do, Q):
     oc.check_gauss_emis(n, Do, Q)
+
+
+def test_probit_lik():
+    oc.check_probit_lik()
