@@ -86,6 +86,17 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
     return GPB_CHECK_LAUNCH();
 }
 
+int gpb_spd_inverse(const double* A, int batch, int M, double* Ainv, double* logdet, void* stream) {
+    if (!A || !Ainv || !logdet || batch < 1 || M < 1) return fail(GPB_ERR_ARG, "spd_inverse: bad argument");
+    if (M > 512) return fail(GPB_ERR_ARG, "spd_inverse: M=%d unsupported (max 512)", M);
+    auto kern = gpb::spd_inverse_kernel<32>;
+    const size_t smem = gpb::SpdInvCfg<32>::smem_bytes(M);
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    GPB_LAUNCH(kern, dim3(batch * gpb::kTailCluster), dim3(256), smem, stream, A, M, Ainv, logdet);
+    return GPB_CHECK_LAUNCH();
+}
+
 int gpb_probit_lik(const double* m, const double* v, const double* y, const double* gh_x,
                    const double* gh_w, int ngh, double alpha, double scale, long total, int mode,
                    double* dm, double* dv, double* out2, void* ws, size_t ws_bytes, void* stream) {

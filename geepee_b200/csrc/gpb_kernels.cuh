@@ -2270,6 +2270,151 @@ GPB_KERNEL void mm_final_kernel(const double* __restrict__ colsum /*[Do*M + M*Q]
     }
 }
 
+// =========================================================================
+// a3 / a4 / a10 building block: batched inverse + log-determinant of SPD M x M matrices
+// (Kuu, Kuu^-1 + theta_1, Kuu^-1 + beta theta_1: base_models.py:464,471,476, aep_models.py:68,78,91,
+// 525,533 -- np.linalg.inv / slogdet in the reference).  fp64 throughout.
+// One thread-block CLUSTER per matrix (kTailCluster CTAs, hardware cluster barrier); blocked
+// Gauss-Jordan without pivoting (valid for SPD), NB = 32:
+//   per block step k:   D = A_kk (Schur complement so far);  logdet += log det D
+//     every CTA:   invert D in shared memory (unblocked GJ), stage the row panel R = A[k,:]
+//     CTA r, its rows i not in k:   P_i = A_ik D^-1;  A_ij -= P_i R_j (j not in k);  A_ik = -P_i
+//     owner of the k rows:          A_kj = D^-1 R_j (j not in k);  A_kk = D^-1
+// The matrix stays in global memory (L2 resident: 0.5 MB at M = 256); a step reads the panel
+// once into shared memory and streams the CTA's row slice through an 8 x 8 register tile per
+// thread.  Two cluster barriers per step.  After M/NB steps the work matrix holds A^-1.
+template <int NB>
+struct SpdInvCfg {
+    static size_t smem_bytes(int M) {
+        const int rows = (M + kTailCluster - 1) / kTailCluster;
+        const int rows8 = (rows + 7) / 8 * 8;
+        return sizeof(double) * ((size_t)NB * (NB + 1) + (size_t)NB * M + (size_t)rows8 * NB + 64);
+    }
+};
+
+template <int NB>
+GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(256) spd_inverse_kernel(
+    const double* __restrict__ A, int M, double* __restrict__ W /* [batch, M, M]: out = A^-1 */,
+    double* __restrict__ logdet /* [batch] */) {
+    GPB_DYN_SMEM(smem);
+    const int tid = threadIdx.x;
+    const int rank = cluster_rank();
+    const int mat = blockIdx.x / kTailCluster;
+    const int rows_per = (M + kTailCluster - 1) / kTailCluster;
+    const int row_lo = rank * rows_per;
+    const int row_hi = (row_lo + rows_per) < M ? (row_lo + rows_per) : M;
+    const int nrows = row_hi > row_lo ? row_hi - row_lo : 0;
+    const int rows8 = (rows_per + 7) / 8 * 8;
+    double* D = (double*)smem;                 // [NB][NB+1]
+    double* R = D + NB * (NB + 1);             // [NB][M]   row panel (original values)
+    double* P = R + (size_t)NB * M;            // [rows8][NB]
+    double* s_ld = P + (size_t)rows8 * NB;     // [1]
+    const double* Am = A + (size_t)mat * M * M;
+    double* Wm = W + (size_t)mat * M * M;
+    // work copy of this CTA's rows
+    for (long i = tid; i < (long)nrows * M; i += kThreads) Wm[(long)row_lo * M + i] = Am[(long)row_lo * M + i];
+    if (tid == 0) s_ld[0] = 0.0;
+    cluster_sync();
+    for (int k0 = 0; k0 < M; k0 += NB) {
+        const int nb = (M - k0) < NB ? (M - k0) : NB;
+        // ---- warp 0: load + invert the diagonal block (one row per lane, warp barriers only);
+        //      warps 1..7: stage the row panel meanwhile ----
+        if (tid < 32) {
+            const int a = tid;
+            for (int b = 0; b < NB; b++)
+                D[a * (NB + 1) + b] = (a < nb && b < nb) ? Wm[(long)(k0 + a) * M + k0 + b] : (a == b ? 1.0 : 0.0);
+            sync_warp();
+            double ld = 0;
+            for (int j = 0; j < nb; j++) {
+                // D <- Gauss-Jordan step on pivot j:  row j scaled, column j eliminated elsewhere
+                const double piv = D[j * (NB + 1) + j];
+                const double ip = 1.0 / piv;
+                ld += log(piv);
+                const double aj = D[a * (NB + 1) + j];
+                double rowv[NB];
+                GPB_UNROLL
+                for (int b = 0; b < NB; b++) {
+                    const double jb = D[j * (NB + 1) + b];
+                    const double ab = D[a * (NB + 1) + b];
+                    rowv[b] = (a == j) ? jb * ip : ab - aj * ip * jb;
+                }
+                sync_warp();                       // everybody has read row j / column j
+                GPB_UNROLL
+                for (int b = 0; b < NB; b++) D[a * (NB + 1) + b] = rowv[b];
+                D[a * (NB + 1) + j] = (a == j) ? ip : -aj * ip;
+                sync_warp();
+            }
+            if (tid == 0) s_ld[0] += ld;
+        } else {
+            for (int i = tid - 32; i < nb * M; i += kThreads - 32) {
+                const int c = i / M, jj = i - c * M;
+                R[c * M + jj] = Wm[(long)(k0 + c) * M + jj];
+            }
+        }
+        sync_threads();
+        // ---- P = A[rows, k] D^-1 for this CTA's rows ----
+        for (int i = tid; i < rows8 * NB; i += kThreads) {
+            const int r = i / NB, c = i - r * NB;
+            const int row = row_lo + r;
+            double acc = 0;
+            if (r < nrows && c < nb && (row < k0 || row >= k0 + nb))
+                for (int b = 0; b < nb; b++) acc += Wm[(long)row * M + k0 + b] * D[b * (NB + 1) + c];
+            P[r * NB + c] = acc;
+        }
+        cluster_sync();            // every CTA holds R, D^-1, P: the k rows / k columns may now change
+        // ---- trailing update of this CTA's rows: 8 x 8 register tiles ----
+        const int tiles_c = (M + 7) / 8, tiles_r = rows8 / 8;
+        for (int t = tid; t < tiles_r * tiles_c; t += kThreads) {
+            const int tr = t / tiles_c, tc = t - tr * tiles_c;
+            const int r0 = tr * 8;           // rows r0..r0+7, columns tc + b * tiles_c (lane-contiguous)
+            double acc[8][8];
+            GPB_UNROLL
+            for (int a = 0; a < 8; a++)
+                GPB_UNROLL
+                for (int b = 0; b < 8; b++) acc[a][b] = 0;
+            for (int c = 0; c < nb; c++) {
+                double pv[8], rv[8];
+                GPB_UNROLL
+                for (int a = 0; a < 8; a++) pv[a] = P[(r0 + a) * NB + c];
+                GPB_UNROLL
+                for (int b = 0; b < 8; b++) rv[b] = (tc + b * tiles_c) < M ? R[c * M + tc + b * tiles_c] : 0.0;
+                GPB_UNROLL
+                for (int a = 0; a < 8; a++)
+                    GPB_UNROLL
+                    for (int b = 0; b < 8; b++) acc[a][b] += pv[a] * rv[b];
+            }
+            GPB_UNROLL
+            for (int a = 0; a < 8; a++) {
+                const int row = row_lo + r0 + a;
+                if (r0 + a >= nrows || (row >= k0 && row < k0 + nb)) continue;
+                GPB_UNROLL
+                for (int b = 0; b < 8; b++) {
+                    const int col = tc + b * tiles_c;
+                    if (col >= M) continue;
+                    if (col >= k0 && col < k0 + nb) Wm[(long)row * M + col] = -P[(r0 + a) * NB + (col - k0)];
+                    else Wm[(long)row * M + col] -= acc[a][b];
+                }
+            }
+        }
+        // ---- the k rows themselves: A_kj = D^-1 R_j, A_kk = D^-1.  Split by COLUMN slices over
+        //      the cluster (not by row ownership), so that no CTA is a straggler at the barrier ----
+        const int ncol = row_hi - row_lo;          // column slice of this CTA = its row range
+        for (int i = tid; i < nb * ncol; i += kThreads) {
+            const int a = i / ncol, j = row_lo + (i - a * ncol);
+            const int row = k0 + a;
+            double v;
+            if (j >= k0 && j < k0 + nb) v = D[a * (NB + 1) + (j - k0)];
+            else {
+                v = 0;
+                for (int c = 0; c < nb; c++) v += D[a * (NB + 1) + c] * R[c * M + j];
+            }
+            Wm[(long)row * M + j] = v;
+        }
+        cluster_sync();            // step complete everywhere before the next panel is staged
+    }
+    if (rank == 0 && tid == 0) logdet[mat] = s_ld[0];
+}
+
 // FMA-pipe peak microbenchmark (roofline denominator): 8 independent chains per thread
 template <typename T>
 GPB_KERNEL void fma_peak_kernel(long iters, double* __restrict__ sink) {

@@ -11,6 +11,7 @@
 #ifndef GPB_CPU_EMU
 // ============================ CUDA ========================================
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #define GPB_DEVICE __device__ __forceinline__
@@ -27,6 +28,15 @@
 namespace gpb {
 
 GPB_DEVICE void sync_threads() { __syncthreads(); }
+// thread-block cluster (sm_90+): hardware barrier over the CTAs of a cluster; global-memory
+// writes made before it are visible to the whole cluster after it
+#define GPB_CLUSTER(n) __cluster_dims__(n, 1, 1)
+constexpr int kTailCluster = 4;
+GPB_DEVICE void cluster_sync() {
+    __threadfence();
+    cooperative_groups::this_cluster().sync();
+}
+GPB_DEVICE int cluster_rank() { return (int)cooperative_groups::this_cluster().block_rank(); }
 GPB_DEVICE void sync_warp() { __syncwarp(); }
 GPB_DEVICE double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -111,6 +121,11 @@ void dmma_f64(double a, double b, double* d0, double* d1);  // one 8x8x4 MMA: re
 namespace gpb {
 
 static inline void sync_threads() { gpb_emu::barrier(); }
+// the emulator runs blocks one after another: cluster kernels are built with clusters of ONE block
+#define GPB_CLUSTER(n)
+constexpr int kTailCluster = 1;
+static inline void cluster_sync() { gpb_emu::barrier(); }
+static inline int cluster_rank() { return 0; }
 static inline void sync_warp() { (void)gpb_emu::shfl_xor_f64(0.0, 0); }   // warp rendezvous
 static inline double shfl_xor(double v, int m) { return gpb_emu::shfl_xor_f64(v, m); }
 static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f64((double)v, m); }

@@ -94,6 +94,19 @@ def gauss_lik(m, v, y, sn, alpha, scale, mode):
     return dm, dv, out2
 
 
+def spd_inverse(A):
+    """Inverse and log-determinant of a batch of SPD matrices [b,M,M] (or one [M,M]), fp64, with the
+    library's cluster Gauss-Jordan kernel (base_models.py:464,471,476; aep_models.py:68,78,91,525,533)."""
+    lib = _lib.get()
+    single = A.dim() == 2
+    Ab = _c(A.reshape(-1, A.shape[-1], A.shape[-1]))
+    b, M = Ab.shape[0], Ab.shape[-1]
+    inv = torch.empty_like(Ab)
+    ld = torch.empty(b, dtype=torch.float64, device=A.device)
+    _chk(lib.gpb_spd_inverse(_p(Ab), b, M, _p(inv), _p(ld), _stream(A)), 'spd_inverse')
+    return (inv[0], ld[0]) if single else (inv, ld)
+
+
 def probit_lik(m, v, y, gh_x, gh_w, alpha, scale, mode):
     """lik_layers.py:303-362 (mode 0) / 418-436 (mode 1).  Returns scaled dm, dv and a device
     tensor [sum of log terms, 0]."""

@@ -69,6 +69,11 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
                   double alpha, double scale, long total, int mode, double* dm, double* dv,
                   double* out2, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- a3 / a4 / a10: batched inverse + log-determinant of SPD matrices A[batch,M,M] (M <= 512), fp64.
+ *      Replaces np.linalg.inv / np.linalg.slogdet of base_models.py:464,471,476 and
+ *      aep_models.py:68,78,91,525,533.  One thread-block cluster per matrix, blocked Gauss-Jordan. */
+int gpb_spd_inverse(const double* A, int batch, int M, double* Ainv, double* logdet, void* stream);
+
 /* ---- (8f rank 1) Probit likelihood, y in {-1,+1}.  mode 0: lik_layers.py:303-362 Probit_Layer.compute_log_Z
  *      (alpha == 1: closed form; otherwise Gauss-Hermite quadrature with the nodes / weights of
  *      numpy.polynomial.hermite.hermgauss(ngh), ngh <= 64, passed in device arrays);

@@ -158,3 +158,25 @@ def check_probit_lik():
     le, rdm, rdv = go.probit_log_lik_exp(m, v, y)
     assert abs(o[0].item() - le) < 1e-10 * abs(le)
     assert gu.rel_err(N(dm), 2.5 * rdm) < 1e-9 and gu.rel_err(N(dv), 2.5 * rdv) < 1e-9
+
+
+def check_spd_inverse(M, batch):
+    """Cluster Gauss-Jordan inverse + log-determinant against numpy (SPD matrices with the
+    conditioning of a jittered kernel matrix)."""
+    from geepee_b200 import ops
+    rng = np.random.RandomState(M + 7 * batch)
+    A = np.empty((batch, M, M))
+    for b in range(batch):
+        z = rng.standard_normal((M, 3))
+        d2 = ((z[:, None, :] - z[None, :, :])**2).sum(-1)
+        A[b] = np.exp(-0.5 * d2) + 1e-5 * np.eye(M) + (0.1 * b) * np.eye(M)
+    inv, ld = ops.spd_inverse(T(A))
+    inv, ld = N(inv), N(ld)
+    for b in range(batch):
+        ref = np.linalg.inv(A[b])
+        # residual-based check (the inverse of an ill-conditioned matrix is itself uncertain)
+        res = np.abs(inv[b].dot(A[b]) - np.eye(M)).max()
+        assert res < 1e-6, (M, b, res)
+        assert gu.rel_err(inv[b], ref) < 1e-5, (M, b, gu.rel_err(inv[b], ref))
+        sref = np.linalg.slogdet(A[b])[1]
+        assert abs(ld[b] - sref) < 1e-8 * max(1.0, abs(sref)), (M, b, ld[b], sref)

@@ -38,3 +38,8 @@ def test_gauss_emis(n, Do, Q):
 
 def test_probit_lik():
     oc.check_probit_lik()
+
+
+@pytest.mark.parametrize('M,batch', [(5, 1), (32, 2), (50, 3), (77, 1)])
+def test_spd_inverse(M, batch):
+    oc.check_spd_inverse(M, batch)
