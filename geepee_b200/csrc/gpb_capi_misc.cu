@@ -93,7 +93,7 @@ int gpb_spd_inverse(const double* A, int batch, int M, double* Ainv, double* log
     const size_t smem = gpb::SpdInvCfg<32>::smem_bytes(M);
     int rc = allow_smem(kern, smem);
     if (rc) return rc;
-    GPB_LAUNCH(kern, dim3(batch * gpb::kTailCluster), dim3(256), smem, stream, A, M, Ainv, logdet);
+    GPB_LAUNCH(kern, dim3(batch * gpb::kTailCluster), dim3(512), smem, stream, A, M, Ainv, logdet);
     return GPB_CHECK_LAUNCH();
 }
 

@@ -2281,22 +2281,23 @@ GPB_KERNEL void mm_final_kernel(const double* __restrict__ colsum /*[Do*M + M*Q]
 //     CTA r, its rows i not in k:   P_i = A_ik D^-1;  A_ij -= P_i R_j (j not in k);  A_ik = -P_i
 //     owner of the k rows:          A_kj = D^-1 R_j (j not in k);  A_kk = D^-1
 // The matrix stays in global memory (L2 resident: 0.5 MB at M = 256); a step reads the panel
-// once into shared memory and streams the CTA's row slice through an 8 x 8 register tile per
-// thread.  Two cluster barriers per step.  After M/NB steps the work matrix holds A^-1.
+// once into shared memory and streams the CTA's row slice through an 8 x 4 register tile per
+// thread (512 threads).  Two cluster barriers per step.  After M/NB steps the work matrix holds A^-1.
 template <int NB>
 struct SpdInvCfg {
     static size_t smem_bytes(int M) {
         const int rows = (M + kTailCluster - 1) / kTailCluster;
         const int rows8 = (rows + 7) / 8 * 8;
-        return sizeof(double) * ((size_t)NB * (NB + 1) + (size_t)NB * M + (size_t)rows8 * NB + 64);
+        return sizeof(double) * (2 * (size_t)NB * (NB + 1) + (size_t)NB * M + (size_t)rows8 * NB + 64);
     }
 };
 
 template <int NB>
-GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(256) spd_inverse_kernel(
+GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(512) spd_inverse_kernel(
     const double* __restrict__ A, int M, double* __restrict__ W /* [batch, M, M]: out = A^-1 */,
     double* __restrict__ logdet /* [batch] */) {
     GPB_DYN_SMEM(smem);
+    constexpr int NT = 512, TC = 4;            // 16 warps per CTA: the kernel is latency bound
     const int tid = threadIdx.x;
     const int rank = cluster_rank();
     const int mat = blockIdx.x / kTailCluster;
@@ -2306,54 +2307,65 @@ GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(256) spd_inverse_ker
     const int nrows = row_hi > row_lo ? row_hi - row_lo : 0;
     const int rows8 = (rows_per + 7) / 8 * 8;
     double* D = (double*)smem;                 // [NB][NB+1]
-    double* R = D + NB * (NB + 1);             // [NB][M]   row panel (original values)
+    double* D2 = D + NB * (NB + 1);            // [NB][NB+1]  ping-pong twin of D
+    double* R = D2 + NB * (NB + 1);            // [NB][M]   row panel (original values)
     double* P = R + (size_t)NB * M;            // [rows8][NB]
     double* s_ld = P + (size_t)rows8 * NB;     // [1]
+    double* s_piv = s_ld + 8;                  // [NB]
     const double* Am = A + (size_t)mat * M * M;
     double* Wm = W + (size_t)mat * M * M;
     // work copy of this CTA's rows
-    for (long i = tid; i < (long)nrows * M; i += kThreads) Wm[(long)row_lo * M + i] = Am[(long)row_lo * M + i];
+    for (long i = tid; i < (long)nrows * M; i += NT) Wm[(long)row_lo * M + i] = Am[(long)row_lo * M + i];
     if (tid == 0) s_ld[0] = 0.0;
     cluster_sync();
     for (int k0 = 0; k0 < M; k0 += NB) {
         const int nb = (M - k0) < NB ? (M - k0) : NB;
         // ---- warp 0: load + invert the diagonal block (one row per lane, warp barriers only);
         //      warps 1..7: stage the row panel meanwhile ----
-        if (tid < 32) {
-            const int a = tid;
-            for (int b = 0; b < NB; b++)
-                D[a * (NB + 1) + b] = (a < nb && b < nb) ? Wm[(long)(k0 + a) * M + k0 + b] : (a == b ? 1.0 : 0.0);
-            sync_warp();
-            double ld = 0;
+        if (tid < 128) {
+            // Warps 0-3 invert the diagonal block: lane = row, warp = group of NB/4 columns;
+            // ping-pong between D and D2 (a Gauss-Jordan step reads the old block and writes the
+            // new one), one 128-thread named barrier per pivot.  The chain of M pivots is the
+            // serial part of the whole inversion, so the logs of the pivots are taken afterwards.
+            constexpr int CG = NB / 4;
+            const int a = tid & 31, cg0 = (tid >> 5) * CG;
+            double* Dc = D;
+            double* Dn = D2;
+            for (int b = cg0; b < cg0 + CG; b++)
+                Dc[a * (NB + 1) + b] = (a < nb && b < nb) ? Wm[(long)(k0 + a) * M + k0 + b] : (a == b ? 1.0 : 0.0);
+            sync_group<1, 128>();
             for (int j = 0; j < nb; j++) {
-                // D <- Gauss-Jordan step on pivot j:  row j scaled, column j eliminated elsewhere
-                const double piv = D[j * (NB + 1) + j];
+                const double piv = Dc[j * (NB + 1) + j];
                 const double ip = 1.0 / piv;
-                ld += log(piv);
-                const double aj = D[a * (NB + 1) + j];
-                double rowv[NB];
+                const double aj = Dc[a * (NB + 1) + j];
+                const double f = (a == j) ? 0.0 : aj * ip;
+                if (tid == j) s_piv[j] = piv;
                 GPB_UNROLL
-                for (int b = 0; b < NB; b++) {
-                    const double jb = D[j * (NB + 1) + b];
-                    const double ab = D[a * (NB + 1) + b];
-                    rowv[b] = (a == j) ? jb * ip : ab - aj * ip * jb;
+                for (int bb = 0; bb < CG; bb++) {
+                    const int b = cg0 + bb;
+                    const double jb = Dc[j * (NB + 1) + b];
+                    const double v = (a == j) ? jb * ip : Dc[a * (NB + 1) + b] - f * jb;
+                    Dn[a * (NB + 1) + b] = (b == j) ? ((a == j) ? ip : -aj * ip) : v;
                 }
-                sync_warp();                       // everybody has read row j / column j
-                GPB_UNROLL
-                for (int b = 0; b < NB; b++) D[a * (NB + 1) + b] = rowv[b];
-                D[a * (NB + 1) + j] = (a == j) ? ip : -aj * ip;
-                sync_warp();
+                sync_group<1, 128>();
+                double* t = Dc; Dc = Dn; Dn = t;
             }
-            if (tid == 0) s_ld[0] += ld;
+            if (Dc != D)                           // odd number of pivots: result sits in D2
+                for (int b = cg0; b < cg0 + CG; b++) D[a * (NB + 1) + b] = Dc[a * (NB + 1) + b];
+            if (tid < 32) {
+                double l = tid < nb ? log(s_piv[tid]) : 0.0;
+                l = warp_sum(l);
+                if (tid == 0) s_ld[0] += l;
+            }
         } else {
-            for (int i = tid - 32; i < nb * M; i += kThreads - 32) {
+            for (int i = tid - 128; i < nb * M; i += NT - 128) {
                 const int c = i / M, jj = i - c * M;
                 R[c * M + jj] = Wm[(long)(k0 + c) * M + jj];
             }
         }
         sync_threads();
         // ---- P = A[rows, k] D^-1 for this CTA's rows ----
-        for (int i = tid; i < rows8 * NB; i += kThreads) {
+        for (int i = tid; i < rows8 * NB; i += NT) {
             const int r = i / NB, c = i - r * NB;
             const int row = row_lo + r;
             double acc = 0;
@@ -2362,33 +2374,34 @@ GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(256) spd_inverse_ker
             P[r * NB + c] = acc;
         }
         cluster_sync();            // every CTA holds R, D^-1, P: the k rows / k columns may now change
-        // ---- trailing update of this CTA's rows: 8 x 8 register tiles ----
-        const int tiles_c = (M + 7) / 8, tiles_r = rows8 / 8;
-        for (int t = tid; t < tiles_r * tiles_c; t += kThreads) {
+        // ---- trailing update of this CTA's rows: 8 x 4 register tiles ----
+        const int tiles_c = (M + TC - 1) / TC, tiles_r = rows8 / 8;
+        for (int t = tid; t < tiles_r * tiles_c; t += NT) {
             const int tr = t / tiles_c, tc = t - tr * tiles_c;
             const int r0 = tr * 8;           // rows r0..r0+7, columns tc + b * tiles_c (lane-contiguous)
-            double acc[8][8];
+            double acc[8][TC];
             GPB_UNROLL
             for (int a = 0; a < 8; a++)
                 GPB_UNROLL
-                for (int b = 0; b < 8; b++) acc[a][b] = 0;
+                for (int b = 0; b < TC; b++) acc[a][b] = 0;
+            GPB_UNROLL_N(4)
             for (int c = 0; c < nb; c++) {
-                double pv[8], rv[8];
+                double pv[8], rv[TC];
                 GPB_UNROLL
                 for (int a = 0; a < 8; a++) pv[a] = P[(r0 + a) * NB + c];
                 GPB_UNROLL
-                for (int b = 0; b < 8; b++) rv[b] = (tc + b * tiles_c) < M ? R[c * M + tc + b * tiles_c] : 0.0;
+                for (int b = 0; b < TC; b++) rv[b] = (tc + b * tiles_c) < M ? R[c * M + tc + b * tiles_c] : 0.0;
                 GPB_UNROLL
                 for (int a = 0; a < 8; a++)
                     GPB_UNROLL
-                    for (int b = 0; b < 8; b++) acc[a][b] += pv[a] * rv[b];
+                    for (int b = 0; b < TC; b++) acc[a][b] += pv[a] * rv[b];
             }
             GPB_UNROLL
             for (int a = 0; a < 8; a++) {
                 const int row = row_lo + r0 + a;
                 if (r0 + a >= nrows || (row >= k0 && row < k0 + nb)) continue;
                 GPB_UNROLL
-                for (int b = 0; b < 8; b++) {
+                for (int b = 0; b < TC; b++) {
                     const int col = tc + b * tiles_c;
                     if (col >= M) continue;
                     if (col >= k0 && col < k0 + nb) Wm[(long)row * M + col] = -P[(r0 + a) * NB + (col - k0)];
@@ -2399,7 +2412,7 @@ GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(256) spd_inverse_ker
         // ---- the k rows themselves: A_kj = D^-1 R_j, A_kk = D^-1.  Split by COLUMN slices over
         //      the cluster (not by row ownership), so that no CTA is a straggler at the barrier ----
         const int ncol = row_hi - row_lo;          // column slice of this CTA = its row range
-        for (int i = tid; i < nb * ncol; i += kThreads) {
+        for (int i = tid; i < nb * ncol; i += NT) {
             const int a = i / ncol, j = row_lo + (i - a * ncol);
             const int row = k0 + a;
             double v;

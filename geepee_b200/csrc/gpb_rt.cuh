@@ -38,6 +38,9 @@ GPB_DEVICE void cluster_sync() {
 }
 GPB_DEVICE int cluster_rank() { return (int)cooperative_groups::this_cluster().block_rank(); }
 GPB_DEVICE void sync_warp() { __syncwarp(); }
+// named barrier over the first `nthreads` threads of the block (a multiple of 32; all of them call it)
+template <int ID, int NTHREADS>
+GPB_DEVICE void sync_group() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
 GPB_DEVICE double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GPB_DEVICE void atomic_add(double* p, double v) { atomicAdd(p, v); }
@@ -108,6 +111,7 @@ namespace gpb_emu {
 extern dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 extern unsigned char* dyn_smem;
 void barrier();                       // yield until every fiber of the block arrives
+void group_barrier(int nthreads);     // yield until the first `nthreads` fibers arrive
 double shfl_xor_f64(double v, int m);  // warp exchange through a mailbox
 double shfl_idx_f64(double v, int src); // read `v` of lane `src`
 void dmma_f64(double a, double b, double* d0, double* d1);  // one 8x8x4 MMA: returns A.B for this lane
@@ -127,6 +131,8 @@ constexpr int kTailCluster = 1;
 static inline void cluster_sync() { gpb_emu::barrier(); }
 static inline int cluster_rank() { return 0; }
 static inline void sync_warp() { (void)gpb_emu::shfl_xor_f64(0.0, 0); }   // warp rendezvous
+template <int ID, int NTHREADS>
+static inline void sync_group() { gpb_emu::group_barrier(NTHREADS); }
 static inline double shfl_xor(double v, int m) { return gpb_emu::shfl_xor_f64(v, m); }
 static inline float shfl_xor(float v, int m) { return (float)gpb_emu::shfl_xor_f64((double)v, m); }
 static inline void atomic_add(double* p, double v) { *p += v; }

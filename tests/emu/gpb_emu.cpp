@@ -21,7 +21,7 @@ namespace gpb_emu {
 dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 unsigned char* dyn_smem = nullptr;
 
-enum { READY = 0, AT_BARRIER = 1, AT_SHFL = 2, DONE = 3 };
+enum { READY = 0, AT_BARRIER = 1, AT_SHFL = 2, DONE = 3, AT_GROUP = 4 };
 struct Fiber {
     ucontext_t ctx;
     unsigned char* stack;
@@ -70,6 +70,12 @@ static void fiber_entry() {
 
 void barrier() {
     fibers[cur].state = AT_BARRIER;
+    swapcontext(&fibers[cur].ctx, &sched);
+}
+
+void group_barrier(int n) {
+    fibers[cur].state = AT_GROUP;
+    fibers[cur].mask = n;
     swapcontext(&fibers[cur].ctx, &sched);
 }
 
@@ -156,6 +162,21 @@ void run_block(void (*tramp)(void*), void* ctx) {
             for (int i = w0; i < w1; i++)
                 if (fibers[i].state == AT_SHFL) fibers[i].state = READY;
             progressed = true;
+        }
+        // named barrier over the first n threads
+        {
+            int n = 0;
+            for (int i = 0; i < nthreads; i++)
+                if (fibers[i].state == AT_GROUP) { n = fibers[i].mask; break; }
+            if (n > 0) {
+                bool ok = true;
+                for (int i = 0; i < n && i < nthreads; i++)
+                    if (fibers[i].state != AT_GROUP) ok = false;
+                if (ok) {
+                    for (int i = 0; i < n && i < nthreads; i++) fibers[i].state = READY;
+                    progressed = true;
+                }
+            }
         }
         // block barrier
         bool all = true, any = false, alldone = true;
