@@ -35,5 +35,9 @@ ls2 = torch.full((Q,), 0.3, dtype=torch.float64, device=dev)
 for _ in range(2):
     mo, vo, va, p1 = ops.mm_fwd(prec, mx, vx, z2, ls2, sf, A, B)
     ops.mm_bwd(prec, mx, vx, z2, ls2, sf, A, B, dm, dv, mo, va, p1)
+from geepee_b200 import layers
+Kuu = ops.kmat(z, z, ls, sf, 1e-5)
+for _ in range(2):
+    layers.spd_inverse(torch.stack([Kuu, Kuu + 0.1 * torch.eye(M, dtype=torch.float64, device=dev)]))
 torch.cuda.synchronize()
 print('ok')
