@@ -434,6 +434,14 @@ def run_gpu(args, w):
         slot = 'det_fwd'
         kname = ('det_fwd_mma_kernel<MP> (Kfu generation fused with Kfu.B on the FP64 tensor cores, DMMA.8x8x4)'
                  if pr == ops.F64 else 'det_fwd_kernel<float,MP> (Kfu generation fused with Kfu.B, SIMT)')
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of
+    # this same command (profiles/traffic.json: {"<workload>/<prec>": {"kernel", "bytes_per_launch", "source"}})
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f).get('%s/%s' % (args.workload, args.prec), {}).get('bytes_per_launch')
+    except Exception:  # noqa: BLE001
+        traffic = None
     k_ms, k_cnt = prof[slot]
     k_ms_step = k_ms / args.steps
     achieved = fl / (k_ms_step * 1e-3) / 1e12 if k_ms_step > 0 else 0.0
@@ -452,7 +460,7 @@ def run_gpu(args, w):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'fp64_fma_pipe' if pr == ops.F64 else 'fp32_fma_pipe', 'kernel': kname,
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tf if peak_tf > 0 else None, 'traffic': None,
+                     'frac': achieved / peak_tf if peak_tf > 0 else None, 'traffic': traffic,
                      'peak_source': 'gpb_fma_peak microbenchmark measured in this run (MEASURED_PEAKS.json has '
                                     'no FP64/FP32 FMA figure)',
                      'kernel_ms_per_step': k_ms_step, 'kernel_launches_per_step': k_cnt / max(args.steps, 1),

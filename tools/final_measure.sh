@@ -19,6 +19,3 @@ for f in sorted(glob.glob("gpurun_out/bench_${TAG}_*.json")):
         print(f, "failed", e)
 PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1300 --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/bench_ncu_${TAG}.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"det_fwd|det_bwd|det_syrk_mma|mm_pairs|mm_psi1|mm_rows|mm_cols|spd_inverse" -c 24 -f -o gpurun_out/prof_all_${TAG} python tools/ncu_target.py fp64 65536 > gpurun_out/ncu_all_${TAG}.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:mm_pairs_kernel -s 14 -c 2 -f -o gpurun_out/prof_bench_pairs_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_bench_pairs_${TAG}.log 2>&1
-tail -2 gpurun_out/ncu_bench_pairs_${TAG}.log
