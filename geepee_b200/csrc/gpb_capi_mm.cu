@@ -255,6 +255,39 @@ int mm_rows_bwd_dispatch(const MMPlan& p, const double* mx, const double* vx, co
 #undef GPB_CALL
 }
 
+// wide-output forward (Do > 4): row-owner kernel, one launch
+template <typename T, int QT, int DOW>
+int mm_fwd_wide_launch(const MMPlan& p, gpb::MMArgs<T> a, int n, void* stream) {
+    typedef gpb::MMWideCfg<T, QT, DOW> C;
+    auto kern = gpb::mm_fwd_wide_kernel<T, QT, DOW>;
+    int rc = allow_smem(kern, C::smem_bytes + 1024);
+    if (rc) return rc;
+    const int nchunks = (int)cdiv(p.P, C::PCW);
+    int nsplit = (int)((long)6 * sm_count() / nchunks);
+    if (nsplit < 1) nsplit = 1;
+    long rps = cdiv(n, nsplit);
+    rps = cdiv(rps, 256) * 256;
+    a.rows_per_split = (int)rps;
+    nsplit = (int)cdiv(n, rps);
+    prof_begin(3, stream);
+    GPB_LAUNCH(kern, dim3(nchunks, nsplit), dim3(256), C::smem_bytes, stream, a);
+    prof_end(3, stream);
+    return GPB_CHECK_LAUNCH();
+}
+template <typename T, int QT>
+int mm_fwd_wide_dow(const MMPlan& p, const gpb::MMArgs<T>& a, int n, int Do, void* stream) {
+    if (Do <= 8) return mm_fwd_wide_launch<T, QT, 8>(p, a, n, stream);
+    if (Do <= 16) return mm_fwd_wide_launch<T, QT, 16>(p, a, n, stream);
+    if (Do <= 32) return mm_fwd_wide_launch<T, QT, 32>(p, a, n, stream);
+    return mm_fwd_wide_launch<T, QT, 64>(p, a, n, stream);
+}
+template <typename T>
+int mm_fwd_wide_dispatch(const MMPlan& p, const gpb::MMArgs<T>& a, int n, int Do, void* stream) {
+#define GPB_CALL(QT) mm_fwd_wide_dow<T, QT>(p, a, n, Do, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
+
 template <typename T>
 int mm_check(int n, int M, int Q, int Do) {
     if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
@@ -282,10 +315,16 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
     a.mx = mx; a.vx = vx; a.ls = ls; a.zh = w.zh; a.ep = w.ep; a.bs = w.bs; a.dv = nullptr;
     a.n = n; a.Qa = Q; a.Do = Do; a.PP = p.PP; a.rows_per_split = p.rows_per_split;
     a.rowacc = w.rowacc; a.pairpart = nullptr; a.full_coef = 0; a.lam_pass = 0;
-    for (int pass = 0; pass < p.npass; pass++) {
-        a.d0 = pass * p.DOC;
-        rc = mm_pairs_dispatch<T, false>(p, a, stream);
+    if (Do > 4) {      // wide layers: row-owner kernel (psi2 evaluated once per row and pair)
+        a.d0 = 0;
+        rc = mm_fwd_wide_dispatch<T>(p, a, n, Do, stream);
         if (rc) return rc;
+    } else {
+        for (int pass = 0; pass < p.npass; pass++) {
+            a.d0 = pass * p.DOC;
+            rc = mm_pairs_dispatch<T, false>(p, a, stream);
+            if (rc) return rc;
+        }
     }
     rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;

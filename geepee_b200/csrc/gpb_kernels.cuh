@@ -1851,6 +1851,101 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     }
 }
 
+// Forward contraction for WIDE output layers (Do > 4, e.g. SGPLVM with Do = 50), roles swapped:
+// a thread owns a ROW (its Do partial sums live in registers, no cross-lane reduction at all) and
+// the CTA's chunk of PCW pairs -- zh, zh^2 and the Do weights of every pair -- is staged once in
+// shared memory and broadcast.  psi2' is evaluated once per (row, pair) instead of once per
+// 4-output pass of the pair-owner kernel (13 passes at Do = 50).
+//   rowacc[n,d] += sum_{p in chunk} bs[d,p] psi2'[n,p]        (aep_models.py:196-198)
+template <typename T, int Q, int DOW>
+struct MMWideCfg {
+    static constexpr int PCW = sizeof(T) == 8 ? (DOW >= 64 ? 192 : 256) : 256;   // pairs per CTA
+    static constexpr int REC = 2 * Q + DOW;                                        // per-pair record
+    static constexpr size_t smem_bytes = sizeof(double) * ExpDom<T>::TAB + sizeof(T) * (size_t)PCW * REC;
+};
+
+template <typename T, int Q, int DOW>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_fwd_wide_kernel(MMArgs<T> a) {
+    typedef MMWideCfg<T, Q, DOW> C;
+    constexpr int PCW = C::PCW, REC = C::REC;
+    constexpr double kS = ExpDom<T>::S;
+    constexpr int kTab = ExpDom<T>::TAB;
+    GPB_DYN_SMEM(dsm);
+    double* s_tab = (double*)dsm;
+    T* s_pair = (T*)(dsm + kTab * sizeof(double));          // [PCW][REC]: zh[Q] | zh2[Q] | bs[DOW]
+    GPB_SHARED double s_l2[Q];
+    const int tid = threadIdx.x, lane16 = tid & 15;
+    const long pbase = (long)blockIdx.x * PCW;
+    const long PP = a.PP;
+    const int Do = a.Do;
+    if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+    if (kTab > 0)
+        for (int i = tid; i < kTab; i += kThreads)
+            s_tab[i] = exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
+    for (int i = tid; i < PCW * REC; i += kThreads) {
+        const int p = i / REC, k = i - p * REC;
+        const long pg = pbase + p;
+        T v = 0;
+        if (pg < PP) {
+            if (k < Q) v = a.zh[(long)k * PP + pg];
+            else if (k < 2 * Q) { const T z = a.zh[(long)(k - Q) * PP + pg]; v = z * z; }
+            else if (k - 2 * Q < Do) v = a.bs[(long)(k - 2 * Q) * PP + pg];
+        }
+        s_pair[i] = v;
+    }
+    sync_threads();
+    const int r_begin = blockIdx.y * a.rows_per_split;
+    const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
+    for (int row = r_begin + tid; row < r_end; row += kThreads) {
+        // row constants of the expanded exponent: xs = a0 + sum_q (b_q zh_q + c_q zh_q^2)
+        T b[Q], c[Q];
+        double lcn = 0, a0d = 0;
+        GPB_UNROLL
+        for (int q = 0; q < Q; q++) {
+            double mu = 0, c2 = 0;
+            if (q < a.Qa) {
+                mu = a.mx[(long)row * a.Qa + q];
+                const double lq = s_l2[q];
+                c2 = 1.0 / (2.0 * a.vx[(long)row * a.Qa + q] + lq);
+                lcn += 0.5 * log(lq * c2);
+            }
+            const double c2s = c2 * kS;
+            b[q] = (T)(2.0 * c2s * mu);
+            c[q] = (T)(-c2s);
+            a0d -= c2s * mu * mu;
+        }
+        const T a0 = (T)(lcn * kS + a0d);
+        T acc[DOW];
+        GPB_UNROLL
+        for (int d = 0; d < DOW; d++) acc[d] = 0;
+        GPB_UNROLL_N(1)
+        for (int p = 0; p < PCW; p += 2) {
+            T x[2];
+            GPB_UNROLL
+            for (int u = 0; u < 2; u++) {
+                const T* rec = s_pair + (p + u) * REC;
+                T xx = a0;
+                GPB_UNROLL
+                for (int q = 0; q < Q; q++) {
+                    xx += b[q] * rec[q];
+                    xx += c[q] * rec[Q + q];
+                }
+                x[u] = xx;
+            }
+            exp_dom_n<2>(x, s_tab, lane16);
+            GPB_UNROLL
+            for (int u = 0; u < 2; u++) {
+                const T* rec = s_pair + (p + u) * REC + 2 * Q;
+                GPB_UNROLL
+                for (int d = 0; d < DOW; d++) acc[d] += rec[d] * x[u];
+            }
+        }
+        GPB_UNROLL
+        for (int d = 0; d < DOW; d++)
+            if (d < Do) atomic_add(a.rowacc + (long)row * Do + d, (double)acc[d]);
+    }
+}
+
 // psi1 forward + moment matching epilogue (kernels.py:214-218,233; aep_models.py:195-198):
 //   psi1[n,m] = sf2 prod_q sqrt(l_q^2 c1_nq) exp(-1/2 sum_q (mu_nq - z_mq)^2 c1_nq),  c1 = 1/(S + l^2)
 //   mout[n,d] = sum_m A[d,m] psi1[n,m] ;  vout[n,d] = sf2 + vacc[n,d] - mout^2
