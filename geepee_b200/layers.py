@@ -131,6 +131,8 @@ class Base_SGP_Layer(object):
     def __getattr__(self, name):
         if name in _EXPORTED:
             t = self.__dict__.get('_t', {})
+            if name in self._B_SRC and self._B_SRC[name] in t:
+                return self._B(name).detach().cpu().numpy()
             if name in t:
                 return t[name].detach().cpu().numpy()
         raise AttributeError(name)
@@ -197,8 +199,10 @@ class Base_SGP_Layer(object):
             t['mu'] = t['theta_2']
         t['Splusmm'] = t['Su'] + outer(t['mu'], t['mu'])
         t['A'] = torch.matmul(t['mu'], Ki)
-        t['B_sto'] = torch.matmul(Ki, torch.matmul(t['Splusmm'], Ki)) - Ki
-        t['B_det'] = torch.matmul(Ki, torch.matmul(t['Su'], Ki)) - Ki
+        # B_sto = Ki Splusmm Ki - Ki and B_det = Ki Su Ki - Ki are formed on first use (_B): a layer
+        # is fed either deterministic or uncertain inputs, never both in one objective call
+        t.pop('B_sto', None)
+        t.pop('B_det', None)
         self._opnd.pop('post', None)
 
     def get_hypers(self, key_suffix=''):
@@ -270,8 +274,18 @@ class Base_SGP_Layer(object):
     def _AB(self, cav, stochastic):
         t = self._t
         if cav:
-            return t['Ahat'], (t['Bhat_sto'] if stochastic else t['Bhat_det'])
-        return t['A'], (t['B_sto'] if stochastic else t['B_det'])
+            return t['Ahat'], self._B('Bhat_sto' if stochastic else 'Bhat_det')
+        return t['A'], self._B('B_sto' if stochastic else 'B_det')
+
+    _B_SRC = {'B_sto': 'Splusmm', 'B_det': 'Su', 'Bhat_sto': 'Splusmmhat', 'Bhat_det': 'Suhat'}
+
+    def _B(self, name):
+        """base_models.py:485-488 / aep_models.py:541-546, lazily: Ki S Ki - Ki."""
+        t = self._t
+        if name not in t:
+            Ki = t['Kuuinv']
+            t[name] = torch.matmul(Ki, torch.matmul(t[self._B_SRC[name]], Ki)) - Ki
+        return t[name]
 
     def _det_operands(self, cav):
         key = 'cav' if cav else 'post'
@@ -405,8 +419,8 @@ class AEP_SGP_Layer(Base_SGP_Layer):
             t['logdet_Suhat'] = -ld
         t['Ahat'] = torch.matmul(t['muhat'], Ki)
         t['Splusmmhat'] = t['Suhat'] + outer(t['muhat'], t['muhat'])
-        t['Bhat_sto'] = torch.matmul(Ki, torch.matmul(t['Splusmmhat'], Ki)) - Ki
-        t['Bhat_det'] = torch.matmul(Ki, torch.matmul(t['Suhat'], Ki)) - Ki
+        t.pop('Bhat_sto', None)      # formed on first use (_B)
+        t.pop('Bhat_det', None)
         self._opnd.pop('cav', None)
 
     def _phi(self, alpha):
