@@ -122,3 +122,59 @@ def test_linearity_in_rows_large():
     a, b = stats(0, 70001), stats(70001, n)
     for f, p, q in zip(full, a, b):
         assert gu.rel_err((p + q).cpu().numpy(), f.cpu().numpy()) < 1e-10
+
+
+def test_sgplvm_wide_medium_vs_oracle():
+    """SGPLVM with a wide output layer (Do = 20 -> the row-owner forward and the 32-dims-per-pass
+    backward), several pair chunks and row splits, against the oracle."""
+    import geepee_oracle as go
+    import bench
+    from geepee_b200 import aep_models as aep
+    w = dict(model='SGPLVM', N=600, Q=3, Do=20, M=40, alpha=0.5, seed=2)
+    X, Y = bench.make_data(w)
+    p = bench.make_params(None, Y, w, X)
+    p['ls'] = 0.3 * np.ones(w['Q'])
+    _oracle_vs_gpu(lambda: go.AepSGPLVM(Y, w['Q'], w['M']), lambda: aep.SGPLVM(Y, w['Q'], w['M']),
+                   p, w['N'], w['alpha'], TOL64)
+
+
+def test_sgpssm_medium_vs_oracle():
+    """SGPSSM with the fused emission kernel and the Q = 4 pair kernels (4 pairs per thread)."""
+    import geepee_oracle as go
+    import bench
+    from geepee_b200 import aep_models as aep
+    w = dict(model='SGPSSM', N=500, Q=4, Do=4, M=30, alpha=0.5, seed=4)
+    X, Y = bench.make_data(w)
+    p = bench.make_params(None, Y, w, X)
+    _oracle_vs_gpu(lambda: go.AepSGPSSM(Y, w['Q'], w['M']), lambda: aep.SGPSSM(Y, w['Q'], w['M']),
+                   p, w['N'], w['alpha'], TOL64)
+
+
+def test_pair_kernels_additive_in_rows_large():
+    """Size-independent property of the moment-matched layer at a large shape (n = 100 000, M = 128):
+    the statistics of a batch equal the sum over two row blocks."""
+    from geepee_b200 import ops
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(1)
+    n, M, Q, Do = 100000, 128, 3, 2
+    mx = torch.randn(n, Q, generator=g, dtype=torch.float64).to(dev)
+    vx = (0.05 + torch.rand(n, Q, generator=g, dtype=torch.float64)).to(dev)
+    z = torch.randn(M, Q, generator=g, dtype=torch.float64).to(dev)
+    ls = torch.full((Q,), 0.2, dtype=torch.float64, device=dev)
+    sf = torch.zeros(1, dtype=torch.float64, device=dev)
+    A = torch.randn(Do, M, generator=g, dtype=torch.float64).to(dev)
+    B = (0.01 * torch.randn(Do, M, M, generator=g, dtype=torch.float64)).to(dev).contiguous()
+    dm = torch.randn(n, Do, generator=g, dtype=torch.float64).to(dev)
+    dv = torch.randn(n, Do, generator=g, dtype=torch.float64).to(dev)
+
+    def stats(lo, hi):
+        a, b, c, d = (t[lo:hi].contiguous() for t in (mx, vx, dm, dv))
+        mo, vo, va, p1 = ops.mm_fwd(ops.F64, a, b, z, ls, sf, A, B)
+        o = ops.mm_bwd(ops.F64, a, b, z, ls, sf, A, B, c, d, mo, va, p1)
+        return [o['dA'], o['dB'], o['dzu'], o['dl'], o['dsf2'], o['dvsum'], mo.sum(0), vo.sum(0),
+                o['dmx'].sum(0), o['dvx'].sum(0)]
+
+    full = stats(0, n)
+    a, b = stats(0, 33333), stats(33333, n)
+    for f, p, q in zip(full, a, b):
+        assert gu.rel_err((p + q).cpu().numpy(), f.cpu().numpy()) < 1e-9
