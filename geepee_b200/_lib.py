@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libgeepee_b200.so')
+# GPB_LIB_PATH: another build of the same CUDA library (development A/B variants, build.py)
+LIB_PATH = os.environ.get('GPB_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libgeepee_b200.so')
 
 _lib = None
 _device_type = 'cuda'

@@ -1,7 +1,7 @@
 """AEP (black-box alpha / approximate EP) models on the B200 hot path.
 
 Reference: geepee/aep_models.py -- SGPR 589-667, SGPLVM 670-867, SDGPR 870-988,
-SGPSSM 991-1437.  Same constructors, same ``objective_function(params, mb_size, alpha,
+SGPSSM 991-1437, SDGPR_H 1440-1864.  Same constructors, same ``objective_function(params, mb_size, alpha,
 prop_mode) -> (energy, grads)`` with the same dict keys and shapes.
 
 Every objective has the same three-phase shape:
@@ -170,6 +170,152 @@ class SDGPR(Base_SDGPR):
             energy = energy + phis[i]
         if self.lik_layer.has_sn:
             grads['sn'] = top['dsn'].reshape(())
+        return self._finish(energy, grads)
+
+
+class SDGPR_H(Base_SDGPR):
+    """aep_models.py:1440-1864: deep GP regression with inference for the hidden variables -- one
+    Gaussian factor per training row and hidden unit (`h_factor_1/2_<i>[N, size[i+1]]`, tied
+    twice: posterior = 2 x factor, cavity = (2 - alpha) x factor) and a transition noise
+    `sn_hidden[i]` per hidden layer.
+
+    The hidden variables decouple the layers: layer i propagates the cavity of hidden layer i-1
+    (the inputs for i = 0) and is matched against the cavity of hidden layer i
+    (compute_transition_tilted, 1710-1745), so every layer's forward + backward pair runs back to
+    back on this rank's rows and only the additive statistics meet in the all-reduce.  Full batch
+    only, like the reference (compute_grads_hidden, 1621-1653, combines the [N, D] factors with
+    batch-sized gradients)."""
+
+    def __init__(self, x_train, y_train, no_pseudos, hidden_sizes, lik='Gaussian',
+                 prec=None, device=None):
+        super(SDGPR_H, self).__init__(x_train, y_train, no_pseudos, hidden_sizes, lik, prec, device)
+        self.sgp_layers = [SGP_Layer(self.N, self.size[i], self.size[i + 1], self.Ms[i], True,
+                                     prec, self.device) for i in range(self.L)]
+        self.sn = np.zeros(self.L - 1)
+        self.h_factor_1 = [np.zeros((self.N, self.size[i + 1])) for i in range(self.L - 1)]
+        self.h_factor_2 = [np.zeros((self.N, self.size[i + 1])) for i in range(self.L - 1)]
+
+    # ---- parameters (aep_models.py:1808-1864) -------------------------------------------------
+    def init_hypers(self, y_train):
+        init_params = super(SDGPR_H, self).init_hypers(y_train)
+        init_params['sn_hidden'] = np.log(0.001) * np.ones(self.L - 1)
+        for i in range(self.L - 1):
+            init_params['h_factor_1_%d' % i] = np.zeros((self.N, self.size[i + 1]))
+            init_params['h_factor_2_%d' % i] = np.log(0.01) * np.ones((self.N, self.size[i + 1]))
+        return init_params
+
+    def get_hypers(self):
+        params = super(SDGPR_H, self).get_hypers()
+        params['sn_hidden'] = self.sn
+        for i in range(self.L - 1):
+            params['h_factor_1_%d' % i] = self.h_factor_1[i]
+            params['h_factor_2_%d' % i] = np.log(self.h_factor_2[i]) / 2
+        return params
+
+    def update_hypers(self, params, _dev=None):
+        dev = pack_to_device(params, self.device) if _dev is None else _dev
+        for i, layer in enumerate(self.sgp_layers):
+            layer.update_hypers(params, key_suffix='_%d' % i, _dev=dev)
+        self.lik_layer.update_hypers(params, _dev=dev)
+        self.sn = params['sn_hidden']
+        for i in range(self.L - 1):
+            self.h_factor_1[i] = params['h_factor_1_%d' % i]
+            self.h_factor_2[i] = np.exp(2 * np.asarray(params['h_factor_2_%d' % i]))
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        _check_mode(prop_mode)
+        N, dev, Ln = self.N, self.device, self.L
+        if mb_size < N:
+            raise NotImplementedError('SDGPR_H: full batches only (the reference combines the [N, D] '
+                                      'hidden factors with batch-sized gradients, aep_models.py:1621-1653)')
+        lo, hi = dist.shard(N)
+        xb, yb = self._x[lo:hi], self._y[lo:hi]
+        scale = -1.0 / alpha                     # scale_logZ = -N / batch_size / alpha, full batch
+        s_post, s_cav = -(1.0 - 1.0 / alpha), -1.0 / alpha
+        for layer in self.sgp_layers:
+            layer._fuse_cavity_alpha = alpha
+        pdev = pack_to_device(params, dev)
+        self.update_hypers(params, _dev=pdev)
+        for layer in self.sgp_layers:
+            layer.compute_cavity(alpha)
+        sn2 = torch.exp(2.0 * pdev['sn_hidden'].reshape(-1))
+        # cavity of the hidden variables of this rank's rows (compute_cavity_h, 1747-1767)
+        h1 = [pdev['h_factor_1_%d' % i].reshape(N, -1)[lo:hi] for i in range(Ln - 1)]
+        h2 = [torch.exp(2.0 * pdev['h_factor_2_%d' % i].reshape(N, -1)[lo:hi]) for i in range(Ln - 1)]
+        c1 = [a * (2.0 - alpha) for a in h1]
+        c2 = [a * (2.0 - alpha) for a in h2]
+        cm = [(a / b).contiguous() for a, b in zip(c1, c2)]
+        cv = [(1.0 / b).contiguous() for b in c2]
+        add = {'logZ': _zeros(dev, 1), 'dsn_hidden': _zeros(dev, Ln - 1), 'dsn': _zeros(dev, 1),
+               'phi_h': _zeros(dev, 1)}
+        dmc, dvc = [], []
+        has_rows = hi > lo
+        for i, layer in enumerate(self.sgp_layers):
+            if not has_rows:
+                _add_stats(add, 's%d_' % i, _zero_stats(layer))
+                continue
+            if i == 0:
+                mp, vp, ctx = layer._fwd_det(xb, cav=True, save=True)
+            else:
+                mp, vp, ctx = layer._fwd_mm(cm[i - 1], cv[i - 1], cav=True)
+            if i < Ln - 1:
+                # compute_transition_tilted (1710-1745) against the cavity of hidden layer i
+                vsum = cv[i] + vp + sn2[i] / alpha
+                md = cm[i] - mp
+                lz = (-0.5 * md**2 / vsum - 0.5 * torch.log(2 * np.pi * vsum)).sum() \
+                    + (hi - lo) * self.size[i + 1] * (0.5 * (1 - alpha) * torch.log(2 * np.pi * sn2[i])
+                                                      - 0.5 * np.log(alpha))
+                dvt = scale * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+                dmt = scale * (-md / vsum)
+                add['logZ'] = add['logZ'] + scale * lz
+                add['dsn_hidden'][i] = dvt.sum() * 2 * sn2[i] / alpha \
+                    + scale * (hi - lo) * self.size[i + 1] * (1 - alpha)
+                dmp, dvp = (-dmt).contiguous(), dvt.contiguous()
+            else:
+                dmp, dvp, lzl, dsn = self.lik_layer._log_Z(mp, vp, yb, alpha, scale)
+                add['logZ'] = add['logZ'] + scale * lzl
+                add['dsn'] = dsn.reshape(1)
+            if i == 0:
+                st = layer._bwd_det(ctx, dmp, dvp)
+            else:
+                st = layer._bwd_mm(ctx, dmp, dvp)
+                dmc[i - 1] = dmc[i - 1] + st['dmx']
+                dvc[i - 1] = dvc[i - 1] + st['dvx']
+            _add_stats(add, 's%d_' % i, st)
+            if i < Ln - 1:
+                dmc.append(dmt)
+                dvc.append(dvt)
+        # compute_grads_hidden (1621-1653) + compute_phi_{cavity,posterior}_h (1655-1690), this
+        # rank's rows; the [N, D] gradients are assembled by the same all-reduce
+        for i in range(Ln - 1):
+            g1 = _zeros(dev, N, self.size[i + 1])
+            g2 = _zeros(dev, N, self.size[i + 1])
+            if has_rows:
+                p1, p2 = 2.0 * h1[i], 2.0 * h2[i]
+                d1 = (2 - alpha) * (dmc[i] / c2[i]) + s_cav * (2 - alpha) * (c1[i] / c2[i]) \
+                    + s_post * 2 * (p1 / p2)
+                d2 = (2 - alpha) * (-dmc[i] * c1[i] / c2[i]**2 - dvc[i] / c2[i]**2) \
+                    + s_cav * (2 - alpha) * (-0.5 * c1[i]**2 / c2[i]**2 - 0.5 / c2[i]) \
+                    + s_post * (-p1**2 / p2**2 - 1 / p2)
+                g1[lo:hi] = d1
+                g2[lo:hi] = 2 * d2 * h2[i]
+                add['phi_h'] = add['phi_h'] + s_cav * (0.5 * (c1[i]**2 / c2[i] - torch.log(c2[i]))).sum() \
+                    + s_post * (0.5 * (p1**2 / p2 - torch.log(p2))).sum()
+            add['gh1_%d' % i], add['gh2_%d' % i] = g1, g2
+        add = dist.allreduce_dict(add)
+        grads = {}
+        energy = add['logZ'] + add['phi_h']
+        for i, layer in enumerate(self.sgp_layers):
+            st = _get_stats(add, 's%d_' % i)
+            g = layer._tail_det(st, alpha) if i == 0 else layer._tail_mm(st, alpha)
+            for k, val in g.items():
+                grads[k + '_%d' % i] = val
+            energy = energy + layer._phi(alpha)
+            if i < Ln - 1:
+                grads['h_factor_1_%d' % i], grads['h_factor_2_%d' % i] = add['gh1_%d' % i], add['gh2_%d' % i]
+        if self.lik_layer.has_sn:
+            grads['sn'] = add['dsn'].reshape(())
+        grads['sn_hidden'] = add['dsn_hidden']
         return self._finish(energy, grads)
 
 

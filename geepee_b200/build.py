@@ -22,15 +22,19 @@ def needs_build():
     return any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps)
 
 
-def build(force=False, verbose=False):
-    """nvcc -c every .cu in parallel (one process per translation unit), then link."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """nvcc -c every .cu in parallel (one process per translation unit), then link.
+    `out` / `extra_flags`: development variants of the library (A/B builds for tools/kbench.py,
+    selected at run time with GPB_LIB_PATH); the product is the default build."""
+    variant = out is not None
+    if not variant and not force and not needs_build():
         return OUT
+    out = out or OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    objdir = os.path.join(CSRC, 'build')
+    objdir = os.path.join(CSRC, 'build' if not variant else 'build_' + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != '-shared'] + (['-Xptxas', '-v'] if verbose else []) + \
-        os.environ.get('GPB_EXTRA_NVCC_FLAGS', '').split()
+        os.environ.get('GPB_EXTRA_NVCC_FLAGS', '').split() + list(extra_flags)
     procs = []
     objs = []
     for src in sources():
@@ -44,9 +48,13 @@ def build(force=False, verbose=False):
         log.close()
         if rc != 0:
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, open(log.name).read()[-4000:]))
-    subprocess.check_call([nvcc, '-shared', '-o', OUT] + objs)
-    return OUT
+    subprocess.check_call([nvcc, '-shared', '-o', out] + objs)
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force=True))
+    import sys
+    if len(sys.argv) > 2:       # python -m geepee_b200.build <out.so> <nvcc flags...>
+        print(build(force=True, out=os.path.abspath(sys.argv[1]), extra_flags=sys.argv[2:]))
+    else:
+        print(build(force=True))

@@ -18,8 +18,12 @@ import numpy as np
 import torch
 
 from . import config, ops, _lib
+from .tailgraph import TailGraph
 
 _F = torch.float64
+
+# the cross-row statistics a post-tail consumes
+_TAIL_STAT_KEYS = ('dA', 'dB', 'dzu', 'dl', 'dsf2', 'dvsum')
 
 # device tensors exposed under the reference's attribute names
 _EXPORTED = ('Kuu', 'Kuuinv', 'Su', 'Suinv', 'mu', 'Splusmm', 'A', 'B_det', 'B_sto', 'theta_1',
@@ -124,6 +128,9 @@ class Base_SGP_Layer(object):
         self._iu = (iu[0].to(self.device), iu[1].to(self.device))
         self._t = {}
         self._opnd = {}
+        self._graphs = {}           # (fused alpha) -> TailGraph of the pre-tail (tailgraph.py)
+        self._active_pre = None     # the captured pre-tail whose static outputs self._t holds
+        self._cavity_done = None
         self.ls = np.zeros([input_size, ])
         self.sf = 0
         self.zu = np.zeros([no_pseudo, input_size])
@@ -141,27 +148,66 @@ class Base_SGP_Layer(object):
     def update_hypers(self, params, key_suffix='', _dev=None):
         """base_models.py:630-658: eta1_R -> R (log-diagonal upper triangle), theta_1 = R^T R.
         `_dev` (optional): the same dict already on the device (models upload all keys at once)."""
-        M, Dout, dev = self.M, self.Dout, self.device
+        dev = self.device
         self.ls = params['ls' + key_suffix]
         self.sf = params['sf' + key_suffix]
         self.zu = params['zu' + key_suffix]
-        t = self._t
         if _dev is None:
             _dev = pack_to_device({k: params[k + key_suffix] for k in ('ls', 'sf', 'zu', 'eta1_R', 'eta2')}, dev)
             key_suffix = ''
-        t['ls'] = _dev['ls' + key_suffix].reshape(self.Din).contiguous()
-        t['sf'] = _dev['sf' + key_suffix].reshape(-1)[:1].contiguous()
-        t['zu'] = _dev['zu' + key_suffix].reshape(M, self.Din).contiguous()
-        eta1 = _dev['eta1_R' + key_suffix].reshape(Dout, -1)
+        ins = {k: _dev[k + key_suffix] for k in ('ls', 'sf', 'zu', 'eta1_R', 'eta2')}
+        self._pre_tail(ins, getattr(self, '_fuse_cavity_alpha', None))
+
+    def _pre_tail(self, ins, alpha):
+        """The data-independent device work of one parameter update (+ cavity and log-partitions
+        when the AEP objective announced its alpha): eager for the first calls, then one CUDA-graph
+        replay per call (tailgraph.py)."""
+        if len(self._graphs) > 4 and alpha not in self._graphs:
+            self._graphs.clear()        # alpha is swept: do not hoard graph memory
+        tg = self._graphs.setdefault(alpha, TailGraph())
+
+        def fn(i):
+            self._t = {}
+            self._pre_device(i, alpha)
+            return dict(self._t), self._cavity_done
+
+        snap, done = tg.run(fn, ins, self.device)
+        self._t = dict(snap)            # also drops the lazily formed B matrices of the last call
+        self._opnd = {}
+        self._cavity_done = done
+        self._cavity_ready = None
+        self._active_pre = tg if tg.captured else None
+
+    def _pre_device(self, ins, alpha):
+        M, Dout, dev = self.M, self.Dout, self.device
+        t = self._t
+        t['ls'] = ins['ls'].reshape(self.Din).contiguous()
+        t['sf'] = ins['sf'].reshape(-1)[:1].contiguous()
+        t['zu'] = ins['zu'].reshape(M, self.Din).contiguous()
+        eta1 = ins['eta1_R'].reshape(Dout, -1)
         R = torch.zeros((Dout, M, M), dtype=_F, device=dev)
         R[:, self._iu[0], self._iu[1]] = eta1
         dg = torch.diagonal(R, dim1=1, dim2=2)
         dg.copy_(torch.exp(dg))
         t['theta_1_R'] = R
         t['theta_1'] = torch.matmul(R.transpose(1, 2), R)
-        t['theta_2'] = _dev['eta2' + key_suffix].reshape(Dout, M).contiguous()
+        t['theta_2'] = ins['eta2'].reshape(Dout, M).contiguous()
+        self._cavity_done = None
         self.compute_kuu()
         self.update_posterior()
+        self._pre_extra(alpha)
+
+    def _pre_extra(self, alpha):
+        pass
+
+    def _post_tail(self, name, impl, st, *args):
+        """Chain rules from the reduced statistics to the parameter gradients; replayed from a
+        graph when this layer's state is the static output of a captured pre-tail."""
+        pre = self._active_pre
+        if pre is None:
+            return impl(st, *args)
+        tg = pre.children.setdefault((name,) + args, TailGraph(warmup=0))
+        return tg.run(lambda i: impl(i, *args), {k: st[k] for k in _TAIL_STAT_KEYS}, self.device)
 
     def compute_kuu(self):
         """base_models.py:454-464."""
@@ -399,6 +445,9 @@ class AEP_SGP_Layer(Base_SGP_Layer):
 
     def compute_cavity(self, alpha):
         """aep_models.py:513-546."""
+        if self._cavity_done is not None and self._cavity_done == alpha:
+            return                      # formed with the parameter update (_pre_extra)
+        self._cavity_done = None
         t = self._t
         Ki = t['Kuuinv']
         beta = (self.N - alpha) * 1.0 / self.N
@@ -421,11 +470,21 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         t['Splusmmhat'] = t['Suhat'] + outer(t['muhat'], t['muhat'])
         t.pop('Bhat_sto', None)      # formed on first use (_B)
         t.pop('Bhat_det', None)
+        t.pop('phi', None)
         self._opnd.pop('cav', None)
+
+    def _pre_extra(self, alpha):
+        """AEP objective: cavity and log-partitions belong to the same (graphable) phase."""
+        if alpha is not None:
+            self.compute_cavity(alpha)
+            self._t['phi'] = self._phi(alpha)
+            self._cavity_done = alpha
 
     def _phi(self, alpha):
         """aep_models.py:62-114 (device scalar)."""
         t = self._t
+        if 'phi' in t and self._cavity_done is not None and self._cavity_done == alpha:
+            return t['phi']
         N = self.N
         phi_prior = 0.5 * self.Dout * t['logdet_Kuu']
         phi_post = 0.5 * t['logdet_Su'].sum() + 0.5 * (t['mu'] * bmv(t['Suinv'], t['mu'])).sum()
@@ -457,6 +516,12 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         return tuple(x.cpu().numpy() for x in r)
 
     def _tail_det(self, st, alpha):
+        return self._post_tail('det', self._tail_det_impl, st, alpha)
+
+    def _tail_mm(self, st, alpha):
+        return self._post_tail('mm', self._tail_mm_impl, st, alpha)
+
+    def _tail_det_impl(self, st, alpha):
         """aep_models.py:462-511 rewritten on the statistics (dA = sum_n dm kfu,
         dB = sum_n dv kfu kfu^T): dmucav = dA Kuuinv, dSucav = Kuuinv dB Kuuinv."""
         t = self._t
@@ -481,7 +546,7 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         dsf, dls, dzu = self._kernel_hyper_tail(st, Mm)
         return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1c + e1p, 'eta2': e2c + e2p}
 
-    def _tail_mm(self, st, alpha):
+    def _tail_mm_impl(self, st, alpha):
         """aep_models.py:252-297 on the statistics (dA = sum_n dm_all psi1, dB = sum_n dv psi2)."""
         t = self._t
         N, Ki = self.N, t['Kuuinv']
@@ -546,9 +611,14 @@ class AEP_SGP_Layer(Base_SGP_Layer):
 class VFE_SGP_Layer(Base_SGP_Layer):
     """vfe_models.py:290-548."""
 
+    def _pre_extra(self, alpha):
+        self._t['kl'] = self._kl()
+
     def _kl(self):
         """vfe_models.py:309-325."""
         t = self._t
+        if 'kl' in t:
+            return t['kl']
         tr = (t['Kuuinv'] * t['Splusmm']).sum()
         return 0.5 * (self.Dout * t['logdet_Kuu'] - t['logdet_Su'].sum() - self.Dout * self.M + tr)
 
@@ -556,6 +626,9 @@ class VFE_SGP_Layer(Base_SGP_Layer):
         return float(self._kl().item())
 
     def _tail(self, st, stochastic):
+        return self._post_tail('vfe', self._tail_impl, st, stochastic)
+
+    def _tail_impl(self, st, stochastic):
         """vfe_models.py:518-541 (det) / 363-394 (mm) on the statistics."""
         t = self._t
         Ki = t['Kuuinv']

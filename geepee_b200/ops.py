@@ -51,8 +51,19 @@ def _ws(nbytes, like):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
 
 
+_launch_adjust = 0
+
+
 def launch_count():
-    return int(_lib.get().gpb_launch_count())
+    """Kernels of libgeepee_b200.so launched so far: the library's own counter plus the library
+    kernels executed through CUDA-graph replays (tailgraph.py; a replay does not pass through
+    the C ABI, so it is accounted here with the count seen at capture time)."""
+    return int(_lib.get().gpb_launch_count()) + _launch_adjust
+
+
+def adjust_launch_count(n):
+    global _launch_adjust
+    _launch_adjust += int(n)
 
 
 def kmat(x, z, ls, sf, jitter=0.0):

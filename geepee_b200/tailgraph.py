@@ -1,0 +1,93 @@
+"""CUDA-graph capture of the replicated O(Dout M^3) tails.
+
+The tail of a sparse-GP layer (q(u) / cavity algebra before the forward, chain rules after the
+backward: base_models.py:454-516,630-658, aep_models.py:62-114,252-297,462-586,
+kernels.py:447-475 of the reference) is ~150 small launches per layer -- the library's own
+`kmat` / `spd_inverse` kernels, cuBLAS fp64 GEMMs and elementwise glue.  Their GPU time is
+a few hundred microseconds, but issued one by one they cost 1-2 ms of launch latency per layer
+and step, which is what bounds the small configs (BASELINE config 1) and what remains exposed
+of the single-layer models and of the 8-GPU runs.  The shapes of a tail never change between
+objective calls, so after a short eager warm-up each phase is captured ONCE into a CUDA graph
+with static input / output buffers and replayed from then on:
+
+    ins (fresh device tensors of this call)  --one multi-tensor copy-->  static inputs
+    graph.replay()                            (current stream; ordering as for any kernel)
+    static outputs                            handed to the caller (valid until the next replay)
+
+Rules the captured functions obey (layers.py): device work only, no host reads, no
+data-dependent shapes, every launch on torch's current stream.  A capture that fails for any
+reason marks the phase as not graphable and the call falls back to the same function run
+eagerly -- still the CUDA path, just launched kernel by kernel.
+
+`TAIL_GRAPHS` / `TAIL_GRAPH_WARMUP` live in config.py; `GPB_TAIL_GRAPHS=0` disables capture.
+"""
+import os
+import warnings
+
+import torch
+
+from . import config, ops
+
+
+def enabled(device):
+    if device.type != 'cuda' or not config.TAIL_GRAPHS:
+        return False
+    return os.environ.get('GPB_TAIL_GRAPHS', '1') != '0'
+
+
+class TailGraph(object):
+    """One tail phase: eager for the first `warmup` calls, then captured and replayed."""
+
+    def __init__(self, warmup=None):
+        self.warmup = config.TAIL_GRAPH_WARMUP if warmup is None else warmup
+        self.calls = 0
+        self.graph = None
+        self.failed = False
+        self.keys = None
+        self.static_in = None
+        self.out = None
+        self.own_launches = 0
+        self.children = {}      # phases captured against this phase's static outputs
+
+    @property
+    def captured(self):
+        return self.graph is not None
+
+    def _load(self, ins):
+        torch._foreach_copy_([self.static_in[k] for k in self.keys], [ins[k] for k in self.keys])
+
+    def run(self, fn, ins, device):
+        """fn(ins: {name: tensor}) -> any Python object holding device tensors."""
+        if self.failed or not enabled(device):
+            return fn(ins)
+        if self.graph is None:
+            self.calls += 1
+            if self.calls <= self.warmup:
+                return fn(ins)
+            self.keys = sorted(ins.keys())
+            self.static_in = {k: torch.empty_like(ins[k], memory_format=torch.contiguous_format)
+                              for k in self.keys}
+            self._load(ins)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            try:
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    out = fn(self.static_in)
+            except NotImplementedError:
+                self.failed = True
+                raise
+            except Exception as e:  # noqa: BLE001  (any capture failure -> eager launches)
+                self.failed = True
+                self.static_in = None
+                warnings.warn('geepee_b200: CUDA-graph capture of a tail phase failed (%s: %s); '
+                              'launching it eagerly' % (type(e).__name__, str(e)[:200]))
+                torch.cuda.synchronize(device)
+                return fn(ins)
+            self.own_launches = ops.launch_count() - n0
+            ops.adjust_launch_count(-self.own_launches)     # captured, not executed
+            self.graph, self.out = g, out
+        else:
+            self._load(ins)
+        self.graph.replay()
+        ops.adjust_launch_count(self.own_launches)
+        return self.out

@@ -712,6 +712,92 @@ class AepSDGPR(object):
         return energy / N, {k: val / N for k, val in g.items()}
 
 
+class AepSDGPR_H(AepSDGPR):
+    """aep_models.py:1440-1864: deep GP with a Gaussian factor per training row and hidden
+    unit (natural parameters h_factor_1/2[N, size[i+1]] per hidden layer, tied twice: posterior =
+    2 x factor, cavity = (2 - alpha) x factor).  The hidden variables decouple the layers: layer i
+    maps the cavity of hidden layer i-1 to a Gaussian that is matched to the cavity of hidden
+    layer i (compute_transition_tilted, 1710-1745).  Full batch only: compute_grads_hidden
+    (1621-1653) combines [N, D] factors with batch-sized gradients."""
+
+    def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
+        N, Ln = self.N, self.L
+        assert mb_size >= N, 'SDGPR_H: the reference only supports full batches'
+        xb, yb = self.x, self.y
+        scale = -N * 1.0 / N / alpha
+        for i, L in enumerate(self.layers):
+            L.set_params(params, '_%d' % i)
+            L.cavity(alpha)
+        snh = np.asarray(params['sn_hidden'], dtype=np.float64)
+        h1 = [np.asarray(params['h_factor_1_%d' % i], dtype=np.float64) for i in range(Ln - 1)]
+        h2 = [np.exp(2.0 * np.asarray(params['h_factor_2_%d' % i], dtype=np.float64)) for i in range(Ln - 1)]
+        c1 = [a * (2.0 - alpha) for a in h1]            # compute_cavity_h, 1747-1767
+        c2 = [a * (2.0 - alpha) for a in h2]
+        cm = [a / b for a, b in zip(c1, c2)]
+        cv = [1.0 / b for b in c2]
+        g, dmc, dvc = {}, [], []
+        dsn = np.zeros_like(snh)
+        logZ = 0.0
+        for i in range(Ln - 1):
+            L = self.layers[i]
+            if i == 0:
+                mp, vp, kfu = L.prop_det(xb)
+            else:
+                mp, vp, psi1, psi2 = L.prop_mm(cm[i - 1], cv[i - 1])
+            # compute_transition_tilted, 1710-1745
+            sn2 = np.exp(2.0 * snh[i])
+            vsum = cv[i] + vp + sn2 / alpha
+            md = cm[i] - mp
+            lz = np.sum(-0.5 * md**2 / vsum - 0.5 * np.log(2 * np.pi * vsum)
+                        + 0.5 * (1 - alpha) * np.log(2 * np.pi * sn2) - 0.5 * np.log(alpha))
+            dvt = -0.5 / vsum + 0.5 * md**2 / vsum**2
+            dmt = -md / vsum
+            dsn[i] = scale * (np.sum(dvt) * 2 * sn2 / alpha + mp.shape[0] * self.size[i + 1] * (1 - alpha))
+            logZ += scale * lz
+            if i == 0:
+                gh = L.aep_grads_det(mp, vp, scale * (-dmt), scale * dvt, kfu, xb, alpha)
+            else:
+                gh, gi = L.aep_grads_mm(mp, vp, scale * (-dmt), scale * dvt, psi1, psi2,
+                                        cm[i - 1], cv[i - 1], alpha)
+                dmc[i - 1] = dmc[i - 1] + gi['mx']
+                dvc[i - 1] = dvc[i - 1] + gi['vx']
+            for k, val in gh.items():
+                g[k + '_%d' % i] = val
+            dmc.append(scale * dmt)
+            dvc.append(scale * dvt)
+        i = Ln - 1
+        L = self.layers[i]
+        mp, vp, psi1, psi2 = L.prop_mm(cm[i - 1], cv[i - 1])
+        gl = {}
+        lzl, dm, dv = lik_log_Z(self.lik, params, mp, vp, yb, alpha, scale, gl)
+        gh, gi = L.aep_grads_mm(mp, vp, scale * dm, scale * dv, psi1, psi2, cm[i - 1], cv[i - 1], alpha)
+        logZ += scale * lzl
+        dmc[i - 1] = dmc[i - 1] + gi['mx']
+        dvc[i - 1] = dvc[i - 1] + gi['vx']
+        for k, val in gh.items():
+            g[k + '_%d' % i] = val
+        g.update(gl)
+        g['sn_hidden'] = dsn
+        # compute_grads_hidden 1621-1653, compute_phi_{cavity,posterior}_h 1655-1690
+        s_post, s_cav = -(1.0 - 1.0 / alpha), -1.0 / alpha
+        phi_h = 0.0
+        for i in range(Ln - 1):
+            p1, p2 = 2.0 * h1[i], 2.0 * h2[i]
+            d1 = (2 - alpha) * (dmc[i] / c2[i]) + s_cav * (2 - alpha) * (c1[i] / c2[i]) \
+                + s_post * 2 * (p1 / p2)
+            d2 = (2 - alpha) * (-dmc[i] * c1[i] / c2[i]**2 - dvc[i] / c2[i]**2) \
+                + s_cav * (2 - alpha) * (-0.5 * c1[i]**2 / c2[i]**2 - 0.5 / c2[i]) \
+                + s_post * (-p1**2 / p2**2 - 1 / p2)
+            g['h_factor_1_%d' % i] = d1
+            g['h_factor_2_%d' % i] = 2 * d2 * h2[i]
+            phi_h += s_cav * np.sum(0.5 * (c1[i]**2 / c2[i] - np.log(c2[i])))
+            phi_h += s_post * np.sum(0.5 * (p1**2 / p2 - np.log(p2)))
+        energy = logZ + sum(L.phi(alpha) for L in self.layers) + phi_h
+        for p in self.fixed_params:
+            g[p] = np.zeros_like(g[p])
+        return energy / N, {k: val / N for k, val in g.items()}
+
+
 def _phi_x(mx, vx):
     """aep_models.py:863-867 compute_phi_x."""
     return (np.sum(0.5 * (mx**2 / vx + np.log(vx))), mx / vx,

@@ -112,6 +112,11 @@ def patch(name, src):
                       'VinvY = np.linalg.solve(Vy, Ydiff[..., None])[..., 0]')
     if name == 'kernels':
         src += PSI_TAIL
+    if name == 'aep_models':
+        # SDGPR_H (aep_models.py:1493,1495) names Gauss_Layer / Probit_Layer, which the module never
+        # imports (NameError as shipped): add the missing import, nothing else
+        src = src.replace('from .base_models import Base_Model\n',
+                          'from .base_models import Base_Model\nfrom .lik_layers import Gauss_Layer, Probit_Layer\n', 1)
     return src
 
 

@@ -294,9 +294,50 @@ def probit_cases():
     case_sgplvm('vfe_sgplvm_probit', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=55, lk='Probit')
 
 
+def case_sdgprh(name, N, M, D, hidden, Do, alpha, seed=60, lk='Gaussian', init_recipe=True):
+    """tests/test_grads_aep.py:340-367 (SDGPR_H: deep GP with per-row hidden-variable factors)."""
+    rng = np.random.RandomState(seed)
+    x = rng.standard_normal((N, D))
+    y = rng.standard_normal((N, Do))
+    if lk == 'Probit':
+        y = 2.0 * (y > 0) - 1.0
+    np.random.seed(seed)
+    model = aep.SDGPR_H(x, y, M, hidden, lik=lk)
+    params = perturb(quiet(model.init_hypers, y), rng)
+    if lk == 'Gaussian':
+        params['sn'] = np.array(np.log(0.3))
+    if not init_recipe:      # moderate factor precisions / transition noise instead of 1e-4 / 1e-3
+        size = [D] + list(hidden) + [Do]
+        params['sn_hidden'] = np.log(0.2) + 0.05 * rng.standard_normal(len(hidden))
+        for i in range(len(hidden)):
+            params['h_factor_1_%d' % i] = 0.5 * rng.standard_normal((N, size[i + 1]))
+            params['h_factor_2_%d' % i] = np.log(1.5) / 2 + 0.1 * rng.standard_normal((N, size[i + 1]))
+    e, g = run(model, params, N, alpha, seed=123)
+    extra = {}
+    if lk == 'Gaussian':
+        xs = rng.standard_normal((6, D))
+        model.update_hypers(params)
+        model.updated = False
+        mf, vf = model.predict_f(xs)
+        my, vy = model.predict_y(xs)
+        extra = {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy}
+    save(name, dict(model='aep_models.SDGPR_H', N=N, M=M, D=D, hidden=hidden, Do=Do, alpha=alpha,
+                    mb_size=N, rng_seed=123, lik=lk), {'x': x, 'y': y}, params, e, g, extra)
+
+
+def sdgprh_cases():
+    case_sdgprh('aep_sdgprh', 10, 5, 2, [3, 2], 3, 0.5)
+    case_sdgprh('aep_sdgprh_moderate', 12, 6, 3, [2, 2], 2, 0.7, seed=61, init_recipe=False)
+    case_sdgprh('aep_sdgprh_alpha_one', 10, 5, 2, [3], 1, 1.0, seed=62, init_recipe=False)
+    case_sdgprh('aep_sdgprh_probit', 8, 4, 2, [3, 2], 3, 0.3, seed=63, lk='Probit', init_recipe=False)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'probit':   # only the files added with the probit layer
         probit_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'sdgprh':   # only the files added with SDGPR_H
+        sdgprh_cases()
         sys.exit(0)
     # tests/test_grads_aep.py:124-135 shape (alpha 0.5) + its alpha=1e-4 + non-natural params
     case_sgpr('aep_sgpr', aep.SGPR, 20, 10, 2, 3, 0.5, True)
@@ -332,3 +373,5 @@ if __name__ == '__main__':
     probit_cases()
     case_kernels()
     case_emis()
+    probit_cases()
+    sdgprh_cases()

@@ -71,6 +71,8 @@ def build_oracle_model(gold):
         return go.VfeSGPR(i['x'], i['y'], m['M'], m['nat_param'], lik=lk)
     if kind == 'aep_models.SDGPR':
         return go.AepSDGPR(i['x'], i['y'], m['M'], m['hidden'], lik=lk)
+    if kind == 'aep_models.SDGPR_H':
+        return go.AepSDGPR_H(i['x'], i['y'], m['M'], m['hidden'], lik=lk)
     if kind == 'aep_models.SGPLVM':
         return go.AepSGPLVM(i['y'], m['Q'], m['M'], lik=lk)
     if kind == 'vfe_models.SGPLVM':

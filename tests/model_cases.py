@@ -20,6 +20,8 @@ def build_model(gold, prec='fp64', device=None):
         return vfe.SGPR(i['x'], i['y'], m['M'], lik=lk, nat_param=m['nat_param'], **kw)
     if kind == 'aep_models.SDGPR':
         return aep.SDGPR(i['x'], i['y'], m['M'], m['hidden'], lik=lk, **kw)
+    if kind == 'aep_models.SDGPR_H':
+        return aep.SDGPR_H(i['x'], i['y'], m['M'], m['hidden'], lik=lk, **kw)
     if kind == 'aep_models.SGPLVM':
         return aep.SGPLVM(i['y'], m['Q'], m['M'], lik=lk, **kw)
     if kind == 'vfe_models.SGPLVM':

@@ -24,6 +24,6 @@ def test_objective_fp32(name):
     mc.check_model(name, 'fp32', 1e-3)
 
 
-@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat'])
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat', 'aep_sdgprh'])
 def test_predict(name):
     mc.check_predict(name, 'fp64', 1e-8)

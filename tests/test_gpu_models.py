@@ -39,7 +39,7 @@ def test_objective_fp32(name):
     mc.check_model(name, 'fp32', TOL32)
 
 
-@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat', 'aep_sgpr_cfg1'])
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat', 'aep_sgpr_cfg1', 'aep_sdgprh'])
 def test_predict(name):
     mc.check_predict(name, 'fp64', 1e-7)
 

@@ -52,11 +52,13 @@ for name, pr, iters in [('fp64', ops.F64, 20000), ('fp32', ops.F32, 40000)]:
         fl[0] = ops.fma_peak(pr, iters, dev)
     med, mn = timeit(run)
     peaks[name] = fl[0] / (mn * 1e-3) / 1e12
-    emit(kind='fma_peak', prec=name, tflops=peaks[name], ms=mn)
+    emit(kind='fma_peak', prec=name, tflops=peaks[name], ms=mn, lib=os.path.basename(_lib.LIB_PATH))
 
 cfgs = [(262144, 256, 10, 1), (262144, 256, 10, 2), (131072, 512, 16, 1), (262144, 128, 5, 1)]
 if len(sys.argv) > 1 and sys.argv[1] == 'quick':
     cfgs = cfgs[:1]
+if len(sys.argv) > 1 and sys.argv[1] == 'mm':       # pair kernels only (library A/B variants)
+    cfgs = []
 for n, M, D, Do in cfgs:
     for name, pr in [('fp64', ops.F64), ('fp32', ops.F32)]:
         x, z = rnd(n, D, seed=1), rnd(M, D, seed=2)
@@ -88,7 +90,7 @@ mm_cfgs = [(32768, 256, 2, 2), (32768, 256, 2, 1), (16384, 200, 4, 4), (8192, 12
 if len(sys.argv) > 1 and sys.argv[1] == 'quick':
     mm_cfgs = mm_cfgs[:1]
 for n, M, Q, Do in mm_cfgs:
-    for name, pr in [('fp64', ops.F64), ('fp32', ops.F32)]:
+    for name, pr in ([('fp64', ops.F64)] if sys.argv[1:2] == ['mm'] else [('fp64', ops.F64), ('fp32', ops.F32)]):
         mx, z = rnd(n, Q, seed=1), rnd(M, Q, seed=2)
         vx = (0.1 + torch.rand(n, Q, dtype=torch.float64)).to(dev)
         ls, sf = torch.full((Q,), 0.3, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.float64, device=dev)

@@ -84,6 +84,17 @@ __global__ void __launch_bounds__(256) probe(long iters, double* sink, const dou
                 if (V == 17) iv[i] = (iv[i] & iv[(i + 1) & 7]) ^ 0x5a5a5a5a;
                 if (V == 18) iv[i] = sm[(iv[i] + threadIdx.x) & 1023];
             }
+        } else if (V == 20) {    // conversions only: 8 x (F2F.F32.F64 + F2F.F64.F32) per iteration
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = (double)((float)a[i] * 1.0000001f);
+        } else if (V == 21) {    // fast DFMA + one F64->F32->F64 round trip per DFMA
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a[i] = a[i] * b[0] + c[0]; b[i] = (double)((float)b[i] * 1.0000001f); }
+        } else if (V == 22) {    // 8 fast DFMA + two round trips (the ratio of a table exp with an fp32 tail)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = a[i] * b[0] + c[0];
+            c[1] = (double)((float)c[1] * 1.0000001f);
+            c[2] = (double)((float)c[2] * 1.0000001f);
         } else if (V == 15) {    // 2x4 outer product: a[i*4+j] += b[i]*c[j]
 #pragma unroll
             for (int i = 0; i < 2; i++)
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(256) probe(long iters, double* sink, const dou
         }
     }
     double r = 0;
-    for (int i = 0; i < 8; i++) r += a[i] + (double)iv[i];
+    for (int i = 0; i < 8; i++) r += a[i] + b[i] + c[i] + (double)iv[i];
     if (r == 1.2345) sink[blockIdx.x] = r;
 }
 
@@ -151,5 +162,8 @@ int main() {
     run<19>("fast DFMA + 2 IMAD each", sms, sink, src, ghz);
     run<17>("fast DFMA + 1 LOP3 each", sms, sink, src, ghz);
     run<18>("fast DFMA + 1 LDS each", sms, sink, src, ghz);
+    run<20>("8 F64->F32->F64 only (as 8)", sms, sink, src, ghz);
+    run<21>("fast DFMA + 1 cvt pair each", sms, sink, src, ghz);
+    run<22>("8 fast DFMA + 2 cvt pairs", sms, sink, src, ghz);
     return 0;
 }
