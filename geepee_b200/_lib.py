@@ -43,6 +43,7 @@ _SIGS = {
     'gpb_det_bwd_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
     'gpb_det_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 9 + [ctypes.c_int] * 4 + [c_dp] * 5 +
                     [ctypes.c_size_t, c_dp]),
+    'gpb_det_dx': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 8 + [ctypes.c_int] * 4 + [c_dp, c_dp]),
     'gpb_det_syrk_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 3),
     'gpb_det_syrk': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp] + [ctypes.c_int] * 3 +
                      [c_dp, c_dp, ctypes.c_size_t, c_dp]),

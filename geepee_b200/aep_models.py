@@ -16,19 +16,28 @@ import torch
 from . import dist
 from .sched import TailStreams
 from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
-from .config import PROP_MM, PROP_MC, PROP_LIN
-from .layers import pack_to_device, AEP_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
+from .config import PROP_MM, PROP_MC, PROP_LIN, MC_NO_SAMPLES
+from .layers import pack_to_device, to_dev, AEP_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
 
 _F = torch.float64
 
 
-def _check_mode(prop_mode):
-    if prop_mode == PROP_MM:
+def _check_mode(prop_mode, mc_ok=False):
+    if prop_mode == PROP_MM or (mc_ok and prop_mode == PROP_MC):
         return
     if prop_mode in (PROP_MC, PROP_LIN):
         raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet '
                                   '(SURVEY.md section 8f)' % prop_mode)
     raise NotImplementedError('propagation mode not implemented')
+
+
+def _mc_eps(n, Q, dev):
+    """eps[K, n, Q] of the Monte-Carlo propagation: drawn on the host from numpy's GLOBAL RNG
+    exactly where the reference draws it (aep_models.py:171, base_models.py:320), so that seeded
+    runs reproduce the reference; every rank draws the same array and keeps its rows."""
+    eps = np.random.randn(MC_NO_SAMPLES, n, Q)
+    lo, hi = dist.shard(n)
+    return to_dev(eps[:, lo:hi], dev)
 
 
 def _zeros(dev, *shape):
@@ -352,9 +361,10 @@ class SGPLVM(Base_SGPLVM):
         return (0.5 * (mx**2 / vx + torch.log(vx))).sum(), mx / vx, 0.5 * (-mx**2 / vx**2 + 1 / vx)
 
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
-        _check_mode(prop_mode)
+        _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
         sel, n = self._rows(mb_size)
+        eps = _mc_eps(n, Q, dev) if prop_mode == PROP_MC else None
         scale_logZ = -N * 1.0 / n / alpha
         s_cav = -N * 1.0 / n / alpha
         s_post = -N * 1.0 / n * (1.0 - 1.0 / alpha)
@@ -367,9 +377,14 @@ class SGPLVM(Base_SGPLVM):
             mcav, vcav = self._cavity_x(alpha, sel)
             p1, p2 = self._post1[sel], self._post2[sel]
             mpost, vpost = p1 / p2, 1.0 / p2
-            m, v, ctx = L._fwd_mm(mcav, vcav, cav=True)
-            dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
-            st = L._bwd_mm(ctx, dm, dv)
+            if eps is not None:     # aep_models.py:745-761
+                m, v, ctx = L._fwd_mc(mcav, vcav, eps, cav=True)
+                dm, dv, logZ, dsn = self.lik_layer._log_Z_mc(m, v, yb, alpha, scale_logZ)
+                st = L._bwd_mc(ctx, dm, dv)
+            else:
+                m, v, ctx = L._fwd_mm(mcav, vcav, cav=True)
+                dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
+                st = L._bwd_mm(ctx, dm, dv)
             _add_stats(add, 's_', st)
             # latent-variable terms, aep_models.py:785-801, 817-838; base_models.py:913-929
             phi_cav, dmc, dvc = self._phi_x(mcav, vcav)
@@ -400,7 +415,8 @@ class SGPLVM(Base_SGPLVM):
             for k in ('logZ', 'dsn', 'phi_cav', 'phi_post'):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
-        grads = L._tail_mm(_get_stats(add, 's_'), alpha)
+        tail = L._tail_mc if prop_mode == PROP_MC else L._tail_mm
+        grads = tail(_get_stats(add, 's_'), alpha)
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']

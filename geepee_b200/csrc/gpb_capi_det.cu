@@ -273,6 +273,32 @@ int gpb_det_bwd(int prec, const double* x, const double* z, const double* ls, co
     return det_bwd_t<float>(x, z, ls, sf, Ap, dm, dv, Ksave, Tsave, n, M, D, Do, dA, dzu, dl, dsf2, ws, ws_bytes, stream);
 }
 
+int gpb_det_dx(int prec, const double* x, const double* z, const double* ls, const void* Ap, const double* dm,
+               const double* dv, const void* Ksave, const void* Tsave, int n, int M, int D, int Do,
+               double* dx, void* stream) {
+    if (!x || !z || !ls || !Ap || !dm || !dv || !Ksave || !Tsave || !dx)
+        return fail(GPB_ERR_ARG, "det_dx: null pointer");
+    const int MP = gpb_det_pad_m(M);
+    if (MP < 0 || n < 1 || D < 1 || D > 32 || Do < 1) return fail(GPB_ERR_ARG, "det_dx: bad size");
+    const size_t smem = sizeof(double) * ((size_t)M * D + D);
+    long blocks = ((long)n + 7) / 8;
+    const long cap = 16L * gpb_sm_count();
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    int rc;
+    if (prec == GPB_F64) {
+        auto kern = gpb::det_dx_kernel<double>;
+        if ((rc = allow_smem(kern, smem))) return rc;
+        GPB_LAUNCH(kern, dim3(grid), dim3(256), smem, stream, x, z, ls, (const double*)Ap, dm, dv,
+                   (const double*)Ksave, (const double*)Tsave, n, M, MP, D, Do, dx);
+    } else {
+        auto kern = gpb::det_dx_kernel<float>;
+        if ((rc = allow_smem(kern, smem))) return rc;
+        GPB_LAUNCH(kern, dim3(grid), dim3(256), smem, stream, x, z, ls, (const float*)Ap, dm, dv,
+                   (const float*)Ksave, (const float*)Tsave, n, M, MP, D, Do, dx);
+    }
+    return GPB_CHECK_LAUNCH();
+}
+
 size_t gpb_det_syrk_ws_bytes(int n, int M, int Do) {
     if (gpb_det_pad_m(M) < 0) return 0;
     SyrkPlan p = syrk_plan(n, M, Do);

@@ -949,6 +949,54 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_bwd_kernel(
     }
 }
 
+// Input gradient of the deterministic layer (Monte-Carlo propagation: the layer is fed samples of an
+// uncertain input and the gradient travels back to the sample, aep_models.py:346-350 +
+// kernels.py:393-395 kfucompDer(grad_x=True)):
+//   L[n,m]  = (sum_d dm[n,d] A[d,m] + 2 dv[n,d] T[n,d,m]) kfu[n,m]
+//   dx[n,q] = sum_m L[n,m] (z[m,q] - x[n,q]) / l_q^2
+// One warp per row streams the saved Kfu / T rows (coalesced), z sits in shared memory; the D + 1
+// row sums are reduced with shuffles.  HBM bound: (1 + Do) MP sizeof(T) bytes per row.
+template <typename T>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_dx_kernel(
+    const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ ls,
+    const T* __restrict__ Ap, const double* __restrict__ dm, const double* __restrict__ dv,
+    const T* __restrict__ Ksave, const T* __restrict__ Tsave, int n, int M, int MP, int D, int Do,
+    double* __restrict__ dx) {
+    GPB_DYN_SMEM(dsm);
+    double* zs = (double*)dsm;              // [M, D]
+    double* il2 = zs + (long)M * D;         // [D]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < M * D; i += kThreads) zs[i] = z[i];
+    for (int i = tid; i < D; i += kThreads) il2[i] = exp(-2.0 * ls[i]);
+    sync_threads();
+    for (long row = (long)blockIdx.x * 8 + warp; row < n; row += (long)gridDim.x * 8) {
+        for (int q0 = 0; q0 < D; q0 += 8) {
+            double acc[8], accL = 0;
+            GPB_UNROLL
+            for (int q = 0; q < 8; q++) acc[q] = 0;
+            for (int m = lane; m < M; m += 32) {
+                double g = 0;
+                for (int d = 0; d < Do; d++)
+                    g += dm[row * Do + d] * (double)Ap[(long)d * MP + m] +
+                         2.0 * dv[row * Do + d] * (double)Tsave[(row * Do + d) * MP + m];
+                const double L = g * (double)Ksave[row * MP + m];
+                accL += L;
+                GPB_UNROLL
+                for (int q = 0; q < 8; q++)
+                    if (q0 + q < D) acc[q] += L * zs[(long)m * D + q0 + q];
+            }
+            accL = warp_sum(accL);
+            GPB_UNROLL
+            for (int q = 0; q < 8; q++) acc[q] = warp_sum(acc[q]);
+            if (lane == 0) {
+                GPB_UNROLL
+                for (int q = 0; q < 8; q++)
+                    if (q0 + q < D) dx[row * D + q0 + q] = (acc[q] - x[row * D + q0 + q] * accL) * il2[q0 + q];
+            }
+        }
+    }
+}
+
 // Ring version of the row-streaming backward (Do <= 4, D <= 16): the saved Kfu / T rows and the
 // per-row x, dm, dv records of TRS rows travel through a cp.async ring (2-3 stages, no register
 // staging), so the global loads of the next chunks are in flight while a chunk is reduced --
@@ -1410,9 +1458,9 @@ struct MMArgs {
 //         reads copy l mod 16, so the data-dependent lookups of a half warp always fall into 16
 //         different 8-byte banks (the un-replicated 2048-entry table of v9 spent 6 wavefronts per
 //         lookup on bank conflicts and made the kernel shared-memory bound; ncu, profiles/).
-//         e^(r h) (h = ln2/256, |r h| <= 1.36e-3) is the degree-4 Taylor polynomial (truncation
-//         3.8e-17) folded with the table value: t + (t r)(c1 + r (c2 + r (c3 + r c4))).
-//         8 fp64 instructions (3 add, 1 mul, 4 fma) instead of ~25 for libm's exp; the 2^k scaling
+//         e^(r h) (h = ln2/256, |r h| <= 1.36e-3) is a Taylor polynomial of degree GPB_EXP_DEG
+//         (default 3, truncation 1.4e-13) folded with the table value: t + (t r)(c1 + r (c2 + r c3)).
+//         7 fp64 instructions (3 add, 1 mul, 3 fma) instead of ~25 for libm's exp; the 2^k scaling
 //         is an integer add into the exponent field with k clamped at -1021 (deep underflow returns
 //         ~1e-308 instead of 0).
 //   fp32: S = log2(e); one SFU instruction (ex2.approx).
@@ -1429,9 +1477,13 @@ template <> struct ExpDom<float> {
     static constexpr double S = 1.4426950408889634074;
 };
 // GPB_EXP_DEG: degree of the e^(r h) polynomial (relative truncation error 3.8e-17 / 1.4e-13 /
-// 4.2e-10 for 4 / 3 / 2; one fp64 instruction per degree).
+// 4.2e-10 for 4 / 3 / 2; one fp64 instruction per degree).  Default 3: its 1.4e-13 is the size of
+// the rounding already accepted in the expanded-form exponents and 7 orders below the 1e-6 parity
+// bar; measured on the B200 (tools/kbench.py): pair kernels -4.3 % (fwd) / -2.9 % (bwd) vs degree 4.
+// Measured and rejected: rounding through the conversion unit (cvt.rni.s32.f64 + cvt.rn.f64.s32
+// instead of the two magic-number DADDs) -- no gain, the fp64 conversions share the fp64 pipe.
 #ifndef GPB_EXP_DEG
-#define GPB_EXP_DEG 4
+#define GPB_EXP_DEG 3
 #endif
 template <int N>
 GPB_DEVICE void exp_dom_n(double (&x)[N], const double* __restrict__ tab, int lane16) {

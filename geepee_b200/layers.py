@@ -372,6 +372,31 @@ class Base_SGP_Layer(object):
         return ops.mm_bwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous(),
                           dm, dv, mout, vacc, psi1)
 
+    def _fwd_mc(self, mx, vx, eps, cav):
+        """aep_models.py:160-180 / base_models.py:309-332: samples x = mx + sqrt(vx) eps (eps[K,n,Q]
+        drawn on the host from numpy's global RNG, as the reference does) pushed through the
+        deterministic-input kernels as K*n stacked rows.  -> mout, vout [K,n,Do], ctx."""
+        K, n, Q = eps.shape
+        xs = (eps * torch.sqrt(vx) + mx).reshape(K * n, Q).contiguous()
+        m, v, ctx = self._fwd_det(xs, cav=cav, save=True)
+        return m.reshape(K, n, self.Dout), v.reshape(K, n, self.Dout), (ctx, eps, vx)
+
+    def _bwd_mc(self, ctx, dm, dv):
+        """Per-row part of backprop_grads_lvm_mc (aep_models.py:307-410, vfe_models.py:405-476) +
+        backprop_grads_reparam (base_models.py:373-388): the deterministic-layer statistics over the
+        stacked samples and the gradient wrt every sample, folded back onto (mx, vx)."""
+        det_ctx, eps, vx = ctx
+        K, n, Q = eps.shape
+        dm2 = dm.reshape(K * n, self.Dout).contiguous()
+        dv2 = dv.reshape(K * n, self.Dout).contiguous()
+        st = self._bwd_det(det_ctx, dm2, dv2)
+        xs, opnd, Ks, Ts = det_ctx
+        t = self._t
+        dx = ops.det_dx(self.prec, xs, t['zu'], t['ls'], opnd, dm2, dv2, Ks, Ts).reshape(K, n, Q)
+        st['dmx'] = dx.sum(0)
+        st['dvx'] = (dx * eps).sum(0) / (2.0 * torch.sqrt(vx))
+        return st
+
     # ---- shared chain rules ------------------------------------------------------------------
     def _pack_eta1(self, dtheta1):
         """theta_1 = R^T R with log-diagonal packing (base_models.py:505-514)."""
@@ -520,6 +545,34 @@ class AEP_SGP_Layer(Base_SGP_Layer):
 
     def _tail_mm(self, st, alpha):
         return self._post_tail('mm', self._tail_mm_impl, st, alpha)
+
+    def _tail_mc(self, st, alpha):
+        return self._post_tail('mc', self._tail_mc_impl, st, alpha)
+
+    def _tail_mc_impl(self, st, alpha):
+        """aep_models.py:352-403 (backprop_grads_lvm_mc) on the statistics of the stacked samples
+        (dA = sum_n dm kfu, dB = sum_n dv kfu kfu^T): with SK = Suhat Kuuinv,
+        dSinv_d = -SK dB_d SK^T - (SK dA_d) muhat_d^T, dtheta2_d = beta SK dA_d + phi terms."""
+        t = self._t
+        N, Ki = self.N, t['Kuuinv']
+        if not self.nat_param:
+            raise NotImplementedError('AEP Monte-Carlo propagation needs nat_param=True (the reference '
+                                      'treats theta as natural parameters: aep_models.py:365-371)')
+        beta = (N - alpha) * 1.0 / N
+        scale_post = N * 1.0 / alpha - 1.0
+        scale_cav = -N * 1.0 / alpha
+        dA, dB = st['dA'], st['dB']
+        SK = torch.matmul(t['Suhat'], Ki)
+        SKdA = bmv(SK, dA)
+        dSinv = -torch.matmul(SK, torch.matmul(dB, SK.transpose(1, 2))) - outer(SKdA, t['muhat'])
+        dtheta1 = beta * dSinv - 0.5 * scale_post * t['Splusmm'] - 0.5 * scale_cav * beta * t['Splusmmhat']
+        dtheta2 = beta * SKdA + scale_post * t['mu'] + scale_cav * beta * t['muhat']
+        dKi = torch.matmul(dA.t(), t['muhat']) \
+            + 2.0 * torch.matmul(SK, dB).sum(0) - dB.sum(0) + dSinv.sum(0)
+        Minner = scale_post * t['Splusmm'].sum(0) + scale_cav * t['Splusmmhat'].sum(0) - 2.0 * dKi
+        M_all = 0.5 * (self.Dout * Ki + torch.matmul(Ki, torch.matmul(Minner, Ki)))
+        dsf, dls, dzu = self._kernel_hyper_tail(st, M_all)
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1(dtheta1), 'eta2': dtheta2}
 
     def _tail_det_impl(self, st, alpha):
         """aep_models.py:462-511 rewritten on the statistics (dA = sum_n dm kfu,

@@ -100,6 +100,25 @@ class Gauss_Layer(Lik_Layer):
         dsn = scale * (o[1] * 2.0 * sn2 / alpha + m.shape[0] * self.D * (1.0 - alpha))
         return dm, dv, o[0], dsn.reshape(())
 
+    def _log_Z_mc(self, m, v, y, alpha, scale):
+        """lik_layers.py:134-150 + 175-181: m, v [K,n,D] from K Monte-Carlo samples of the layer
+        input; log-mean-exp of the per-sample tilted log-partitions (elementwise, on the device).
+        Same contract as _log_Z: (scale*dm, scale*dv, logZ_sum unscaled, dsn)."""
+        sn2 = torch.exp(2.0 * self._sn)
+        vv = v + sn2 / alpha
+        d = y.unsqueeze(0) - m
+        lz = -0.5 * (torch.log(2 * np.pi * vv) + d * d / vv) \
+            + (0.5 * torch.log(2 * np.pi * sn2 / alpha) - 0.5 * alpha * torch.log(2 * np.pi * sn2))
+        lmax = lz.max(dim=0).values
+        ex = torch.exp(lz - lmax)
+        se = ex.sum(0)
+        logZ = (lmax + torch.log(se) - np.log(m.shape[0])).sum()
+        w = ex / se
+        dm = w * d / vv
+        dv = w * (-0.5 / vv + 0.5 * d * d / (vv * vv))
+        dsn = scale * (dv.sum() * 2.0 * sn2 / alpha + m.shape[1] * self.D * (1.0 - alpha))
+        return (scale * dm).contiguous(), (scale * dv).contiguous(), logZ, dsn.reshape(())
+
     def _log_lik_exp(self, m, v, y, scale):
         """lik_layers.py:183-199 + 217-226."""
         dm, dv, o = ops.gauss_lik(m, v, y, self._sn, 1.0, scale, 1)

@@ -204,6 +204,17 @@ def det_bwd(prec, x, z, ls, sf, opnd, dm, dv, Ks, Ts):
     return dA, dzu, dl, dsf2
 
 
+def det_dx(prec, x, z, ls, opnd, dm, dv, Ks, Ts):
+    """aep_models.py:346-350 + kernels.py:393-395: gradient wrt the inputs of the deterministic
+    layer (Monte-Carlo propagation feeds it samples of an uncertain input).  -> dx[n,D]."""
+    lib = _lib.get()
+    n, D = x.shape
+    dx = torch.empty((n, D), dtype=torch.float64, device=x.device)
+    _chk(lib.gpb_det_dx(prec, _p(_c(x)), _p(_c(z)), _p(_c(ls)), _p(opnd.Ap), _p(_c(dm)), _p(_c(dv)),
+                        _p(Ks), _p(Ts), n, opnd.M, D, opnd.Do, _p(dx), _stream(x)), 'det_dx')
+    return dx
+
+
 def det_syrk(prec, Ks, dv, M):
     """aep_models.py:493  dB[d] = sum_n dv[n,d] kfu kfu^T."""
     lib = _lib.get()

@@ -9,9 +9,9 @@ import numpy as np
 import torch
 
 from . import dist
-from .aep_models import _add_stats, _get_stats, _zero_stats, _zeros, _check_mode
+from .aep_models import _add_stats, _get_stats, _zero_stats, _zeros, _check_mode, _mc_eps
 from .base_models import Base_SGPR, Base_SGPLVM, Base_SGPSSM
-from .config import PROP_MM
+from .config import PROP_MM, PROP_MC
 from .layers import VFE_SGP_Layer as SGP_Layer  # noqa: F401  (reference name)
 
 _F = torch.float64
@@ -57,9 +57,10 @@ class SGPLVM(Base_SGPLVM):
         self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
 
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode=PROP_MM):
-        _check_mode(prop_mode)
+        _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
         sel, n = self._rows(mb_size)
+        eps = _mc_eps(n, Q, dev) if prop_mode == PROP_MC else None
         scale = -N * 1.0 / n
         sx = N * 1.0 / n
         self.update_hypers(params)
@@ -69,9 +70,17 @@ class SGPLVM(Base_SGPLVM):
             yb = self._y.index_select(0, sel)
             p1, p2 = self._post1[sel], self._post2[sel]
             mx, vx = (p1 / p2).contiguous(), (1.0 / p2).contiguous()
-            m, v, ctx = L._fwd_mm(mx, vx, cav=False)
-            dm, dv, ll, dsn = self.lik_layer._log_lik_exp(m, v, yb, scale)
-            st = L._bwd_mm(ctx, dm, dv)
+            if eps is not None:     # vfe_models.py:793-808: sample average of the expected log-lik
+                K = eps.shape[0]
+                m, v, ctx = L._fwd_mc(mx, vx, eps, cav=False)
+                dm, dv, ll, dsn = self.lik_layer._log_lik_exp(
+                    m.reshape(-1, self.Dout), v.reshape(-1, self.Dout), yb.repeat(K, 1), scale / K)
+                ll = ll / K
+                st = L._bwd_mc(ctx, dm, dv)
+            else:
+                m, v, ctx = L._fwd_mm(mx, vx, cav=False)
+                dm, dv, ll, dsn = self.lik_layer._log_lik_exp(m, v, yb, scale)
+                st = L._bwd_mm(ctx, dm, dv)
             _add_stats(add, 's_', st)
             # KL of q(x) (vfe_models.py:857-863) and chain to x1, x2 (base_models.py:913-929)
             klx = (0.5 * (np.log(v0) - torch.log(vx) + (vx + (mx - m0)**2) / v0 - 1)).sum()
@@ -91,7 +100,7 @@ class SGPLVM(Base_SGPLVM):
             for k in ('ll', 'dsn', 'klx'):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
-        grads = L._tail(_get_stats(add, 's_'), True)
+        grads = L._tail(_get_stats(add, 's_'), prop_mode != PROP_MC)
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']

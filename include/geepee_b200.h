@@ -116,6 +116,13 @@ int gpb_det_bwd(int prec, const double* x, const double* z, const double* ls, co
                 const void* Ap, const double* dm, const double* dv, const void* Ksave,
                 const void* Tsave, int n, int M, int D, int Do, double* dA, double* dzu,
                 double* dl, double* dsf2, void* ws, size_t ws_bytes, void* stream);
+/* Monte-Carlo propagation: gradient wrt the layer INPUT of the deterministic layer,
+ *      aep_models.py:346-350 (backprop_grads_lvm_mc) + kernels.py:393-395 (kfucompDer, grad_x=True):
+ *      dx[n,D] = sum_m (dm A + 2 dv T)[n,m] kfu[n,m] (z[m,:] - x[n,:]) / l^2, from the buffers
+ *      gpb_det_fwd saved. */
+int gpb_det_dx(int prec, const double* x, const double* z, const double* ls, const void* Ap,
+               const double* dm, const double* dv, const void* Ksave, const void* Tsave,
+               int n, int M, int D, int Do, double* dx, void* stream);
 /* a8 (rank update): aep_models.py:493  dB[Do,M,M] = sum_n dv[n,d] kfu kfu^T */
 size_t gpb_det_syrk_ws_bytes(int n, int M, int Do);
 int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, int Do,

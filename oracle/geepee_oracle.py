@@ -28,6 +28,8 @@ import numpy as np
 
 JITTER = 1e-5            # config.py:11
 PROP_MM = 'MM'           # config.py:13
+PROP_MC = 'MC'           # config.py:15
+MC_NO_SAMPLES = 5        # config.py:16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CLIB = None
@@ -282,6 +284,58 @@ class Layer(object):
         vout = np.exp(2.0 * self.sf) + np.einsum('dab,nab->nd', B, psi2) - mout**2
         return mout, vout, psi1, psi2
 
+    # ---- Monte-Carlo propagation: aep_models.py:160-180, base_models.py:309-332 ----
+    def prop_mc(self, mx, vx, cav=True, K=None):
+        """Samples x = mx + sqrt(vx) eps with eps from the GLOBAL numpy RNG, exactly as the
+        reference draws it; returns 3-D (m, v) and the stacked intermediates."""
+        K = MC_NO_SAMPLES if K is None else K
+        n = mx.shape[0]
+        eps = np.random.randn(K, n, self.Din)
+        x = eps * np.sqrt(vx) + mx
+        xs = x.reshape(K * n, self.Din)
+        ms, vs, kfus = self.prop_det(xs, cav=cav)
+        return ms.reshape(K, n, self.Dout), vs.reshape(K, n, self.Dout), (ms, vs, kfus, xs, eps)
+
+    @staticmethod
+    def reparam(dx, v, eps):
+        """base_models.py:373-388 backprop_grads_reparam."""
+        dx = dx.reshape(eps.shape)
+        return {'mx': np.sum(dx, axis=0), 'vx': np.sum(dx * eps, axis=0) / (2 * np.sqrt(v))}
+
+    def aep_grads_mc(self, m, v, dm, dv, kfu, x, alpha):
+        """aep_models.py:307-410 backprop_grads_lvm_mc (stacked samples; natural parameters)."""
+        N, Ki = self.N, self.Kuuinv
+        ls, sf2 = np.exp(self.ls), np.exp(2 * self.sf)
+        dm, dv = dm.reshape(m.shape), dv.reshape(v.shape)
+        beta = (N - alpha) * 1.0 / N
+        s_post, s_cav = N * 1.0 / alpha - 1.0, -N * 1.0 / alpha
+        dkfu = np.einsum('nd,dm->nm', dm, self.Ahat) + 2 * np.einsum('nd,dab,na->nb', dv, self.Bhat_det, kfu)
+        dsf2, dls, dzu, dx = kfu_derivs(dkfu, kfu, ls, sf2, x, self.zu, grad_x=True)
+        kK = kfu.dot(Ki)
+        SK = np.einsum('dab,nb->nda', self.Suhat, kK)
+        dSinv = -np.einsum('nda,nd,ndb->dab', SK, dv, SK) - np.einsum('nda,nd,db->dab', SK, dm, self.muhat)
+        dtheta1 = beta * dSinv - 0.5 * s_post * self.Spmm - 0.5 * s_cav * beta * self.Spmmhat
+        dtheta2 = beta * np.einsum('nda,nd->da', SK, dm) + s_post * self.mu + s_cav * beta * self.muhat
+        dA = np.einsum('nd,nm->dm', dm, kfu)
+        dB = np.einsum('nd,na,nb->dab', dv, kfu, kfu)
+        KS = np.einsum('ab,dbc->dac', Ki, self.Suhat)
+        dKi = np.einsum('da,db->ab', dA, self.muhat) + 2 * np.einsum('dab,dac->bc', KS, dB) \
+            - np.sum(dB, axis=0) + np.sum(dSinv, axis=0)
+        Minner = s_post * np.sum(self.Spmm, axis=0) + s_cav * np.sum(self.Spmmhat, axis=0) - 2.0 * dKi
+        M_all = 0.5 * (self.Dout * Ki + Ki.dot(Minner).dot(Ki))
+        dsf, dls, dzu = self._kernel_hyper_tail(dsf2, dls, dzu, np.sum(dv), M_all)
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': _triu_pack_grad(self.R, dtheta1),
+                'eta2': dtheta2}, dx
+
+    def vfe_grads_mc(self, m, v, dm, dv, kfu, x):
+        """vfe_models.py:405-476 backprop_grads_lvm_mc: the deterministic-input chain rules
+        (vfe_grads_det) on the stacked samples + the gradient wrt the samples."""
+        dm, dv = dm.reshape(m.shape), dv.reshape(v.shape)
+        g = self.vfe_grads_det(m, v, dm, dv, kfu, x)
+        dkfu = np.einsum('nd,dm->nm', dm, self.A) + 2 * np.einsum('nd,dab,na->nb', dv, self.B_det, kfu)
+        dx = kfu_derivs(dkfu, kfu, np.exp(self.ls), np.exp(2 * self.sf), x, self.zu, grad_x=True)[3]
+        return g, dx
+
     # ---- log-partitions: aep_models.py:62-114 ----------------------------
     def phi(self, alpha):
         N = self.N
@@ -465,6 +519,26 @@ def gauss_log_Z(sn, mout, vout, y, alpha):
     dm = (y - mout) / v
     dv = -0.5 / v + 0.5 * (y - mout)**2 / v**2
     return logZ, dm, dv
+
+
+def gauss_log_Z_mc(sn, mout, vout, y, alpha):
+    """lik_layers.py:134-150: 3-D branch (samples on axis 0), log-mean-exp over the samples."""
+    sn2 = np.exp(2.0 * sn)
+    vout = vout + sn2 / alpha
+    lz = -0.5 * (np.log(2 * np.pi * vout) + (y - mout)**2 / vout)
+    lz = lz + (0.5 * np.log(2 * np.pi * sn2 / alpha) - 0.5 * alpha * np.log(2 * np.pi * sn2))
+    lmax = np.max(lz, axis=0)
+    ex = np.exp(lz - lmax)
+    se = np.sum(ex, axis=0)
+    logZ = np.sum(lmax + np.log(se) - np.log(mout.shape[0]))
+    w = ex / se
+    return logZ, w * (y - mout) / vout, w * (-0.5 / vout + 0.5 * (y - mout)**2 / vout**2)
+
+
+def gauss_dsn_mc(sn, mout, dv, alpha, scale):
+    """lik_layers.py:154-181 backprop_grads, 3-D branch (dim_prod = batch x D)."""
+    sn2 = np.exp(2.0 * sn)
+    return scale * (np.sum(dv) * 2 * sn2 / alpha + mout.shape[1] * mout.shape[2] * (1 - alpha))
 
 
 def gauss_dsn(sn, mout, dv, alpha, scale):
@@ -836,10 +910,18 @@ class AepSGPLVM(object):
         c2 = self.prior_x2 + (1.0 - alpha) * f2[idx]
         mcav, vcav = c1 / c2, 1.0 / c2
         mpost, vpost = post1[idx] / post2[idx], 1.0 / post2[idx]
-        m, v, psi1, psi2 = L.prop_mm(mcav, vcav)
         gl = {}
-        logZ, dm, dv = lik_log_Z(self.lik, params, m, v, yb, alpha, scale, gl)
-        g, gin = L.aep_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mcav, vcav, alpha)
+        if prop_mode == PROP_MC:                            # aep_models.py:745-761
+            assert self.lik == 'Gaussian'
+            m, v, (ms, vs, kfus, xs, eps) = L.prop_mc(mcav, vcav)
+            logZ, dm, dv = gauss_log_Z_mc(sn, m, v, yb, alpha)
+            gl['sn'] = gauss_dsn_mc(sn, m, dv, alpha, scale)
+            g, dx = L.aep_grads_mc(ms, vs, scale * dm, scale * dv, kfus, xs, alpha)
+            gin = L.reparam(dx, vcav, eps)
+        else:
+            m, v, psi1, psi2 = L.prop_mm(mcav, vcav)
+            logZ, dm, dv = lik_log_Z(self.lik, params, m, v, yb, alpha, scale, gl)
+            g, gin = L.aep_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mcav, vcav, alpha)
         g.update(gl)
         # aep_models.py:785-801
         phi_prior, _, _ = _phi_x(self.prior_mean, self.prior_var)
@@ -901,10 +983,21 @@ class VfeSGPLVM(object):
         else:
             post1, post2 = f1 / f2, 1.0 / f2
         mx, vx = post1[idx] / post2[idx], 1.0 / post2[idx]
-        m, v, psi1, psi2 = L.prop_mm(mx, vx, cav=False)
         gl = {}
-        ll, dm, dv = lik_log_lik_exp(self.lik, params, m, v, yb, scale, gl)
-        g, gin = L.vfe_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mx, vx)
+        if prop_mode == PROP_MC:                            # vfe_models.py:793-808
+            assert self.lik == 'Gaussian'
+            m, v, (ms, vs, kfus, xs, eps) = L.prop_mc(mx, vx, cav=False)
+            K = m.shape[0]
+            sn2 = np.exp(2.0 * sn)                          # lik_layers.py:209-216, 229-234
+            ll = np.sum(np.mean(-0.5 * np.log(2 * np.pi * sn2) - 0.5 * ((yb - m)**2 + v) / sn2, axis=0))
+            dm, dv = (yb - m) / sn2 / K, -0.5 / sn2 * np.ones_like(v) / K
+            gl['sn'] = scale * np.sum(-1 + ((yb - m)**2 + v) / sn2) / K
+            g, dx = L.vfe_grads_mc(ms, vs, scale * dm, scale * dv, kfus, xs)
+            gin = L.reparam(dx, vx, eps)
+        else:
+            m, v, psi1, psi2 = L.prop_mm(mx, vx, cav=False)
+            ll, dm, dv = lik_log_lik_exp(self.lik, params, m, v, yb, scale, gl)
+            g, gin = L.vfe_grads_mm(m, v, scale * dm, scale * dv, psi1, psi2, mx, vx)
         g.update(gl)
         m0, v0 = self.prior_mean, self.prior_var            # vfe_models.py:857-863
         klx = np.sum(0.5 * (np.log(v0) - np.log(vx) + (vx + (mx - m0)**2) / v0 - 1))

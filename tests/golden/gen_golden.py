@@ -64,7 +64,7 @@ def quiet(fn, *a, **k):
 FLOORS = {}
 
 
-def run(model, params, mb, alpha, seed=None):
+def run(model, params, mb, alpha, seed=None, prop_mode=None):
     """Evaluate the reference; also estimate its own conditioning floor: how much
     each output moves when every parameter is perturbed by ~1e-15 relative (three
     draws).  Parity cannot be tighter than that, whatever the implementation."""
@@ -72,7 +72,8 @@ def run(model, params, mb, alpha, seed=None):
     p = copy.deepcopy(params)
     if seed is not None:
         np.random.seed(seed)
-    e, g = model.objective_function(p, mb, alpha=alpha)
+    kw = {} if prop_mode is None else {'prop_mode': prop_mode}
+    e, g = model.objective_function(p, mb, alpha=alpha, **kw)
     e = np.array(e, dtype=np.float64).copy()
     g = {k: np.array(v, dtype=np.float64).copy() for k, v in g.items()}
     rng = np.random.RandomState(999)
@@ -83,7 +84,7 @@ def run(model, params, mb, alpha, seed=None):
              for k, v in params.items()}
         if seed is not None:
             np.random.seed(seed)
-        e2, g2 = model.objective_function(q, mb, alpha=alpha)
+        e2, g2 = model.objective_function(q, mb, alpha=alpha, **kw)
         floor['energy'] = max(floor['energy'], float(np.max(np.abs(e2 - e)) / np.max(np.abs(e))))
         for k in g:
             sc = max(np.max(np.abs(g[k])), 1e-300)
@@ -169,7 +170,7 @@ def lvm_params(model, y, rng):
     return p
 
 
-def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2, lk='Gaussian'):
+def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2, lk='Gaussian', prop_mode=None):
     rng = np.random.RandomState(seed)
     y = rng.standard_normal((N, Do))
     if lk == 'Probit':       # tests/test_grads_aep.py:33-40
@@ -179,10 +180,12 @@ def case_sgplvm(name, cls, N, M, Q, Do, alpha, nat=True, mb=None, seed=2, lk='Ga
     model._gold_lik = lk
     params = lvm_params(model, y, rng)
     mbs = N if mb is None else mb
-    e, g = run(model, params, mbs, alpha, seed=123)
-    save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPLVM', N=N, M=M, Q=Q, Do=Do,
-                    alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123, lik=lk),
-         {'y': y}, params, e, g)
+    e, g = run(model, params, mbs, alpha, seed=123, prop_mode=prop_mode)
+    meta = dict(model=cls.__module__.split('.')[-1] + '.SGPLVM', N=N, M=M, Q=Q, Do=Do,
+                alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123, lik=lk)
+    if prop_mode is not None:
+        meta['prop_mode'] = prop_mode
+    save(name, meta, {'y': y}, params, e, g)
 
 
 def ssm_params(model, y, rng, gp_emi):
@@ -332,9 +335,20 @@ def sdgprh_cases():
     case_sdgprh('aep_sdgprh_probit', 8, 4, 2, [3, 2], 3, 0.3, seed=63, lk='Probit', init_recipe=False)
 
 
+def mc_cases():
+    """Monte-Carlo propagation (config.PROP_MC): eps comes from the global numpy RNG, which the
+    harness re-seeds before every evaluation (as tests/test_utils.py:70-72 does for stochastic runs)."""
+    case_sgplvm('aep_sgplvm_mc', aep.SGPLVM, 10, 5, 3, 2, 0.5, seed=70, prop_mode='MC')
+    case_sgplvm('aep_sgplvm_mc_minibatch', aep.SGPLVM, 12, 6, 2, 3, 0.8, mb=5, seed=71, prop_mode='MC')
+    case_sgplvm('vfe_sgplvm_mc', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=72, prop_mode='MC')
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'probit':   # only the files added with the probit layer
         probit_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'mc':
+        mc_cases()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sdgprh':   # only the files added with SDGPR_H
         sdgprh_cases()
@@ -375,3 +389,4 @@ if __name__ == '__main__':
     case_emis()
     probit_cases()
     sdgprh_cases()
+    mc_cases()

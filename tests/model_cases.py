@@ -39,7 +39,8 @@ def check_model(name, prec, tol, device=None):
     model = build_model(gold, prec, device)
     m = gold['meta']
     np.random.seed(m['rng_seed'])
-    e, g = model.objective_function(copy.deepcopy(gold['p']), m['mb_size'], alpha=m['alpha'])
+    e, g = model.objective_function(copy.deepcopy(gold['p']), m['mb_size'], alpha=m['alpha'],
+                                    prop_mode=m.get('prop_mode', 'MM'))
     gu.assert_close(e, g, gold, tol, '%s[%s]' % (name, prec))
     return model, gold
 

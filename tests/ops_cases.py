@@ -60,6 +60,10 @@ def check_det_layer(n, M, D, Do, prec, tol):
     assert gu.rel_err(N(dzu), r_z) < tol
     assert gu.rel_err(N(dl), r_l) < tol
     assert gu.rel_err(N(dsf2), np.ravel(r_var)) < tol
+    # input gradient (Monte-Carlo propagation; kernels.py:393-395 kfucompDer grad_x=True)
+    dx = ops.det_dx(pr, x, z, ls, opnd, dm, dv, Ks, Ts)
+    r_x = go.kfu_derivs(dkfu, kfu, np.exp(p['ls']), np.exp(2 * p['sf']), p['x'], p['z'], grad_x=True)[3]
+    assert gu.rel_err(N(dx), r_x) < tol
 
 
 MM_SHAPES = [(9, 6, 3, 2), (40, 5, 2, 1), (21, 50, 1, 4), (13, 12, 5, 3), (11, 7, 7, 2), (10, 9, 4, 6),

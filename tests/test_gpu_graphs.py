@@ -13,7 +13,8 @@ import model_cases as mc
 pytestmark = pytest.mark.gpu
 
 CASES = ['aep_sgpr', 'aep_sgpr_cfg1', 'aep_sgpr_nonnat', 'aep_sdgpr', 'aep_sgplvm', 'aep_sgpssm_lin',
-         'aep_sgpssm_gp', 'vfe_sgpr', 'vfe_sgplvm', 'vfe_sgpssm_lin', 'aep_sgpr_probit', 'aep_sdgprh_moderate']
+         'aep_sgpssm_gp', 'vfe_sgpr', 'vfe_sgplvm', 'vfe_sgpssm_lin', 'aep_sgpr_probit', 'aep_sdgprh_moderate',
+         'aep_sgplvm_mc', 'vfe_sgplvm_mc']
 
 
 @pytest.fixture(scope='module', autouse=True)
@@ -43,7 +44,8 @@ def _perturbed(p, seed):
 def _call(model, gold, p):
     m = gold['meta']
     np.random.seed(m['rng_seed'])
-    return model.objective_function(copy.deepcopy(p), m['mb_size'], alpha=m['alpha'])
+    return model.objective_function(copy.deepcopy(p), m['mb_size'], alpha=m['alpha'],
+                                    prop_mode=m.get('prop_mode', 'MM'))
 
 
 @pytest.mark.parametrize('name', CASES)

@@ -18,7 +18,8 @@ def test_models_match_reference(name):
     model = gu.build_oracle_model(gold)
     m = gold['meta']
     np.random.seed(m['rng_seed'])
-    e, g = model.objective_function(copy.deepcopy(gold['p']), m['mb_size'], alpha=m['alpha'])
+    e, g = model.objective_function(copy.deepcopy(gold['p']), m['mb_size'], alpha=m['alpha'],
+                                    prop_mode=m.get('prop_mode', 'MM'))
     gu.assert_close(e, g, gold, TOL, name)
 
 
