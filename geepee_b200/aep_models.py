@@ -441,12 +441,17 @@ class SGPSSM(Base_SGPSSM):
                                        prec, self.device)
 
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
-        _check_mode(prop_mode)
+        _check_mode(prop_mode, mc_ok=True)
         N, Q, dev = self.N, self.Din, self.device
         dyn, emi = self.dyn_layer, self.emi_layer
         start, end = self._window(mb_size)
         n_emi = end - start
         n_dyn = n_emi - 1
+        mc = prop_mode == PROP_MC
+        # Monte-Carlo propagation: the reference draws eps inside the transition forward, then inside
+        # the emission forward (aep_models.py:1116, 1129) -- same order here
+        eps_dyn = _mc_eps(n_dyn, Q + self.Dcon_dyn, dev) if mc else None
+        eps_emi = _mc_eps(n_emi, Q + self.Dcon_emi, dev) if (mc and self.gp_emi) else None
         s_dyn = -(N - 1) * 1.0 / n_dyn / alpha
         s_emi = -N * 1.0 / n_emi / alpha
         dyn._fuse_cavity_alpha = alpha
@@ -476,16 +481,30 @@ class SGPSSM(Base_SGPSSM):
         if t1 > t0:
             mtm1, vtm1 = self._with_control(cav_m[t0:t1], cav_v[t0:t1], t0, t1, self.Dcon_dyn)
             mt, vt = cav_m[t0 + 1:t1 + 1], cav_v[t0 + 1:t1 + 1]
-            mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=True)
+            if mc:
+                mp, vp, ctx = dyn._fwd_mc(mtm1.contiguous(), vtm1.contiguous(), eps_dyn, cav=True)
+            else:
+                mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=True)
             vsum = vt + vp + sn2 / alpha
             md = mt - mp
             lz = -0.5 * md**2 / vsum - 0.5 * torch.log(1 + alpha * (vt + vp) / sn2) \
                 - 0.5 * alpha * torch.log(2 * np.pi * sn2)
-            dvt = s_dyn * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
-            dmt = s_dyn * (-md / vsum)
-            add['logZ_dyn'] = (s_dyn * lz.sum()).reshape(1)
+            if mc:      # 3-D branch of compute_transition_tilted (aep_models.py:1349-1369)
+                lmax = lz.max(dim=0).values
+                ex = torch.exp(lz - lmax)
+                se = ex.sum(0)
+                add['logZ_dyn'] = (s_dyn * (lmax + torch.log(se) - np.log(mp.shape[0])).sum()).reshape(1)
+                w = s_dyn * ex / se
+                dmp = w * md / vsum
+                dvp = w * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+                dmt, dvt = -dmp.sum(0), dvp.sum(0)
+                st = dyn._bwd_mc(ctx, dmp, dvp)
+            else:
+                dvt = s_dyn * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+                dmt = s_dyn * (-md / vsum)
+                add['logZ_dyn'] = (s_dyn * lz.sum()).reshape(1)
+                st = dyn._bwd_mm(ctx, (-dmt).contiguous(), dvt.contiguous())
             add['dsn'] = (dvt.sum() * 2 * sn2 / alpha + s_dyn * (t1 - t0) * Q * (1 - alpha)).reshape(1)
-            st = dyn._bwd_mm(ctx, (-dmt).contiguous(), dvt.contiguous())
             _add_stats(add, 'd_', st)
             push(t0 + 1, t1 + 1, dmt, dvt)                                   # "prev" source
             push(t0, t1, st['dmx'][:, :Q], st['dvx'][:, :Q])                 # "next" source
@@ -499,9 +518,14 @@ class SGPSSM(Base_SGPSSM):
             mup, vup = self._with_control(cav_m[e0:e1], cav_v[e0:e1], e0, e1, self.Dcon_emi)
             yb = self._y[e0:e1]
             if self.gp_emi:
-                mo, vo, ctx = emi._fwd_mm(mup, vup, cav=True)
-                dme, dve, lZe, dsn_e = self.lik_layer._log_Z(mo, vo, yb, alpha, s_emi)
-                ste = emi._bwd_mm(ctx, dme, dve)
+                if mc:      # aep_models.py:1127-1145
+                    mo, vo, ctx = emi._fwd_mc(mup.contiguous(), vup.contiguous(), eps_emi, cav=True)
+                    dme, dve, lZe, dsn_e = self.lik_layer._log_Z_mc(mo, vo, yb, alpha, s_emi)
+                    ste = emi._bwd_mc(ctx, dme, dve)
+                else:
+                    mo, vo, ctx = emi._fwd_mm(mup, vup, cav=True)
+                    dme, dve, lZe, dsn_e = self.lik_layer._log_Z(mo, vo, yb, alpha, s_emi)
+                    ste = emi._bwd_mm(ctx, dme, dve)
                 _add_stats(add, 'e_', ste)
                 add['logZ_emi'] = (s_emi * lZe).reshape(1)
                 add['dsn_emission'] = dsn_e.reshape(1)
@@ -523,10 +547,10 @@ class SGPSSM(Base_SGPSSM):
 
         # ---- replicated tail ----------------------------------------------------------------
         grads = {'sn': add['dsn'].reshape(tuple(np.shape(self.sn)))}
-        for k, val in dyn._tail_mm(_get_stats(add, 'd_'), alpha).items():
+        for k, val in (dyn._tail_mc if mc else dyn._tail_mm)(_get_stats(add, 'd_'), alpha).items():
             grads[k + '_dynamic'] = val
         if self.gp_emi:
-            for k, val in emi._tail_mm(_get_stats(add, 'e_'), alpha).items():
+            for k, val in (emi._tail_mc if mc else emi._tail_mm)(_get_stats(add, 'e_'), alpha).items():
                 grads[k + '_emission'] = val
             grads['sn_emission'] = add['dsn_emission'].reshape(())
         else:

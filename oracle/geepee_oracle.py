@@ -1094,21 +1094,46 @@ class AepSGPSSM(_SSMBase):
         mt, vt = cav_m[dyn_idx + 1], cav_v[dyn_idx + 1]
         mtm1, vtm1 = self._with_control(cav_m[dyn_idx], cav_v[dyn_idx], dyn_idx, self.Dcon_dyn)
         mup, vup = self._with_control(cav_m[emi_idx], cav_v[emi_idx], emi_idx, self.Dcon_emi)
-        # transition factors (aep_models.py:1092-1098, 1317-1374)
-        mp, vp, psi1, psi2 = self.dyn.prop_mm(mtm1, vtm1)
+        # transition factors (aep_models.py:1092-1098 / 1114-1126, 1317-1374)
+        mc = prop_mode == PROP_MC
         sn2 = np.exp(2 * self.sn)
+        if mc:
+            mp, vp, (ms, vs, kfus, xs, eps) = self.dyn.prop_mc(mtm1, vtm1)
+        else:
+            mp, vp, psi1, psi2 = self.dyn.prop_mm(mtm1, vtm1)
         vsum = vt + vp + sn2 / alpha
         md = mt - mp
         lz = -0.5 * md**2 / vsum - 0.5 * np.log(1 + alpha * (vt + vp) / sn2) \
             - 0.5 * alpha * np.log(2 * np.pi * sn2)
-        logZ_dyn = s_dyn * np.sum(lz)
-        dvt = s_dyn * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
-        dmt = s_dyn * (-md / vsum)
-        dsn = np.sum(dvt) * 2 * sn2 / alpha + s_dyn * mp.shape[0] * Q * (1 - alpha)
-        gdyn, gin_dyn = self.dyn.aep_grads_mm(mp, vp, -dmt, dvt, psi1, psi2, mtm1, vtm1, alpha)
+        if mc:                                               # 3-D branch, 1349-1369
+            lmax = np.max(lz, axis=0)
+            ex = np.exp(lz - lmax)
+            se = np.sum(ex, axis=0)
+            logZ_dyn = s_dyn * np.sum(lmax + np.log(se) - np.log(mp.shape[0]))
+            w = s_dyn * ex / se
+            dmp = w * md / vsum
+            dvp = w * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+            dmt, dvt = -np.sum(dmp, axis=0), np.sum(dvp, axis=0)
+            dsn = np.sum(dvp) * 2 * sn2 / alpha + s_dyn * mp.shape[1] * Q * (1 - alpha)
+            gdyn, dx = self.dyn.aep_grads_mc(ms, vs, dmp, dvp, kfus, xs, alpha)
+            gin_dyn = self.dyn.reparam(dx, vtm1, eps)
+        else:
+            logZ_dyn = s_dyn * np.sum(lz)
+            dvt = s_dyn * (-0.5 / vsum + 0.5 * md**2 / vsum**2)
+            dmt = s_dyn * (-md / vsum)
+            dsn = np.sum(dvt) * 2 * sn2 / alpha + s_dyn * mp.shape[0] * Q * (1 - alpha)
+            gdyn, gin_dyn = self.dyn.aep_grads_mm(mp, vp, -dmt, dvt, psi1, psi2, mtm1, vtm1, alpha)
         g = {'sn': dsn}
         # emission factors
-        if self.gp_emi:
+        if self.gp_emi and mc:                               # aep_models.py:1127-1145
+            sn_e = params['sn_emission']
+            mo, vo, (ms, vs, kfus, xs, eps) = self.emi.prop_mc(mup, vup)
+            lZe, dme, dve = gauss_log_Z_mc(sn_e, mo, vo, yb, alpha)
+            logZ_emi = s_emi * lZe
+            gemi, dx = self.emi.aep_grads_mc(ms, vs, s_emi * dme, s_emi * dve, kfus, xs, alpha)
+            gin_emi = self.emi.reparam(dx, vup, eps)
+            g['sn_emission'] = gauss_dsn_mc(sn_e, mo, dve, alpha, s_emi)
+        elif self.gp_emi:
             sn_e = params['sn_emission']
             mo, vo, q1, q2 = self.emi.prop_mm(mup, vup)
             lZe, dme, dve = gauss_log_Z(sn_e, mo, vo, yb, alpha)

@@ -217,7 +217,8 @@ def ssm_params(model, y, rng, gp_emi):
     return p
 
 
-def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True, mb=None, seed=3):
+def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True, mb=None, seed=3,
+                prop_mode=None):
     rng = np.random.RandomState(seed)
     y = np.cumsum(0.3 * rng.standard_normal((N, Do)), axis=0)
     xc = rng.standard_normal((N, control)) if control else None
@@ -228,14 +229,16 @@ def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True
         model = cls(y, Q, M, lik='Gaussian', x_control=xc, gp_emi=gp_emi, nat_param=nat)
     params = ssm_params(model, y, rng, gp_emi)
     mbs = N if mb is None else mb
-    e, g = run(model, params, mbs, alpha, seed=123)
+    e, g = run(model, params, mbs, alpha, seed=123, prop_mode=prop_mode)
     inputs = {'y': y}
     if control:
         inputs['x_control'] = xc
-    save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPSSM', N=N, M=M, Q=Q, Do=Do,
-                    alpha=alpha, gp_emi=gp_emi, control=control, nat_param=nat, mb_size=mbs,
-                    rng_seed=123),
-         inputs, params, e, g)
+    meta = dict(model=cls.__module__.split('.')[-1] + '.SGPSSM', N=N, M=M, Q=Q, Do=Do,
+                alpha=alpha, gp_emi=gp_emi, control=control, nat_param=nat, mb_size=mbs,
+                rng_seed=123)
+    if prop_mode is not None:
+        meta['prop_mode'] = prop_mode
+    save(name, meta, inputs, params, e, g)
 
 
 def case_kernels(seed=4):
@@ -341,6 +344,9 @@ def mc_cases():
     case_sgplvm('aep_sgplvm_mc', aep.SGPLVM, 10, 5, 3, 2, 0.5, seed=70, prop_mode='MC')
     case_sgplvm('aep_sgplvm_mc_minibatch', aep.SGPLVM, 12, 6, 2, 3, 0.8, mb=5, seed=71, prop_mode='MC')
     case_sgplvm('vfe_sgplvm_mc', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=72, prop_mode='MC')
+    case_sgpssm('aep_sgpssm_lin_mc', aep.SGPSSM, 20, 4, 2, 2, 0.5, seed=73, prop_mode='MC')
+    case_sgpssm('aep_sgpssm_gp_mc', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=74, prop_mode='MC')
+    case_sgpssm('aep_sgpssm_control_mc', aep.SGPSSM, 12, 4, 2, 2, 0.7, control=1, mb=7, seed=75, prop_mode='MC')
 
 
 if __name__ == '__main__':

@@ -46,7 +46,8 @@ def _worker(rank, world, port, names, q):
 @pytest.mark.parametrize('names', [
     ['aep_sgpr', 'aep_sgpr_minibatch', 'aep_sdgpr', 'vfe_sgpr', 'aep_sdgprh', 'aep_sdgprh_alpha_one'],
     ['aep_sgplvm', 'aep_sgplvm_minibatch', 'aep_sgpssm_lin', 'aep_sgpssm_lin_window', 'aep_sgpssm_gp',
-     'vfe_sgplvm', 'vfe_sgpssm_lin', 'aep_sgplvm_mc', 'aep_sgplvm_mc_minibatch', 'vfe_sgplvm_mc'],
+     'vfe_sgplvm', 'vfe_sgpssm_lin', 'aep_sgplvm_mc', 'aep_sgplvm_mc_minibatch', 'vfe_sgplvm_mc', 'aep_sgpssm_lin_mc',
+     'aep_sgpssm_gp_mc', 'aep_sgpssm_control_mc'],
 ])
 def test_two_ranks_match_golden(names):
     import emu_util
