@@ -123,11 +123,14 @@ class SGPSSM(Base_SGPSSM):
                                        prec, self.device)
 
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode=PROP_MM):
-        _check_mode(prop_mode)
+        _check_mode(prop_mode, mc_ok=True)
         N, Q, dev = self.N, self.Din, self.device
         dyn, emi = self.dyn_layer, self.emi_layer
         start, end = self._window(mb_size)
         nb = end - start
+        mc = prop_mode == PROP_MC       # eps in the reference's draw order (vfe_models.py:985, 998)
+        eps_dyn = _mc_eps(nb - 1, Q + self.Dcon_dyn, dev) if mc else None
+        eps_emi = _mc_eps(nb, Q + self.Dcon_emi, dev) if (mc and self.gp_emi) else None
         s_dyn = -(N - 1) * 1.0 / (nb - 1)
         s_emi = -N * 1.0 / nb
         s_ent = -N * 1.0 / nb
@@ -142,13 +145,23 @@ class SGPSSM(Base_SGPSSM):
         if t1 > t0:
             mtm1, vtm1 = self._with_control(pm[t0:t1], pv[t0:t1], t0, t1, self.Dcon_dyn)
             mt, vt = pm[t0 + 1:t1 + 1], pv[t0 + 1:t1 + 1]
-            mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=False)
+            if mc:
+                mp, vp, ctx = dyn._fwd_mc(mtm1.contiguous(), vtm1.contiguous(), eps_dyn, cav=False)
+            else:
+                mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=False)
+            K = mp.shape[0] if mc else 1        # 3-D branch: sample average (vfe_models.py:1094-1104)
             t2 = -0.5 / sn2 * (mt**2 + vt - 2 * mt * mp + mp**2 + vp)
-            add['logZ_dyn'] = (s_dyn * (-0.5 * torch.log(2 * np.pi * sn2) * t2.numel() + t2.sum())).reshape(1)
-            dmt = -s_dyn / sn2 * (mt - mp)
-            dvt = -s_dyn * 0.5 / sn2 * torch.ones_like(vt)
-            add['dsn'] = (s_dyn * (-1 - 2 * t2).sum()).reshape(1)
-            st = dyn._bwd_mm(ctx, (-dmt).contiguous(), dvt.contiguous())
+            add['logZ_dyn'] = (s_dyn * (-0.5 * torch.log(2 * np.pi * sn2) * t2.numel() + t2.sum()) / K).reshape(1)
+            add['dsn'] = (s_dyn * (-1 - 2 * t2).sum() / K).reshape(1)
+            if mc:
+                dmp = s_dyn / sn2 * (mt - mp) / K
+                dvp = -s_dyn * 0.5 / sn2 * torch.ones_like(vp) / K
+                dmt, dvt = -dmp.sum(0), dvp.sum(0)
+                st = dyn._bwd_mc(ctx, dmp, dvp)
+            else:
+                dmt = -s_dyn / sn2 * (mt - mp)
+                dvt = -s_dyn * 0.5 / sn2 * torch.ones_like(vt)
+                st = dyn._bwd_mm(ctx, (-dmt).contiguous(), dvt.contiguous())
             _add_stats(add, 'd_', st)
             add['dm'][t0 + 1:t1 + 1] += dmt
             add['dv'][t0 + 1:t1 + 1] += dvt
@@ -163,7 +176,18 @@ class SGPSSM(Base_SGPSSM):
         if e1 > e0:
             mup, vup = self._with_control(pm[e0:e1], pv[e0:e1], e0, e1, self.Dcon_emi)
             yb = self._y[e0:e1]
-            if self.gp_emi:
+            if self.gp_emi and mc:      # vfe_models.py:996-1010
+                K = eps_emi.shape[0]
+                mo, vo, ctx = emi._fwd_mc(mup.contiguous(), vup.contiguous(), eps_emi, cav=False)
+                dme, dve, lle, dsn_e = self.lik_layer._log_lik_exp(
+                    mo.reshape(-1, self.Dout), vo.reshape(-1, self.Dout), yb.repeat(K, 1), s_emi / K)
+                lle = lle / K
+                ste = emi._bwd_mc(ctx, dme, dve)
+                _add_stats(add, 'e_', ste)
+                add['logZ_emi'] = (s_emi * lle).reshape(1)
+                add['dsn_emission'] = dsn_e.reshape(1)
+                dmx, dvx = ste['dmx'], ste['dvx']
+            elif self.gp_emi:
                 mo, vo, ctx = emi._fwd_mm(mup, vup, cav=False)
                 dme, dve, lle, dsn_e = self.lik_layer._log_lik_exp(mo, vo, yb, s_emi)
                 ste = emi._bwd_mm(ctx, dme, dve)
@@ -189,10 +213,10 @@ class SGPSSM(Base_SGPSSM):
         add = dist.allreduce_dict(add)
 
         grads = {'sn': add['dsn'].reshape(tuple(np.shape(self.sn)))}
-        for k, val in dyn._tail(_get_stats(add, 'd_'), True).items():
+        for k, val in dyn._tail(_get_stats(add, 'd_'), not mc).items():
             grads[k + '_dynamic'] = val
         if self.gp_emi:
-            for k, val in emi._tail(_get_stats(add, 'e_'), True).items():
+            for k, val in emi._tail(_get_stats(add, 'e_'), not mc).items():
                 grads[k + '_emission'] = val
             grads['sn_emission'] = add['dsn_emission'].reshape(())
         else:

@@ -1210,16 +1210,40 @@ class VfeSGPSSM(_SSMBase):
         mt, vt = pm[1:], pv[1:]
         mtm1, vtm1 = self._with_control(pm[:-1], pv[:-1], dyn_idx, self.Dcon_dyn)
         mup, vup = self._with_control(pm, pv, emi_idx, self.Dcon_emi)
-        mp, vp, psi1, psi2 = self.dyn.prop_mm(mtm1, vtm1, cav=False)
-        sn2 = np.exp(2 * self.sn)                           # vfe_models.py:1080-1092
-        t2 = -0.5 / sn2 * (mt**2 + vt - 2 * mt * mp + mp**2 + vp)
-        logZ_dyn = s_dyn * np.sum(-0.5 * np.log(2 * np.pi * sn2) + t2)
-        dmt = -s_dyn / sn2 * (mt - mp)
-        dvt = -s_dyn * 0.5 / sn2 * np.ones_like(vt)
-        dsn = s_dyn * np.sum(-1 - 2 * t2)
-        gdyn, gin_dyn = self.dyn.vfe_grads_mm(mp, vp, -dmt, dvt, psi1, psi2, mtm1, vtm1)
+        mc = prop_mode == PROP_MC
+        sn2 = np.exp(2 * self.sn)                           # vfe_models.py:1080-1108
+        if mc:                                              # vfe_models.py:983-995, 3-D branch 1094-1104
+            mp, vp, (ms, vs, kfus, xs, eps) = self.dyn.prop_mc(mtm1, vtm1, cav=False)
+            K = mp.shape[0]
+            t2 = -0.5 / sn2 * (mt**2 + vt - 2 * mt * mp + mp**2 + vp)
+            logZ_dyn = s_dyn * np.sum(-0.5 * np.log(2 * np.pi * sn2) + t2) / K
+            dmp = s_dyn / sn2 * (mt - mp) / K
+            dvp = -s_dyn * 0.5 / sn2 * np.ones_like(vp) / K
+            dmt, dvt = -np.sum(dmp, axis=0), np.sum(dvp, axis=0)
+            dsn = s_dyn * np.sum(-1 - 2 * t2) / K
+            gdyn, dx = self.dyn.vfe_grads_mc(ms, vs, dmp, dvp, kfus, xs)
+            gin_dyn = self.dyn.reparam(dx, vtm1, eps)
+        else:
+            mp, vp, psi1, psi2 = self.dyn.prop_mm(mtm1, vtm1, cav=False)
+            t2 = -0.5 / sn2 * (mt**2 + vt - 2 * mt * mp + mp**2 + vp)
+            logZ_dyn = s_dyn * np.sum(-0.5 * np.log(2 * np.pi * sn2) + t2)
+            dmt = -s_dyn / sn2 * (mt - mp)
+            dvt = -s_dyn * 0.5 / sn2 * np.ones_like(vt)
+            dsn = s_dyn * np.sum(-1 - 2 * t2)
+            gdyn, gin_dyn = self.dyn.vfe_grads_mm(mp, vp, -dmt, dvt, psi1, psi2, mtm1, vtm1)
         g = {'sn': dsn}
-        if self.gp_emi:
+        if self.gp_emi and mc:                              # vfe_models.py:996-1010
+            sn_e = params['sn_emission']
+            mo, vo, (ms, vs, kfus, xs, eps) = self.emi.prop_mc(mup, vup, cav=False)
+            K = mo.shape[0]
+            sn2e = np.exp(2.0 * sn_e)
+            lle = np.sum(np.mean(-0.5 * np.log(2 * np.pi * sn2e) - 0.5 * ((yb - mo)**2 + vo) / sn2e, axis=0))
+            dme, dve = (yb - mo) / sn2e / K, -0.5 / sn2e * np.ones_like(vo) / K
+            logZ_emi = s_emi * lle
+            gemi, dx = self.emi.vfe_grads_mc(ms, vs, s_emi * dme, s_emi * dve, kfus, xs)
+            gin_emi = self.emi.reparam(dx, vup, eps)
+            g['sn_emission'] = s_emi * np.sum(-1 + ((yb - mo)**2 + vo) / sn2e) / K
+        elif self.gp_emi:
             sn_e = params['sn_emission']
             mo, vo, q1, q2 = self.emi.prop_mm(mup, vup, cav=False)
             lle, dme, dve = gauss_log_lik_exp(sn_e, mo, vo, yb)
