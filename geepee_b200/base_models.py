@@ -12,7 +12,7 @@ import torch
 from scipy.optimize import minimize
 
 from . import config, dist
-from .config import PROP_MM, PROP_MC
+from .config import PROP_MM, PROP_MC, PROP_LIN
 from .layers import default_device, to_dev, pack_to_device, to_host
 from .lik_layers import Gauss_Layer, Probit_Layer, Gauss_Emis
 from .utils import ObjectiveWrapper, flatten_dict, unflatten_dict, adam, PCA_reduce
@@ -159,6 +159,16 @@ class Base_SGPR(Base_Model):
             self.updated = True
         return self.sgp_layer.forward_prop_thru_post(inputs)
 
+    def sample_f(self, inputs, no_samples=1):
+        """base_models.py:1000-1018."""
+        if not self.updated:
+            self.sgp_layer.update_posterior()
+            self.updated = True
+        fs = np.zeros((inputs.shape[0], self.Dout, no_samples))
+        for k in range(no_samples):
+            fs[:, :, k] = self.sgp_layer.sample(inputs)
+        return fs
+
     def predict_y(self, inputs):
         mf, vf = self.predict_f(inputs)
         return self.lik_layer.output_probabilistic(mf, vf)
@@ -202,9 +212,11 @@ class Base_SDGPR(Base_Model):
     _batch = Base_SGPR._batch
 
     def predict_f(self, inputs, prop_mode=PROP_MM, no_samples=200):
-        """base_models.py:1132-1158 (moment matching)."""
+        """base_models.py:1132-1158 (moment matching) / 1160-1184 (Monte Carlo)."""
+        if prop_mode == PROP_MC:
+            return self.predict_f_mc(inputs, no_samples)
         if prop_mode != PROP_MM:
-            raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet' % prop_mode)
+            raise NotImplementedError('prop_mode %s unknown' % prop_mode)
         if not self.updated:
             for layer in self.sgp_layers:
                 layer.update_posterior()
@@ -216,6 +228,41 @@ class Base_SDGPR(Base_Model):
             else:
                 mf, vf, _ = layer._fwd_mm(mf, vf, cav=False, save=False)
         return mf.cpu().numpy(), vf.cpu().numpy()
+
+    def predict_f_mc(self, inputs, no_samples):
+        """base_models.py:1160-1184: `no_samples` particles per input pushed through the layers
+        (deterministic-input kernels on the stacked particles); draws from numpy's global RNG in
+        the reference's order.  -> samples[no_samples, n, Dout], and mf, vf of the last layer."""
+        if not self.updated:
+            for layer in self.sgp_layers:
+                layer.update_posterior()
+            self.updated = True
+        dev = self.device
+        samples = to_dev(inputs, dev)
+        for i, layer in enumerate(self.sgp_layers):
+            mf, vf, _ = layer._fwd_det(samples.contiguous(), cav=False, save=False)
+            if i == 0:
+                eps = to_dev(np.random.randn(no_samples, mf.shape[0], mf.shape[1]), dev)
+                samples = (torch.sqrt(vf) * eps + mf).reshape(no_samples * mf.shape[0], mf.shape[1])
+            else:
+                eps = to_dev(np.random.randn(mf.shape[0], mf.shape[1]), dev)
+                samples = torch.sqrt(vf) * eps + mf
+        samples = samples.reshape(no_samples, inputs.shape[0], self.sgp_layers[-1].Dout)
+        return samples.cpu().numpy(), mf.cpu().numpy(), vf.cpu().numpy()
+
+    def sample_f(self, inputs, no_samples=1):
+        """base_models.py:1239-1262."""
+        if not self.updated:
+            for layer in self.sgp_layers:
+                layer.update_posterior()
+            self.updated = True
+        fs = np.zeros((inputs.shape[0], self.Dout, no_samples))
+        for k in range(no_samples):
+            outputs = inputs
+            for layer in self.sgp_layers:
+                outputs = layer.sample(outputs)
+            fs[:, :, k] = outputs
+        return fs
 
     def predict_y(self, inputs):
         mf, vf = self.predict_f(inputs)
@@ -381,11 +428,107 @@ class Base_SGPSSM(Base_Model):
     def predict_f(self, inputs):
         return self.dyn_layer.forward_prop_thru_post(inputs)
 
+    def predict_y(self, inputs):
+        """base_models.py:1544-1560: one transition step from given states, then the emission."""
+        mf, vf = self.dyn_layer.forward_prop_thru_post(inputs)
+        if self.gp_emi:
+            mg, vg = self.emi_layer.forward_prop_thru_post(mf, vf)
+            return self.lik_layer.output_probabilistic(mg, vg)
+        my, _, vy = self.emi_layer.output_probabilistic(mf, vf)
+        return my, np.diagonal(vy, axis1=1, axis2=2)
+
+    def predict_forward(self, T, x_control=None, prop_mode=PROP_MM, no_samples=200):
+        """base_models.py:1453-1461."""
+        if prop_mode == PROP_MM:
+            return self.predict_forward_mm(T, x_control)
+        if prop_mode == PROP_LIN:
+            raise NotImplementedError('TODO')
+        if prop_mode == PROP_MC:
+            return self.predict_forward_mc(T, x_control, no_samples)
+        raise NotImplementedError('unknown prop mode %s' % prop_mode)
+
+    def predict_forward_mm(self, T, x_control):
+        """base_models.py:1463-1502: T-step roll-out from the last posterior state with moment
+        matching (a sequential chain of one-row layer evaluations: launch bound by nature)."""
+        mx, vx = np.zeros((T, self.Din)), np.zeros((T, self.Din))
+        my, vy_noiseless, vy = (np.zeros((T, self.Dout)) for _ in range(3))
+        post_m, post_v = self.get_posterior_x()
+        mtm1, vtm1 = post_m[[-1], :], post_v[[-1], :]
+        for t in range(T):
+            if self.Dcon_dyn > 0:
+                mtm1 = np.hstack((mtm1, x_control[[t], :]))
+                vtm1 = np.hstack((vtm1, np.zeros((1, self.Dcon_dyn))))
+            mt, vt = self.dyn_layer.forward_prop_thru_post(mtm1, vtm1)
+            if self.Dcon_emi > 0:
+                mtc = np.hstack((mt, x_control[[t], :]))
+                vtc = np.hstack((vt, np.zeros((1, self.Dcon_emi))))
+            else:
+                mtc, vtc = mt, vt
+            if self.gp_emi:
+                mft, vft = self.emi_layer.forward_prop_thru_post(mtc, vtc)
+                myt, vyt_n = self.lik_layer.output_probabilistic(mft, vft)
+            else:
+                # (the reference passes the un-augmented state here, base_models.py:1492, which
+                #  only works without control inputs to the emission; the augmented one is meant)
+                myt, vyt, vyt_n = self.emi_layer.output_probabilistic(mtc, vtc)
+                vft = np.diagonal(vyt, axis1=1, axis2=2)
+                vyt_n = np.diagonal(vyt_n, axis1=1, axis2=2)
+            mx[t, :], vx[t, :] = mt, vt
+            my[t, :], vy_noiseless[t, :], vy[t, :] = myt, vft, vyt_n
+            mtm1, vtm1 = mt, vt
+        return mx, vx, my, vy_noiseless, vy
+
+    def predict_forward_mc(self, T, x_control, no_samples):
+        """base_models.py:1504-1542: roll-out of `no_samples` particles; the standard-normal draws
+        come from numpy's global RNG in the reference's order."""
+        x = np.zeros((T, no_samples, self.Din))
+        my, vy = np.zeros((T, no_samples, self.Dout)), np.zeros((T, no_samples, self.Dout))
+        post_m, post_v = self.get_posterior_x()
+        mtm1, vtm1 = post_m[[-1], :], post_v[[-1], :]
+        eps = np.random.randn(no_samples, self.Din)
+        x_samples = eps * np.sqrt(vtm1) + mtm1
+        for t in range(T):
+            if self.Dcon_dyn > 0:
+                xc_samples = np.hstack((x_samples, np.tile(x_control[[t], :], [no_samples, 1])))
+            else:
+                xc_samples = x_samples
+            mt, vt = self.dyn_layer.forward_prop_thru_post(xc_samples)
+            eps = np.random.randn(no_samples, self.Din)
+            x_samples = eps * np.sqrt(vt) + mt
+            if self.Dcon_emi > 0:
+                xc_samples = np.hstack((x_samples, np.tile(x_control[[t], :], [no_samples, 1])))
+            else:
+                xc_samples = x_samples
+            if self.gp_emi:
+                mft, vft = self.emi_layer.forward_prop_thru_post(xc_samples)
+                myt, vyt_n = self.lik_layer.output_probabilistic(mft, vft)
+            else:
+                myt, _, vyt_n = self.emi_layer.output_probabilistic(xc_samples, np.zeros_like(xc_samples))
+                vyt_n = np.diagonal(vyt_n, axis1=1, axis2=2)
+            x[t, :, :] = x_samples
+            my[t, :, :], vy[t, :, :] = myt, vyt_n
+        return x, my, vy
+
     def get_posterior_x(self, idxs=None):
         p1, p2 = self._post1.cpu().numpy(), self._post2.cpu().numpy()
         if idxs is not None:
             p1, p2 = p1[idxs, :], p2[idxs, :]
         return p1 / p2, 1.0 / p2
+
+    def get_posterior_y(self):
+        """base_models.py:1578-1595."""
+        mx, vx = self.get_posterior_x()
+        if self.Dcon_emi > 0:
+            mx = np.hstack((mx, self.x_control))
+            vx = np.hstack((vx, np.zeros((self.N, self.Dcon_emi))))
+        if self.gp_emi:
+            mf, vf = self.emi_layer.forward_prop_thru_post(mx, vx)
+            my, vyn = self.lik_layer.output_probabilistic(mf, vf)
+        else:
+            my, vy, vyn = self.emi_layer.output_probabilistic(mx, vx)
+            vf = np.diagonal(vy, axis1=1, axis2=2)
+            vyn = np.diagonal(vyn, axis1=1, axis2=2)
+        return my, vf, vyn
 
     def get_hypers(self):
         params = dict(self.dyn_layer.get_hypers(key_suffix='_dynamic'))

@@ -442,6 +442,27 @@ class Base_SGP_Layer(object):
             g_z = g_z + Xb * Mb.sum(0).unsqueeze(1) - torch.matmul(Mb, Xb)
         return dsf + 2.0 * g_sf, dls + 2.0 * g_ls, st['dzu'] + g_z
 
+    def sample(self, x):
+        """base_models.py:428-452: one joint draw of f(x) -- u ~ q(u), then f | u at the test
+        inputs.  The standard-normal draws come from numpy's global RNG in the reference's order;
+        the algebra (two Cholesky factorisations, kernel matrices from the library) runs on the
+        device."""
+        t = self._t
+        dev = self.device
+        xd = to_dev(x, dev)
+        Lu = torch.linalg.cholesky(t['Su'])
+        eps_u = to_dev(np.random.randn(self.Dout, self.M), dev)
+        u = t['mu'] + bmv(Lu, eps_u)
+        n = xd.shape[0]
+        kff = ops.kmat(xd, xd, t['ls'], t['sf'], config.JITTER)
+        kfu = ops.kmat(xd, t['zu'], t['ls'], t['sf'])
+        qfu = torch.matmul(kfu, t['Kuuinv'])
+        mf = torch.matmul(qfu, u.t())
+        vf = kff - torch.matmul(qfu, kfu.t())
+        Lf = torch.linalg.cholesky(vf)
+        eps_f = to_dev(np.random.randn(n, self.Dout), dev)
+        return (mf + torch.matmul(Lf, eps_f)).cpu().numpy()
+
     # ---- prediction path (base_models.py:235-307) -----------------------------------------
     def forward_prop_thru_post(self, mx, vx=None, mode=config.PROP_MM, return_info=False):
         dev = self.device

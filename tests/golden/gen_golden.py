@@ -117,7 +117,9 @@ def case_sgpr(name, cls, N, M, D, Do, alpha, nat, mb=None, seed=0, xy=None, lk='
         model.updated = False
         mf, vf = model.predict_f(xs)
         my, vy = model.predict_y(xs)
-        extra = {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy}
+        np.random.seed(555)
+        fs = model.sample_f(xs, 2)                      # base_models.py:1000-1018, 428-452
+        extra = {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy, 'fs': fs}
     save(name, dict(model=cls.__module__.split('.')[-1] + '.SGPR', N=N, M=M, D=D, Do=Do,
                     alpha=alpha, nat_param=nat, mb_size=mbs, rng_seed=123, lik=lk),
          {'x': x, 'y': y}, params, e, g, extra)
@@ -145,9 +147,14 @@ def case_sdgpr(name, N, M, D, hidden, Do, alpha, mb=None, seed=1, lk='Gaussian')
     model.updated = False
     mf, vf = model.predict_f(xs)
     my, vy = model.predict_y(xs)
+    np.random.seed(556)
+    smp, mmc, vmc = model.predict_f(xs, prop_mode='MC', no_samples=3)     # base_models.py:1160-1184
+    np.random.seed(557)
+    fs = model.sample_f(xs, 2)                                            # base_models.py:1239-1262
     save(name, dict(model='aep_models.SDGPR', N=N, M=M, D=D, hidden=hidden, Do=Do, alpha=alpha,
                     mb_size=mbs, rng_seed=123),
-         {'x': x, 'y': y}, params, e, g, {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy})
+         {'x': x, 'y': y}, params, e, g, {'xs': xs, 'mf': mf, 'vf': vf, 'my': my, 'vy': vy,
+                                          'mc_samples': smp, 'mc_mf': mmc, 'mc_vf': vmc, 'fs': fs})
 
 
 def lvm_params(model, y, rng):
@@ -218,7 +225,7 @@ def ssm_params(model, y, rng, gp_emi):
 
 
 def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True, mb=None, seed=3,
-                prop_mode=None):
+                prop_mode=None, predict=False):
     rng = np.random.RandomState(seed)
     y = np.cumsum(0.3 * rng.standard_normal((N, Do)), axis=0)
     xc = rng.standard_normal((N, control)) if control else None
@@ -238,7 +245,26 @@ def case_sgpssm(name, cls, N, M, Q, Do, alpha, gp_emi=False, control=0, nat=True
                 rng_seed=123)
     if prop_mode is not None:
         meta['prop_mode'] = prop_mode
-    save(name, meta, inputs, params, e, g)
+    extra = {}
+    if predict:
+        # prediction API around the path (base_models.py:1453-1595): T-step roll-outs from the last
+        # state (moment matching / particles), one-step predict_y, posterior over the observations
+        model.update_hypers(params)
+        Tf = 4
+        xcf = rng.standard_normal((Tf, control)) if control else None
+        pf = model.predict_forward_mm(Tf, xcf)
+        xin = rng.standard_normal((5, Q + control))
+        py = model.predict_y(xin)
+        gy = model.get_posterior_y()
+        np.random.seed(321)
+        pmc = model.predict_forward_mc(3, xcf, 4) if not (control and not gp_emi) else None
+        extra = {'pf_mx': pf[0], 'pf_vx': pf[1], 'pf_my': pf[2], 'pf_vyn': pf[3], 'pf_vy': pf[4],
+                 'py_in': xin, 'py_my': py[0], 'py_vy': py[1], 'gy_my': gy[0], 'gy_vf': gy[1], 'gy_vyn': gy[2]}
+        if xcf is not None:
+            extra['pf_xc'] = xcf
+        if pmc is not None:
+            extra.update({'mc_x': pmc[0], 'mc_my': pmc[1], 'mc_vy': pmc[2]})
+    save(name, meta, inputs, params, e, g, extra)
 
 
 def case_kernels(seed=4):
@@ -355,6 +381,14 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'probit':   # only the files added with the probit layer
         probit_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'sample':
+        case_sgpr('aep_sgpr', aep.SGPR, 20, 10, 2, 3, 0.5, True)
+        case_sdgpr('aep_sdgpr', 10, 5, 2, [3, 2], 2, 1.0)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'ssm_predict':
+        case_sgpssm('aep_sgpssm_lin', aep.SGPSSM, 20, 4, 2, 2, 0.5, predict=True)
+        case_sgpssm('aep_sgpssm_gp', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=42, predict=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'mc':
         mc_cases()
         sys.exit(0)
@@ -384,10 +418,10 @@ if __name__ == '__main__':
     case_sgplvm('vfe_sgplvm', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=31)
     case_sgplvm('vfe_sgplvm_nonnat', vfe.SGPLVM, 10, 5, 3, 2, 1.0, nat=False, seed=32)
     # tests/test_grads_aep.py:370-410; tests/test_grads_vfe.py:371-411
-    case_sgpssm('aep_sgpssm_lin', aep.SGPSSM, 20, 4, 2, 2, 0.5)
+    case_sgpssm('aep_sgpssm_lin', aep.SGPSSM, 20, 4, 2, 2, 0.5, predict=True)
     case_sgpssm('aep_sgpssm_lin_1d', aep.SGPSSM, 30, 4, 1, 1, 0.4, seed=40)
     case_sgpssm('aep_sgpssm_lin_window', aep.SGPSSM, 20, 4, 2, 2, 0.5, mb=8, seed=41)
-    case_sgpssm('aep_sgpssm_gp', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=42)
+    case_sgpssm('aep_sgpssm_gp', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=42, predict=True)
     case_sgpssm('aep_sgpssm_control', aep.SGPSSM, 12, 4, 2, 2, 0.5, control=1, seed=43)
     case_sgpssm('vfe_sgpssm_lin', vfe.SGPSSM, 20, 4, 2, 2, 1.0, seed=44)
     case_sgpssm('vfe_sgpssm_gp', vfe.SGPSSM, 10, 4, 2, 3, 1.0, gp_emi=True, seed=45)

@@ -55,3 +55,49 @@ def check_predict(name, prec, tol, device=None):
     my, vy = model.predict_y(x['xs'])
     for got, key in [(mf, 'mf'), (vf, 'vf'), (my, 'my'), (vy, 'vy')]:
         assert gu.rel_err(got, x[key]) < tol, (name, key, gu.rel_err(got, x[key]))
+
+
+def check_ssm_predict(name, tol, device=None):
+    """Prediction API of the state-space model around the hot path (base_models.py:1453-1595):
+    predict_forward_mm / _mc, predict_y, get_posterior_y against the reference's outputs."""
+    gold = gu.load(name)
+    model = build_model(gold, 'fp64', device)
+    model.update_hypers(copy.deepcopy(gold['p']))
+    x = gold['x']
+    xc = x.get('pf_xc')
+    pf = model.predict_forward_mm(x['pf_mx'].shape[0], xc)
+    for got, key in zip(pf, ('pf_mx', 'pf_vx', 'pf_my', 'pf_vyn', 'pf_vy')):
+        assert gu.rel_err(got, x[key]) < tol, (name, key, gu.rel_err(got, x[key]))
+    py = model.predict_y(x['py_in'])
+    for got, key in zip(py, ('py_my', 'py_vy')):
+        assert gu.rel_err(got, x[key]) < tol, (name, key, gu.rel_err(got, x[key]))
+    gy = model.get_posterior_y()
+    for got, key in zip(gy, ('gy_my', 'gy_vf', 'gy_vyn')):
+        assert gu.rel_err(got, x[key]) < tol, (name, key, gu.rel_err(got, x[key]))
+    if 'mc_x' in x:
+        np.random.seed(321)
+        T, S = x['mc_x'].shape[0], x['mc_x'].shape[1]
+        pmc = model.predict_forward(T, xc, prop_mode='MC', no_samples=S)
+        for got, key in zip(pmc, ('mc_x', 'mc_my', 'mc_vy')):
+            assert gu.rel_err(got, x[key]) < tol, (name, key, gu.rel_err(got, x[key]))
+
+
+def check_sampling(name, tol, device=None):
+    """sample_f (base_models.py:428-452, 1000-1018, 1239-1262) and the particle prediction of the
+    deep GP (1160-1184), seeded like the golden generator.  The f | u draw factorises
+    kff - kfu Kuu^-1 kuf, which is close to singular by construction: tolerance 1e-5."""
+    gold = gu.load(name)
+    model = build_model(gold, 'fp64', device)
+    model.update_hypers(copy.deepcopy(gold['p']))
+    model.updated = False
+    x = gold['x']
+    if 'mc_samples' in x:
+        np.random.seed(556)
+        smp, mf, vf = model.predict_f(x['xs'], prop_mode='MC', no_samples=x['mc_samples'].shape[0])
+        for got, key in ((smp, 'mc_samples'), (mf, 'mc_mf'), (vf, 'mc_vf')):
+            assert gu.rel_err(got, x[key]) < 1e-7, (name, key, gu.rel_err(got, x[key]))
+        np.random.seed(557)
+    else:
+        np.random.seed(555)
+    fs = model.sample_f(x['xs'], x['fs'].shape[2])
+    assert gu.rel_err(fs, x['fs']) < tol, (name, 'fs', gu.rel_err(fs, x['fs']))

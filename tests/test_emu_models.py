@@ -27,3 +27,13 @@ def test_objective_fp32(name):
 @pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sdgpr', 'aep_sgpr_nonnat', 'aep_sdgprh'])
 def test_predict(name):
     mc.check_predict(name, 'fp64', 1e-8)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr'])
+def test_sampling(name):
+    mc.check_sampling(name, 1e-5)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpssm_lin', 'aep_sgpssm_gp'])
+def test_ssm_predict(name):
+    mc.check_ssm_predict(name, 1e-8)

@@ -44,6 +44,16 @@ def test_predict(name):
     mc.check_predict(name, 'fp64', 1e-7)
 
 
+@pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr'])
+def test_sampling(name):
+    mc.check_sampling(name, 1e-5)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpssm_lin', 'aep_sgpssm_gp'])
+def test_ssm_predict(name):
+    mc.check_ssm_predict(name, 1e-7)
+
+
 def _oracle_vs_gpu(make_oracle, make_gpu, params, N, alpha, tol):
     """Compare with the oracle on the same inputs.  The oracle's own conditioning floor (how far
     its output moves when every input is perturbed by 1e-15 relative, as in gen_golden.py) bounds
