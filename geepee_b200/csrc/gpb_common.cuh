@@ -6,6 +6,23 @@
 // synchronisation, no torch types.  The same file is compiled with -DGPB_CPU_EMU by
 // tests/emu/build.py, where GPB_LAUNCH runs the kernels on the fiber emulator.
 #pragma once
+// Development knobs of the fp64 pair kernels (A/B builds, geepee_b200/build.py); the defaults are the
+// product configuration.  GPB_MM_RP64: cap on the pairs a thread owns (0 = automatic);
+// GPB_MM_MINBLOCKS: resident CTAs per SM requested through __launch_bounds__;
+// GPB_EXP_REP: replicas of the exp table in shared memory; GPB_MM_NR_FWD: rows per loop trip of
+// the forward kernel.
+#ifndef GPB_MM_RP64
+#define GPB_MM_RP64 0
+#endif
+#ifndef GPB_MM_MINBLOCKS
+#define GPB_MM_MINBLOCKS 1
+#endif
+#ifndef GPB_EXP_REP
+#define GPB_EXP_REP 16
+#endif
+#ifndef GPB_MM_NR_FWD
+#define GPB_MM_NR_FWD 2
+#endif
 #include "../../include/geepee_b200.h"
 #include "gpb_kernels.cuh"
 

@@ -1427,7 +1427,8 @@ template <typename T, int Q, int DOC>
 struct MMCfg {
     // pairs per thread, sized to keep the per-thread pair state in registers (fp32: twice as many,
     // the fp32 path is issue bound and the per-row overhead is amortised over the pairs)
-    static constexpr int RP64 = (2 * Q + 2 * DOC + 2) <= 18 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
+    static constexpr int RPA = (2 * Q + 2 * DOC + 2) <= 18 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
+    static constexpr int RP64 = (GPB_MM_RP64 > 0 && GPB_MM_RP64 < RPA) ? GPB_MM_RP64 : RPA;
     static constexpr int RP = sizeof(T) == 4 ? 2 * RP64 : RP64;
     static constexpr int TR = 32;             // rows per staged tile = lanes per warp
     static constexpr int PC = kThreads * RP;  // pairs per block
@@ -1468,7 +1469,7 @@ struct MMArgs {
 // the fp64 pipe overlap the 8-deep dependency chains of different pairs / rows.
 template <typename T> struct ExpDom;
 template <> struct ExpDom<double> {
-    static constexpr int ENT = 256, REP = 16;
+    static constexpr int ENT = 256, REP = GPB_EXP_REP;
     static constexpr int TAB = ENT * REP;                 // doubles of dynamic shared memory
     static constexpr double S = 256.0 / 0.693147180559945309417232;
 };
@@ -1503,7 +1504,7 @@ GPB_DEVICE void exp_dom_n(double (&x)[N], const double* __restrict__ tab, int la
         memcpy(&bits, &kd[i], 8);
         n[i] = (int)(int32_t)(bits & 0xffffffff);
 #endif
-        t[i] = tab[((n[i] & 255) << 4) + lane16];
+        t[i] = tab[(n[i] & 255) * ExpDom<double>::REP + lane16];
     }
     GPB_UNROLL
     for (int i = 0; i < N; i++) kd[i] -= magic;
@@ -1594,7 +1595,7 @@ struct RowXpose {
 // GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
 // GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
 template <typename T, int Q, int DOC, bool BWD, bool GEN>
-GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
+GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, GPB_MM_MINBLOCKS) mm_pairs_kernel(MMArgs<T> a) {
     typedef MMCfg<T, Q, DOC> C;
     constexpr int RP = C::RP, TR = C::TR;
     constexpr int NS = BWD ? 2 * Q : DOC;
@@ -1604,7 +1605,8 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     constexpr int RLraw = 1 + 2 * Q + (BWD ? DOC : 0);
     constexpr int RL = (RLraw + VW - 1) / VW * VW;       // row record length (16-byte multiple)
     constexpr int kTab = ExpDom<T>::TAB;
-    constexpr int NR = Q <= 4 ? 2 : 1;  // rows per loop trip (wide inputs: one, register budget)
+    // rows per loop trip (wide inputs: one, register budget)
+    constexpr int NR = Q <= 4 ? ((!BWD && sizeof(T) == 8 && Q <= 2 && DOC <= 2) ? GPB_MM_NR_FWD : 2) : 1;
     constexpr double kS = ExpDom<T>::S;
     // Row tiles are double buffered (tile t+1 is staged while tile t is consumed) and so is the
     // cross-warp staging of the row sums, which leaves ONE barrier per tile.  For wide inputs the
@@ -1648,7 +1650,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     if (kTab > 0)
         for (int i = tid; i < kTab; i += kThreads)
             s_tab[i] = exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
-    const int lane16 = lane & 15;
+    const int lane16 = lane & ((ExpDom<T>::REP > 0 ? ExpDom<T>::REP : 1) - 1);
     unsigned char* xw = dsm + kTab * sizeof(double) + warp * X::kWarpB;   // this warp's buffer
 
     const int r_begin = blockIdx.y * a.rows_per_split;
@@ -1941,7 +1943,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_fwd_wide_kernel(MMArgs<T> a) {
     double* s_tab = (double*)dsm;
     T* s_pair = (T*)(dsm + kTab * sizeof(double));          // [PCW][REC]: zh[Q] | zh2[Q] | bs[DOW]
     GPB_SHARED double s_l2[Q];
-    const int tid = threadIdx.x, lane16 = tid & 15;
+    const int tid = threadIdx.x, lane16 = tid & ((ExpDom<T>::REP > 0 ? ExpDom<T>::REP : 1) - 1);
     const long pbase = (long)blockIdx.x * PCW;
     const long PP = a.PP;
     const int Do = a.Do;

@@ -20,6 +20,7 @@
 #define GPB_SHARED __shared__
 #define GPB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define GPB_LAUNCH_BOUNDS(n) __launch_bounds__(n)
+#define GPB_LAUNCH_BOUNDS2(n, m) __launch_bounds__(n, m)
 #define GPB_UNROLL _Pragma("unroll")
 #define GPB_UNROLL_N(n) _Pragma(GPB_STR(unroll n))
 #define GPB_STR(x) #x
@@ -91,6 +92,7 @@ GPB_DEVICE float ldg(const float* p) { return __ldg(p); }
 #define GPB_SHARED static
 #define GPB_DYN_SMEM(name) unsigned char* name = gpb_emu::dyn_smem
 #define GPB_LAUNCH_BOUNDS(n)
+#define GPB_LAUNCH_BOUNDS2(n, m)
 #define GPB_UNROLL
 #define GPB_UNROLL_N(n)
 #define GPB_ALIGN16 __attribute__((aligned(16)))
