@@ -9,6 +9,8 @@ struct MMPlan {
     long P, PP;
     int nchunks, nsplit, rows_per_split, npass;
     int rows_grid, cols_grid, cols_rows_per_block, fwd_grid;
+    // fp64 backward of wide layers (Do > 4, Qt <= 8): tensor-core kernel over 64-pair chunks
+    int wide_mma, w_nchunks, w_nsplit, w_rows_per_split;
     // workspace byte offsets are carved in order by mm_carve
 };
 int q_template(int Q) {
@@ -62,6 +64,20 @@ MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do, int backward) {
     if (crpb < 32) crpb = 32;
     p.cols_rows_per_block = (int)crpb;
     p.cols_grid = (int)cdiv(n, crpb);
+    p.wide_mma = (backward && tbytes == 8 && Do > 4 && p.Qt <= 8) ? 1 : 0;
+    p.w_nchunks = (int)(p.PP / 64);
+    p.w_nsplit = 1;
+    p.w_rows_per_split = n;
+    if (p.wide_mma) {   // one CTA per SM: row splits that fill an integer number of waves
+        int bestw = 1;
+        for (int waves = 8; waves >= 1; waves--) {
+            int ns = (int)((long)waves * sm_count() / p.w_nchunks);
+            if (ns >= 1 && cdiv(n, ns) >= 4 * TR) { bestw = ns; break; }
+        }
+        long wr = cdiv(cdiv(n, bestw), TR) * TR;
+        p.w_rows_per_split = (int)wr;
+        p.w_nsplit = (int)cdiv(n, wr);
+    }
     return p;
 }
 
@@ -83,7 +99,9 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
         w.pairpart = w.pairsum = w.rowpart = w.rowsum = w.colpart = w.colsum = w.dZ2 = w.dlW = nullptr;
     } else {
         w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * (2 * p.Qt));
-        w.pairpart = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * (p.DOC + 1 + p.Qt) * p.PP);
+        size_t npart = (size_t)p.nsplit * (p.DOC + 1 + p.Qt) * p.PP;
+        if (p.wide_mma) npart = (size_t)p.w_nsplit * (Do + 1 + p.Qt) * p.PP;
+        w.pairpart = (double*)cv.take(sizeof(double) * npart);
         w.pairsum = (double*)cv.take(sizeof(double) * (size_t)(Do + 1 + p.Qt) * p.PP);
         w.rowpart = (double*)cv.take(sizeof(double) * (size_t)p.rows_grid * (2 + Q));
         w.rowsum = (double*)cv.take(sizeof(double) * (2 + Q));
@@ -289,6 +307,29 @@ int mm_fwd_wide_dispatch(const MMPlan& p, const gpb::MMArgs<T>& a, int n, int Do
 #undef GPB_CALL
 }
 
+template <int QT>
+int mm_bwd_wide_mma_launch(const MMPlan& p, gpb::MMArgs<double> a, void* stream) {
+    if constexpr (QT <= 8) {
+        typedef gpb::MMWideMma<QT> C;
+        auto kern = gpb::mm_bwd_wide_mma_kernel<QT>;
+        if (mm_pairs_smem(kern, C::smem_bytes)) return GPB_ERR_CUDA;
+        a.rows_per_split = p.w_rows_per_split;
+        const int DOP8 = (a.Do + 7) / 8 * 8;
+        prof_begin(4, stream);
+        GPB_LAUNCH(kern, dim3(p.w_nchunks, p.w_nsplit), dim3(256), C::smem_bytes, stream, a, DOP8);
+        prof_end(4, stream);
+        return GPB_OK;
+    } else {
+        (void)p; (void)a; (void)stream;
+        return fail(GPB_ERR_ARG, "mm_bwd_wide_mma: Q template %d unsupported", QT);
+    }
+}
+int mm_bwd_wide_mma_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, void* stream) {
+#define GPB_CALL(QT) mm_bwd_wide_mma_launch<QT>(p, a, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
+
 template <typename T>
 int mm_check(int n, int M, int Q, int Do) {
     if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
@@ -357,7 +398,18 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
     a.full_coef = p.npass > 1 ? 1 : 0;
     auto red = gpb::reduce_partials_kernel;
     const long recstride = (long)(p.DOC + 1 + p.Qt) * p.PP;
-    for (int pass = 0; pass < p.npass; pass++) {
+    bool wide_done = false;
+    if constexpr (sizeof(T) == 8) {
+        if (p.wide_mma) {   // wide fp64 layers: one tensor-core kernel, no d-passes
+            rc = mm_bwd_wide_mma_dispatch(p, a, stream);
+            if (rc) return rc;
+            const long wlen = (long)(Do + 1 + p.Qt) * p.PP;
+            GPB_LAUNCH(red, dim3(elementwise_grid(wlen)), dim3(256), 0, stream, w.pairpart, p.w_nsplit, wlen,
+                       wlen, w.pairsum, 0);
+            wide_done = true;
+        }
+    }
+    for (int pass = 0; pass < (wide_done ? 0 : p.npass); pass++) {
         a.d0 = pass * p.DOC;
         a.lam_pass = pass == 0 ? 1 : 0;
         rc = mm_pairs_dispatch<T, true>(p, a, stream);

@@ -2022,6 +2022,217 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_fwd_wide_kernel(MMArgs<T> a) {
 // psi1 tile in shared memory and -- coalesced -- the optional psi1 save buffer that both
 // backward kernels stream instead of re-evaluating the exponentials.  Phase B: each warp takes
 // 4 rows, lanes stride over the columns, warp reduction per (row, d).
+// Backward contraction for WIDE output layers (Do > 4, fp64) on the FP64 tensor cores.
+// With Do in the tens, everything the pair backward does after generating psi2' is GEMM-shaped
+// (rows r of a 32-row tile, pairs p of the CTA's 64-pair chunk, output dims d, 2Q moment columns s):
+//   G1  Lraw[r,p] = sum_d dv[r,d] bs[d,p]          -> Lam = Lraw * psi2'   (aep_models.py:243, kernels.py:415-419)
+//   G2  dBp[d,p] += sum_r dv[r,d] psi2'[r,p]                               (aep_models.py:240)
+//   G3  W[p,s]   += sum_r Lam[r,p] R[r,s],  R = [c2 mu | c2]   -> S1[p,q] = W[p,q] - zh[p,q] W[p,Q+q]
+//   G4  V[r,s]    = sum_p Lam[r,p] Z[p,s],  Z = [zh | zh^2]    -> rowacc[r,:] (one atomic per value)
+// so a thread never holds Do accumulators: psi2' is evaluated ONCE per (row, pair) by the SIMT phase
+// (expanded-form exponent + table exp, one pair column and 8 rows per thread) into shared memory
+// and the four products run as DMMA.8x8x4 tiles (fragments: a = A[g][t], b = B[t][g], c = C[g][2t..]).
+// All shared-memory strides are 4 mod 16 doubles, so every fragment load is conflict free.
+// dBp / W accumulate in registers over the CTA's rows; S0 = sum_d bs dBp is derived at the end.
+// Replaces two passes of the 32-outputs-per-thread SIMT kernel for SGPLVM-like layers (Do = 50).
+template <int Q>
+struct MMWideMma {
+    static constexpr int PCW = 64, TR = 32, LDP = PCW + 4, LDV = 68, LDZ = 20;
+    static constexpr int QB = (2 * Q + 7) / 8;          // 8-column blocks of the moment columns
+    static constexpr int RL = (1 + 2 * Q + 1) / 2 * 2;  // row-constant record (even length)
+    static constexpr size_t n_tab = ExpDom<double>::TAB;
+    static constexpr size_t n_bs = 64 * LDP, n_dv = TR * LDV, n_psi = TR * LDP, n_lam = TR * LDP;
+    static constexpr size_t n_Z = PCW * LDZ, n_R = TR * LDZ, n_rc = TR * RL;
+    static constexpr size_t smem_bytes = 8 * (n_tab + n_bs + n_dv + n_psi + n_lam + n_Z + n_R + n_rc);
+    static_assert(2 * Q <= 16, "moment columns must fit two 8-column blocks");
+    static_assert(n_psi + n_lam >= 64 * LDP, "the dBp staging aliases psi | lam");
+};
+
+template <int Q>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, int DOP8) {
+    typedef MMWideMma<Q> C;
+    constexpr int PCW = C::PCW, TR = C::TR, LDP = C::LDP, LDV = C::LDV, LDZ = C::LDZ, QB = C::QB, RL = C::RL;
+    constexpr double kS = ExpDom<double>::S;
+    GPB_DYN_SMEM(dsm);
+    double* s_tab = (double*)dsm;
+    double* s_bs = s_tab + C::n_tab;     // [DOP8][LDP]   bs[d, p]
+    double* s_dv = s_bs + C::n_bs;       // [TR][LDV]     dv[r, d]
+    double* s_psi = s_dv + C::n_dv;      // [TR][LDP]     psi2'[r, p]
+    double* s_lam = s_psi + C::n_psi;    // [TR][LDP]     Lam[r, p]
+    double* s_Z = s_lam + C::n_lam;      // [PCW][LDZ]    zh | zh^2
+    double* s_R = s_Z + C::n_Z;          // [TR][LDZ]     c2 mu | c2
+    double* s_rc = s_R + C::n_R;         // [TR][RL]      expanded-form row constants
+    GPB_SHARED double s_l2[Q];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int lane16 = lane & (ExpDom<double>::REP - 1);
+    const long pbase = (long)blockIdx.x * PCW;
+    const long PP = a.PP;
+    const int Do = a.Do, DB = DOP8 / 8, KB1 = DOP8 / 4;
+
+    for (int i = tid; i < (int)C::n_tab; i += kThreads)
+        s_tab[i] = exp2((double)(i / ExpDom<double>::REP) * (1.0 / ExpDom<double>::ENT));
+    for (int i = tid; i < 64 * PCW; i += kThreads) {
+        const int d = i / PCW, p = i - d * PCW;
+        s_bs[d * LDP + p] = d < Do ? a.bs[(long)d * PP + pbase + p] : 0.0;
+    }
+    for (int i = tid; i < PCW * 16; i += kThreads) {
+        const int p = i >> 4, sc = i & 15;
+        double v = 0.0;
+        if (sc < Q) v = a.zh[(long)sc * PP + pbase + p];
+        else if (sc < 2 * Q) { const double zz = a.zh[(long)(sc - Q) * PP + pbase + p]; v = zz * zz; }
+        s_Z[p * LDZ + sc] = v;
+    }
+    if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+    // SIMT phase: this thread's pair column and its rows ra, ra+4, ...
+    const int pa = tid & (PCW - 1), ra = tid >> 6;
+    double zh[Q], zh2[Q];
+    GPB_UNROLL
+    for (int q = 0; q < Q; q++) {
+        zh[q] = a.zh[(long)q * PP + pbase + pa];
+        zh2[q] = zh[q] * zh[q];
+    }
+    double accB[8][2], accW[QB][2];
+    GPB_UNROLL
+    for (int i = 0; i < 8; i++) accB[i][0] = accB[i][1] = 0.0;
+    GPB_UNROLL
+    for (int j = 0; j < QB; j++) accW[j][0] = accW[j][1] = 0.0;
+
+    const int r_begin = blockIdx.y * a.rows_per_split;
+    const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
+    sync_threads();
+    for (int t0 = r_begin; t0 < r_end; t0 += TR) {
+        const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+        // ---- stage the row tile: constants of the exponent, R, dv ------------------------------
+        if (tid < TR) {
+            const int row = tid;
+            const bool ok = row < tv;
+            double lcn = 0.0, a0 = 0.0;
+            for (int q = 0; q < Q; q++) {
+                double mu = 0, c2 = 0;
+                if (ok && q < a.Qa) {
+                    mu = a.mx[(long)(t0 + row) * a.Qa + q];
+                    const double lq = s_l2[q];
+                    c2 = 1.0 / (2.0 * a.vx[(long)(t0 + row) * a.Qa + q] + lq);
+                    lcn += 0.5 * log(lq * c2);
+                }
+                const double c2s = c2 * kS;
+                s_rc[row * RL + 1 + q] = 2.0 * c2s * mu;
+                s_rc[row * RL + 1 + Q + q] = -c2s;
+                a0 -= c2s * mu * mu;
+                s_R[row * LDZ + q] = c2 * mu;
+                s_R[row * LDZ + Q + q] = c2;
+            }
+            for (int sc = 2 * Q; sc < 16; sc++) s_R[row * LDZ + sc] = 0.0;
+            // rows past the end: psi2' ~ 0 and their dv is 0
+            s_rc[row * RL] = (ok ? lcn : -1.0e5) * kS + a0;
+        }
+        for (int i = tid; i < TR * 64; i += kThreads) {
+            const int r = i >> 6, d = i & 63;
+            s_dv[r * LDV + d] = (r < tv && d < Do) ? a.dv[(long)(t0 + r) * Do + d] : 0.0;
+        }
+        sync_threads();
+        // ---- SIMT phase: psi2'[r, p] ---------------------------------------------------------
+        {
+            double x[TR / 4];
+            GPB_UNROLL
+            for (int i = 0; i < TR / 4; i++) {
+                const double* rc = s_rc + (ra + 4 * i) * RL;
+                double xx = rc[0];
+                GPB_UNROLL
+                for (int q = 0; q < Q; q++) {
+                    xx += rc[1 + q] * zh[q];
+                    xx += rc[1 + Q + q] * zh2[q];
+                }
+                x[i] = xx;
+            }
+            exp_dom_n<TR / 4>(x, s_tab, lane16);
+            GPB_UNROLL
+            for (int i = 0; i < TR / 4; i++) s_psi[(ra + 4 * i) * LDP + pa] = x[i];
+        }
+        sync_threads();
+        // ---- G1: Lam = (dv . bs) * psi2' -----------------------------------------------------
+        {
+            const int rb = warp >> 1, cb0 = (warp & 1) * 4;
+            double c[4][2];
+            GPB_UNROLL
+            for (int j = 0; j < 4; j++) c[j][0] = c[j][1] = 0.0;
+            for (int k = 0; k < KB1; k++) {
+                const double av = s_dv[(8 * rb + g) * LDV + 4 * k + t];
+                GPB_UNROLL
+                for (int j = 0; j < 4; j++)
+                    dmma(c[j][0], c[j][1], av, s_bs[(4 * k + t) * LDP + 8 * (cb0 + j) + g]);
+            }
+            GPB_UNROLL
+            for (int j = 0; j < 4; j++) {
+                const int idx = (8 * rb + g) * LDP + 8 * (cb0 + j) + 2 * t;
+                s_lam[idx] = c[j][0] * s_psi[idx];
+                s_lam[idx + 1] = c[j][1] * s_psi[idx + 1];
+            }
+        }
+        sync_threads();
+        // ---- G2: dBp[d, p] += dv^T psi2' (this warp: pair columns 8 warp .. +7, all d blocks) ----
+        GPB_UNROLL_N(2)
+        for (int k = 0; k < TR / 4; k++) {
+            const double bv = s_psi[(4 * k + t) * LDP + 8 * warp + g];
+            GPB_UNROLL
+            for (int i = 0; i < 8; i++)
+                if (i < DB) dmma(accB[i][0], accB[i][1], s_dv[(4 * k + t) * LDV + 8 * i + g], bv);
+        }
+        // ---- G3: W[p, s] += Lam^T R ------------------------------------------------------------
+        GPB_UNROLL_N(2)
+        for (int k = 0; k < TR / 4; k++) {
+            const double av = s_lam[(4 * k + t) * LDP + 8 * warp + g];
+            GPB_UNROLL
+            for (int j = 0; j < QB; j++) dmma(accW[j][0], accW[j][1], av, s_R[(4 * k + t) * LDZ + 8 * j + g]);
+        }
+        // ---- G4: V[r, s] = Lam Z -> row sums ---------------------------------------------------
+        {
+            const int rb = warp >> 1, cb = warp & 1;
+            if (cb < QB) {
+                double v0 = 0.0, v1 = 0.0;
+                GPB_UNROLL_N(4)
+                for (int k = 0; k < PCW / 4; k++)
+                    dmma(v0, v1, s_lam[(8 * rb + g) * LDP + 4 * k + t], s_Z[(4 * k + t) * LDZ + 8 * cb + g]);
+                const int r = 8 * rb + g, sc = 8 * cb + 2 * t;
+                if (r < tv) {
+                    if (sc < 2 * Q) atomic_add(a.rowacc + (long)(t0 + r) * (2 * Q) + sc, v0);
+                    if (sc + 1 < 2 * Q) atomic_add(a.rowacc + (long)(t0 + r) * (2 * Q) + sc + 1, v1);
+                }
+            }
+        }
+        sync_threads();     // tile buffers free
+    }
+    // ---- pair sums of this (chunk, row split): {dBp_d, S0, S1_q} ------------------------------
+    double* U = s_psi;      // [DOP8][LDP], aliases psi | lam
+    double* WS = s_Z;       // [PCW][LDZ]
+    GPB_UNROLL
+    for (int i = 0; i < 8; i++)
+        if (i < DB) {
+            U[(8 * i + g) * LDP + 8 * warp + 2 * t] = accB[i][0];
+            U[(8 * i + g) * LDP + 8 * warp + 2 * t + 1] = accB[i][1];
+        }
+    GPB_UNROLL
+    for (int j = 0; j < QB; j++) {
+        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t] = accW[j][0];
+        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t + 1] = accW[j][1];
+    }
+    sync_threads();
+    double* rec = a.pairpart + (long)blockIdx.y * (Do + 1 + Q) * PP;
+    for (int i = tid; i < Do * PCW; i += kThreads) {
+        const int d = i / PCW, p = i - d * PCW;
+        rec[(long)d * PP + pbase + p] = a.ep[pbase + p] * U[d * LDP + p];
+    }
+    if (tid < PCW) {
+        double s0 = 0.0;
+        for (int d = 0; d < Do; d++) s0 += s_bs[d * LDP + tid] * U[d * LDP + tid];
+        rec[(long)Do * PP + pbase + tid] = s0;
+        for (int q = 0; q < Q; q++)
+            rec[(long)(Do + 1 + q) * PP + pbase + tid] =
+                WS[tid * LDZ + q] - a.zh[(long)q * PP + pbase + tid] * WS[tid * LDZ + Q + q];
+    }
+}
+
 template <typename T> struct Psi1Dom;   // exponent scale folded into c1 (argument of exp is -e)
 template <> struct Psi1Dom<double> { static constexpr double kH = 0.5 * 64.0 / 0.693147180559945309417232; };
 template <> struct Psi1Dom<float> { static constexpr double kH = 0.5 * 1.4426950408889634074; };

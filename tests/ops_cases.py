@@ -67,7 +67,8 @@ def check_det_layer(n, M, D, Do, prec, tol):
 
 
 MM_SHAPES = [(9, 6, 3, 2), (40, 5, 2, 1), (21, 50, 1, 4), (13, 12, 5, 3), (11, 7, 7, 2), (10, 9, 4, 6),
-             (12, 8, 3, 12), (9, 10, 2, 20), (8, 7, 5, 40), (35, 6, 16, 3), (14, 11, 4, 4), (16, 9, 3, 3)]
+             (12, 8, 3, 12), (9, 10, 2, 20), (8, 7, 5, 40), (35, 6, 16, 3), (14, 11, 4, 4), (16, 9, 3, 3),
+             (150, 12, 5, 50), (70, 9, 8, 9), (45, 13, 1, 64), (33, 6, 16, 7)]
 
 
 def check_mm_layer(n, M, Q, Do, prec, tol):
