@@ -2043,8 +2043,9 @@ struct MMWideMma {
     static constexpr size_t n_tab = ExpDom<double>::TAB;
     static constexpr size_t n_bs = 64 * LDP, n_dv = TR * LDV, n_psi = TR * LDP, n_lam = TR * LDP;
     static constexpr size_t n_Z = PCW * LDZ, n_R = TR * LDZ, n_rc = TR * RL;
-    static constexpr size_t smem_bytes = 8 * (n_tab + n_bs + n_dv + n_psi + n_lam + n_Z + n_R + n_rc);
-    static_assert(2 * Q <= 16, "moment columns must fit two 8-column blocks");
+    static constexpr size_t n_stage = n_dv + n_R + n_rc;     // per row tile, double buffered
+    static constexpr size_t smem_bytes = 8 * (n_tab + n_bs + n_psi + n_lam + n_Z + 2 * n_stage);
+    static_assert(2 * Q <= 16 && Q <= 8, "moment columns must fit two 8-column blocks");
     static_assert(n_psi + n_lam >= 64 * LDP, "the dBp staging aliases psi | lam");
 };
 
@@ -2056,13 +2057,11 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
     GPB_DYN_SMEM(dsm);
     double* s_tab = (double*)dsm;
     double* s_bs = s_tab + C::n_tab;     // [DOP8][LDP]   bs[d, p]
-    double* s_dv = s_bs + C::n_bs;       // [TR][LDV]     dv[r, d]
-    double* s_psi = s_dv + C::n_dv;      // [TR][LDP]     psi2'[r, p]
+    double* s_psi = s_bs + C::n_bs;      // [TR][LDP]     psi2'[r, p]
     double* s_lam = s_psi + C::n_psi;    // [TR][LDP]     Lam[r, p]
     double* s_Z = s_lam + C::n_lam;      // [PCW][LDZ]    zh | zh^2
-    double* s_R = s_Z + C::n_Z;          // [TR][LDZ]     c2 mu | c2
-    double* s_rc = s_R + C::n_R;         // [TR][RL]      expanded-form row constants
-    GPB_SHARED double s_l2[Q];
+    double* s_stage = s_Z + C::n_Z;      // 2 x { dv[TR][LDV] | R[TR][LDZ] = c2 mu | c2 | rc[TR][RL] }
+    GPB_SHARED double s_l2[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int lane16 = lane & (ExpDom<double>::REP - 1);
@@ -2083,7 +2082,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         else if (sc < 2 * Q) { const double zz = a.zh[(long)(sc - Q) * PP + pbase + p]; v = zz * zz; }
         s_Z[p * LDZ + sc] = v;
     }
-    if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+    if (tid < 8) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
     // SIMT phase: this thread's pair column and its rows ra, ra+4, ...
     const int pa = tid & (PCW - 1), ra = tid >> 6;
     double zh[Q], zh2[Q];
@@ -2092,46 +2091,87 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         zh[q] = a.zh[(long)q * PP + pbase + pa];
         zh2[q] = zh[q] * zh[q];
     }
-    double accB[8][2], accW[QB][2];
+    double accB[8][2], accW[QB][2], accW2[QB][2];
     GPB_UNROLL
     for (int i = 0; i < 8; i++) accB[i][0] = accB[i][1] = 0.0;
     GPB_UNROLL
-    for (int j = 0; j < QB; j++) accW[j][0] = accW[j][1] = 0.0;
+    for (int j = 0; j < QB; j++) accW[j][0] = accW[j][1] = accW2[j][0] = accW2[j][1] = 0.0;
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
-    sync_threads();
-    for (int t0 = r_begin; t0 < r_end; t0 += TR) {
+
+    // Stage one row tile in two halves so that the global-memory latency hides under the tensor
+    // phases: stage_load issues the loads of the NEXT tile (mu, vx of one (row, q) and 8 dv values
+    // per thread) into registers, stage_store turns them into shared-memory operands two phases
+    // later.  8 lanes per row (lane q of the group owns input dim q), the sums over q by shuffles.
+    // rc = expanded-form constants of the exponent in the scaled domain:
+    //   [0] = kS (lcn - sum c2 mu^2), [1+q] = 2 kS c2 mu, [1+Q+q] = -kS c2      (kernels.py:188-190)
+    double g_mu = 0.0, g_vx = 0.0, g_dv[8];
+    auto stage_load = [&](int t0) {
         const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
-        // ---- stage the row tile: constants of the exponent, R, dv ------------------------------
-        if (tid < TR) {
-            const int row = tid;
+        const int row = tid >> 3, q = tid & 7;
+        const bool ok = row < tv && q < a.Qa;
+        g_mu = ok ? a.mx[(long)(t0 + row) * a.Qa + q] : 0.0;
+        g_vx = ok ? a.vx[(long)(t0 + row) * a.Qa + q] : 0.0;
+        GPB_UNROLL
+        for (int i = 0; i < 8; i++) {
+            const int idx = tid + i * kThreads, r = idx >> 6, d = idx & 63;
+            g_dv[i] = (r < tv && d < Do) ? a.dv[(long)(t0 + r) * Do + d] : 0.0;
+        }
+    };
+    auto stage_store = [&](int buf, int t0) {
+        double* s_dv = s_stage + (size_t)buf * C::n_stage;
+        double* s_R = s_dv + C::n_dv;
+        double* s_rc = s_R + C::n_R;
+        const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+        {
+            const int row = tid >> 3, q = tid & 7;
             const bool ok = row < tv;
-            double lcn = 0.0, a0 = 0.0;
-            for (int q = 0; q < Q; q++) {
-                double mu = 0, c2 = 0;
-                if (ok && q < a.Qa) {
-                    mu = a.mx[(long)(t0 + row) * a.Qa + q];
-                    const double lq = s_l2[q];
-                    c2 = 1.0 / (2.0 * a.vx[(long)(t0 + row) * a.Qa + q] + lq);
-                    lcn += 0.5 * log(lq * c2);
-                }
-                const double c2s = c2 * kS;
+            double c2 = 0.0, pr = 1.0;
+            if (ok && q < a.Qa) {
+                const double lq = s_l2[q];
+                c2 = 1.0 / (2.0 * g_vx + lq);
+                pr = lq * c2;
+            }
+            const double mu = g_mu, c2s = c2 * kS;
+            double a0 = -c2s * mu * mu;
+            GPB_UNROLL
+            for (int m = 1; m < 8; m <<= 1) {
+                a0 += shfl_xor(a0, m);
+                pr *= shfl_xor(pr, m);
+            }
+            if (q < Q) {
                 s_rc[row * RL + 1 + q] = 2.0 * c2s * mu;
                 s_rc[row * RL + 1 + Q + q] = -c2s;
-                a0 -= c2s * mu * mu;
                 s_R[row * LDZ + q] = c2 * mu;
                 s_R[row * LDZ + Q + q] = c2;
             }
-            for (int sc = 2 * Q; sc < 16; sc++) s_R[row * LDZ + sc] = 0.0;
+            if (2 * Q + q < 16) s_R[row * LDZ + 2 * Q + q] = 0.0;
+            if (2 * Q + 8 + q < 16) s_R[row * LDZ + 2 * Q + 8 + q] = 0.0;
             // rows past the end: psi2' ~ 0 and their dv is 0
-            s_rc[row * RL] = (ok ? lcn : -1.0e5) * kS + a0;
+            if (q == 0) s_rc[row * RL] = (ok ? 0.5 * log(pr) : -1.0e5) * kS + a0;
         }
-        for (int i = tid; i < TR * 64; i += kThreads) {
-            const int r = i >> 6, d = i & 63;
-            s_dv[r * LDV + d] = (r < tv && d < Do) ? a.dv[(long)(t0 + r) * Do + d] : 0.0;
+        GPB_UNROLL
+        for (int i = 0; i < 8; i++) {
+            const int idx = tid + i * kThreads, r = idx >> 6, d = idx & 63;
+            s_dv[r * LDV + d] = g_dv[i];
         }
-        sync_threads();
+    };
+
+    sync_threads();
+    if (r_begin < r_end) {
+        stage_load(r_begin);
+        stage_store(0, r_begin);
+    }
+    sync_threads();
+    int buf = 0;
+    for (int t0 = r_begin; t0 < r_end; t0 += TR, buf ^= 1) {
+        const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
+        const double* s_dv = s_stage + (size_t)buf * C::n_stage;
+        const double* s_R = s_dv + C::n_dv;
+        const double* s_rc = s_R + C::n_R;
+        const bool more = t0 + TR < r_end;
+        if (more) stage_load(t0 + TR);      // loads in flight during the SIMT phase and G1
         // ---- SIMT phase: psi2'[r, p] ---------------------------------------------------------
         {
             double x[TR / 4];
@@ -2171,6 +2211,8 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
             }
         }
         sync_threads();
+        // next tile's constants / dv go to the other buffer while the products below run
+        if (more) stage_store(buf ^ 1, t0 + TR);
         // ---- G2: dBp[d, p] += dv^T psi2' (this warp: pair columns 8 warp .. +7, all d blocks) ----
         GPB_UNROLL_N(2)
         for (int k = 0; k < TR / 4; k++) {
@@ -2179,21 +2221,33 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
             for (int i = 0; i < 8; i++)
                 if (i < DB) dmma(accB[i][0], accB[i][1], s_dv[(4 * k + t) * LDV + 8 * i + g], bv);
         }
-        // ---- G3: W[p, s] += Lam^T R ------------------------------------------------------------
+        // ---- G3: W[p, s] += Lam^T R (even / odd k in separate accumulators: shorter chains) ----
         GPB_UNROLL_N(2)
-        for (int k = 0; k < TR / 4; k++) {
-            const double av = s_lam[(4 * k + t) * LDP + 8 * warp + g];
+        for (int k = 0; k < TR / 4; k += 2) {
+            const double av0 = s_lam[(4 * k + t) * LDP + 8 * warp + g];
+            const double av1 = s_lam[(4 * k + 4 + t) * LDP + 8 * warp + g];
             GPB_UNROLL
-            for (int j = 0; j < QB; j++) dmma(accW[j][0], accW[j][1], av, s_R[(4 * k + t) * LDZ + 8 * j + g]);
+            for (int j = 0; j < QB; j++) {
+                dmma(accW[j][0], accW[j][1], av0, s_R[(4 * k + t) * LDZ + 8 * j + g]);
+                dmma(accW2[j][0], accW2[j][1], av1, s_R[(4 * k + 4 + t) * LDZ + 8 * j + g]);
+            }
         }
         // ---- G4: V[r, s] = Lam Z -> row sums ---------------------------------------------------
         {
             const int rb = warp >> 1, cb = warp & 1;
             if (cb < QB) {
-                double v0 = 0.0, v1 = 0.0;
-                GPB_UNROLL_N(4)
-                for (int k = 0; k < PCW / 4; k++)
-                    dmma(v0, v1, s_lam[(8 * rb + g) * LDP + 4 * k + t], s_Z[(4 * k + t) * LDZ + 8 * cb + g]);
+                double vv[4][2];     // four independent chains over k
+                GPB_UNROLL
+                for (int c4 = 0; c4 < 4; c4++) vv[c4][0] = vv[c4][1] = 0.0;
+                GPB_UNROLL_N(2)
+                for (int k = 0; k < PCW / 4; k += 4) {
+                    GPB_UNROLL
+                    for (int c4 = 0; c4 < 4; c4++)
+                        dmma(vv[c4][0], vv[c4][1], s_lam[(8 * rb + g) * LDP + 4 * (k + c4) + t],
+                             s_Z[(4 * (k + c4) + t) * LDZ + 8 * cb + g]);
+                }
+                const double v0 = (vv[0][0] + vv[1][0]) + (vv[2][0] + vv[3][0]);
+                const double v1 = (vv[0][1] + vv[1][1]) + (vv[2][1] + vv[3][1]);
                 const int r = 8 * rb + g, sc = 8 * cb + 2 * t;
                 if (r < tv) {
                     if (sc < 2 * Q) atomic_add(a.rowacc + (long)(t0 + r) * (2 * Q) + sc, v0);
@@ -2201,7 +2255,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
                 }
             }
         }
-        sync_threads();     // tile buffers free
+        sync_threads();     // psi / lam free, next tile staged
     }
     // ---- pair sums of this (chunk, row split): {dBp_d, S0, S1_q} ------------------------------
     double* U = s_psi;      // [DOP8][LDP], aliases psi | lam
@@ -2214,8 +2268,8 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         }
     GPB_UNROLL
     for (int j = 0; j < QB; j++) {
-        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t] = accW[j][0];
-        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t + 1] = accW[j][1];
+        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t] = accW[j][0] + accW2[j][0];
+        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t + 1] = accW[j][1] + accW2[j][1];
     }
     sync_threads();
     double* rec = a.pairpart + (long)blockIdx.y * (Do + 1 + Q) * PP;
