@@ -330,6 +330,30 @@ int mm_bwd_wide_mma_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, void
 #undef GPB_CALL
 }
 
+template <int QT>
+int mm_fwd_wide_mma_launch(const MMPlan& p, const gpb::MMArgs<double>& a, void* stream) {
+    if constexpr (QT <= 8) {
+        typedef gpb::MMFwdWideMma<QT> C;
+        auto kern = gpb::mm_fwd_wide_mma_kernel<QT>;
+        if (mm_pairs_smem(kern, C::smem_bytes)) return GPB_ERR_CUDA;
+        const int DOP8 = (a.Do + 7) / 8 * 8;
+        const int nrb = (int)cdiv(a.n, C::TRF);
+        const int grid = nrb < sm_count() ? nrb : sm_count();     // one persistent CTA per SM
+        prof_begin(3, stream);
+        GPB_LAUNCH(kern, dim3(grid), dim3(256), C::smem_bytes, stream, a, DOP8, (int)(p.PP / C::PCW));
+        prof_end(3, stream);
+        return GPB_OK;
+    } else {
+        (void)p; (void)a; (void)stream;
+        return fail(GPB_ERR_ARG, "mm_fwd_wide_mma: Q template %d unsupported", QT);
+    }
+}
+int mm_fwd_wide_mma_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, void* stream) {
+#define GPB_CALL(QT) mm_fwd_wide_mma_launch<QT>(p, a, stream)
+    GPB_QT_SWITCH(GPB_CALL);
+#undef GPB_CALL
+}
+
 template <typename T>
 int mm_check(int n, int M, int Q, int Do) {
     if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
@@ -357,10 +381,20 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
     a.mx = mx; a.vx = vx; a.ls = ls; a.zh = w.zh; a.ep = w.ep; a.bs = w.bs; a.dv = nullptr;
     a.n = n; a.Qa = Q; a.Do = Do; a.PP = p.PP; a.rows_per_split = p.rows_per_split;
     a.rowacc = w.rowacc; a.pairpart = nullptr; a.full_coef = 0; a.lam_pass = 0;
-    if (Do > 4) {      // wide layers: row-owner kernel (psi2 evaluated once per row and pair)
+    if (Do > 4) {      // wide layers: psi2 evaluated once per row and pair
         a.d0 = 0;
-        rc = mm_fwd_wide_dispatch<T>(p, a, n, Do, stream);
-        if (rc) return rc;
+        bool done = false;
+        if constexpr (sizeof(T) == 8) {
+            if (p.Qt <= 8) {    // fp64: contraction on the FP64 tensor cores
+                rc = mm_fwd_wide_mma_dispatch(p, a, stream);
+                if (rc) return rc;
+                done = true;
+            }
+        }
+        if (!done) {            // fp32 / Q = 16: SIMT row-owner kernel
+            rc = mm_fwd_wide_dispatch<T>(p, a, n, Do, stream);
+            if (rc) return rc;
+        }
     } else {
         for (int pass = 0; pass < p.npass; pass++) {
             a.d0 = pass * p.DOC;

@@ -2287,6 +2287,152 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
     }
 }
 
+// Forward contraction for WIDE output layers (Do > 4, fp64) on the FP64 tensor cores:
+//   vacc[r, d] = sum_p bs[d, p] psi2'[r, p]                                  (aep_models.py:196-198)
+// A CTA owns 64 rows at a time and sweeps ALL pair chunks: per chunk of 64 pairs the SIMT phase
+// evaluates psi2'[64 x 64] into shared memory (one pair column and 16 rows per thread) and the
+// product runs transposed as DMMA tiles, V^T[d, r] += bs[d, p] psi2'[r, p]^T, so that both
+// operands are read with the conflict-free fragment pattern; warp w keeps the 8 rows 8w..8w+7 for
+// every output block (<= 16 accumulators per thread).  The sums leave the CTA complete: plain
+// stores, no atomics, no per-chunk partials (the SIMT row-owner kernel needed 255 registers and was
+// shared-memory bound on the per-pair weight broadcasts).
+template <int Q>
+struct MMFwdWideMma {
+    static constexpr int PCW = 64, TRF = 64, LDP = PCW + 4;
+    static constexpr int RL = (1 + 2 * Q + 1) / 2 * 2;
+    static constexpr size_t n_tab = ExpDom<double>::TAB;
+    static constexpr size_t n_bs = 64 * LDP, n_psi = TRF * LDP, n_rc = TRF * RL;
+    static constexpr size_t smem_bytes = 8 * (n_tab + n_bs + n_psi + n_rc);
+    static_assert(Q <= 8, "8 staging lanes per row");
+};
+
+template <int Q>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_fwd_wide_mma_kernel(MMArgs<double> a, int DOP8, int nchunks) {
+    typedef MMFwdWideMma<Q> C;
+    constexpr int PCW = C::PCW, TRF = C::TRF, LDP = C::LDP, RL = C::RL;
+    constexpr double kS = ExpDom<double>::S;
+    GPB_DYN_SMEM(dsm);
+    double* s_tab = (double*)dsm;
+    double* s_bs = s_tab + C::n_tab;     // [DOP8][LDP]   bs[d, p] of the current chunk
+    double* s_psi = s_bs + C::n_bs;      // [TRF][LDP]    psi2'[r, p]
+    double* s_rc = s_psi + C::n_psi;     // [TRF][RL]     expanded-form row constants
+    GPB_SHARED double s_l2[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int lane16 = lane & (ExpDom<double>::REP - 1);
+    const long PP = a.PP;
+    const int Do = a.Do, DB = DOP8 / 8;
+    const int pa = tid & (PCW - 1), ra = tid >> 6;
+
+    for (int i = tid; i < (int)C::n_tab; i += kThreads)
+        s_tab[i] = exp2((double)(i / ExpDom<double>::REP) * (1.0 / ExpDom<double>::ENT));
+    if (tid < 8) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
+    sync_threads();
+
+    const int nrb = (a.n + TRF - 1) / TRF;
+    for (int rbk = blockIdx.x; rbk < nrb; rbk += gridDim.x) {
+        const int t0 = rbk * TRF;
+        const int tv = (a.n - t0) < TRF ? (a.n - t0) : TRF;
+        // row constants: 8 lanes per row, two rows per 8-lane group (kernels.py:188-190)
+        GPB_UNROLL
+        for (int h = 0; h < TRF / 32; h++) {
+            const int row = (tid >> 3) + 32 * h, q = tid & 7;
+            const bool ok = row < tv;
+            double mu = 0.0, c2 = 0.0, pr = 1.0;
+            if (ok && q < a.Qa) {
+                mu = a.mx[(long)(t0 + row) * a.Qa + q];
+                const double lq = s_l2[q];
+                c2 = 1.0 / (2.0 * a.vx[(long)(t0 + row) * a.Qa + q] + lq);
+                pr = lq * c2;
+            }
+            const double c2s = c2 * kS;
+            double a0 = -c2s * mu * mu;
+            GPB_UNROLL
+            for (int m = 1; m < 8; m <<= 1) {
+                a0 += shfl_xor(a0, m);
+                pr *= shfl_xor(pr, m);
+            }
+            if (q < Q) {
+                s_rc[row * RL + 1 + q] = 2.0 * c2s * mu;
+                s_rc[row * RL + 1 + Q + q] = -c2s;
+            }
+            if (q == 0) s_rc[row * RL] = (ok ? 0.5 * log(pr) : -1.0e5) * kS + a0;
+        }
+        double acc[8][2];
+        GPB_UNROLL
+        for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = 0.0;
+        sync_threads();
+        // the weights / pair centres of chunk ch+1 are fetched into registers while chunk ch is
+        // processed (global latency hidden under the SIMT and tensor phases)
+        double g_bs[16], g_zh[Q];
+        auto fetch = [&](int ch) {
+            const long pb = (long)ch * PCW;
+            GPB_UNROLL
+            for (int i = 0; i < 16; i++) {
+                const int idx = tid + i * kThreads, d = idx >> 6, p = idx & 63;
+                g_bs[i] = d < Do ? a.bs[(long)d * PP + pb + p] : 0.0;
+            }
+            GPB_UNROLL
+            for (int q = 0; q < Q; q++) g_zh[q] = a.zh[(long)q * PP + pb + pa];
+        };
+        fetch(0);
+        for (int ch = 0; ch < nchunks; ch++) {
+            // this chunk's weights -> shared memory
+            GPB_UNROLL
+            for (int i = 0; i < 16; i++) {
+                const int idx = tid + i * kThreads, d = idx >> 6, p = idx & 63;
+                if (d < DOP8) s_bs[d * LDP + p] = g_bs[i];
+            }
+            // SIMT phase: psi2' of this thread's pair column for its 16 rows, 8 at a time
+            double zh[Q], zh2[Q];
+            GPB_UNROLL
+            for (int q = 0; q < Q; q++) {
+                zh[q] = g_zh[q];
+                zh2[q] = zh[q] * zh[q];
+            }
+            if (ch + 1 < nchunks) fetch(ch + 1);
+            GPB_UNROLL
+            for (int h = 0; h < 2; h++) {
+                double x[8];
+                GPB_UNROLL
+                for (int i = 0; i < 8; i++) {
+                    const double* rc = s_rc + (ra + 4 * (i + 8 * h)) * RL;
+                    double xx = rc[0];
+                    GPB_UNROLL
+                    for (int q = 0; q < Q; q++) {
+                        xx += rc[1 + q] * zh[q];
+                        xx += rc[1 + Q + q] * zh2[q];
+                    }
+                    x[i] = xx;
+                }
+                exp_dom_n<8>(x, s_tab, lane16);
+                GPB_UNROLL
+                for (int i = 0; i < 8; i++) s_psi[(ra + 4 * (i + 8 * h)) * LDP + pa] = x[i];
+            }
+            sync_threads();
+            // V^T[d, r] += bs[d, p] psi2'[r, p]: b = psi2'[r = 8 warp + g][p = 4k + t]
+            GPB_UNROLL_N(2)
+            for (int k = 0; k < PCW / 4; k++) {
+                const double bv = s_psi[(8 * warp + g) * LDP + 4 * k + t];
+                GPB_UNROLL
+                for (int i = 0; i < 8; i++)
+                    if (i < DB) dmma(acc[i][0], acc[i][1], s_bs[(8 * i + g) * LDP + 4 * k + t], bv);
+            }
+            sync_threads();     // s_bs / s_psi free
+        }
+        // c0 = V^T[d = 8i + g][r = 8 warp + 2t], c1: r + 1
+        GPB_UNROLL
+        for (int i = 0; i < 8; i++)
+            if (i < DB) {
+                const int d = 8 * i + g, r = 8 * warp + 2 * t;
+                if (d < Do) {
+                    if (r < tv) a.rowacc[(long)(t0 + r) * Do + d] = acc[i][0];
+                    if (r + 1 < tv) a.rowacc[(long)(t0 + r + 1) * Do + d] = acc[i][1];
+                }
+            }
+    }
+}
+
 template <typename T> struct Psi1Dom;   // exponent scale folded into c1 (argument of exp is -e)
 template <> struct Psi1Dom<double> { static constexpr double kH = 0.5 * 64.0 / 0.693147180559945309417232; };
 template <> struct Psi1Dom<float> { static constexpr double kH = 0.5 * 1.4426950408889634074; };
