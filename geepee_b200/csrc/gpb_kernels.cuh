@@ -2214,7 +2214,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         // next tile's constants / dv go to the other buffer while the products below run
         if (more) stage_store(buf ^ 1, t0 + TR);
         // ---- G2: dBp[d, p] += dv^T psi2' (this warp: pair columns 8 warp .. +7, all d blocks) ----
-        GPB_UNROLL_N(2)
+        GPB_UNROLL
         for (int k = 0; k < TR / 4; k++) {
             const double bv = s_psi[(4 * k + t) * LDP + 8 * warp + g];
             GPB_UNROLL
@@ -2222,7 +2222,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
                 if (i < DB) dmma(accB[i][0], accB[i][1], s_dv[(4 * k + t) * LDV + 8 * i + g], bv);
         }
         // ---- G3: W[p, s] += Lam^T R (even / odd k in separate accumulators: shorter chains) ----
-        GPB_UNROLL_N(2)
+        GPB_UNROLL
         for (int k = 0; k < TR / 4; k += 2) {
             const double av0 = s_lam[(4 * k + t) * LDP + 8 * warp + g];
             const double av1 = s_lam[(4 * k + 4 + t) * LDP + 8 * warp + g];
@@ -2239,7 +2239,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
                 double vv[4][2];     // four independent chains over k
                 GPB_UNROLL
                 for (int c4 = 0; c4 < 4; c4++) vv[c4][0] = vv[c4][1] = 0.0;
-                GPB_UNROLL_N(2)
+                GPB_UNROLL
                 for (int k = 0; k < PCW / 4; k += 4) {
                     GPB_UNROLL
                     for (int c4 = 0; c4 < 4; c4++)
