@@ -311,12 +311,13 @@ template <int QT>
 int mm_bwd_wide_mma_launch(const MMPlan& p, gpb::MMArgs<double> a, void* stream) {
     if constexpr (QT <= 8) {
         typedef gpb::MMWideMma<QT> C;
-        auto kern = gpb::mm_bwd_wide_mma_kernel<QT>;
+        constexpr int NW = GPB_MM_WIDE_WARPS;
+        auto kern = gpb::mm_bwd_wide_mma_kernel<QT, NW>;
         if (mm_pairs_smem(kern, C::smem_bytes)) return GPB_ERR_CUDA;
         a.rows_per_split = p.w_rows_per_split;
         const int DOP8 = (a.Do + 7) / 8 * 8;
         prof_begin(4, stream);
-        GPB_LAUNCH(kern, dim3(p.w_nchunks, p.w_nsplit), dim3(256), C::smem_bytes, stream, a, DOP8);
+        GPB_LAUNCH(kern, dim3(p.w_nchunks, p.w_nsplit), dim3(NW * 32), C::smem_bytes, stream, a, DOP8);
         prof_end(4, stream);
         return GPB_OK;
     } else {

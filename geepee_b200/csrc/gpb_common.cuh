@@ -23,6 +23,10 @@
 #ifndef GPB_MM_NR_FWD
 #define GPB_MM_NR_FWD 2
 #endif
+// warps per CTA of the wide-layer tensor-core backward (8 or 16; measured equal on the B200: 14.17 vs 14.04 ms at the cfg2 shape)
+#ifndef GPB_MM_WIDE_WARPS
+#define GPB_MM_WIDE_WARPS 8
+#endif
 #include "../../include/geepee_b200.h"
 #include "gpb_kernels.cuh"
 

@@ -2049,10 +2049,18 @@ struct MMWideMma {
     static_assert(n_psi + n_lam >= 64 * LDP, "the dBp staging aliases psi | lam");
 };
 
-template <int Q>
-GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, int DOP8) {
+// NW = warps per CTA (8 or 16).  With 16 warps the tiles of every product are spread over twice as
+// many warps (4 per scheduler instead of 2 hide the DMMA / shared-memory latencies between the
+// barriers); G3 and G4 then run side by side on the two warp halves.
+template <int Q, int NW>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(NW * 32) mm_bwd_wide_mma_kernel(MMArgs<double> a, int DOP8) {
     typedef MMWideMma<Q> C;
     constexpr int PCW = C::PCW, TR = C::TR, LDP = C::LDP, LDV = C::LDV, LDZ = C::LDZ, QB = C::QB, RL = C::RL;
+    constexpr int NT = NW * 32;
+    constexpr int RPT = TR * PCW / NT, RSTEP = NT / PCW;     // SIMT phase: rows per thread / row stride
+    constexpr int DVT = TR * 64 / NT;                        // dv values staged per thread
+    constexpr int NJ = 32 / NW;                              // G1: column blocks per warp
+    constexpr int DSTEP = NW / 8, NI = 8 / DSTEP;            // G2: d-blocks interleaved over warp halves
     constexpr double kS = ExpDom<double>::S;
     GPB_DYN_SMEM(dsm);
     double* s_tab = (double*)dsm;
@@ -2069,13 +2077,13 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
     const long PP = a.PP;
     const int Do = a.Do, DB = DOP8 / 8, KB1 = DOP8 / 4;
 
-    for (int i = tid; i < (int)C::n_tab; i += kThreads)
+    for (int i = tid; i < (int)C::n_tab; i += NT)
         s_tab[i] = exp2((double)(i / ExpDom<double>::REP) * (1.0 / ExpDom<double>::ENT));
-    for (int i = tid; i < 64 * PCW; i += kThreads) {
+    for (int i = tid; i < 64 * PCW; i += NT) {
         const int d = i / PCW, p = i - d * PCW;
         s_bs[d * LDP + p] = d < Do ? a.bs[(long)d * PP + pbase + p] : 0.0;
     }
-    for (int i = tid; i < PCW * 16; i += kThreads) {
+    for (int i = tid; i < PCW * 16; i += NT) {
         const int p = i >> 4, sc = i & 15;
         double v = 0.0;
         if (sc < Q) v = a.zh[(long)sc * PP + pbase + p];
@@ -2083,7 +2091,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         s_Z[p * LDZ + sc] = v;
     }
     if (tid < 8) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
-    // SIMT phase: this thread's pair column and its rows ra, ra+4, ...
+    // SIMT phase: this thread's pair column and its rows ra, ra + RSTEP, ...
     const int pa = tid & (PCW - 1), ra = tid >> 6;
     double zh[Q], zh2[Q];
     GPB_UNROLL
@@ -2091,31 +2099,33 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         zh[q] = a.zh[(long)q * PP + pbase + pa];
         zh2[q] = zh[q] * zh[q];
     }
-    double accB[8][2], accW[QB][2], accW2[QB][2];
+    double accB[NI][2], accW[QB][2], accW2[QB][2];
     GPB_UNROLL
-    for (int i = 0; i < 8; i++) accB[i][0] = accB[i][1] = 0.0;
+    for (int i = 0; i < NI; i++) accB[i][0] = accB[i][1] = 0.0;
     GPB_UNROLL
     for (int j = 0; j < QB; j++) accW[j][0] = accW[j][1] = accW2[j][0] = accW2[j][1] = 0.0;
+    const int cbw = warp & 7, dpar = warp >> 3;              // G2 / G3: this warp's pair block
+    const bool do_g3 = NW == 8 || warp >= 8, do_g4 = NW == 8 || warp < 8;
 
     const int r_begin = blockIdx.y * a.rows_per_split;
     const int r_end = (r_begin + a.rows_per_split) < a.n ? (r_begin + a.rows_per_split) : a.n;
 
     // Stage one row tile in two halves so that the global-memory latency hides under the tensor
-    // phases: stage_load issues the loads of the NEXT tile (mu, vx of one (row, q) and 8 dv values
+    // phases: stage_load issues the loads of the NEXT tile (mu, vx of one (row, q) and DVT dv values
     // per thread) into registers, stage_store turns them into shared-memory operands two phases
     // later.  8 lanes per row (lane q of the group owns input dim q), the sums over q by shuffles.
     // rc = expanded-form constants of the exponent in the scaled domain:
     //   [0] = kS (lcn - sum c2 mu^2), [1+q] = 2 kS c2 mu, [1+Q+q] = -kS c2      (kernels.py:188-190)
-    double g_mu = 0.0, g_vx = 0.0, g_dv[8];
+    double g_mu = 0.0, g_vx = 0.0, g_dv[DVT];
     auto stage_load = [&](int t0) {
         const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
         const int row = tid >> 3, q = tid & 7;
-        const bool ok = row < tv && q < a.Qa;
+        const bool ok = row < tv && q < a.Qa;      // (row >= TR for the upper half of a 16-warp CTA)
         g_mu = ok ? a.mx[(long)(t0 + row) * a.Qa + q] : 0.0;
         g_vx = ok ? a.vx[(long)(t0 + row) * a.Qa + q] : 0.0;
         GPB_UNROLL
-        for (int i = 0; i < 8; i++) {
-            const int idx = tid + i * kThreads, r = idx >> 6, d = idx & 63;
+        for (int i = 0; i < DVT; i++) {
+            const int idx = tid + i * NT, r = idx >> 6, d = idx & 63;
             g_dv[i] = (r < tv && d < Do) ? a.dv[(long)(t0 + r) * Do + d] : 0.0;
         }
     };
@@ -2124,7 +2134,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         double* s_R = s_dv + C::n_dv;
         double* s_rc = s_R + C::n_R;
         const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
-        {
+        if (tid < TR * 8) {      // whole warps (TR * 8 = 256)
             const int row = tid >> 3, q = tid & 7;
             const bool ok = row < tv;
             double c2 = 0.0, pr = 1.0;
@@ -2152,8 +2162,8 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
             if (q == 0) s_rc[row * RL] = (ok ? 0.5 * log(pr) : -1.0e5) * kS + a0;
         }
         GPB_UNROLL
-        for (int i = 0; i < 8; i++) {
-            const int idx = tid + i * kThreads, r = idx >> 6, d = idx & 63;
+        for (int i = 0; i < DVT; i++) {
+            const int idx = tid + i * NT, r = idx >> 6, d = idx & 63;
             s_dv[r * LDV + d] = g_dv[i];
         }
     };
@@ -2174,10 +2184,10 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         if (more) stage_load(t0 + TR);      // loads in flight during the SIMT phase and G1
         // ---- SIMT phase: psi2'[r, p] ---------------------------------------------------------
         {
-            double x[TR / 4];
+            double x[RPT];
             GPB_UNROLL
-            for (int i = 0; i < TR / 4; i++) {
-                const double* rc = s_rc + (ra + 4 * i) * RL;
+            for (int i = 0; i < RPT; i++) {
+                const double* rc = s_rc + (ra + RSTEP * i) * RL;
                 double xx = rc[0];
                 GPB_UNROLL
                 for (int q = 0; q < Q; q++) {
@@ -2186,25 +2196,25 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
                 }
                 x[i] = xx;
             }
-            exp_dom_n<TR / 4>(x, s_tab, lane16);
+            exp_dom_n<RPT>(x, s_tab, lane16);
             GPB_UNROLL
-            for (int i = 0; i < TR / 4; i++) s_psi[(ra + 4 * i) * LDP + pa] = x[i];
+            for (int i = 0; i < RPT; i++) s_psi[(ra + RSTEP * i) * LDP + pa] = x[i];
         }
         sync_threads();
         // ---- G1: Lam = (dv . bs) * psi2' -----------------------------------------------------
         {
-            const int rb = warp >> 1, cb0 = (warp & 1) * 4;
-            double c[4][2];
+            const int rb = warp / (8 / NJ), cb0 = (warp % (8 / NJ)) * NJ;
+            double c[NJ][2];
             GPB_UNROLL
-            for (int j = 0; j < 4; j++) c[j][0] = c[j][1] = 0.0;
+            for (int j = 0; j < NJ; j++) c[j][0] = c[j][1] = 0.0;
             for (int k = 0; k < KB1; k++) {
                 const double av = s_dv[(8 * rb + g) * LDV + 4 * k + t];
                 GPB_UNROLL
-                for (int j = 0; j < 4; j++)
+                for (int j = 0; j < NJ; j++)
                     dmma(c[j][0], c[j][1], av, s_bs[(4 * k + t) * LDP + 8 * (cb0 + j) + g]);
             }
             GPB_UNROLL
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NJ; j++) {
                 const int idx = (8 * rb + g) * LDP + 8 * (cb0 + j) + 2 * t;
                 s_lam[idx] = c[j][0] * s_psi[idx];
                 s_lam[idx + 1] = c[j][1] * s_psi[idx + 1];
@@ -2213,28 +2223,31 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
         sync_threads();
         // next tile's constants / dv go to the other buffer while the products below run
         if (more) stage_store(buf ^ 1, t0 + TR);
-        // ---- G2: dBp[d, p] += dv^T psi2' (this warp: pair columns 8 warp .. +7, all d blocks) ----
+        // ---- G2: dBp[d, p] += dv^T psi2' (pair columns 8 cbw .. +7, d blocks dpar, dpar + DSTEP, ..) ----
         GPB_UNROLL
         for (int k = 0; k < TR / 4; k++) {
-            const double bv = s_psi[(4 * k + t) * LDP + 8 * warp + g];
+            const double bv = s_psi[(4 * k + t) * LDP + 8 * cbw + g];
             GPB_UNROLL
-            for (int i = 0; i < 8; i++)
-                if (i < DB) dmma(accB[i][0], accB[i][1], s_dv[(4 * k + t) * LDV + 8 * i + g], bv);
+            for (int i = 0; i < NI; i++)
+                if (dpar + DSTEP * i < DB)
+                    dmma(accB[i][0], accB[i][1], s_dv[(4 * k + t) * LDV + 8 * (dpar + DSTEP * i) + g], bv);
         }
         // ---- G3: W[p, s] += Lam^T R (even / odd k in separate accumulators: shorter chains) ----
-        GPB_UNROLL
-        for (int k = 0; k < TR / 4; k += 2) {
-            const double av0 = s_lam[(4 * k + t) * LDP + 8 * warp + g];
-            const double av1 = s_lam[(4 * k + 4 + t) * LDP + 8 * warp + g];
+        if (do_g3) {
             GPB_UNROLL
-            for (int j = 0; j < QB; j++) {
-                dmma(accW[j][0], accW[j][1], av0, s_R[(4 * k + t) * LDZ + 8 * j + g]);
-                dmma(accW2[j][0], accW2[j][1], av1, s_R[(4 * k + 4 + t) * LDZ + 8 * j + g]);
+            for (int k = 0; k < TR / 4; k += 2) {
+                const double av0 = s_lam[(4 * k + t) * LDP + 8 * cbw + g];
+                const double av1 = s_lam[(4 * k + 4 + t) * LDP + 8 * cbw + g];
+                GPB_UNROLL
+                for (int j = 0; j < QB; j++) {
+                    dmma(accW[j][0], accW[j][1], av0, s_R[(4 * k + t) * LDZ + 8 * j + g]);
+                    dmma(accW2[j][0], accW2[j][1], av1, s_R[(4 * k + 4 + t) * LDZ + 8 * j + g]);
+                }
             }
         }
         // ---- G4: V[r, s] = Lam Z -> row sums ---------------------------------------------------
-        {
-            const int rb = warp >> 1, cb = warp & 1;
+        if (do_g4) {
+            const int rb = cbw >> 1, cb = cbw & 1;
             if (cb < QB) {
                 double vv[4][2];     // four independent chains over k
                 GPB_UNROLL
@@ -2261,19 +2274,22 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_bwd_wide_mma_kernel(MMArgs<double> a, 
     double* U = s_psi;      // [DOP8][LDP], aliases psi | lam
     double* WS = s_Z;       // [PCW][LDZ]
     GPB_UNROLL
-    for (int i = 0; i < 8; i++)
-        if (i < DB) {
-            U[(8 * i + g) * LDP + 8 * warp + 2 * t] = accB[i][0];
-            U[(8 * i + g) * LDP + 8 * warp + 2 * t + 1] = accB[i][1];
+    for (int i = 0; i < NI; i++)
+        if (dpar + DSTEP * i < DB) {
+            const int d = 8 * (dpar + DSTEP * i) + g;
+            U[d * LDP + 8 * cbw + 2 * t] = accB[i][0];
+            U[d * LDP + 8 * cbw + 2 * t + 1] = accB[i][1];
         }
-    GPB_UNROLL
-    for (int j = 0; j < QB; j++) {
-        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t] = accW[j][0] + accW2[j][0];
-        WS[(8 * warp + g) * LDZ + 8 * j + 2 * t + 1] = accW[j][1] + accW2[j][1];
+    if (do_g3) {
+        GPB_UNROLL
+        for (int j = 0; j < QB; j++) {
+            WS[(8 * cbw + g) * LDZ + 8 * j + 2 * t] = accW[j][0] + accW2[j][0];
+            WS[(8 * cbw + g) * LDZ + 8 * j + 2 * t + 1] = accW[j][1] + accW2[j][1];
+        }
     }
     sync_threads();
     double* rec = a.pairpart + (long)blockIdx.y * (Do + 1 + Q) * PP;
-    for (int i = tid; i < Do * PCW; i += kThreads) {
+    for (int i = tid; i < Do * PCW; i += NT) {
         const int d = i / PCW, p = i - d * PCW;
         rec[(long)d * PP + pbase + p] = a.ep[pbase + p] * U[d * LDP + p];
     }
