@@ -8,20 +8,23 @@
 #pragma once
 // Development knobs of the fp64 pair kernels (A/B builds, geepee_b200/build.py); the defaults are the
 // product configuration.  GPB_MM_RP64: cap on the pairs a thread owns (0 = automatic);
-// GPB_MM_MINBLOCKS: resident CTAs per SM requested through __launch_bounds__;
 // GPB_EXP_REP: replicas of the exp table in shared memory; GPB_MM_NR_FWD: rows per loop trip of
 // the forward kernel.
 #ifndef GPB_MM_RP64
 #define GPB_MM_RP64 0
 #endif
-#ifndef GPB_MM_MINBLOCKS
-#define GPB_MM_MINBLOCKS 1
-#endif
+// (a second __launch_bounds__ argument is deliberately NOT exposed: `(256, 1)` let ptxas take 176
+//  registers for the backward kernel -> one CTA per SM, +12 % time; `(256, 3)` is the rejected
+//  3-CTA experiment of DESIGN.md section 7)
 #ifndef GPB_EXP_REP
 #define GPB_EXP_REP 16
 #endif
 #ifndef GPB_MM_NR_FWD
 #define GPB_MM_NR_FWD 2
+#endif
+// 1: __launch_bounds__(256, 2) on the pair kernels (register cap 128 for every instantiation)
+#ifndef GPB_MM_LB2
+#define GPB_MM_LB2 0
 #endif
 // warps per CTA of the wide-layer tensor-core backward (8 or 16; measured equal on the B200: 14.17 vs 14.04 ms at the cfg2 shape)
 #ifndef GPB_MM_WIDE_WARPS

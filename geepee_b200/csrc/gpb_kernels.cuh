@@ -1595,7 +1595,11 @@ struct RowXpose {
 // GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
 // GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
 template <typename T, int Q, int DOC, bool BWD, bool GEN>
-GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, GPB_MM_MINBLOCKS) mm_pairs_kernel(MMArgs<T> a) {
+#if GPB_MM_LB2
+GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairs_kernel(MMArgs<T> a) {
+#else
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
+#endif
     typedef MMCfg<T, Q, DOC> C;
     constexpr int RP = C::RP, TR = C::TR;
     constexpr int NS = BWD ? 2 * Q : DOC;
