@@ -13,7 +13,7 @@ from scipy.optimize import minimize
 
 from . import config, dist
 from .config import PROP_MM, PROP_MC, PROP_LIN
-from .layers import default_device, to_dev, pack_to_device, to_host
+from .layers import _host_copy, default_device, to_dev, pack_to_device, to_host
 from .lik_layers import Gauss_Layer, Probit_Layer, Gauss_Emis
 from .utils import ObjectiveWrapper, flatten_dict, unflatten_dict, adam, PCA_reduce
 
@@ -110,7 +110,9 @@ class Base_Model(object):
         out, off = {}, 1
         for k in keys:
             n = grads[k].numel()
-            out[k] = host[off:off + n].reshape(tuple(grads[k].shape)).copy()
+            arr = np.empty(n, dtype=np.float64)
+            _host_copy(arr, host[off:off + n])
+            out[k] = arr.reshape(tuple(grads[k].shape))
             off += n
         for p in self.fixed_params:
             out[p] = np.zeros_like(out[p])

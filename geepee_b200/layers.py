@@ -53,6 +53,29 @@ def _pinned(device, n, slot):
     return buf
 
 
+_BIG = 1 << 20          # elements: arrays above this are copied by several host threads
+_POOL = None
+
+
+def _host_copy(dst, src):
+    """dst[:] = src for flat fp64 numpy views; large copies are split over a few threads (numpy
+    releases the GIL in memcpy; one core moves ~8 GB/s, the latent arrays of an SGPSSM / SGPLVM with
+    1e6 rows are 32 MB per parameter and direction)."""
+    n = src.size
+    if n < _BIG:
+        dst[:] = src
+        return
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4)
+    step = (n + 3) // 4
+
+    def part(i):
+        dst[i:i + step] = src[i:i + step]
+    list(_POOL.map(part, range(0, n, step)))
+
+
 def pack_to_device(params, device):
     """Upload a whole parameter dict with ONE host->device copy; returns {key: fp64 device view}.
     On a GPU the arrays are gathered straight into a pinned staging buffer (no pageable bounce:
@@ -68,7 +91,7 @@ def pack_to_device(params, device):
         view = pin.numpy()
         off = 0
         for a in arrs:
-            view[off:off + a.size] = a.reshape(-1)
+            _host_copy(view[off:off + a.size], a.reshape(-1))
             off += a.size
         t = torch.empty(total, dtype=torch.float64, device=device)
         t.copy_(pin[:total], non_blocking=True)

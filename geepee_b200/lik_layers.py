@@ -55,6 +55,39 @@ class Probit_Layer(Lik_Layer):
         dm, dv, o = ops.probit_lik(m, v, y, self._gx, self._gw, 1.0, scale, 1)
         return dm, dv, o[0], o[1].reshape(())
 
+    def _log_Z_mc(self, m, v, y, alpha, scale):
+        """lik_layers.py:364-409: m, v [K,n,D] from K Monte-Carlo samples; log-mean-exp over the
+        samples of the per-sample tilted log-partitions (elementwise, on the device; the
+        reference's eps = 1e-16 and its `+ eps` on the derivatives kept)."""
+        eps = 1e-16
+        yy = y.unsqueeze(0)
+        if alpha == 1.0:
+            t = yy * m / torch.sqrt(1 + v)
+            Z = 0.5 * (1 + torch.erf(t / np.sqrt(2)))
+            lt = torch.log(Z + eps)
+        else:
+            gx = self._gx.reshape(-1, 1, 1, 1)
+            gw = self._gw.reshape(-1, 1, 1, 1)
+            ts = gx * torch.sqrt(2 * v) + m
+            pdfs = 0.5 * (1 + torch.erf(yy * ts / np.sqrt(2))) + eps
+            Zt = (pdfs**alpha * gw).sum(0) / np.sqrt(np.pi)
+            lt = torch.log(Zt)
+        lmax = lt.max(dim=0).values
+        ex = torch.exp(lt - lmax)
+        se = ex.sum(0)
+        logZ = (lmax + torch.log(se) - np.log(m.shape[0])).sum()
+        w = ex / se
+        if alpha == 1.0:
+            dt = 1 / (Z + eps) / np.sqrt(2 * np.pi) * torch.exp(-t**2 / 2)
+            dm = w * dt * yy / torch.sqrt(1 + v)
+            dv = w * dt * (-0.5 * yy * m / (1 + v)**1.5)
+        else:
+            a = pdfs**(alpha - 1.0) * torch.exp(-ts**2 / 2)
+            dm = w * ((gw * a).sum(0) * yy * alpha / np.pi / np.sqrt(2)) / Zt + eps
+            dv = w * ((gw * (a * gx)).sum(0) * yy * alpha / np.pi / np.sqrt(2) / torch.sqrt(2 * v)) / Zt + eps
+        zero = torch.zeros((), dtype=_F, device=m.device)
+        return (scale * dm).contiguous(), (scale * dv).contiguous(), logZ, zero
+
     # ---- reference API (numpy) ---------------------------------------------------------------
     def compute_log_Z(self, mout, vout, y, alpha=1.0, compute_dm2=False):
         if mout.ndim != 2 or compute_dm2:

@@ -586,6 +586,36 @@ def probit_log_Z(mout, vout, y, alpha):
     return logZ, dZdm / Zt + eps, dZdv / Zt + eps
 
 
+def probit_log_Z_mc(mout, vout, y, alpha):
+    """lik_layers.py:364-409 Probit_Layer.compute_log_Z, 3-D branch: log-mean-exp over the samples on
+    axis 0 (note eps = 1e-16 here, 1e-8 in the 2-D quadrature branch, and the `+ eps` on dm, dv)."""
+    from scipy import special
+    eps = 1e-16
+    if alpha == 1.0:
+        t = y * mout / np.sqrt(1 + vout)
+        Z = 0.5 * (1 + special.erf(t / np.sqrt(2)))
+        lt = np.log(Z + eps)
+    else:
+        gh_x, gh_w = np.polynomial.hermite.hermgauss(GH_DEGREE)
+        gh_x, gh_w = gh_x[:, None, None, None], gh_w[:, None, None, None]
+        ts = gh_x * np.sqrt(2 * vout) + mout
+        pdfs = 0.5 * (1 + special.erf(y * ts / np.sqrt(2))) + eps
+        Zt = np.sum(pdfs**alpha * gh_w, axis=0) / np.sqrt(np.pi)
+        lt = np.log(Zt)
+    lmax = np.max(lt, axis=0)
+    ex = np.exp(lt - lmax)
+    se = np.sum(ex, axis=0)
+    logZ = np.sum(lmax + np.log(se) - np.log(mout.shape[0]))
+    w = ex / se
+    if alpha == 1.0:
+        dt = 1 / (Z + eps) / np.sqrt(2 * np.pi) * np.exp(-t**2.0 / 2)
+        return logZ, w * dt * y / np.sqrt(1 + vout), w * dt * (-0.5 * y * mout / (1 + vout)**1.5)
+    a = pdfs**(alpha - 1.0) * np.exp(-ts**2 / 2)
+    dZdm = np.sum(gh_w * a, axis=0) * y * alpha / np.pi / np.sqrt(2)
+    dZdv = np.sum(gh_w * (a * gh_x), axis=0) * y * alpha / np.pi / np.sqrt(2) / np.sqrt(2 * vout)
+    return logZ, w * dZdm / Zt + eps, w * dZdv / Zt + eps
+
+
 def probit_log_lik_exp(m, v, y):
     """lik_layers.py:418-436 Probit_Layer.compute_log_lik_exp, 2-D branch."""
     from scipy.stats import norm
@@ -912,10 +942,12 @@ class AepSGPLVM(object):
         mpost, vpost = post1[idx] / post2[idx], 1.0 / post2[idx]
         gl = {}
         if prop_mode == PROP_MC:                            # aep_models.py:745-761
-            assert self.lik == 'Gaussian'
             m, v, (ms, vs, kfus, xs, eps) = L.prop_mc(mcav, vcav)
-            logZ, dm, dv = gauss_log_Z_mc(sn, m, v, yb, alpha)
-            gl['sn'] = gauss_dsn_mc(sn, m, dv, alpha, scale)
+            if self.lik == 'Probit':
+                logZ, dm, dv = probit_log_Z_mc(m, v, yb, alpha)
+            else:
+                logZ, dm, dv = gauss_log_Z_mc(sn, m, v, yb, alpha)
+                gl['sn'] = gauss_dsn_mc(sn, m, dv, alpha, scale)
             g, dx = L.aep_grads_mc(ms, vs, scale * dm, scale * dv, kfus, xs, alpha)
             gin = L.reparam(dx, vcav, eps)
         else:
@@ -985,13 +1017,16 @@ class VfeSGPLVM(object):
         mx, vx = post1[idx] / post2[idx], 1.0 / post2[idx]
         gl = {}
         if prop_mode == PROP_MC:                            # vfe_models.py:793-808
-            assert self.lik == 'Gaussian'
             m, v, (ms, vs, kfus, xs, eps) = L.prop_mc(mx, vx, cav=False)
             K = m.shape[0]
-            sn2 = np.exp(2.0 * sn)                          # lik_layers.py:209-216, 229-234
-            ll = np.sum(np.mean(-0.5 * np.log(2 * np.pi * sn2) - 0.5 * ((yb - m)**2 + v) / sn2, axis=0))
-            dm, dv = (yb - m) / sn2 / K, -0.5 / sn2 * np.ones_like(v) / K
-            gl['sn'] = scale * np.sum(-1 + ((yb - m)**2 + v) / sn2) / K
+            if self.lik == 'Probit':                        # lik_layers.py:437-455: sample average
+                ll, dm, dv = probit_log_lik_exp(ms, vs, np.tile(yb, (K, 1)))
+                ll, dm, dv = ll / K, dm.reshape(m.shape) / K, dv.reshape(v.shape) / K
+            else:
+                sn2 = np.exp(2.0 * sn)                      # lik_layers.py:209-216, 229-234
+                ll = np.sum(np.mean(-0.5 * np.log(2 * np.pi * sn2) - 0.5 * ((yb - m)**2 + v) / sn2, axis=0))
+                dm, dv = (yb - m) / sn2 / K, -0.5 / sn2 * np.ones_like(v) / K
+                gl['sn'] = scale * np.sum(-1 + ((yb - m)**2 + v) / sn2) / K
             g, dx = L.vfe_grads_mc(ms, vs, scale * dm, scale * dv, kfus, xs)
             gin = L.reparam(dx, vx, eps)
         else:

@@ -372,6 +372,9 @@ def mc_cases():
     case_sgplvm('vfe_sgplvm_mc', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=72, prop_mode='MC')
     case_sgpssm('aep_sgpssm_lin_mc', aep.SGPSSM, 20, 4, 2, 2, 0.5, seed=73, prop_mode='MC')
     case_sgpssm('aep_sgpssm_gp_mc', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=74, prop_mode='MC')
+    case_sgplvm('aep_sgplvm_probit_mc', aep.SGPLVM, 10, 5, 3, 2, 0.5, seed=78, lk='Probit', prop_mode='MC')
+    case_sgplvm('aep_sgplvm_probit_mc_alpha_one', aep.SGPLVM, 10, 5, 2, 2, 1.0, seed=79, lk='Probit', prop_mode='MC')
+    case_sgplvm('vfe_sgplvm_probit_mc', vfe.SGPLVM, 10, 5, 3, 2, 1.0, seed=80, lk='Probit', prop_mode='MC')
     case_sgpssm('vfe_sgpssm_lin_mc', vfe.SGPSSM, 20, 4, 2, 2, 1.0, seed=76, prop_mode='MC')
     case_sgpssm('vfe_sgpssm_gp_mc', vfe.SGPSSM, 10, 4, 2, 3, 1.0, gp_emi=True, seed=77, prop_mode='MC')
     case_sgpssm('aep_sgpssm_control_mc', aep.SGPSSM, 12, 4, 2, 2, 0.7, control=1, mb=7, seed=75, prop_mode='MC')
