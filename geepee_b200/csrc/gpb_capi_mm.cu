@@ -21,7 +21,7 @@ int q_template(int Q) {
 }
 // pairs per thread: mirrors gpb::MMCfg<T,Q,DOC>::RP (fp32 holds twice as many)
 int mm_rp(int tbytes, int Qt, int DOC) {
-    int rp = (2 * Qt + 2 * DOC + 2) <= 18 ? 4 : ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1);
+    int rp = (2 * Qt + 2 * DOC + 2) <= GPB_MM_RP4_MAX ? 4 : ((2 * Qt + 2 * DOC + 2) <= 26 ? 2 : 1);
     if (GPB_MM_RP64 > 0 && GPB_MM_RP64 < rp) rp = GPB_MM_RP64;
     return tbytes == 4 ? 2 * rp : rp;
 }

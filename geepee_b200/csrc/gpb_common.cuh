@@ -13,6 +13,10 @@
 #ifndef GPB_MM_RP64
 #define GPB_MM_RP64 0
 #endif
+// largest per-pair state size (2Q + 2DOC + 2 values) for which a thread owns 4 pairs
+#ifndef GPB_MM_RP4_MAX
+#define GPB_MM_RP4_MAX 18
+#endif
 // (a second __launch_bounds__ argument is deliberately NOT exposed: `(256, 1)` let ptxas take 176
 //  registers for the backward kernel -> one CTA per SM, +12 % time; `(256, 3)` is the rejected
 //  3-CTA experiment of DESIGN.md section 7)

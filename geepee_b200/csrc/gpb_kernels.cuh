@@ -1427,7 +1427,7 @@ template <typename T, int Q, int DOC>
 struct MMCfg {
     // pairs per thread, sized to keep the per-thread pair state in registers (fp32: twice as many,
     // the fp32 path is issue bound and the per-row overhead is amortised over the pairs)
-    static constexpr int RPA = (2 * Q + 2 * DOC + 2) <= 18 ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
+    static constexpr int RPA = (2 * Q + 2 * DOC + 2) <= GPB_MM_RP4_MAX ? 4 : ((2 * Q + 2 * DOC + 2) <= 26 ? 2 : 1);
     static constexpr int RP64 = (GPB_MM_RP64 > 0 && GPB_MM_RP64 < RPA) ? GPB_MM_RP64 : RPA;
     static constexpr int RP = sizeof(T) == 4 ? 2 * RP64 : RP64;
     static constexpr int TR = 32;             // rows per staged tile = lanes per warp
