@@ -145,7 +145,11 @@ int mm_pairs_launch(const MMPlan& p, const gpb::MMArgs<T>& a, void* stream) {
             return GPB_OK;
         }
     }
-    {
+    if constexpr (!BWD && sizeof(T) == 8 && DOC <= 4 && Q <= 4) {   // fp64 forward: two-CTA register budget
+        auto kern = gpb::mm_pairs_fwd64_kernel<Q, DOC>;
+        if (mm_pairs_smem(kern, smem)) return GPB_ERR_CUDA;
+        GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), smem, stream, a);
+    } else {
         auto kern = gpb::mm_pairs_kernel<T, Q, DOC, BWD, false>;
         if (mm_pairs_smem(kern, smem)) return GPB_ERR_CUDA;
         GPB_LAUNCH(kern, dim3(p.nchunks, p.nsplit), dim3(256), smem, stream, a);

@@ -26,10 +26,6 @@
 #ifndef GPB_MM_NR_FWD
 #define GPB_MM_NR_FWD 2
 #endif
-// 1: __launch_bounds__(256, 2) on the pair kernels (register cap 128 for every instantiation)
-#ifndef GPB_MM_LB2
-#define GPB_MM_LB2 0
-#endif
 // warps per CTA of the wide-layer tensor-core backward (8 or 16; measured equal on the B200: 14.17 vs 14.04 ms at the cfg2 shape)
 #ifndef GPB_MM_WIDE_WARPS
 #define GPB_MM_WIDE_WARPS 8

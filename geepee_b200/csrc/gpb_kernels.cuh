@@ -1594,12 +1594,9 @@ struct RowXpose {
 // the 8 warps through shared memory, and over the pair chunks (blocks) by one fp64 atomic per value.
 // GEN = true: generic multi-pass path for Do > DOC (runtime full_coef / lam_pass flags);
 // GEN = false (Do <= DOC): single pass, Lambda sums always on, coefficient from registers.
-template <typename T, int Q, int DOC, bool BWD, bool GEN>
-#if GPB_MM_LB2
-GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairs_kernel(MMArgs<T> a) {
-#else
-GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
-#endif
+// (the body is a device function so that two kernels with different register budgets can share it)
+template <typename T, int Q, int DOC, bool BWD, bool GEN, int NRF>
+GPB_DEVICE void mm_pairs_body(MMArgs<T> a) {
     typedef MMCfg<T, Q, DOC> C;
     constexpr int RP = C::RP, TR = C::TR;
     constexpr int NS = BWD ? 2 * Q : DOC;
@@ -1610,7 +1607,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
     constexpr int RL = (RLraw + VW - 1) / VW * VW;       // row record length (16-byte multiple)
     constexpr int kTab = ExpDom<T>::TAB;
     // rows per loop trip (wide inputs: one, register budget)
-    constexpr int NR = Q <= 4 ? ((!BWD && sizeof(T) == 8 && Q <= 2 && DOC <= 2) ? GPB_MM_NR_FWD : 2) : 1;
+    constexpr int NR = Q <= 4 ? ((!BWD && sizeof(T) == 8 && Q <= 2 && DOC <= 2) ? NRF : 2) : 1;
     constexpr double kS = ExpDom<T>::S;
     // Row tiles are double buffered (tile t+1 is staged while tile t is consumed) and so is the
     // cross-warp staging of the row sums, which leaves ONE barrier per tile.  For wide inputs the
@@ -1922,6 +1919,19 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
             for (int q = 0; q < Q; q++) rec[(long)(DOC + 1 + q) * PP + p] = (double)accS1[j][q] * (1.0 / kS);
         }
     }
+}
+
+template <typename T, int Q, int DOC, bool BWD, bool GEN>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) mm_pairs_kernel(MMArgs<T> a) {
+    mm_pairs_body<T, Q, DOC, BWD, GEN, 2>(a);
+}
+// fp64 forward with <= 4 output dims: ptxas' own heuristic stops at 94 registers although two CTAs per
+// SM leave 128; asking for exactly two resident CTAs lets it keep more of the lock-step exp chains in
+// registers (measured -4 % on the B200).  The same bound makes the backward kernel no faster and
+// spills in fp32 instantiations, hence a separate entry point.
+template <int Q, int DOC>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairs_fwd64_kernel(MMArgs<double> a) {
+    mm_pairs_body<double, Q, DOC, false, false, GPB_MM_NR_FWD>(a);
 }
 
 // Forward contraction for WIDE output layers (Do > 4, e.g. SGPLVM with Do = 50), roles swapped:
