@@ -429,6 +429,9 @@ def run_gpu(args, w):
         P = w['M'] * (w['M'] + 1) // 2
         fl = sum(rows_rank * P * (14 * sizes[i] + 4 * sizes[i + 1] + 5) for i in range(1, len(sizes) - 1))
         slot, kname = 'mm_pairs_bwd', 'mm_pairs_kernel<T,Q,DOC,BWD=true> (psi2 regenerated on chip; all moment-matched layers)'
+        if pr == ops.F64 and sizes[-1] > 4 and sizes[1] <= 8:
+            kname = ('mm_bwd_wide_mma_kernel<Q> (psi2 once per row and pair on chip, the four backward '
+                     'contractions as DMMA.8x8x4 tiles on the FP64 tensor cores)')
     else:
         fl = rows_rank * 2.0 * w['Do'] * w['M'] ** 2
         slot = 'det_fwd'
