@@ -100,3 +100,21 @@ def test_predict_after_replay():
     x = gold['x']
     mf, vf = model.predict_f(x['xs'])
     assert gu.rel_err(mf, x['mf']) < 1e-7 and gu.rel_err(vf, x['vf']) < 1e-7
+
+
+def test_alpha_switching_keeps_graphs_apart(monkeypatch):
+    """One captured pre-/post-tail pair per alpha: switching back and forth must replay the right
+    one (the cavity and the log-partition scales depend on alpha)."""
+    from geepee_b200 import config
+    gold = gu.load('aep_sgpr')
+    model = mc.build_model(gold)
+    monkeypatch.setattr(config, 'TAIL_GRAPHS', False)
+    twin = mc.build_model(gold)
+    ref = {}
+    for alpha in (0.5, 1.0, 0.25):
+        ref[alpha] = twin.objective_function(copy.deepcopy(gold['p']), gold['meta']['mb_size'], alpha=alpha)
+    monkeypatch.setattr(config, 'TAIL_GRAPHS', True)
+    for alpha in (0.5, 0.5, 0.5, 0.5, 1.0, 1.0, 1.0, 1.0, 0.5, 0.25, 1.0, 0.25, 0.25, 0.25, 0.5):
+        e, g = model.objective_function(copy.deepcopy(gold['p']), gold['meta']['mb_size'], alpha=alpha)
+        gu.assert_close(e, g, {'energy': ref[alpha][0], 'g': ref[alpha][1], 'meta': {}}, 1e-9, 'alpha %g' % alpha)
+    assert len(model.sgp_layer._graphs) == 3
