@@ -48,7 +48,7 @@ def build(force=False, verbose=False, out=None, extra_flags=()):
         log.close()
         if rc != 0:
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, open(log.name).read()[-4000:]))
-    subprocess.check_call([nvcc, '-shared', '-o', out] + objs)
+    subprocess.check_call([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs)
     return out
 
 
