@@ -252,6 +252,27 @@ class Base_SDGPR(Base_Model):
         samples = samples.reshape(no_samples, inputs.shape[0], self.sgp_layers[-1].Dout)
         return samples.cpu().numpy(), mf.cpu().numpy(), vf.cpu().numpy()
 
+    def predict_f_with_input_grad(self, inputs):
+        """base_models.py:1186-1237.  As in the reference this is defined for a single GP layer only
+        (its deeper branch calls ``backprop_predictive_grads_lvm_mm``, which no layer defines) and
+        both gradients it returns are d mf / d inputs (base_models.py:424-425)."""
+        if not self.updated:
+            for layer in self.sgp_layers:
+                layer.update_posterior()
+            self.updated = True
+        if self.L != 1:
+            raise AttributeError("'SGP_Layer' object has no attribute 'backprop_predictive_grads_lvm_mm'")
+        x = to_dev(inputs, self.device)
+        mf, vf, dx = self.sgp_layers[0]._predictive_dx(x, np.ones((1, 1)), np.zeros((1, 1)))
+        dx = dx.cpu().numpy()
+        return mf.cpu().numpy(), vf.cpu().numpy(), dx, dx.copy()
+
+    def predict_y_with_input_grad(self, inputs):
+        """base_models.py:1277-1289."""
+        mf, vf, dm_dx, dv_dx = self.predict_f_with_input_grad(inputs)
+        my, vy = self.lik_layer.output_probabilistic(mf, vf)
+        return my, vy, dm_dx, dv_dx
+
     def sample_f(self, inputs, no_samples=1):
         """base_models.py:1239-1262."""
         if not self.updated:

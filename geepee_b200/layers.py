@@ -420,6 +420,25 @@ class Base_SGP_Layer(object):
         st['dvx'] = (dx * eps).sum(0) / (2.0 * torch.sqrt(vx))
         return st
 
+    def _predictive_dx(self, x, dm_dm, dm_dv):
+        """d(sum_d dm_dm*m_d + dm_dv*v_d)/dx of the posterior deterministic-input layer on the device:
+        det_fwd (saving Kfu and T = B_det kfu) followed by the det_dx kernel.  -> dx[n,D]."""
+        t = self._t
+        m, v, ctx = self._fwd_det(x, cav=False, save=True)
+        _, opnd, Ks, Ts = ctx
+        n = x.shape[0]
+        dm = to_dev(np.asarray(dm_dm, dtype=np.float64), self.device).expand(n, self.Dout).contiguous()
+        dv = to_dev(np.asarray(dm_dv, dtype=np.float64), self.device).expand(n, self.Dout).contiguous()
+        return m, v, ops.det_dx(self.prec, x, t['zu'], t['ls'], opnd, dm, dv, Ks, Ts)
+
+    def backprop_predictive_grads_reg(self, m, v, dm_dm, dm_dv, dv_dm, dv_dv, kfu, x):
+        """base_models.py:391-426.  The reference forms the second gradient from ``dkfu_m`` as well
+        (base_models.py:424-425), so both returned arrays are d m / d x; kept as is (dv_dm / dv_dv
+        are accepted and, as there, unused).  Kfu is regenerated on the device from ``x``."""
+        _, _, dx = self._predictive_dx(to_dev(x, self.device), dm_dm, dm_dv)
+        dx = dx.cpu().numpy()
+        return dx, dx.copy()
+
     # ---- shared chain rules ------------------------------------------------------------------
     def _pack_eta1(self, dtheta1):
         """theta_1 = R^T R with log-diagonal packing (base_models.py:505-514)."""

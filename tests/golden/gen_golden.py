@@ -357,6 +357,41 @@ def case_sdgprh(name, N, M, D, hidden, Do, alpha, seed=60, lk='Gaussian', init_r
                     mb_size=N, rng_seed=123, lik=lk), {'x': x, 'y': y}, params, e, g, extra)
 
 
+def case_input_grad(seed=70):
+    """predict_f_with_input_grad / predict_y_with_input_grad (base_models.py:1186-1237,1277-1289) and
+    the layer-level backprop_predictive_grads_reg (391-426) of single-layer deep GPs (the only depth
+    the reference defines them for), scalar and 2-D outputs."""
+    out = {}
+    meta = dict(model='aep_models.SDGPR', cases=[])
+    for tag, N, M, D, Do in (('a', 12, 5, 3, 1), ('b', 9, 4, 2, 2)):
+        rng = np.random.RandomState(seed + Do)
+        x = rng.standard_normal((N, D))
+        y = rng.standard_normal((N, Do))
+        np.random.seed(seed)
+        model = aep.SDGPR(x, y, M, [], lik='Gaussian')
+        params = perturb(quiet(model.init_hypers, y), rng)
+        params['sn'] = np.array(np.log(0.3))
+        xs = rng.standard_normal((7, D))
+        model.update_hypers(params)
+        model.updated = False
+        mf, vf, dm_dx, dv_dx = model.predict_f_with_input_grad(xs)
+        my, vy, _, _ = model.predict_y_with_input_grad(xs)
+        layer = model.sgp_layers[0]
+        m0, v0, kfu = layer.forward_prop_thru_post(xs, return_info=True)
+        w_m = rng.standard_normal((1, Do))
+        w_v = rng.standard_normal((1, Do))
+        l_dm, l_dv = layer.backprop_predictive_grads_reg(m0, v0, w_m, w_v, np.zeros((1, 1)), np.ones((1, 1)), kfu, xs)
+        meta['cases'].append(dict(tag=tag, N=N, M=M, D=D, Do=Do))
+        for k, v in params.items():
+            out['%s_p_%s' % (tag, k)] = np.asarray(v)
+        for k, v in dict(x=x, y=y, xs=xs, mf=mf, vf=vf, dm_dx=dm_dx, dv_dx=dv_dx, my=my, vy=vy,
+                         w_m=w_m, w_v=w_v, l_dm=l_dm, l_dv=l_dv).items():
+            out['%s_%s' % (tag, k)] = np.asarray(v)
+    meta.update(numpy=np.__version__, scipy=scipy.__version__)
+    np.savez_compressed(os.path.join(HERE, 'input_grad.npz'), meta=json.dumps(meta), **out)
+    print('wrote input_grad')
+
+
 def sdgprh_cases():
     case_sdgprh('aep_sdgprh', 10, 5, 2, [3, 2], 3, 0.5)
     case_sdgprh('aep_sdgprh_moderate', 12, 6, 3, [2, 2], 2, 0.7, seed=61, init_recipe=False)
@@ -391,6 +426,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'ssm_predict':
         case_sgpssm('aep_sgpssm_lin', aep.SGPSSM, 20, 4, 2, 2, 0.5, predict=True)
         case_sgpssm('aep_sgpssm_gp', aep.SGPSSM, 10, 4, 2, 3, 0.5, gp_emi=True, seed=42, predict=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'input_grad':
+        case_input_grad()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'mc':
         mc_cases()
@@ -435,3 +473,4 @@ if __name__ == '__main__':
     probit_cases()
     sdgprh_cases()
     mc_cases()
+    case_input_grad()

@@ -101,3 +101,38 @@ def check_sampling(name, tol, device=None):
         np.random.seed(555)
     fs = model.sample_f(x['xs'], x['fs'].shape[2])
     assert gu.rel_err(fs, x['fs']) < tol, (name, 'fs', gu.rel_err(fs, x['fs']))
+
+
+def check_input_grad(tol, device=None):
+    """predict_f_with_input_grad / predict_y_with_input_grad / layer.backprop_predictive_grads_reg
+    (base_models.py:1186-1237,1277-1289,391-426) against outputs of the reference itself
+    (tests/golden/input_grad.npz, gen_golden.py::case_input_grad)."""
+    import json
+    import os
+    from geepee_b200 import aep_models as aep
+    f = np.load(os.path.join(gu.GOLDEN, 'input_grad.npz'), allow_pickle=False)
+    for c in json.loads(str(f['meta']))['cases']:
+        t = c['tag'] + '_'
+        g = {k[len(t):]: np.array(f[k]) for k in f.files if k.startswith(t)}
+        params = {k[2:]: v for k, v in g.items() if k.startswith('p_')}
+        model = aep.SDGPR(g['x'], g['y'], c['M'], [], lik='Gaussian', prec='fp64', device=device)
+        model.update_hypers(copy.deepcopy(params))
+        model.updated = False
+        mf, vf, dm_dx, dv_dx = model.predict_f_with_input_grad(g['xs'])
+        my, vy, dm2, dv2 = model.predict_y_with_input_grad(g['xs'])
+        layer = model.sgp_layers[0]
+        m0, v0, kfu = layer.forward_prop_thru_post(g['xs'], return_info=True)
+        l_dm, l_dv = layer.backprop_predictive_grads_reg(m0, v0, g['w_m'], g['w_v'], np.zeros((1, 1)),
+                                                         np.ones((1, 1)), kfu, g['xs'])
+        for got, key in ((mf, 'mf'), (vf, 'vf'), (dm_dx, 'dm_dx'), (dv_dx, 'dv_dx'), (my, 'my'), (vy, 'vy'),
+                         (dm2, 'dm_dx'), (dv2, 'dv_dx'), (l_dm, 'l_dm'), (l_dv, 'l_dv')):
+            assert got.shape == g[key].shape, (c, key, got.shape, g[key].shape)
+            assert gu.rel_err(got, g[key]) < tol, (c, key, gu.rel_err(got, g[key]))
+    # deeper models: the reference fails on the undefined lvm_mm twin (base_models.py:1231)
+    deep = aep.SDGPR(g['x'], g['y'], c['M'], [2], lik='Gaussian', prec='fp64', device=device)
+    deep.update_hypers(deep.init_hypers(g['y']))
+    try:
+        deep.predict_f_with_input_grad(g['xs'])
+    except AttributeError:
+        return
+    raise AssertionError('predict_f_with_input_grad on a 2-layer model should fail as the reference does')

@@ -37,3 +37,7 @@ def test_sampling(name):
 @pytest.mark.parametrize('name', ['aep_sgpssm_lin', 'aep_sgpssm_gp'])
 def test_ssm_predict(name):
     mc.check_ssm_predict(name, 1e-8)
+
+
+def test_predict_with_input_grad():
+    mc.check_input_grad(1e-8)

@@ -1,0 +1,18 @@
+"""predict_f_with_input_grad / predict_y_with_input_grad / backprop_predictive_grads_reg on the B200
+(det_fwd + det_dx kernels with the posterior operands) against outputs of the reference itself
+(tests/golden/input_grad.npz).  Added after the round's last GPU session: verified on the CPU fiber
+emulator only (tests/test_emu_models.py::test_predict_with_input_grad), hence collected last."""
+import pytest
+import torch
+
+import model_cases as mc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_predict_with_input_grad():
+    from geepee_b200 import _lib
+    _lib._testing_detach()
+    assert torch.cuda.is_available()
+    _lib.get()
+    mc.check_input_grad(1e-7)
