@@ -582,6 +582,21 @@ class AEP_SGP_Layer(Base_SGP_Layer):
     def compute_phi(self, alpha=1.0):
         return float(self._phi(alpha).item())
 
+    def compute_phi_prior(self):
+        """aep_models.py:62-70."""
+        return float((0.5 * self.Dout * self._t['logdet_Kuu']).item())
+
+    def compute_phi_posterior(self):
+        """aep_models.py:72-83."""
+        t = self._t
+        return float((0.5 * t['logdet_Su'].sum() + 0.5 * (t['mu'] * bmv(t['Suinv'], t['mu'])).sum()).item())
+
+    def compute_phi_cavity(self):
+        """aep_models.py:85-97 (after compute_cavity)."""
+        t = self._t
+        return float((0.5 * t['logdet_Suhat'].sum()
+                      + 0.5 * (t['muhat'] * bmv(t['Suhatinv'], t['muhat'])).sum()).item())
+
     def _cav_grad_u(self, dmu, dSu, alpha):
         """aep_models.py:548-586."""
         t = self._t

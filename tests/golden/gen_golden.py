@@ -392,6 +392,63 @@ def case_input_grad(seed=70):
     print('wrote input_grad')
 
 
+def case_layer_iface(seed=80):
+    """Layer-level interface of SURVEY 8b on small shapes: compute_cavity / forward_prop_thru_cav /
+    backprop_grads_reg / backprop_grads_lvm_mm / compute_phi (+ prior, posterior, cavity) /
+    forward_prop_thru_post of aep.SGP_Layer (aep_models.py:62-304,413-546), compute_KL and the two
+    backprops of vfe.SGP_Layer (vfe_models.py:309-401,479-548), natural and non-natural parameters."""
+    out = {}
+    meta = dict(cases=[])
+    for tag, mod, nat, alpha in (('aep_nat', 'aep', True, 0.6), ('aep_non', 'aep', False, 0.3),
+                                 ('vfe_nat', 'vfe', True, 1.0), ('vfe_non', 'vfe', False, 1.0)):
+        N, M, D, Do, n = 30, 6, 3, 2, 8
+        rng = np.random.RandomState(seed + len(meta['cases']))
+        np.random.seed(seed)
+        cls = aep.SGP_Layer if mod == 'aep' else vfe.SGP_Layer
+        layer = cls(N, D, Do, M, nat)
+        xtr = rng.standard_normal((N, D))
+        params = perturb(quiet(layer.init_hypers, xtr), rng)
+        layer.update_hypers(params)
+        layer.compute_kuu()
+        layer.update_posterior()
+        r = {}
+        x = rng.standard_normal((n, D))
+        mx = rng.standard_normal((n, D))
+        vx = 0.1 + rng.rand(n, D)
+        dm, dv = rng.standard_normal((n, Do)), rng.standard_normal((n, Do))
+        dm2, dv2 = rng.standard_normal((n, Do)), rng.standard_normal((n, Do))
+        if mod == 'aep':
+            layer.compute_cavity(alpha)
+            r['phi'] = np.array([layer.compute_phi(alpha), layer.compute_phi_prior(),
+                                 layer.compute_phi_posterior(), layer.compute_phi_cavity()])
+            m, v, kfu = layer.forward_prop_thru_cav(x)
+            g = layer.backprop_grads_reg(m, v, dm, dv, kfu, x, alpha)
+            ms, vs, psi1, psi2 = layer.forward_prop_thru_cav(mx, vx, mode='MM')
+            gs, gx = layer.backprop_grads_lvm_mm(ms, vs, dm2, dv2, psi1, psi2, mx, vx, alpha)
+        else:
+            r['phi'] = np.array([layer.compute_KL()])
+            m, v, kfu = layer.forward_prop_thru_post(x, return_info=True)
+            g = layer.backprop_grads_reg(m, v, dm, dv, kfu, x)
+            ms, vs, psi1, psi2 = layer.forward_prop_thru_post(mx, vx, mode='MM', return_info=True)
+            gs, gx = layer.backprop_grads_lvm_mm(ms, vs, dm2, dv2, psi1, psi2, mx, vx)
+        pm, pv = layer.forward_prop_thru_post(x)
+        pms, pvs = layer.forward_prop_thru_post(mx, vx, mode='MM')
+        r.update(xtr=xtr, x=x, mx=mx, vx=vx, dm=dm, dv=dv, dm2=dm2, dv2=dv2, m=m, v=v, kfu=kfu, ms=ms, vs=vs,
+                 psi1=psi1, psi2=psi2, pm=pm, pv=pv, pms=pms, pvs=pvs, gx_mx=gx['mx'], gx_vx=gx['vx'])
+        for k, a in params.items():
+            r['p_' + k] = a
+        for k, a in g.items():
+            r['g_' + k] = a
+        for k, a in gs.items():
+            r['gs_' + k] = a
+        for k, a in r.items():
+            out[tag + '__' + k] = np.asarray(a)
+        meta['cases'].append(dict(tag=tag, mod=mod, nat=nat, alpha=alpha, N=N, M=M, D=D, Do=Do))
+    meta.update(numpy=np.__version__, scipy=scipy.__version__)
+    np.savez_compressed(os.path.join(HERE, 'layer_iface.npz'), meta=json.dumps(meta), **out)
+    print('wrote layer_iface')
+
+
 def sdgprh_cases():
     case_sdgprh('aep_sdgprh', 10, 5, 2, [3, 2], 3, 0.5)
     case_sdgprh('aep_sdgprh_moderate', 12, 6, 3, [2, 2], 2, 0.7, seed=61, init_recipe=False)
@@ -429,6 +486,9 @@ if __name__ == '__main__':
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'input_grad':
         case_input_grad()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'layer_iface':
+        case_layer_iface()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'mc':
         mc_cases()
@@ -474,3 +534,4 @@ if __name__ == '__main__':
     sdgprh_cases()
     mc_cases()
     case_input_grad()
+    case_layer_iface()

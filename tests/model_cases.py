@@ -136,3 +136,69 @@ def check_input_grad(tol, device=None):
     except AttributeError:
         return
     raise AssertionError('predict_f_with_input_grad on a 2-layer model should fail as the reference does')
+
+
+def check_layer_iface(tol, device=None):
+    """SURVEY 8b layer-level interface (compute_cavity / forward_prop_thru_cav / backprop_grads_reg /
+    backprop_grads_lvm_mm / compute_phi* / compute_KL / forward_prop_thru_post) against outputs of the
+    reference's layers (tests/golden/layer_iface.npz, gen_golden.py::case_layer_iface)."""
+    import json
+    import os
+    from geepee_b200 import aep_models as aep, vfe_models as vfe
+    f = np.load(os.path.join(gu.GOLDEN, 'layer_iface.npz'), allow_pickle=False)
+    for c in json.loads(str(f['meta']))['cases']:
+        t = c['tag'] + '__'
+        g = {k[len(t):]: np.array(f[k]) for k in f.files if k.startswith(t)}
+        params = {k[2:]: v for k, v in g.items() if k.startswith('p_')}
+        cls = aep.SGP_Layer if c['mod'] == 'aep' else vfe.SGP_Layer
+        layer = cls(c['N'], c['D'], c['Do'], c['M'], c['nat'], 'fp64', device)
+        layer.update_hypers(copy.deepcopy(params))
+        layer.compute_kuu()
+        layer.update_posterior()
+        alpha = c['alpha']
+        x, mx, vx = g['x'], g['mx'], g['vx']
+        if c['mod'] == 'aep':
+            layer.compute_cavity(alpha)
+            phi = np.array([layer.compute_phi(alpha), layer.compute_phi_prior(),
+                            layer.compute_phi_posterior(), layer.compute_phi_cavity()])
+            m, v, kfu = layer.forward_prop_thru_cav(x)
+            gr = layer.backprop_grads_reg(m, v, g['dm'], g['dv'], kfu, x, alpha)
+            ms, vs, psi1, psi2 = layer.forward_prop_thru_cav(mx, vx, mode='MM')
+            if c['nat']:
+                gs, gx = layer.backprop_grads_lvm_mm(ms, vs, g['dm2'], g['dv2'], psi1, psi2, mx, vx, alpha)
+            else:
+                # the reference applies its natural-parameter chain rule here whatever nat_param is
+                # (aep_models.py:252-297 use theta_2 / theta_1_R unconditionally); the product refuses
+                # instead of reproducing those numbers, so the recorded gs_* / gx_* are not compared
+                try:
+                    layer.backprop_grads_lvm_mm(ms, vs, g['dm2'], g['dv2'], psi1, psi2, mx, vx, alpha)
+                except NotImplementedError:
+                    gs, gx = None, None
+                else:
+                    raise AssertionError('non-natural AEP moment-matched backprop should refuse')
+        else:
+            phi = np.array([layer.compute_KL()])
+            m, v, kfu = layer.forward_prop_thru_post(x, return_info=True)
+            gr = layer.backprop_grads_reg(m, v, g['dm'], g['dv'], kfu, x)
+            ms, vs, psi1, psi2 = layer.forward_prop_thru_post(mx, vx, mode='MM', return_info=True)
+            gs, gx = layer.backprop_grads_lvm_mm(ms, vs, g['dm2'], g['dv2'], psi1, psi2, mx, vx)
+        pm, pv = layer.forward_prop_thru_post(x)
+        pms, pvs = layer.forward_prop_thru_post(mx, vx, mode='MM')
+        got = dict(phi=phi, m=m, v=v, kfu=kfu, ms=ms, vs=vs, psi1=psi1, psi2=psi2, pm=pm, pv=pv, pms=pms,
+                   pvs=pvs)
+        got.update({'g_' + k: a for k, a in gr.items()})
+        want = {k for k in g if not k.startswith('p_')} - {'xtr', 'x', 'mx', 'vx', 'dm', 'dv', 'dm2', 'dv2'}
+        if gs is not None:
+            got.update(gx_mx=gx['mx'], gx_vx=gx['vx'])
+            got.update({'gs_' + k: a for k, a in gs.items()})
+        else:
+            want = {k for k in want if not k.startswith(('gs_', 'gx_'))}
+        assert set(got) == want, (c['tag'], sorted(set(got) ^ want))
+        for k in sorted(want):
+            a = np.asarray(got[k], dtype=np.float64)
+            assert a.size == g[k].size, (c['tag'], k, a.shape, g[k].shape)
+            if k == 'phi':      # four independent scalars
+                for i in range(a.size):
+                    assert abs(a[i] - g[k][i]) <= tol * max(abs(g[k][i]), 1e-12), (c['tag'], k, i, a, g[k])
+                continue
+            assert gu.rel_err(a, g[k]) < tol, (c['tag'], k, gu.rel_err(a, g[k]))

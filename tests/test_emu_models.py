@@ -41,3 +41,7 @@ def test_ssm_predict(name):
 
 def test_predict_with_input_grad():
     mc.check_input_grad(1e-8)
+
+
+def test_layer_interface():
+    mc.check_layer_iface(1e-7)

@@ -10,9 +10,20 @@ import model_cases as mc
 pytestmark = pytest.mark.gpu
 
 
-def test_predict_with_input_grad():
+@pytest.fixture(scope='module', autouse=True)
+def cuda_lib():
     from geepee_b200 import _lib
     _lib._testing_detach()
     assert torch.cuda.is_available()
     _lib.get()
+    yield
+
+
+def test_predict_with_input_grad():
     mc.check_input_grad(1e-7)
+
+
+def test_layer_interface():
+    """SURVEY 8b layer-level interface (tests/golden/layer_iface.npz); emulator twin:
+    tests/test_emu_models.py::test_layer_interface."""
+    mc.check_layer_iface(1e-6)
