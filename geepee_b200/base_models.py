@@ -219,6 +219,10 @@ class Base_SDGPR(Base_Model):
             return self.predict_f_mc(inputs, no_samples)
         if prop_mode != PROP_MM:
             raise NotImplementedError('prop_mode %s unknown' % prop_mode)
+        return self.predict_f_mm(inputs)
+
+    def predict_f_mm(self, inputs):
+        """base_models.py:1143-1158."""
         if not self.updated:
             for layer in self.sgp_layers:
                 layer.update_posterior()
