@@ -202,3 +202,21 @@ def check_layer_iface(tol, device=None):
                     assert abs(a[i] - g[k][i]) <= tol * max(abs(g[k][i]), 1e-12), (c['tag'], k, i, a, g[k])
                 continue
             assert gu.rel_err(a, g[k]) < tol, (c['tag'], k, gu.rel_err(a, g[k]))
+
+
+def check_aep_to_vfe_limit(name, device=None, alpha=1e-6, tol=1e-5):
+    """tests/test_aep_vfe_limits.py:17-127 through the product: the AEP energy at alpha -> 0 equals
+    the VFE energy at the same parameters (aep.SGPLVM is not divided by N: aep_models.py:803-815)."""
+    gold = gu.load(name)
+    m = gold['meta']
+    p = copy.deepcopy(gold['p'])
+    if 'sn' in p:
+        p['sn'] = np.array(np.log(0.5))       # alpha*vout/sn2 << 1 (SURVEY A6.1)
+    ev, _ = build_model(gold, 'fp64', device).objective_function(copy.deepcopy(p), m['N'])
+    g2 = dict(gold)
+    g2['meta'] = dict(m, model=m['model'].replace('vfe_', 'aep_'))
+    ea, _ = build_model(g2, 'fp64', device).objective_function(copy.deepcopy(p), m['N'], alpha=alpha)
+    ev, ea = float(np.ravel(ev)[0]), float(np.ravel(ea)[0])
+    if 'SGPLVM' in m['model']:
+        ea /= m['N']
+    assert abs(ea - ev) < tol * abs(ev), (name, ea, ev)

@@ -45,3 +45,8 @@ def test_predict_with_input_grad():
 
 def test_layer_interface():
     mc.check_layer_iface(1e-7)
+
+
+@pytest.mark.parametrize('name', ['vfe_sgpr', 'vfe_sgpr_probit', 'vfe_sgplvm', 'vfe_sgplvm_probit'])
+def test_aep_alpha_to_zero_is_vfe(name):
+    mc.check_aep_to_vfe_limit(name)

@@ -27,3 +27,9 @@ def test_layer_interface():
     """SURVEY 8b layer-level interface (tests/golden/layer_iface.npz); emulator twin:
     tests/test_emu_models.py::test_layer_interface."""
     mc.check_layer_iface(1e-6)
+
+
+@pytest.mark.parametrize('name', ['vfe_sgpr', 'vfe_sgpr_probit', 'vfe_sgplvm', 'vfe_sgplvm_probit'])
+def test_aep_alpha_to_zero_is_vfe(name):
+    """tests/test_aep_vfe_limits.py:17-127 on the B200; emulator twin in tests/test_emu_models.py."""
+    mc.check_aep_to_vfe_limit(name)
