@@ -220,3 +220,31 @@ def check_aep_to_vfe_limit(name, device=None, alpha=1e-6, tol=1e-5):
     if 'SGPLVM' in m['model']:
         ea /= m['N']
     assert abs(ea - ev) < tol * abs(ev), (name, ea, ev)
+
+
+def check_finite_differences(name, device=None, per_key=2):
+    """The reference's own gradient harness (tests/test_utils.py:61-138, used by tests/test_grads_*.py)
+    applied to the product: central differences with eps = 1e-5 on a few random entries of every
+    parameter key against the analytic gradient the kernels return."""
+    gold = gu.load(name)
+    model = build_model(gold, 'fp64', device)
+    m = gold['meta']
+    mb, alpha = m['N'], m['alpha']
+    p0 = gold['p']
+    _, g = model.objective_function(copy.deepcopy(p0), mb, alpha=alpha)
+    rng = np.random.RandomState(1)
+    eps = 1e-5
+    for key in sorted(p0):
+        flat = np.asarray(p0[key]).reshape(-1)
+        for j in rng.choice(flat.size, size=min(per_key, flat.size), replace=False):
+            vals = []
+            for sgn in (+1, -1):
+                p = copy.deepcopy(p0)
+                q = np.array(p[key], dtype=np.float64)
+                q.reshape(-1)[j] += sgn * eps
+                p[key] = q
+                e, _ = model.objective_function(p, mb, alpha=alpha)
+                vals.append(float(np.ravel(e)[0]))
+            num = (vals[0] - vals[1]) / (2 * eps)
+            ana = float(np.asarray(g[key]).reshape(-1)[j])
+            assert abs(ana - num) <= 2e-4 * max(abs(num), abs(ana)) + 1e-6, (name, key, j, ana, num)

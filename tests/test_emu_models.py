@@ -50,3 +50,9 @@ def test_layer_interface():
 @pytest.mark.parametrize('name', ['vfe_sgpr', 'vfe_sgpr_probit', 'vfe_sgplvm', 'vfe_sgplvm_probit'])
 def test_aep_alpha_to_zero_is_vfe(name):
     mc.check_aep_to_vfe_limit(name)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr', 'aep_sgplvm', 'aep_sgpssm_lin_1d', 'vfe_sgpr',
+                                  'vfe_sgplvm', 'aep_sgpr_probit'])
+def test_finite_differences(name):
+    mc.check_finite_differences(name, per_key=1)     # the fiber emulator is slow; GPU twin checks 3 per key

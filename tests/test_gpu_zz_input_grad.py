@@ -1,7 +1,8 @@
-"""predict_f_with_input_grad / predict_y_with_input_grad / backprop_predictive_grads_reg on the B200
-(det_fwd + det_dx kernels with the posterior operands) against outputs of the reference itself
-(tests/golden/input_grad.npz).  Added after the round's last GPU session: verified on the CPU fiber
-emulator only (tests/test_emu_models.py::test_predict_with_input_grad), hence collected last."""
+"""GPU twins of tests added after the round's last GPU session (GPU budget spent): input gradients
+of the prediction (det_fwd + det_dx kernels with the posterior operands), the layer-level interface
+of SURVEY 8b, the AEP(alpha -> 0) = VFE identity and the reference's finite-difference harness, all
+through the product.  Each has been verified on the CPU fiber emulator (tests/test_emu_models.py);
+the file name makes pytest collect it last, after the GPU-verified suites."""
 import pytest
 import torch
 
@@ -33,3 +34,10 @@ def test_layer_interface():
 def test_aep_alpha_to_zero_is_vfe(name):
     """tests/test_aep_vfe_limits.py:17-127 on the B200; emulator twin in tests/test_emu_models.py."""
     mc.check_aep_to_vfe_limit(name)
+
+
+@pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr', 'aep_sgplvm', 'aep_sgpssm_lin_1d', 'vfe_sgpr',
+                                  'vfe_sgplvm', 'aep_sgpr_probit'])
+def test_finite_differences(name):
+    """The reference's tests/test_grads_* harness (tests/test_utils.py:61-138) on the B200."""
+    mc.check_finite_differences(name, per_key=3)
