@@ -420,6 +420,44 @@ class Base_SGP_Layer(object):
         st['dvx'] = (dx * eps).sum(0) / (2.0 * torch.sqrt(vx))
         return st
 
+    def _forward_mc_iface(self, mx, vx, cav):
+        """Layer-level Monte-Carlo forward (aep_models.py:160-180 / base_models.py:309-332): eps from
+        numpy's global RNG as in the reference, samples through the deterministic-input kernels.
+        -> (mout, vout, kfu, x, eps) [K,n,.] and their stacked [K*n,.] views, numpy."""
+        dev, t = self.device, self._t
+        n = mx.shape[0]
+        eps_h = np.random.randn(config.MC_NO_SAMPLES, n, self.Din)
+        m, v, (det_ctx, eps, _) = self._fwd_mc(to_dev(mx, dev), to_dev(vx, dev), to_dev(eps_h, dev), cav=cav)
+        xs = det_ctx[0]
+        K = config.MC_NO_SAMPLES
+        m_stk = m.reshape(K * n, self.Dout).cpu().numpy()
+        v_stk = v.reshape(K * n, self.Dout).cpu().numpy()
+        kfu_stk = ops.kmat(xs, t['zu'], t['ls'], t['sf']).cpu().numpy()
+        x_stk = xs.cpu().numpy()
+        e_stk = eps_h.reshape(K * n, self.Din)
+        return ((m_stk.reshape(K, n, self.Dout), v_stk.reshape(K, n, self.Dout), kfu_stk.reshape(K, n, self.M),
+                 x_stk.reshape(K, n, self.Din), eps_h), (m_stk, v_stk, kfu_stk, x_stk, e_stk))
+
+    def _backprop_mc_iface(self, dm, dv, x, cav):
+        """Statistics + per-sample input gradient of the stacked samples (Kfu regenerated on chip)."""
+        dev, t = self.device, self._t
+        xs = to_dev(x, dev)
+        n = xs.shape[0]
+        _, _, ctx = self._fwd_det(xs, cav=cav, save=True)
+        dm2 = to_dev(np.reshape(dm, (n, self.Dout)), dev)
+        dv2 = to_dev(np.reshape(dv, (n, self.Dout)), dev)
+        st = self._bwd_det(ctx, dm2, dv2)
+        _, opnd, Ks, Ts = ctx
+        return st, ops.det_dx(self.prec, xs, t['zu'], t['ls'], opnd, dm2, dv2, Ks, Ts)
+
+    def backprop_grads_reparam(self, dx, m, v, eps):
+        """base_models.py:373-388: sample gradients folded back onto the input mean / variance."""
+        dev = self.device
+        e = to_dev(eps, dev)
+        d = to_dev(dx, dev).reshape(e.shape)
+        return {'mx': d.sum(0).cpu().numpy(),
+                'vx': ((d * e).sum(0) / (2.0 * torch.sqrt(to_dev(v, dev)))).cpu().numpy()}
+
     def _predictive_dx(self, x, dm_dm, dm_dv):
         """d(sum_d dm_dm*m_d + dm_dv*v_d)/dx of the posterior deterministic-input layer on the device:
         det_fwd (saving Kfu and T = B_det kfu) followed by the det_dx kernel.  -> dx[n,D]."""
@@ -523,8 +561,11 @@ class Base_SGP_Layer(object):
                 p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
                 return m.cpu().numpy(), v.cpu().numpy(), p1.cpu().numpy(), p2.cpu().numpy()
             return m.cpu().numpy(), v.cpu().numpy()
-        if mode in (config.PROP_MC, config.PROP_LIN):
-            raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet (SURVEY 8f)' % mode)
+        if mode == config.PROP_MC:
+            res, res_s = self._forward_mc_iface(mx, vx, cav=False)
+            return (res, res_s) if return_info else (res[0], res[1])
+        if mode == config.PROP_LIN:
+            raise NotImplementedError('Prediction with linearisation not implemented TODO')   # base_models.py:255-259
         raise NotImplementedError('unknown propagation mode')
 
 
@@ -717,9 +758,17 @@ class AEP_SGP_Layer(Base_SGP_Layer):
             m, v, _ = self._fwd_mm(a, b, cav=True, save=False)
             p1, p2 = ops.psi_stats(a, b, t['zu'], t['ls'], t['sf'])
             return m.cpu().numpy(), v.cpu().numpy(), p1.cpu().numpy(), p2.cpu().numpy()
-        if mode in (config.PROP_MC, config.PROP_LIN):
-            raise NotImplementedError('prop_mode %s: not part of the B200 hot path yet (SURVEY 8f)' % mode)
+        if mode == config.PROP_MC:
+            return self._forward_mc_iface(mx, vx, cav=True)
+        if mode == config.PROP_LIN:
+            raise NotImplementedError('prop_mode LIN: the reference has no linearised layer either '
+                                      '(aep_models.py:135-136 calls an undefined method)')
         raise NotImplementedError('unknown propagation mode')
+
+    def backprop_grads_lvm_mc(self, m, v, dm, dv, kfu, x, alpha=1.0):
+        """aep_models.py:307-410 on stacked samples x[K*n,Din]: -> (hyper grads, dx[K*n,Din])."""
+        st, dx = self._backprop_mc_iface(dm, dv, x, cav=True)
+        return {k: g.cpu().numpy() for k, g in self._tail_mc(st, alpha).items()}, dx.cpu().numpy()
 
     def backprop_grads_reg(self, m, v, dm, dv, kfu, x, alpha=1.0):
         """aep_models.py:413-511.  kfu is recomputed on chip; the argument is ignored."""
@@ -785,6 +834,11 @@ class VFE_SGP_Layer(Base_SGP_Layer):
         _, _, ctx = self._fwd_det(to_dev(x, dev), cav=False, save=True)
         st = self._bwd_det(ctx, to_dev(dm, dev), to_dev(dv, dev))
         return {k: g.cpu().numpy() for k, g in self._tail(st, False).items()}
+
+    def backprop_grads_lvm_mc(self, m, v, dm, dv, kfu, x):
+        """vfe_models.py:405-476 on stacked samples: -> (hyper grads, dx[K*n,Din])."""
+        st, dx = self._backprop_mc_iface(dm, dv, x, cav=False)
+        return {k: g.cpu().numpy() for k, g in self._tail(st, False).items()}, dx.cpu().numpy()
 
     def backprop_grads_lvm_mm(self, m, v, dm, dv, psi1, psi2, mx, vx):
         """vfe_models.py:328-401."""

@@ -433,6 +433,28 @@ def case_layer_iface(seed=80):
             gs, gx = layer.backprop_grads_lvm_mm(ms, vs, dm2, dv2, psi1, psi2, mx, vx)
         pm, pv = layer.forward_prop_thru_post(x)
         pms, pvs = layer.forward_prop_thru_post(mx, vx, mode='MM')
+        # Monte-Carlo propagation at layer level (aep_models.py:160-180,307-410; base_models.py:309-332,
+        # 373-388; vfe_models.py:405-476); the reference's AEP chain rule is natural-parameter only
+        if not (mod == 'aep' and not nat):
+            np.random.seed(321)
+            if mod == 'aep':
+                res, res_s = layer.forward_prop_thru_cav(mx, vx, mode='MC')
+            else:
+                res, res_s = layer.forward_prop_thru_post(mx, vx, mode='MC', return_info=True)
+            K = res[0].shape[0]
+            dm3, dv3 = rng.standard_normal((K, n, Do)), rng.standard_normal((K, n, Do))
+            if mod == 'aep':
+                gmc, dxs = layer.backprop_grads_lvm_mc(res_s[0], res_s[1], dm3, dv3, res_s[2], res_s[3], alpha)
+            else:
+                gmc, dxs = layer.backprop_grads_lvm_mc(res_s[0], res_s[1], dm3, dv3, res_s[2], res_s[3])
+            gin = layer.backprop_grads_reparam(dxs, mx, vx, res[4])
+            r.update(dm3=dm3, dv3=dv3, mc_m=res[0], mc_v=res[1], mc_kfu=res[2], mc_x=res[3], mc_eps=res[4],
+                     mc_dxs=dxs, mc_gx_mx=gin['mx'], mc_gx_vx=gin['vx'])
+            for k, a in gmc.items():
+                r['mcg_' + k] = a
+            np.random.seed(322)
+            pmc = layer.forward_prop_thru_post(mx, vx, mode='MC')
+            r.update(mc_pm=pmc[0], mc_pv=pmc[1])
         r.update(xtr=xtr, x=x, mx=mx, vx=vx, dm=dm, dv=dv, dm2=dm2, dv2=dv2, m=m, v=v, kfu=kfu, ms=ms, vs=vs,
                  psi1=psi1, psi2=psi2, pm=pm, pv=pv, pms=pms, pvs=pvs, gx_mx=gx['mx'], gx_vx=gx['vx'])
         for k, a in params.items():

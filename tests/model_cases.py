@@ -186,8 +186,26 @@ def check_layer_iface(tol, device=None):
         pms, pvs = layer.forward_prop_thru_post(mx, vx, mode='MM')
         got = dict(phi=phi, m=m, v=v, kfu=kfu, ms=ms, vs=vs, psi1=psi1, psi2=psi2, pm=pm, pv=pv, pms=pms,
                    pvs=pvs)
+        if 'mc_m' in g:         # Monte-Carlo propagation at layer level, eps from the same numpy seed
+            np.random.seed(321)
+            if c['mod'] == 'aep':
+                res, res_s = layer.forward_prop_thru_cav(mx, vx, mode='MC')
+                gmc, dxs = layer.backprop_grads_lvm_mc(res_s[0], res_s[1], g['dm3'], g['dv3'], res_s[2],
+                                                       res_s[3], alpha)
+            else:
+                res, res_s = layer.forward_prop_thru_post(mx, vx, mode='MC', return_info=True)
+                gmc, dxs = layer.backprop_grads_lvm_mc(res_s[0], res_s[1], g['dm3'], g['dv3'], res_s[2], res_s[3])
+            gin = layer.backprop_grads_reparam(dxs, mx, vx, res[4])
+            K, n = res[0].shape[:2]
+            for a, b in zip(res, res_s):
+                assert np.array_equal(a.reshape(b.shape), b)
+            got.update(mc_m=res[0], mc_v=res[1], mc_kfu=res[2], mc_x=res[3], mc_eps=res[4], mc_dxs=dxs,
+                       mc_gx_mx=gin['mx'], mc_gx_vx=gin['vx'])
+            got.update({'mcg_' + k: a for k, a in gmc.items()})
+            np.random.seed(322)
+            got['mc_pm'], got['mc_pv'] = layer.forward_prop_thru_post(mx, vx, mode='MC')
         got.update({'g_' + k: a for k, a in gr.items()})
-        want = {k for k in g if not k.startswith('p_')} - {'xtr', 'x', 'mx', 'vx', 'dm', 'dv', 'dm2', 'dv2'}
+        want = {k for k in g if not k.startswith('p_')} - {'xtr', 'x', 'mx', 'vx', 'dm', 'dv', 'dm2', 'dv2', 'dm3', 'dv3'}
         if gs is not None:
             got.update(gx_mx=gx['mx'], gx_vx=gx['vx'])
             got.update({'gs_' + k: a for k, a in gs.items()})
