@@ -90,17 +90,27 @@ class Probit_Layer(Lik_Layer):
 
     # ---- reference API (numpy) ---------------------------------------------------------------
     def compute_log_Z(self, mout, vout, y, alpha=1.0, compute_dm2=False):
-        if mout.ndim != 2 or compute_dm2:
-            raise NotImplementedError('Monte-Carlo (3-D) branch / dm2 are not part of the B200 hot path yet')
+        """lik_layers.py:303-411 (2-D and Monte-Carlo 3-D branches)."""
+        if mout.ndim not in (2, 3):
+            raise RuntimeError('invalid ndim, ndim=%d' % mout.ndim)
+        if compute_dm2:
+            raise NotImplementedError('dm2 of the probit likelihood is used by pep_models only (out of scope)')
         dev = self.device
+        if mout.ndim == 3:
+            dm, dv, logZ, _ = self._log_Z_mc(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), alpha, 1.0)
+            return float(logZ.item()), dm.cpu().numpy(), dv.cpu().numpy()
         dm, dv, o = ops.probit_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._gx, self._gw,
                                    alpha, 1.0, 0)
         return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
 
     def compute_log_lik_exp(self, m, v, y):
-        if m.ndim != 2:
-            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+        """lik_layers.py:418-457: 3-D inputs (Monte-Carlo propagation) are averaged over the K samples."""
         dev = self.device
+        if m.ndim == 3:
+            K = m.shape[0]
+            dm, dv, o = ops.probit_lik(to_dev(m, dev).reshape(-1, self.D), to_dev(v, dev).reshape(-1, self.D),
+                                       to_dev(y, dev).repeat(K, 1), self._gx, self._gw, 1.0, 1.0 / K, 1)
+            return float(o[0].item()) / K, dm.reshape(m.shape).cpu().numpy(), dv.reshape(m.shape).cpu().numpy()
         dm, dv, o = ops.probit_lik(to_dev(m, dev), to_dev(v, dev), to_dev(y, dev), self._gx, self._gw,
                                    1.0, 1.0, 1)
         return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
@@ -158,28 +168,55 @@ class Gauss_Layer(Lik_Layer):
         return dm, dv, o[0], (scale * o[1]).reshape(())
 
     # ---- reference API (numpy) ---------------------------------------------------------------
-    def compute_log_Z(self, mout, vout, y, alpha=1.0):
-        """lik_layers.py:104-133, 2-D branch.  Like the reference, adds sn2/alpha to the
-        caller's vout array in place (line 122)."""
-        if mout.ndim != 2:
-            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+    def compute_log_Z(self, mout, vout, y, alpha=1.0, compute_dm2=False):
+        """lik_layers.py:104-152: 2-D branch and the 3-D branch of Monte-Carlo propagation (log-mean-exp
+        over the K samples).  Like the reference, adds sn2/alpha to the caller's vout in place (122/136)."""
+        if mout.ndim not in (2, 3):
+            raise RuntimeError('invalid ndim, ndim=%d' % mout.ndim)
         dev = self._sn.device
+        if mout.ndim == 3:
+            dm, dv, logZ, _ = self._log_Z_mc(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), alpha, 1.0)
+            vout += np.exp(2.0 * self.sn) / alpha
+            return float(logZ.item()), dm.cpu().numpy(), dv.cpu().numpy()
         dm, dv, o = ops.gauss_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._sn, alpha, 1.0, 0)
         vout += np.exp(2.0 * self.sn) / alpha
+        if compute_dm2:
+            return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy(), -1.0 / vout
         return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
 
     def backprop_grads(self, mout, vout, dmout, dvout, alpha=1.0, scale=1.0):
         """lik_layers.py:154-181."""
+        if mout.ndim not in (2, 3):
+            raise RuntimeError('invalid ndim, ndim=%d' % mout.ndim)
         sn2 = np.exp(2.0 * self.sn)
-        dim_prod = mout.shape[0] * self.D
+        dim_prod = mout.shape[mout.ndim - 2] * self.D
         return {'sn': scale * (np.sum(dvout) * 2 * sn2 / alpha + dim_prod * (1 - alpha))}
 
     def compute_log_lik_exp(self, mout, vout, y):
-        if mout.ndim != 2:
-            raise NotImplementedError('Monte-Carlo (3-D) branch is not part of the B200 hot path yet')
+        """lik_layers.py:183-218: expected log-likelihood; 3-D inputs are averaged over the K samples."""
+        if mout.ndim not in (2, 3):
+            raise RuntimeError('invalid ndim, ndim=%d' % mout.ndim)
         dev = self._sn.device
+        if mout.ndim == 3:
+            K = mout.shape[0]
+            yk = to_dev(y, dev).repeat(K, 1)
+            dm, dv, o = ops.gauss_lik(to_dev(mout, dev).reshape(-1, self.D), to_dev(vout, dev).reshape(-1, self.D),
+                                      yk, self._sn, 1.0, 1.0 / K, 1)
+            return float(o[0].item()) / K, dm.reshape(mout.shape).cpu().numpy(), dv.reshape(mout.shape).cpu().numpy()
         dm, dv, o = ops.gauss_lik(to_dev(mout, dev), to_dev(vout, dev), to_dev(y, dev), self._sn, 1.0, 1.0, 1)
         return float(o[0].item()), dm.cpu().numpy(), dv.cpu().numpy()
+
+    def backprop_grads_log_lik_exp(self, m, v, dm, dv, y, scale=1.0):
+        """lik_layers.py:220-236: d/dsn of the expected log-likelihood (the gauss_lik kernel's second
+        output is sum(-1 + ((y-m)^2+v)/sn2))."""
+        if m.ndim not in (2, 3):
+            raise RuntimeError('invalid ndim, ndim=%d' % m.ndim)
+        dev = self._sn.device
+        K = m.shape[0] if m.ndim == 3 else 1
+        yk = to_dev(y, dev).repeat(K, 1) if m.ndim == 3 else to_dev(y, dev)
+        _, _, o = ops.gauss_lik(to_dev(m, dev).reshape(-1, self.D), to_dev(v, dev).reshape(-1, self.D), yk,
+                                self._sn, 1.0, 1.0, 1)
+        return {'sn': scale * float(o[1].item()) / K}
 
     def output_probabilistic(self, mf, vf, alpha=1.0):
         """lik_layers.py:238-249."""

@@ -471,6 +471,45 @@ def case_layer_iface(seed=80):
     print('wrote layer_iface')
 
 
+def case_lik_iface(seed=90):
+    """Public likelihood-layer interface (lik_layers.py:104-236 Gauss_Layer, 303-457 Probit_Layer):
+    compute_log_Z / backprop_grads / compute_log_lik_exp / backprop_grads_log_lik_exp on 2-D inputs and
+    on the 3-D inputs of Monte-Carlo propagation, alpha = 0.4 and 1, plus Gauss compute_dm2."""
+    rng = np.random.RandomState(seed)
+    n, D, K = 7, 2, 4
+    out, cases = {}, []
+    for name in ('Gauss', 'Probit'):
+        for alpha in (0.4, 1.0):
+            for shape in ((n, D), (K, n, D)):
+                tag = '%s_a%g_%dd' % (name, alpha, len(shape))
+                L = getattr(lik, name + '_Layer')(n, D)
+                if name == 'Gauss':
+                    L.update_hypers({'sn': np.array(np.log(0.3))})
+                    y = rng.standard_normal((n, D))
+                else:
+                    y = 2.0 * (rng.standard_normal((n, D)) > 0) - 1
+                m, v = rng.standard_normal(shape), 0.2 + rng.rand(*shape)
+                v1 = v.copy()
+                r = L.compute_log_Z(m, v1, y, alpha)
+                g = L.backprop_grads(m, v1, r[1], r[2], alpha, 0.7)
+                e = L.compute_log_lik_exp(m, v, y)
+                ge = L.backprop_grads_log_lik_exp(m, v, e[1], e[2], y, 0.7)
+                d = dict(y=y, m=m, v=v, vout=v1, logZ=np.array([r[0]]), dm=r[1], dv=r[2], ll=np.array([e[0]]),
+                         edm=e[1], edv=e[2])
+                if name == 'Gauss':
+                    d.update(g_sn=np.array([g['sn']]), ge_sn=np.array([ge['sn']]))
+                    if len(shape) == 2:
+                        d['dm2'] = L.compute_log_Z(m, v.copy(), y, alpha, compute_dm2=True)[3]
+                else:
+                    assert g == {} and ge == {}
+                for k, a in d.items():
+                    out[tag + '__' + k] = np.asarray(a)
+                cases.append(dict(tag=tag, lik=name, alpha=alpha, n=n, D=D))
+    meta = dict(cases=cases, sn=float(np.log(0.3)), numpy=np.__version__, scipy=scipy.__version__)
+    np.savez_compressed(os.path.join(HERE, 'lik_iface.npz'), meta=json.dumps(meta), **out)
+    print('wrote lik_iface')
+
+
 def sdgprh_cases():
     case_sdgprh('aep_sdgprh', 10, 5, 2, [3, 2], 3, 0.5)
     case_sdgprh('aep_sdgprh_moderate', 12, 6, 3, [2, 2], 2, 0.7, seed=61, init_recipe=False)
@@ -511,6 +550,9 @@ if __name__ == '__main__':
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'layer_iface':
         case_layer_iface()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'lik_iface':
+        case_lik_iface()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'mc':
         mc_cases()
@@ -557,3 +599,4 @@ if __name__ == '__main__':
     mc_cases()
     case_input_grad()
     case_layer_iface()
+    case_lik_iface()

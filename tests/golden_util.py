@@ -23,7 +23,7 @@ def load(name):
 
 def model_cases(prefix=None):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')))
-    names = [n for n in names if n not in ('kernels', 'gauss_emis', 'input_grad', 'layer_iface')]
+    names = [n for n in names if n not in ('kernels', 'gauss_emis', 'input_grad', 'layer_iface', 'lik_iface')]
     if prefix:
         names = [n for n in names if n.startswith(prefix)]
     return names

@@ -266,3 +266,44 @@ def check_finite_differences(name, device=None, per_key=2):
             num = (vals[0] - vals[1]) / (2 * eps)
             ana = float(np.asarray(g[key]).reshape(-1)[j])
             assert abs(ana - num) <= 2e-4 * max(abs(num), abs(ana)) + 1e-6, (name, key, j, ana, num)
+
+
+def check_lik_iface(tol, device=None):
+    """Public likelihood-layer interface, 2-D and Monte-Carlo 3-D branches, against outputs of the
+    reference's Gauss_Layer / Probit_Layer (tests/golden/lik_iface.npz, gen_golden.py::case_lik_iface)."""
+    import json
+    import os
+    from geepee_b200 import lik_layers as plik
+    f = np.load(os.path.join(gu.GOLDEN, 'lik_iface.npz'), allow_pickle=False)
+    meta = json.loads(str(f['meta']))
+    for c in meta['cases']:
+        t = c['tag'] + '__'
+        g = {k[len(t):]: np.array(f[k]) for k in f.files if k.startswith(t)}
+        L = getattr(plik, c['lik'] + '_Layer')(c['n'], c['D'], device)
+        if c['lik'] == 'Gauss':
+            L.update_hypers({'sn': np.array(meta['sn'])})
+        m, v, y, alpha = g['m'], g['v'], g['y'], c['alpha']
+        v1 = v.copy()
+        r = L.compute_log_Z(m, v1, y, alpha)
+        gr = L.backprop_grads(m, v1, r[1], r[2], alpha, 0.7)
+        e = L.compute_log_lik_exp(m, v, y)
+        ge = L.backprop_grads_log_lik_exp(m, v, e[1], e[2], y, 0.7)
+        got = dict(logZ=[r[0]], dm=r[1], dv=r[2], ll=[e[0]], edm=e[1], edv=e[2])
+        if c['lik'] == 'Gauss':
+            got.update(vout=v1, g_sn=[gr['sn']], ge_sn=[ge['sn']])
+            if m.ndim == 2:
+                got['dm2'] = L.compute_log_Z(m, v.copy(), y, alpha, compute_dm2=True)[3]
+        else:
+            assert gr == {} and ge == {}
+            assert np.array_equal(v1, v)          # the probit layer leaves vout alone
+        for k, a in got.items():
+            a = np.asarray(a, dtype=np.float64)
+            assert a.shape == g[k].shape, (c['tag'], k, a.shape, g[k].shape)
+            assert gu.rel_err(a, g[k]) < tol, (c['tag'], k, gu.rel_err(a, g[k]))
+    L = plik.Gauss_Layer(3, 2, device)
+    L.update_hypers({'sn': np.array(0.0)})
+    try:
+        L.compute_log_Z(np.zeros(3), np.ones(3), np.zeros(3))
+    except RuntimeError:
+        return
+    raise AssertionError('1-D input should raise RuntimeError (lik_layers.py:152)')

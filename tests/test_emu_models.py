@@ -56,3 +56,7 @@ def test_aep_alpha_to_zero_is_vfe(name):
                                   'vfe_sgplvm', 'aep_sgpr_probit'])
 def test_finite_differences(name):
     mc.check_finite_differences(name, per_key=1)     # the fiber emulator is slow; GPU twin checks 3 per key
+
+
+def test_lik_interface():
+    mc.check_lik_iface(1e-9)

@@ -41,3 +41,8 @@ def test_aep_alpha_to_zero_is_vfe(name):
 def test_finite_differences(name):
     """The reference's tests/test_grads_* harness (tests/test_utils.py:61-138) on the B200."""
     mc.check_finite_differences(name, per_key=3)
+
+
+def test_lik_interface():
+    """Public Gauss_Layer / Probit_Layer interface incl. the Monte-Carlo 3-D branches."""
+    mc.check_lik_iface(1e-8)
