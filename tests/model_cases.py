@@ -307,3 +307,22 @@ def check_lik_iface(tol, device=None):
     except RuntimeError:
         return
     raise AssertionError('1-D input should raise RuntimeError (lik_layers.py:152)')
+
+
+def check_gauss_emis_limit(device=None):
+    """tests/test_grads_emis.py:212-240 through the product: the tilted emission log-partition at
+    alpha -> 0, scaled by 1/alpha, equals the expected log-likelihood (SURVEY 8c pin iii)."""
+    from geepee_b200 import lik_layers as plik
+    rng = np.random.RandomState(11)
+    N, Dout, Din, alpha = 5, 3, 2, 1e-5
+    y = rng.standard_normal((N, Dout))
+    emis = plik.Gauss_Emis(y, Dout, Din, device)
+    emis.update_hypers({'C': rng.standard_normal((Dout, Din)), 'R': rng.standard_normal(Dout)})
+    mx, vx = rng.standard_normal((N, Din)), rng.rand(N, Din)
+    z1, gi1, gp1 = emis.compute_emission_tilted(mx, vx, alpha, 1.0 / alpha)
+    z2, gi2, gp2 = emis.compute_emission_log_lik_exp(mx, vx, 1.0)
+    assert abs(z1 - z2) < 1e-3 * abs(z2), (z1, z2)
+    for a, b in ((gi1, gi2), (gp1, gp2)):
+        assert set(a) == set(b)
+        for k in a:
+            assert gu.rel_err(a[k], b[k]) < 1e-3, (k, gu.rel_err(a[k], b[k]))

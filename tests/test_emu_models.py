@@ -60,3 +60,7 @@ def test_finite_differences(name):
 
 def test_lik_interface():
     mc.check_lik_iface(1e-9)
+
+
+def test_gauss_emis_limit():
+    mc.check_gauss_emis_limit()

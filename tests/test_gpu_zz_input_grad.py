@@ -46,3 +46,8 @@ def test_finite_differences(name):
 def test_lik_interface():
     """Public Gauss_Layer / Probit_Layer interface incl. the Monte-Carlo 3-D branches."""
     mc.check_lik_iface(1e-8)
+
+
+def test_gauss_emis_limit():
+    """tests/test_grads_emis.py:212-240 on the B200."""
+    mc.check_gauss_emis_limit()
