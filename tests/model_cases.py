@@ -326,3 +326,29 @@ def check_gauss_emis_limit(device=None):
         assert set(a) == set(b)
         for k in a:
             assert gu.rel_err(a[k], b[k]) < 1e-3, (k, gu.rel_err(a[k], b[k]))
+
+
+def check_psi_zero_variance_is_kernel(device=None):
+    """TODO.txt:65-66 / SURVEY 8c pin (iv) through the product: psi1(vx = 0) = Kfu and
+    psi2(vx = 0) = Kfu (x) Kfu, and the moment-matched layer with vx = 0 returns the deterministic
+    layer's mean (its variance differs by the Bhat_sto / Bhat_det choice, aep_models.py:155,196)."""
+    import torch
+    from geepee_b200 import ops
+    from geepee_b200.layers import to_dev, default_device
+    dev = device or default_device()
+    rng = np.random.RandomState(0)
+    mx, z = to_dev(rng.standard_normal((9, 3)), dev), to_dev(rng.standard_normal((6, 3)), dev)
+    ls, sf = to_dev(0.2 * rng.standard_normal(3), dev), to_dev(np.array([0.1]), dev)
+    k = ops.kmat(mx, z, ls, sf).cpu().numpy()
+    p1, p2 = ops.psi_stats(mx, torch.zeros_like(mx), z, ls, sf)
+    assert gu.rel_err(p1.cpu().numpy(), k) < 1e-13
+    assert gu.rel_err(p2.cpu().numpy(), k[:, :, None] * k[:, None, :]) < 1e-13
+    gold = gu.load('aep_sgplvm')
+    model = build_model(gold, 'fp64', device)
+    model.update_hypers(copy.deepcopy(gold['p']))
+    layer = model.sgp_layer
+    layer.compute_cavity(0.5)
+    x = rng.standard_normal((7, layer.Din))
+    md, _, _ = layer.forward_prop_thru_cav(x)
+    ms, _, _, _ = layer.forward_prop_thru_cav(x, np.zeros_like(x), mode='MM')
+    assert gu.rel_err(ms, md) < 1e-9, gu.rel_err(ms, md)

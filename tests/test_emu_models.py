@@ -64,3 +64,7 @@ def test_lik_interface():
 
 def test_gauss_emis_limit():
     mc.check_gauss_emis_limit()
+
+
+def test_psi_with_zero_variance_is_the_kernel():
+    mc.check_psi_zero_variance_is_kernel()

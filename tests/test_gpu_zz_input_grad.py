@@ -51,3 +51,8 @@ def test_lik_interface():
 def test_gauss_emis_limit():
     """tests/test_grads_emis.py:212-240 on the B200."""
     mc.check_gauss_emis_limit()
+
+
+def test_psi_with_zero_variance_is_the_kernel():
+    """TODO.txt:65-66 of the reference (SURVEY 8c pin iv) on the B200."""
+    mc.check_psi_zero_variance_is_kernel()
