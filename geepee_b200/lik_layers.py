@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .layers import to_dev
+from .layers import to_dev, default_device
 
 _F = torch.float64
 
@@ -38,7 +38,7 @@ class Probit_Layer(Lik_Layer):
 
     def __init__(self, N, D, device=None):
         super(Probit_Layer, self).__init__(N, D)
-        self.device = device
+        self.device = device = device if device is not None else default_device()
         from . import config
         gx, gw = np.polynomial.hermite.hermgauss(config.GH_DEGREE)   # lik_layers.py:290-301
         self._gx, self._gw = to_dev(gx, device), to_dev(gw, device)
@@ -131,7 +131,7 @@ class Gauss_Layer(Lik_Layer):
     def __init__(self, N, D, device=None):
         super(Gauss_Layer, self).__init__(N, D)
         self.sn = 0
-        self.device = device
+        self.device = device if device is not None else default_device()
         self._sn = None
 
     # ---- device path ------------------------------------------------------------------------
@@ -245,7 +245,7 @@ class Gauss_Emis(object):
         self.N = y.shape[0]
         self.Dout = Dout
         self.Din = Din
-        self.device = device
+        self.device = device = device if device is not None else default_device()
         self.C = np.zeros((Dout, Din))
         self.R = np.zeros(Dout)
         self._y = to_dev(y, device)
