@@ -23,6 +23,10 @@
 #ifndef GPB_EXP_REP
 #define GPB_EXP_REP 16
 #endif
+// bit-field argument reduction of the fp64 exp in the pair kernels (gpb_kernels.cuh, ExpBits)
+#ifndef GPB_EXP_BITS
+#define GPB_EXP_BITS 1
+#endif
 #ifndef GPB_MM_NR_FWD
 #define GPB_MM_NR_FWD 2
 #endif

@@ -1540,6 +1540,96 @@ GPB_DEVICE void exp_dom_n(double (&x)[N], const double* __restrict__ tab, int la
 #endif
     }
 }
+// Bit-field variant (GPB_EXP_BITS, pair kernels): the caller adds ExpBits::OFF to the row constant of
+// the exponent, so that every argument that matters lies in ONE binade, xs' = xs + OFF in [2^16, 2^17):
+//   xs' = 2^16 + 256 k' + j + f,   k' = k + 252 in [0, 256),  j in [0, 256),  f in [0, 1)
+// and the high word of the double holds k' (mantissa bits 19:12), j (11:4) and the top bits of f.
+// The argument reduction is then integer work on that word instead of two magic-number DADDs:
+//   clamp      : high word = max(high word, hi(2^16))  (deep underflow -> 2^-252, sign bit included)
+//   r = f - 1/2: xs' - (xs' with the mantissa below j cleared and the 1/2 bit set)      -- ONE DADD, exact
+//   table      : 2^((j + 1/2)/256 - 252), replicated like the table of exp_dom_n
+//   e^(r h)    : 1 + r (c1 + r (c2 + r c3))  -- every FMA has a constant operand (full issue rate)
+//   2^k'       : integer add of k' << 20 into the exponent field of the product
+// 5 fp64 instructions (1 add, 3 fma, 1 mul) instead of 7.  The price is the resolution of the sum:
+// ulp(xs') = 2^-36, i.e. 2^-37 * ln2/256 = 2e-14 relative per rounding of the 2Q-term exponent, the
+// size of the polynomial's own 1.4e-13 truncation.
+struct ExpBits {
+    static constexpr double OFF = 65536.0 + 252.0 * 256.0;
+    static constexpr int HI_MIN = 0x40F00000;     // high word of 2^16
+};
+GPB_DEVICE double exp_bits_table(int j) { return exp2(((double)j + 0.5) * (1.0 / 256.0) - 252.0); }
+GPB_DEVICE int exp_hi(double x) {
+#ifndef GPB_CPU_EMU
+    return __double2hiint(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int)(int32_t)(b >> 32);
+#endif
+}
+GPB_DEVICE double exp_sethi(double x, int hi) {
+#ifndef GPB_CPU_EMU
+    return __hiloint2double(hi, __double2loint(x));
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    b = (int64_t)(((uint64_t)(uint32_t)hi << 32) | ((uint64_t)b & 0xffffffffull));
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+// The two (a & imm) | reg combinations are written as explicit LOP3s: two immediates cannot be
+// encoded and the compiler otherwise spends two instructions on each (the integer pipe is as narrow as
+// the fp64 pipe on this chip); `half_bit` is the constant 8 kept in a register by the caller.
+template <int N>
+GPB_DEVICE void exp_dom_bits_n(double (&x)[N], const double* __restrict__ tab, int lane16, int half_bit) {
+    constexpr double h = 0.693147180559945309417232 / 256.0;
+    constexpr double c1 = h, c2 = h * h / 2.0, c3 = h * h * h / 6.0;
+    int hi[N];
+    double t[N], q[N];
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
+        hi[i] = exp_hi(x[i]);
+        hi[i] = hi[i] < ExpBits::HI_MIN ? ExpBits::HI_MIN : hi[i];
+    }
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
+#ifndef GPB_CPU_EMU
+        int idx;       // (j << 4) | lane16: element index into the [256][16] table
+        asm("lop3.b32 %0, %1, 0xff0, %2, 0xEA;" : "=r"(idx) : "r"(hi[i]), "r"(lane16));
+        t[i] = tab[idx];
+#else
+        t[i] = tab[(hi[i] & 0xff0) | lane16];
+#endif
+    }
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
+#ifndef GPB_CPU_EMU
+        int th;        // high word of xs' with the mantissa below j cleared and the 1/2 bit set
+        asm("lop3.b32 %0, %1, 0xFFFFFFF0, %2, 0xEA;" : "=r"(th) : "r"(hi[i]), "r"(half_bit));
+#else
+        const int th = (hi[i] & (int)0xFFFFFFF0) | half_bit;
+#endif
+        x[i] = exp_sethi(x[i], hi[i]) - exp_sethi(0.0, th);   // r in [-1/2, 1/2), exact
+    }
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = c3 * x[i] + c2;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = q[i] * x[i] + c1;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) q[i] = q[i] * x[i] + 1.0;
+    GPB_UNROLL
+    for (int i = 0; i < N; i++) {
+        const double p = t[i] * q[i];
+#ifndef GPB_CPU_EMU
+        int nh;        // exponent field += k' (one multiply-add; the compiler's own form takes three)
+        asm("mad.lo.s32 %0, %1, 256, %2;" : "=r"(nh) : "r"(hi[i] & 0xFF000), "r"(exp_hi(p)));
+        x[i] = exp_sethi(p, nh);
+#else
+        x[i] = exp_sethi(p, exp_hi(p) + ((hi[i] & 0xFF000) << 8));
+#endif
+    }
+}
 template <int N>
 GPB_DEVICE void exp_dom_n(float (&x)[N], const double*, int) {
     GPB_UNROLL
@@ -1553,6 +1643,14 @@ GPB_DEVICE void exp_dom_n(float (&x)[N], const double*, int) {
 #endif
     }
 }
+
+template <bool BITS, int N>
+GPB_DEVICE void pair_exp(double (&x)[N], const double* tab, int lane16, int half_bit) {
+    if (BITS) exp_dom_bits_n<N>(x, tab, lane16, half_bit);
+    else exp_dom_n<N>(x, tab, lane16);
+}
+template <bool BITS, int N>
+GPB_DEVICE void pair_exp(float (&x)[N], const double* tab, int lane16, int) { exp_dom_n<N>(x, tab, lane16); }
 
 // Geometry of the per-warp transposition buffer of the pair kernel: every lane stores the NS row
 // sums of its pairs for HT consecutive rows (one 16-byte padded line of 32 lane records per row);
@@ -1602,6 +1700,7 @@ GPB_DEVICE void mm_pairs_body(MMArgs<T> a) {
     constexpr int NS = BWD ? 2 * Q : DOC;
     constexpr bool kGen = BWD && GEN;
     constexpr bool kExpand = !BWD && sizeof(T) == 8;
+    constexpr bool kBits = GPB_EXP_BITS != 0 && sizeof(T) == 8;     // bit-field argument reduction
     constexpr int VW = 16 / (int)sizeof(T);
     constexpr int RLraw = 1 + 2 * Q + (BWD ? DOC : 0);
     constexpr int RL = (RLraw + VW - 1) / VW * VW;       // row record length (16-byte multiple)
@@ -1650,8 +1749,10 @@ GPB_DEVICE void mm_pairs_body(MMArgs<T> a) {
     if (tid < Q) s_l2[tid] = tid < a.Qa ? exp(2.0 * a.ls[tid]) : 1.0;
     if (kTab > 0)
         for (int i = tid; i < kTab; i += kThreads)
-            s_tab[i] = exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
+            s_tab[i] = kBits ? exp_bits_table(i / (ExpDom<T>::REP > 0 ? ExpDom<T>::REP : 1))
+                             : exp2((double)(i / ExpDom<T>::REP) * (1.0 / (ExpDom<T>::ENT > 0 ? ExpDom<T>::ENT : 1)));
     const int lane16 = lane & ((ExpDom<T>::REP > 0 ? ExpDom<T>::REP : 1) - 1);
+    const int half_bit = 8 + (a.n < 0);      // = 8, opaque to constant folding (LOP3 operand, exp_dom_bits_n)
     unsigned char* xw = dsm + kTab * sizeof(double) + warp * X::kWarpB;   // this warp's buffer
 
     const int r_begin = blockIdx.y * a.rows_per_split;
@@ -1686,7 +1787,7 @@ GPB_DEVICE void mm_pairs_body(MMArgs<T> a) {
                 }
             }
             // rows past the end: psi2' = exp(-1e5 + ...) ~ 0 (1e-308 in fp64) and their dv is 0
-            rec[0] = (T)((ok ? lcn : -1.0e5) * kS + a0);
+            rec[0] = (T)((ok ? lcn : -1.0e5) * kS + a0 + (kBits ? ExpBits::OFF : 0.0));
             if (BWD) {
                 for (int d = 0; d < DOC; d++)
                     rec[1 + 2 * Q + d] =
@@ -1746,7 +1847,7 @@ GPB_DEVICE void mm_pairs_body(MMArgs<T> a) {
                     x[i * RP + j] = xx;
                 }
             }
-            exp_dom_n<NR * RP>(x, s_tab, lane16);
+            pair_exp<kBits>(x, s_tab, lane16, half_bit);
             if (BWD && !GEN && DOC <= 4) {
                 // Register-operand bandwidth: an fp64 FMA with three distinct register operands
                 // issues at ~2/3 rate on this chip, one that shares an operand with its predecessor

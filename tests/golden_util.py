@@ -21,9 +21,13 @@ def load(name):
     return out
 
 
-def model_cases(prefix=None):
+def model_cases(prefix=None, bench=False):
+    """Golden model cases.  `bench_*` files are reduced-n runs at the benchmark's own shapes
+    (M = 128 ... 512; tests/golden/gen_golden_bench.py): too slow for the CPU fiber emulator and
+    the numpy oracle, so they are listed only when `bench` is set (GPU tests)."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')))
     names = [n for n in names if n not in ('kernels', 'gauss_emis', 'input_grad', 'layer_iface', 'lik_iface')]
+    names = [n for n in names if n.startswith('bench_') == bool(bench)]
     if prefix:
         names = [n for n in names if n.startswith(prefix)]
     return names

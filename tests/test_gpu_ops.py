@@ -36,6 +36,30 @@ def test_mm_layer(n, M, Q, Do, prec, tol):
     oc.check_mm_layer(n, M, Q, Do, prec, tol)
 
 
+# the (M, Q, Dout) of the BASELINE.json configs: cfg3 layers 1 / 2 (M=256, Q=2, Dout=2 / 1), cfg4
+# (M=200, Q=4, Dout=4), cfg2 (M=128, Q=5, Dout=50), a Q=10 layer at M=256; n small enough for the
+# oracle's [n,M,M] psi2, plus one n that spans several row tiles and row splits of the pair kernels
+BENCH_MM = [(96, 256, 2, 2), (96, 256, 2, 1), (96, 200, 4, 4), (64, 128, 5, 50), (64, 256, 10, 1),
+            (700, 256, 2, 2)]
+BENCH_DET = [(256, 256, 10, 2), (300, 512, 16, 1), (256, 256, 10, 1)]
+
+
+@pytest.mark.parametrize('prec,tol', [('fp64', 1e-10), ('fp32', 5e-4)])
+@pytest.mark.parametrize('n,M,Q,Do', BENCH_MM)
+def test_mm_layer_bench_shapes(n, M, Q, Do, prec, tol):
+    """Every output of the moment-matched forward / backward ops against the oracle's
+    psi_stats / psi_derivs at the benchmark's own pseudo-point counts (the wide DMMA kernels, the
+    129-block pair grid at M = 256, row splits).  fp64 1e-10 (x10 on the cancelling sums) is three
+    orders inside the 1e-6 bar."""
+    oc.check_mm_layer(n, M, Q, Do, prec, tol)
+
+
+@pytest.mark.parametrize('prec,tol', [('fp64', 1e-10), ('fp32', 5e-4)])
+@pytest.mark.parametrize('n,M,D,Do', BENCH_DET)
+def test_det_layer_bench_shapes(n, M, D, Do, prec, tol):
+    oc.check_det_layer(n, M, D, Do, prec, tol)
+
+
 def test_kmat_psi_lik():
     oc.check_kmat_psi_lik()
 
