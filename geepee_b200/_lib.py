@@ -52,6 +52,9 @@ _SIGS = {
                    [c_dp, c_dp, c_dp, c_dp, c_dp, ctypes.c_size_t, c_dp]),
     'gpb_mm_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 12 + [ctypes.c_int] * 4 + [c_dp] * 9 +
                    [ctypes.c_size_t, c_dp]),
+    'gpb_tail_exec': (ctypes.c_int, [c_dp, ctypes.c_int, c_dp]),
+    'gpb_tail_gather': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp]),
+    'gpb_tail_copy': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, c_dp, c_dp]),
     'gpb_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'gpb_profile_collect': (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     'gpb_fma_peak': (ctypes.c_int, [ctypes.c_int, ctypes.c_long, c_dp, ctypes.POINTER(ctypes.c_double), c_dp]),

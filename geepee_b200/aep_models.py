@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import dist
+from . import tail as tl
 from .sched import TailStreams
 from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
 from .config import PROP_MM, PROP_MC, PROP_LIN, MC_NO_SAMPLES
@@ -91,7 +92,7 @@ class SGPR(Base_SGPR):
         grads = L._tail_det(_get_stats(add, 's_'), alpha)
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
-        energy = scale_logZ * add['logZ'] + L._phi(alpha)
+        energy = tl.dots([(scale_logZ, add['logZ'], None), (1.0, L._phi(alpha), None)])
         return self._finish(energy, grads)
 
 
@@ -174,9 +175,7 @@ class SDGPR(Base_SDGPR):
                 if i == self.L - 1:
                     top = add
         ts.join_all()
-        energy = scale_logZ * top['logZ']
-        for i in range(self.L):
-            energy = energy + phis[i]
+        energy = tl.dots([(scale_logZ, top['logZ'], None)] + [(1.0, phis[i], None) for i in range(self.L)])
         if self.lik_layer.has_sn:
             grads['sn'] = top['dsn'].reshape(())
         return self._finish(energy, grads)

@@ -12,6 +12,7 @@ import torch
 from scipy.optimize import minimize
 
 from . import config, dist
+from . import tail as tl
 from .config import PROP_MM, PROP_MC, PROP_LIN
 from .layers import _host_copy, default_device, to_dev, pack_to_device, to_host
 from .lik_layers import Gauss_Layer, Probit_Layer, Gauss_Emis
@@ -105,7 +106,7 @@ class Base_Model(object):
         device->host copy."""
         keys = sorted(grads.keys())
         scale = 1.0 / self.N if divide_by_N else 1.0
-        flat = torch.cat([energy.reshape(1)] + [grads[k].reshape(-1) for k in keys]) * scale
+        flat = tl.gather([energy.reshape(1)] + [grads[k].reshape(-1) for k in keys], scale)
         host = to_host(flat)
         out, off = {}, 1
         for k in keys:

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import config, ops, _lib
+from . import tail as tl
 from .tailgraph import TailGraph
 
 _F = torch.float64
@@ -130,12 +131,13 @@ def spd_inverse(A):
 
 
 def bmv(A, x):
-    """batched matrix-vector product [d,a,b] x [d,b] -> [d,a]"""
-    return torch.matmul(A, x.unsqueeze(-1)).squeeze(-1)
+    """batched matrix-vector product [d,a,b] x [d,b] -> [d,a] (library kernel, tail.py)"""
+    return tl.matvec(A, x)
 
 
-def outer(a, b):
-    return a.unsqueeze(-1) * b.unsqueeze(-2)
+def sandwich(L, X, alpha=1.0, C=None, beta=0.0):
+    """alpha L X L (+ beta C) for (batches of) M x M matrices: two tensor-core products."""
+    return tl.gemm(L, tl.gemm(X, L), alpha=alpha, C=C, beta=beta)
 
 
 class Base_SGP_Layer(object):
@@ -207,13 +209,9 @@ class Base_SGP_Layer(object):
         t['ls'] = ins['ls'].reshape(self.Din).contiguous()
         t['sf'] = ins['sf'].reshape(-1)[:1].contiguous()
         t['zu'] = ins['zu'].reshape(M, self.Din).contiguous()
-        eta1 = ins['eta1_R'].reshape(Dout, -1)
-        R = torch.zeros((Dout, M, M), dtype=_F, device=dev)
-        R[:, self._iu[0], self._iu[1]] = eta1
-        dg = torch.diagonal(R, dim1=1, dim2=2)
-        dg.copy_(torch.exp(dg))
+        R = tl.unpack_r(ins['eta1_R'].reshape(Dout, -1).contiguous(), M)      # base_models.py:645-653
         t['theta_1_R'] = R
-        t['theta_1'] = torch.matmul(R.transpose(1, 2), R)
+        t['theta_1'] = tl.gemm(R, R, ta=True)
         t['theta_2'] = ins['eta2'].reshape(Dout, M).contiguous()
         self._cavity_done = None
         self.compute_kuu()
@@ -244,30 +242,33 @@ class Base_SGP_Layer(object):
         Ki = t['Kuuinv']
         self._cavity_ready = None
         alpha = getattr(self, '_fuse_cavity_alpha', None)
+        # log-determinants are kept as the kernel returns them: `ld_Su` holds log|Su^-1| when the inverse
+        # was factorised (natural parameters) and log|Su| otherwise; _sign_Su turns it into log|Su|
+        self._sign_Su = -1.0 if self.nat_param else 1.0
         if self.nat_param and alpha is not None:
             # AEP fast path: q(u) and the cavity need inv(Ki + theta_1) and inv(Ki + beta theta_1);
             # factorise both in ONE batched call (halves the launch count of the tail)
             beta = (self.N - alpha) * 1.0 / self.N
             Do = self.Dout
-            both = torch.cat((Ki + t['theta_1'], Ki + beta * t['theta_1']), dim=0)
+            both = torch.empty((2 * Do, self.M, self.M), dtype=_F, device=Ki.device)
+            tl.lincomb([(1.0, Ki), (1.0, t['theta_1'])], out=both[:Do])
+            tl.lincomb([(1.0, Ki), (beta, t['theta_1'])], out=both[Do:])
             inv, ld = spd_inverse(both)
             t['Suinv'], t['Suhatinv'] = both[:Do], both[Do:]
             t['Su'], t['Suhat'] = inv[:Do], inv[Do:]
-            t['logdet_Su'], t['logdet_Suhat'] = -ld[:Do], -ld[Do:]
+            t['ld_Su'], t['ld_Suhat'] = ld[:Do], ld[Do:]
             t['mu'] = bmv(t['Su'], t['theta_2'])
             self._cavity_ready = alpha
         elif self.nat_param:
-            t['Suinv'] = Ki + t['theta_1']
-            t['Su'], ld = spd_inverse(t['Suinv'])
-            t['logdet_Su'] = -ld
+            t['Suinv'] = tl.lincomb([(1.0, Ki), (1.0, t['theta_1'])])
+            t['Su'], t['ld_Su'] = spd_inverse(t['Suinv'])
             t['mu'] = bmv(t['Su'], t['theta_2'])
         else:
             t['Su'] = t['theta_1']
-            t['Suinv'], ld = spd_inverse(t['Su'])
-            t['logdet_Su'] = ld
+            t['Suinv'], t['ld_Su'] = spd_inverse(t['Su'])
             t['mu'] = t['theta_2']
-        t['Splusmm'] = t['Su'] + outer(t['mu'], t['mu'])
-        t['A'] = torch.matmul(t['mu'], Ki)
+        t['Splusmm'] = tl.lincomb([(1.0, t['Su'])], outer=(1.0, t['mu'], t['mu']))
+        t['A'] = tl.matvec(Ki, t['mu'], t0=True)
         # B_sto = Ki Splusmm Ki - Ki and B_det = Ki Su Ki - Ki are formed on first use (_B): a layer
         # is fed either deterministic or uncertain inputs, never both in one objective call
         t.pop('B_sto', None)
@@ -353,7 +354,7 @@ class Base_SGP_Layer(object):
         t = self._t
         if name not in t:
             Ki = t['Kuuinv']
-            t[name] = torch.matmul(Ki, torch.matmul(t[self._B_SRC[name]], Ki)) - Ki
+            t[name] = sandwich(Ki, t[self._B_SRC[name]], C=Ki, beta=-1.0)
         return t[name]
 
     def _det_operands(self, cav):
@@ -376,8 +377,7 @@ class Base_SGP_Layer(object):
         x, opnd, Ks, Ts = ctx
         dA, dzu, dl, dsf2 = ops.det_bwd(self.prec, x, t['zu'], t['ls'], t['sf'], opnd, dm, dv, Ks, Ts)
         dB = ops.det_syrk(self.prec, Ks, dv, self.M)
-        return {'dA': dA, 'dB': dB, 'dzu': dzu, 'dl': dl, 'dsf2': dsf2,
-                'dvsum': dv.sum().reshape(1)}
+        return {'dA': dA, 'dB': dB, 'dzu': dzu, 'dl': dl, 'dsf2': dsf2, 'dvsum': tl.total(dv)}
 
     def _fwd_mm(self, mx, vx, cav, save=True):
         """a6 on the device (save=False: prediction, nothing kept for a backward)."""
@@ -478,49 +478,46 @@ class Base_SGP_Layer(object):
         return dx, dx.copy()
 
     # ---- shared chain rules ------------------------------------------------------------------
-    def _pack_eta1(self, dtheta1):
-        """theta_1 = R^T R with log-diagonal packing (base_models.py:505-514)."""
+    def _pack_eta1(self, terms):
+        """theta_1 = R^T R with log-diagonal packing (base_models.py:505-514) of sum_i c_i dtheta1_i;
+        terms: one or two (coef, [Dout,M,M])."""
         R = self._t['theta_1_R']
-        dR = torch.matmul(R, dtheta1 + dtheta1.transpose(1, 2))
-        dg = torch.diagonal(dR, dim1=1, dim2=2)
-        dg.mul_(torch.diagonal(R, dim1=1, dim2=2))
-        return dR[:, self._iu[0], self._iu[1]]
+        sym = tl.lincomb([(c, X) for c, X in terms] + [(c, X, True) for c, X in terms])
+        return tl.pack_r(tl.gemm(R, sym), R)
 
     def _posterior_grad_u(self, dmu, dSu):
-        """base_models.py:490-516 -> (deta1_R, deta2, dKuuinv)."""
+        """base_models.py:490-516 -> (dSuinv or dSu [the theta_1 gradient before packing], deta2, dKuuinv or None)."""
         t = self._t
         if self.nat_param:
-            dSu = dSu + outer(dmu, t['theta_2'])
-            dSuinv = -torch.matmul(t['Su'], torch.matmul(dSu, t['Su']))
-            return self._pack_eta1(dSuinv), bmv(t['Su'], dmu), dSuinv.sum(0)
-        return self._pack_eta1(dSu), dmu, torch.zeros_like(t['Kuu'])
+            dSu = tl.lincomb([(1.0, dSu)], outer=(1.0, dmu, t['theta_2']))
+            dSuinv = sandwich(t['Su'], dSu, alpha=-1.0)
+            return dSuinv, bmv(t['Su'], dmu), tl.lincomb([(1.0, dSuinv)], reduce=True)
+        return dSu, dmu, None
 
     def compute_posterior_grad_u(self, dmu, dSu):
-        r = self._posterior_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device))
-        return tuple(x.cpu().numpy() for x in r)
+        d1, e2, dKi = self._posterior_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device))
+        e1 = self._pack_eta1([(1.0, d1)])
+        dKi = dKi.cpu().numpy() if dKi is not None else np.zeros((self.M, self.M))
+        return e1.cpu().numpy(), e2.cpu().numpy(), dKi
+
+    def _stats_record(self, st):
+        """[dzu | dl | dsf2 | dvsum] as one contiguous record (the order of a layer's packed statistics)."""
+        parts = [st['dzu'], st['dl'], st['dsf2'], st['dvsum']]
+        p0 = parts[0].data_ptr()
+        off = 0
+        for x in parts:
+            if x.data_ptr() != p0 + 8 * off or not x.is_contiguous():
+                return tl.gather([q.contiguous() for q in parts])
+            off += x.numel()
+        return torch.as_strided(parts[0], (off,), (1,))
 
     def _kernel_hyper_tail(self, st, Mm):
         """aep_models.py:455-460 + 497-504 + kernels.py:447-475 (d_trace_MKzz_dhypers with
-        Kzz = Kuu - JITTER I): fold direct kernel derivatives with the Kuu path."""
+        Kzz = Kuu - JITTER I): fold direct kernel derivatives with the Kuu path; one launch."""
         t = self._t
-        z = t['zu']
-        l = torch.exp(t['ls'])
-        ls2 = l * l
-        sf2 = torch.exp(2.0 * t['sf'])
-        Kzz = t['Kuu'] - config.JITTER * torch.eye(self.M, dtype=_F, device=z.device)
-        dls = st['dl'] * l
-        dsf = 2.0 * sf2 * (st['dsf2'] + st['dvsum'])
-        g_sf = (Mm * Kzz).sum()
-        Ml = 0.5 * Mm * Kzz
-        Xl = z / l
-        Xl2 = Xl * Xl
-        g_ls = (Ml.sum(0).unsqueeze(1) * Xl2).sum(0) + (Ml.sum(1).unsqueeze(1) * Xl2).sum(0) \
-            - 2.0 * (Xl * torch.matmul(Ml, Xl)).sum(0)
-        Xb = z / ls2
-        g_z = torch.zeros_like(z)
-        for Mb in (-Mm.t() * Kzz, -Mm * Kzz):
-            g_z = g_z + Xb * Mb.sum(0).unsqueeze(1) - torch.matmul(Mb, Xb)
-        return dsf + 2.0 * g_sf, dls + 2.0 * g_ls, st['dzu'] + g_z
+        M, D = self.M, self.Din
+        out = tl.khyper(Mm, t['Kuu'], t['zu'], t['ls'], t['sf'], self._stats_record(st), config.JITTER)
+        return out[0:1], out[1:1 + D], out[1 + D:].reshape(M, D)
 
     def sample(self, x):
         """base_models.py:428-452: one joint draw of f(x) -- u ~ q(u), then f | u at the test
@@ -532,7 +529,7 @@ class Base_SGP_Layer(object):
         xd = to_dev(x, dev)
         Lu = torch.linalg.cholesky(t['Su'])
         eps_u = to_dev(np.random.randn(self.Dout, self.M), dev)
-        u = t['mu'] + bmv(Lu, eps_u)
+        u = t['mu'] + torch.matmul(Lu, eps_u.unsqueeze(-1)).squeeze(-1)
         n = xd.shape[0]
         kff = ops.kmat(xd, xd, t['ls'], t['sf'], config.JITTER)
         kfu = ops.kmat(xd, t['zu'], t['ls'], t['sf'])
@@ -580,23 +577,19 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         t = self._t
         Ki = t['Kuuinv']
         beta = (self.N - alpha) * 1.0 / self.N
-        ld = None
         if self.nat_param and getattr(self, '_cavity_ready', None) == alpha:
-            t['muhat'] = bmv(t['Suhat'], beta * t['theta_2'])     # Suhat came with the posterior
+            t['muhat'] = tl.matvec(t['Suhat'], t['theta_2'], c0=beta)     # Suhat came with the posterior
         elif self.nat_param:
-            t['Suhatinv'] = Ki + beta * t['theta_1']
-            t['Suhat'], ld = spd_inverse(t['Suhatinv'])
-            t['muhat'] = bmv(t['Suhat'], beta * t['theta_2'])
+            t['Suhatinv'] = tl.lincomb([(1.0, Ki), (beta, t['theta_1'])])
+            t['Suhat'], t['ld_Suhat'] = spd_inverse(t['Suhatinv'])
+            t['muhat'] = tl.matvec(t['Suhat'], t['theta_2'], c0=beta)
         else:
-            f1 = t['Suinv'] - Ki
             f2 = bmv(t['Suinv'], t['mu'])
-            t['Suhatinv'] = Ki + beta * f1
-            t['Suhat'], ld = spd_inverse(t['Suhatinv'])
-            t['muhat'] = bmv(t['Suhat'], beta * f2)
-        if ld is not None:
-            t['logdet_Suhat'] = -ld
-        t['Ahat'] = torch.matmul(t['muhat'], Ki)
-        t['Splusmmhat'] = t['Suhat'] + outer(t['muhat'], t['muhat'])
+            t['Suhatinv'] = tl.lincomb([(1.0 - beta, Ki), (beta, t['Suinv'])])      # Ki + beta (Suinv - Ki)
+            t['Suhat'], t['ld_Suhat'] = spd_inverse(t['Suhatinv'])
+            t['muhat'] = tl.matvec(t['Suhat'], f2, c0=beta)
+        t['Ahat'] = tl.matvec(Ki, t['muhat'], t0=True)
+        t['Splusmmhat'] = tl.lincomb([(1.0, t['Suhat'])], outer=(1.0, t['muhat'], t['muhat']))
         t.pop('Bhat_sto', None)      # formed on first use (_B)
         t.pop('Bhat_det', None)
         t.pop('phi', None)
@@ -615,49 +608,52 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         if 'phi' in t and self._cavity_done is not None and self._cavity_done == alpha:
             return t['phi']
         N = self.N
-        phi_prior = 0.5 * self.Dout * t['logdet_Kuu']
-        phi_post = 0.5 * t['logdet_Su'].sum() + 0.5 * (t['mu'] * bmv(t['Suinv'], t['mu'])).sum()
-        phi_cav = 0.5 * t['logdet_Suhat'].sum() + 0.5 * (t['muhat'] * bmv(t['Suhatinv'], t['muhat'])).sum()
-        return phi_prior + (N * 1.0 / alpha - 1.0) * phi_post - (N * 1.0 / alpha) * phi_cav
+        sp, sc = N * 1.0 / alpha - 1.0, N * 1.0 / alpha
+        v1 = bmv(t['Suinv'], t['mu'])
+        v2 = bmv(t['Suhatinv'], t['muhat'])
+        # phi_prior + sp phi_post - sc phi_cav; log|Suhat| = -ld_Suhat (the inverse was factorised)
+        return tl.dots([(0.5 * self.Dout, t['logdet_Kuu'], None), (0.5 * sp * self._sign_Su, t['ld_Su'], None),
+                        (0.5 * sp, t['mu'], v1), (0.5 * sc, t['ld_Suhat'], None), (-0.5 * sc, t['muhat'], v2)])
 
     def compute_phi(self, alpha=1.0):
         return float(self._phi(alpha).item())
 
     def compute_phi_prior(self):
         """aep_models.py:62-70."""
-        return float((0.5 * self.Dout * self._t['logdet_Kuu']).item())
+        return float(0.5 * self.Dout * self._t['logdet_Kuu'].item())
 
     def compute_phi_posterior(self):
         """aep_models.py:72-83."""
         t = self._t
-        return float((0.5 * t['logdet_Su'].sum() + 0.5 * (t['mu'] * bmv(t['Suinv'], t['mu'])).sum()).item())
+        return float(tl.dots([(0.5 * self._sign_Su, t['ld_Su'], None),
+                              (0.5, t['mu'], bmv(t['Suinv'], t['mu']))]).item())
 
     def compute_phi_cavity(self):
         """aep_models.py:85-97 (after compute_cavity)."""
         t = self._t
-        return float((0.5 * t['logdet_Suhat'].sum()
-                      + 0.5 * (t['muhat'] * bmv(t['Suhatinv'], t['muhat'])).sum()).item())
+        return float(tl.dots([(-0.5, t['ld_Suhat'], None),
+                              (0.5, t['muhat'], bmv(t['Suhatinv'], t['muhat']))]).item())
 
     def _cav_grad_u(self, dmu, dSu, alpha):
-        """aep_models.py:548-586."""
+        """aep_models.py:548-586 -> (theta_1 gradient before packing, deta2, dKuuinv)."""
         t = self._t
         beta = (self.N - alpha) * 1.0 / self.N
         if self.nat_param:
-            dSu = dSu + outer(dmu, beta * t['theta_2'])
-            dSuinv = -torch.matmul(t['Suhat'], torch.matmul(dSu, t['Suhat']))
-            return self._pack_eta1(beta * dSuinv), beta * bmv(t['Suhat'], dmu), dSuinv.sum(0)
+            dSu = tl.lincomb([(1.0, dSu)], outer=(beta, dmu, t['theta_2']))
+            dSuinv = sandwich(t['Suhat'], dSu, alpha=-1.0)
+            return ((beta, dSuinv),), tl.matvec(t['Suhat'], dmu, c0=beta), tl.lincomb([(1.0, dSuinv)], reduce=True)
         f2 = bmv(t['Suinv'], t['mu'])
-        dSuhat = dSu + outer(dmu, beta * f2)
-        dSuhatinv = -torch.matmul(t['Suhat'], torch.matmul(dSuhat, t['Suhat']))
-        dSuinv_1 = beta * dSuhatinv
+        dSuhat = tl.lincomb([(1.0, dSu)], outer=(beta, dmu, f2))
+        dSuhatinv = sandwich(t['Suhat'], dSuhat, alpha=-1.0)
         Sdm = bmv(t['Suhat'], dmu)
-        dSuinv = dSuinv_1 + beta * outer(Sdm, t['mu'])
-        dtheta1 = -torch.matmul(t['Suinv'], torch.matmul(dSuinv, t['Suinv']))
-        return self._pack_eta1(dtheta1), beta * bmv(t['Suinv'], Sdm), (1 - beta) / beta * dSuinv_1.sum(0)
+        dSuinv = tl.lincomb([(beta, dSuhatinv)], outer=(beta, Sdm, t['mu']))
+        dtheta1 = sandwich(t['Suinv'], dSuinv, alpha=-1.0)
+        return ((1.0, dtheta1),), tl.matvec(t['Suinv'], Sdm, c0=beta), \
+            tl.lincomb([(1.0 - beta, dSuhatinv)], reduce=True)
 
     def compute_cav_grad_u(self, dmu, dSu, alpha):
-        r = self._cav_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device), alpha)
-        return tuple(x.cpu().numpy() for x in r)
+        d1, e2, dKi = self._cav_grad_u(to_dev(dmu, self.device), to_dev(dSu, self.device), alpha)
+        return self._pack_eta1(list(d1)).cpu().numpy(), e2.cpu().numpy(), dKi.cpu().numpy()
 
     def _tail_det(self, st, alpha):
         return self._post_tail('det', self._tail_det_impl, st, alpha)
@@ -668,12 +664,22 @@ class AEP_SGP_Layer(Base_SGP_Layer):
     def _tail_mc(self, st, alpha):
         return self._post_tail('mc', self._tail_mc_impl, st, alpha)
 
+    def _dKi_common(self, dA, dB, S):
+        """sum_d dA_d muhat_d^T + 2 sum_d (Ki S_d)^T dB_d as tensor-core products with K = Dout (resp.
+        Dout M): the sums over the output dimensions are the products' inner dimension."""
+        t = self._t
+        Do, M = self.Dout, self.M
+        Y = tl.gemm(t['Kuuinv'], S)                                                # [Do, M, M]
+        Z = tl.gemm(Y.reshape(Do * M, M), dB.reshape(Do * M, M), ta=True, alpha=2.0)
+        return tl.gemm(dA, t['muhat'], ta=True, C=Z, beta=1.0)
+
     def _tail_mc_impl(self, st, alpha):
         """aep_models.py:352-403 (backprop_grads_lvm_mc) on the statistics of the stacked samples
         (dA = sum_n dm kfu, dB = sum_n dv kfu kfu^T): with SK = Suhat Kuuinv,
         dSinv_d = -SK dB_d SK^T - (SK dA_d) muhat_d^T, dtheta2_d = beta SK dA_d + phi terms."""
         t = self._t
         N, Ki = self.N, t['Kuuinv']
+        Do, M = self.Dout, self.M
         if not self.nat_param:
             raise NotImplementedError('AEP Monte-Carlo propagation needs nat_param=True (the reference '
                                       'treats theta as natural parameters: aep_models.py:365-371)')
@@ -681,47 +687,62 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         scale_post = N * 1.0 / alpha - 1.0
         scale_cav = -N * 1.0 / alpha
         dA, dB = st['dA'], st['dB']
-        SK = torch.matmul(t['Suhat'], Ki)
+        SK = tl.gemm(t['Suhat'], Ki)
         SKdA = bmv(SK, dA)
-        dSinv = -torch.matmul(SK, torch.matmul(dB, SK.transpose(1, 2))) - outer(SKdA, t['muhat'])
-        dtheta1 = beta * dSinv - 0.5 * scale_post * t['Splusmm'] - 0.5 * scale_cav * beta * t['Splusmmhat']
-        dtheta2 = beta * SKdA + scale_post * t['mu'] + scale_cav * beta * t['muhat']
-        dKi = torch.matmul(dA.t(), t['muhat']) \
-            + 2.0 * torch.matmul(SK, dB).sum(0) - dB.sum(0) + dSinv.sum(0)
-        Minner = scale_post * t['Splusmm'].sum(0) + scale_cav * t['Splusmmhat'].sum(0) - 2.0 * dKi
-        M_all = 0.5 * (self.Dout * Ki + torch.matmul(Ki, torch.matmul(Minner, Ki)))
+        X = tl.gemm(SK, tl.gemm(dB, SK, tb=True))
+        dSinv = tl.lincomb([(-1.0, X)], outer=(-1.0, SKdA, t['muhat']))
+        dtheta1 = tl.lincomb([(beta, dSinv), (-0.5 * scale_post, t['Splusmm']),
+                              (-0.5 * scale_cav * beta, t['Splusmmhat'])])
+        dtheta2 = tl.veccomb([(beta, SKdA), (scale_post, t['mu']), (scale_cav * beta, t['muhat'])])
+        # dKi = dA^T muhat + 2 sum_d SK_d dB_d - sum_d dB_d + sum_d dSinv_d
+        Z = tl.gemm(self._stack_t(SK), dB.reshape(Do * M, M), ta=True, alpha=2.0)
+        Z = tl.gemm(dA, t['muhat'], ta=True, C=Z, beta=1.0)
+        T1 = tl.lincomb([(-1.0, dB), (1.0, dSinv), (-0.5 * scale_post, t['Splusmm']),
+                         (-0.5 * scale_cav, t['Splusmmhat'])], reduce=True)
+        # Minner = scale_post sum Splusmm + scale_cav sum Splusmmhat - 2 dKi  = -2 (Z + T1)
+        Minner = tl.lincomb([(-2.0, Z), (-2.0, T1)])
+        M_all = sandwich(Ki, Minner, alpha=0.5, C=Ki, beta=0.5 * Do)
         dsf, dls, dzu = self._kernel_hyper_tail(st, M_all)
-        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1(dtheta1), 'eta2': dtheta2}
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1([(1.0, dtheta1)]), 'eta2': dtheta2}
+
+    def _stack_t(self, X):
+        """[Do, M, M] -> the [Do M, M] matrix of the TRANSPOSED blocks (so that a product with ta=True
+        contracts sum_d X_d Y_d)."""
+        return tl.lincomb([(1.0, X, True)]).reshape(self.Dout * self.M, self.M)
 
     def _tail_det_impl(self, st, alpha):
         """aep_models.py:462-511 rewritten on the statistics (dA = sum_n dm kfu,
         dB = sum_n dv kfu kfu^T): dmucav = dA Kuuinv, dSucav = Kuuinv dB Kuuinv."""
         t = self._t
         N, Ki = self.N, t['Kuuinv']
+        Do = self.Dout
         scale_post = N * 1.0 / alpha - 1.0
         scale_cav = -N * 1.0 / alpha
         dA, dB = st['dA'], st['dB']
-        dmucav = torch.matmul(dA, Ki)
-        dSucav = torch.matmul(Ki, torch.matmul(dB, Ki))
         Sim = bmv(t['Suhatinv'], t['muhat'])
-        dmucav = dmucav + scale_cav * Sim
-        dSucav = dSucav + scale_cav * (0.5 * t['Suhatinv'] - 0.5 * outer(Sim, Sim))
-        e1c, e2c, dKi_cav = self._cav_grad_u(dmucav, dSucav, alpha)
-        Sim = bmv(t['Suinv'], t['mu'])
-        dmu = scale_post * Sim
-        dSu = scale_post * (0.5 * t['Suinv'] - 0.5 * outer(Sim, Sim))
-        e1p, e2p, dKi_post = self._posterior_grad_u(dmu, dSu)
-        dKi = torch.matmul(dA.t(), t['muhat']) \
-            + 2.0 * torch.matmul(torch.matmul(Ki, t['Suhat']).transpose(1, 2), dB).sum(0) \
-            - dB.sum(0) + dKi_cav + dKi_post - 0.5 * self.Dout * t['Kuu']
-        Mm = -torch.matmul(Ki, torch.matmul(dKi, Ki))
+        dmucav = tl.matvec(Ki, dA, t0=True, w0=Sim, cw0=scale_cav)
+        dSucav = tl.lincomb([(1.0, sandwich(Ki, dB)), (0.5 * scale_cav, t['Suhatinv'])],
+                            outer=(-0.5 * scale_cav, Sim, Sim))
+        d1c, e2c, dKi_cav = self._cav_grad_u(dmucav, dSucav, alpha)
+        Simp = bmv(t['Suinv'], t['mu'])
+        dSu = tl.lincomb([(0.5 * scale_post, t['Suinv'])], outer=(-0.5 * scale_post, Simp, Simp))
+        d1p, e2p, dKi_post = self._posterior_grad_u(tl.veccomb([(scale_post, Simp)]), dSu)
+        # dKi = dA^T muhat + 2 sum_d (Ki Suhat_d)^T dB_d - sum_d dB_d + dKi_cav + dKi_post - Dout/2 Kuu
+        Z = self._dKi_common(dA, dB, t['Suhat'])
+        sumB = tl.lincomb([(1.0, dB)], reduce=True)
+        terms = [(1.0, Z), (-1.0, sumB), (1.0, dKi_cav)] + ([(1.0, dKi_post)] if dKi_post is not None else [])
+        dKi = tl.lincomb(terms)
+        dKi = tl.lincomb([(1.0, dKi), (-0.5 * Do, t['Kuu'])])
+        Mm = sandwich(Ki, dKi, alpha=-1.0)
         dsf, dls, dzu = self._kernel_hyper_tail(st, Mm)
-        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1c + e1p, 'eta2': e2c + e2p}
+        e1 = self._pack_eta1(list(d1c) + [(1.0, d1p)])
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1, 'eta2': tl.veccomb([(1.0, e2c), (1.0, e2p)])}
 
     def _tail_mm_impl(self, st, alpha):
         """aep_models.py:252-297 on the statistics (dA = sum_n dm_all psi1, dB = sum_n dv psi2)."""
         t = self._t
         N, Ki = self.N, t['Kuuinv']
+        Do = self.Dout
         if not self.nat_param:
             raise NotImplementedError('AEP moment-matched layers need nat_param=True (the reference '
                                       'has no valid non-natural variant: aep_models.py:252-297)')
@@ -729,21 +750,23 @@ class AEP_SGP_Layer(Base_SGP_Layer):
         scale_post = N * 1.0 / alpha - 1.0
         scale_cav = -N * 1.0 / alpha
         dA, dB = st['dA'], st['dB']
-        dvcav = torch.matmul(Ki, torch.matmul(dB, Ki))
-        dmcav = 2.0 * bmv(dvcav, t['muhat']) + torch.matmul(dA, Ki)
-        dvcav = dvcav + beta * outer(dmcav, t['theta_2'])
-        dvcavinv = -torch.matmul(t['Suhat'], torch.matmul(dvcav, t['Suhat']))
-        dtheta1 = beta * dvcavinv
-        dtheta2 = beta * bmv(t['Suhat'], dmcav)
-        dKi = torch.matmul(dA.t(), t['muhat']) \
-            + 2.0 * torch.matmul(torch.matmul(Ki, t['Splusmmhat']).transpose(1, 2), dB).sum(0) \
-            - dB.sum(0) + dvcavinv.sum(0)
-        Minner = scale_post * t['Splusmm'].sum(0) + scale_cav * t['Splusmmhat'].sum(0) - 2.0 * dKi
-        dtheta1 = -0.5 * scale_post * t['Splusmm'] - 0.5 * scale_cav * beta * t['Splusmmhat'] + dtheta1
-        dtheta2 = scale_post * t['mu'] + scale_cav * beta * t['muhat'] + dtheta2
-        M_all = 0.5 * (self.Dout * Ki + torch.matmul(Ki, torch.matmul(Minner, Ki)))
+        dvcav = sandwich(Ki, dB)
+        dmcav = tl.matvec(dvcav, t['muhat'], c0=2.0, A1=Ki, x1=dA, t1=True)
+        dvcav = tl.lincomb([(1.0, dvcav)], outer=(beta, dmcav, t['theta_2']))
+        dvcavinv = sandwich(t['Suhat'], dvcav, alpha=-1.0)
+        dtheta1 = tl.lincomb([(beta, dvcavinv), (-0.5 * scale_post, t['Splusmm']),
+                              (-0.5 * scale_cav * beta, t['Splusmmhat'])])
+        dtheta2 = tl.matvec(t['Suhat'], dmcav, c0=beta, w0=t['mu'], cw0=scale_post, w1=t['muhat'],
+                            cw1=scale_cav * beta)
+        # dKi = dA^T muhat + 2 sum_d (Ki Splusmmhat_d)^T dB_d - sum_d dB_d + sum_d dvcavinv_d
+        Z = self._dKi_common(dA, dB, t['Splusmmhat'])
+        # Minner = scale_post sum Splusmm + scale_cav sum Splusmmhat - 2 dKi
+        T1 = tl.lincomb([(2.0, dB), (-2.0, dvcavinv), (scale_post, t['Splusmm']), (scale_cav, t['Splusmmhat'])],
+                        reduce=True)
+        Minner = tl.lincomb([(-2.0, Z), (1.0, T1)])
+        M_all = sandwich(Ki, Minner, alpha=0.5, C=Ki, beta=0.5 * Do)
         dsf, dls, dzu = self._kernel_hyper_tail(st, M_all)
-        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1(dtheta1), 'eta2': dtheta2}
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1([(1.0, dtheta1)]), 'eta2': dtheta2}
 
     # ---- layer-level API of the reference (numpy in / numpy out; small n) ------------------
     def forward_prop_thru_cav(self, mx, vx=None, mode=config.PROP_MM):
@@ -799,8 +822,10 @@ class VFE_SGP_Layer(Base_SGP_Layer):
         t = self._t
         if 'kl' in t:
             return t['kl']
-        tr = (t['Kuuinv'] * t['Splusmm']).sum()
-        return 0.5 * (self.Dout * t['logdet_Kuu'] - t['logdet_Su'].sum() - self.Dout * self.M + tr)
+        Ssum = tl.lincomb([(1.0, t['Splusmm'])], reduce=True)
+        # 0.5 (Dout log|Kuu| - sum log|Su| - Dout M + tr(Kuuinv Splusmm))
+        return tl.dots([(0.5 * self.Dout, t['logdet_Kuu'], None), (-0.5 * self._sign_Su, t['ld_Su'], None),
+                        (0.5, t['Kuuinv'], Ssum)], const=-0.5 * self.Dout * self.M)
 
     def compute_KL(self):
         return float(self._kl().item())
@@ -812,21 +837,26 @@ class VFE_SGP_Layer(Base_SGP_Layer):
         """vfe_models.py:518-541 (det) / 363-394 (mm) on the statistics."""
         t = self._t
         Ki = t['Kuuinv']
+        Do, M = self.Dout, self.M
         dA, dB = st['dA'], st['dB']
-        dSu = torch.matmul(Ki, torch.matmul(dB, Ki))
-        dmu = torch.matmul(dA, Ki)
+        dSu0 = sandwich(Ki, dB)
+        # dmu = dA Ki (+ 2 dSu mu) + mu Ki
         if stochastic:
-            dmu = dmu + 2.0 * bmv(dSu, t['mu'])
-        dmu = dmu + torch.matmul(t['mu'], Ki)
-        dSu = dSu + 0.5 * (Ki - t['Suinv'])
-        e1, e2, dKi_u = self._posterior_grad_u(dmu, dSu)
+            dmu = tl.matvec(Ki, dA, t0=True, A1=dSu0, x1=t['mu'], c1=2.0, w0=t['A'])
+        else:
+            dmu = tl.matvec(Ki, dA, t0=True, w0=t['A'])
+        dSu = tl.lincomb([(1.0, dSu0), (0.5, Ki), (-0.5, t['Suinv'])])
+        d1, e2, dKi_u = self._posterior_grad_u(dmu, dSu)
         S = t['Splusmm'] if stochastic else t['Su']
-        dKi = torch.matmul(dA.t(), t['mu']) \
-            + 2.0 * torch.matmul(torch.matmul(Ki, S).transpose(1, 2), dB).sum(0) - dB.sum(0) \
-            + dKi_u - 0.5 * self.Dout * t['Kuu'] + 0.5 * t['Splusmm'].sum(0)
-        Mm = -torch.matmul(Ki, torch.matmul(dKi, Ki))
+        Y = tl.gemm(Ki, S)
+        Z = tl.gemm(Y.reshape(Do * M, M), dB.reshape(Do * M, M), ta=True, alpha=2.0)
+        Z = tl.gemm(dA, t['mu'], ta=True, C=Z, beta=1.0)
+        T1 = tl.lincomb([(-1.0, dB), (0.5, t['Splusmm'])], reduce=True)
+        terms = [(1.0, Z), (1.0, T1), (-0.5 * Do, t['Kuu'])] + ([(1.0, dKi_u)] if dKi_u is not None else [])
+        dKi = tl.lincomb(terms)
+        Mm = sandwich(Ki, dKi, alpha=-1.0)
         dsf, dls, dzu = self._kernel_hyper_tail(st, Mm)
-        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': e1, 'eta2': e2}
+        return {'sf': dsf, 'ls': dls, 'zu': dzu, 'eta1_R': self._pack_eta1([(1.0, d1)]), 'eta2': e2}
 
     def backprop_grads_reg(self, m, v, dm, dv, kfu, x):
         """vfe_models.py:479-548."""

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import ops
+from . import tail as tl
 from .layers import to_dev, default_device
 
 _F = torch.float64
@@ -139,8 +140,8 @@ class Gauss_Layer(Lik_Layer):
         """lik_layers.py:104-133 + 154-181.  Returns (scale*dm, scale*dv, logZ_sum, dsn) with
         logZ_sum unscaled and dsn = scale*(sum(dv) 2 sn2/alpha + n D (1-alpha)), all on device."""
         dm, dv, o = ops.gauss_lik(m, v, y, self._sn, alpha, scale, 0)
-        sn2 = torch.exp(2.0 * self._sn)
-        dsn = scale * (o[1] * 2.0 * sn2 / alpha + m.shape[0] * self.D * (1.0 - alpha))
+        sn2 = float(np.exp(2.0 * np.ravel(self.sn)[0]))           # host copy of the same parameter
+        dsn = tl.dots([(scale * 2.0 * sn2 / alpha, o[1:2], None)], const=scale * m.shape[0] * self.D * (1.0 - alpha))
         return dm, dv, o[0], dsn.reshape(())
 
     def _log_Z_mc(self, m, v, y, alpha, scale):
@@ -165,7 +166,7 @@ class Gauss_Layer(Lik_Layer):
     def _log_lik_exp(self, m, v, y, scale):
         """lik_layers.py:183-199 + 217-226."""
         dm, dv, o = ops.gauss_lik(m, v, y, self._sn, 1.0, scale, 1)
-        return dm, dv, o[0], (scale * o[1]).reshape(())
+        return dm, dv, o[0], tl.dots([(scale, o[1:2], None)]).reshape(())
 
     # ---- reference API (numpy) ---------------------------------------------------------------
     def compute_log_Z(self, mout, vout, y, alpha=1.0, compute_dm2=False):

@@ -54,7 +54,8 @@ class TailGraph(object):
         return self.graph is not None
 
     def _load(self, ins):
-        torch._foreach_copy_([self.static_in[k] for k in self.keys], [ins[k] for k in self.keys])
+        from . import tail
+        tail.multicopy([self.static_in[k] for k in self.keys], [ins[k].contiguous() for k in self.keys])
 
     def run(self, fn, ins, device):
         """fn(ins: {name: tensor}) -> any Python object holding device tensors."""

@@ -150,6 +150,68 @@ int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, co
                double* dA, double* dB, double* dzu, double* dl, double* dsf2, double* dvsum,
                double* dmx, double* dvx, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- the replicated O(Dout M^3) tail (tail_pre / tail_post) -------------
+ *      Everything the reference computes between the parameters and the per-row work
+ *      (update_hypers / compute_kuu / update_posterior base_models.py:630-658,454-488, compute_cavity
+ *      aep_models.py:513-546, compute_phi 62-114, compute_KL vfe_models.py:309-325) and between
+ *      the reduced statistics and the parameter gradients (aep_models.py:252-297,462-511,548-586,
+ *      base_models.py:490-516, vfe_models.py:363-394,518-541, d_trace_MKzz_dhypers kernels.py:447-475)
+ *      is numpy einsum / linalg there.  Here a phase is a PROGRAM of batched fp64 primitives that the
+ *      host side assembles once per layer shape and the library executes in order on `stream`
+ *      (`gpb_tail_exec`; the matrix inverses are `gpb_spd_inverse`).  Matrices are row-major with
+ *      leading dimension ld[i]; sstride[i] is the batch stride of operand i in elements (0 = shared
+ *      by the whole batch); unused operands are NULL.
+ *
+ *      GPB_TOP_GEMM     dst[b] (m x n) = coef[0] op(src0[b]) (m x k) op(src1[b]) (k x n) + coef[1] src2[b]
+ *                       flags bit0 / bit1: src0 / src1 stored transposed.  FP64 tensor cores (DMMA).
+ *      GPB_TOP_LINCOMB  dst[b][i][j] = sum_{s<4} coef[s] src_s[b][i][j] (flags bit s: [j][i])
+ *                       + coef[4] src4[b][i] src5[b][j] + coef[5] (i == j);  flags bit 8: summed over b;
+ *                       flags bit 9: src2, src3 are a second outer pair (coef[2] src2[b][i] src3[b][j])
+ *      GPB_TOP_MATVEC   dst[b][i] = coef[0] (op(src0[b]) src1[b])_i + coef[1] (op(src2[b]) src3[b])_i
+ *                       + coef[2] src4[b][i] + coef[3] src5[b][i]   (m outputs, k inner; flags bit0/1: transposed)
+ *      GPB_TOP_DOTS     dst[0] = (flags bit0 ? dst[0] : 0) + coef[6] + sum_{t<3} coef[t] sum_{e<ld[2t]}
+ *                       src_{2t}[e] (src_{2t+1} ? src_{2t+1}[e] : 1)
+ *      GPB_TOP_UNPACK_R dst[b] (m x m) = upper-triangular R from src0[b][m(m+1)/2], diagonal exponentiated
+ *                       (base_models.py:645-653)
+ *      GPB_TOP_PACK_R   dst[b][m(m+1)/2] = coef[0] triu(src0[b]) with the diagonal times diag(src1[b])
+ *                       (base_models.py:505-514)
+ *      GPB_TOP_KHYPER   kernels.py:447-475 folded with aep_models.py:455-460,497-504: src = {Mm, Kuu, zu,
+ *                       ls, sf, stats = [dzu0[m*k] | dl[k] | dsf2 | dvsum]}; dst = coef[1] [dsf | dls[k] | dzu[m*k]];
+ *                       coef[0] = jitter; m = M, k = D <= 32
+ *      GPB_TOP_SUM      dst[0] = sum of src0[0 .. sstride[0]) (any length; src1 = scratch of >= 1024 doubles) */
+#define GPB_TOP_GEMM 1
+#define GPB_TOP_LINCOMB 2
+#define GPB_TOP_MATVEC 3
+#define GPB_TOP_DOTS 4
+#define GPB_TOP_UNPACK_R 5
+#define GPB_TOP_PACK_R 6
+#define GPB_TOP_KHYPER 7
+#define GPB_TOP_SUM 8
+typedef struct GpbTailOp {
+    int kind, flags;
+    int batch, m, n, k;
+    const double* src[6];
+    long sstride[6];
+    int ld[6];
+    double coef[8];
+    double* dst;
+    long dstride;
+    int ldd;
+} GpbTailOp;
+/* run `n_ops` tail primitives in order on `stream` (h_ops: HOST array; one kernel launch per op,
+ * two for GPB_TOP_SUM) */
+int gpb_tail_exec(const GpbTailOp* h_ops, int n_ops, void* stream);
+/* dst = scale * concat(src_0[0..count_0), src_1[0..count_1), ...): the flat energy + gradient vector that
+ * goes back to the optimiser with one copy (utils.py:68-90 flatten order is the caller's).
+ * h_srcs / h_counts: HOST arrays of n device pointers / element counts. */
+int gpb_tail_gather(int n, const double* const* h_srcs, const long* h_counts, double scale,
+                    double* dst, void* stream);
+
+/* dst_i[0..count_i) = src_i[0..count_i) for i < n in one launch (per 24 entries): refreshes the static
+ * input buffers of a captured tail phase.  h_*: HOST arrays. */
+int gpb_tail_copy(int n, const double* const* h_srcs, double* const* h_dsts, const long* h_counts,
+                  void* stream);
+
 /* ---- per-kernel device timing for bench.py's roofline (CUDA events on the launching stream).
  *      slots: 0 det_fwd, 1 det_bwd, 2 det_syrk, 3 mm_pairs(fwd), 4 mm_pairs(bwd), 5 mm_rows_bwd,
  *      6 mm_cols_bwd, 7 mm_psi1_fwd.  collect() synchronises the recorded events, returns the summed

@@ -185,3 +185,85 @@ def check_spd_inverse(M, batch):
         assert gu.rel_err(inv[b], ref) < 1e-5, (M, b, gu.rel_err(inv[b], ref))
         sref = np.linalg.slogdet(A[b])[1]
         assert abs(ld[b] - sref) < 1e-8 * max(1.0, abs(sref)), (M, b, ld[b], sref)
+
+
+def check_tail_primitives(seed=0):
+    """Every primitive of the tail program (include/geepee_b200.h GpbTailOp; geepee_b200/tail.py) against
+    numpy, with odd sizes, shared (2-D) operands, transposes, strided views and batch sums."""
+    from geepee_b200 import tail
+    rng = np.random.RandomState(seed)
+    r = rng.standard_normal
+    # --- GEMM: all four transpose combinations, batch broadcast, C accumulation, both tile shapes
+    for (b, m, n, k) in [(3, 37, 29, 41), (1, 5, 7, 3), (2, 64, 64, 64), (5, 70, 130, 33), (40, 96, 96, 20)]:
+        for ta in (False, True):
+            for tb in (False, True):
+                A = r((b,) + ((k, m) if ta else (m, k)))
+                B = r(((n, k) if tb else (k, n)))                  # shared operand
+                C = r((b, m, n))
+                ref = 0.7 * np.einsum('bmk,kn->bmn', np.swapaxes(A, 1, 2) if ta else A, B.T if tb else B) - 1.3 * C
+                got = tail.gemm(T(A), T(B), ta=ta, tb=tb, alpha=0.7, C=T(C), beta=-1.3)
+                assert gu.rel_err(N(got), ref) < 1e-13, (b, m, n, k, ta, tb)
+    A, B = r((4, 20, 9)), r((4, 20, 11))
+    got = tail.gemm(T(A).reshape(80, 9), T(B).reshape(80, 11), ta=True, alpha=2.0)     # sum_d A_d^T B_d as ONE product
+    assert gu.rel_err(N(got), 2.0 * np.einsum('dka,dkb->ab', A, B)) < 1e-13
+    # --- LINCOMB
+    S0, S1, S2 = r((3, 6, 6)), r((6, 6)), r((3, 6, 6))
+    u, v, u2, v2 = r((3, 6)), r((6,)), r((3, 6)), r((3, 6))
+    got = tail.lincomb([(0.5, T(S0)), (-2.0, T(S1), True), (1.5, T(S2), True)], outer=(3.0, T(u), T(v)), eye=0.25)
+    ref = 0.5 * S0 - 2.0 * S1.T[None] + 1.5 * np.swapaxes(S2, 1, 2) + 3.0 * u[:, :, None] * v[None, None, :] \
+        + 0.25 * np.eye(6)[None]
+    assert gu.rel_err(N(got), ref) < 1e-14
+    got = tail.lincomb([(1.0, T(S0))], outer=(1.0, T(u), T(u)), outer2=(-2.0, T(u2), T(v2)))
+    assert gu.rel_err(N(got), S0 + u[:, :, None] * u[:, None, :] - 2.0 * u2[:, :, None] * v2[:, None, :]) < 1e-14
+    got = tail.lincomb([(1.0, T(S0)), (-1.0, T(S2))], reduce=True)
+    assert gu.rel_err(N(got), (S0 - S2).sum(0)) < 1e-14
+    got = tail.veccomb([(2.0, T(u)), (-1.0, T(u2))])
+    assert got.shape == (3, 6) and gu.rel_err(N(got), 2 * u - u2) < 1e-15
+    # --- MATVEC
+    A0, A1, x0, x1, w0 = r((3, 7, 5)), r((5, 7)), r((3, 5)), r((3, 5)), r((3, 7))
+    got = tail.matvec(T(A0), T(x0), c0=0.3, A1=T(A1), x1=T(x1), t1=True, c1=-1.1, w0=T(w0), cw0=2.0)
+    ref = 0.3 * np.einsum('bik,bk->bi', A0, x0) - 1.1 * np.einsum('ki,bk->bi', A1, x1) + 2.0 * w0
+    assert gu.rel_err(N(got), ref) < 1e-14
+    # --- DOTS / total
+    a, b2, c = r(1000), r(1000), r((3, 50))
+    got = tail.dots([(2.0, T(a), T(b2)), (-1.0, T(c), None), (0.5, T(a), None), (3.0, T(b2), T(b2))], const=0.125)
+    ref = 2.0 * a.dot(b2) - c.sum() + 0.5 * a.sum() + 3.0 * b2.dot(b2) + 0.125
+    assert abs(got.item() - ref) < 1e-12 * abs(ref)
+    big = r(300001)
+    assert abs(tail.total(T(big)).item() - big.sum()) < 1e-10
+    # --- R packing
+    M, Do = 9, 3
+    P = M * (M + 1) // 2
+    e = 0.3 * r((Do, P))
+    R = N(tail.unpack_r(T(e), M))
+    iu = np.triu_indices(M)
+    Rr = np.zeros((Do, M, M))
+    for d in range(Do):
+        Rr[d][iu] = e[d]
+        Rr[d][np.diag_indices(M)] = np.exp(Rr[d][np.diag_indices(M)])
+    assert gu.rel_err(R, Rr) < 1e-15
+    dR = r((Do, M, M))
+    got = N(tail.pack_r(T(dR), T(Rr), 0.5))
+    ref = np.zeros((Do, P))
+    for d in range(Do):
+        g = dR[d].copy()
+        g[np.diag_indices(M)] *= Rr[d][np.diag_indices(M)]
+        ref[d] = 0.5 * g[iu]
+    assert gu.rel_err(got, ref) < 1e-15
+    # --- KHYPER against the reference formulas (golden kernels.npz: d_trace_MKzz_dhypers)
+    f = np.load(gu.GOLDEN + '/kernels.npz')
+    z, ls, sf, Mm, Kzz = f['z'], f['ls'], f['sf'], f['Mm'], f['Kzz']
+    Mz, D = z.shape
+    st = np.concatenate([r(Mz * D), r(D), r(1), r(1)])
+    out = N(tail.khyper(T(Mm), T(Kzz + 1e-5 * np.eye(Mz)), T(z), T(ls), T(sf), T(st), 1e-5, 0.5))
+    dzu0, dl, dsf2, dvsum = st[:Mz * D].reshape(Mz, D), st[Mz * D:Mz * D + D], st[-2], st[-1]
+    ref_sf = 2 * np.exp(2 * sf[0]) * (dsf2 + dvsum) + 2 * f['tr_sf']
+    ref_ls = dl * np.exp(ls) + 2 * f['tr_ls']
+    ref_z = dzu0 + f['tr_z']
+    assert abs(out[0] - 0.5 * np.ravel(ref_sf)[0]) < 1e-12 * abs(np.ravel(ref_sf)[0])
+    assert gu.rel_err(out[1:1 + D], 0.5 * ref_ls) < 1e-12
+    assert gu.rel_err(out[1 + D:].reshape(Mz, D), 0.5 * ref_z) < 1e-12
+    # --- GATHER
+    parts = [r(5), r((3, 4)), r(1)]
+    got = N(tail.gather([T(p) for p in parts], 0.25))
+    assert gu.rel_err(got, 0.25 * np.concatenate([p.reshape(-1) for p in parts])) < 1e-15

@@ -64,6 +64,12 @@ def test_kmat_psi_lik():
     oc.check_kmat_psi_lik()
 
 
+def test_tail_primitives():
+    """GpbTailOp program ops (batched DMMA GEMM, fused linear combinations, R packing, kernel-hyper
+    chain rule ...) against numpy."""
+    oc.check_tail_primitives()
+
+
 @pytest.mark.parametrize('n,Do,Q', oc.EMIS_SHAPES)
 def test_gauss_emis(n, Do, Q):
     oc.check_gauss_emis(n, Do, Q)
