@@ -260,6 +260,21 @@ def time_cpu(w, budget_s, steps=1, warmup=0, want_floor=False):
         last.clear()
         last.update(keep)
         last['floor'] = floor
+        if w['model'] == 'SDGPR':
+            # A second, WELL-CONDITIONED parameter point of the same shape: the init recipe puts the pseudo-inputs
+            # of every hidden layer on one line with unit lengthscale (base_models.py:534-536), where the
+            # reference's own gradients move by ~1e-3 under the 1e-15 perturbation above, so 1e-6 parity is
+            # undecidable there.  Spread over [-2,2]^Q with lengthscale 0.2 it is decidable
+            # (tests/golden/gen_golden_bench.py uses the same point for bench_cfg3_sdgpr_wc_n512).
+            p2 = {k: np.array(v, dtype=np.float64) for k, v in keep['params'].items()}
+            rng = np.random.RandomState(77)
+            for i in range(1, len(w['hidden']) + 1):
+                p2['zu_%d' % i] = rng.uniform(-2.0, 2.0, p2['zu_%d' % i].shape)
+                p2['ls_%d' % i] = np.log(0.2) * np.ones_like(p2['ls_%d' % i])
+            m = build(w, keep['X'], keep['Y'])
+            e3, g3 = m.objective_function(copy.deepcopy(p2), keep['n'], alpha=w['alpha'])
+            last['wc'] = dict(n=keep['n'], X=keep['X'], Y=keep['Y'], params=p2, energy=float(np.ravel(e3)[0]),
+                              grads=g3)
     b = (t2 - t1) / (n2 - n1)
     if b <= 0:
         b = t2 / n2
@@ -647,7 +662,18 @@ def run_gpu(args, w):
             except Exception as ex:  # noqa: BLE001
                 line['secondary'] = {'error': repr(ex)}
         try:
-            line['parity'] = gpu_parity(w, r['last'], args.prec, dev, 1e-6 if pr == ops.F64 else 1e-3)
+            tol = 1e-6 if pr == ops.F64 else 1e-3
+            par = gpu_parity(w, r['last'], args.prec, dev, tol)
+            if 'wc' in r['last']:
+                # headline parity block: the well-conditioned point, plain tolerance (no floor);
+                # the init-recipe point of the timed workload is kept beside it with the reference's floor
+                wc = gpu_parity(w, r['last']['wc'], args.prec, dev, tol)
+                wc['params'] = ('same rows and shapes as the timed workload; hidden-layer pseudo-inputs ~ U[-2,2]^Q, '
+                                'lengthscale 0.2 (well conditioned); plain tolerance, no floor')
+                par['params'] = 'init recipe of the timed workload (ill conditioned: see ill_conditioned_keys)'
+                wc['at_init_params'] = par
+                par = wc
+            line['parity'] = par
         except Exception as ex:  # noqa: BLE001  (reported, never hidden)
             line['parity'] = {'ok': False, 'error': repr(ex)}
     print(json.dumps(line))

@@ -40,6 +40,8 @@ _SIGS = {
     'gpb_gauss_emis_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 3),
     'gpb_gauss_emis': (ctypes.c_int, [c_dp] * 5 + [ctypes.c_double, ctypes.c_double] + [ctypes.c_int] * 3 +
                        [c_dp, c_dp, c_dp, c_dp, ctypes.c_size_t, c_dp]),
+    'gpb_gauss_emis_finish': (ctypes.c_int, [c_dp, c_dp, ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_int,
+                                             ctypes.c_int, c_dp, c_dp]),
     'gpb_det_bwd_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
     'gpb_det_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 9 + [ctypes.c_int] * 4 + [c_dp] * 5 +
                     [ctypes.c_size_t, c_dp]),
@@ -53,8 +55,22 @@ _SIGS = {
     'gpb_mm_bwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 12 + [ctypes.c_int] * 4 + [c_dp] * 9 +
                    [ctypes.c_size_t, c_dp]),
     'gpb_tail_exec': (ctypes.c_int, [c_dp, ctypes.c_int, c_dp]),
+    'gpb_tail_khyper_out_len': (ctypes.c_long, [ctypes.c_int, ctypes.c_int]),
     'gpb_tail_gather': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp]),
     'gpb_tail_copy': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, c_dp, c_dp]),
+    'gpb_latent_ws_bytes': (ctypes.c_size_t, [ctypes.c_long]),
+    'gpb_lvm_x_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_long, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp]),
+    'gpb_lvm_x_bwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_long, ctypes.c_int,
+                                     ctypes.c_long, ctypes.c_int] + [ctypes.c_double] * 5 + [c_dp] * 6 +
+                      [ctypes.c_size_t, c_dp]),
+    'gpb_ssm_cavity': (ctypes.c_int, [c_dp, c_dp, ctypes.c_long, ctypes.c_int] + [ctypes.c_double] * 3 + [c_dp] * 3),
+    'gpb_ssm_transition': (ctypes.c_int, [c_dp] * 5 + [ctypes.c_long, ctypes.c_double, ctypes.c_double] + [c_dp] * 4 +
+                           [ctypes.c_size_t, c_dp]),
+    'gpb_ssm_sources': (ctypes.c_int, [c_dp, c_dp, ctypes.c_long, ctypes.c_int] + [ctypes.c_double] * 3 +
+                        [c_dp, c_dp, ctypes.c_long, ctypes.c_long, ctypes.c_int] * 3 + [c_dp] * 3),
+    'gpb_ssm_xfinal': (ctypes.c_int, [c_dp, c_dp, ctypes.c_long, ctypes.c_int] + [ctypes.c_double] * 3 + [c_dp] * 6 +
+                       [ctypes.c_size_t, c_dp]),
     'gpb_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'gpb_profile_collect': (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]),
     'gpb_fma_peak': (ctypes.c_int, [ctypes.c_int, ctypes.c_long, c_dp, ctypes.POINTER(ctypes.c_double), c_dp]),

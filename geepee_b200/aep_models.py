@@ -13,7 +13,7 @@ Every objective has the same three-phase shape:
 import numpy as np
 import torch
 
-from . import dist
+from . import dist, ops
 from . import tail as tl
 from .sched import TailStreams
 from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
@@ -345,6 +345,7 @@ class SGPLVM(Base_SGPLVM):
         return m.cpu().numpy(), v.cpu().numpy()
 
     def _cavity_x(self, alpha, sel):
+        """numpy-API twin of ops.lvm_x_fwd (the objective uses the kernel)."""
         if self.nat_param:
             c1 = self.prior_x1 + (1.0 - alpha) * self._f1[sel]
             c2 = self.prior_x2 + (1.0 - alpha) * self._f2[sel]
@@ -362,7 +363,7 @@ class SGPLVM(Base_SGPLVM):
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
-        sel, n = self._rows(mb_size)
+        sel, lo, cnt, n = self._rows(mb_size)
         eps = _mc_eps(n, Q, dev) if prop_mode == PROP_MC else None
         scale_logZ = -N * 1.0 / n / alpha
         s_cav = -N * 1.0 / n / alpha
@@ -370,12 +371,12 @@ class SGPLVM(Base_SGPLVM):
         L._fuse_cavity_alpha = alpha
         self.update_hypers(params)
         L.compute_cavity(alpha)
-        add = {'gx1': _zeros(dev, N, Q), 'gx2': _zeros(dev, N, Q)}
-        if sel.shape[0] > 0:
-            yb = self._y.index_select(0, sel)
-            mcav, vcav = self._cavity_x(alpha, sel)
-            p1, p2 = self._post1[sel], self._post2[sel]
-            mpost, vpost = p1 / p2, 1.0 / p2
+        add = {}
+        if cnt > 0:
+            yb = self._y[lo:lo + cnt] if sel is None else self._y.index_select(0, sel)
+            x1d, x2d = self._x1d, self._x2d
+            # cavity of x for this rank's rows (aep_models.py:840-861), one kernel
+            mcav, vcav = ops.lvm_x_fwd(0, self.nat_param, x1d, x2d, sel, lo, cnt, self.prior_x1, self.prior_x2, alpha)
             if eps is not None:     # aep_models.py:745-761
                 m, v, ctx = L._fwd_mc(mcav, vcav, eps, cav=True)
                 dm, dv, logZ, dsn = self.lik_layer._log_Z_mc(m, v, yb, alpha, scale_logZ)
@@ -385,32 +386,16 @@ class SGPLVM(Base_SGPLVM):
                 dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
                 st = L._bwd_mm(ctx, dm, dv)
             _add_stats(add, 's_', st)
-            # latent-variable terms, aep_models.py:785-801, 817-838; base_models.py:913-929
-            phi_cav, dmc, dvc = self._phi_x(mcav, vcav)
-            phi_post, dmp, dvp = self._phi_x(mpost, vpost)
-            dmc = s_cav * dmc + st['dmx']
-            dvc = s_cav * dvc + st['dvx']
-            dmp, dvp = s_post * dmp, s_post * dvp
-            f2 = self._f2[sel]
-            t1, t2 = mcav / vcav, 1.0 / vcav
-            d1 = (1.0 - alpha) * dmc / t2
-            d2 = (1.0 - alpha) * (-dmc * t1 / t2**2 - dvc / t2**2)
-            if self.nat_param:
-                d2 = d2 * 2 * f2
-                d1 = d1 + dmp / p2
-                d2 = d2 + (-dmp * p1 / p2**2 - dvp / p2**2) * 2 * f2
-            else:
-                mp_, vp_ = self._f1[sel], f2
-                dmq = d1 / vp_
-                dvq = -d1 * mp_ / vp_**2 - d2 / vp_**2
-                d1 = dmq + dmp
-                d2 = (dvq + dvp) * 2 * f2
-            add['gx1'].index_copy_(0, sel, d1)
-            add['gx2'].index_copy_(0, sel, d2)
+            # latent-variable terms (aep_models.py:785-801, 817-838, 863-867; base_models.py:913-929): phi_x of
+            # cavity and posterior, their chain rules and the layer's input gradients -> x1, x2, one kernel
+            add['gx1'], add['gx2'], sums = ops.lvm_x_bwd(0, self.nat_param, x1d, x2d, sel, lo, cnt, self.prior_x1,
+                                                         self.prior_x2, alpha, s_cav, s_post,
+                                                         st['dmx'].contiguous(), st['dvx'].contiguous())
             add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
-            add['phi_cav'], add['phi_post'] = phi_cav.reshape(1), phi_post.reshape(1)
+            add['phi_cav'], add['phi_post'] = sums[0:1], sums[1:2]
         else:
             _add_stats(add, 's_', _zero_stats(L))
+            add['gx1'], add['gx2'] = _zeros(dev, N, Q), _zeros(dev, N, Q)
             for k in ('logZ', 'dsn', 'phi_cav', 'phi_post'):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
@@ -421,8 +406,9 @@ class SGPLVM(Base_SGPLVM):
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']
         pm, pv = self.prior_mean, self.prior_var
         phi_prior = 0.5 * (pm**2 / pv + np.log(pv)) * N * Q
-        x_contrib = phi_prior + s_cav * add['phi_cav'] + s_post * add['phi_post']
-        energy = scale_logZ * add['logZ'] + x_contrib + L._phi(alpha)
+        # energy = scale_logZ logZ + [phi_prior + s_cav phi_cav + s_post phi_post] + phi
+        energy = tl.dots([(scale_logZ, add['logZ'], None), (s_cav, add['phi_cav'], None),
+                          (s_post, add['phi_post'], None), (1.0, L._phi(alpha), None)], const=phi_prior)
         return self._finish(energy, grads, divide_by_N=False)   # aep_models.py:815: no /N
 
 
@@ -438,6 +424,89 @@ class SGPSSM(Base_SGPSSM):
         if gp_emi:
             self.emi_layer = SGP_Layer(self.N, self.Din + self.Dcon_emi, self.Dout, self.M, True,
                                        prec, self.device)
+
+    def _objective_mm(self, params, alpha, start, end, s_dyn, s_emi):
+        """Moment-matched objective with the latent-state algebra in the library's elementwise kernels
+        (ops.ssm_*): cavity of every state, tilted transition, the three gradient
+        sources chained to the cavity naturals, posterior / cavity log-partitions over all T rows."""
+        N, Q, dev = self.N, self.Din, self.device
+        dyn, emi = self.dyn_layer, self.emi_layer
+        n_emi = end - start
+        n_dyn = n_emi - 1
+        xf1, xf2 = self._x1d, self._x2d
+        pr1, pr2 = self.x_prior_1, self.x_prior_2
+        cav_m, cav_v = ops.ssm_cavity(xf1, xf2, pr1, pr2, alpha)
+        add = {}
+        prev = nxt = up = None
+        # ---- transition factors t -> t+1 (aep_models.py:1092-1098, 1317-1348) ---------------
+        dlo, dhi = dist.shard(n_dyn)
+        t0, t1 = start + dlo, start + dhi
+        if t1 > t0:
+            mtm1, vtm1 = self._with_control(cav_m[t0:t1], cav_v[t0:t1], t0, t1, self.Dcon_dyn)
+            mp, vp, ctx = dyn._fwd_mm(mtm1, vtm1, cav=True)
+            dml, dvt, sums = ops.ssm_transition(cav_m[t0 + 1:t1 + 1], cav_v[t0 + 1:t1 + 1], mp, vp, self._sn,
+                                                alpha, s_dyn)
+            st = dyn._bwd_mm(ctx, dml, dvt)
+            sn2 = float(np.exp(2.0 * np.ravel(self.sn)[0]))
+            add['logZ_dyn'] = tl.dots([(s_dyn, sums[0:1], None)])
+            add['dsn'] = tl.dots([(2.0 * sn2 / alpha, sums[1:2], None)], const=s_dyn * (t1 - t0) * Q * (1 - alpha))
+            _add_stats(add, 'd_', st)
+            prev = (dml, dvt, t0 + 1)                         # targets of the transitions (dml = -dmt)
+            nxt = (st['dmx'], st['dvx'], t0)                  # inputs of the transitions
+        else:
+            _add_stats(add, 'd_', _zero_stats(dyn))
+            add['logZ_dyn'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
+        # ---- emission factors (aep_models.py:1100-1113, 1149-1151) --------------------------
+        elo, ehi = dist.shard(n_emi)
+        e0, e1 = start + elo, start + ehi
+        if e1 > e0:
+            mup, vup = self._with_control(cav_m[e0:e1], cav_v[e0:e1], e0, e1, self.Dcon_emi)
+            yb = self._y[e0:e1]
+            if self.gp_emi:
+                mo, vo, ctx = emi._fwd_mm(mup, vup, cav=True)
+                dme, dve, lZe, dsn_e = self.lik_layer._log_Z(mo, vo, yb, alpha, s_emi)
+                ste = emi._bwd_mm(ctx, dme, dve)
+                _add_stats(add, 'e_', ste)
+                add['logZ_emi'] = tl.dots([(s_emi, lZe.reshape(1), None)])
+                add['dsn_emission'] = dsn_e.reshape(1)
+                up = (ste['dmx'], ste['dvx'], e0)
+            else:
+                lZe, dmx, dvx, ge = emi._tilted(mup, vup, alpha, s_emi, yb)
+                add['logZ_emi'] = lZe.reshape(1)
+                add['dC'], add['dR'] = ge['C'], ge['R']
+                up = (dmx, dvx, e0)
+        else:
+            add['logZ_emi'] = _zeros(dev, 1)
+            if self.gp_emi:
+                _add_stats(add, 'e_', _zero_stats(emi))
+                add['dsn_emission'] = _zeros(dev, 1)
+            else:
+                add['dC'] = _zeros(dev, self.Dout, Q + self.Dcon_emi)
+                add['dR'] = _zeros(dev, self.Dout)
+        # the three logZ sources of every latent state -> cavity naturals (aep_models.py:1234-1285)
+        add['l1'], add['l2'] = ops.ssm_sources(xf1, xf2, pr1, pr2, alpha, prev, nxt, up)
+        add = dist.allreduce_dict(add)
+
+        # ---- replicated tail ----------------------------------------------------------------
+        grads = {'sn': add['dsn'].reshape(tuple(np.shape(self.sn)))}
+        for k, val in dyn._tail_mm(_get_stats(add, 'd_'), alpha).items():
+            grads[k + '_dynamic'] = val
+        if self.gp_emi:
+            for k, val in emi._tail_mm(_get_stats(add, 'e_'), alpha).items():
+                grads[k + '_emission'] = val
+            grads['sn_emission'] = add['dsn_emission'].reshape(())
+        else:
+            grads['C_emission'], grads['R_emission'] = add['dC'], add['dR']
+        # x gradients and log-partitions over ALL T rows (aep_models.py:1208-1232, 1287-1315, 1389-1437)
+        grads['x_factor_1'], grads['x_factor_2'], sums = ops.ssm_xfinal(xf1, xf2, pr1, pr2, alpha,
+                                                                          add['l1'], add['l2'])
+        m0, v0 = pr1 / pr2, 1.0 / pr2
+        phi_prior = 0.5 * Q * (m0**2 / v0 + np.log(v0))
+        terms = [(1.0, add['logZ_dyn'], None), (1.0, add['logZ_emi'], None), (1.0, sums[0:1], None),
+                 (1.0, sums[1:2], None), (1.0, dyn._phi(alpha), None)]
+        if self.gp_emi:
+            terms.append((1.0, emi._phi(alpha), None))
+        return self._finish(tl.dots(terms, const=phi_prior), grads)
 
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
@@ -460,6 +529,9 @@ class SGPSSM(Base_SGPSSM):
         dyn.compute_cavity(alpha)
         if self.gp_emi:
             emi.compute_cavity(alpha)
+        if not mc:
+            return self._objective_mm(params, alpha, start, end, s_dyn, s_emi)
+        # ---- Monte-Carlo propagation: elementwise terms stay on torch (3-D branches) -----------
         # cavity of every latent state (aep_models.py:1376-1387); replicated elementwise work
         f1, f2, p1, p2 = self._f1, self._f2, self._post1, self._post2
         cav1 = p1 - alpha * f1

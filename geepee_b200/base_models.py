@@ -399,23 +399,44 @@ class Base_SGPLVM(Base_Model):
         self.lik_layer.update_hypers(params, _dev=dev)
         self.factor_x1 = params['x1']
         self.factor_x2 = np.exp(2 * params['x2'])
-        self._f1 = dev['x1'].reshape(self.N, self.Din)
-        self._f2 = torch.exp(2.0 * dev['x2'].reshape(self.N, self.Din))
-        if self.nat_param:
-            self._post1 = self.prior_x1 + self._f1
-            self._post2 = self.prior_x2 + self._f2
-        else:
-            self._post1 = self._f1 / self._f2
-            self._post2 = 1.0 / self._f2
+        # raw device parameters: the objective's latent-variable kernels (ops.lvm_x_fwd / lvm_x_bwd) read
+        # them directly; the derived arrays below exist for the prediction / inspection API only
+        self._x1d = dev['x1'].reshape(self.N, self.Din)
+        self._x2d = dev['x2'].reshape(self.N, self.Din)
+        self._lazy = {}
+
+    @property
+    def _f1(self):
+        return self._x1d
+
+    @property
+    def _f2(self):
+        if 'f2' not in self._lazy:
+            self._lazy['f2'] = torch.exp(2.0 * self._x2d)
+        return self._lazy['f2']
+
+    @property
+    def _post1(self):
+        if 'p1' not in self._lazy:
+            self._lazy['p1'] = (self.prior_x1 + self._f1) if self.nat_param else self._f1 / self._f2
+        return self._lazy['p1']
+
+    @property
+    def _post2(self):
+        if 'p2' not in self._lazy:
+            self._lazy['p2'] = (self.prior_x2 + self._f2) if self.nat_param else 1.0 / self._f2
+        return self._lazy['p2']
 
     def _rows(self, mb_size):
-        """-> (device index tensor of this rank's minibatch rows or None, batch_size, (lo, hi))"""
+        """This rank's rows of the minibatch -> (sel, lo, cnt, n): `sel` = device int64 indices of a drawn
+        minibatch (cnt of them), or None for the contiguous rows lo .. lo+cnt-1 of the full batch; n = size of
+        the whole minibatch."""
         idxs = self._minibatch_rows(mb_size, exact=True)
         n = self.N if idxs is None else idxs.shape[0]
         lo, hi = dist.shard(n)
         if idxs is None:
-            return torch.arange(lo, hi, device=self.device), n
-        return torch.as_tensor(idxs[lo:hi], device=self.device), n
+            return None, lo, hi - lo, n
+        return torch.as_tensor(idxs[lo:hi], device=self.device), 0, hi - lo, n
 
 
 class Base_SGPSSM(Base_Model):
@@ -580,19 +601,45 @@ class Base_SGPSSM(Base_Model):
         self._sn = dp['sn'].reshape(-1)[:1].contiguous()
         self.x_factor_1 = params['x_factor_1']
         self.x_factor_2 = np.exp(2 * params['x_factor_2'])
-        self._f1 = dp['x_factor_1'].reshape(self.N, self.Din)
-        self._f2 = torch.exp(2.0 * dp['x_factor_2'].reshape(self.N, self.Din))
-        if self.nat_param:
-            w = torch.full((self.N, 1), 3.0, dtype=_F, device=dev)
-            w[0] = 2.0
-            w[-1] = 2.0
-            self._post1 = w * self._f1
-            self._post2 = w * self._f2
-            self._post1[0] += self.x_prior_1
-            self._post2[0] += self.x_prior_2
-        else:
-            self._post1 = self._f1 / self._f2
-            self._post2 = 1.0 / self._f2
+        # raw device parameters: the moment-matched AEP objective's latent-state kernels (ops.ssm_*) read
+        # them directly; the derived arrays below are formed on first use (Monte-Carlo / VFE / prediction paths)
+        self._x1d = dp['x_factor_1'].reshape(self.N, self.Din)
+        self._x2d = dp['x_factor_2'].reshape(self.N, self.Din)
+        self._lazy = {}
+
+    @property
+    def _f1(self):
+        return self._x1d
+
+    @property
+    def _f2(self):
+        if 'f2' not in self._lazy:
+            self._lazy['f2'] = torch.exp(2.0 * self._x2d)
+        return self._lazy['f2']
+
+    def _posts(self):
+        if 'p1' not in self._lazy:
+            if self.nat_param:      # base_models.py:1719-1725: factors tied 3x (2x at the ends) + prior at t = 0
+                w = torch.full((self.N, 1), 3.0, dtype=_F, device=self.device)
+                w[0] = 2.0
+                w[-1] = 2.0
+                p1 = w * self._f1
+                p2 = w * self._f2
+                p1[0] += self.x_prior_1
+                p2[0] += self.x_prior_2
+            else:
+                p1 = self._f1 / self._f2
+                p2 = 1.0 / self._f2
+            self._lazy['p1'], self._lazy['p2'] = p1, p2
+        return self._lazy['p1'], self._lazy['p2']
+
+    @property
+    def _post1(self):
+        return self._posts()[0]
+
+    @property
+    def _post2(self):
+        return self._posts()[1]
 
     def _window(self, mb_size):
         """aep_models.py:1045-1057: whole series or one random contiguous window."""

@@ -30,9 +30,8 @@ int emis_launch(const double* mx, const double* vx, const double* y, const doubl
     auto kern = gpb::gauss_emis_kernel<DO, QT>;
     GPB_LAUNCH(kern, dim3(grid), dim3(128), 0, stream, mx, vx, y, C, R, alpha, scale, n, Q, Do, dmx, dvx, part);
     // fold the per-block records, then compact the padded record to [2 + Do + Do*Q]
-    auto red = gpb::reduce_partials_kernel;
     double* full = part + (size_t)grid * NV;
-    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)part, grid, (long)NV, (long)NV, full, 0);
+    launch_reduce_partials((const double*)part, grid, (long)NV, (long)NV, full, 0, stream);
     auto cmp = gpb::gauss_emis_compact_kernel;
     GPB_LAUNCH(cmp, dim3(1), dim3(128), 0, stream, (const double*)full, DO, QT, Do, Q, out);
     return GPB_CHECK_LAUNCH();
@@ -81,8 +80,7 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
     auto kern = gpb::gauss_lik_kernel;
     GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, m, v, y, sn, alpha, scale, total, mode, dm, dv,
                (double*)ws);
-    auto red = gpb::reduce_partials_kernel;
-    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)ws, grid, 2L, 2L, out2, 0);
+    launch_reduce_partials((const double*)ws, grid, 2L, 2L, out2, 0, stream);
     return GPB_CHECK_LAUNCH();
 }
 
@@ -108,8 +106,7 @@ int gpb_probit_lik(const double* m, const double* v, const double* y, const doub
     auto kern = gpb::probit_lik_kernel;
     GPB_LAUNCH(kern, dim3(grid), dim3(256), 0, stream, m, v, y, gh_x, gh_w, ngh, alpha, scale, total, mode,
                dm, dv, (double*)ws);
-    auto red = gpb::reduce_partials_kernel;
-    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, (const double*)ws, grid, 2L, 2L, out2, 0);
+    launch_reduce_partials((const double*)ws, grid, 2L, 2L, out2, 0, stream);
     return GPB_CHECK_LAUNCH();
 }
 
@@ -136,6 +133,14 @@ int gpb_gauss_emis(const double* mx, const double* vx, const double* y, const do
     GPB_EMIS(8, 2); GPB_EMIS(8, 4); GPB_EMIS(8, 8);
 #undef GPB_EMIS
     return fail(GPB_ERR_ARG, "gauss_emis: unreachable");
+}
+
+int gpb_gauss_emis_finish(const double* raw, const double* R, double alpha, double scale, long Nb, int Do,
+                          int Q, double* fin, void* stream) {
+    if (!raw || !R || !fin || Do < 1 || Q < 1) return fail(GPB_ERR_ARG, "gauss_emis_finish: bad argument");
+    auto kern = gpb::gauss_emis_finish_kernel;
+    GPB_LAUNCH(kern, dim3(1), dim3(64), 0, stream, raw, R, alpha, scale, (double)Nb, Do, Q, fin);
+    return GPB_CHECK_LAUNCH();
 }
 
 int gpb_profile_enable(int on) {

@@ -435,7 +435,6 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
     a.n = n; a.Qa = Q; a.Do = Do; a.PP = p.PP; a.rows_per_split = p.rows_per_split;
     a.rowacc = w.rowacc; a.pairpart = w.pairpart;
     a.full_coef = p.npass > 1 ? 1 : 0;
-    auto red = gpb::reduce_partials_kernel;
     const long recstride = (long)(p.DOC + 1 + p.Qt) * p.PP;
     bool wide_done = false;
     if constexpr (sizeof(T) == 8) {
@@ -443,8 +442,7 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
             rc = mm_bwd_wide_mma_dispatch(p, a, stream);
             if (rc) return rc;
             const long wlen = (long)(Do + 1 + p.Qt) * p.PP;
-            GPB_LAUNCH(red, dim3(elementwise_grid(wlen)), dim3(256), 0, stream, w.pairpart, p.w_nsplit, wlen,
-                       wlen, w.pairsum, 0);
+            launch_reduce_partials(w.pairpart, p.w_nsplit, wlen, wlen, w.pairsum, 0, stream);
             wide_done = true;
         }
     }
@@ -455,12 +453,9 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
         if (rc) return rc;
         // fold the row splits: dBp rows of this d-chunk, and (first pass) S0 | S1
         int nd = (Do - a.d0) < p.DOC ? (Do - a.d0) : p.DOC;
-        GPB_LAUNCH(red, dim3(elementwise_grid((long)nd * p.PP)), dim3(256), 0, stream, w.pairpart,
-                   p.nsplit, recstride, (long)nd * p.PP, w.pairsum + (long)a.d0 * p.PP, 0);
+        launch_reduce_partials(w.pairpart, p.nsplit, recstride, (long)nd * p.PP, w.pairsum + (long)a.d0 * p.PP, 0, stream);
         if (pass == 0)
-            GPB_LAUNCH(red, dim3(elementwise_grid((long)(1 + p.Qt) * p.PP)), dim3(256), 0, stream,
-                       w.pairpart + (long)p.DOC * p.PP, p.nsplit, recstride, (long)(1 + p.Qt) * p.PP,
-                       w.pairsum + (long)Do * p.PP, 0);
+            launch_reduce_partials(w.pairpart + (long)p.DOC * p.PP, p.nsplit, recstride, (long)(1 + p.Qt) * p.PP, w.pairsum + (long)Do * p.PP, 0, stream);
     }
     rc = GPB_CHECK_LAUNCH();
     if (rc) return rc;
@@ -468,14 +463,12 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
     rc = mm_rows_bwd_dispatch(p, mx, vx, z, ls, sf, A, dm, dv, mout, vacc, w.rowacc, psi1, n, M, Q, Do, dmx,
                               dvx, w.rowpart, stream);
     if (rc) return rc;
-    GPB_LAUNCH(red, dim3(1), dim3(256), 0, stream, w.rowpart, p.rows_grid, (long)(2 + Q),
-               (long)(2 + Q), w.rowsum, 0);
+    launch_reduce_partials(w.rowpart, p.rows_grid, (long)(2 + Q), (long)(2 + Q), w.rowsum, 0, stream);
     {   // column-wise psi1 part: dA, dZ1
         rc = mm_cols_bwd_dispatch(p, mx, vx, z, ls, A, dm, dv, mout, psi1, n, M, Q, Do, w.colpart, stream);
         if (rc) return rc;
         long len = (long)Do * M + (long)M * Q;
-        GPB_LAUNCH(red, dim3(elementwise_grid(len)), dim3(256), 0, stream, w.colpart, p.cols_grid, len,
-                   len, w.colsum, 0);
+        launch_reduce_partials(w.colpart, p.cols_grid, len, len, w.colsum, 0, stream);
     }
     {
         auto kern = gpb::mm_pair_finish_kernel;

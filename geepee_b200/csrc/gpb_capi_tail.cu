@@ -14,10 +14,10 @@ gpb::TailOp to_dev_op(const GpbTailOp& h) {
     return o;
 }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, bool VEC>
 int launch_gemm(const gpb::TailOp& o, void* stream) {
     typedef gpb::TailGemmCfg<BM, BN, WM, WN> C;
-    auto kern = gpb::tail_gemm_kernel<BM, BN, WM, WN>;
+    auto kern = gpb::tail_gemm_kernel<BM, BN, WM, WN, VEC>;
     int rc = allow_smem(kern, C::smem_bytes);
     if (rc != GPB_OK) return rc;
     dim3 grid((unsigned)cdiv(o.n, BN), (unsigned)cdiv(o.m, BM), (unsigned)o.batch);
@@ -33,9 +33,12 @@ int run_op(const GpbTailOp& h, void* stream) {
         if (!h.src[0] || !h.src[1] || h.m < 1 || h.n < 1 || h.k < 1) return fail(GPB_ERR_ARG, "tail gemm: bad argument");
         // small problems: 32x32 tiles so that more SMs take part (the tail is latency bound)
         const long tiles64 = cdiv(h.m, 64) * cdiv(h.n, 64) * (long)h.batch;
-        if (tiles64 >= sm_count() || (h.m > 32 && h.n > 32 && tiles64 * 4 > 6L * sm_count()))
-            return launch_gemm<64, 64, 2, 4>(o, stream);
-        return launch_gemm<32, 32, 2, 2>(o, stream);
+        // 16-byte staging needs even leading dimensions / batch strides and 16-byte aligned bases
+        const bool vec = ((h.ld[0] | h.ld[1]) & 1) == 0 && ((h.sstride[0] | h.sstride[1]) & 1) == 0 &&
+                         (((size_t)h.src[0] | (size_t)h.src[1]) & 15) == 0;
+        const bool big = tiles64 >= sm_count() || (h.m > 32 && h.n > 32 && tiles64 * 4 > 6L * sm_count());
+        if (big) return vec ? launch_gemm<64, 64, 2, 4, true>(o, stream) : launch_gemm<64, 64, 2, 4, false>(o, stream);
+        return vec ? launch_gemm<32, 32, 2, 2, true>(o, stream) : launch_gemm<32, 32, 2, 2, false>(o, stream);
     }
     case GPB_TOP_LINCOMB: {
         if (h.m < 1 || h.n < 1) return fail(GPB_ERR_ARG, "tail lincomb: bad argument");
@@ -75,10 +78,17 @@ int run_op(const GpbTailOp& h, void* stream) {
         for (int i = 0; i < 6; i++)
             if (!h.src[i]) return fail(GPB_ERR_ARG, "tail khyper: null operand %d", i);
         if (h.m < 1 || h.k < 1 || h.k > 32) return fail(GPB_ERR_ARG, "tail khyper: D=%d unsupported (1..32)", h.k);
-        if (h.k <= 4) { auto kern = gpb::tail_khyper_kernel<4>; GPB_LAUNCH(kern, dim3(1), dim3(256), 0, stream, o); }
-        else if (h.k <= 8) { auto kern = gpb::tail_khyper_kernel<8>; GPB_LAUNCH(kern, dim3(1), dim3(256), 0, stream, o); }
-        else if (h.k <= 16) { auto kern = gpb::tail_khyper_kernel<16>; GPB_LAUNCH(kern, dim3(1), dim3(256), 0, stream, o); }
-        else { auto kern = gpb::tail_khyper_kernel<32>; GPB_LAUNCH(kern, dim3(1), dim3(256), 0, stream, o); }
+        // scratch for the per-block shares of the D + 1 scalar sums: behind the output record
+        // (the caller sizes dst as gpb_tail_khyper_out_len(M, D) doubles)
+        const int nb = (int)cdiv(h.m, 8);
+        double* part = h.dst + 1 + h.k + (long)h.m * h.k;
+        int dmax;
+        if (h.k <= 4) { dmax = 4; auto kern = gpb::tail_khyper_kernel<4>; GPB_LAUNCH(kern, dim3(nb), dim3(256), 0, stream, o, part); }
+        else if (h.k <= 8) { dmax = 8; auto kern = gpb::tail_khyper_kernel<8>; GPB_LAUNCH(kern, dim3(nb), dim3(256), 0, stream, o, part); }
+        else if (h.k <= 16) { dmax = 16; auto kern = gpb::tail_khyper_kernel<16>; GPB_LAUNCH(kern, dim3(nb), dim3(256), 0, stream, o, part); }
+        else { dmax = 32; auto kern = gpb::tail_khyper_kernel<32>; GPB_LAUNCH(kern, dim3(nb), dim3(256), 0, stream, o, part); }
+        auto fin = gpb::tail_khyper_finish_kernel;
+        GPB_LAUNCH(fin, dim3(1), dim3(64), 0, stream, o, (const double*)part, nb, dmax);
         return GPB_OK;
     }
     case GPB_TOP_SUM: {
@@ -89,8 +99,7 @@ int run_op(const GpbTailOp& h, void* stream) {
         double* part = const_cast<double*>(h.src[1]);
         auto kern = gpb::tail_sum_partial_kernel;
         GPB_LAUNCH(kern, dim3((unsigned)blocks), dim3(256), 0, stream, h.src[0], count, part);
-        auto red = gpb::reduce_partials_kernel;
-        GPB_LAUNCH(red, dim3(1), dim3(32), 0, stream, (const double*)part, (int)blocks, 1L, 1L, h.dst, 0);
+        launch_reduce_partials((const double*)part, (int)blocks, 1L, 1L, h.dst, 0, stream);
         return GPB_OK;
     }
     default:
@@ -109,6 +118,10 @@ int gpb_tail_exec(const GpbTailOp* h_ops, int n_ops, void* stream) {
         if (rc != GPB_OK) return rc;
     }
     return GPB_CHECK_LAUNCH();
+}
+
+long gpb_tail_khyper_out_len(int M, int D) {
+    return 1 + D + (long)M * D + cdiv(M, 8) * 33;
 }
 
 int gpb_tail_gather(int n, const double* const* h_srcs, const long* h_counts, double scale, double* dst,

@@ -27,6 +27,9 @@
 #ifndef GPB_EXP_BITS
 #define GPB_EXP_BITS 1
 #endif
+#ifndef GPB_SYRK_WAVES
+#define GPB_SYRK_WAVES 2
+#endif
 #ifndef GPB_MM_NR_FWD
 #define GPB_MM_NR_FWD 2
 #endif
@@ -169,6 +172,21 @@ inline int elementwise_grid(long total) {
     long b = cdiv(total, 256);
     long cap = (long)sm_count() * 8;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// second stage of the deterministic two-stage reductions: out[i] (+)= sum_g part[g*gstride + i]
+inline void launch_reduce_partials(const double* part, int G, long gstride, long len, double* out,
+                                   int accumulate, void* stream) {
+    if (G >= 64) {      // a thread per output would walk G partials serially (1184 after gauss_lik: 85 us)
+        auto red = gpb::reduce_partials_warp_kernel;
+        long blocks = cdiv(len, 8);
+        const long cap = (long)sm_count() * 8;
+        GPB_LAUNCH(red, dim3((unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks))), dim3(256), 0, stream,
+                   part, G, gstride, len, out, accumulate);
+    } else {
+        auto red = gpb::reduce_partials_kernel;
+        GPB_LAUNCH(red, dim3(elementwise_grid(len)), dim3(256), 0, stream, part, G, gstride, len, out, accumulate);
+    }
 }
 
 }  // namespace

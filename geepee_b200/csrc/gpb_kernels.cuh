@@ -38,6 +38,21 @@ GPB_KERNEL void reduce_partials_kernel(const double* __restrict__ part, int G, l
         out[i] = accumulate ? out[i] + s : s;
     }
 }
+// same result layout, many partials per output (G >= 64): one WARP per output element, the lanes
+// share the G partials (fixed assignment and a fixed shuffle tree: deterministic)
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) reduce_partials_warp_kernel(const double* __restrict__ part, int G,
+                                                                  long gstride, long len,
+                                                                  double* __restrict__ out, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const long wid = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long i = wid; i < len; i += nw) {
+        double s = 0;
+        for (int g = lane; g < G; g += 32) s += part[(long)g * gstride + i];
+        s = warp_sum(s);
+        if (lane == 0) out[i] = accumulate ? out[i] + s : s;
+    }
+}
 
 // sum of one double per thread over the block -> returned to thread 0 (others get junk)
 GPB_DEVICE double block_sum(double v, double* scratch /* >= 8 doubles of smem */) {
@@ -371,6 +386,25 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(128) gauss_emis_kernel(
 }
 
 // padded record [2 | DO | DO*QT] -> compact [2 | Do | Do*Q]
+// lik_layers.py:600-627: the sums of gauss_emis -> scale*logZ, scale*dR (wrt log-sqrt R), scale*dC
+//   raw = [quad | log|Vy| sum | dRacc[Do] | dC[Do*Q]], R = variances;  fin = [scale logZ | 0 | dR[Do] | dC[Do*Q]]
+GPB_KERNEL void gauss_emis_finish_kernel(const double* __restrict__ raw, const double* __restrict__ R, double alpha,
+                                         double scale, double Nb, int Do, int Q, double* __restrict__ fin) {
+    if (threadIdx.x == 0) {
+        double slr = 0.0, slra = 0.0;
+        for (int d = 0; d < Do; d++) {
+            slr += log(R[d]);
+            slra += log(R[d] / alpha);
+        }
+        const double vlog = -0.5 * (raw[1] - Nb * slra);
+        fin[0] = scale * (-Nb * Do * 0.5 * alpha * log(2.0 * 3.14159265358979323846) - 0.5 * Nb * alpha * slr
+                          + vlog + raw[0]);
+        fin[1] = 0.0;
+    }
+    for (int i = threadIdx.x; i < Do; i += blockDim.x)
+        fin[2 + i] = scale * ((raw[2 + i] / alpha + 0.5 * Nb * (1.0 - alpha) / R[i]) * 2.0 * R[i]);
+    for (int i = threadIdx.x; i < Do * Q; i += blockDim.x) fin[2 + Do + i] = scale * raw[2 + Do + i];
+}
 GPB_KERNEL void gauss_emis_compact_kernel(const double* __restrict__ full, int DO, int QT, int Do, int Q,
                                           double* __restrict__ out) {
     for (int i = threadIdx.x; i < 2 + Do + Do * Q; i += blockDim.x) {

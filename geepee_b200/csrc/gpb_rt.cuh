@@ -63,6 +63,11 @@ GPB_DEVICE void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool vali
     int n = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(n));
 }
+// 16-byte copy of which only the first `nbytes` (0, 8 or 16) are read; the rest is zero filled
+GPB_DEVICE void cp_async16_bytes(void* smem_dst, const void* gmem_src, int nbytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(nbytes));
+}
 // 8-byte variant (element-granular staging of small per-row records), zero-fill when !valid
 GPB_DEVICE void cp_async8_zfill(void* smem_dst, const void* gmem_src, bool valid) {
     uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -151,6 +156,10 @@ static inline void cp_async16_zfill(void* d, const void* s, bool valid) {
 }
 static inline void cp_async8_zfill(void* d, const void* s, bool valid) {
     if (valid) memcpy(d, s, 8); else memset(d, 0, 8);
+}
+static inline void cp_async16_bytes(void* d, const void* s, int nbytes) {
+    memset(d, 0, 16);
+    if (nbytes > 0) memcpy(d, s, nbytes);
 }
 static inline void cp_async_commit() {}
 template <int N>

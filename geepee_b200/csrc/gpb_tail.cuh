@@ -33,29 +33,58 @@ struct TailOp {            // mirrors GpbTailOp (include/geepee_b200.h)
 };
 
 // ---- GEMM ---------------------------------------------------------------------------------
-// CTA tile BM x BN, K chunks of 16 staged with 8-byte cp.async (operands may have odd leading
-// dimensions; out-of-range elements are zero filled), double buffered.  Shared-memory strides are
-// 4 resp. 8 mod 16 doubles so that every DMMA fragment load of a warp touches 32 different banks:
-//   A as [m][k] (stride 20)   a = A[g][t] -> 20 g + t        B as [k][n] (stride BN + 8)   b = B[t][g] -> (BN+8) t + g
-//   A as [k][m] (stride BM+8) a = A^T[t][g]                  B as [n][k] (stride 20)       b = B^T[g][t]
+// CTA tile BM x BN, K chunks of 32 through a 3-stage cp.async ring (the tail's products are small
+// and latency bound: two chunks are always in flight).  VEC: 16-byte copies (all leading dimensions,
+// batch strides and base addresses even / 16-byte aligned); otherwise 8-byte copies, so that operands
+// with odd leading dimensions work too.  Out-of-range elements are zero filled.  Shared-memory
+// strides are 4 resp. 8 mod 16 doubles so that every DMMA fragment load of a warp touches 32
+// different banks:
+//   A as [m][k] (stride 36)   a = A[g][t] -> 36 g + t        B as [k][n] (stride BN + 8)   b = B[t][g] -> (BN+8) t + g
+//   A as [k][m] (stride BM+8) a = A^T[t][g]                  B as [n][k] (stride 36)       b = B^T[g][t]
 template <int BM, int BN, int WM, int WN>
 struct TailGemmCfg {
-    static constexpr int KC = 16;
+    static constexpr int KC = 32, STAGES = 3;
     static constexpr int NT = WM * WN * 32;
     static constexpr int TM = BM / WM / 8, TN = BN / WN / 8;     // DMMA tiles per warp
     static constexpr int LDK = KC + 4;
     static constexpr int A_ELEMS = (BM * LDK > KC * (BM + 8)) ? BM * LDK : KC * (BM + 8);
     static constexpr int B_ELEMS = (BN * LDK > KC * (BN + 8)) ? BN * LDK : KC * (BN + 8);
-    static constexpr size_t smem_bytes = sizeof(double) * 2 * (A_ELEMS + B_ELEMS);
+    static constexpr size_t smem_bytes = sizeof(double) * STAGES * (A_ELEMS + B_ELEMS);
 };
 
-template <int BM, int BN, int WM, int WN>
+// one operand tile -> shared memory.  ROWS x KC logical tile (rows = m or n index, KC = k index);
+// `kmajor_src`: the source is stored [k][rows] (contiguous along rows), else [rows][k].
+template <int ROWS, int KC, int NT, bool VEC>
+GPB_DEVICE void tail_gemm_stage(double* dst, const double* __restrict__ src, int ld, bool kmajor_src, int r0,
+                                int k0, int R, int K, int tid) {
+    constexpr int LDK = KC + 4, LDR = ROWS + 8;
+    constexpr int W = VEC ? 2 : 1;
+    if (!kmajor_src) {      // [rows][k]: consecutive threads along k
+        for (int i = tid; i < ROWS * (KC / W); i += NT) {
+            const int r = i / (KC / W), c = (i % (KC / W)) * W;
+            const int left = ((r0 + r) < R) ? (K - (k0 + c)) : 0;
+            const double* g = src + (left > 0 ? (long)(r0 + r) * ld + (k0 + c) : 0);
+            if (VEC) cp_async16_bytes(dst + r * LDK + c, g, left >= 2 ? 16 : (left == 1 ? 8 : 0));
+            else cp_async8_zfill(dst + r * LDK + c, g, left > 0);
+        }
+    } else {                // [k][rows]: consecutive threads along rows
+        for (int i = tid; i < KC * (ROWS / W); i += NT) {
+            const int c = i / (ROWS / W), r = (i % (ROWS / W)) * W;
+            const int left = ((k0 + c) < K) ? (R - (r0 + r)) : 0;
+            const double* g = src + (left > 0 ? (long)(k0 + c) * ld + (r0 + r) : 0);
+            if (VEC) cp_async16_bytes(dst + c * LDR + r, g, left >= 2 ? 16 : (left == 1 ? 8 : 0));
+            else cp_async8_zfill(dst + c * LDR + r, g, left > 0);
+        }
+    }
+}
+
+template <int BM, int BN, int WM, int WN, bool VEC>
 GPB_KERNEL void GPB_LAUNCH_BOUNDS(WM * WN * 32) tail_gemm_kernel(TailOp o) {
     typedef TailGemmCfg<BM, BN, WM, WN> C;
-    constexpr int KC = C::KC, NT = C::NT, TM = C::TM, TN = C::TN, LDK = C::LDK;
+    constexpr int KC = C::KC, NT = C::NT, TM = C::TM, TN = C::TN, LDK = C::LDK, ST = C::STAGES;
     GPB_DYN_SMEM(dsm);
-    double* sA = (double*)dsm;                    // [2][A_ELEMS]
-    double* sB = sA + 2 * C::A_ELEMS;             // [2][B_ELEMS]
+    double* sA = (double*)dsm;                    // [ST][A_ELEMS]
+    double* sB = sA + ST * C::A_ELEMS;            // [ST][B_ELEMS]
     const bool ta = o.flags & 1, tb = (o.flags >> 1) & 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -64,7 +93,6 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(WM * WN * 32) tail_gemm_kernel(TailOp o) {
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const double* A = o.src[0] + (long)b * o.sstride[0];
     const double* B = o.src[1] + (long)b * o.sstride[1];
-    const int lda = o.ld[0], ldb = o.ld[1];
     const int M = o.m, N = o.n, K = o.k;
 
     double acc[TM][TN][2];
@@ -74,48 +102,24 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(WM * WN * 32) tail_gemm_kernel(TailOp o) {
         for (int j = 0; j < TN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stage = [&](int buf, int k0) {
-        double* a_s = sA + buf * C::A_ELEMS;
-        double* b_s = sB + buf * C::B_ELEMS;
-        if (!ta) {      // A[m][k] row-major: consecutive threads along k
-            for (int i = tid; i < BM * KC; i += NT) {
-                const int r = i / KC, c = i % KC;
-                const bool ok = (m0 + r) < M && (k0 + c) < K;
-                cp_async8_zfill(a_s + r * LDK + c, A + (ok ? (long)(m0 + r) * lda + (k0 + c) : 0), ok);
-            }
-        } else {        // stored [k][m]: consecutive threads along m
-            for (int i = tid; i < KC * BM; i += NT) {
-                const int c = i / BM, r = i % BM;
-                const bool ok = (m0 + r) < M && (k0 + c) < K;
-                cp_async8_zfill(a_s + c * (BM + 8) + r, A + (ok ? (long)(k0 + c) * lda + (m0 + r) : 0), ok);
-            }
-        }
-        if (!tb) {      // B[k][n] row-major: consecutive threads along n
-            for (int i = tid; i < KC * BN; i += NT) {
-                const int c = i / BN, r = i % BN;
-                const bool ok = (n0 + r) < N && (k0 + c) < K;
-                cp_async8_zfill(b_s + c * (BN + 8) + r, B + (ok ? (long)(k0 + c) * ldb + (n0 + r) : 0), ok);
-            }
-        } else {        // stored [n][k]
-            for (int i = tid; i < BN * KC; i += NT) {
-                const int r = i / KC, c = i % KC;
-                const bool ok = (n0 + r) < N && (k0 + c) < K;
-                cp_async8_zfill(b_s + r * LDK + c, B + (ok ? (long)(n0 + r) * ldb + (k0 + c) : 0), ok);
-            }
-        }
+        // op(A) is m x k: stored [m][k] (not transposed) or [k][m]; op(B) is k x n: stored [k][n] or [n][k]
+        tail_gemm_stage<BM, KC, NT, VEC>(sA + buf * C::A_ELEMS, A, o.ld[0], ta, m0, k0, M, K, tid);
+        tail_gemm_stage<BN, KC, NT, VEC>(sB + buf * C::B_ELEMS, B, o.ld[1], !tb, n0, k0, N, K, tid);
         cp_async_commit();
     };
 
     const int nk = (K + KC - 1) / KC;
-    stage(0, 0);
+    GPB_UNROLL
+    for (int s = 0; s < ST - 1; s++) {
+        if (s < nk) stage(s, s * KC);
+        else cp_async_commit();          // keep the group count uniform
+    }
     for (int kc = 0; kc < nk; kc++) {
-        const int buf = kc & 1;
-        if (kc + 1 < nk) {
-            stage(buf ^ 1, (kc + 1) * KC);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        sync_threads();
+        const int buf = kc % ST;
+        cp_async_wait<ST - 2>();         // chunk kc has landed (for this thread)
+        sync_threads();                  // ... for every thread; and chunk kc-1's buffer is free
+        if (kc + ST - 1 < nk) stage((kc + ST - 1) % ST, (kc + ST - 1) * KC);
+        else cp_async_commit();
         const double* a_s = sA + buf * C::A_ELEMS;
         const double* b_s = sB + buf * C::B_ELEMS;
         GPB_UNROLL
@@ -136,7 +140,6 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(WM * WN * 32) tail_gemm_kernel(TailOp o) {
                 GPB_UNROLL
                 for (int j = 0; j < TN; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        sync_threads();
     }
     // epilogue: dst = alpha acc + beta C0   (C0 = src[2], may alias dst)
     const double alpha = o.coef[0], beta = o.coef[1];
@@ -299,9 +302,12 @@ GPB_KERNEL void tail_pack_r_kernel(TailOp o) {
 //   dzu[a,q] = dzu0[a,q] + sum_b (Mm_ab + Mm_ba) Kzz_ab (z_bq - z_aq) / l_q^2
 // src = {Mm, Kuu, zu, ls, sf, stats}, stats = the contiguous record [dzu0[M*D] | dl[D] | dsf2 | dvsum] (the
 // tail of a layer's packed statistics).  dst = [dsf | dls[D] | dzu[M*D]] scaled by coef[1].
-// coef[0] = jitter.  One CTA of 8 warps, one warp per row a; m = M, k = D <= DMAX.
+// coef[0] = jitter; m = M, k = D <= DMAX.  Two launches: CTAs of 8 warps take 8 rows a each (one warp
+// per row: dzu[a,:] is complete there) and leave their share of the D + 1 scalar sums in `part`
+// ([gridDim.x][DMAX + 1], the op's scratch operand dst + 1 + D + M*D); a one-block finish kernel adds
+// the shares in a fixed order (deterministic) and writes dsf and dls.
 template <int DMAX>
-GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) tail_khyper_kernel(TailOp o) {
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) tail_khyper_kernel(TailOp o, double* __restrict__ part) {
     GPB_SHARED double s_ls[DMAX + 1][9];      // per-warp partials of the D lengthscale sums + the sf sum
     GPB_SHARED double s_il2[DMAX];
     const int M = o.m, D = o.k;
@@ -310,19 +316,19 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) tail_khyper_kernel(TailOp o) {
     const double* Kuu = o.src[1];
     const double* z = o.src[2];
     const double* dzu0 = o.src[5];
-    const double* dl = dzu0 + (long)M * D;
-    const double* dsf2 = dl + D;
-    const double* dvsum = dsf2 + 1;
     const double jitter = o.coef[0], scale = o.coef[1];
     if ((int)threadIdx.x < D) s_il2[threadIdx.x] = exp(-2.0 * o.src[3][threadIdx.x]);
     sync_threads();
     double gl[DMAX], gsf = 0.0;
     GPB_UNROLL
     for (int q = 0; q < DMAX; q++) gl[q] = 0.0;
-    for (int a = warp; a < M; a += nwarp) {
-        double gz[DMAX];
+    for (int a = blockIdx.x * nwarp + warp; a < M; a += gridDim.x * nwarp) {
+        double gz[DMAX], za[DMAX];
         GPB_UNROLL
-        for (int q = 0; q < DMAX; q++) gz[q] = 0.0;
+        for (int q = 0; q < DMAX; q++) {
+            gz[q] = 0.0;
+            za[q] = q < D ? z[(long)a * D + q] : 0.0;
+        }
         for (int b = lane; b < M; b += 32) {
             const double kzz = Kuu[(long)a * o.ld[1] + b] - (a == b ? jitter : 0.0);
             const double mab = Mm[(long)a * o.ld[0] + b], mba = Mm[(long)b * o.ld[0] + a];
@@ -331,7 +337,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) tail_khyper_kernel(TailOp o) {
             GPB_UNROLL
             for (int q = 0; q < DMAX; q++) {
                 if (q < D) {
-                    const double dz = z[(long)b * D + q] - z[(long)a * D + q];
+                    const double dz = z[(long)b * D + q] - za[q];
                     gz[q] += ws * dz * s_il2[q];
                     gl[q] += w * dz * dz * s_il2[q];
                 }
@@ -357,15 +363,28 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) tail_khyper_kernel(TailOp o) {
         if (lane == 0) s_ls[DMAX][warp] = s;
     }
     sync_threads();
-    if ((int)threadIdx.x < D) {
-        const int q = threadIdx.x;
+    if ((int)threadIdx.x <= D) {
+        const int q = (int)threadIdx.x < D ? (int)threadIdx.x : DMAX;
         double s = 0.0;
         for (int w = 0; w < nwarp; w++) s += s_ls[q][w];
+        part[(long)blockIdx.x * (DMAX + 1) + q] = s;
+    }
+}
+GPB_KERNEL void tail_khyper_finish_kernel(TailOp o, const double* __restrict__ part, int nblocks, int DMAX) {
+    const int M = o.m, D = o.k;
+    const double* dl = o.src[5] + (long)M * D;
+    const double* dsf2 = dl + D;
+    const double* dvsum = dsf2 + 1;
+    const double scale = o.coef[1];
+    const int q = threadIdx.x;
+    if (q < D) {
+        double s = 0.0;
+        for (int g = 0; g < nblocks; g++) s += part[(long)g * (DMAX + 1) + q];
         o.dst[1 + q] = scale * (dl[q] * exp(o.src[3][q]) + s);
     }
-    if (threadIdx.x == 32) {
+    if (q == 32) {
         double s = 0.0;
-        for (int w = 0; w < nwarp; w++) s += s_ls[DMAX][w];
+        for (int g = 0; g < nblocks; g++) s += part[(long)g * (DMAX + 1) + DMAX];
         const double sf2 = exp(2.0 * o.src[4][0]);
         o.dst[0] = scale * (2.0 * sf2 * (dsf2[0] + dvsum[0]) + 2.0 * s);
     }

@@ -281,13 +281,8 @@ class Gauss_Emis(object):
         if ops.gauss_emis_supported(Do, self.Din) and Nb > 0:
             # fused per-row kernel (Cholesky / inverse of the Do x Do matrices in registers)
             dmx, dvx, out = ops.gauss_emis(mx.contiguous(), vx.contiguous(), y.contiguous(), C, R, alpha, scale)
-            quad, ld_Vy = out[0], out[1]
-            vlog = -0.5 * (ld_Vy - Nb * torch.log(R / alpha).sum())
-            logZ = (-Nb * Do * 0.5 * alpha * np.log(2 * np.pi) - 0.5 * Nb * alpha * torch.log(R).sum()
-                    + vlog + quad)
-            dR = (out[2:2 + Do] / alpha + 0.5 * Nb * (1 - alpha) / R) * 2 * R
-            dC = out[2 + Do:].reshape(Do, self.Din)
-            return logZ * scale, dmx, dvx, {'C': dC * scale, 'R': dR * scale}
+            fin = ops.gauss_emis_finish(out, R, alpha, scale, Nb, Do, self.Din)     # lik_layers.py:600-627
+            return fin[0], dmx, dvx, {'C': fin[2 + Do:].reshape(Do, self.Din), 'R': fin[2:2 + Do]}
         CVC = torch.einsum('da,na,ba->ndb', C, vx, C)
         Vy = torch.diag(R / alpha).unsqueeze(0) + CVC
         Yd = y - torch.matmul(mx, C.t())

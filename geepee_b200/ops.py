@@ -152,6 +152,14 @@ def gauss_emis(mx, vx, y, C, R, alpha, scale):
     return dmx, dvx, out
 
 
+def gauss_emis_finish(raw, R, alpha, scale, Nb, Do, Q):
+    """lik_layers.py:600-627 from the sums of gauss_emis -> [scale*logZ | 0 | scale*dR[Do] | scale*dC[Do*Q]]."""
+    fin = torch.empty_like(raw)
+    _chk(_lib.get().gpb_gauss_emis_finish(_p(_c(raw)), _p(_c(R)), float(alpha), float(scale), int(Nb), int(Do), int(Q),
+                                          _p(fin), _stream(raw)), 'gauss_emis_finish')
+    return fin
+
+
 class DetOperands(object):
     """Zero-padded, precision-typed copies of (A, B_det) for the deterministic layer."""
 
@@ -295,3 +303,96 @@ def profile_collect():
     cnt = (ctypes.c_long * 8)()
     _lib.get().gpb_profile_collect(ms, cnt)
     return {PROFILE_SLOTS[i]: (ms[i], cnt[i]) for i in range(8)}
+
+
+# ---- a12 / a13: elementwise latent-variable kernels (csrc/gpb_latent.cuh) --------------------
+def _sel_args(sel, lo):
+    if sel is None:
+        return None, int(lo)
+    if sel.dtype != torch.int64 or not sel.is_contiguous():
+        raise RuntimeError('geepee_b200: row selection must be a contiguous int64 device tensor')
+    return ctypes.c_void_p(sel.data_ptr()), 0
+
+
+def lvm_x_fwd(mode, nat, x1, x2, sel, lo, n, prior1, prior2, alpha):
+    """aep_models.py:840-861 (mode 0: cavity of x) / base_models.py:765-775 (mode 1: posterior of x) for the
+    rows `sel` (device int64) or lo..lo+n-1 of the raw [N,Q] parameters.  -> m, v [n,Q]."""
+    lib = _lib.get()
+    Q = x1.shape[1]
+    m = torch.empty((n, Q), dtype=torch.float64, device=x1.device)
+    v = torch.empty((n, Q), dtype=torch.float64, device=x1.device)
+    sp, lo = _sel_args(sel, lo)
+    _chk(lib.gpb_lvm_x_fwd(int(mode), int(bool(nat)), _p(_c(x1)), _p(_c(x2)), sp, lo, int(n), Q, float(prior1),
+                           float(prior2), float(alpha), _p(m), _p(v), _stream(x1)), 'lvm_x_fwd')
+    return m, v
+
+
+def lvm_x_bwd(mode, nat, x1, x2, sel, lo, n, prior1, prior2, alpha, s_cav, s_post, dmx, dvx):
+    """aep_models.py:785-801,817-838,863-867 + base_models.py:913-929 (mode 0) / vfe_models.py:826-840,857-863
+    (mode 1).  -> gx1, gx2 [N,Q] (zero outside the selection), sums[2]."""
+    lib = _lib.get()
+    N, Q = x1.shape
+    dev = x1.device
+    gx1 = torch.empty((N, Q), dtype=torch.float64, device=dev)
+    gx2 = torch.empty((N, Q), dtype=torch.float64, device=dev)
+    sums = torch.empty(2, dtype=torch.float64, device=dev)
+    ws = _ws(lib.gpb_latent_ws_bytes(n * Q), x1)
+    sp, lo = _sel_args(sel, lo)
+    _chk(lib.gpb_lvm_x_bwd(int(mode), int(bool(nat)), _p(_c(x1)), _p(_c(x2)), sp, lo, int(n), int(N), Q,
+                           float(prior1), float(prior2), float(alpha), float(s_cav), float(s_post), _p(_c(dmx)),
+                           _p(_c(dvx)), _p(gx1), _p(gx2), _p(sums), _p(ws), ws.numel(), _stream(x1)), 'lvm_x_bwd')
+    return gx1, gx2, sums
+
+
+def ssm_cavity(xf1, xf2, prior1, prior2, alpha):
+    """aep_models.py:1376-1387 over all T latent states -> cav_m, cav_v [T,Q]."""
+    lib = _lib.get()
+    T, Q = xf1.shape
+    cm, cv = torch.empty_like(xf1), torch.empty_like(xf1)
+    _chk(lib.gpb_ssm_cavity(_p(_c(xf1)), _p(_c(xf2)), int(T), Q, float(prior1), float(prior2), float(alpha),
+                            _p(cm), _p(cv), _stream(xf1)), 'ssm_cavity')
+    return cm, cv
+
+
+def ssm_transition(mt, vt, mp, vp, sn, alpha, s_dyn):
+    """aep_models.py:1334-1348 -> dm for the layer (= -dmt), dvt, sums[2] = {sum lz, sum dvt}."""
+    lib = _lib.get()
+    total = mp.numel()
+    dm, dv = torch.empty_like(mp), torch.empty_like(mp)
+    sums = torch.empty(2, dtype=torch.float64, device=mp.device)
+    ws = _ws(lib.gpb_latent_ws_bytes(total), mp)
+    _chk(lib.gpb_ssm_transition(_p(_c(mt)), _p(_c(vt)), _p(_c(mp)), _p(_c(vp)), _p(_c(sn)), int(total), float(alpha),
+                                float(s_dyn), _p(dm), _p(dv), _p(sums), _p(ws), ws.numel(), _stream(mp)),
+         'ssm_transition')
+    return dm, dv, sums
+
+
+def ssm_sources(xf1, xf2, prior1, prior2, alpha, prev, nxt, up):
+    """aep_models.py:1234-1285 -> l1, l2 [T,Q].  prev / nxt / up: None or (dm, dv, first_row) with dm, dv
+    [count, ld >= Q] contiguous."""
+    lib = _lib.get()
+    T, Q = xf1.shape
+    l1, l2 = torch.empty_like(xf1), torch.empty_like(xf1)
+    args = []
+    for s in (prev, nxt, up):
+        if s is None:
+            args += [None, None, 0, 0, Q]
+        else:
+            dm, dv, first = s
+            args += [_p(_c(dm)), _p(_c(dv)), int(first), int(dm.shape[0]), int(dm.shape[1])]
+    _chk(lib.gpb_ssm_sources(_p(_c(xf1)), _p(_c(xf2)), int(T), Q, float(prior1), float(prior2), float(alpha),
+                             *args, _p(l1), _p(l2), _stream(xf1)), 'ssm_sources')
+    return l1, l2
+
+
+def ssm_xfinal(xf1, xf2, prior1, prior2, alpha, l1, l2):
+    """aep_models.py:1208-1232,1287-1315,1389-1437 -> gx1, gx2 [T,Q], sums[2] = {phi_post, phi_cav}."""
+    lib = _lib.get()
+    T, Q = xf1.shape
+    gx1, gx2 = torch.empty_like(xf1), torch.empty_like(xf1)
+    sums = torch.empty(2, dtype=torch.float64, device=xf1.device)
+    ws = _ws(lib.gpb_latent_ws_bytes(T * Q), xf1)
+    _chk(lib.gpb_ssm_xfinal(_p(_c(xf1)), _p(_c(xf2)), int(T), Q, float(prior1), float(prior2), float(alpha),
+                            _p(_c(l1)), _p(_c(l2)), _p(gx1), _p(gx2), _p(sums), _p(ws), ws.numel(), _stream(xf1)),
+         'ssm_xfinal')
+    return gx1, gx2, sums

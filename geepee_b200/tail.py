@@ -310,8 +310,11 @@ def khyper(Mm, Kuu, zu, ls, sf, stats, jitter, scale=1.0, out=None):
         _check(t)
     if stats.numel() != M * D + D + 2 or not stats.is_contiguous():
         raise RuntimeError('geepee_b200.tail.khyper: statistics record has the wrong size')
+    need = int(_lib.get().gpb_tail_khyper_out_len(M, D))       # record + per-block scratch
     if out is None:
-        out = torch.empty(1 + D + M * D, dtype=_F, device=zu.device)
+        out = torch.empty(need, dtype=_F, device=zu.device)
+    elif out.numel() < need:
+        raise RuntimeError('geepee_b200.tail.khyper: output buffer too small (%d < %d)' % (out.numel(), need))
     op = GpbTailOp()
     op.kind, op.batch, op.m, op.k = KHYPER, 1, M, D
     _set(op, 0, Mm, 0, Mm.stride(0))
@@ -323,7 +326,7 @@ def khyper(Mm, Kuu, zu, ls, sf, stats, jitter, scale=1.0, out=None):
     op.coef[0], op.coef[1] = float(jitter), float(scale)
     op.dst = out.data_ptr()
     _run(op, zu)
-    return out
+    return out[:1 + D + M * D]
 
 
 def multicopy(dsts, srcs):

@@ -8,7 +8,8 @@ a different, full-batch algorithm and out of scope.
 import numpy as np
 import torch
 
-from . import dist
+from . import dist, ops
+from . import tail as tl
 from .aep_models import _add_stats, _get_stats, _zero_stats, _zeros, _check_mode, _mc_eps
 from .base_models import Base_SGPR, Base_SGPLVM, Base_SGPSSM
 from .config import PROP_MM, PROP_MC
@@ -43,7 +44,7 @@ class SGPR(Base_SGPR):
         grads = L._tail(_get_stats(add, 's_'), False)
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
-        energy = scale * add['ll'] + L._kl()
+        energy = tl.dots([(scale, add['ll'], None), (1.0, L._kl(), None)])
         return self._finish(energy, grads)
 
 
@@ -59,17 +60,18 @@ class SGPLVM(Base_SGPLVM):
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
-        sel, n = self._rows(mb_size)
+        sel, lo, cnt, n = self._rows(mb_size)
         eps = _mc_eps(n, Q, dev) if prop_mode == PROP_MC else None
         scale = -N * 1.0 / n
         sx = N * 1.0 / n
         self.update_hypers(params)
         m0, v0 = self.prior_mean, self.prior_var
-        add = {'gx1': _zeros(dev, N, Q), 'gx2': _zeros(dev, N, Q)}
-        if sel.shape[0] > 0:
-            yb = self._y.index_select(0, sel)
-            p1, p2 = self._post1[sel], self._post2[sel]
-            mx, vx = (p1 / p2).contiguous(), (1.0 / p2).contiguous()
+        add = {}
+        if cnt > 0:
+            yb = self._y[lo:lo + cnt] if sel is None else self._y.index_select(0, sel)
+            x1d, x2d = self._x1d, self._x2d
+            # posterior of x for this rank's rows (base_models.py:765-775), one kernel
+            mx, vx = ops.lvm_x_fwd(1, self.nat_param, x1d, x2d, sel, lo, cnt, m0, v0, 1.0)
             if eps is not None:     # vfe_models.py:793-808: sample average of the expected log-lik
                 K = eps.shape[0]
                 m, v, ctx = L._fwd_mc(mx, vx, eps, cav=False)
@@ -82,21 +84,13 @@ class SGPLVM(Base_SGPLVM):
                 dm, dv, ll, dsn = self.lik_layer._log_lik_exp(m, v, yb, scale)
                 st = L._bwd_mm(ctx, dm, dv)
             _add_stats(add, 's_', st)
-            # KL of q(x) (vfe_models.py:857-863) and chain to x1, x2 (base_models.py:913-929)
-            klx = (0.5 * (np.log(v0) - torch.log(vx) + (vx + (mx - m0)**2) / v0 - 1)).sum()
-            dmx = st['dmx'] + sx * (mx - m0) / v0
-            dvx = st['dvx'] + sx * (-0.5 / vx + 0.5 / v0)
-            f2 = self._f2[sel]
-            if self.nat_param:
-                d1 = dmx / p2
-                d2 = (-dmx * p1 / p2**2 - dvx / p2**2) * 2 * f2
-            else:
-                d1, d2 = dmx, dvx * 2 * f2
-            add['gx1'].index_copy_(0, sel, d1)
-            add['gx2'].index_copy_(0, sel, d2)
-            add['ll'], add['dsn'], add['klx'] = ll.reshape(1), dsn.reshape(1), klx.reshape(1)
+            # KL of q(x) (vfe_models.py:857-863) and the chain to x1, x2 (base_models.py:913-929), one kernel
+            add['gx1'], add['gx2'], sums = ops.lvm_x_bwd(1, self.nat_param, x1d, x2d, sel, lo, cnt, m0, v0, 1.0, sx, 0.0,
+                                                         st['dmx'].contiguous(), st['dvx'].contiguous())
+            add['ll'], add['dsn'], add['klx'] = ll.reshape(1), dsn.reshape(1), sums[0:1]
         else:
             _add_stats(add, 's_', _zero_stats(L))
+            add['gx1'], add['gx2'] = _zeros(dev, N, Q), _zeros(dev, N, Q)
             for k in ('ll', 'dsn', 'klx'):
                 add[k] = _zeros(dev, 1)
         add = dist.allreduce_dict(add)
@@ -104,7 +98,7 @@ class SGPLVM(Base_SGPLVM):
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
         grads['x1'], grads['x2'] = add['gx1'], add['gx2']
-        energy = scale * add['ll'] + sx * add['klx'] + L._kl()
+        energy = tl.dots([(scale, add['ll'], None), (sx, add['klx'], None), (1.0, L._kl(), None)])
         return self._finish(energy, grads)
 
 

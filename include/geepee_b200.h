@@ -93,6 +93,10 @@ size_t gpb_gauss_emis_ws_bytes(int n, int Do, int Q);
 int gpb_gauss_emis(const double* mx, const double* vx, const double* y, const double* C, const double* R,
                    double alpha, double scale, int n, int Q, int Do, double* dmx, double* dvx,
                    double* out, void* ws, size_t ws_bytes, void* stream);
+/*      lik_layers.py:600-627 from those sums: fin = [scale*logZ | 0 | scale*dR[Do] (wrt the log-sqrt parameter) |
+ *      scale*dC[Do*Q]]; raw = the `out` of gpb_gauss_emis over Nb rows. */
+int gpb_gauss_emis_finish(const double* raw, const double* R, double alpha, double scale, long Nb, int Do,
+                          int Q, double* fin, void* stream);
 
 /* ---- deterministic-input layer -------------------------------------------------------------- */
 /* M padded to the GEMM tile (128, 256 or 512); -1 if M > 512. */
@@ -176,8 +180,9 @@ int gpb_mm_bwd(int prec, const double* mx, const double* vx, const double* z, co
  *      GPB_TOP_PACK_R   dst[b][m(m+1)/2] = coef[0] triu(src0[b]) with the diagonal times diag(src1[b])
  *                       (base_models.py:505-514)
  *      GPB_TOP_KHYPER   kernels.py:447-475 folded with aep_models.py:455-460,497-504: src = {Mm, Kuu, zu,
- *                       ls, sf, stats = [dzu0[m*k] | dl[k] | dsf2 | dvsum]}; dst = coef[1] [dsf | dls[k] | dzu[m*k]];
- *                       coef[0] = jitter; m = M, k = D <= 32
+ *                       ls, sf, stats = [dzu0[m*k] | dl[k] | dsf2 | dvsum]}; dst = coef[1] [dsf | dls[k] | dzu[m*k]]
+ *                       followed by scratch: dst holds gpb_tail_khyper_out_len(m, k) doubles;
+ *                       coef[0] = jitter; m = M, k = D <= 32 (two launches)
  *      GPB_TOP_SUM      dst[0] = sum of src0[0 .. sstride[0]) (any length; src1 = scratch of >= 1024 doubles) */
 #define GPB_TOP_GEMM 1
 #define GPB_TOP_LINCOMB 2
@@ -198,6 +203,7 @@ typedef struct GpbTailOp {
     long dstride;
     int ldd;
 } GpbTailOp;
+long gpb_tail_khyper_out_len(int M, int D);
 /* run `n_ops` tail primitives in order on `stream` (h_ops: HOST array; one kernel launch per op,
  * two for GPB_TOP_SUM) */
 int gpb_tail_exec(const GpbTailOp* h_ops, int n_ops, void* stream);
@@ -211,6 +217,45 @@ int gpb_tail_gather(int n, const double* const* h_srcs, const long* h_counts, do
  * input buffers of a captured tail phase.  h_*: HOST arrays. */
 int gpb_tail_copy(int n, const double* const* h_srcs, double* const* h_dsts, const long* h_counts,
                   void* stream);
+
+/* ---- a12 / a13: elementwise latent-variable algebra (one thread per (row, latent dim)) ----------
+ *      SGPLVM: get_cavity_x aep_models.py:840-861, compute_phi_x 863-867, compute_cav_grad_x 817-838,
+ *      get_posterior_x base_models.py:765-775, compute_posterior_grad_x 913-929; VFE twin vfe_models.py:749-845.
+ *      x1, x2: the raw [N,Q] parameters on the device; sel: device row indices of the minibatch (NULL: rows
+ *      lo .. lo+n-1); mode 0 = AEP (prior1/prior2 = prior natural parameters; output = cavity moments),
+ *      mode 1 = VFE (prior1/prior2 = prior mean / variance; output = posterior moments). */
+size_t gpb_latent_ws_bytes(long total);
+int gpb_lvm_x_fwd(int mode, int nat, const double* x1, const double* x2, const long* sel, long lo, int n, int Q,
+                  double prior1, double prior2, double alpha, double* m /*[n,Q]*/, double* v /*[n,Q]*/, void* stream);
+/* backward: dmx, dvx[n,Q] from the layer -> gx1, gx2[N,Q] (rows outside the selection zeroed) and
+ * sums[2] = {phi_x(cavity), phi_x(posterior)} (AEP) / {KL(q(x)||p(x)), 0} (VFE).  s_cav, s_post: the
+ * scale factors of the two log-partition terms (AEP) / s_cav = N/n (VFE). */
+int gpb_lvm_x_bwd(int mode, int nat, const double* x1, const double* x2, const long* sel, long lo, int n, long N,
+                  int Q, double prior1, double prior2, double alpha, double s_cav, double s_post,
+                  const double* dmx, const double* dvx, double* gx1, double* gx2, double* sums, void* ws,
+                  size_t ws_bytes, void* stream);
+/*      SGPSSM (natural parameters): compute_cavity_x aep_models.py:1376-1387 */
+int gpb_ssm_cavity(const double* xf1, const double* xf2, long T, int Q, double prior1, double prior2,
+                   double alpha, double* cav_m, double* cav_v, void* stream);
+/*      compute_transition_tilted aep_models.py:1317-1348 (2-D branch) on `total` = rows*Q elements:
+ *      mt, vt = cavity of state t+1, mp, vp = propagated moments.  -> dm_layer = -dmt, dvt (scaled by s_dyn),
+ *      sums[2] = {sum log Z terms, sum dvt} */
+int gpb_ssm_transition(const double* mt, const double* vt, const double* mp, const double* vp, const double* sn,
+                       long total, double alpha, double s_dyn, double* dm_layer, double* dvt, double* sums,
+                       void* ws, size_t ws_bytes, void* stream);
+/*      compute_logZ_grad_x aep_models.py:1234-1285: the three gradient sources of every latent state chained
+ *      to its cavity naturals -> l1, l2[T,Q].  prev: (-dmt, dvt) of the transitions INTO rows first..; next /
+ *      up: the layers' input gradients (row stride ld >= Q).  NULL dm = no such source. */
+int gpb_ssm_sources(const double* xf1, const double* xf2, long T, int Q, double prior1, double prior2, double alpha,
+                    const double* prev_dm, const double* prev_dv, long prev_first, long prev_count, int prev_ld,
+                    const double* next_dm, const double* next_dv, long next_first, long next_count, int next_ld,
+                    const double* up_dm, const double* up_dv, long up_first, long up_count, int up_ld,
+                    double* l1, double* l2, void* stream);
+/*      compute_posterior_grad_x / compute_cavity_grad_x / compute_phi_{posterior,cavity}_x
+ *      aep_models.py:1208-1232,1287-1315,1389-1437 over ALL T rows -> gx1, gx2[T,Q], sums[2] = {phi_post, phi_cav} */
+int gpb_ssm_xfinal(const double* xf1, const double* xf2, long T, int Q, double prior1, double prior2, double alpha,
+                   const double* l1, const double* l2, double* gx1, double* gx2, double* sums, void* ws,
+                   size_t ws_bytes, void* stream);
 
 /* ---- per-kernel device timing for bench.py's roofline (CUDA events on the launching stream).
  *      slots: 0 det_fwd, 1 det_bwd, 2 det_syrk, 3 mm_pairs(fwd), 4 mm_pairs(bwd), 5 mm_rows_bwd,

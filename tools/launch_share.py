@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Share of each kernel in the LAST step of an `ncu --metrics gpu__time_duration.sum --csv` launch
-list of `bench.py --steps 1 --warmup W` (the steps are delimited by the packed parameter upload's
-first library kernel; simpler and robust: split the launch list into W+1(+e2e) equal-structure
-groups by the det_fwd launches and summarise the group before the e2e pass).
-usage: launch_share.py launches.csv"""
+"""Per-kernel share of ONE objective call from an `ncu --metrics gpu__time_duration.sum --csv` launch
+list of `bench.py --steps 1 --warmup W --no-cpu` (every objective call launches the same kernel
+sequence -- eagerly or from CUDA-graph replays -- so the step is the shortest period of the name
+sequence once the trailing FMA-peak probe is dropped).
+usage: launch_share.py launches.csv [--all]"""
 import collections
 import csv
 import sys
@@ -15,19 +15,29 @@ recs = [(r[ci['Kernel Name']], float(r[ci['Metric Value']].replace(',', '')), r[
         for r in rows[1:] if len(r) > ci['Metric Value'] and r[ci['Metric Name']] == 'gpu__time_duration.sum']
 scale = {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 'nsecond': 1e-6, 'usecond': 1e-3, 'msecond': 1.0}
 recs = [(k, v * scale.get(u, 1e-6)) for k, v, u in recs]
-starts = [i for i, (k, _) in enumerate(recs) if 'det_fwd' in k]
-print('launches %d, steps found %d' % (len(recs), len(starts)))
-if len(starts) >= 2:
-    # the objective's first library launches (kmat / pre-tail) precede det_fwd; take whole periods
-    period = starts[-1] - starts[-2]
-    lo = starts[-2]
-    step = recs[lo:lo + period]
+while recs and ('fma_peak' in recs[-1][0] or 'FillFunctor' in recs[-1][0]):
+    recs.pop()
+names = [k for k, _ in recs]
+period = None
+for p in range(8, len(names) // 2 + 1):
+    if names[-p:] == names[-2 * p:-p]:
+        period = p
+        break
+print('launches %d, period %s' % (len(recs), period))
+if period:
+    step = recs[-period:]
     tot = sum(v for _, v in step)
-    agg = collections.Counter()
+
+    def short(k):
+        return k.split('(')[0].replace('void ', '').replace('gpb::', '')[:70]
+    agg, cnt = collections.Counter(), collections.Counter()
     for k, v in step:
-        name = k.split('(')[0].split('<')[0].replace('void ', '').replace('gpb::', '')
-        agg[name] += v
-    print('one step: %d launches, %.3f ms of kernel time (serialised, cold cache)' % (len(step), tot))
-    lib = sum(v for k, v in agg.items() if not k.startswith(('at::', 'cublas', 'cutlass', 'sm', 'void at')) and 'at::native' not in k)
-    for k, v in agg.most_common(14):
-        print('  %-48s %9.3f ms  %5.1f %%' % (k[:48], v, 100 * v / tot))
+        agg[short(k)] += v
+        cnt[short(k)] += 1
+    foreign = [k for k in agg if k.startswith(('at::', 'cublas', 'cutlass', 'sm80', 'sm90', 'sm100', 'nccl')) or 'at::native' in k
+               or 'cublas' in k.lower() or 'gemv' in k.lower() or 'elementwise' in k]
+    print('one step: %d launches, %.3f ms of kernel time (serialised, cold cache); not from this library: %d launches %.3f ms'
+          % (len(step), tot, sum(cnt[k] for k in foreign), sum(agg[k] for k in foreign)))
+    lim = 1000 if '--all' in sys.argv else 24
+    for k, v in agg.most_common(lim):
+        print('  %-70s x%-3d %9.4f ms  %5.1f %%%s' % (k, cnt[k], v, 100 * v / tot, '   <-- foreign' if k in foreign else ''))
