@@ -36,7 +36,7 @@ def _mc_eps(n, Q, dev):
     """eps[K, n, Q] of the Monte-Carlo propagation: drawn on the host from numpy's GLOBAL RNG
     exactly where the reference draws it (aep_models.py:171, base_models.py:320), so that seeded
     runs reproduce the reference; every rank draws the same array and keeps its rows."""
-    eps = np.random.randn(MC_NO_SAMPLES, n, Q)
+    eps = dist.agree(np.random.randn(MC_NO_SAMPLES, n, Q))
     lo, hi = dist.shard(n)
     return to_dev(eps[:, lo:hi], dev)
 
@@ -81,10 +81,12 @@ class SGPR(Base_SGPR):
         L.compute_cavity(alpha)
         add = {}
         if xb.shape[0] > 0:
-            m, v, ctx = L._fwd_det(xb, cav=True, save=True)
-            dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb, alpha, scale_logZ)
-            _add_stats(add, 's_', L._bwd_det(ctx, dm, dv))
-            add['logZ'], add['dsn'] = logZ.reshape(1), dsn.reshape(1)
+            def lik(m, v, c0, c1):
+                dm, dv, logZ, dsn = self.lik_layer._log_Z(m, v, yb[c0:c1], alpha, scale_logZ)
+                return dm, dv, {'logZ': logZ.reshape(1), 'dsn': dsn.reshape(1)}
+            st, ext = L.det_step(xb, lik, cav=True)       # row-chunked: saved Kfu / T stay bounded
+            _add_stats(add, 's_', st)
+            add.update(ext)
         else:
             _add_stats(add, 's_', _zero_stats(L))
             add['logZ'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)
@@ -165,6 +167,7 @@ class SDGPR(Base_SDGPR):
                 add['logZ'] = logZ.reshape(1) if has_rows else _zeros(dev, 1)
                 add['dsn'] = dsn.reshape(1) if has_rows else _zeros(dev, 1)
             ts.fork(i)
+            ts.keep(i, add.values())
             with ts.on(i):
                 add = dist.allreduce_dict(add)
                 g = layer._tail_det(_get_stats(add, 's_'), alpha) if i == 0 else \

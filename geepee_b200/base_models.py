@@ -126,7 +126,7 @@ class Base_Model(object):
         full = (mb_size == N) if exact else (mb_size >= N)
         if full:
             return None
-        return np.random.choice(N, mb_size, replace=False)
+        return dist.agree(np.random.choice(N, mb_size, replace=False))
 
 
 class Base_SGPR(Base_Model):
@@ -334,7 +334,8 @@ class Base_SGPLVM(Base_Model):
         self.nat_param = nat_param
         self.lik_layer = _make_lik(lik, self.N, self.Dout, self.device)
         self.factor_x1 = np.zeros((self.N, self.Din))
-        self.factor_x2 = np.zeros((self.N, self.Din))
+        self._x2_raw = None         # the log-sqrt parameter as given; factor_x2 = exp(2 x2) on first use
+        self._factor_x2 = np.zeros((self.N, self.Din))
         self.prior_mean = prior_mean
         self.prior_var = prior_var
         self.prior_x1 = prior_mean / prior_var
@@ -350,6 +351,16 @@ class Base_SGPLVM(Base_Model):
     def predict_y(self, inputs):
         mf, vf = self.predict_f(inputs)
         return self.lik_layer.output_probabilistic(mf, vf)
+
+    @property
+    def factor_x2(self):
+        if self._factor_x2 is None:
+            self._factor_x2 = np.exp(2 * self._x2_raw)
+        return self._factor_x2
+
+    @factor_x2.setter
+    def factor_x2(self, value):
+        self._factor_x2 = value
 
     def get_posterior_x(self, idxs=None):
         """base_models.py:765-775."""
@@ -398,7 +409,9 @@ class Base_SGPLVM(Base_Model):
         self.sgp_layer.update_hypers(params, _dev=dev)
         self.lik_layer.update_hypers(params, _dev=dev)
         self.factor_x1 = params['x1']
-        self.factor_x2 = np.exp(2 * params['x2'])
+        # the reference stores exp(2 x2) here (base_models.py:903); only get_hypers reads it back, and N Q
+        # host exponentials per objective call cost milliseconds at N = 1e5 .. 1e6 -> formed on first use
+        self._x2_raw, self._factor_x2 = params['x2'], None
         # raw device parameters: the objective's latent-variable kernels (ops.lvm_x_fwd / lvm_x_bwd) read
         # them directly; the derived arrays below exist for the prediction / inspection API only
         self._x1d = dev['x1'].reshape(self.N, self.Din)
@@ -579,6 +592,16 @@ class Base_SGPSSM(Base_Model):
             vyn = np.diagonal(vyn, axis1=1, axis2=2)
         return my, vf, vyn
 
+    @property
+    def x_factor_2(self):
+        if self._x_factor_2 is None:
+            self._x_factor_2 = np.exp(2 * self._xf2_raw)
+        return self._x_factor_2
+
+    @x_factor_2.setter
+    def x_factor_2(self, value):
+        self._x_factor_2 = value
+
     def get_hypers(self):
         params = dict(self.dyn_layer.get_hypers(key_suffix='_dynamic'))
         params.update(self.emi_layer.get_hypers(key_suffix='_emission'))
@@ -600,7 +623,8 @@ class Base_SGPSSM(Base_Model):
         self.sn = params['sn']
         self._sn = dp['sn'].reshape(-1)[:1].contiguous()
         self.x_factor_1 = params['x_factor_1']
-        self.x_factor_2 = np.exp(2 * params['x_factor_2'])
+        # exp(2 x_factor_2) (base_models.py:1716) is only read back by get_hypers: formed on first use
+        self._xf2_raw, self._x_factor_2 = params['x_factor_2'], None
         # raw device parameters: the moment-matched AEP objective's latent-state kernels (ops.ssm_*) read
         # them directly; the derived arrays below are formed on first use (Monte-Carlo / VFE / prediction paths)
         self._x1d = dp['x_factor_1'].reshape(self.N, self.Din)
@@ -646,7 +670,7 @@ class Base_SGPSSM(Base_Model):
         N = self.N
         if mb_size >= N:
             return 0, N
-        start = np.random.randint(0, N - mb_size)
+        start = int(dist.agree(np.random.randint(0, N - mb_size)))
         return start, start + mb_size
 
     def _with_control(self, m, v, lo, hi, Dcon):

@@ -1,5 +1,6 @@
 // gpb_capi_mm.cu -- moment-matched (uncertain-input) layer entry points (a2+a6, a2+a9).
 #include "gpb_common.cuh"
+#include "gpb_pairsx.cuh"
 
 namespace {
 
@@ -11,8 +12,28 @@ struct MMPlan {
     int rows_grid, cols_grid, cols_rows_per_block, fwd_grid;
     // fp64 backward of wide layers (Do > 4, Qt <= 8): tensor-core kernel over 64-pair chunks
     int wide_mma, w_nchunks, w_nsplit, w_rows_per_split;
+    // fp64 narrow layers (Do <= 4, Qt <= 4): pair kernels with the exponent on the FP64 tensor cores
+    int xpath, x_nchunks, x_nsplit, x_rows_per_split, x_rlg;
+    long x_npad;
     // workspace byte offsets are carved in order by mm_carve
 };
+// row splits of the tensor-exponent pair kernels: two resident blocks per SM; take the split count (<= 48,
+// >= 4 row tiles per block) whose block count fills whole waves best, the smallest one on ties
+void mmx_splits(int n, int nchunks, int* nsplit, int* rows_per_split) {
+    const long slots = 2L * sm_count();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ns = 1; ns <= 48; ns++) {
+        if (ns > 1 && cdiv(n, ns) < 4 * 32) break;
+        const long rps = cdiv(cdiv(n, ns), 32) * 32;
+        const long total = (long)nchunks * cdiv(n, rps);
+        const double eff = (double)total / (double)(cdiv(total, slots) * slots);
+        if (eff > best_eff + 0.01) { best_eff = eff; best = ns; }
+    }
+    const long rps = cdiv(cdiv(n, best), 32) * 32;
+    *rows_per_split = (int)rps;
+    *nsplit = (int)cdiv(n, rps);
+}
 int q_template(int Q) {
     if (Q <= 6) return Q;
     if (Q <= 8) return 8;
@@ -64,6 +85,16 @@ MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do, int backward) {
     if (crpb < 32) crpb = 32;
     p.cols_rows_per_block = (int)crpb;
     p.cols_grid = (int)cdiv(n, crpb);
+    p.xpath = (GPB_MM_XPATH && tbytes == 8 && Do <= 4 && p.Qt <= 4) ? 1 : 0;
+    p.x_nchunks = p.x_nsplit = p.x_rows_per_split = p.x_rlg = 0;
+    p.x_npad = 0;
+    if (p.xpath) {
+        const int kq = (2 * p.Qt + 3) / 4;
+        p.x_nchunks = (int)(p.PP / (64 * gpb::mmx_npg(p.Qt, p.DOC, backward != 0)));
+        p.x_rlg = (4 * kq + 1 + (backward ? p.DOC : 0) + 1) / 2 * 2;
+        p.x_npad = cdiv(n, 32) * 32;
+        mmx_splits(n, p.x_nchunks, &p.x_nsplit, &p.x_rows_per_split);
+    }
     p.wide_mma = (backward && tbytes == 8 && Do > 4 && p.Qt <= 8) ? 1 : 0;
     p.w_nchunks = (int)(p.PP / 64);
     p.w_nsplit = 1;
@@ -85,6 +116,7 @@ template <typename T>
 struct MMWs {
     T *zh, *ep, *bs;
     double *rowacc, *pairpart, *pairsum, *rowpart, *rowsum, *colpart, *colsum, *dZ2, *dlW;
+    double* rowfeat;
     size_t bytes;
 };
 template <typename T>
@@ -94,12 +126,13 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
     w.zh = (T*)cv.take(sizeof(T) * p.Qt * p.PP);
     w.ep = (T*)cv.take(sizeof(T) * p.PP);
     w.bs = (T*)cv.take(sizeof(T) * Do * p.PP);
+    w.rowfeat = p.xpath ? (double*)cv.take(sizeof(double) * (size_t)p.x_npad * p.x_rlg) : nullptr;
     if (!backward) {
         w.rowacc = nullptr;   // the forward accumulates straight into the caller's vacc[n,Do]
         w.pairpart = w.pairsum = w.rowpart = w.rowsum = w.colpart = w.colsum = w.dZ2 = w.dlW = nullptr;
     } else {
         w.rowacc = (double*)cv.take(sizeof(double) * (size_t)n * (2 * p.Qt));
-        size_t npart = (size_t)p.nsplit * (p.DOC + 1 + p.Qt) * p.PP;
+        size_t npart = (size_t)(p.xpath ? p.x_nsplit : p.nsplit) * (p.DOC + 1 + p.Qt) * p.PP;
         if (p.wide_mma) npart = (size_t)p.w_nsplit * (Do + 1 + p.Qt) * p.PP;
         w.pairpart = (double*)cv.take(sizeof(double) * npart);
         w.pairsum = (double*)cv.take(sizeof(double) * (size_t)(Do + 1 + p.Qt) * p.PP);
@@ -129,6 +162,43 @@ int mm_pairs_smem(K kern, size_t dyn) {
     (void)kern; (void)dyn;
 #endif
     return GPB_OK;
+}
+
+// tensor-exponent pair kernels (gpb_pairsx.cuh): row records first, then the pair kernel
+template <int Q, int DOC, bool BWD>
+int mm_pairsx_launch(const MMPlan& p, gpb::MMArgs<double> a, double* rowfeat, void* stream) {
+    typedef gpb::MMXCfg<Q, DOC, BWD> C;
+    static_assert(C::PCX == 64 * gpb::mmx_npg(Q, DOC, BWD), "mm_plan assumes this pair-chunk size");
+    auto kern = gpb::mm_pairsx_kernel<Q, DOC, BWD>;
+    if (mm_pairs_smem(kern, C::smem_bytes)) return GPB_ERR_CUDA;
+    if (p.x_rlg != C::RLG) return fail(GPB_ERR_ARG, "mm_pairsx: record length mismatch (%d vs %d)", p.x_rlg, C::RLG);
+    a.rows_per_split = p.x_rows_per_split;
+    prof_begin(BWD ? 4 : 3, stream);
+    auto feat = gpb::mm_rowfeat_kernel<Q>;
+    GPB_LAUNCH(feat, dim3(elementwise_grid(p.x_npad)), dim3(256), 0, stream, a.mx, a.vx, a.ls,
+               BWD ? a.dv : (const double*)nullptr, a.n, (int)p.x_npad, a.Qa, a.Do, DOC, C::RLG, rowfeat);
+    GPB_LAUNCH(kern, dim3(p.x_nchunks, p.x_nsplit), dim3(256), C::smem_bytes, stream, a, (const double*)rowfeat);
+    prof_end(BWD ? 4 : 3, stream);
+    return GPB_OK;
+}
+template <int Q, bool BWD>
+int mm_pairsx_doc(const MMPlan& p, const gpb::MMArgs<double>& a, double* rowfeat, void* stream) {
+    switch (p.DOC) {
+        case 1: return mm_pairsx_launch<Q, 1, BWD>(p, a, rowfeat, stream);
+        case 2: return mm_pairsx_launch<Q, 2, BWD>(p, a, rowfeat, stream);
+        case 4: return mm_pairsx_launch<Q, 4, BWD>(p, a, rowfeat, stream);
+    }
+    return fail(GPB_ERR_ARG, "mm_pairsx: bad DOC %d", p.DOC);
+}
+template <bool BWD>
+int mm_pairsx_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, double* rowfeat, void* stream) {
+    switch (p.Qt) {
+        case 1: return mm_pairsx_doc<1, BWD>(p, a, rowfeat, stream);
+        case 2: return mm_pairsx_doc<2, BWD>(p, a, rowfeat, stream);
+        case 3: return mm_pairsx_doc<3, BWD>(p, a, rowfeat, stream);
+        case 4: return mm_pairsx_doc<4, BWD>(p, a, rowfeat, stream);
+    }
+    return fail(GPB_ERR_ARG, "mm_pairsx: input dim template %d unsupported", p.Qt);
 }
 
 template <typename T, int Q, int DOC, bool BWD>
@@ -232,23 +302,24 @@ int mm_cols_bwd_launch(const MMPlan& p, const double* mx, const double* vx, cons
                        const double* mout, const double* psi1, int n, int M, int Q, int Do,
                        double* colpart, void* stream) {
     const size_t smem = sizeof(double) * 32 * (2 * (size_t)QT + Do);
-    const int DOB = Do == 1 ? 1 : (Do == 2 ? 2 : 4);
+    // output dims per pass: every pass re-streams psi1[n,M], so wide layers take 16 at a time
+    // (Do = 50: 4 passes instead of 13)
+    const int DOB = Do == 1 ? 1 : (Do == 2 ? 2 : (Do <= 4 ? 4 : (Do <= 8 ? 8 : 16)));
     prof_begin(6, stream);
-    for (int d0 = 0; d0 < Do; d0 += DOB) {
-        if (DOB == 1) {
-            auto kern = gpb::mm_cols_bwd_kernel<QT, 1>;
-            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
-                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
-        } else if (DOB == 2) {
-            auto kern = gpb::mm_cols_bwd_kernel<QT, 2>;
-            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
-                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
-        } else {
-            auto kern = gpb::mm_cols_bwd_kernel<QT, 4>;
-            GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1,
-                       n, M, Q, Do, d0, p.cols_rows_per_block, colpart);
-        }
+#define GPB_COLS(DOBV)                                                                                          \
+    {                                                                                                           \
+        auto kern = gpb::mm_cols_bwd_kernel<QT, DOBV>;                                                          \
+        GPB_LAUNCH(kern, dim3(p.cols_grid), dim3(256), smem, stream, mx, vx, z, ls, A, dm, dv, mout, psi1, n, M, \
+                   Q, Do, d0, p.cols_rows_per_block, colpart);                                                  \
     }
+    for (int d0 = 0; d0 < Do; d0 += DOB) {
+        if (DOB == 1) GPB_COLS(1)
+        else if (DOB == 2) GPB_COLS(2)
+        else if (DOB == 4) GPB_COLS(4)
+        else if (DOB == 8) GPB_COLS(8)
+        else GPB_COLS(16)
+    }
+#undef GPB_COLS
     prof_end(6, stream);
     return GPB_CHECK_LAUNCH();
 }
@@ -401,7 +472,16 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
             if (rc) return rc;
         }
     } else {
-        for (int pass = 0; pass < p.npass; pass++) {
+        bool done = false;
+        if constexpr (sizeof(T) == 8) {
+            if (p.xpath) {      // exponent on the FP64 tensor cores
+                a.d0 = 0;
+                rc = mm_pairsx_dispatch<false>(p, a, w.rowfeat, stream);
+                if (rc) return rc;
+                done = true;
+            }
+        }
+        for (int pass = 0; pass < (done ? 0 : p.npass); pass++) {
             a.d0 = pass * p.DOC;
             rc = mm_pairs_dispatch<T, false>(p, a, stream);
             if (rc) return rc;
@@ -443,6 +523,19 @@ int mm_bwd_t(const double* mx, const double* vx, const double* z, const double* 
             if (rc) return rc;
             const long wlen = (long)(Do + 1 + p.Qt) * p.PP;
             launch_reduce_partials(w.pairpart, p.w_nsplit, wlen, wlen, w.pairsum, 0, stream);
+            wide_done = true;
+        }
+    }
+    if constexpr (sizeof(T) == 8) {
+        if (p.xpath && !wide_done) {    // narrow fp64 layers: exponent on the FP64 tensor cores, one pass
+            a.d0 = 0;
+            a.lam_pass = 1;
+            rc = mm_pairsx_dispatch<true>(p, a, w.rowfeat, stream);
+            if (rc) return rc;
+            const long xlen = (long)(p.DOC + 1 + p.Qt) * p.PP;
+            launch_reduce_partials(w.pairpart, p.x_nsplit, xlen, (long)(Do < p.DOC ? Do : p.DOC) * p.PP, w.pairsum, 0, stream);
+            launch_reduce_partials(w.pairpart + (long)p.DOC * p.PP, p.x_nsplit, xlen, (long)(1 + p.Qt) * p.PP,
+                                   w.pairsum + (long)Do * p.PP, 0, stream);
             wide_done = true;
         }
     }

@@ -27,6 +27,10 @@
 #ifndef GPB_EXP_BITS
 #define GPB_EXP_BITS 1
 #endif
+// narrow fp64 moment-matched layers: pair kernels with the exponent on the FP64 tensor cores (gpb_pairsx.cuh)
+#ifndef GPB_MM_XPATH
+#define GPB_MM_XPATH 1
+#endif
 #ifndef GPB_SYRK_WAVES
 #define GPB_SYRK_WAVES 2
 #endif

@@ -22,6 +22,18 @@ def shard(n):
     return (rank * n) // ws, ((rank + 1) * n) // ws
 
 
+def agree(arr):
+    """Host-side random draws (minibatch rows, SSM window, Monte-Carlo eps) must be THE SAME array on every
+    rank: each rank draws from its own numpy RNG in the reference's order, then rank 0's draw is broadcast
+    so that unsynchronised RNG states cannot make the ranks shard different minibatches.  No-op with one rank."""
+    rank, ws = world()
+    if ws == 1:
+        return arr
+    box = [arr]
+    torch.distributed.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 def allreduce_packed(tensors):
     """Sum a list of same-dtype device tensors across ranks with one collective.
     Returns new tensors (views into the packed buffer)."""

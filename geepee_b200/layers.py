@@ -379,6 +379,40 @@ class Base_SGP_Layer(object):
         dB = ops.det_syrk(self.prec, Ks, dv, self.M)
         return {'dA': dA, 'dB': dB, 'dzu': dzu, 'dl': dl, 'dsf2': dsf2, 'dvsum': tl.total(dv)}
 
+    def det_chunks(self, n):
+        """[(c0, c1)] row chunks of a deterministic-layer step whose saved Kfu / T buffers stay below
+        config.DET_SAVE_BYTES (one chunk when everything fits)."""
+        esize = 8 if self.prec == ops.F64 else 4
+        MP = _lib.get().gpb_det_pad_m(self.M)
+        per_row = (1 + self.Dout) * max(MP, 1) * esize
+        rows = max(int(config.DET_SAVE_BYTES // per_row), config.DET_MIN_CHUNK_ROWS)
+        if n <= rows:
+            return [(0, n)]
+        k = -(-n // rows)
+        step = -(-n // k)
+        if step >= 128:
+            step = -(-step // 128) * 128      # whole row tiles
+        return [(c0, min(c0 + step, n)) for c0 in range(0, n, step)]
+
+    def det_step(self, xb, lik_fn, cav):
+        """Forward, likelihood and per-row backward of a single deterministic layer, chunked over rows
+        (aep_models.py:142-158 + lik + 452-493).  lik_fn(m, v, c0, c1) -> (dm, dv, extras: dict of additive
+        [1]-tensors).  -> (statistics, summed extras)."""
+        acc, ext = None, None
+        for c0, c1 in self.det_chunks(xb.shape[0]):
+            m, v, ctx = self._fwd_det(xb[c0:c1], cav=cav, save=True)
+            dm, dv, e = lik_fn(m, v, c0, c1)
+            st = self._bwd_det(ctx, dm, dv)
+            del ctx, m, v
+            if acc is None:
+                acc, ext = st, e
+            else:
+                for d_acc, d_new in ((acc, st), (ext, e)):
+                    for k in d_acc:
+                        a = d_acc[k].reshape(1, -1)
+                        tl.lincomb([(1.0, a), (1.0, d_new[k].reshape(1, -1))], out=a)
+        return acc, ext
+
     def _fwd_mm(self, mx, vx, cav, save=True):
         """a6 on the device (save=False: prediction, nothing kept for a backward)."""
         t = self._t

@@ -48,6 +48,15 @@ class TailStreams(object):
             return torch.cuda.stream(self.streams[i])
         return contextlib.nullcontext()
 
+    def keep(self, i, tensors):
+        """Tensors allocated on the main stream that side stream i is about to read: tell the caching
+        allocator, so that a free on the main stream cannot hand their memory out while stream i still
+        reads them."""
+        if self.cuda:
+            for t in tensors:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(self.streams[i])
+
     def join(self, i):
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.streams[i])

@@ -33,10 +33,12 @@ class SGPR(Base_SGPR):
         self.update_hypers(params)
         add = {}
         if xb.shape[0] > 0:
-            m, v, ctx = L._fwd_det(xb, cav=False, save=True)
-            dm, dv, ll, dsn = self.lik_layer._log_lik_exp(m, v, yb, scale)
-            _add_stats(add, 's_', L._bwd_det(ctx, dm, dv))
-            add['ll'], add['dsn'] = ll.reshape(1), dsn.reshape(1)
+            def lik(m, v, c0, c1):
+                dm, dv, ll, dsn = self.lik_layer._log_lik_exp(m, v, yb[c0:c1], scale)
+                return dm, dv, {'ll': ll.reshape(1), 'dsn': dsn.reshape(1)}
+            st, ext = L.det_step(xb, lik, cav=False)      # row-chunked: saved Kfu / T stay bounded
+            _add_stats(add, 's_', st)
+            add.update(ext)
         else:
             _add_stats(add, 's_', _zero_stats(L))
             add['ll'], add['dsn'] = _zeros(dev, 1), _zeros(dev, 1)

@@ -45,6 +45,19 @@ def check_model(name, prec, tol, device=None):
     return model, gold
 
 
+def check_chunked(name, prec, tol, device=None):
+    """Row-chunked deterministic step (config.DET_SAVE_BYTES): forcing several chunks must reproduce the
+    golden energy and gradients (the statistics are additive over rows)."""
+    from geepee_b200 import config
+    old = config.DET_SAVE_BYTES, config.DET_MIN_CHUNK_ROWS
+    config.DET_SAVE_BYTES, config.DET_MIN_CHUNK_ROWS = 1, 7
+    try:
+        model, gold = check_model(name, prec, tol, device)
+        assert len(model.sgp_layer.det_chunks(gold['meta']['mb_size'])) > 1
+    finally:
+        config.DET_SAVE_BYTES, config.DET_MIN_CHUNK_ROWS = old
+
+
 def check_predict(name, prec, tol, device=None):
     gold = gu.load(name)
     model = build_model(gold, prec, device)

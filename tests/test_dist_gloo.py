@@ -68,3 +68,36 @@ def test_two_ranks_match_golden(names):
 def test_shard_covers_rows():
     from geepee_b200 import dist
     assert dist.shard(10) == (0, 10)
+
+
+def _worker_rng(rank, world, port, q):
+    """Ranks with DIFFERENT numpy RNG states must still shard the same minibatch / window / eps."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, '..'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.distributed.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from geepee_b200 import dist
+        np.random.seed(1000 + rank)                     # unsynchronised on purpose
+        rows = dist.agree(np.random.choice(50, 7, replace=False))
+        start = int(dist.agree(np.random.randint(0, 40)))
+        eps = dist.agree(np.random.randn(2, 5, 3))
+        q.put((rank, rows.tolist(), start, float(eps.sum())))
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+def test_random_draws_agree_across_ranks():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_rng, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1:] == res[1][1:], res
+    ref = np.random.RandomState(1000).choice(50, 7, replace=False).tolist()     # rank 0's own draw
+    assert res[0][1] == ref

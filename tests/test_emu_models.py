@@ -19,6 +19,11 @@ def test_objective_fp64(name):
     mc.check_model(name, 'fp64', 1e-6)
 
 
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sgpr_probit'])
+def test_chunked_rows(name):
+    mc.check_chunked(name, 'fp64', 1e-6)
+
+
 @pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr', 'aep_sgplvm', 'aep_sgpssm_lin', 'vfe_sgpr'])
 def test_objective_fp32(name):
     mc.check_model(name, 'fp32', 1e-3)

@@ -56,6 +56,13 @@ def test_predict(name):
     mc.check_predict(name, 'fp64', 1e-7)
 
 
+@pytest.mark.parametrize('name', ['aep_sgpr', 'vfe_sgpr', 'aep_sgpr_probit', 'bench_ns_sgpr_n2048'])
+def test_chunked_rows(name):
+    """config.DET_SAVE_BYTES: the single-layer models process rows in chunks whose saved Kfu / T tiles stay
+    bounded; forcing many chunks reproduces the reference."""
+    mc.check_chunked(name, 'fp64', TOL64)
+
+
 @pytest.mark.parametrize('name', ['aep_sgpr', 'aep_sdgpr'])
 def test_sampling(name):
     mc.check_sampling(name, 1e-5)
