@@ -24,13 +24,13 @@ void mmx_splits(int n, int nchunks, int* nsplit, int* rows_per_split) {
     int best = 1;
     double best_eff = 0.0;
     for (int ns = 1; ns <= 48; ns++) {
-        if (ns > 1 && cdiv(n, ns) < 4 * 32) break;
-        const long rps = cdiv(cdiv(n, ns), 32) * 32;
+        if (ns > 1 && cdiv(n, ns) < 4 * 64) break;
+        const long rps = cdiv(cdiv(n, ns), 64) * 64;
         const long total = (long)nchunks * cdiv(n, rps);
         const double eff = (double)total / (double)(cdiv(total, slots) * slots);
         if (eff > best_eff + 0.01) { best_eff = eff; best = ns; }
     }
-    const long rps = cdiv(cdiv(n, best), 32) * 32;
+    const long rps = cdiv(cdiv(n, best), 64) * 64;      // whole row tiles (MMXCfg::TR)
     *rows_per_split = (int)rps;
     *nsplit = (int)cdiv(n, rps);
 }
@@ -85,14 +85,14 @@ MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do, int backward) {
     if (crpb < 32) crpb = 32;
     p.cols_rows_per_block = (int)crpb;
     p.cols_grid = (int)cdiv(n, crpb);
-    p.xpath = (GPB_MM_XPATH && tbytes == 8 && Do <= 4 && p.Qt <= 4) ? 1 : 0;
+    p.xpath = (GPB_MM_XPATH && (!backward || GPB_MM_XPATH_BWD) && tbytes == 8 && Do <= 4 && p.Qt <= 4) ? 1 : 0;
     p.x_nchunks = p.x_nsplit = p.x_rows_per_split = p.x_rlg = 0;
     p.x_npad = 0;
     if (p.xpath) {
         const int kq = (2 * p.Qt + 3) / 4;
         p.x_nchunks = (int)(p.PP / (64 * gpb::mmx_npg(p.Qt, p.DOC, backward != 0)));
         p.x_rlg = (4 * kq + 1 + (backward ? p.DOC : 0) + 1) / 2 * 2;
-        p.x_npad = cdiv(n, 32) * 32;
+        p.x_npad = cdiv(n, 64) * 64;
         mmx_splits(n, p.x_nchunks, &p.x_nsplit, &p.x_rows_per_split);
     }
     p.wide_mma = (backward && tbytes == 8 && Do > 4 && p.Qt <= 8) ? 1 : 0;
@@ -192,6 +192,10 @@ int mm_pairsx_doc(const MMPlan& p, const gpb::MMArgs<double>& a, double* rowfeat
 }
 template <bool BWD>
 int mm_pairsx_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, double* rowfeat, void* stream) {
+    if constexpr (BWD && !GPB_MM_XPATH_BWD) {
+        (void)p; (void)a; (void)rowfeat; (void)stream;
+        return fail(GPB_ERR_ARG, "mm_pairsx: backward variant not built (GPB_MM_XPATH_BWD)");
+    } else
     switch (p.Qt) {
         case 1: return mm_pairsx_doc<1, BWD>(p, a, rowfeat, stream);
         case 2: return mm_pairsx_doc<2, BWD>(p, a, rowfeat, stream);

@@ -31,6 +31,13 @@
 #ifndef GPB_MM_XPATH
 #define GPB_MM_XPATH 1
 #endif
+// ... and their backward twin.  Measured on the B200 (tools/kbench.py mm, n = 32768): forward 1.368 vs 1.460 ms
+// (M=256, Q=2, Do=2), backward 3.43 vs 2.85 ms -- a block of the tensor-exponent kernel covers 128 pairs instead
+// of 1024, so the per-tile barrier, the row staging and the cross-warp row sums are amortised over 8x fewer
+// pairs, which costs the backward (4 + 2Q row sums per row) more than the tensor instruction saves.  Off.
+#ifndef GPB_MM_XPATH_BWD
+#define GPB_MM_XPATH_BWD 0
+#endif
 #ifndef GPB_SYRK_WAVES
 #define GPB_SYRK_WAVES 2
 #endif

@@ -16,8 +16,8 @@
 // on those values with the pair constants in registers.  Per-pair sums over rows are therefore spread over
 // the 8 lanes with the same t and folded ONCE at the end of the kernel; per-row sums over pairs are spread
 // over the 4 lanes of a quad, the 8 warps and the pair chunks (blocks): per-lane partials go to shared
-// memory, one thread group per (row, value) adds them after the tile's only barrier and issues one fp64
-// atomic per value.
+// memory atomics (after two quad shuffles), and after the tile's only barrier one fp64 atomic per
+// (row, value) goes to the global row sums.
 //
 // Row records are precomputed once per launch by mm_rowfeat_kernel (the divisions / logarithms of
 // kernels.py:188-190 are per row, not per row and pair chunk) and staged 32 rows at a time with cp.async:
@@ -38,15 +38,12 @@ struct MMXCfg {
     static constexpr int NPG = mmx_npg(Q, DOC, BWD);      // pair groups (of 8) per warp
     static constexpr int NRG = 2;                         // row groups (of 8) per loop trip
     static constexpr int PCX = 8 * NPG * 8;               // pairs per block
-    static constexpr int TR = 32;                         // rows per staged tile
+    static constexpr int TR = 64;                         // rows per staged tile (one barrier per tile)
     static constexpr int RL = KQ == 1 ? 12 : 20;          // row record stride in shared memory (doubles)
     static constexpr int RLG = (4 * KQ + 1 + (BWD ? DOC : 0) + 1) / 2 * 2;   // ... in global memory (even)
     static constexpr int NS = BWD ? 2 * Q : DOC;          // per-row sums
     static constexpr int NSP = (NS + 1) / 2 * 2;
-    static constexpr bool QRED = NS > 4;                  // fold the quad with shuffles first (smem budget)
-    static constexpr int NT = QRED ? 1 : 4;
-    static constexpr size_t smem_bytes =
-        sizeof(double) * ((size_t)ExpDom<double>::TAB + 2 * TR * RL + 2 * 8 * TR * NT * NSP);
+    static constexpr size_t smem_bytes = sizeof(double) * ((size_t)ExpDom<double>::TAB + 2 * TR * RL + 2 * TR * NSP);
 };
 
 // one record per row (rows n .. n_pad-1: null records whose psi2' underflows and whose dv is 0)
@@ -87,14 +84,12 @@ template <int Q, int DOC, bool BWD>
 GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, const double* __restrict__ rowfeat) {
     typedef MMXCfg<Q, DOC, BWD> C;
     constexpr int KQ = C::KQ, NPG = C::NPG, NRG = C::NRG, TR = C::TR, RL = C::RL, NS = C::NS, NSP = C::NSP;
-    constexpr int NT = C::NT;
-    constexpr bool QRED = C::QRED;
     constexpr int kTab = ExpDom<double>::TAB;
     constexpr double kS = ExpDom<double>::S;
     GPB_DYN_SMEM(dsm);
     double* s_tab = (double*)dsm;
     double* s_row = s_tab + kTab;                  // [2][TR * RL]
-    double* s_red = s_row + 2 * TR * RL;           // [2][8 warps][TR][NT][NSP]
+    double* s_acc = s_row + 2 * TR * RL;           // [2][TR][NSP] row sums of the tile (shared-memory atomics)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const long PP = a.PP;
@@ -140,6 +135,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
             }
         }
     for (int i = tid; i < kTab; i += 256) s_tab[i] = exp_bits_table(i / ExpDom<double>::REP);
+    for (int i = tid; i < 2 * TR * NSP; i += 256) s_acc[i] = 0.0;
     const int lane16 = lane & (ExpDom<double>::REP - 1);
     const int half_bit = 8 + (a.n < 0);      // = 8, kept in a register (LOP3 operand of exp_dom_bits_n)
 
@@ -164,7 +160,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
         const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
         if (t0 + TR < r_end) stage(buf ^ 1, t0 + TR);
         const double* rows = s_row + buf * TR * RL;
-        double* red = s_red + (size_t)buf * 8 * TR * NT * NSP + (size_t)warp * TR * NT * NSP;
+        double* acc_t = s_acc + buf * TR * NSP;
         GPB_UNROLL_N(1)
         for (int trip = 0; trip < TR / (8 * NRG); trip++) {
             double x[NRG][NPG * 2];
@@ -249,48 +245,35 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
                             for (int rg = 0; rg < NRG; rg++) v[rg][Q + q] += lam[rg][2 * gi + e] * zh2[gi][e][q];
                         }
             }
-            // this lane's share of the row sums -> shared memory
+            // row sums: fold the 4 lanes of a quad (they hold different pairs of the same row) with two
+            // shuffles, then one lane per quad adds into the tile's accumulators in shared memory (the 8
+            // warps hold different pairs of the same rows; fp64 shared atomics are CAS loops, collisions
+            // between warps are rare)
             GPB_UNROLL
             for (int rg = 0; rg < NRG; rg++) {
                 const int row = trip * 8 * NRG + rg * 8 + g;
-                if (QRED) {
+                GPB_UNROLL
+                for (int s_ = 0; s_ < NS; s_++) {
+                    v[rg][s_] += shfl_xor(v[rg][s_], 1);
+                    v[rg][s_] += shfl_xor(v[rg][s_], 2);
+                }
+                if (t == 0) {
                     GPB_UNROLL
-                    for (int s = 0; s < NS; s++) {
-                        v[rg][s] += shfl_xor(v[rg][s], 1);
-                        v[rg][s] += shfl_xor(v[rg][s], 2);
-                    }
-                    if (t == 0) {
-                        GPB_UNROLL
-                        for (int s = 0; s < NSP; s += 2)
-                            *(double2*)(red + row * NSP + s) = make_double2(v[rg][s], v[rg][s + 1]);
-                    }
-                } else {
-                    GPB_UNROLL
-                    for (int s = 0; s < NSP; s += 2)
-                        *(double2*)(red + (row * 4 + t) * NSP + s) = make_double2(v[rg][s], v[rg][s + 1]);
+                    for (int s_ = 0; s_ < NS; s_++) atomic_add(acc_t + row * NSP + s_, v[rg][s_]);
                 }
             }
         }
         cp_async_wait<0>();
         sync_threads();         // the only barrier per tile: partials complete, next tile staged
-        {
-            // (row, value) sums over the 8 warps (x 4 quad lanes): 4 threads per output, 2 warps each
-            const double* redt = s_red + (size_t)buf * 8 * TR * NT * NSP;
-            const int part = tid & 3;
-            for (int o = tid >> 2; o < TR * NS; o += 64) {
-                const int row = o / NS, s = o - row * NS;
-                double acc = 0.0;
-                GPB_UNROLL
-                for (int w = 0; w < 2; w++)
-                    GPB_UNROLL
-                    for (int tt = 0; tt < NT; tt++)
-                        acc += redt[((size_t)(2 * part + w) * TR * NT + row * NT + tt) * NSP + s];
-                acc += shfl_xor(acc, 1);
-                acc += shfl_xor(acc, 2);
-                if (part == 0 && row < tv) {
-                    if (BWD) atomic_add(a.rowacc + (long)(t0 + row) * NS + s, acc);
-                    else if (s < a.Do) atomic_add(a.rowacc + (long)(t0 + row) * a.Do + s, acc);
-                }
+        // tile complete: one fp64 atomic per (row, value) into the global row sums; re-arm the accumulators
+        for (int o = tid; o < TR * NS; o += 256) {
+            const int row = o / NS, s_ = o - row * NS;
+            double* ap = s_acc + buf * TR * NSP + row * NSP + s_;
+            const double acc = *ap;
+            *ap = 0.0;
+            if (row < tv) {
+                if (BWD) atomic_add(a.rowacc + (long)(t0 + row) * NS + s_, acc);
+                else if (s_ < a.Do) atomic_add(a.rowacc + (long)(t0 + row) * a.Do + s_, acc);
             }
         }
     }
