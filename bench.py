@@ -449,7 +449,7 @@ def secondary_workload(name, args, dev, peak_tf):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 10)):
         step()
     ops.profile_enable(True)
     ops.profile_collect()
@@ -651,16 +651,18 @@ def run_gpu(args, w):
         for v in pairs.values():
             v['frac'] = v['achieved'] / peak_tf
         line['roofline']['pair_kernels'] = pairs
+    if world == 1 and args.workload == 'cfg3_sdgpr' and not args.no_secondary:
+        # measured right after the main workload, while the GPU is still at its working clocks (the CPU
+        # baseline leg below keeps it idle for a minute)
+        try:
+            line['secondary'] = {'ns_sgpr': secondary_workload('ns_sgpr', args, dev, peak_tf)}
+        except Exception as ex:  # noqa: BLE001
+            line['secondary'] = {'error': repr(ex)}
     if world == 1 and not args.no_cpu:
         r = time_cpu(w, budget_s=10.0, want_floor=True)
         line['cpu_baseline'] = {'value': r['value'], 'unit': 'rows/s', 'cores': r['cores'],
                                 'threads_available': r['threads_available'], 'kind': r['kind'],
                                 'sample': r['sample']}
-        if args.workload == 'cfg3_sdgpr' and not args.no_secondary:
-            try:
-                line['secondary'] = {'ns_sgpr': secondary_workload('ns_sgpr', args, dev, peak_tf)}
-            except Exception as ex:  # noqa: BLE001
-                line['secondary'] = {'error': repr(ex)}
         try:
             tol = 1e-6 if pr == ops.F64 else 1e-3
             par = gpu_parity(w, r['last'], args.prec, dev, tol)

@@ -401,7 +401,11 @@ class SGPLVM(Base_SGPLVM):
             add['gx1'], add['gx2'] = _zeros(dev, N, Q), _zeros(dev, N, Q)
             for k in ('logZ', 'dsn', 'phi_cav', 'phi_post'):
                 add[k] = _zeros(dev, 1)
+        # full batch: the x1 / x2 gradients are sharded with the rows -> gathered, not all-reduced
+        gx = (add.pop('gx1'), add.pop('gx2')) if sel is None else None
         add = dist.allreduce_dict(add)
+        if gx is not None:
+            add['gx1'], add['gx2'] = dist.gather_rows(gx[0], N), dist.gather_rows(gx[1], N)
         tail = L._tail_mc if prop_mode == PROP_MC else L._tail_mm
         grads = tail(_get_stats(add, 's_'), alpha)
         if self.lik_layer.has_sn:

@@ -95,7 +95,11 @@ class SGPLVM(Base_SGPLVM):
             add['gx1'], add['gx2'] = _zeros(dev, N, Q), _zeros(dev, N, Q)
             for k in ('ll', 'dsn', 'klx'):
                 add[k] = _zeros(dev, 1)
+        # full batch: the x1 / x2 gradients are sharded with the rows -> gathered, not all-reduced
+        gx = (add.pop('gx1'), add.pop('gx2')) if sel is None else None
         add = dist.allreduce_dict(add)
+        if gx is not None:
+            add['gx1'], add['gx2'] = dist.gather_rows(gx[0], N), dist.gather_rows(gx[1], N)
         grads = L._tail(_get_stats(add, 's_'), prop_mode != PROP_MC)
         if self.lik_layer.has_sn:
             grads['sn'] = add['dsn'].reshape(())
