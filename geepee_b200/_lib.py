@@ -34,6 +34,11 @@ _SIGS = {
     'gpb_det_pad_operands': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, ctypes.c_int, ctypes.c_int,
                                             c_dp, c_dp, c_dp]),
     'gpb_det_fwd': (ctypes.c_int, [ctypes.c_int] + [c_dp] * 6 + [ctypes.c_int] * 4 + [c_dp] * 5),
+    'gpb_det_tc_available': (ctypes.c_int, []),
+    'gpb_det_tc_bu_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'gpb_det_tc_zs_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    'gpb_det_tc_prep': (ctypes.c_int, [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp]),
+    'gpb_det_fwd_tc': (ctypes.c_int, [c_dp] * 6 + [ctypes.c_int] * 4 + [c_dp] * 5),
     'gpb_spd_inverse': (ctypes.c_int, [c_dp, ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp]),
     'gpb_probit_lik': (ctypes.c_int, [c_dp] * 5 + [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long,
                                                ctypes.c_int] + [c_dp, c_dp, c_dp, c_dp, ctypes.c_size_t, c_dp]),

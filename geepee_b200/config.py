@@ -18,6 +18,10 @@ DEFAULT_PREC = 'fp64'
 DET_SAVE_BYTES = 8 << 30
 DET_MIN_CHUNK_ROWS = 4096
 
+# fp32-psi mode: deterministic-layer forward on the 5th-generation tensor cores (tcgen05, 3xTF32; csrc/gpb_umma.cuh)
+# instead of the SIMT fp32 kernel
+DET_FP32_TENSOR_CORES = True
+
 # replicated M x M tails: capture each phase in a CUDA graph after this many eager calls
 # (tailgraph.py); GPB_TAIL_GRAPHS=0 in the environment disables capture
 TAIL_GRAPHS = True

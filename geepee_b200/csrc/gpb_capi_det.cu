@@ -1,5 +1,6 @@
 // gpb_capi_det.cu -- deterministic-input layer entry points (a5, a8).
 #include "gpb_common.cuh"
+#include "gpb_umma.cuh"
 
 namespace {
 
@@ -81,6 +82,31 @@ int det_fwd_t(const double* x, const double* z, const double* ls, const double* 
     }
     return fail(GPB_ERR_ARG, "det_fwd: M=%d unsupported (max 512)", M);
 }
+
+// fp32-psi mode on tcgen05 (gpb_umma.cuh): 3xTF32 Kfu . B_d with TMEM accumulators
+#ifndef GPB_CPU_EMU
+template <int MP, int DP>
+int det_fwd_umma_launch(const gpb::DetUmmaArgs& a, void* stream) {
+    typedef gpb::DetUmmaCfg<MP> C;
+    auto kern = gpb::det_fwd_umma_kernel<MP, DP>;
+    int rc = allow_smem(kern, C::smem_bytes(DP));
+    if (rc) return rc;
+    const int ntiles = (int)cdiv(a.n, 128);
+    const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    prof_begin(0, stream);
+    GPB_LAUNCH(kern, dim3(grid), dim3(256), C::smem_bytes(DP), stream, a);
+    prof_end(0, stream);
+    return GPB_CHECK_LAUNCH();
+}
+template <int MP>
+int det_fwd_umma_dp(const gpb::DetUmmaArgs& a, void* stream) {
+    if (a.D <= 4) return det_fwd_umma_launch<MP, 4>(a, stream);
+    if (a.D <= 8) return det_fwd_umma_launch<MP, 8>(a, stream);
+    if (a.D <= 16) return det_fwd_umma_launch<MP, 16>(a, stream);
+    return det_fwd_umma_launch<MP, 32>(a, stream);
+}
+#endif
+int det_tc_dp(int D) { return D <= 4 ? 4 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32)); }
 
 // fp64: tensor-core (DMMA) kernel
 template <int MP>
@@ -253,6 +279,58 @@ int gpb_det_fwd(int prec, const double* x, const double* z, const double* ls, co
     if (D > 32) return fail(GPB_ERR_ARG, "det_fwd: D=%d unsupported (max 32)", D);
     if (prec == GPB_F64) return det_fwd_t<double>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
     return det_fwd_t<float>(x, z, ls, sf, Ap, Bp, n, M, D, Do, mout, vout, Ksave, Tsave, stream);
+}
+
+int gpb_det_tc_available(void) {
+#ifndef GPB_CPU_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
+size_t gpb_det_tc_bu_bytes(int M, int Do) {
+    const int MP = gpb_det_pad_m(M);
+    return MP < 0 ? 0 : sizeof(float) * 2 * (size_t)Do * MP * MP;
+}
+size_t gpb_det_tc_zs_bytes(int M, int D) {
+    const int MP = gpb_det_pad_m(M);
+    return (MP < 0 || D < 1 || D > 32) ? 0 : sizeof(float) * (size_t)MP * det_tc_dp(D);
+}
+int gpb_det_tc_prep(const void* Bp, const double* z, const double* ls, int M, int D, int Do, void* Bu, void* Zs,
+                    void* stream) {
+#ifndef GPB_CPU_EMU
+    const int MP = gpb_det_pad_m(M);
+    if (MP < 0 || !Bp || !z || !ls || !Bu || !Zs || D < 1 || D > 32 || Do < 1)
+        return fail(GPB_ERR_ARG, "det_tc_prep: bad argument");
+    auto kern = gpb::det_umma_prep_kernel;
+    GPB_LAUNCH(kern, dim3(elementwise_grid((long)Do * MP * MP)), dim3(256), 0, stream, (const float*)Bp, z, ls, M, MP,
+               D, det_tc_dp(D), Do, (float*)Bu, (float*)Zs);
+    return GPB_CHECK_LAUNCH();
+#else
+    (void)Bp; (void)z; (void)ls; (void)M; (void)D; (void)Do; (void)Bu; (void)Zs; (void)stream;
+    return fail(GPB_ERR_ARG, "det_tc_prep: tcgen05 path not available in this build");
+#endif
+}
+int gpb_det_fwd_tc(const double* x, const double* ls, const double* sf, const void* Zs, const void* Ap,
+                   const void* Bu, int n, int M, int D, int Do, double* mout, double* vout, void* Ksave,
+                   void* Tsave, void* stream) {
+#ifndef GPB_CPU_EMU
+    if (!x || !ls || !sf || !Zs || !Ap || !Bu || !mout || !vout || !Ksave || !Tsave || n < 1 || D < 1 || D > 32 || Do < 1)
+        return fail(GPB_ERR_ARG, "det_fwd_tc: bad argument");
+    gpb::DetUmmaArgs a;
+    a.x = x; a.ls = ls; a.sf = sf; a.Zs = (const float*)Zs; a.Ap = (const float*)Ap; a.Bu = (const float*)Bu;
+    a.n = n; a.M = M; a.D = D; a.Do = Do; a.mout = mout; a.vout = vout; a.Ksave = (float*)Ksave; a.Tsave = (float*)Tsave;
+    switch (gpb_det_pad_m(M)) {
+        case 128: return det_fwd_umma_dp<128>(a, stream);
+        case 256: return det_fwd_umma_dp<256>(a, stream);
+        case 512: return det_fwd_umma_dp<512>(a, stream);
+    }
+    return fail(GPB_ERR_ARG, "det_fwd_tc: M=%d unsupported (max 512)", M);
+#else
+    (void)x; (void)ls; (void)sf; (void)Zs; (void)Ap; (void)Bu; (void)n; (void)M; (void)D; (void)Do; (void)mout;
+    (void)vout; (void)Ksave; (void)Tsave; (void)stream;
+    return fail(GPB_ERR_ARG, "det_fwd_tc: tcgen05 path not available in this build");
+#endif
 }
 
 size_t gpb_det_bwd_ws_bytes(int n, int M, int D, int Do) {

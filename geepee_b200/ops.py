@@ -8,7 +8,7 @@ import ctypes
 
 import torch
 
-from . import _lib
+from . import _lib, config
 
 F64 = 0
 F32 = 1
@@ -190,6 +190,14 @@ def det_fwd(prec, x, z, ls, sf, opnd, save=True):
         dt = prec_dtype(prec)
         Ks = torch.empty((n, MP), dtype=dt, device=x.device)
         Ts = torch.empty((n, Do, MP), dtype=dt, device=x.device)
+    if prec == F32 and save and config.DET_FP32_TENSOR_CORES and lib.gpb_det_tc_available():
+        # fp32-psi mode on tcgen05: 3xTF32 Kfu . B_d, accumulators in TMEM (csrc/gpb_umma.cuh)
+        Bu = torch.empty(lib.gpb_det_tc_bu_bytes(M, Do) // 4, dtype=torch.float32, device=x.device)
+        Zs = torch.empty(lib.gpb_det_tc_zs_bytes(M, D) // 4, dtype=torch.float32, device=x.device)
+        _chk(lib.gpb_det_tc_prep(_p(opnd.Bp), _p(_c(z)), _p(_c(ls)), M, D, Do, _p(Bu), _p(Zs), _stream(x)), 'det_tc_prep')
+        _chk(lib.gpb_det_fwd_tc(_p(_c(x)), _p(_c(ls)), _p(_c(sf)), _p(Zs), _p(opnd.Ap), _p(Bu), n, M, D, Do,
+                                _p(mout), _p(vout), _p(Ks), _p(Ts), _stream(x)), 'det_fwd_tc')
+        return mout, vout, Ks, Ts
     _chk(lib.gpb_det_fwd(prec, _p(_c(x)), _p(_c(z)), _p(_c(ls)), _p(_c(sf)), _p(opnd.Ap), _p(opnd.Bp),
                          n, M, D, Do, _p(mout), _p(vout), _p(Ks), _p(Ts), _stream(x)), 'det_fwd')
     return mout, vout, Ks, Ts

@@ -112,6 +112,19 @@ int gpb_det_pad_operands(int prec, const double* A, const double* B, int M, int 
 int gpb_det_fwd(int prec, const double* x, const double* z, const double* ls, const double* sf,
                 const void* Ap, const void* Bp, int n, int M, int D, int Do,
                 double* mout, double* vout, void* Ksave, void* Tsave, void* stream);
+/* a5 in fp32-psi mode on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 operand split, fp32
+ *      accumulators in TMEM, B tiles through the TMA engine).  gpb_det_tc_prep turns the padded fp32 B operand and
+ *      the pseudo-inputs into the layouts the kernel consumes (Bu: gpb_det_tc_bu_bytes, Zs: gpb_det_tc_zs_bytes);
+ *      gpb_det_fwd_tc has the semantics of gpb_det_fwd(GPB_F32, ...) with mandatory save buffers.
+ *      gpb_det_tc_available() is 0 in builds without the tensor-core path (the CPU emulator of the tests). */
+int gpb_det_tc_available(void);
+size_t gpb_det_tc_bu_bytes(int M, int Do);
+size_t gpb_det_tc_zs_bytes(int M, int D);
+int gpb_det_tc_prep(const void* Bp, const double* z, const double* ls, int M, int D, int Do, void* Bu, void* Zs,
+                    void* stream);
+int gpb_det_fwd_tc(const double* x, const double* ls, const double* sf, const void* Zs, const void* Ap,
+                   const void* Bu, int n, int M, int D, int Do, double* mout, double* vout, void* Ksave,
+                   void* Tsave, void* stream);
 /* a8 (per-row part): aep_models.py:452-460,490 + kernels.py:381-399 (kfucompDer), vfe twin
  *      vfe_models.py:498-506.  dm, dv are the SCALED upstream gradients.
  *      -> dA[Do,M] = sum_n dm kfu ; dzu[M,D] ; dl[D] (wrt lengthscale) ; dsf2[1] (wrt variance) */
