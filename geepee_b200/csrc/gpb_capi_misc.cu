@@ -87,11 +87,19 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
 int gpb_spd_inverse(const double* A, int batch, int M, double* Ainv, double* logdet, void* stream) {
     if (!A || !Ainv || !logdet || batch < 1 || M < 1) return fail(GPB_ERR_ARG, "spd_inverse: bad argument");
     if (M > 512) return fail(GPB_ERR_ARG, "spd_inverse: M=%d unsupported (max 512)", M);
+    if (M <= 256) {      // register-resident variant
+        auto k256 = gpb::spd_inverse256_kernel<gpb::kInvCluster>;
+        const size_t smem256 = gpb::SpdInv256Cfg<gpb::kInvCluster>::smem_bytes;
+        int rc256 = allow_smem(k256, smem256);
+        if (rc256) return rc256;
+        GPB_LAUNCH(k256, dim3(batch * gpb::kInvCluster), dim3(512), smem256, stream, A, M, Ainv, logdet);
+        return GPB_CHECK_LAUNCH();
+    }
     auto kern = gpb::spd_inverse_kernel<32>;
     const size_t smem = gpb::SpdInvCfg<32>::smem_bytes(M);
     int rc = allow_smem(kern, smem);
     if (rc) return rc;
-    GPB_LAUNCH(kern, dim3(batch * gpb::kTailCluster), dim3(512), smem, stream, A, M, Ainv, logdet);
+    GPB_LAUNCH(kern, dim3(batch * gpb::kInvCluster), dim3(512), smem, stream, A, M, Ainv, logdet);
     return GPB_CHECK_LAUNCH();
 }
 

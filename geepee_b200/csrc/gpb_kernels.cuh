@@ -3014,156 +3014,407 @@ GPB_KERNEL void mm_final_kernel(const double* __restrict__ colsum /*[Do*M + M*Q]
 // a3 / a4 / a10 building block: batched inverse + log-determinant of SPD M x M matrices
 // (Kuu, Kuu^-1 + theta_1, Kuu^-1 + beta theta_1: base_models.py:464,471,476, aep_models.py:68,78,91,
 // 525,533 -- np.linalg.inv / slogdet in the reference).  fp64 throughout.
-// One thread-block CLUSTER per matrix (kTailCluster CTAs, hardware cluster barrier); blocked
+// One thread-block CLUSTER per matrix (kInvCluster CTAs, hardware cluster barrier); blocked
 // Gauss-Jordan without pivoting (valid for SPD), NB = 32:
 //   per block step k:   D = A_kk (Schur complement so far);  logdet += log det D
-//     every CTA:   invert D in shared memory (unblocked GJ), stage the row panel R = A[k,:]
-//     CTA r, its rows i not in k:   P_i = A_ik D^-1;  A_ij -= P_i R_j (j not in k);  A_ik = -P_i
-//     owner of the k rows:          A_kj = D^-1 R_j (j not in k);  A_kk = D^-1
-// The matrix stays in global memory (L2 resident: 0.5 MB at M = 256); a step reads the panel
-// once into shared memory and streams the CTA's row slice through an 8 x 4 register tile per
-// thread (512 threads).  Two cluster barriers per step.  After M/NB steps the work matrix holds A^-1.
+//     every CTA:   stage the row panel R = A[k,:] and its own column block A[rows,k] (cp.async),
+//                  invert D in shared memory (unblocked GJ, 4 warps, reciprocal by Newton iteration)
+//     CTA r, its rows i not in k:   P_i = A_ik D^-1;  A_ij -= P_i R_j (j not in k; FP64 tensor cores);  A_ik = -P_i
+//     column slice r of the k rows: A_kj = D^-1 R_j (j not in k);  A_kk = D^-1
+// The matrix stays in global memory (L2 resident: 0.5 MB at M = 256); a step reads the panel once into shared
+// memory and applies the rank-NB update to the CTA's row slice with DMMA 8x8x4 (P: A fragments, R: B fragments;
+// strides = 4 / 8 mod 16 doubles keep both fragment loads conflict free).  Two cluster barriers per step.
+// After M/NB steps the work matrix holds A^-1.
+#ifndef GPB_CPU_EMU
+constexpr int kInvCluster = 8;
+GPB_DEVICE double pivot_rcp(double x) {     // 1/x off the long IEEE-division path: the pivots form a serial chain
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+#else
+constexpr int kInvCluster = 1;
+static inline double pivot_rcp(double x) { return 1.0 / x; }
+#endif
+
 template <int NB>
 struct SpdInvCfg {
+    static constexpr int PS = NB + 4;                       // P / column-block row stride (= 4 mod 16)
+    static int rows8(int M) { return ((M + kInvCluster - 1) / kInvCluster + 7) / 8 * 8; }
+    static int rs(int M) { return (M + 15) / 16 * 16 + 8; } // panel row stride (= 8 mod 16)
     static size_t smem_bytes(int M) {
-        const int rows = (M + kTailCluster - 1) / kTailCluster;
-        const int rows8 = (rows + 7) / 8 * 8;
-        return sizeof(double) * (2 * (size_t)NB * (NB + 1) + (size_t)NB * M + (size_t)rows8 * NB + 64);
+        return sizeof(double) * (2 * (size_t)NB * (NB + 1) + (size_t)NB * rs(M) + 2 * (size_t)rows8(M) * PS + 64);
     }
 };
 
 template <int NB>
-GPB_KERNEL void GPB_CLUSTER(kTailCluster) GPB_LAUNCH_BOUNDS(512) spd_inverse_kernel(
+GPB_KERNEL void GPB_CLUSTER(kInvCluster) GPB_LAUNCH_BOUNDS(512) spd_inverse_kernel(
     const double* __restrict__ A, int M, double* __restrict__ W /* [batch, M, M]: out = A^-1 */,
     double* __restrict__ logdet /* [batch] */) {
     GPB_DYN_SMEM(smem);
-    constexpr int NT = 512, TC = 4;            // 16 warps per CTA: the kernel is latency bound
-    const int tid = threadIdx.x;
+    constexpr int NT = 512, NW = NT / 32, PS = SpdInvCfg<NB>::PS, TB = 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int rank = cluster_rank();
-    const int mat = blockIdx.x / kTailCluster;
-    const int rows_per = (M + kTailCluster - 1) / kTailCluster;
-    const int row_lo = rank * rows_per;
+    const int mat = blockIdx.x / kInvCluster;
+    const int rows_per = (M + kInvCluster - 1) / kInvCluster;
+    const int row_lo = rank * rows_per < M ? rank * rows_per : M;
     const int row_hi = (row_lo + rows_per) < M ? (row_lo + rows_per) : M;
-    const int nrows = row_hi > row_lo ? row_hi - row_lo : 0;
-    const int rows8 = (rows_per + 7) / 8 * 8;
+    const int nrows = row_hi - row_lo;
+    const int rows8 = (rows_per + 7) / 8 * 8, RS = (M + 15) / 16 * 16 + 8;   // = SpdInvCfg::rows8 / rs
     double* D = (double*)smem;                 // [NB][NB+1]
     double* D2 = D + NB * (NB + 1);            // [NB][NB+1]  ping-pong twin of D
-    double* R = D2 + NB * (NB + 1);            // [NB][M]   row panel (original values)
-    double* P = R + (size_t)NB * M;            // [rows8][NB]
-    double* s_ld = P + (size_t)rows8 * NB;     // [1]
+    double* R = D2 + NB * (NB + 1);            // [NB][RS]    row panel (values before the step)
+    double* P = R + (size_t)NB * RS;           // [rows8][PS] A_ik D^-1
+    double* Ac = P + (size_t)rows8 * PS;       // [rows8][PS] A_ik (values before the step)
+    double* s_ld = Ac + (size_t)rows8 * PS;    // [1]
     double* s_piv = s_ld + 8;                  // [NB]
     const double* Am = A + (size_t)mat * M * M;
     double* Wm = W + (size_t)mat * M * M;
+    const bool even = (M & 1) == 0 && ((size_t)Wm & 15) == 0;   // rows 16-byte aligned: 16-byte asynchronous copies
     // work copy of this CTA's rows
     for (long i = tid; i < (long)nrows * M; i += NT) Wm[(long)row_lo * M + i] = Am[(long)row_lo * M + i];
     if (tid == 0) s_ld[0] = 0.0;
     cluster_sync();
     for (int k0 = 0; k0 < M; k0 += NB) {
         const int nb = (M - k0) < NB ? (M - k0) : NB;
-        // ---- warp 0: load + invert the diagonal block (one row per lane, warp barriers only);
-        //      warps 1..7: stage the row panel meanwhile ----
+        // ---- stage the row panel (rows past nb zero) and this CTA's column block ----
+        if (even) {
+            const int Mh = M >> 1;
+            for (int i = tid; i < NB * Mh; i += NT) {
+                const int c = i / Mh, jj = 2 * (i - c * Mh);
+                cp_async16_zfill(&R[c * RS + jj], &Wm[(long)(k0 + (c < nb ? c : 0)) * M + jj], c < nb);
+            }
+        } else {
+            for (int i = tid; i < NB * M; i += NT) {
+                const int c = i / M, jj = i - c * M;
+                cp_async8_zfill(&R[c * RS + jj], &Wm[(long)(k0 + (c < nb ? c : 0)) * M + jj], c < nb);
+            }
+        }
+        for (int i = tid; i < rows8 * NB; i += NT) {
+            const int r = i / NB, c = i - r * NB;
+            const bool ok = r < nrows && c < nb;
+            cp_async8_zfill(&Ac[r * PS + c], &Wm[ok ? (long)(row_lo + r) * M + k0 + c : 0], ok);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        sync_threads();
+        // ---- warps 0-3 invert the diagonal block: lane = row, warp = group of NB/4 columns; ping-pong between
+        //      D and D2 (a Gauss-Jordan step reads the old block and writes the new one), one 128-thread named
+        //      barrier per pivot.  The chain of M pivots is the serial part of the whole inversion: the
+        //      reciprocal is a Newton iteration and the logs of the pivots are taken afterwards. ----
         if (tid < 128) {
-            // Warps 0-3 invert the diagonal block: lane = row, warp = group of NB/4 columns;
-            // ping-pong between D and D2 (a Gauss-Jordan step reads the old block and writes the
-            // new one), one 128-thread named barrier per pivot.  The chain of M pivots is the
-            // serial part of the whole inversion, so the logs of the pivots are taken afterwards.
             constexpr int CG = NB / 4;
             const int a = tid & 31, cg0 = (tid >> 5) * CG;
             double* Dc = D;
             double* Dn = D2;
             for (int b = cg0; b < cg0 + CG; b++)
-                Dc[a * (NB + 1) + b] = (a < nb && b < nb) ? Wm[(long)(k0 + a) * M + k0 + b] : (a == b ? 1.0 : 0.0);
+                Dc[a * (NB + 1) + b] = (a < nb && b < nb) ? R[a * RS + k0 + b] : (a == b ? 1.0 : 0.0);
             sync_group<1, 128>();
             for (int j = 0; j < nb; j++) {
                 const double piv = Dc[j * (NB + 1) + j];
-                const double ip = 1.0 / piv;
                 const double aj = Dc[a * (NB + 1) + j];
+                double jb[CG], ab[CG];
+                GPB_UNROLL
+                for (int bb = 0; bb < CG; bb++) {
+                    jb[bb] = Dc[j * (NB + 1) + cg0 + bb];
+                    ab[bb] = Dc[a * (NB + 1) + cg0 + bb];
+                }
+                const double ip = pivot_rcp(piv);
                 const double f = (a == j) ? 0.0 : aj * ip;
                 if (tid == j) s_piv[j] = piv;
                 GPB_UNROLL
                 for (int bb = 0; bb < CG; bb++) {
                     const int b = cg0 + bb;
-                    const double jb = Dc[j * (NB + 1) + b];
-                    const double v = (a == j) ? jb * ip : Dc[a * (NB + 1) + b] - f * jb;
+                    const double v = (a == j) ? jb[bb] * ip : ab[bb] - f * jb[bb];
                     Dn[a * (NB + 1) + b] = (b == j) ? ((a == j) ? ip : -aj * ip) : v;
                 }
                 sync_group<1, 128>();
-                double* t = Dc; Dc = Dn; Dn = t;
+                double* tp = Dc; Dc = Dn; Dn = tp;
             }
-            if (Dc != D)                           // odd number of pivots: result sits in D2
+            if (Dc != D) {                         // odd number of pivots: result sits in D2
                 for (int b = cg0; b < cg0 + CG; b++) D[a * (NB + 1) + b] = Dc[a * (NB + 1) + b];
+            }
             if (tid < 32) {
                 double l = tid < nb ? log(s_piv[tid]) : 0.0;
                 l = warp_sum(l);
                 if (tid == 0) s_ld[0] += l;
             }
-        } else {
-            for (int i = tid - 128; i < nb * M; i += NT - 128) {
-                const int c = i / M, jj = i - c * M;
-                R[c * M + jj] = Wm[(long)(k0 + c) * M + jj];
-            }
         }
         sync_threads();
-        // ---- P = A[rows, k] D^-1 for this CTA's rows ----
+        // ---- P = A[rows, k] D^-1 for this CTA's rows (zero rows: the k rows themselves and the padding) ----
         for (int i = tid; i < rows8 * NB; i += NT) {
             const int r = i / NB, c = i - r * NB;
             const int row = row_lo + r;
             double acc = 0;
-            if (r < nrows && c < nb && (row < k0 || row >= k0 + nb))
-                for (int b = 0; b < nb; b++) acc += Wm[(long)row * M + k0 + b] * D[b * (NB + 1) + c];
-            P[r * NB + c] = acc;
+            if (r < nrows && c < nb && (row < k0 || row >= k0 + nb)) {
+                GPB_UNROLL_N(8)
+                for (int b = 0; b < nb; b++) acc += Ac[r * PS + b] * D[b * (NB + 1) + c];
+            }
+            P[r * PS + c] = acc;
         }
         cluster_sync();            // every CTA holds R, D^-1, P: the k rows / k columns may now change
-        // ---- trailing update of this CTA's rows: 8 x 4 register tiles ----
-        const int tiles_c = (M + TC - 1) / TC, tiles_r = rows8 / 8;
-        for (int t = tid; t < tiles_r * tiles_c; t += NT) {
-            const int tr = t / tiles_c, tc = t - tr * tiles_c;
-            const int r0 = tr * 8;           // rows r0..r0+7, columns tc + b * tiles_c (lane-contiguous)
-            double acc[8][TC];
+        // ---- trailing update of this CTA's rows on the FP64 tensor cores: 8 x 8 tiles, TB per warp at a time
+        //      (their old values are fetched before the MMAs) ----
+        const int tiles_r = rows8 / 8, tiles_c = (M + 7) / 8, ntile = tiles_r * tiles_c;
+        for (int tile0 = warp; tile0 < ntile; tile0 += NW * TB) {
+            double w0[TB], w1[TB], c0[TB], c1[TB];
+            int rl[TB], col[TB];
+            bool rok[TB];
             GPB_UNROLL
-            for (int a = 0; a < 8; a++)
-                GPB_UNROLL
-                for (int b = 0; b < TC; b++) acc[a][b] = 0;
-            GPB_UNROLL_N(4)
-            for (int c = 0; c < nb; c++) {
-                double pv[8], rv[TC];
-                GPB_UNROLL
-                for (int a = 0; a < 8; a++) pv[a] = P[(r0 + a) * NB + c];
-                GPB_UNROLL
-                for (int b = 0; b < TC; b++) rv[b] = (tc + b * tiles_c) < M ? R[c * M + tc + b * tiles_c] : 0.0;
-                GPB_UNROLL
-                for (int a = 0; a < 8; a++)
-                    GPB_UNROLL
-                    for (int b = 0; b < TC; b++) acc[a][b] += pv[a] * rv[b];
+            for (int u = 0; u < TB; u++) {
+                const int tile = tile0 + u * NW;
+                const bool tv = tile < ntile;
+                const int tr = tv ? tile % tiles_r : 0, tc = tv ? tile / tiles_r : 0;
+                rl[u] = tr * 8 + g;
+                col[u] = tc * 8 + 2 * t4;
+                const int row = row_lo + rl[u];
+                rok[u] = tv && rl[u] < nrows && (row < k0 || row >= k0 + nb);
+                w0[u] = (rok[u] && col[u] < M) ? Wm[(long)row * M + col[u]] : 0.0;
+                w1[u] = (rok[u] && col[u] + 1 < M) ? Wm[(long)row * M + col[u] + 1] : 0.0;
+                c0[u] = 0.0;
+                c1[u] = 0.0;
             }
             GPB_UNROLL
-            for (int a = 0; a < 8; a++) {
-                const int row = row_lo + r0 + a;
-                if (r0 + a >= nrows || (row >= k0 && row < k0 + nb)) continue;
+            for (int ks = 0; ks < NB / 4; ks++) {
                 GPB_UNROLL
-                for (int b = 0; b < TC; b++) {
-                    const int col = tc + b * tiles_c;
-                    if (col >= M) continue;
-                    if (col >= k0 && col < k0 + nb) Wm[(long)row * M + col] = -P[(r0 + a) * NB + (col - k0)];
-                    else Wm[(long)row * M + col] -= acc[a][b];
+                for (int u = 0; u < TB; u++) {
+                    const double pa = P[rl[u] * PS + 4 * ks + t4];
+                    const double rb = R[(4 * ks + t4) * RS + (col[u] - 2 * t4) + g];
+                    dmma(c0[u], c1[u], pa, rb);
+                }
+            }
+            GPB_UNROLL
+            for (int u = 0; u < TB; u++) {
+                if (!rok[u]) continue;
+                const long base = (long)(row_lo + rl[u]) * M;
+                if (col[u] < M) {
+                    const int cc = col[u];
+                    Wm[base + cc] = (cc >= k0 && cc < k0 + nb) ? -P[rl[u] * PS + cc - k0] : w0[u] - c0[u];
+                }
+                if (col[u] + 1 < M) {
+                    const int cc = col[u] + 1;
+                    Wm[base + cc] = (cc >= k0 && cc < k0 + nb) ? -P[rl[u] * PS + cc - k0] : w1[u] - c1[u];
                 }
             }
         }
         // ---- the k rows themselves: A_kj = D^-1 R_j, A_kk = D^-1.  Split by COLUMN slices over
         //      the cluster (not by row ownership), so that no CTA is a straggler at the barrier ----
-        const int ncol = row_hi - row_lo;          // column slice of this CTA = its row range
+        const int ncol = nrows;                    // column slice of this CTA = its row range
         for (int i = tid; i < nb * ncol; i += NT) {
             const int a = i / ncol, j = row_lo + (i - a * ncol);
-            const int row = k0 + a;
             double v;
             if (j >= k0 && j < k0 + nb) v = D[a * (NB + 1) + (j - k0)];
             else {
                 v = 0;
-                for (int c = 0; c < nb; c++) v += D[a * (NB + 1) + c] * R[c * M + j];
+                GPB_UNROLL_N(8)
+                for (int c = 0; c < nb; c++) v += D[a * (NB + 1) + c] * R[c * RS + j];
             }
-            Wm[(long)row * M + j] = v;
+            Wm[(long)(k0 + a) * M + j] = v;
         }
         cluster_sync();            // step complete everywhere before the next panel is staged
+    }
+    if (rank == 0 && tid == 0) logdet[mat] = s_ld[0];
+}
+
+// M <= 256: the same blocked Gauss-Jordan with the matrix held in REGISTERS.  The problem is padded to 256 x 256 with
+// an identity block and cut into 8 panels of 32 rows; a CTA holds 256 / CL panel rows as DMMA accumulator tiles
+// (8 x 8, 16 warps, static tile -> warp map), so a step is
+//   stage panel k from global (cp.async) -> invert D (4 warps) -> P rows: D^-1 (rows of panel k) or -A_ik D^-1 (others)
+//   -> tile += P R on the FP64 tensor cores (panel-k rows start from 0; k columns take P itself)
+//   -> the holder of panel k + 1 writes those rows back -> ONE cluster barrier.
+// Nothing but the next panel travels through global memory / L2, and the pivot chain computes the next pivot
+// speculatively so that only reciprocal + one FMA separate two pivots.  CL = 8 on the GPU (4 row tiles per CTA),
+// 1 in the CPU emulator (one block holds all 32 row tiles).
+template <int CL>
+struct SpdInv256Cfg {
+    static constexpr int NB = 32, MP = 256, PS = NB + 4, RS = MP + 8, RPC = MP / CL;
+    static constexpr size_t smem_bytes = sizeof(double) * (2 * NB * (NB + 1) + NB * RS + 2 * RPC * PS + 64);
+};
+
+template <int CL>
+GPB_KERNEL void GPB_CLUSTER(CL) GPB_LAUNCH_BOUNDS(512) spd_inverse256_kernel(
+    const double* __restrict__ A, int M, double* __restrict__ W /* [batch, M, M]: out = A^-1 */,
+    double* __restrict__ logdet /* [batch] */) {
+    typedef SpdInv256Cfg<CL> C;
+    GPB_DYN_SMEM(smem);
+    constexpr int NB = C::NB, NT = 512, NW = NT / 32, PS = C::PS, RS = C::RS, RPC = C::RPC;
+    constexpr int TR = RPC / 8, TPW = TR * (C::MP / 8) / NW;       // row tiles per CTA, tiles per warp
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int rank = cluster_rank();
+    const int mat = blockIdx.x / CL;
+    const int row_base = rank * RPC;
+    double* D = (double*)smem;                 // [NB][NB+1]
+    double* D2 = D + NB * (NB + 1);            // [NB][NB+1]  ping-pong twin of D
+    double* R = D2 + NB * (NB + 1);            // [NB][RS]    row panel k (values before the step)
+    double* P = R + (size_t)NB * RS;           // [RPC][PS]
+    double* Ac = P + (size_t)RPC * PS;         // [RPC][PS]   A_ik (values before the step)
+    double* s_ld = Ac + (size_t)RPC * PS;      // [1]
+    double* s_piv = s_ld + 8;                  // [NB]
+    const double* Am = A + (size_t)mat * M * M;
+    double* Wm = W + (size_t)mat * M * M;
+    const bool even = (M & 1) == 0 && ((size_t)Wm & 15) == 0 && ((size_t)Am & 15) == 0;
+    const int nsteps = (M + NB - 1) / NB;
+    const int M8 = (M + 7) & ~7;
+    const bool cta_live = row_base < M;
+
+    // tile i of this warp: rows trow[i] + g (CTA-local), columns tcol[i] + 2 t4, + 1
+    double c0[TPW], c1[TPW];
+    GPB_UNROLL
+    for (int i = 0; i < TPW; i++) {
+        const int tile = warp + NW * i;
+        const int row = row_base + (tile % TR) * 8 + g, col = (tile / TR) * 8 + 2 * t4;
+        c0[i] = (row < M && col < M) ? Am[(long)row * M + col] : (row == col ? 1.0 : 0.0);
+        c1[i] = (row < M && col + 1 < M) ? Am[(long)row * M + col + 1] : (row == col + 1 ? 1.0 : 0.0);
+    }
+    if (tid == 0) s_ld[0] = 0.0;
+    for (int k = 0; k < nsteps; k++) {
+        const int k0 = k * NB;
+        if (cta_live) {
+            // ---- stage panel k (rows / columns past M: the identity padding) ----
+            const double* src = k == 0 ? Am : Wm;
+            if (even) {
+                const int U = M8 >> 1;
+                for (int i = tid; i < NB * U; i += NT) {
+                    const int c = i / U, jj = 2 * (i - c * U), row = k0 + c;
+                    if (row < M) cp_async16_zfill(&R[c * RS + jj], &src[jj < M ? (long)row * M + jj : 0], jj < M);
+                    else {
+                        R[c * RS + jj] = jj == row ? 1.0 : 0.0;
+                        R[c * RS + jj + 1] = jj + 1 == row ? 1.0 : 0.0;
+                    }
+                }
+            } else {
+                for (int i = tid; i < NB * M8; i += NT) {
+                    const int c = i / M8, jj = i - c * M8, row = k0 + c;
+                    if (row < M) cp_async8_zfill(&R[c * RS + jj], &src[jj < M ? (long)row * M + jj : 0], jj < M);
+                    else R[c * RS + jj] = jj == row ? 1.0 : 0.0;
+                }
+            }
+            cp_async_commit();
+            // ---- this CTA's column block k, out of the register tiles ----
+            GPB_UNROLL
+            for (int i = 0; i < TPW; i++) {
+                const int tile = warp + NW * i;
+                const int tc = tile / TR, rl = (tile % TR) * 8 + g;
+                if ((tc >> 2) == k) {
+                    Ac[rl * PS + tc * 8 + 2 * t4 - k0] = c0[i];
+                    Ac[rl * PS + tc * 8 + 2 * t4 + 1 - k0] = c1[i];
+                }
+            }
+            cp_async_wait<0>();
+            sync_threads();
+            // ---- warps 0-3 invert the diagonal block: lane = row, warp = group of NB/4 columns; ping-pong
+            //      between D and D2, one 128-thread named barrier per pivot.  Every thread forms the next pivot
+            //      itself from the old block, so the serial chain per pivot is reciprocal + one FMA. ----
+            if (tid < 128) {
+                constexpr int CG = NB / 4;
+                const int a = tid & 31, cg0 = (tid >> 5) * CG;
+                double* Dc = D;
+                double* Dn = D2;
+                for (int b = cg0; b < cg0 + CG; b++)       // (the panel is staged up to column M8 only)
+                    Dc[a * (NB + 1) + b] = (k0 + a < M && k0 + b < M) ? R[a * RS + k0 + b] : (a == b ? 1.0 : 0.0);
+                sync_group<1, 128>();
+                double piv = Dc[0];
+                for (int j = 0; j < NB; j++) {
+                    // row a != j:  new = old - (a_aj a_jb) / piv ;  row j:  new = a_jb / piv  (multiplier -1, old 0);
+                    // column j is overwritten afterwards by the thread that holds it
+                    const bool isj = a == j;
+                    const double aj = Dc[a * (NB + 1) + j];
+                    const double mj = isj ? -1.0 : aj, keep = isj ? 0.0 : 1.0;
+                    double tj[CG], ab[CG];
+                    GPB_UNROLL
+                    for (int bb = 0; bb < CG; bb++) {
+                        tj[bb] = mj * Dc[j * (NB + 1) + cg0 + bb];
+                        ab[bb] = keep * Dc[a * (NB + 1) + cg0 + bb];
+                    }
+                    const int j1 = j + 1 < NB ? j + 1 : j;
+                    const double n11 = Dc[j1 * (NB + 1) + j1];
+                    const double nt = Dc[j1 * (NB + 1) + j] * Dc[j * (NB + 1) + j1];
+                    const double ip = pivot_rcp(piv);
+                    if (tid == j) s_piv[j] = piv;
+                    piv = fma(-nt, ip, n11);                      // pivot j + 1
+                    GPB_UNROLL
+                    for (int bb = 0; bb < CG; bb++) Dn[a * (NB + 1) + cg0 + bb] = fma(-tj[bb], ip, ab[bb]);
+                    if (j >= cg0 && j < cg0 + CG) Dn[a * (NB + 1) + j] = isj ? ip : -aj * ip;
+                    sync_group<1, 128>();
+                    double* tp = Dc; Dc = Dn; Dn = tp;
+                }
+                // NB is even: the result sits in D
+                if (tid < 32) {
+                    double l = log(s_piv[tid]);
+                    l = warp_sum(l);
+                    if (tid == 0) s_ld[0] += l;
+                }
+            }
+            sync_threads();
+            // ---- P rows: D^-1 for the rows of panel k, -A_ik D^-1 for the others (DMMA), 0 for the padding ----
+            for (int tile = warp; tile < TR * (NB / 8); tile += NW) {
+                const int rl0 = (tile % TR) * 8, cb = (tile / TR) * 8;
+                const int row0 = row_base + rl0;
+                double p0 = 0.0, p1 = 0.0;
+                if (row0 < M8) {
+                    if (row0 >= k0 && row0 < k0 + NB) {
+                        p0 = D[(row0 + g - k0) * (NB + 1) + cb + 2 * t4];
+                        p1 = D[(row0 + g - k0) * (NB + 1) + cb + 2 * t4 + 1];
+                    } else {
+                        GPB_UNROLL
+                        for (int ks = 0; ks < NB / 4; ks++)
+                            dmma(p0, p1, -Ac[(rl0 + g) * PS + 4 * ks + t4], D[(4 * ks + t4) * (NB + 1) + cb + g]);
+                        if (row0 + g >= M) {
+                            p0 = 0.0;
+                            p1 = 0.0;
+                        }
+                    }
+                }
+                P[(rl0 + g) * PS + cb + 2 * t4] = p0;
+                P[(rl0 + g) * PS + cb + 2 * t4 + 1] = p1;
+            }
+            sync_threads();
+            // ---- tiles += P R on the FP64 tensor cores ----
+            GPB_UNROLL
+            for (int i = 0; i < TPW; i++) {
+                const int tile = warp + NW * i;
+                const int tc = tile / TR, rl0 = (tile % TR) * 8;
+                if (row_base + rl0 >= M || tc * 8 >= M) continue;           // padding tile (warp uniform)
+                if (row_base + rl0 >= k0 && row_base + rl0 < k0 + NB) {
+                    c0[i] = 0.0;
+                    c1[i] = 0.0;
+                }
+                GPB_UNROLL
+                for (int ks = 0; ks < NB / 4; ks++)
+                    dmma(c0[i], c1[i], P[(rl0 + g) * PS + 4 * ks + t4], R[(4 * ks + t4) * RS + tc * 8 + g]);
+                if ((tc >> 2) == k) {
+                    c0[i] = P[(rl0 + g) * PS + tc * 8 + 2 * t4 - k0];
+                    c1[i] = P[(rl0 + g) * PS + tc * 8 + 2 * t4 + 1 - k0];
+                }
+            }
+            // ---- the holder of panel k + 1 publishes those rows ----
+            if (k + 1 < nsteps) {
+                GPB_UNROLL
+                for (int i = 0; i < TPW; i++) {
+                    const int tile = warp + NW * i;
+                    const int row = row_base + (tile % TR) * 8 + g, col = (tile / TR) * 8 + 2 * t4;
+                    if (row >= k0 + NB && row < k0 + 2 * NB && row < M) {
+                        if (col < M) Wm[(long)row * M + col] = c0[i];
+                        if (col + 1 < M) Wm[(long)row * M + col + 1] = c1[i];
+                    }
+                }
+            }
+        }
+        cluster_barrier();
+    }
+    GPB_UNROLL
+    for (int i = 0; i < TPW; i++) {
+        const int tile = warp + NW * i;
+        const int row = row_base + (tile % TR) * 8 + g, col = (tile / TR) * 8 + 2 * t4;
+        if (row < M) {
+            if (col < M) Wm[(long)row * M + col] = c0[i];
+            if (col + 1 < M) Wm[(long)row * M + col + 1] = c1[i];
+        }
     }
     if (rank == 0 && tid == 0) logdet[mat] = s_ld[0];
 }

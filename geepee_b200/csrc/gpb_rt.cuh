@@ -32,11 +32,13 @@ GPB_DEVICE void sync_threads() { __syncthreads(); }
 // thread-block cluster (sm_90+): hardware barrier over the CTAs of a cluster; global-memory
 // writes made before it are visible to the whole cluster after it
 #define GPB_CLUSTER(n) __cluster_dims__(n, 1, 1)
-constexpr int kTailCluster = 4;
 GPB_DEVICE void cluster_sync() {
     __threadfence();
     cooperative_groups::this_cluster().sync();
 }
+// the cluster barrier alone: arrive has release and wait has acquire semantics at cluster scope, which already
+// orders the global-memory accesses of the cluster's threads
+GPB_DEVICE void cluster_barrier() { cooperative_groups::this_cluster().sync(); }
 GPB_DEVICE int cluster_rank() { return (int)cooperative_groups::this_cluster().block_rank(); }
 GPB_DEVICE void sync_warp() { __syncwarp(); }
 // named barrier over the first `nthreads` threads of the block (a multiple of 32; all of them call it)
@@ -134,8 +136,8 @@ namespace gpb {
 static inline void sync_threads() { gpb_emu::barrier(); }
 // the emulator runs blocks one after another: cluster kernels are built with clusters of ONE block
 #define GPB_CLUSTER(n)
-constexpr int kTailCluster = 1;
 static inline void cluster_sync() { gpb_emu::barrier(); }
+static inline void cluster_barrier() { gpb_emu::barrier(); }
 static inline int cluster_rank() { return 0; }
 static inline void sync_warp() { (void)gpb_emu::shfl_xor_f64(0.0, 0); }   // warp rendezvous
 template <int ID, int NTHREADS>
