@@ -1,6 +1,7 @@
 // gpb_capi_mm.cu -- moment-matched (uncertain-input) layer entry points (a2+a6, a2+a9).
 #include "gpb_common.cuh"
 #include "gpb_pairsx.cuh"
+#include "gpb_umma.cuh"
 
 namespace {
 
@@ -15,6 +16,8 @@ struct MMPlan {
     // fp64 narrow layers (Do <= 4, Qt <= 4): pair kernels with the exponent on the FP64 tensor cores
     int xpath, x_nchunks, x_nsplit, x_rows_per_split, x_rlg;
     long x_npad;
+    // fp32 narrow layers, forward: exponent GEMM on tcgen05 (gpb_umma.cuh), K = 8 tc_ks features
+    int tc, tc_ks;
     // workspace byte offsets are carved in order by mm_carve
 };
 // row splits of the tensor-exponent pair kernels: two resident blocks per SM; take the split count (<= 48,
@@ -95,6 +98,11 @@ MMPlan mm_plan(int tbytes, int n, int M, int Q, int Do, int backward) {
         p.x_npad = cdiv(n, 64) * 64;
         mmx_splits(n, p.x_nchunks, &p.x_nsplit, &p.x_rows_per_split);
     }
+    p.tc = 0;
+    p.tc_ks = (2 * Q + 1 + 7) / 8;
+#ifndef GPB_CPU_EMU
+    p.tc = (GPB_MM_TC && !backward && tbytes == 4 && Do <= 4 && p.tc_ks <= 2 && p.PP % 256 == 0) ? 1 : 0;
+#endif
     p.wide_mma = (backward && tbytes == 8 && Do > 4 && p.Qt <= 8) ? 1 : 0;
     p.w_nchunks = (int)(p.PP / 64);
     p.w_nsplit = 1;
@@ -117,6 +125,7 @@ struct MMWs {
     T *zh, *ep, *bs;
     double *rowacc, *pairpart, *pairsum, *rowpart, *rowsum, *colpart, *colsum, *dZ2, *dlW;
     double* rowfeat;
+    float* gu;           // tcgen05 forward: pre-split pair features
     size_t bytes;
 };
 template <typename T>
@@ -127,6 +136,7 @@ MMWs<T> mm_carve(const MMPlan& p, int n, int M, int Q, int Do, int backward, voi
     w.ep = (T*)cv.take(sizeof(T) * p.PP);
     w.bs = (T*)cv.take(sizeof(T) * Do * p.PP);
     w.rowfeat = p.xpath ? (double*)cv.take(sizeof(double) * (size_t)p.x_npad * p.x_rlg) : nullptr;
+    w.gu = p.tc ? (float*)cv.take(sizeof(float) * (size_t)p.PP * 8 * p.tc_ks * 2) : nullptr;
     if (!backward) {
         w.rowacc = nullptr;   // the forward accumulates straight into the caller's vacc[n,Do]
         w.pairpart = w.pairsum = w.rowpart = w.rowsum = w.colpart = w.colsum = w.dZ2 = w.dlW = nullptr;
@@ -434,6 +444,48 @@ int mm_fwd_wide_mma_dispatch(const MMPlan& p, const gpb::MMArgs<double>& a, void
 #undef GPB_CALL
 }
 
+// fp32 forward of narrow layers with the exponent GEMM on tcgen05 (gpb_umma.cuh)
+#ifndef GPB_CPU_EMU
+template <int KS, int DN>
+int mm_pairs_tc_pass(const gpb::MMTcArgs& t, int grid, void* stream) {
+    typedef gpb::MMTcCfg<KS> C;
+    auto kern = gpb::mm_pairs_tc_kernel<KS, DN>;
+    // One CTA per SM, enforced through the shared-memory request: a CTA owns all 512 TMEM columns, so a second
+    // resident CTA would sit in tcgen05.alloc until the first one has walked ALL its tiles (measured: the kernel
+    // took 1.5x as long whenever a side-stream kernel delayed the placement of a few CTAs).
+    const size_t smem = C::smem_bytes > 120 * 1024 ? C::smem_bytes : 120 * 1024;
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    GPB_LAUNCH(kern, dim3(grid), dim3(288), smem, stream, t);
+    return GPB_OK;
+}
+template <int KS>
+int mm_pairs_tc_launch(const MMPlan& p, const gpb::MMArgs<float>& a, float* gu, void* stream) {
+    auto prep = gpb::mm_tc_prep_kernel;
+    GPB_LAUNCH(prep, dim3(elementwise_grid(p.PP * 8 * KS)), dim3(256), 0, stream, a.zh, p.PP, a.Qa, KS, gu);
+    const int ntiles = (int)cdiv(a.n, 128);
+    const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    gpb::MMTcArgs t;
+    t.mx = a.mx; t.vx = a.vx; t.ls = a.ls; t.Gu = gu; t.bs = a.bs; t.n = a.n; t.Q = a.Qa; t.Do = a.Do; t.PP = p.PP;
+    t.rowacc = a.rowacc;
+    prof_begin(3, stream);
+    int rc = GPB_OK;
+    for (int d0 = 0; d0 < a.Do && !rc; d0 += 4) {
+        t.d0 = d0;
+        t.dn = (a.Do - d0) < 4 ? (a.Do - d0) : 4;
+        switch (t.dn) {
+            case 1: rc = mm_pairs_tc_pass<KS, 1>(t, grid, stream); break;
+            case 2: rc = mm_pairs_tc_pass<KS, 2>(t, grid, stream); break;
+            case 3: rc = mm_pairs_tc_pass<KS, 3>(t, grid, stream); break;
+            default: rc = mm_pairs_tc_pass<KS, 4>(t, grid, stream); break;
+        }
+    }
+    prof_end(3, stream);
+    if (rc) return rc;
+    return GPB_CHECK_LAUNCH();
+}
+#endif
+
 template <typename T>
 int mm_check(int n, int M, int Q, int Do) {
     if (n < 1 || M < 1 || Q < 1 || Do < 1) return fail(GPB_ERR_ARG, "mm: empty problem");
@@ -485,6 +537,16 @@ int mm_fwd_t(const double* mx, const double* vx, const double* z, const double* 
                 done = true;
             }
         }
+#ifndef GPB_CPU_EMU
+        if constexpr (sizeof(T) == 4) {
+            if (p.tc) {         // exponent on the 5th-generation tensor cores
+                a.d0 = 0;
+                rc = p.tc_ks == 1 ? mm_pairs_tc_launch<1>(p, a, w.gu, stream) : mm_pairs_tc_launch<2>(p, a, w.gu, stream);
+                if (rc) return rc;
+                done = true;
+            }
+        }
+#endif
         for (int pass = 0; pass < (done ? 0 : p.npass); pass++) {
             a.d0 = pass * p.DOC;
             rc = mm_pairs_dispatch<T, false>(p, a, stream);

@@ -28,6 +28,10 @@
 #define GPB_EXP_BITS 1
 #endif
 // narrow fp64 moment-matched layers: pair kernels with the exponent on the FP64 tensor cores (gpb_pairsx.cuh)
+// fp32 forward of narrow moment-matched layers: exponent GEMM on tcgen05 (gpb_umma.cuh)
+#ifndef GPB_MM_TC
+#define GPB_MM_TC 1
+#endif
 #ifndef GPB_MM_XPATH
 #define GPB_MM_XPATH 1
 #endif

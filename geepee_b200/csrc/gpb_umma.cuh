@@ -386,5 +386,281 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_umma_kernel(DetUmmaArgs a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
 }
 
+// =========================================================================
+// fp32-psi mode, moment-matched layer forward (a2 + a6, narrow layers Dout <= 4):
+//     vacc[n, d] = sum_p bs[d, p] psi2'[n, p],      psi2'[n, p] = cn_n exp(-sum_q c2_nq (mu_nq - zh_pq)^2)
+// The exponent is bilinear in per-row and per-pair features (kernels.py:201-234 expanded),
+//     log2 psi2'[n, p] = sum_k F[n, k] G[p, k],   F = log2(e) [2 c2 mu (Q) | -c2 (Q) | log cn - sum c2 mu^2],
+//                                                 G = [zh (Q) | zh^2 (Q) | 1],
+// so a tile of 128 rows x 256 pairs of exponents is ONE tcgen05.mma (K = 8 features; x3 for the TF32 hi/lo split,
+// x2 when 2Q + 1 > 8) into a TMEM accumulator, and what the CUDA cores are left with per row and pair is the
+// tcgen05.ld share, one ex2 and Dout FMAs -- the SIMT kernel spends ~10 issue slots there.  The kernel is bound by
+// the 16 ex2/clk/SM of the SFU.
+//   * one persistent CTA per SM walks row tiles of 128; the row features are built once per tile straight into the
+//     UMMA K-major layout (hi / lo tiles);
+//   * the pair operand (pre-split, pre-laid-out by mm_tc_prep_kernel: [chunk][hi|lo][k/4][256][4]) and the chunk's
+//     weights bs[d][256] arrive by cp.async.bulk into a 4-stage ring (mbarrier expect_tx);
+//   * TMEM holds two 256-column accumulators: thread 0 issues the MMAs of chunk c, then all 256 threads (row = lane,
+//     half of the columns each) run the exp / FMA epilogue of chunk c - 1.
+template <int KS>
+struct MMTcCfg {
+    static constexpr int NP = 256;                      // pairs per chunk
+    static constexpr int A_BYTES = 128 * 8 * KS * 4;    // hi or lo of the row-feature tile
+    static constexpr int G_BYTES = NP * 8 * KS * 4;     // hi or lo of one pair chunk
+    static constexpr int NSTAGE = 4;
+    static constexpr int STAGE = 2 * G_BYTES + 4 * NP * 4;          // + weights of up to 4 output dims
+    static constexpr size_t smem_bytes = 2 * (size_t)A_BYTES + (size_t)NSTAGE * STAGE + 128;
+};
+
+// Gu[chunk][hl][k/4][pair in chunk][k%4] = hi | lo of G[p][k]
+GPB_KERNEL void mm_tc_prep_kernel(const float* __restrict__ zh, long PP, int Q, int KS, float* __restrict__ Gu) {
+    const int K = 8 * KS;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < PP * K; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const long p = i / K;
+        double v = 0.0;
+        if (k < Q) v = zh[(long)k * PP + p];
+        else if (k < 2 * Q) {
+            const double z = zh[(long)(k - Q) * PP + p];
+            v = z * z;
+        } else if (k == 2 * Q) v = 1.0;
+        const float f = (float)v;
+        const float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
+        const float lo = f - hi;
+        const long chunk = p >> 8;
+        const int pc = (int)(p & 255);
+        float* base = Gu + chunk * (2L * 256 * K);
+        base[((long)(k >> 2) * 256 + pc) * 4 + (k & 3)] = hi;
+        base[256L * K + ((long)(k >> 2) * 256 + pc) * 4 + (k & 3)] = lo;
+    }
+}
+
+struct MMTcArgs {
+    const double* mx;    // [n, Q]
+    const double* vx;    // [n, Q]
+    const double* ls;    // [Q]
+    const float* Gu;     // [PP/256][2][2 KS][256][4]
+    const float* bs;     // [Do, PP]
+    int n, Q, Do, d0, dn; // dn output dims d0 .. d0 + dn - 1 in this pass (<= 4)
+    long PP;
+    double* rowacc;      // [n, Do]
+};
+
+GPB_DEVICE void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// 288 threads: warps 0-7 build the row features and run the exp / FMA epilogue (thread = row, half of the chunk's
+// columns); warp 8 is the producer: one elected thread streams the pair chunks (cp.async.bulk) and issues the MMAs.
+// The two sides only meet on mbarriers:
+//   s_full[stage]   producer's bulk copies landed                  (expect_tx)
+//   s_done[buffer]  MMAs of a chunk complete                       (tcgen05.commit)
+//   s_free[buffer]  epilogue finished with a TMEM accumulator      (256 arrivals)
+//   s_empty[stage]  epilogue finished with a stage's weights       (256 arrivals)
+//   s_aready        row features of the tile are in shared memory  (256 arrivals)
+template <int KS, int DN>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(288) mm_pairs_tc_kernel(MMTcArgs a) {
+    typedef MMTcCfg<KS> C;
+    constexpr int NP = C::NP, NST = C::NSTAGE, K = 8 * KS;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_full[NST], s_empty[NST], s_done[2], s_free[2], s_aready;
+    __shared__ uint32_t s_tmem;
+    __shared__ double s_part[128][4];
+    float* sA_hi = (float*)smem;
+    float* sA_lo = (float*)(smem + C::A_BYTES);
+    unsigned char* stages = smem + 2 * C::A_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, rowt = tid & 127, half = (tid >> 7) & 1;
+    const int n = a.n, Q = a.Q;
+    const int nch = (int)(a.PP / NP);
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma_smem_u32(&s_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(umma_smem_u32(&s_empty[s])));
+        }
+        for (int s = 0; s < 2; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma_smem_u32(&s_done[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(umma_smem_u32(&s_free[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(umma_smem_u32(&s_aready)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(umma_smem_u32(&s_tmem)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = s_tmem;
+    const int ntiles = (n + 127) / 128;
+
+    if (warp == 8) {
+        // ------------------------------ producer ------------------------------
+        if (tid == 256) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t tx_bytes = (uint32_t)(2 * C::G_BYTES + DN * NP * 4);
+            long sl_load = 0, sl_mma = 0;        // chunk slots loaded / multiplied so far (all tiles)
+            int ntile_done = 0;
+            auto load = [&](int c) {             // chunk c of the current tile -> ring stage sl_load % NST
+                const int s = (int)(sl_load % NST);
+                if (sl_load >= NST) mbar_wait(umma_smem_u32(&s_empty[s]), (uint32_t)((sl_load / NST - 1) & 1));
+                unsigned char* st = stages + (size_t)s * C::STAGE;
+                const uint32_t bar = umma_smem_u32(&s_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(umma_smem_u32(st)), "l"(a.Gu + (long)c * (2L * NP * K)), "r"((uint32_t)(2 * C::G_BYTES)),
+                               "r"(bar) : "memory");
+                GPB_UNROLL
+                for (int d = 0; d < DN; d++)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(umma_smem_u32(st + 2 * C::G_BYTES + d * NP * 4)),
+                                   "l"(a.bs + (long)(a.d0 + d) * a.PP + (long)c * NP), "r"((uint32_t)(NP * 4)), "r"(bar)
+                                 : "memory");
+                sl_load++;
+            };
+            auto mma = [&]() {                   // next chunk in order
+                const int s = (int)(sl_mma % NST);
+                const int bf = (int)(sl_mma & 1);
+                mbar_wait(umma_smem_u32(&s_full[s]), (uint32_t)((sl_mma / NST) & 1));
+                if (sl_mma >= 2) mbar_wait(umma_smem_u32(&s_free[bf]), (uint32_t)(((sl_mma >> 1) - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t gh = umma_smem_u32(stages + (size_t)s * C::STAGE), gl = gh + C::G_BYTES;
+                const uint32_t td = tbase + (uint32_t)bf * NP;
+                GPB_UNROLL
+                for (int ks = 0; ks < KS; ks++) {
+                    const uint64_t a_hi = umma_desc(umma_smem_u32(sA_hi) + ks * 2 * (128 * 16), 128 * 16, 128);
+                    const uint64_t a_lo = umma_desc(umma_smem_u32(sA_lo) + ks * 2 * (128 * 16), 128 * 16, 128);
+                    const uint64_t g_hi = umma_desc(gh + ks * 2 * (NP * 16), NP * 16, 128);
+                    const uint64_t g_lo = umma_desc(gl + ks * 2 * (NP * 16), NP * 16, 128);
+                    umma_tf32(td, a_hi, g_hi, idesc, ks > 0 ? 1u : 0u);
+                    umma_tf32(td, a_hi, g_lo, idesc, 1u);
+                    umma_tf32(td, a_lo, g_hi, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(umma_smem_u32(&s_done[bf])) : "memory");
+                sl_mma++;
+            };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // MMA(m) is issued as soon as the epilogue of chunk m - 2 has released its accumulator, i.e. while
+                // the epilogue of chunk m - 1 runs; the same event frees the ring stage chunk m - 2 + NST goes into.
+                // The first MMA of a tile waits for the tile's row features.
+                int cl = 0;
+                for (; cl < NST && cl < nch; cl++) load(cl);
+                mbar_wait(umma_smem_u32(&s_aready), (uint32_t)(ntile_done & 1));
+                for (int m = 0; m < nch; m++) {
+                    mma();
+                    if (m >= 2 && cl < nch) load(cl++);
+                }
+                ntile_done++;
+            }
+        }
+    } else {
+        // ------------------------------ features + epilogue ------------------------------
+        const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        long sl = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int row = tile * 128 + rowt;
+            const bool rv = row < n;
+            {   // row features of the tile (every thread forms its row's and stores its half of the k groups);
+                // all MMAs of the previous tile are complete: this thread has waited for the last one
+                float f[K];
+                GPB_UNROLL
+                for (int k = 0; k < K; k++) f[k] = 0.0f;
+                const double L2E = 1.4426950408889634074;
+                double a0 = rv ? 0.0 : -1.0e5;
+                if (rv) {
+                    GPB_UNROLL
+                    for (int q = 0; q < (K - 1) / 2; q++) {
+                        if (q < Q) {
+                            const double mu = a.mx[(long)row * Q + q];
+                            const double lq = exp(2.0 * a.ls[q]);
+                            const double c2 = 1.0 / (2.0 * a.vx[(long)row * Q + q] + lq);
+                            a0 += 0.5 * log(lq * c2) - c2 * mu * mu;
+                            f[q] = (float)(2.0 * c2 * mu * L2E);
+                            GPB_UNROLL
+                            for (int k = 0; k < K; k++)
+                                if (k == Q + q) f[k] = (float)(-c2 * L2E);
+                        }
+                    }
+                }
+                GPB_UNROLL
+                for (int k = 0; k < K; k++)
+                    if (k == 2 * Q) f[k] = (float)(a0 * L2E);
+                GPB_UNROLL
+                for (int j = 0; j < 2 * KS; j++) {
+                    float hi[4], lo[4];
+                    GPB_UNROLL
+                    for (int e = 0; e < 4; e++) {
+                        hi[e] = __uint_as_float(__float_as_uint(f[4 * j + e]) & 0xFFFFE000u);
+                        lo[e] = f[4 * j + e] - hi[e];
+                    }
+                    if ((j & 1) == half) {
+                        *(float4*)(sA_hi + (j * 128 + rowt) * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *(float4*)(sA_lo + (j * 128 + rowt) * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(umma_smem_u32(&s_aready));
+            double acc[DN];
+            GPB_UNROLL
+            for (int d = 0; d < DN; d++) acc[d] = 0.0;
+            for (int c = 0; c < nch; c++, sl++) {
+                const int s = (int)(sl % NST), bf = (int)(sl & 1);
+                mbar_wait(umma_smem_u32(&s_full[s]), (uint32_t)((sl / NST) & 1));     // the weights landed
+                mbar_wait(umma_smem_u32(&s_done[bf]), (uint32_t)((sl >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float* sbs = (const float*)(stages + (size_t)s * C::STAGE + 2 * C::G_BYTES);
+                const uint32_t tcol = tlane + (uint32_t)bf * NP + half * 128;
+                uint32_t v[2][32];
+                tmem_ld32(tcol, v[0]);
+                GPB_UNROLL
+                for (int cb = 0; cb < 4; cb++) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cb < 3) tmem_ld32(tcol + (cb + 1) * 32, v[(cb + 1) & 1]);   // in flight during the math
+                    const int col0 = half * 128 + cb * 32;
+                    float part[DN][2];
+                    GPB_UNROLL
+                    for (int d = 0; d < DN; d++) part[d][0] = part[d][1] = 0.0f;
+                    GPB_UNROLL
+                    for (int u = 0; u < 8; u++) {
+                        float e[4];
+                        GPB_UNROLL
+                        for (int j = 0; j < 4; j++)
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(__uint_as_float(v[cb & 1][4 * u + j])));
+                        GPB_UNROLL
+                        for (int d = 0; d < DN; d++) {
+                            const float4 w = *(const float4*)(sbs + d * NP + col0 + 4 * u);
+                            part[d][0] = fmaf(e[0], w.x, part[d][0]);
+                            part[d][1] = fmaf(e[1], w.y, part[d][1]);
+                            part[d][0] = fmaf(e[2], w.z, part[d][0]);
+                            part[d][1] = fmaf(e[3], w.w, part[d][1]);
+                        }
+                    }
+                    GPB_UNROLL
+                    for (int d = 0; d < DN; d++) acc[d] += (double)(part[d][0] + part[d][1]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(umma_smem_u32(&s_free[bf]));      // accumulator and stage back to the producer
+                mbar_arrive(umma_smem_u32(&s_empty[s]));
+            }
+            if (half == 1) {
+                GPB_UNROLL
+                for (int d = 0; d < DN; d++) s_part[rowt][d] = acc[d];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0 && rv) {
+                GPB_UNROLL
+                for (int d = 0; d < DN; d++) a.rowacc[(long)row * a.Do + a.d0 + d] = acc[d] + s_part[rowt][d];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // s_part free
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
 }  // namespace gpb
 #endif  // GPB_CPU_EMU

@@ -14,16 +14,18 @@ so layer i+1's pre-tail overlaps layer i's forward kernels, and layer i's all-re
 overlap the backward kernels of the layers below it.  Memory discipline (torch caching
 allocator): every step starts with fork() of all side streams and ends with join() of all of
 them, so a block freed by one stream's tensors is never handed out while the other stream still
-reads it.  On the CPU (emulator tests) everything runs inline.
+reads it.  On the CPU (emulator tests) everything runs inline; GPB_NO_SIDE_STREAMS=1 in the environment does the
+same on the GPU (diagnostic: it is how the TMEM co-residency stall of profiles/r2_mm_pairs_tc.txt was found).
 """
 import contextlib
+import os
 
 import torch
 
 
 class TailStreams(object):
     def __init__(self, device, n):
-        self.cuda = (device.type == 'cuda')
+        self.cuda = (device.type == 'cuda') and not os.environ.get('GPB_NO_SIDE_STREAMS')
         self.streams = [torch.cuda.Stream(device) for _ in range(n)] if self.cuda else [None] * n
 
     def mark(self):
