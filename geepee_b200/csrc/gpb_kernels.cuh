@@ -2917,14 +2917,17 @@ GPB_KERNEL void mm_pair_finish_kernel(const double* __restrict__ pairsum, int DO
         int hi = a > b ? a : b, lo = a > b ? b : a;
         dB[idx] = pairsum[(long)d * PP + (long)hi * (hi + 1) / 2 + lo];
     }
+    // one warp per (a, q): the M-term sums over b run across the lanes (a thread per (a, q) walked them one
+    // dependent global load at a time: 145 us at M = 256, a constant of the step that no row count amortises)
     const long totalZ = (long)M * Q;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < totalZ;
-         idx += (long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long nwarp = (long)gridDim.x * (blockDim.x >> 5);
+    for (long idx = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < totalZ; idx += nwarp) {
         int q = (int)(idx % Q), a = (int)(idx / Q);
         const double il2 = exp(-2.0 * ls[q]);
         const double za = z[(long)a * Q + q];
         double g = 0, w = 0;
-        for (int b = 0; b < M; b++) {
+        for (int b = lane; b < M; b += 32) {
             int hi = a > b ? a : b, lo = a > b ? b : a;
             long p = (long)hi * (hi + 1) / 2 + lo;
             double s1 = S1[(long)q * PP + p];
@@ -2936,8 +2939,12 @@ GPB_KERNEL void mm_pair_finish_kernel(const double* __restrict__ pairsum, int DO
                 if (b < a) w += S0[p] * dzb * dzb * 0.25;   // each unordered pair once
             }
         }
-        dZ2[idx] = g;
-        dlW[idx] = w;
+        g = warp_sum(g);
+        w = warp_sum(w);
+        if (lane == 0) {
+            dZ2[idx] = g;
+            dlW[idx] = w;
+        }
     }
 }
 

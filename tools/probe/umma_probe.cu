@@ -3,7 +3,7 @@
 //   element (r, k) at  (k / 4) * (R * 16) + r * 16 + (k % 4) * 4  bytes      (R = rows of the operand)
 // i.e. "core matrices" of 8 rows x 16 bytes, SBO = 128 B between 8-row groups, LBO = R * 16 B between
 // the two 16-byte K chunks of one K = 8 instruction.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe umma_probe.cu ; run: ./umma_probe [N] [K]
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe umma_probe.cu ; run: ./umma_probe [N] [K] [mode]
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -23,20 +23,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 __global__ void __launch_bounds__(128) umma_probe(const float* __restrict__ A, const float* __restrict__ B,
-                                                  float* __restrict__ C, int N, int K) {
+                                                  float* __restrict__ C, int N, int K, int mode) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* sA = (float*)smem;                       // [K/4][128][4]
     float* sB = sA + 128 * K;                       // [K/4][N][4]
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
+    // mode 0: K-major (above).  mode 1 / 2: MN-major, no swizzle: core matrix = 8 k x 16 bytes (4 rows),
+    //   element (r, k) at ((k / 8) * (R / 4) + r / 4) * 128 + (k % 8) * 16 + (r % 4) * 4 bytes;
+    //   mode 1 passes the 128-byte distance between 4-row groups as SBO, mode 2 as LBO.
     for (int i = tid; i < 128 * K; i += 128) {
         const int r = i / K, k = i % K;
-        sA[(k / 4) * 128 * 4 + r * 4 + (k % 4)] = A[r * K + k];
+        if (mode == 0) sA[(k / 4) * 128 * 4 + r * 4 + (k % 4)] = A[r * K + k];
+        else sA[((k / 8) * 32 + r / 4) * 32 + (k % 8) * 4 + (r % 4)] = A[r * K + k];
     }
     for (int i = tid; i < N * K; i += 128) {
         const int r = i / K, k = i % K;
-        sB[(k / 4) * N * 4 + r * 4 + (k % 4)] = B[r * K + k];
+        if (mode == 0) sB[(k / 4) * N * 4 + r * 4 + (k % 4)] = B[r * K + k];
+        else sB[((k / 8) * (N / 4) + r / 4) * 32 + (k % 8) * 4 + (r % 4)] = B[r * K + k];
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -53,10 +58,18 @@ __global__ void __launch_bounds__(128) umma_probe(const float* __restrict__ A, c
     const uint32_t tbase = tmem_base;
     if (tid == 0) {
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        if (mode) idesc |= (1u << 15) | (1u << 16);            // a_major = b_major = MN
         for (int ks = 0; ks < K / 8; ks++) {
-            const uint64_t da = make_desc(smem_u32(sA) + ks * 2 * (128 * 16), 128 * 16, 128);
-            const uint64_t db = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+            uint64_t da = make_desc(smem_u32(sA) + ks * 2 * (128 * 16), 128 * 16, 128);
+            uint64_t db = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+            if (mode == 1) {
+                da = make_desc(smem_u32(sA) + ks * 32 * 128, 32 * 128, 128);
+                db = make_desc(smem_u32(sB) + ks * (N / 4) * 128, (N / 4) * 128, 128);
+            } else if (mode == 2) {
+                da = make_desc(smem_u32(sA) + ks * 32 * 128, 128, 32 * 128);
+                db = make_desc(smem_u32(sB) + ks * (N / 4) * 128, 128, (N / 4) * 128);
+            }
             const uint32_t acc = ks > 0;
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -91,7 +104,7 @@ __global__ void __launch_bounds__(128) umma_probe(const float* __restrict__ A, c
 }
 
 int main(int argc, char** argv) {
-    const int N = argc > 1 ? atoi(argv[1]) : 64, K = argc > 2 ? atoi(argv[2]) : 32;
+    const int N = argc > 1 ? atoi(argv[1]) : 64, K = argc > 2 ? atoi(argv[2]) : 32, mode = argc > 3 ? atoi(argv[3]) : 0;
     std::vector<float> A(128 * K), B((size_t)N * K), C((size_t)128 * N);
     srand(1);
     for (auto& x : A) x = (float)(rand() % 17 - 8) / 8.0f;        // exactly representable in TF32
@@ -103,7 +116,7 @@ int main(int argc, char** argv) {
     cudaMemset(dC, 0xff, C.size() * 4);
     const size_t smem = (size_t)(128 + N) * K * 4;
     cudaFuncSetAttribute(umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    umma_probe<<<1, 128, smem>>>(dA, dB, dC, N, K);
+    umma_probe<<<1, 128, smem>>>(dA, dB, dC, N, K, mode);
     cudaError_t e = cudaDeviceSynchronize();
     printf("launch: %s\n", cudaGetErrorString(e));
     cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost);
@@ -117,6 +130,6 @@ int main(int argc, char** argv) {
             if (d > worst) worst = d;
             if (d > 1e-4 && bad < 8) { printf("  mismatch r=%d c=%d got %g ref %g\n", r, c, C[(size_t)r * N + c], ref); bad++; }
         }
-    printf("N=%d K=%d worst abs err %.3g -> %s\n", N, K, worst, worst < 1e-4 ? "OK" : "FAIL");
+    printf("mode=%d N=%d K=%d worst abs err %.3g -> %s\n", mode, N, K, worst, worst < 1e-4 ? "OK" : "FAIL");
     return worst < 1e-4 ? 0 : 1;
 }
