@@ -199,9 +199,65 @@ int det_bwd_t(const double* x, const double* z, const double* ls, const double* 
     return GPB_CHECK_LAUNCH();
 }
 
+// fp32 on tcgen05 (gpb_umma.cuh): MP <= 256; one CTA per SM over (row splits x Dout)
+struct SyrkTcPlan {
+    int use, MP, nbu, nsplit, rows_per_split;
+};
+SyrkTcPlan syrk_tc_plan(int n, int M, int Do) {
+    SyrkTcPlan p;
+    p.MP = gpb_det_pad_m(M);
+    p.nbu = p.MP == 256 ? 3 : 1;
+    p.use = 0;
+#ifndef GPB_CPU_EMU
+    p.use = (GPB_DET_SYRK_TC && (p.MP == 128 || p.MP == 256)) ? 1 : 0;
+#endif
+    int ns = sm_count() / Do;
+    if (ns < 1) ns = 1;
+    if ((long)ns * 512 > n) ns = (int)cdiv(n, 512);
+    int rps = (int)(cdiv(cdiv(n, ns), 16) * 16);
+    p.rows_per_split = rps;
+    p.nsplit = (int)cdiv(n, rps);
+    return p;
+}
+#ifndef GPB_CPU_EMU
+template <int MP>
+int det_syrk_umma_launch(const SyrkTcPlan& p, const float* Ksave, const double* dv, int n, int Do, double* part,
+                         void* stream) {
+    typedef gpb::SyrkUmmaCfg<MP> C;
+    auto kern = gpb::det_syrk_umma_kernel<MP>;
+    // (one CTA per SM: the kernel allocates all TMEM columns; at MP = 128 the request is padded accordingly)
+    const size_t smem = C::smem_bytes > 120 * 1024 ? C::smem_bytes : 120 * 1024;
+    int rc = allow_smem(kern, smem);
+    if (rc) return rc;
+    gpb::SyrkUmmaArgs a;
+    a.Ksave = Ksave; a.dv = dv; a.n = n; a.Do = Do; a.rows_per_split = p.rows_per_split; a.part = part;
+    prof_begin(2, stream);
+    GPB_LAUNCH(kern, dim3(p.nsplit, Do), dim3(256), smem, stream, a);
+    prof_end(2, stream);
+    return GPB_CHECK_LAUNCH();
+}
+#endif
+
 template <typename T>
 int det_syrk_t(const void* Ksave, const double* dv, int n, int M, int Do, double* dB, void* ws,
                size_t ws_bytes, void* stream) {
+#ifndef GPB_CPU_EMU
+    if constexpr (sizeof(T) == 4) {
+        SyrkTcPlan tp = syrk_tc_plan(n, M, Do);
+        if (tp.use) {
+            Carver cvt(ws, ws_bytes);
+            double* tpart = (double*)cvt.take(sizeof(double) * (size_t)tp.nsplit * Do * tp.nbu * 128 * 128);
+            if (!cvt.ok()) return fail(GPB_ERR_WS, "det_syrk: workspace %zu < %zu", ws_bytes, cvt.off);
+            int rct = tp.MP == 256 ? det_syrk_umma_launch<256>(tp, (const float*)Ksave, dv, n, Do, tpart, stream)
+                                   : det_syrk_umma_launch<128>(tp, (const float*)Ksave, dv, n, Do, tpart, stream);
+            if (rct) return rct;
+            auto fint = gpb::det_syrk_finish_kernel;
+            GPB_LAUNCH(fint, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, tpart, tp.nsplit,
+                       tp.MP, M, Do, dB, 1);
+            return GPB_CHECK_LAUNCH();
+        }
+    }
+#endif
     SyrkPlan p = syrk_plan(n, M, Do);
     Carver cv(ws, ws_bytes);
     double* part = (double*)cv.take(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
@@ -217,7 +273,7 @@ int det_syrk_t(const void* Ksave, const double* dv, int n, int M, int Do, double
     if (rc) return rc;
     auto fin = gpb::det_syrk_finish_kernel;
     GPB_LAUNCH(fin, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, part, p.nsplit,
-               p.MP, M, Do, dB);
+               p.MP, M, Do, dB, 0);
     return GPB_CHECK_LAUNCH();
 }
 
@@ -240,7 +296,7 @@ int det_syrk_t<double>(const void* Ksave, const double* dv, int n, int M, int Do
     if (rc) return rc;
     auto fin = gpb::det_syrk_finish_kernel;
     GPB_LAUNCH(fin, dim3(elementwise_grid((long)Do * M * M)), dim3(256), 0, stream, part, p.nsplit,
-               p.MP, M, Do, dB);
+               p.MP, M, Do, dB, 0);
     return GPB_CHECK_LAUNCH();
 }
 
@@ -380,7 +436,10 @@ int gpb_det_dx(int prec, const double* x, const double* z, const double* ls, con
 size_t gpb_det_syrk_ws_bytes(int n, int M, int Do) {
     if (gpb_det_pad_m(M) < 0) return 0;
     SyrkPlan p = syrk_plan(n, M, Do);
-    return align256(sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128);
+    SyrkTcPlan tp = syrk_tc_plan(n, M, Do);
+    const size_t b0 = sizeof(double) * (size_t)p.nsplit * Do * p.nbu * 128 * 128;
+    const size_t b1 = tp.use ? sizeof(double) * (size_t)tp.nsplit * Do * tp.nbu * 128 * 128 : 0;
+    return align256(b0 > b1 ? b0 : b1);
 }
 
 int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, int Do, double* dB,

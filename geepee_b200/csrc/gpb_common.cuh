@@ -28,6 +28,10 @@
 #define GPB_EXP_BITS 1
 #endif
 // narrow fp64 moment-matched layers: pair kernels with the exponent on the FP64 tensor cores (gpb_pairsx.cuh)
+// fp32 dB rank update of the deterministic layer on tcgen05 (gpb_umma.cuh)
+#ifndef GPB_DET_SYRK_TC
+#define GPB_DET_SYRK_TC 1
+#endif
 // fp32 forward of narrow moment-matched layers: exponent GEMM on tcgen05 (gpb_umma.cuh)
 #ifndef GPB_MM_TC
 #define GPB_MM_TC 1

@@ -1394,7 +1394,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_mma_kernel(const double* __restr
 
 // sum the row-splits of det_syrk and expand the block upper-triangle to dB[Do,M,M]
 GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nsplit, int MP, int M,
-                                       int Do, double* __restrict__ dB) {
+                                       int Do, double* __restrict__ dB, int tr /* blocks stored transposed */) {
     const int nb = MP / 128, nbu = nb * (nb + 1) / 2;
     const long total = (long)Do * M * M;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1409,7 +1409,7 @@ GPB_KERNEL void det_syrk_finish_kernel(const double* __restrict__ part, int nspl
         ub += bj - bi;
         double s = 0;
         for (int sp = 0; sp < nsplit; sp++)
-            s += part[(((long)sp * Do + d) * nbu + ub) * (128 * 128) + ii * 128 + jj];
+            s += part[(((long)sp * Do + d) * nbu + ub) * (128 * 128) + (tr ? jj * 128 + ii : ii * 128 + jj)];
         dB[idx] = s;
     }
 }

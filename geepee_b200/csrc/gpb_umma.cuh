@@ -662,5 +662,191 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(288) mm_pairs_tc_kernel(MMTcArgs a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
 }
 
+// =========================================================================
+// fp32-psi mode, deterministic-input layer: dB[d] = sum_n dv[n, d] kfu[n, :] kfu[n, :]^T  (aep_models.py:493) from the
+// saved fp32 Kfu, on tcgen05.  Here the GEMM's inner dimension is the data row: A = (dv kfu)^T and B = kfu^T must
+// have 4 consecutive ROWS of one pseudo-point in each 16-byte piece of the K-major UMMA layout, so the saved tile
+// [row][pseudo-point] is transposed on its way into the operand tiles:
+//   * cp.async ring (4 stages) of raw 16-row chunks [16][MP] + their dv;
+//   * thread = pseudo-point m: reads its column of the chunk (a warp reads 32 consecutive floats: conflict free),
+//     forms dv k and the TF32 hi / lo splits and stores four 16-byte pieces per operand tile
+//     (A_hi, A_lo, B_hi, B_lo; a warp stores 512 contiguous bytes: conflict free);
+//   * thread 0 issues the 3xTF32 MMAs of the chunk: rows 0-127 of the output against all MP columns and, for
+//     MP = 256, rows 128-255 against columns 128-255 only (upper block triangle: 384 TMEM columns);
+//   * fp32 accumulation in TMEM is flushed to the CTA's fp64 partial record every 2048 rows (coalesced, the
+//     record is stored transposed), so no sum runs longer than that in fp32;
+//   * grid = (row splits, Dout); det_syrk_finish_kernel (tr = 1) folds the splits.
+template <int MP>
+struct SyrkUmmaCfg {
+    static constexpr int RK = 16;                        // rows per chunk = 2 MMA K-steps
+    static constexpr int RAW = RK * MP * 4 + 128;        // raw chunk + dv[16]
+    static constexpr int NRAW = 4;
+    static constexpr int TILE = RK * MP * 4;             // one operand tile (hi or lo of A or B)
+    static constexpr int OST = 4 * TILE;                 // operand stage: A_hi | A_lo | B_hi | B_lo
+    static constexpr int NCOL = MP == 256 ? 384 : 128;   // accumulator columns
+    static constexpr int FLUSH = 2048 / RK;              // chunks between flushes
+    static constexpr size_t smem_bytes = (size_t)NRAW * RAW + 2 * (size_t)OST + 128;
+};
+
+struct SyrkUmmaArgs {
+    const float* Ksave;   // [n, MP]
+    const double* dv;     // [n, Do]
+    int n, Do, rows_per_split;
+    double* part;         // [nsplit][Do][nbu][128 * 128], blocks stored transposed
+};
+
+template <int MP>
+GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_syrk_umma_kernel(SyrkUmmaArgs a) {
+    typedef SyrkUmmaCfg<MP> C;
+    constexpr int RK = C::RK, NRAW = C::NRAW, NCOL = C::NCOL;
+    constexpr int NBU = MP == 256 ? 3 : 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_done[2];
+    __shared__ uint32_t s_tmem;
+    unsigned char* raws = smem;
+    unsigned char* osts = smem + (size_t)NRAW * C::RAW;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = blockIdx.y, split = blockIdx.x;
+    const long row_lo = (long)split * a.rows_per_split;
+    const long row_hi = (row_lo + a.rows_per_split) < a.n ? (row_lo + a.rows_per_split) : a.n;
+    const int nchunk = row_hi > row_lo ? (int)((row_hi - row_lo + RK - 1) / RK) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma_smem_u32(&s_done[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(umma_smem_u32(&s_tmem)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tbase = s_tmem;
+    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t idesc_full = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MP >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_half = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+
+    auto issue = [&](int c) {          // raw chunk c -> ring stage c % NRAW (all threads; an empty group past the end)
+        if (c < nchunk) {
+            unsigned char* st = raws + (size_t)(c % NRAW) * C::RAW;
+            const long r0 = row_lo + (long)c * RK;
+            for (int i = tid; i < RK * (MP / 4); i += 256) {
+                const int r = i / (MP / 4), m4 = i - r * (MP / 4);
+                const bool ok = r0 + r < row_hi;
+                cp_async16_zfill(st + (size_t)(r * MP + 4 * m4) * 4, a.Ksave + (ok ? (r0 + r) * MP + 4 * m4 : 0), ok);
+            }
+            if (tid < RK) {
+                const bool ok = r0 + tid < row_hi;
+                cp_async8_zfill(st + RK * MP * 4 + tid * 8, a.dv + (ok ? (r0 + tid) * a.Do + d : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+    // flush: accumulators (+)= into this CTA's partial record; thread = output row (TMEM lane), half of the columns
+    auto flush = [&](bool first) {
+        double* rec = a.part + ((long)split * a.Do + d) * NBU * (128 * 128);
+        const int c_lo = (warp >> 2) * (NCOL / 2), c_hi = c_lo + NCOL / 2;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tlane + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            GPB_UNROLL
+            for (int j = 0; j < 32; j++) {
+                const int c = c0 + j;
+                // columns 0..MP-1: output rows 0..127, columns 0..MP-1; columns 256..383: block (1, 1)
+                const int ub = c >> 7, jj = c & 127;
+                double* o = rec + (long)ub * (128 * 128) + jj * 128 + (tid & 127);
+                const double x = (double)__uint_as_float(v[j]);
+                *o = first ? x : *o + x;
+            }
+        }
+    };
+
+    uint32_t used[2] = {0, 0}, seen[2] = {0, 0};
+    bool first_flush = true;
+    int since = 0;                      // chunks accumulated in TMEM since the last flush
+    for (int c = 0; c < NRAW - 1; c++) issue(c);
+    for (int c = 0; c < nchunk; c++) {
+        const int s = c & 1;
+        issue(c + NRAW - 1);
+        cp_async_wait<NRAW - 1>();      // raw chunk c has landed (this thread's copies)
+        if (used[s] > seen[s]) {        // the MMAs that read operand stage s two chunks ago are complete
+            mbar_wait(umma_smem_u32(&s_done[s]), seen[s] & 1);
+            seen[s]++;
+        }
+        __syncthreads();                // ... everyone's copies
+        const float* raw = (const float*)(raws + (size_t)(c % NRAW) * C::RAW);
+        const double* rdv = (const double*)(raws + (size_t)(c % NRAW) * C::RAW + RK * MP * 4);
+        unsigned char* ost = osts + (size_t)s * C::OST;
+        if (tid < MP) {
+            GPB_UNROLL
+            for (int kg = 0; kg < RK / 4; kg++) {
+                float bh[4], bl[4], ah[4], al[4];
+                GPB_UNROLL
+                for (int e = 0; e < 4; e++) {
+                    const float k = raw[(4 * kg + e) * MP + tid];
+                    const float ka = k * (float)rdv[4 * kg + e];
+                    bh[e] = __uint_as_float(__float_as_uint(k) & 0xFFFFE000u);
+                    bl[e] = k - bh[e];
+                    ah[e] = __uint_as_float(__float_as_uint(ka) & 0xFFFFE000u);
+                    al[e] = ka - ah[e];
+                }
+                const size_t off = (size_t)kg * (MP * 16) + (size_t)tid * 16;
+                *(float4*)(ost + off) = make_float4(ah[0], ah[1], ah[2], ah[3]);
+                *(float4*)(ost + C::TILE + off) = make_float4(al[0], al[1], al[2], al[3]);
+                *(float4*)(ost + 2 * C::TILE + off) = make_float4(bh[0], bh[1], bh[2], bh[3]);
+                *(float4*)(ost + 3 * C::TILE + off) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = umma_smem_u32(ost), al = ah + C::TILE, bh = ah + 2 * C::TILE, bl = ah + 3 * C::TILE;
+            GPB_UNROLL
+            for (int ks = 0; ks < RK / 8; ks++) {
+                const uint32_t ko = ks * 2 * (MP * 16);
+                const uint32_t acc = (since > 0 || ks > 0) ? 1u : 0u;
+                // output rows 0..127 against all MP columns
+                umma_tf32(tbase, umma_desc(ah + ko, MP * 16, 128), umma_desc(bh + ko, MP * 16, 128), idesc_full, acc);
+                umma_tf32(tbase, umma_desc(ah + ko, MP * 16, 128), umma_desc(bl + ko, MP * 16, 128), idesc_full, 1u);
+                umma_tf32(tbase, umma_desc(al + ko, MP * 16, 128), umma_desc(bh + ko, MP * 16, 128), idesc_full, 1u);
+                if (MP == 256) {        // output rows 128..255 against columns 128..255
+                    const uint32_t ro = 128 * 16;
+                    umma_tf32(tbase + 256, umma_desc(ah + ko + ro, MP * 16, 128), umma_desc(bh + ko + ro, MP * 16, 128), idesc_half, acc);
+                    umma_tf32(tbase + 256, umma_desc(ah + ko + ro, MP * 16, 128), umma_desc(bl + ko + ro, MP * 16, 128), idesc_half, 1u);
+                    umma_tf32(tbase + 256, umma_desc(al + ko + ro, MP * 16, 128), umma_desc(bh + ko + ro, MP * 16, 128), idesc_half, 1u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(umma_smem_u32(&s_done[s])) : "memory");
+        }
+        used[s]++;
+        since++;
+        if (since == C::FLUSH || c == nchunk - 1) {
+            GPB_UNROLL
+            for (int q = 0; q < 2; q++)
+                if (used[q] > seen[q]) {
+                    mbar_wait(umma_smem_u32(&s_done[q]), seen[q] & 1);
+                    seen[q]++;
+                }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            flush(first_flush);
+            first_flush = false;
+            since = 0;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
+    }
+    if (nchunk == 0) {                   // empty split: a zero record
+        double* rec = a.part + ((long)split * a.Do + d) * NBU * (128 * 128);
+        for (int i = tid; i < NBU * 128 * 128; i += 256) rec[i] = 0.0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase));
+}
+
 }  // namespace gpb
 #endif  // GPB_CPU_EMU
