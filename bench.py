@@ -600,7 +600,9 @@ def run_gpu(args, w):
         fl = rows_rank * 2.0 * w['Do'] * w['M'] ** 2
         slot = 'det_fwd'
         kname = ('det_fwd_mma_kernel<MP> (Kfu generation fused with Kfu.B on the FP64 tensor cores, DMMA.8x8x4)'
-                 if pr == ops.F64 else 'det_fwd_kernel<float,MP> (Kfu generation fused with Kfu.B, SIMT)')
+                 if pr == ops.F64 else
+                 'det_fwd_umma_kernel<MP,DP> (Kfu generation fused with 3xTF32 Kfu.B on tcgen05, TMEM accumulators)'
+                 if w['M'] <= 512 else 'det_fwd_kernel<float,MP> (SIMT)')
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of
     # this same command (profiles/traffic.json: {"<workload>/<prec>": {"kernel", "bytes_per_launch", "source"}})
     traffic = None
@@ -650,7 +652,31 @@ def run_gpu(args, w):
     if pairs is not None and peak_tf > 0:
         for v in pairs.values():
             v['frac'] = v['achieved'] / peak_tf
+        if pr != ops.F64 and all(sizes[i + 1] <= 4 and 2 * sizes[i] + 1 <= 16 for i in range(1, len(sizes) - 1)):
+            # fp32 forward of narrow layers: exponent GEMM on tcgen05, the kernel is bound by the SFU (one ex2 per row and pair)
+            nexp = sum(rows_rank * P for _ in range(1, len(sizes) - 1))
+            sfu_peak = 148 * 16 * (clocks.get('sm_mhz') or 1965.0) * 1e6
+            pairs['fwd'].update({'kernel': 'mm_pairs_tc_kernel<KS,DN> (3xTF32 exponent GEMM on tcgen05, ex2 + FMA epilogue)',
+                                 'bound': 'sfu_ex2', 'exp_per_s': nexp / (pairs['fwd']['ms_per_step'] * 1e-3),
+                                 'sfu_peak_exp_per_s': sfu_peak,
+                                 'sfu_frac': nexp / (pairs['fwd']['ms_per_step'] * 1e-3) / sfu_peak,
+                                 'sfu_peak_source': 'nominal 148 SMs x 16 ex2/clk x sm_mhz under load'})
         line['roofline']['pair_kernels'] = pairs
+    if pr != ops.F64 and slot == 'det_fwd' and w['M'] <= 512:
+        # fp32 single-layer models: the dominant kernel runs on the 5th-generation tensor cores
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                bf16 = float(json.load(f)['bf16_tflops'])
+            src = 'MEASURED_PEAKS.json bf16_tflops (burst) / 2 = TF32 dense rate'
+        except Exception:  # noqa: BLE001
+            bf16, src = 2250.0, 'nominal 2.25 PFLOP/s bf16 / 2 (MEASURED_PEAKS.json absent)'
+        tpeak = bf16 / 2.0
+        line['roofline'].update({
+            'bound': 'tensor', 'peak': tpeak, 'frac': achieved / tpeak, 'peak_source': src,
+            'whole_step_frac': flops_per_row(w) * N / world / (ms_step * 1e-3) / 1e12 / tpeak,
+            'note': 'achieved counts the ALGORITHMIC 2 Do M^2 flops per row; the 3xTF32 split issues three MMAs per '
+                    'product, so the tensor pipe is busy for 3x that (issued fraction = 3 x frac)',
+            'fp32_fma_peak': peak_tf})
     if world == 1 and args.workload == 'cfg3_sdgpr' and not args.no_secondary:
         # measured right after the main workload, while the GPU is still at its working clocks (the CPU
         # baseline leg below keeps it idle for a minute)

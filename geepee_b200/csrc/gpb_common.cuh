@@ -28,6 +28,11 @@
 #define GPB_EXP_BITS 1
 #endif
 // narrow fp64 moment-matched layers: pair kernels with the exponent on the FP64 tensor cores (gpb_pairsx.cuh)
+// mm_pairs_tc_kernel, single-output passes: how many of every 4 exponentials are evaluated on the FMA pipe
+// instead of the SFU
+#ifndef GPB_MM_TC_POLY
+#define GPB_MM_TC_POLY 1
+#endif
 // fp32 dB rank update of the deterministic layer on tcgen05 (gpb_umma.cuh)
 #ifndef GPB_DET_SYRK_TC
 #define GPB_DET_SYRK_TC 1

@@ -6,9 +6,11 @@ O=gpurun_out; mkdir -p $O
 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/${TAG}_gputest.log; tail -2 $O/${TAG}_gputest.log
 python bench.py > $O/${TAG}_bench_default.json 2> $O/${TAG}_bench_default.err
 python bench.py --impl reference > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err
-python bench.py --prec fp32 --no-cpu --no-secondary > $O/${TAG}_bench_fp32.json 2> $O/${TAG}_bench_fp32.err
+python bench.py --prec fp32 --no-secondary > $O/${TAG}_bench_fp32.json 2> $O/${TAG}_bench_fp32.err
+python bench.py --prec fp32 --workload ns_sgpr --no-cpu --no-secondary --steps 20 --warmup 10 > $O/${TAG}_bench_ns_sgpr_fp32.json 2> $O/${TAG}_bench_ns_sgpr_fp32.err
+python bench.py --prec fp32 --workload cfg4_sgpssm --no-cpu --no-secondary > $O/${TAG}_bench_cfg4_sgpssm_fp32.json 2> $O/${TAG}_bench_cfg4_sgpssm_fp32.err
 for w in ns_sgpr cfg1_sgpr cfg2_sgplvm cfg4_sgpssm cfg5_sgpr; do
-  python bench.py --workload $w --no-cpu > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err
+  python bench.py --workload $w --no-cpu --steps 10 --warmup 10 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err
 done
 python - <<PY
 import json, glob
