@@ -82,3 +82,57 @@ def test_probit_lik():
 @pytest.mark.parametrize('M,batch', [(5, 1), (32, 2), (50, 3), (77, 1), (128, 4), (200, 2), (256, 5), (512, 2)])
 def test_spd_inverse(M, batch):
     oc.check_spd_inverse(M, batch)
+
+
+# Row counts the oracle cannot reach: the fp32-psi kernels (tcgen05: several row tiles per persistent CTA, ring /
+# accumulator phases carried from tile to tile, several fp64 flushes of the TMEM accumulators per row split) against
+# the fp64 kernels of the same library, which the tests above pin to the oracle.
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize('n,M,D,Do', [(300000, 256, 10, 2), (150001, 200, 16, 1), (200000, 128, 3, 4)])
+def test_det_layer_many_rows_fp32_vs_fp64(n, M, D, Do):
+    from geepee_b200 import ops
+    g = torch.Generator().manual_seed(n + M)
+    dev = torch.device('cuda')
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g, dtype=torch.float64).to(dev)
+    x, z = rnd(n, D), rnd(M, D)
+    ls = torch.full((D,), 0.4, dtype=torch.float64, device=dev)
+    sf = torch.full((1,), 0.1, dtype=torch.float64, device=dev)
+    A, B = rnd(Do, M), 0.05 * rnd(Do, M, M)
+    B = (B + B.transpose(1, 2)).contiguous()
+    dm, dv = rnd(n, Do), rnd(n, Do)
+    out = {}
+    for name in ('fp64', 'fp32'):
+        pr = ops.PREC[name]
+        opnd = ops.DetOperands(pr, A, B)
+        m, v, Ks, Ts = ops.det_fwd(pr, x, z, ls, sf, opnd, save=True)
+        dA, dzu, dl, dsf2 = ops.det_bwd(pr, x, z, ls, sf, opnd, dm, dv, Ks, Ts)
+        dB = ops.det_syrk(pr, Ks, dv, M)
+        out[name] = dict(m=m, v=v, dA=dA, dzu=dzu, dl=dl, dsf2=dsf2, dB=dB)
+        del Ks, Ts
+    for k in out['fp64']:
+        assert _rel(out['fp32'][k], out['fp64'][k]) < 5e-4, (k, _rel(out['fp32'][k], out['fp64'][k]))
+
+
+@pytest.mark.parametrize('n,M,Q,Do', [(100000, 128, 2, 2), (60000, 200, 4, 1), (50001, 64, 7, 3), (80000, 96, 3, 4)])
+def test_mm_forward_many_rows_fp32_vs_fp64(n, M, Q, Do):
+    from geepee_b200 import ops
+    g = torch.Generator().manual_seed(n + M + Q)
+    dev = torch.device('cuda')
+
+    def rnd(*s):
+        return torch.randn(*s, generator=g, dtype=torch.float64).to(dev)
+    mx, z = rnd(n, Q), rnd(M, Q)
+    vx = (0.05 + torch.rand(n, Q, generator=g, dtype=torch.float64)).to(dev)
+    ls = torch.full((Q,), 0.3, dtype=torch.float64, device=dev)
+    sf = torch.zeros(1, dtype=torch.float64, device=dev)
+    A, B = rnd(Do, M), 0.05 * rnd(Do, M, M)
+    B = (B + B.transpose(1, 2)).contiguous()
+    o64 = ops.mm_fwd(ops.PREC['fp64'], mx, vx, z, ls, sf, A, B)
+    o32 = ops.mm_fwd(ops.PREC['fp32'], mx, vx, z, ls, sf, A, B)
+    for i, k in enumerate(('mout', 'vout', 'vacc', 'psi1')):
+        assert _rel(o32[i], o64[i]) < 5e-4, (k, _rel(o32[i], o64[i]))
