@@ -24,8 +24,17 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream(t):
+    """torch's current stream on the tensor's device as a raw handle (every launch goes there).  The raw getter
+    costs a fraction of a microsecond; torch.cuda.current_stream() builds a Stream object (7-8 us, 15 times per step
+    of the small configs)."""
     if t.is_cuda:
+        if _raw_stream is not None:
+            return ctypes.c_void_p(_raw_stream(t.device.index if t.device.index is not None
+                                               else torch.cuda.current_device()))
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     return None
 

@@ -342,7 +342,15 @@ def multicopy(dsts, srcs):
     sp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
     dp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in dsts])
     counts = (ctypes.c_long * n)(*[t.numel() for t in srcs])
-    rc = _lib.get().gpb_tail_copy(n, sp, dp, counts, ops._stream(dsts[0]))
+    desc = (n, sp, dp, counts)
+    multicopy_prepared(desc, dsts[0])
+    return desc
+
+
+def multicopy_prepared(desc, like):
+    """Re-issue a multicopy whose tensors (addresses, sizes) are unchanged: `desc` is what multicopy returned."""
+    n, sp, dp, counts = desc
+    rc = _lib.get().gpb_tail_copy(n, sp, dp, counts, ops._stream(like))
     ops._chk(rc, 'tail_copy')
 
 

@@ -29,6 +29,18 @@ with contextlib.redirect_stdout(io.StringIO()):
 for _ in range(6):
     model.objective_function(params, w['N'], alpha=w['alpha'])
 torch.cuda.synchronize()
+import time
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+t0 = time.perf_counter()
+host = 0.0
+for _ in range(10):
+    h0 = time.perf_counter()
+    model.objective_function(params, w['N'], alpha=w['alpha'])
+    host += time.perf_counter() - h0
+e1.record()
+torch.cuda.synchronize()
+print('untraced: %.3f ms per step by CUDA events, %.3f ms per call on the host clock' % (e0.elapsed_time(e1) / 10, 1e3 * host / 10))
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
@@ -66,3 +78,11 @@ for b in bigs + [None]:
             '; '.join('%s x%d %.0fus' % (k, c, t) for k, (c, t) in top)))
     if b is not None:
         cur = max(cur, b.time_range.end)
+if os.environ.get('GPB_TRACE_HEAD'):
+    nh = int(os.environ['GPB_TRACE_HEAD'])
+    print('first %d activities of the step (start offset us, duration us, name):' % nh)
+    for e in step[:nh]:
+        print('  %9.1f %8.1f  %s' % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:90]))
+    print('last %d activities:' % nh)
+    for e in step[-nh - 25:]:
+        print('  %9.1f %8.1f  %s' % (e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:90]))
