@@ -16,8 +16,8 @@
 // on those values with the pair constants in registers.  Per-pair sums over rows are therefore spread over
 // the 8 lanes with the same t and folded ONCE at the end of the kernel; per-row sums over pairs are spread
 // over the 4 lanes of a quad, the 8 warps and the pair chunks (blocks): per-lane partials go to shared
-// memory atomics (after two quad shuffles), and after the tile's only barrier one fp64 atomic per
-// (row, value) goes to the global row sums.
+// memory slot of the warp (after two quad shuffles), and after the tile's only barrier the 8 slots are summed and
+// one fp64 atomic per (row, value) goes to the global row sums.
 //
 // Row records are precomputed once per launch by mm_rowfeat_kernel (the divisions / logarithms of
 // kernels.py:188-190 are per row, not per row and pair chunk) and staged 32 rows at a time with cp.async:
@@ -43,7 +43,7 @@ struct MMXCfg {
     static constexpr int RLG = (4 * KQ + 1 + (BWD ? DOC : 0) + 1) / 2 * 2;   // ... in global memory (even)
     static constexpr int NS = BWD ? 2 * Q : DOC;          // per-row sums
     static constexpr int NSP = (NS + 1) / 2 * 2;
-    static constexpr size_t smem_bytes = sizeof(double) * ((size_t)ExpDom<double>::TAB + 2 * TR * RL + 2 * TR * NSP);
+    static constexpr size_t smem_bytes = sizeof(double) * ((size_t)ExpDom<double>::TAB + 2 * TR * RL + 2 * 8 * TR * NSP);
 };
 
 // one record per row (rows n .. n_pad-1: null records whose psi2' underflows and whose dv is 0)
@@ -89,7 +89,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
     GPB_DYN_SMEM(dsm);
     double* s_tab = (double*)dsm;
     double* s_row = s_tab + kTab;                  // [2][TR * RL]
-    double* s_acc = s_row + 2 * TR * RL;           // [2][TR][NSP] row sums of the tile (shared-memory atomics)
+    double* s_acc = s_row + 2 * TR * RL;           // [2][8 warps][TR][NSP] row sums of the tile, one slot per warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const long PP = a.PP;
@@ -135,7 +135,6 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
             }
         }
     for (int i = tid; i < kTab; i += 256) s_tab[i] = exp_bits_table(i / ExpDom<double>::REP);
-    for (int i = tid; i < 2 * TR * NSP; i += 256) s_acc[i] = 0.0;
     const int lane16 = lane & (ExpDom<double>::REP - 1);
     const int half_bit = 8 + (a.n < 0);      // = 8, kept in a register (LOP3 operand of exp_dom_bits_n)
 
@@ -160,7 +159,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
         const int tv = (r_end - t0) < TR ? (r_end - t0) : TR;
         if (t0 + TR < r_end) stage(buf ^ 1, t0 + TR);
         const double* rows = s_row + buf * TR * RL;
-        double* acc_t = s_acc + buf * TR * NSP;
+        double* acc_t = s_acc + (size_t)(buf * 8 + warp) * TR * NSP;     // this warp's slots of the tile
         GPB_UNROLL_N(1)
         for (int trip = 0; trip < TR / (8 * NRG); trip++) {
             double x[NRG][NPG * 2];
@@ -246,9 +245,10 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
                         }
             }
             // row sums: fold the 4 lanes of a quad (they hold different pairs of the same row) with two
-            // shuffles, then one lane per quad adds into the tile's accumulators in shared memory (the 8
-            // warps hold different pairs of the same rows; fp64 shared atomics are CAS loops, collisions
-            // between warps are rare)
+            // shuffles, then one lane per quad stores into the warp's own slot of the tile in shared memory
+            // (every (warp, row) meets once per tile: plain stores, 8 lanes = 8 consecutive records; the first
+            // version used fp64 shared-memory atomics, which are CAS spin loops that the 8 warps -- walking the
+            // same rows in step -- kept colliding in)
             GPB_UNROLL
             for (int rg = 0; rg < NRG; rg++) {
                 const int row = trip * 8 * NRG + rg * 8 + g;
@@ -259,7 +259,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
                 }
                 if (t == 0) {
                     GPB_UNROLL
-                    for (int s_ = 0; s_ < NS; s_++) atomic_add(acc_t + row * NSP + s_, v[rg][s_]);
+                    for (int s_ = 0; s_ < NS; s_++) acc_t[row * NSP + s_] = v[rg][s_];
                 }
             }
         }
@@ -268,9 +268,10 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS2(256, 2) mm_pairsx_kernel(MMArgs<double> a, co
         // tile complete: one fp64 atomic per (row, value) into the global row sums; re-arm the accumulators
         for (int o = tid; o < TR * NS; o += 256) {
             const int row = o / NS, s_ = o - row * NS;
-            double* ap = s_acc + buf * TR * NSP + row * NSP + s_;
-            const double acc = *ap;
-            *ap = 0.0;
+            const double* ap = s_acc + (size_t)buf * 8 * TR * NSP + row * NSP + s_;
+            double acc = 0.0;
+            GPB_UNROLL
+            for (int w8 = 0; w8 < 8; w8++) acc += ap[(size_t)w8 * TR * NSP];
             if (row < tv) {
                 if (BWD) atomic_add(a.rowacc + (long)(t0 + row) * NS + s_, acc);
                 else if (s_ < a.Do) atomic_add(a.rowacc + (long)(t0 + row) * a.Do + s_, acc);
