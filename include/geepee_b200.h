@@ -71,7 +71,8 @@ int gpb_gauss_lik(const double* m, const double* v, const double* y, const doubl
 
 /* ---- a3 / a4 / a10: batched inverse + log-determinant of SPD matrices A[batch,M,M] (M <= 512), fp64.
  *      Replaces np.linalg.inv / np.linalg.slogdet of base_models.py:464,471,476 and
- *      aep_models.py:68,78,91,525,533.  One thread-block cluster per matrix, blocked Gauss-Jordan. */
+ *      aep_models.py:68,78,91,525,533.  One thread-block cluster (8 CTAs) per matrix, blocked Gauss-Jordan;
+ *      M <= 256: the matrix lives in FP64 tensor-core accumulator tiles in registers. */
 int gpb_spd_inverse(const double* A, int batch, int M, double* Ainv, double* logdet, void* stream);
 
 /* ---- (8f rank 1) Probit likelihood, y in {-1,+1}.  mode 0: lik_layers.py:303-362 Probit_Layer.compute_log_Z
@@ -140,7 +141,8 @@ int gpb_det_bwd(int prec, const double* x, const double* z, const double* ls, co
 int gpb_det_dx(int prec, const double* x, const double* z, const double* ls, const void* Ap,
                const double* dm, const double* dv, const void* Ksave, const void* Tsave,
                int n, int M, int D, int Do, double* dx, void* stream);
-/* a8 (rank update): aep_models.py:493  dB[Do,M,M] = sum_n dv[n,d] kfu kfu^T */
+/* a8 (rank update): aep_models.py:493  dB[Do,M,M] = sum_n dv[n,d] kfu kfu^T
+ *      (fp64: FP64 tensor cores; fp32 with M <= 256: tcgen05, 3xTF32, fp64 flush every 2048 rows) */
 size_t gpb_det_syrk_ws_bytes(int n, int M, int Do);
 int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, int Do,
                  double* dB, void* ws, size_t ws_bytes, void* stream);
@@ -149,7 +151,8 @@ int gpb_det_syrk(int prec, const void* Ksave, const double* dv, int n, int M, in
 /* a6: aep_models.py:183-199 _forward_prop_random_thru_cav_mm (post twin base_models.py:286-307):
  *      mout = psi1 A^T, vout = sf2 + sum_ab B[d,a,b] psi2[n,a,b] - mout^2; psi2 never stored.
  *      Also returns vacc[n,Do] = sum_ab B[d,a,b] psi2[n,a,b] and (if psi1save != NULL) psi1[n,M],
- *      which the backward reuses instead of re-evaluating them. */
+ *      which the backward reuses instead of re-evaluating them.
+ *      (fp32, Do <= 4, Q <= 7: the pair exponents are a 3xTF32 tcgen05 GEMM of row against pair features.) */
 size_t gpb_mm_ws_bytes(int n, int M, int Q, int Do, int backward);
 int gpb_mm_fwd(int prec, const double* mx, const double* vx, const double* z, const double* ls,
                const double* sf, const double* A, const double* B, int n, int M, int Q, int Do,
