@@ -103,6 +103,12 @@ struct DetUmmaArgs {
     float* Tsave;        // [n, Do, MP]
 };
 
+// one 256-bit store (STG.E.ENL2.256, sm_100): 8 consecutive floats, 32-byte aligned -- a whole sector per instruction
+GPB_DEVICE void st_global_v8(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+
 // tcgen05.ld of 8 / 32 consecutive accumulator columns of the warp's 32 lanes
 GPB_DEVICE void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -217,6 +223,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_umma_kernel(DetUmmaArgs a) {
                     }
                 }
                 // this thread's 8 kernel values of the chunk: hi / lo tiles in the UMMA layout + Ksave
+                float kall[8];
                 GPB_UNROLL
                 for (int jj = 0; jj < 2; jj++) {
                     const int j = 2 * half + jj;
@@ -251,9 +258,12 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_umma_kernel(DetUmmaArgs a) {
                     }
                     *(float4*)(sA_hi + (j * 128 + rowt) * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     *(float4*)(sA_lo + (j * 128 + rowt) * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    if (rv && d0 == 0)
-                        *(float4*)(a.Ksave + (long)row * MP + c * KC + 4 * j) = make_float4(kv[0], kv[1], kv[2], kv[3]);
+                    GPB_UNROLL
+                    for (int e = 0; e < 4; e++) kall[4 * jj + e] = kv[e];
                 }
+                if (rv && d0 == 0)
+                    st_global_v8(a.Ksave + (long)row * MP + c * KC + 8 * half, kall[0], kall[1], kall[2], kall[3], kall[4],
+                                 kall[5], kall[6], kall[7]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
                 __syncthreads();
                 if (tid == 0) {
@@ -317,11 +327,7 @@ GPB_KERNEL void GPB_LAUNCH_BOUNDS(256) det_fwd_umma_kernel(DetUmmaArgs a) {
                             for (int i = 0; i < 8; i++) t[i] = __uint_as_float(v[u][i]);
                             part += (double)(kr[0] * t[0] + kr[1] * t[1]) + (double)(kr[2] * t[2] + kr[3] * t[3]);
                             part += (double)(kr[4] * t[4] + kr[5] * t[5]) + (double)(kr[6] * t[6] + kr[7] * t[7]);
-                            if (rv) {
-                                float4* tq = (float4*)(tp + (c4 + u) * KC);
-                                tq[0] = make_float4(t[0], t[1], t[2], t[3]);
-                                tq[1] = make_float4(t[4], t[5], t[6], t[7]);
-                            }
+                            if (rv) st_global_v8(tp + (c4 + u) * KC, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
                         }
                         vacc[dd] += part;
                     }
