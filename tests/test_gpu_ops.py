@@ -136,3 +136,17 @@ def test_mm_forward_many_rows_fp32_vs_fp64(n, M, Q, Do):
     o32 = ops.mm_fwd(ops.PREC['fp32'], mx, vx, z, ls, sf, A, B)
     for i, k in enumerate(('mout', 'vout', 'vacc', 'psi1')):
         assert _rel(o32[i], o64[i]) < 5e-4, (k, _rel(o32[i], o64[i]))
+
+
+# edge shapes of the tcgen05 kernels: row counts around the 128-row tile, pseudo-point counts around the padding steps,
+# every input-dimension template (4 / 8 / 16 / 32), several output dims (TMEM passes), feature counts around K = 8 / 16
+@pytest.mark.parametrize('n,M,D,Do', [(1, 7, 1, 1), (127, 128, 4, 2), (129, 129, 5, 3), (255, 200, 8, 1), (257, 256, 9, 5),
+                                       (1000, 31, 17, 2), (513, 256, 32, 4), (2049, 64, 3, 1)])
+def test_det_layer_edge_shapes_fp32_vs_fp64(n, M, D, Do):
+    test_det_layer_many_rows_fp32_vs_fp64(n, M, D, Do)
+
+
+@pytest.mark.parametrize('n,M,Q,Do', [(1, 5, 1, 1), (127, 23, 3, 4), (129, 64, 4, 1), (255, 33, 7, 2), (257, 40, 2, 3),
+                                       (640, 128, 1, 2), (385, 17, 6, 4)])
+def test_mm_forward_edge_shapes_fp32_vs_fp64(n, M, Q, Do):
+    test_mm_forward_many_rows_fp32_vs_fp64(n, M, Q, Do)
