@@ -517,18 +517,65 @@ def run_gpu(args, w):
     # each rank's inputs for a step are its own contiguous slice of the rows (geepee_b200/dist.py)
     lo, hi = (rank * N) // world, ((rank + 1) * N) // world
 
-    def step_e2e():
-        if xh is not None:
-            model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
-        model._y[lo:hi].copy_(yh[lo:hi], non_blocking=True)
-        return model.objective_function(params, N, alpha=alpha)
+    # End-to-end leg: every step's inputs come from pinned host memory.  They are double buffered: the rows of step
+    # t + 1 are uploaded on a copy stream while step t computes (what an input pipeline does); one upload per step is
+    # issued inside the timed region and the region ends only after the last one has landed (e2e_finish).  The step's
+    # own small parameter upload does not queue behind that copy: it is read from pinned memory by a copy kernel
+    # (layers._zero_copy_upload).
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [(model._x if xh is not None else None, model._y),
+            (torch.empty_like(model._x) if xh is not None else None, torch.empty_like(model._y))]
+    if xh is not None:
+        bufs[1][0].copy_(model._x)
+    bufs[1][1].copy_(model._y)
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {'t': 0, 'primed': False}
 
-    def timed(fn, steps):
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[i])          # the step that last read buffer i has finished
+            if xh is not None:
+                bufs[i][0][lo:hi].copy_(xh[lo:hi], non_blocking=True)
+            bufs[i][1][lo:hi].copy_(yh[lo:hi], non_blocking=True)
+            ev_copied[i].record(copy_stream)
+
+    in_bytes = (X[lo:hi].nbytes if xh is not None else 0) + Y[lo:hi].nbytes
+    pipelined = in_bytes >= (4 << 20)       # tiny inputs (cfg1: 4.8 KB): the in-stream copy costs less than the stream hand-offs
+
+    def step_e2e():
+        if not pipelined:
+            if xh is not None:
+                model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
+            model._y[lo:hi].copy_(yh[lo:hi], non_blocking=True)
+            return model.objective_function(params, N, alpha=alpha)
+        i = e2e_state['t'] % 2
+        if not e2e_state['primed']:
+            ev_done[0].record()
+            ev_done[1].record()
+            prefetch(i)
+            e2e_state['primed'] = True
+        prefetch(1 - i)                                  # next step's inputs, overlapped with this step
+        torch.cuda.current_stream().wait_event(ev_copied[i])
+        if xh is not None:
+            model._x = bufs[i][0]
+        model._y = bufs[i][1]
+        out = model.objective_function(params, N, alpha=alpha)
+        ev_done[i].record()
+        e2e_state['t'] += 1
+        return out
+
+    def e2e_finish():
+        torch.cuda.current_stream().wait_stream(copy_stream)
+
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             out = fn()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -552,7 +599,7 @@ def run_gpu(args, w):
     value = N / (ms_step * 1e-3)
     # ---- end-to-end timing ----
     step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps, e2e_finish)
     ms_e2e /= args.steps
     h2d = ((X[lo:hi].nbytes if xh is not None else 0) + Y[lo:hi].nbytes) * world + world * sum(np.asarray(v).nbytes for v in params.values())
     d2h = world * (8 + sum(np.asarray(v).nbytes for v in grads.values()))
@@ -636,7 +683,10 @@ def run_gpu(args, w):
         'energy': energy,
         'clocks': clocks,
         'e2e': {'value': N / (ms_e2e * 1e-3), 'unit': 'rows/s', 'ms_per_step': ms_e2e,
-                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'input_pipeline': ('double buffered: the rows of step t+1 are uploaded from pinned memory on a copy stream '
+                                   'while step t computes; one upload per step inside the timed region') if pipelined
+                else 'in-stream copy from pinned memory before each step'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'fp64_fma_pipe' if pr == ops.F64 else 'fp32_fma_pipe', 'kernel': kname,
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',

@@ -63,6 +63,7 @@ _SIGS = {
     'gpb_tail_khyper_out_len': (ctypes.c_long, [ctypes.c_int, ctypes.c_int]),
     'gpb_tail_gather': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, ctypes.c_double, c_dp, c_dp]),
     'gpb_tail_copy': (ctypes.c_int, [ctypes.c_int, c_dp, c_dp, c_dp, c_dp]),
+    'gpb_host_device_ptr': (ctypes.c_int, [c_dp, c_dp]),
     'gpb_latent_ws_bytes': (ctypes.c_size_t, [ctypes.c_long]),
     'gpb_lvm_x_fwd': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_dp, c_dp, c_dp, ctypes.c_long, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp, c_dp]),

@@ -170,4 +170,24 @@ int gpb_tail_copy(int n, const double* const* h_srcs, double* const* h_dsts, con
     return GPB_CHECK_LAUNCH();
 }
 
+/* Device-side address of page-locked (pinned, mapped) host memory, so that a copy KERNEL can read it directly:
+ * small per-step uploads (the parameter vector) then bypass the H2D copy engine, whose FIFO would otherwise put them
+ * behind any large input copy that is in flight.  Returns GPB_ERR_ARG if the memory is not mapped. */
+int gpb_host_device_ptr(const void* host_ptr, void** dev_ptr) {
+    if (!host_ptr || !dev_ptr) return fail(GPB_ERR_ARG, "host_device_ptr: null pointer");
+#ifndef GPB_CPU_EMU
+    void* d = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(host_ptr), 0);
+    if (e != cudaSuccess || !d) {
+        (void)cudaGetLastError();      // not sticky: clear it
+        return fail(GPB_ERR_ARG, "host_device_ptr: memory is not mapped pinned host memory (%s)",
+                    cudaGetErrorString(e));
+    }
+    *dev_ptr = d;
+#else
+    *dev_ptr = const_cast<void*>(host_ptr);
+#endif
+    return GPB_OK;
+}
+
 }  // extern "C"

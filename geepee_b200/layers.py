@@ -54,6 +54,36 @@ def _pinned(device, n, slot):
     return buf
 
 
+_ZC_MAX = 1 << 20       # elements: uploads up to this size are read from pinned memory by a copy kernel
+_ZC = {}                # pinned buffer address -> device-side address (0: not mapped, use the copy engine)
+
+
+def _zero_copy_upload(pin, t, total):
+    """t[:total] = pin[:total] by a copy kernel that reads the pinned staging buffer over PCIe (gpb_tail_copy), so that
+    the per-step parameter upload does not queue on the H2D copy engine behind a large input copy in flight.
+    GPB_UPLOAD_DMA=1 forces the copy engine.  Returns False when the pinned buffer is not device-mapped."""
+    import ctypes
+    import os
+    if os.environ.get('GPB_UPLOAD_DMA'):
+        return False
+    from . import _lib as _l, ops
+    lib = _l.get()
+    hp = pin.data_ptr()
+    dp = _ZC.get(hp)
+    if dp is None:
+        out = ctypes.c_void_p()
+        rc = lib.gpb_host_device_ptr(ctypes.c_void_p(hp), ctypes.byref(out))
+        dp = out.value if rc == 0 and out.value else 0
+        _ZC[hp] = dp
+    if not dp:
+        return False
+    srcs = (ctypes.c_void_p * 1)(dp)
+    dsts = (ctypes.c_void_p * 1)(t.data_ptr())
+    counts = (ctypes.c_long * 1)(total)
+    ops._chk(lib.gpb_tail_copy(1, srcs, dsts, counts, ops._stream(t)), 'tail_copy')
+    return True
+
+
 _BIG = 1 << 20          # elements: arrays above this are copied by several host threads
 _POOL = None
 
@@ -95,7 +125,8 @@ def pack_to_device(params, device):
             _host_copy(view[off:off + a.size], a.reshape(-1))
             off += a.size
         t = torch.empty(total, dtype=torch.float64, device=device)
-        t.copy_(pin[:total], non_blocking=True)
+        if total > _ZC_MAX or not _zero_copy_upload(pin, t, total):
+            t.copy_(pin[:total], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
         _PIN[(str(device), 'h2d_event')] = ev

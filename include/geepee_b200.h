@@ -234,6 +234,11 @@ int gpb_tail_gather(int n, const double* const* h_srcs, const long* h_counts, do
 int gpb_tail_copy(int n, const double* const* h_srcs, double* const* h_dsts, const long* h_counts,
                   void* stream);
 
+/* Device-side address of pinned (mapped) host memory: lets gpb_tail_copy read a small per-step upload (the parameter
+ * vector the optimiser hands to objective_function, utils.py:42-53) straight from host memory instead of queueing it on
+ * the H2D copy engine behind a large input copy.  Error if the memory is not mapped. */
+int gpb_host_device_ptr(const void* host_ptr, void** dev_ptr);
+
 /* ---- a12 / a13: elementwise latent-variable algebra (one thread per (row, latent dim)) ----------
  *      SGPLVM: get_cavity_x aep_models.py:840-861, compute_phi_x 863-867, compute_cav_grad_x 817-838,
  *      get_posterior_x base_models.py:765-775, compute_posterior_grad_x 913-929; VFE twin vfe_models.py:749-845.
