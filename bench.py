@@ -415,6 +415,69 @@ def gpu_parity(w, last, prec, dev, tol):
             'against': 'the cpu_baseline call (same rows, same params) of this run'}
 
 
+class InputPipeline(object):
+    """End-to-end input path of a step: the rank's rows [lo, hi) of x (None for the latent-variable models) and y come
+    from pinned host memory every step.  They are double buffered: the rows of step t + 1 are uploaded on a copy
+    stream while step t computes (what an input pipeline does); one upload per step is issued inside the timed
+    region and the region ends only after the last one has landed (finish()).  The step's own small parameter
+    upload does not queue behind that copy on the H2D engine: it is read from pinned memory by a copy kernel
+    (geepee_b200.layers._zero_copy_upload).  Inputs below 4 MB per step (cfg1: 4.8 KB) keep a plain in-stream
+    copy: the stream hand-offs cost more than the copy there."""
+
+    def __init__(self, model, xh, yh, lo, hi, dev):
+        import torch
+        self.torch, self.model, self.xh, self.yh, self.lo, self.hi = torch, model, xh, yh, lo, hi
+        in_bytes = sum(t[lo:hi].numel() * t.element_size() for t in (xh, yh) if t is not None)
+        self.pipelined = in_bytes >= (4 << 20)
+        self.t, self.primed = 0, False
+        if not self.pipelined:
+            return
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.bufs = [(model._x if xh is not None else None, model._y),
+                     (torch.empty_like(model._x) if xh is not None else None, torch.empty_like(model._y))]
+        if xh is not None:
+            self.bufs[1][0].copy_(model._x)
+        self.bufs[1][1].copy_(model._y)
+        self.ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def _prefetch(self, i):
+        lo, hi = self.lo, self.hi
+        with self.torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_done[i])     # the step that last read buffer i has finished
+            if self.xh is not None:
+                self.bufs[i][0][lo:hi].copy_(self.xh[lo:hi], non_blocking=True)
+            self.bufs[i][1][lo:hi].copy_(self.yh[lo:hi], non_blocking=True)
+            self.ev_copied[i].record(self.copy_stream)
+
+    def step(self, fn):
+        model, lo, hi = self.model, self.lo, self.hi
+        if not self.pipelined:
+            if self.xh is not None:
+                model._x[lo:hi].copy_(self.xh[lo:hi], non_blocking=True)
+            model._y[lo:hi].copy_(self.yh[lo:hi], non_blocking=True)
+            return fn()
+        i = self.t % 2
+        if not self.primed:
+            self.ev_done[0].record()
+            self.ev_done[1].record()
+            self._prefetch(i)
+            self.primed = True
+        self._prefetch(1 - i)                                # next step's inputs, overlapped with this step
+        self.torch.cuda.current_stream().wait_event(self.ev_copied[i])
+        if self.xh is not None:
+            model._x = self.bufs[i][0]
+        model._y = self.bufs[i][1]
+        out = fn()
+        self.ev_done[i].record()
+        self.t += 1
+        return out
+
+    def finish(self):
+        if self.pipelined:
+            self.torch.cuda.current_stream().wait_stream(self.copy_stream)
+
+
 def secondary_workload(name, args, dev, peak_tf):
     """A second, smaller measurement inside the default line (world size 1 only): the literal
     north-star shape aep.SGPR N=1e6, D=10, M=256, so that it gets a driver record too.  Same
@@ -434,17 +497,19 @@ def secondary_workload(name, args, dev, peak_tf):
     def step():
         return model.objective_function(params, N, alpha=w['alpha'])
 
-    def step_e2e():
-        model._x.copy_(xh, non_blocking=True)
-        model._y.copy_(yh, non_blocking=True)
-        return model.objective_function(params, N, alpha=w['alpha'])
+    pipe = InputPipeline(model, xh, yh, 0, N, dev)
 
-    def timed(fn, steps):
+    def step_e2e():
+        return pipe.step(step)
+
+    def timed(fn, steps, finish=None):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
@@ -457,7 +522,7 @@ def secondary_workload(name, args, dev, peak_tf):
     prof = ops.profile_collect()
     ops.profile_enable(False)
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, pipe.finish)
     k_ms = prof['det_fwd'][0] / args.steps
     fl = N * 2.0 * w['Do'] * w['M'] ** 2
     out = {'workload': name + ': ' + w['desc'], 'ms_per_step': ms, 'value': N / (ms * 1e-3), 'unit': 'rows/s',
@@ -517,56 +582,11 @@ def run_gpu(args, w):
     # each rank's inputs for a step are its own contiguous slice of the rows (geepee_b200/dist.py)
     lo, hi = (rank * N) // world, ((rank + 1) * N) // world
 
-    # End-to-end leg: every step's inputs come from pinned host memory.  They are double buffered: the rows of step
-    # t + 1 are uploaded on a copy stream while step t computes (what an input pipeline does); one upload per step is
-    # issued inside the timed region and the region ends only after the last one has landed (e2e_finish).  The step's
-    # own small parameter upload does not queue behind that copy: it is read from pinned memory by a copy kernel
-    # (layers._zero_copy_upload).
-    copy_stream = torch.cuda.Stream(dev)
-    bufs = [(model._x if xh is not None else None, model._y),
-            (torch.empty_like(model._x) if xh is not None else None, torch.empty_like(model._y))]
-    if xh is not None:
-        bufs[1][0].copy_(model._x)
-    bufs[1][1].copy_(model._y)
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-    e2e_state = {'t': 0, 'primed': False}
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_done[i])          # the step that last read buffer i has finished
-            if xh is not None:
-                bufs[i][0][lo:hi].copy_(xh[lo:hi], non_blocking=True)
-            bufs[i][1][lo:hi].copy_(yh[lo:hi], non_blocking=True)
-            ev_copied[i].record(copy_stream)
-
-    in_bytes = (X[lo:hi].nbytes if xh is not None else 0) + Y[lo:hi].nbytes
-    pipelined = in_bytes >= (4 << 20)       # tiny inputs (cfg1: 4.8 KB): the in-stream copy costs less than the stream hand-offs
-
-    def step_e2e():
-        if not pipelined:
-            if xh is not None:
-                model._x[lo:hi].copy_(xh[lo:hi], non_blocking=True)
-            model._y[lo:hi].copy_(yh[lo:hi], non_blocking=True)
-            return model.objective_function(params, N, alpha=alpha)
-        i = e2e_state['t'] % 2
-        if not e2e_state['primed']:
-            ev_done[0].record()
-            ev_done[1].record()
-            prefetch(i)
-            e2e_state['primed'] = True
-        prefetch(1 - i)                                  # next step's inputs, overlapped with this step
-        torch.cuda.current_stream().wait_event(ev_copied[i])
-        if xh is not None:
-            model._x = bufs[i][0]
-        model._y = bufs[i][1]
-        out = model.objective_function(params, N, alpha=alpha)
-        ev_done[i].record()
-        e2e_state['t'] += 1
-        return out
-
-    def e2e_finish():
-        torch.cuda.current_stream().wait_stream(copy_stream)
+    # End-to-end leg: every step's inputs come from pinned host memory, double buffered (InputPipeline above).
+    pipe = InputPipeline(model, xh, yh, lo, hi, dev)
+    pipelined = pipe.pipelined
+    step_e2e = lambda: pipe.step(lambda: model.objective_function(params, N, alpha=alpha))  # noqa: E731
+    e2e_finish = pipe.finish
 
     def timed(fn, steps, finish=None):
         barrier()

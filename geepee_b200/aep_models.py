@@ -13,7 +13,7 @@ Every objective has the same three-phase shape:
 import numpy as np
 import torch
 
-from . import dist, ops
+from . import dist, nvtx, ops
 from . import tail as tl
 from .sched import TailStreams
 from .base_models import Base_SGPR, Base_SDGPR, Base_SGPLVM, Base_SGPSSM
@@ -72,6 +72,7 @@ class SGPR(Base_SGPR):
         super(SGPR, self).__init__(x_train, y_train, no_pseudo, lik, nat_param, prec, device)
         self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         N, L, dev = self.N, self.sgp_layer, self.device
         xb, yb, n = self._batch(mb_size)
@@ -108,6 +109,7 @@ class SDGPR(Base_SDGPR):
                                      prec, self.device) for i in range(self.L)]
         self._tail_streams = TailStreams(self.device, self.L)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         """aep_models.py:895-988.  Per-row kernels on the current stream; every layer's tail (and,
         with several ranks, the all-reduce of its statistics) on its own side stream (sched.py)."""
@@ -233,6 +235,7 @@ class SDGPR_H(Base_SDGPR):
             self.h_factor_1[i] = params['h_factor_1_%d' % i]
             self.h_factor_2[i] = np.exp(2 * np.asarray(params['h_factor_2_%d' % i]))
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         _check_mode(prop_mode)
         N, dev, Ln = self.N, self.device, self.L
@@ -363,6 +366,7 @@ class SGPLVM(Base_SGPLVM):
         """aep_models.py:863-867."""
         return (0.5 * (mx**2 / vx + torch.log(vx))).sum(), mx / vx, 0.5 * (-mx**2 / vx**2 + 1 / vx)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
@@ -515,6 +519,7 @@ class SGPSSM(Base_SGPSSM):
             terms.append((1.0, emi._phi(alpha), None))
         return self._finish(tl.dots(terms, const=phi_prior), grads)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha=1.0, prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, Q, dev = self.N, self.Din, self.device

@@ -17,7 +17,7 @@ are materialised on attribute access for the layer-level API and the tests.
 import numpy as np
 import torch
 
-from . import config, ops, _lib
+from . import config, nvtx, ops, _lib
 from . import tail as tl
 from .tailgraph import TailGraph
 
@@ -214,6 +214,7 @@ class Base_SGP_Layer(object):
         ins = {k: _dev[k + key_suffix] for k in ('ls', 'sf', 'zu', 'eta1_R', 'eta2')}
         self._pre_tail(ins, getattr(self, '_fuse_cavity_alpha', None))
 
+    @nvtx.annotate('pre_tail')
     def _pre_tail(self, ins, alpha):
         """The data-independent device work of one parameter update (+ cavity and log-partitions
         when the AEP objective announced its alpha): eager for the first calls, then one CUDA-graph
@@ -252,6 +253,7 @@ class Base_SGP_Layer(object):
     def _pre_extra(self, alpha):
         pass
 
+    @nvtx.annotate('post_tail')
     def _post_tail(self, name, impl, st, *args):
         """Chain rules from the reduced statistics to the parameter gradients; replayed from a
         graph when this layer's state is the static output of a captured pre-tail."""
@@ -395,6 +397,7 @@ class Base_SGP_Layer(object):
             self._opnd[key] = ops.DetOperands(self.prec, A.contiguous(), B.contiguous())
         return self._opnd[key]
 
+    @nvtx.annotate('fwd_det')
     def _fwd_det(self, x, cav, save):
         """a5 on the device: (mout, vout, ctx)."""
         t = self._t
@@ -402,6 +405,7 @@ class Base_SGP_Layer(object):
         m, v, Ks, Ts = ops.det_fwd(self.prec, x, t['zu'], t['ls'], t['sf'], opnd, save=save)
         return m, v, (x, opnd, Ks, Ts)
 
+    @nvtx.annotate('bwd_det')
     def _bwd_det(self, ctx, dm, dv):
         """a8 per-row part: sufficient statistics of one deterministic layer."""
         t = self._t
@@ -444,6 +448,7 @@ class Base_SGP_Layer(object):
                         tl.lincomb([(1.0, a), (1.0, d_new[k].reshape(1, -1))], out=a)
         return acc, ext
 
+    @nvtx.annotate('fwd_mm')
     def _fwd_mm(self, mx, vx, cav, save=True):
         """a6 on the device (save=False: prediction, nothing kept for a backward)."""
         t = self._t
@@ -452,6 +457,7 @@ class Base_SGP_Layer(object):
                                       B.contiguous(), save=save)
         return m, v, (mx, vx, cav, m, vacc, psi1)
 
+    @nvtx.annotate('bwd_mm')
     def _bwd_mm(self, ctx, dm, dv):
         """a9 per-row part: statistics + per-row input gradients."""
         t = self._t
@@ -460,6 +466,7 @@ class Base_SGP_Layer(object):
         return ops.mm_bwd(self.prec, mx, vx, t['zu'], t['ls'], t['sf'], A.contiguous(), B.contiguous(),
                           dm, dv, mout, vacc, psi1)
 
+    @nvtx.annotate('fwd_mc')
     def _fwd_mc(self, mx, vx, eps, cav):
         """aep_models.py:160-180 / base_models.py:309-332: samples x = mx + sqrt(vx) eps (eps[K,n,Q]
         drawn on the host from numpy's global RNG, as the reference does) pushed through the
@@ -469,6 +476,7 @@ class Base_SGP_Layer(object):
         m, v, ctx = self._fwd_det(xs, cav=cav, save=True)
         return m.reshape(K, n, self.Dout), v.reshape(K, n, self.Dout), (ctx, eps, vx)
 
+    @nvtx.annotate('bwd_mc')
     def _bwd_mc(self, ctx, dm, dv):
         """Per-row part of backprop_grads_lvm_mc (aep_models.py:307-410, vfe_models.py:405-476) +
         backprop_grads_reparam (base_models.py:373-388): the deterministic-layer statistics over the

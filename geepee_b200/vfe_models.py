@@ -8,7 +8,7 @@ a different, full-batch algorithm and out of scope.
 import numpy as np
 import torch
 
-from . import dist, ops
+from . import dist, nvtx, ops
 from . import tail as tl
 from .aep_models import _add_stats, _get_stats, _zero_stats, _zeros, _check_mode, _mc_eps
 from .base_models import Base_SGPR, Base_SGPLVM, Base_SGPSSM
@@ -26,6 +26,7 @@ class SGPR(Base_SGPR):
         super(SGPR, self).__init__(x_train, y_train, no_pseudo, lik, nat_param, prec, device)
         self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode='not_used'):
         N, L, dev = self.N, self.sgp_layer, self.device
         xb, yb, n = self._batch(mb_size)
@@ -59,6 +60,7 @@ class SGPLVM(Base_SGPLVM):
                                      nat_param, prec, device)
         self.sgp_layer = SGP_Layer(self.N, self.Din, self.Dout, self.M, nat_param, prec, self.device)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, L, dev, Q = self.N, self.sgp_layer, self.device, self.Din
@@ -122,6 +124,7 @@ class SGPSSM(Base_SGPSSM):
             self.emi_layer = SGP_Layer(self.N, self.Din + self.Dcon_emi, self.Dout, self.M, nat_param,
                                        prec, self.device)
 
+    @nvtx.annotate('objective_function')
     def objective_function(self, params, mb_size, alpha='not_used', prop_mode=PROP_MM):
         _check_mode(prop_mode, mc_ok=True)
         N, Q, dev = self.N, self.Din, self.device

@@ -50,3 +50,28 @@ def test_optimise_reduces_energy_on_emulator():
         assert mf.shape == (5, 1) and np.all(vf > 0)
     finally:
         emu_util.detach()
+
+
+def test_nvtx_annotate_is_identity_when_off_and_wraps_when_on(monkeypatch):
+    """geepee_b200/nvtx.py: no wrapper on the default path; with GPB_NVTX=1 the phase runs between a push and a pop
+    (also when it raises)."""
+    import torch
+    from geepee_b200 import nvtx
+
+    def f(a, b=1):
+        return a + b
+
+    monkeypatch.setattr(nvtx, 'ENABLED', False)
+    assert nvtx.annotate('x')(f) is f
+    calls = []
+    monkeypatch.setattr(nvtx, 'ENABLED', True)
+    monkeypatch.setattr(torch.cuda.nvtx, 'range_push', lambda s: calls.append(('push', s)))
+    monkeypatch.setattr(torch.cuda.nvtx, 'range_pop', lambda: calls.append(('pop',)))
+    g = nvtx.annotate('phase')(f)
+    assert g(2, b=3) == 5 and calls == [('push', 'geepee/phase'), ('pop',)]
+
+    def boom():
+        raise ValueError('x')
+    with pytest.raises(ValueError):
+        nvtx.annotate('boom')(boom)()
+    assert calls[-1] == ('pop',) and len(calls) == 4
