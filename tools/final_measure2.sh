@@ -1,9 +1,5 @@
-set -x
-python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/r2z_gputest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2z_gputest.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_smoke.txt 2>&1
 python bench.py > gpurun_out/r2z_bench_default.json 2> gpurun_out/r2z_bench_default.err
 python bench.py --workload ns_sgpr --no-secondary > gpurun_out/r2z_bench_ns_sgpr.json 2> gpurun_out/r2z_bench_ns_sgpr.err
 python bench.py --workload ns_sgpr --prec fp32 --no-secondary > gpurun_out/r2z_bench_ns_sgpr_fp32.json 2> gpurun_out/r2z_bench_ns_sgpr_fp32.err
-python bench.py --workload cfg5_sgpr --no-secondary > gpurun_out/r2z_bench_cfg5_sgpr.json 2> gpurun_out/r2z_bench_cfg5_sgpr.err
 python bench.py --workload cfg1_sgpr --no-secondary > gpurun_out/r2z_bench_cfg1_sgpr.json 2> gpurun_out/r2z_bench_cfg1_sgpr.err
-tail -2 gpurun_out/r2z_gputest.log; cat gpurun_out/r2z_smoke.txt | tail -1
+python bench.py --prec fp32 --no-secondary > gpurun_out/r2z_bench_fp32.json 2> gpurun_out/r2z_bench_fp32.err
