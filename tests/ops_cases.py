@@ -119,6 +119,52 @@ def check_kmat_psi_lik():
     assert gu.rel_err(N(dm), -2.5 * rdm) < 1e-13 and gu.rel_err(N(dv), -2.5 * rdv) < 1e-13
 
 
+def check_torch_custom_ops():
+    """geepee_b200/torch_ops.py: the library through the PyTorch dispatcher (`torch.ops.geepee_b200.*`) -- golden
+    vectors of the reference for kmat / psi_stats (kernels.py:10-22, 181-240), the oracle for the Gaussian likelihood,
+    and bit-equality with the direct ctypes wrappers for the moment-matched forward / backward pair."""
+    import torch
+    import geepee_b200.torch_ops as to
+    from geepee_b200 import ops
+    g = torch.ops.geepee_b200
+    f = np.load(gu.GOLDEN + '/kernels.npz')
+    ls, sf, mx, vx, z = (T(f[k]) for k in ['ls', 'sf', 'mx', 'vx', 'z'])
+    assert gu.rel_err(N(g.kmat(mx, z, ls, sf)), f['kfu']) < 1e-14
+    p1, p2 = g.psi_stats(mx, vx, z, ls, sf)
+    assert gu.rel_err(N(p1), f['psi1']) < 1e-13 and gu.rel_err(N(p2), f['psi2']) < 1e-13
+    M = z.shape[0]
+    kuu = g.kmat(z, z, ls, sf, 1e-5)
+    inv, ld = g.spd_inverse(kuu)
+    assert gu.rel_err(N(inv), np.linalg.inv(N(kuu))) < 1e-9
+    assert abs(ld.item() - np.linalg.slogdet(N(kuu))[1]) < 1e-9 * max(1.0, abs(ld.item()))
+    rng = np.random.RandomState(5)
+    m, v, y = rng.standard_normal((40, 2)), rng.rand(40, 2) + 0.1, rng.standard_normal((40, 2))
+    sn = np.array([-0.4])
+    dm, dv, o = g.gauss_lik(T(m), T(v), T(y), T(sn), 0.6, -2.5, 0)
+    lz, rdm, rdv = go.gauss_log_Z(sn[0], m, v, y, 0.6)
+    assert abs(o[0].item() - lz) < 1e-12 * abs(lz) and gu.rel_err(N(dm), -2.5 * rdm) < 1e-13
+    n, Q, Do = mx.shape[0], mx.shape[1], 2
+    A = T(rng.standard_normal((Do, M)))
+    B = rng.standard_normal((Do, M, M))
+    B = T(B + B.transpose(0, 2, 1))
+    fw = g.mm_fwd(ops.F64, mx, vx, z, ls, sf, A, B)
+    fw_direct = ops.mm_fwd(ops.F64, mx, vx, z, ls, sf, A, B, save=True)
+    # outputs reduced with atomics (vacc and what derives from it) may differ in the last bits between two launches
+    for a, b in zip(fw, fw_direct):
+        assert gu.rel_err(N(a), N(b)) < 1e-13
+    # the forward against the materialised statistics: mout = psi1 A^T, vacc = sum_ab B psi2 (aep_models.py:196-198)
+    assert gu.rel_err(N(fw[0]), f['psi1'] @ N(A).T) < 1e-12
+    assert gu.rel_err(N(fw[2]), np.einsum('nab,dab->nd', f['psi2'], N(B))) < 1e-12
+    dmo, dvo = T(rng.standard_normal((n, Do))), T(rng.standard_normal((n, Do)))
+    bw = g.mm_bwd(ops.F64, mx, vx, z, ls, sf, A, B, dmo, dvo, fw[0], fw[2], fw[3])
+    bw_direct = ops.mm_bwd(ops.F64, mx, vx, z, ls, sf, A, B, dmo, dvo, fw[0], fw[2], fw[3])
+    assert len(bw) == len(to.MM_BWD_OUTPUTS)
+    for a, k in zip(bw, to.MM_BWD_OUTPUTS):
+        assert gu.rel_err(N(a), N(bw_direct[k])) < 1e-12, k
+    # dB[d] = sum_n dv[n,d] psi2[n] (aep_models.py:243)
+    assert gu.rel_err(N(bw[1]), np.einsum('nd,nab->dab', N(dvo), f['psi2'])) < 1e-12
+
+
 EMIS_SHAPES = [(37, 3, 2), (300, 4, 4), (129, 5, 3), (64, 8, 8), (50, 1, 6)]
 
 

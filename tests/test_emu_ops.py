@@ -31,6 +31,10 @@ def test_kmat_psi_lik():
     oc.check_kmat_psi_lik()
 
 
+def test_torch_custom_ops():
+    oc.check_torch_custom_ops()
+
+
 @pytest.mark.parametrize('n,Do,Q', oc.EMIS_SHAPES)
 def test_gauss_emis(n, Do, Q):
     oc.check_gauss_emis(n, Do, Q)

@@ -64,6 +64,11 @@ def test_kmat_psi_lik():
     oc.check_kmat_psi_lik()
 
 
+def test_torch_custom_ops():
+    """`torch.ops.geepee_b200.*` (geepee_b200/torch_ops.py) on the device."""
+    oc.check_torch_custom_ops()
+
+
 def test_tail_primitives():
     """GpbTailOp program ops (batched DMMA GEMM, fused linear combinations, R packing, kernel-hyper
     chain rule ...) against numpy."""
